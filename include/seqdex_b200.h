@@ -1,0 +1,149 @@
+/* seqdex_b200 -- C-ABI of the B200-native SeqDex hot path.
+ *
+ * Every entry point replaces a call the reference makes into Isaac Gym /
+ * rl_games (both closed / external).  Citations are into
+ * /root/reference/dexteroushandenvs:
+ *   BT = tasks/hand_base/base_task.py
+ *   GS = tasks/block_assembly/allegro_hand_block_assembly_grasp_sim.py
+ *   VR = tasks/hand_base/vec_task_rlgames.py
+ *   RGC = utils/rl_games_custom.py   TVF = policy_sequencing/terminal_value_function.py
+ *
+ * Plain pointers and sizes only: no torch types.  All `*_dev` pointers are
+ * device pointers on the env's device; `*_host` pointers are host memory
+ * (pinned for full speed).  Every function returns 0 on success, non-zero on
+ * failure (message via sdx_last_error()); nothing falls back to the CPU.
+ */
+#ifndef SEQDEX_B200_H
+#define SEQDEX_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDX_MAX_BRICKS 72
+#define SDX_MAX_FIXED 60
+#define SDX_NL 24          /* robot bodies after collapse_fixed_joints (GS:540-557) */
+#define SDX_ND 23          /* robot DoFs */
+#define SDX_MAX_RSHAPES 32
+#define SDX_MAX_STATIC 80
+#define SDX_ACTORS_PER_ENV 142
+#define SDX_RB_PER_ENV 165 /* 24 robot + object + goal + table + 5 bin + 132 bricks + base-plate */
+#define SDX_OBS_FRAME 132  /* GS:193 */
+#define SDX_STATE_FRAME 188/* GS:204 */
+#define SDX_STACK 3        /* GS:189 */
+#define SDX_NUM_ACTIONS 23 /* GS:211 */
+#define SDX_MAX_CONTACTS 1024
+#define SDX_TVALUE_PARAMS 42562 /* 4->256->128->64->2 (TVF:30-46) */
+#define SDX_GRASP_BANK 11024    /* 10000+1024 rows per brick type (GS:391-394) */
+
+/* Constant scene tables (seqdex_b200/scene.py builds them; layout is ABI). */
+typedef struct sdx_scene_t {
+  int n_bricks, n_fixed, n_rshapes, n_static;
+  int substeps, iters, max_episode_length, pad0;
+  float dt, gravity_z, contact_offset, friction, baumgarte, slop, max_depen_vel, brick_ang_damp, max_ang_vel,
+      max_lin_vel, brick_lin_damp, pad1;
+  float base_pos[3], base_quat[4], pad2;
+  int body_parent[SDX_NL];
+  unsigned link_anc_mask[SDX_NL];            /* bit j: DoF j moves link */
+  float joint_xyz[SDX_ND * 3], joint_quat[SDX_ND * 4], joint_axis[SDX_ND * 3];
+  float dof_lo[SDX_ND], dof_hi[SDX_ND], dof_kp[SDX_ND], dof_kd[SDX_ND], dof_effort[SDX_ND], dof_vmax[SDX_ND],
+      dof_inertia[SDX_ND];
+  int rs_body[SDX_MAX_RSHAPES];
+  float rs_c[SDX_MAX_RSHAPES * 3], rs_quat[SDX_MAX_RSHAPES * 4], rs_h[SDX_MAX_RSHAPES * 3];
+  float br_half[SDX_MAX_BRICKS * 3], br_coff[SDX_MAX_BRICKS * 3], br_invm[SDX_MAX_BRICKS],
+      br_invI[SDX_MAX_BRICKS * 3];
+  float st_c[SDX_MAX_STATIC * 3], st_h[SDX_MAX_STATIC * 3];
+  float fixed_root[SDX_MAX_FIXED * 13];
+  float brick_init[SDX_MAX_BRICKS * 13];
+  float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
+  float cam_off_pos[3], cam_off_quat[4];
+  float act_moving_average, av_factor, vel_obs_scale, pad3[2];
+} sdx_scene_t;
+
+/* Tensor kinds for sdx_tensor(): device buffers owned by the env. dtype 0=f32 1=i64 2=i32 */
+enum {
+  SDX_T_BRICK = 0,      /* f32 [N][13][72]  free-brick COM state, SoA inside an env block            */
+  SDX_T_DOF = 1,        /* f32 [N][3][24]   q | qd | position target (GS:313-316, 328-329)           */
+  SDX_T_LINK = 2,       /* f32 [N][24][13]  robot rigid-body rows (rigid_body_states GS:318)         */
+  SDX_T_JAC7 = 3,       /* f32 [N][6][7]    jacobian_tensor[:, link7-1, :, :7] (GS:1601)             */
+  SDX_T_NETF = 4,       /* f32 [N][24][3]   net contact force on robot links (GS:1159)               */
+  SDX_T_ACTIONS = 5,    /* f32 [N][23]                                                              */
+  SDX_T_OBS = 6,        /* f32 [N][396]  obs_buf (BT:57)                                             */
+  SDX_T_STATES = 7,     /* f32 [N][564]  states_buf (BT:59)                                          */
+  SDX_T_REW = 8,        /* f32 [N]       rew_buf                                                     */
+  SDX_T_RESET = 9,      /* i64 [N]       reset_buf (BT:63)                                           */
+  SDX_T_PROGRESS = 10,  /* i64 [N]       progress_buf                                                */
+  SDX_T_TVALUE = 11,    /* f32 [N]       sigmoid(t_value(q_cam))[:,1] (GS:1200-1201)                  */
+  SDX_T_TARGET_INIT = 12,/* f32 [N][7]   segmentation_target_init_{pos,rot} (GS:1547-1548)           */
+  SDX_T_SUCCESSES = 13, /* f32 [N]                                                                   */
+  SDX_T_CONSEC = 14,    /* f32 [1]       consecutive_successes                                       */
+  SDX_T_NCONTACT = 15,  /* i32 [N][2]    contacts in the last sub-step | dropped (overflow)          */
+  SDX_T_ROOT = 16,      /* f32 [N*142][13] actor_root_state_tensor, filled by sdx_refresh            */
+  SDX_T_RB = 17,        /* f32 [N*165][13] rigid_body_state_tensor, filled by sdx_refresh            */
+  SDX_T_DOF_STATE = 18, /* f32 [N*23][2]   dof_state_tensor, filled by sdx_refresh                    */
+  SDX_T_JACOBIAN = 19,  /* f32 [N][23][6][23] jacobian tensor, filled by sdx_refresh                  */
+  SDX_T_EPISODE = 20,   /* i32 [N]       per-env episode counter (keys the reset RNG)                */
+  SDX_T_CONTACTS = 21,  /* f32 [N][SDX_MAX_CONTACTS][8] debug dump of the last sub-step's contacts   */
+  SDX_T_COUNT = 22
+};
+
+typedef struct sdx_env sdx_env_t;
+
+const char* sdx_last_error(void);
+
+/* gym.create_sim + _create_envs + prepare_sim (BT:122-126, GS:505-523, BT:84). */
+int sdx_create(const sdx_scene_t* scene, int num_envs, int device, uint64_t seed, sdx_env_t** out);
+void sdx_destroy(sdx_env_t* env);
+/* CUDA stream all subsequent launches go to (cudaStream_t as void*). */
+int sdx_set_stream(sdx_env_t* env, void* stream);
+int sdx_num_envs(const sdx_env_t* env);
+
+/* acquire_*_tensor + gymtorch.wrap_tensor (GS:237-246): zero-copy device view. */
+int sdx_tensor(sdx_env_t* env, int kind, void** dev_ptr, int64_t shape[4], int* ndim, int* dtype);
+/* refresh_{actor_root_state,rigid_body_state,dof_state,jacobian}_tensor (GS:1091-1095). */
+int sdx_refresh(sdx_env_t* env, int kind);
+
+/* set_actor_root_state_tensor_indexed (GS:1514): rows of the facade root tensor named by
+ * sim-domain actor indices (int32) are written back into the simulation state. */
+int sdx_set_actor_root_state_indexed(sdx_env_t* env, const float* root_dev, const int32_t* actor_idx_dev, int n);
+/* set_dof_state_tensor_indexed / set_dof_position_target_tensor_indexed (GS:1539-1545):
+ * indices are sim-domain actor indices of the hand actors (= env*142). */
+int sdx_set_dof_state_indexed(sdx_env_t* env, const float* dof_state_dev, const int32_t* actor_idx_dev, int n);
+int sdx_set_dof_target_indexed(sdx_env_t* env, const float* targets_dev, const int32_t* actor_idx_dev, int n);
+/* set_dof_position_target_tensor (GS:1638). targets [N][23]. */
+int sdx_set_dof_targets(sdx_env_t* env, const float* targets_dev);
+
+/* Terminal-state heap bank the task samples on reset: the stand-in for
+ * saved_searching_ternimal_states_*.pkl = list[8] of [B,132,13] (GS:412-413, 1507-1511).
+ * bank_host: f32 [8][per_type][72][13] root-frame rows of the 72 free bricks. */
+int sdx_set_heap_bank(sdx_env_t* env, const float* bank_host, int per_type);
+/* GraspInsertTValue parameters, torch state_dict order: W1[256][4] b1 W2[128][256] b2 W3[64][128] b3 W4[2][64] b4. */
+int sdx_set_tvalue_weights(sdx_env_t* env, const float* weights_host);
+/* Put every env into the scene's initial state (lattice of bricks GS:737-742, robot at the
+ * prepare pose GS:267-272), progress 0, reset 1 (BT:63). */
+int sdx_reset_all(sdx_env_t* env);
+
+/* The three phases of BaseTask.step (BT:130-150). */
+int sdx_pre_physics(sdx_env_t* env, const float* actions_dev); /* GS:1555-1638 incl. reset_idx GS:1361-1553 */
+int sdx_simulate(sdx_env_t* env);                              /* gym.simulate BT:140 */
+int sdx_post_physics(sdx_env_t* env);                          /* GS:1640-1645: obs, states, reward, reset  */
+int sdx_step(sdx_env_t* env, const float* actions_dev);        /* all three */
+/* RLgamesVecTaskPython.step with host buffers (VR:165-177): H2D actions, step, clamp +-5, D2H results. */
+int sdx_step_host(sdx_env_t* env, const float* actions_host, float* obs_host, float* states_host, float* rew_host,
+                  int64_t* reset_host);
+/* settle the heap: n steps of sdx_simulate with targets frozen (bank generation). */
+int sdx_simulate_n(sdx_env_t* env, int n);
+/* number of kernels this library has launched on behalf of env since creation */
+int64_t sdx_launch_count(const sdx_env_t* env);
+
+/* ---- PPO (rl_games 1.5.2 semantics; RGC:1394-1483, 1767-1911, 2115-2132) ---- */
+/* discount_values: GAE sweep. rewards/values/dones [H][N], last_values/last_dones [N] -> advantages [H][N]. */
+int sdx_gae(const float* rewards_dev, const float* values_dev, const float* dones_dev, const float* last_values_dev,
+            const float* last_dones_dev, float* adv_dev, float* returns_dev, int horizon, int n, float gamma,
+            float tau, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

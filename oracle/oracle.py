@@ -1,0 +1,170 @@
+"""ctypes front-end of the CPU ORACLE (oracle/sdx_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  ``OracleEnv`` holds the same state arrays, in the same layouts, as the CUDA env
+(include/seqdex_b200.h tensor kinds) and runs BaseTask.step's three phases (BT:130-150) on the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+NB, NL, ND, MAXC = 72, 24, 23, 1024
+F32P = ctypes.POINTER(ctypes.c_float)
+I32P = ctypes.POINTER(ctypes.c_int)
+I64P = ctypes.POINTER(ctypes.c_int64)
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libsdx_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = ctypes.CDLL(so)
+        _LIB.sdxo_tvalue_one.restype = ctypes.c_float
+    return _LIB
+
+
+def fp(a):
+    return a.ctypes.data_as(F32P) if a is not None else None
+
+
+def ip(a):
+    return a.ctypes.data_as(I32P)
+
+
+def lp(a):
+    return a.ctypes.data_as(I64P)
+
+
+def default_tvalue_weights(seed=0):
+    """torch-default init of GraspInsertTValue(4, 2) (TVF:30-46) as one flat f32 vector."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for (o, i) in ((256, 4), (128, 256), (64, 128), (2, 64)):
+        bound = 1.0 / np.sqrt(i)
+        w = (torch.rand(o, i, generator=g) * 2 - 1) * bound
+        b = (torch.rand(o, generator=g) * 2 - 1) * bound
+        out += [w.reshape(-1), b]
+    return torch.cat(out).numpy().astype(np.float32)
+
+
+class OracleEnv:
+    def __init__(self, scene, num_envs, seed=22, tvalue_weights=None):
+        self.L = lib()
+        assert self.L.sdxo_scene_size() == ctypes.sizeof(scene.c), "scene struct ABI mismatch"
+        self.scene = scene
+        self.S = ctypes.byref(scene.c)
+        self.n = n = num_envs
+        self.seed = seed
+        self.brick = np.zeros((n, 13, NB), np.float32)
+        self.dof = np.zeros((n, 3, 24), np.float32)
+        self.link = np.zeros((n, NL, 13), np.float32)
+        self.jac7 = np.zeros((n, 6, 7), np.float32)
+        self.netf = np.zeros((n, NL, 3), np.float32)
+        self.actions = np.zeros((n, 23), np.float32)
+        self.obs = np.zeros((n, 396), np.float32)
+        self.states = np.zeros((n, 564), np.float32)
+        self.rew = np.zeros(n, np.float32)
+        self.reset = np.ones(n, np.int64)           # BT:63
+        self.progress = np.zeros(n, np.int64)
+        self.tvalue = np.zeros(n, np.float32)
+        self.finger_dist = np.zeros(n, np.float32)
+        self.target_init = np.zeros((n, 7), np.float32)
+        self.successes = np.zeros(n, np.float32)
+        self.consec = np.zeros(1, np.float32)
+        self.ncontact = np.zeros((n, 2), np.int32)
+        self.episode = np.zeros(n, np.int32)
+        self.condump = np.zeros((n, MAXC, 8), np.float32)
+        self.gb_hand = np.zeros((8, 11024, 23, 2), np.float32)
+        self.gb_obj = np.zeros((8, 11024, 13), np.float32)
+        self.gb_index = np.zeros(8, np.int32)
+        self.total_steps = 0
+        self.tv = (tvalue_weights if tvalue_weights is not None else default_tvalue_weights()).astype(np.float32)
+        self.bank = None
+        self.per_type = 0
+        self.reset_all()
+
+    # ---- state helpers
+    def reset_all(self):
+        c = self.scene.c
+        rows = np.ctypeslib.as_array(c.brick_init).reshape(NB, 13).astype(np.float32)
+        self.set_brick_roots(np.broadcast_to(rows, (self.n, NB, 13)).copy())
+        lo, hi = self.scene.dof_lo, self.scene.dof_hi
+        q = np.zeros(24, np.float32)
+        q[:7] = np.ctypeslib.as_array(c.prepare_arm)
+        fr = np.ctypeslib.as_array(c.finger_reset_unscaled).astype(np.float32)
+        q[7:23] = (np.float32(0.5) * (fr + np.float32(1.0)) * (hi[7:] - lo[7:]) + lo[7:]).astype(np.float32)
+        self.dof[:, 0, :] = q
+        self.dof[:, 1, :] = 0
+        self.dof[:, 2, :] = q
+        self.progress[:] = 0
+        self.reset[:] = 1
+        self.refresh_links()
+
+    def set_brick_roots(self, rows):
+        rows = np.ascontiguousarray(rows, np.float32)
+        self.L.sdxo_brick_from_root_rows(self.S, self.n, fp(self.brick), fp(rows))
+
+    def brick_roots(self):
+        rows = np.zeros((self.n, NB, 13), np.float32)
+        self.L.sdxo_brick_root_rows(self.S, self.n, fp(self.brick), fp(rows))
+        return rows
+
+    def refresh_links(self):
+        self.L.sdxo_refresh_links(self.S, self.n, fp(self.dof), fp(self.link), fp(self.jac7))
+
+    def set_heap_bank(self, bank):
+        self.bank = np.ascontiguousarray(bank, np.float32)
+        self.per_type = bank.shape[1]
+
+    # ---- BaseTask.step phases
+    def simulate(self, dump=False):
+        self.L.sdxo_simulate(self.S, self.n, fp(self.brick), fp(self.dof), fp(self.link), fp(self.jac7), fp(self.netf),
+                             ip(self.ncontact), fp(self.condump) if dump else None)
+
+    def pre_physics(self, actions):
+        if self.reset.any():
+            assert self.bank is not None, "reset needs a heap bank (GS:412-413)"
+            self.L.sdxo_reset(self.S, self.n, ctypes.c_uint64(self.seed), fp(self.bank), self.per_type, fp(self.brick),
+                              fp(self.dof), fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.successes),
+                              ip(self.episode), int(self.total_steps > 0), fp(self.finger_dist), fp(self.tvalue),
+                              fp(self.gb_hand), fp(self.gb_obj), ip(self.gb_index))
+        a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)   # VR:166
+        self.L.sdxo_pre_physics(self.S, self.n, fp(a), fp(self.actions), fp(self.dof), fp(self.link), fp(self.jac7),
+                                lp(self.progress), fp(self.target_init))
+
+    def post_physics(self):
+        self.L.sdxo_post_physics(self.S, self.n, fp(self.tv), fp(self.brick), fp(self.dof), fp(self.link), fp(self.actions),
+                                 fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.obs), fp(self.states),
+                                 fp(self.rew), fp(self.tvalue), fp(self.finger_dist), fp(self.successes), fp(self.consec))
+        self.total_steps += 1
+
+    def step(self, actions):
+        self.pre_physics(actions)
+        self.simulate()
+        self.post_physics()
+        return (np.clip(self.obs, -5, 5), np.clip(self.states, -5, 5), self.rew, self.reset)   # VR:171-177
+
+
+def gae(rewards, values, dones, last_values, last_dones, gamma, tau):
+    H, n = rewards.shape
+    adv = np.zeros((H, n), np.float32)
+    ret = np.zeros((H, n), np.float32)
+    lib().sdxo_gae(fp(np.ascontiguousarray(rewards, np.float32)), fp(np.ascontiguousarray(values, np.float32)),
+                   fp(np.ascontiguousarray(dones, np.float32)), fp(np.ascontiguousarray(last_values, np.float32)),
+                   fp(np.ascontiguousarray(last_dones, np.float32)), fp(adv), fp(ret), H, n,
+                   ctypes.c_float(gamma), ctypes.c_float(tau))
+    return adv, ret

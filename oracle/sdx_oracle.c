@@ -1,0 +1,891 @@
+/* sdx_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * Plain-C restatement of the SeqDex hot path for BlockAssemblyGraspSim.  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product (seqdex_b200/) never does.
+ *
+ * PARITY STATUS:
+ *   * task ops (pre_physics / control_ik / observations / reward / reset / t-value,
+ *     GAE): restated from the reference Python cited per function below, and
+ *     PINNED against golden vectors produced by importing the reference's own
+ *     functions with Isaac Gym stubbed (oracle/gen_golden.py -> tests/golden/).
+ *   * contact step (gym.simulate): the reference executes NVIDIA PhysX, a closed
+ *     binary that is absent here -> "PARITY UNPINNED".  This file defines the
+ *     algorithm (box-SDF contacts, mass-splitting Jacobi, implicit PD joints); the
+ *     CUDA kernel must match it BIT FOR BIT, and physics-invariant tests stand in
+ *     for a reference trajectory.
+ *
+ * Bit-exactness contract with the CUDA path: IEEE fp32, no FMA contraction
+ * (gcc -ffp-contract=off  <->  nvcc -fmad=false), correctly-rounded sqrt and
+ * division, and our own sincos/exp polynomials (no libm transcendentals), every
+ * sum in the order written here.
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#define SDX_MAX_BRICKS 72
+#define SDX_MAX_FIXED 60
+#define SDX_NL 24
+#define SDX_ND 23
+#define SDX_MAX_RSHAPES 32
+#define SDX_MAX_STATIC 80
+#define SDX_MAX_CONTACTS 1024
+#define NB SDX_MAX_BRICKS
+#define NBODY (NB + SDX_NL)
+#define NSHAPE (NB + SDX_MAX_RSHAPES + SDX_MAX_STATIC)
+#define KC 32 /* broad-phase candidates kept per owner shape */
+#define STATIC_BODY 255
+#define OBS_FRAME 132
+#define STATE_FRAME 188
+
+typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
+  int n_bricks, n_fixed, n_rshapes, n_static;
+  int substeps, iters, max_episode_length, pad0;
+  float dt, gravity_z, contact_offset, friction, baumgarte, slop, max_depen_vel, brick_ang_damp, max_ang_vel,
+      max_lin_vel, brick_lin_damp, pad1;
+  float base_pos[3], base_quat[4], pad2;
+  int body_parent[SDX_NL];
+  unsigned link_anc_mask[SDX_NL];
+  float joint_xyz[SDX_ND * 3], joint_quat[SDX_ND * 4], joint_axis[SDX_ND * 3];
+  float dof_lo[SDX_ND], dof_hi[SDX_ND], dof_kp[SDX_ND], dof_kd[SDX_ND], dof_effort[SDX_ND], dof_vmax[SDX_ND],
+      dof_inertia[SDX_ND];
+  int rs_body[SDX_MAX_RSHAPES];
+  float rs_c[SDX_MAX_RSHAPES * 3], rs_quat[SDX_MAX_RSHAPES * 4], rs_h[SDX_MAX_RSHAPES * 3];
+  float br_half[SDX_MAX_BRICKS * 3], br_coff[SDX_MAX_BRICKS * 3], br_invm[SDX_MAX_BRICKS],
+      br_invI[SDX_MAX_BRICKS * 3];
+  float st_c[SDX_MAX_STATIC * 3], st_h[SDX_MAX_STATIC * 3];
+  float fixed_root[SDX_MAX_FIXED * 13];
+  float brick_init[SDX_MAX_BRICKS * 13];
+  float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
+  float cam_off_pos[3], cam_off_quat[4];
+  float act_moving_average, av_factor, vel_obs_scale, pad3[2];
+} sdx_scene_t;
+
+/* ------------------------------------------------------------------ math */
+typedef struct { float x, y, z; } v3;
+typedef struct { float x, y, z, w; } q4;
+
+static inline v3 V3(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 vadd(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 vsub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 vscale(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+static inline float vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+static inline v3 vcross(v3 a, v3 b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+static inline v3 vneg(v3 a) { return V3(-a.x, -a.y, -a.z); }
+
+/* isaacgym.torch_utils.quat_mul (xyzw), same operation order as the public
+ * IsaacGymEnvs torch_jit_utils restatement. */
+static inline q4 qmul(q4 a, q4 b) {
+  float x1 = a.x, y1 = a.y, z1 = a.z, w1 = a.w, x2 = b.x, y2 = b.y, z2 = b.z, w2 = b.w;
+  float ww = (z1 + x1) * (x2 + y2);
+  float yy = (w1 - y1) * (w2 + z2);
+  float zz = (w1 + y1) * (w2 - z2);
+  float xx = ww + yy + zz;
+  float qq = 0.5f * (xx + (z1 - x1) * (x2 - y2));
+  q4 r;
+  r.w = qq - ww + (z1 - y1) * (y2 - z2);
+  r.x = qq - xx + (x1 + w1) * (x2 + w2);
+  r.y = qq - yy + (w1 - x1) * (y2 + z2);
+  r.z = qq - zz + (z1 + y1) * (w2 - x2);
+  return r;
+}
+static inline q4 qconj(q4 a) { q4 r = {-a.x, -a.y, -a.z, a.w}; return r; }
+/* quat_apply: b + w*t + xyz x t, t = 2 (xyz x b) */
+static inline v3 qrot(q4 q, v3 b) {
+  v3 xyz = V3(q.x, q.y, q.z);
+  v3 t = vscale(vcross(xyz, b), 2.0f);
+  return vadd(vadd(b, vscale(t, q.w)), vcross(xyz, t));
+}
+/* rotation matrix (row-major) of a unit quaternion */
+static inline void qmat(q4 q, float* R) {
+  float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z, xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z,
+        xw = q.x * q.w, yw = q.y * q.w, zw = q.z * q.w;
+  R[0] = 1.0f - 2.0f * (yy + zz); R[1] = 2.0f * (xy - zw); R[2] = 2.0f * (xz + yw);
+  R[3] = 2.0f * (xy + zw); R[4] = 1.0f - 2.0f * (xx + zz); R[5] = 2.0f * (yz - xw);
+  R[6] = 2.0f * (xz - yw); R[7] = 2.0f * (yz + xw); R[8] = 1.0f - 2.0f * (xx + yy);
+}
+static inline v3 mcol(const float* R, int k) { return V3(R[k], R[3 + k], R[6 + k]); }
+static inline v3 mmul(const float* R, v3 a) {
+  return V3(R[0] * a.x + R[1] * a.y + R[2] * a.z, R[3] * a.x + R[4] * a.y + R[5] * a.z,
+            R[6] * a.x + R[7] * a.y + R[8] * a.z);
+}
+static inline v3 mtmul(const float* R, v3 a) {
+  return V3(R[0] * a.x + R[3] * a.y + R[6] * a.z, R[1] * a.x + R[4] * a.y + R[7] * a.z,
+            R[2] * a.x + R[5] * a.y + R[8] * a.z);
+}
+
+/* sin/cos for |x| < ~100: Cody-Waite reduction by pi/2, cephes sinf/cosf minimax kernels */
+static inline void sdx_sincos(float x, float* s, float* c) {
+  float k = rintf(x * 0.63661977236758134f);
+  float r = x - k * 1.5703125f;
+  r = r - k * 4.837512969970703125e-4f;
+  r = r - k * 7.54978995489188e-8f;
+  float z = r * r;
+  float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+  float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z - 0.5f * z + 1.0f;
+  int n = ((int)k) & 3;
+  float ss = (n & 1) ? cp : sp;
+  float cc = (n & 1) ? sp : cp;
+  if (n == 1 || n == 2) cc = -cc;
+  if (n >= 2) ss = -ss;
+  *s = ss; *c = cc;
+}
+/* exp: cephes expf kernel, exact 2^n scaling */
+static inline float sdx_exp(float x) {
+  if (x > 88.0f) x = 88.0f;
+  if (x < -87.0f) x = -87.0f;
+  float n = rintf(x * 1.44269504088896341f);
+  float r = x - n * 0.693359375f;
+  r = r - n * -2.12194440e-4f;
+  float z = r * r;
+  float p = ((((1.9875691500e-4f * r + 1.3981999507e-3f) * r + 8.3334519073e-3f) * r + 4.1665795894e-2f) * r +
+             1.6666665459e-1f) * r + 5.0000001201e-1f;
+  float y = p * z + r + 1.0f;
+  union { uint32_t u; float f; } sc;
+  sc.u = (uint32_t)((int)n + 127) << 23;
+  return y * sc.f;
+}
+static inline float sdx_elu(float x) { return x > 0.0f ? x : sdx_exp(x) - 1.0f; }
+static inline float clampf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
+/* torch_utils.scale / unscale */
+static inline float scalef(float x, float lo, float hi) { return 0.5f * (x + 1.0f) * (hi - lo) + lo; }
+static inline float unscalef(float x, float lo, float hi) { return (2.0f * x - hi - lo) / (hi - lo); }
+
+/* Philox4x32-10, key = seed, counter = (env, episode, stream, 0) */
+static inline void philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t out[4]) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c[4] = {c0, c1, c2, 0u};
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1,
+             n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+
+/* ------------------------------------------------------------------ kinematics */
+typedef struct {
+  v3 lx[SDX_NL];   /* link origin (world, env-local) */
+  q4 lq[SDX_NL];
+  v3 ja[SDX_ND];   /* joint axis world */
+  v3 jo[SDX_ND];   /* joint origin world */
+} fk_t;
+
+/* forward kinematics of the collapsed Panda+Allegro tree */
+static void robot_fk(const sdx_scene_t* S, const float* q, fk_t* K) {
+  K->lx[0] = V3(S->base_pos[0], S->base_pos[1], S->base_pos[2]);
+  K->lq[0].x = S->base_quat[0]; K->lq[0].y = S->base_quat[1]; K->lq[0].z = S->base_quat[2]; K->lq[0].w = S->base_quat[3];
+  for (int j = 0; j < SDX_ND; ++j) {
+    int L = j + 1, P = S->body_parent[L];
+    q4 qf = {S->joint_quat[4 * j], S->joint_quat[4 * j + 1], S->joint_quat[4 * j + 2], S->joint_quat[4 * j + 3]};
+    v3 ax = V3(S->joint_axis[3 * j], S->joint_axis[3 * j + 1], S->joint_axis[3 * j + 2]);
+    q4 qj = qmul(K->lq[P], qf);
+    v3 x = vadd(K->lx[P], qrot(K->lq[P], V3(S->joint_xyz[3 * j], S->joint_xyz[3 * j + 1], S->joint_xyz[3 * j + 2])));
+    float s, c;
+    sdx_sincos(0.5f * q[j], &s, &c);
+    q4 qr = {ax.x * s, ax.y * s, ax.z * s, c};
+    K->lq[L] = qmul(qj, qr);
+    K->lx[L] = x;
+    K->ja[j] = qrot(qj, ax);
+    K->jo[j] = x;
+  }
+}
+
+/* ------------------------------------------------------------------ contact step */
+typedef struct {
+  uint32_t word;   /* a_body | b_body<<8 | b_shape<<16 | axis<<24 | sign<<26 */
+  float w[3];      /* contact point, world */
+  float bias;      /* target normal velocity */
+  float den[3];    /* mass-split effective inverse mass along n, t1, t2 */
+  float lam[3];
+} contact_t;
+
+typedef struct {
+  /* bodies: bricks 0..71 (origin = COM), links 72..95 (origin = link frame origin) */
+  v3 bx[NBODY]; q4 bq[NBODY]; float bR[NBODY][9];
+  v3 bv[NBODY], bw[NBODY];
+  v3 vfree[NB], wfree[NB];
+  float q[SDX_ND], qd[SDX_ND], tgt[SDX_ND], qdfree[SDX_ND], ieff[SDX_ND];
+  fk_t K;
+  /* target boxes: bricks, robot shapes, statics */
+  v3 sc[NSHAPE]; float sR[NSHAPE][9]; v3 sh[NSHAPE]; float srad[NSHAPE]; int sbody[NSHAPE];
+  v3 sa[NSHAPE]; float spd[NSHAPE];
+  unsigned char cand[NB + SDX_MAX_RSHAPES][KC]; int ncand[NB + SDX_MAX_RSHAPES];
+  contact_t con[SDX_MAX_CONTACTS]; int ncon, ndropped;
+  int nb[NBODY]; int nj[SDX_ND];
+  int inc_off[NBODY + 1]; unsigned short inc[2 * SDX_MAX_CONTACTS];
+  v3 linkF[SDX_NL], linkM[SDX_NL];
+} work_t;
+
+static inline v3 brick_Iinv_mul(const sdx_scene_t* S, const work_t* W, int b, v3 u) {
+  v3 l = mtmul(W->bR[b], u);
+  l.x = l.x * S->br_invI[3 * b]; l.y = l.y * S->br_invI[3 * b + 1]; l.z = l.z * S->br_invI[3 * b + 2];
+  return mmul(W->bR[b], l);
+}
+
+static void link_twists(const sdx_scene_t* S, work_t* W) {
+  for (int L = 0; L < SDX_NL; ++L) {
+    v3 w = V3(0, 0, 0), v = V3(0, 0, 0);
+    unsigned m = S->link_anc_mask[L];
+    for (int j = 0; j < SDX_ND; ++j)
+      if (m & (1u << j)) {
+        w = vadd(w, vscale(W->K.ja[j], W->qd[j]));
+        v = vadd(v, vscale(vcross(W->K.ja[j], vsub(W->K.lx[L], W->K.jo[j])), W->qd[j]));
+      }
+    W->bv[NB + L] = v; W->bw[NB + L] = w;
+  }
+}
+
+static void contact_axes(const work_t* W, const contact_t* c, v3* n, v3* t1, v3* t2) {
+  int sh = (c->word >> 16) & 255, k = (c->word >> 24) & 3;
+  float sg = ((c->word >> 26) & 1) ? -1.0f : 1.0f;
+  *n = vscale(mcol(W->sR[sh], k), sg);
+  *t1 = mcol(W->sR[sh], (k + 1) % 3);
+  *t2 = mcol(W->sR[sh], (k + 2) % 3);
+}
+
+static float body_k(const sdx_scene_t* S, const work_t* W, int body, v3 wpt, v3 d) {
+  if (body == STATIC_BODY) return 0.0f;
+  if (body < NB) {
+    v3 rxd = vcross(vsub(wpt, W->bx[body]), d);
+    float k = S->br_invm[body] + vdot(rxd, brick_Iinv_mul(S, W, body, rxd));
+    return (float)W->nb[body] * k;
+  }
+  int L = body - NB;
+  unsigned m = S->link_anc_mask[L];
+  float k = 0.0f;
+  for (int j = 0; j < SDX_ND; ++j)
+    if (m & (1u << j)) {
+      float g = vdot(W->K.ja[j], vcross(vsub(wpt, W->K.jo[j]), d));
+      k = k + (float)W->nj[j] * (g * g) / W->ieff[j];
+    }
+  return k;
+}
+
+/* one env, one control step = `substeps` sub-steps (gym.simulate, BT:140; yaml sim: substeps 2,
+ * 16 position iterations).  brick: [13][72]; dof: [3][24]; link_out: [24][13]; jac7: [6][7];
+ * netf: [24][3]; ncontact: [2]; condump: [MAXC][8] or NULL */
+static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_out, float* jac7, float* netf,
+                    int* ncontact, float* condump, work_t* W) {
+  const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;
+  const int n_owner = NB + nrs, n_target = NB + nrs + nst;
+  const float h = S->dt / (float)S->substeps;
+  const float margin = S->contact_offset;
+  for (int b = 0; b < NB; ++b) {
+    W->bx[b] = V3(brick[0 * NB + b], brick[1 * NB + b], brick[2 * NB + b]);
+    W->bq[b].x = brick[3 * NB + b]; W->bq[b].y = brick[4 * NB + b]; W->bq[b].z = brick[5 * NB + b]; W->bq[b].w = brick[6 * NB + b];
+    W->bv[b] = V3(brick[7 * NB + b], brick[8 * NB + b], brick[9 * NB + b]);
+    W->bw[b] = V3(brick[10 * NB + b], brick[11 * NB + b], brick[12 * NB + b]);
+  }
+  for (int j = 0; j < SDX_ND; ++j) { W->q[j] = dof[j]; W->qd[j] = dof[24 + j]; W->tgt[j] = dof[48 + j]; }
+  /* static target boxes never change */
+  for (int s = 0; s < nst; ++s) {
+    int t = NB + nrs + s;
+    W->sc[t] = V3(S->st_c[3 * s], S->st_c[3 * s + 1], S->st_c[3 * s + 2]);
+    W->sh[t] = V3(S->st_h[3 * s], S->st_h[3 * s + 1], S->st_h[3 * s + 2]);
+    for (int i = 0; i < 9; ++i) W->sR[t][i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    W->sbody[t] = STATIC_BODY;
+    W->srad[t] = 0.0f;
+  }
+  for (int sub = 0; sub < S->substeps; ++sub) {
+    /* 1. kinematics + shape poses */
+    robot_fk(S, W->q, &W->K);
+    for (int L = 0; L < SDX_NL; ++L) { W->bx[NB + L] = W->K.lx[L]; W->bq[NB + L] = W->K.lq[L]; qmat(W->K.lq[L], W->bR[NB + L]); }
+    for (int b = 0; b < NB; ++b) {
+      qmat(W->bq[b], W->bR[b]);
+      W->sc[b] = W->bx[b];
+      for (int i = 0; i < 9; ++i) W->sR[b][i] = W->bR[b][i];
+      W->sh[b] = V3(S->br_half[3 * b], S->br_half[3 * b + 1], S->br_half[3 * b + 2]);
+      W->srad[b] = sqrtf(vdot(W->sh[b], W->sh[b]));
+      W->sbody[b] = b;
+    }
+    for (int r = 0; r < nrs; ++r) {
+      int t = NB + r, L = S->rs_body[r];
+      q4 ql = {S->rs_quat[4 * r], S->rs_quat[4 * r + 1], S->rs_quat[4 * r + 2], S->rs_quat[4 * r + 3]};
+      W->sc[t] = vadd(W->K.lx[L], qrot(W->K.lq[L], V3(S->rs_c[3 * r], S->rs_c[3 * r + 1], S->rs_c[3 * r + 2])));
+      qmat(qmul(W->K.lq[L], ql), W->sR[t]);
+      W->sh[t] = V3(S->rs_h[3 * r], S->rs_h[3 * r + 1], S->rs_h[3 * r + 2]);
+      W->srad[t] = sqrtf(vdot(W->sh[t], W->sh[t]));
+      W->sbody[t] = NB + L;
+    }
+    /* 2. free velocities: gravity + angular damping on bricks, implicit PD on joints */
+    {
+      float damp = 1.0f - h * S->brick_ang_damp;
+      float ldamp = 1.0f - h * S->brick_lin_damp;
+      for (int b = 0; b < NB; ++b) {
+        W->vfree[b] = vscale(V3(W->bv[b].x, W->bv[b].y, W->bv[b].z + h * S->gravity_z), ldamp);
+        W->wfree[b] = vscale(W->bw[b], damp);
+        if (b >= nbr) { W->vfree[b] = V3(0, 0, 0); W->wfree[b] = V3(0, 0, 0); }
+        W->bv[b] = W->vfree[b]; W->bw[b] = W->wfree[b];
+      }
+      for (int j = 0; j < SDX_ND; ++j) {
+        float I = S->dof_inertia[j], kp = S->dof_kp[j], kd = S->dof_kd[j];
+        float ieff = I + h * kd + (h * h) * kp;
+        float qn = (I * W->qd[j] + h * kp * (W->tgt[j] - W->q[j])) / ieff;
+        float tau = I * (qn - W->qd[j]) / h;
+        if (tau > S->dof_effort[j]) qn = W->qd[j] + S->dof_effort[j] * h / I;
+        if (tau < -S->dof_effort[j]) qn = W->qd[j] - S->dof_effort[j] * h / I;
+        qn = clampf(qn, -S->dof_vmax[j], S->dof_vmax[j]);
+        W->ieff[j] = ieff; W->qdfree[j] = qn; W->qd[j] = qn;
+      }
+      link_twists(S, W);
+    }
+    /* 3. broad phase: per owner shape, candidate target boxes in index order (world-AABB overlap,
+     *    inflated by the contact offset plus the distance both shapes can travel in this sub-step) */
+    for (int t = 0; t < n_target; ++t) {
+      const float* R = W->sR[t];
+      W->sa[t] = V3(fabsf(R[0]) * W->sh[t].x + fabsf(R[1]) * W->sh[t].y + fabsf(R[2]) * W->sh[t].z,
+                    fabsf(R[3]) * W->sh[t].x + fabsf(R[4]) * W->sh[t].y + fabsf(R[5]) * W->sh[t].z,
+                    fabsf(R[6]) * W->sh[t].x + fabsf(R[7]) * W->sh[t].y + fabsf(R[8]) * W->sh[t].z);
+      float spd = 0.0f;
+      if (t < NB + nrs) {
+        int bd = W->sbody[t];
+        v3 dc = vsub(W->sc[t], W->bx[bd]);
+        float reach = sqrtf(vdot(dc, dc)) + W->srad[t];
+        spd = h * (sqrtf(vdot(W->bv[bd], W->bv[bd])) + sqrtf(vdot(W->bw[bd], W->bw[bd])) * reach);
+      }
+      W->spd[t] = spd;
+    }
+    int cand_dropped = 0;
+    for (int a = 0; a < n_owner; ++a) {
+      int k = 0;
+      if (a < NB && a >= nbr) { W->ncand[a] = 0; continue; }
+      for (int t = 0; t < n_target; ++t) {
+        if (t == a) continue;
+        if (t < NB && t >= nbr) continue;
+        if (a >= NB && t >= NB && t < NB + nrs) continue; /* robot-robot filtered (GS:906 filter -1) */
+        v3 d = vsub(W->sc[a], W->sc[t]);
+        float m = margin + W->spd[a] + W->spd[t];
+        int hit = fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
+                  fabsf(d.z) <= W->sa[a].z + W->sa[t].z + m;
+        if (hit) { if (k < KC) W->cand[a][k++] = (unsigned char)t; else cand_dropped++; }
+      }
+      W->ncand[a] = k;
+    }
+    /* 4. narrow phase, per ordered pair (owner a, target t): reference face of t = its axis of least
+     *    overlap with a (SAT over t's three face axes); a's sample points that lie over that face and
+     *    within the speculative margin below/above it become contacts.  Order: owner, candidate, point. */
+    W->ncon = 0; W->ndropped = cand_dropped;
+    for (int a = 0; a < n_owner; ++a) {
+      int npts = (a < NB && W->sh[a].x > 0.04f) ? 12 : 8; /* long bricks add 4 mid-edge points */
+      for (int ci = 0; ci < W->ncand[a]; ++ci) {
+        int t = W->cand[a][ci];
+        float m = margin + W->spd[a] + W->spd[t];
+        v3 lc = mtmul(W->sR[t], vsub(W->sc[a], W->sc[t]));
+        float C[9]; /* C = R_t^T R_a */
+        for (int r = 0; r < 3; ++r)
+          for (int c2 = 0; c2 < 3; ++c2)
+            C[3 * r + c2] = W->sR[t][r] * W->sR[a][c2] + W->sR[t][3 + r] * W->sR[a][3 + c2] + W->sR[t][6 + r] * W->sR[a][6 + c2];
+        v3 ha = W->sh[a], ht = W->sh[t];
+        float o0 = ht.x + (fabsf(C[0]) * ha.x + fabsf(C[1]) * ha.y + fabsf(C[2]) * ha.z) - fabsf(lc.x);
+        float o1 = ht.y + (fabsf(C[3]) * ha.x + fabsf(C[4]) * ha.y + fabsf(C[5]) * ha.z) - fabsf(lc.y);
+        float o2 = ht.z + (fabsf(C[6]) * ha.x + fabsf(C[7]) * ha.y + fabsf(C[8]) * ha.z) - fabsf(lc.z);
+        int k = 0; float ov = o0;
+        if (o1 < ov) { k = 1; ov = o1; }
+        if (o2 < ov) { k = 2; ov = o2; }
+        if (ov < -m) continue;
+        float lck = k == 0 ? lc.x : (k == 1 ? lc.y : lc.z);
+        float sgf = lck >= 0.0f ? 1.0f : -1.0f;
+        uint32_t sg = lck >= 0.0f ? 0u : 1u;
+        float htk = k == 0 ? ht.x : (k == 1 ? ht.y : ht.z);
+        for (int p = 0; p < npts; ++p) {
+          v3 pl;
+          if (p < 8) pl = V3((p & 1) ? ha.x : -ha.x, (p & 2) ? ha.y : -ha.y, (p & 4) ? ha.z : -ha.z);
+          else pl = V3(0.0f, (p & 1) ? ha.y : -ha.y, (p & 2) ? ha.z : -ha.z);
+          v3 l = vadd(lc, mmul(C, pl));
+          float lk = k == 0 ? l.x : (k == 1 ? l.y : l.z);
+          float depth = htk - sgf * lk;
+          if (!(depth > -m)) continue;
+          int inface = (k == 0 || fabsf(l.x) <= ht.x + margin) && (k == 1 || fabsf(l.y) <= ht.y + margin) &&
+                       (k == 2 || fabsf(l.z) <= ht.z + margin);
+          if (!inface) continue;
+          if (W->ncon >= SDX_MAX_CONTACTS) { W->ndropped++; continue; }
+          contact_t* c = &W->con[W->ncon++];
+          v3 wpt = vadd(W->sc[a], mmul(W->sR[a], pl));
+          c->word = (uint32_t)W->sbody[a] | ((uint32_t)W->sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)k << 24) | (sg << 26);
+          c->w[0] = wpt.x; c->w[1] = wpt.y; c->w[2] = wpt.z;
+          float bias = 0.0f;
+          if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
+          else if (depth < 0.0f) bias = depth / h;
+          c->bias = bias;
+          c->lam[0] = c->lam[1] = c->lam[2] = 0.0f;
+          c->den[0] = depth; /* scratch: kept for the debug dump, overwritten below */
+        }
+      }
+    }
+    /* 5. incidence (CSR in contact order) + mass-splitting counts */
+    for (int b = 0; b < NBODY; ++b) W->nb[b] = 0;
+    for (int i = 0; i < W->ncon; ++i) {
+      int a = W->con[i].word & 255, b = (W->con[i].word >> 8) & 255;
+      W->nb[a]++; if (b != STATIC_BODY) W->nb[b]++;
+    }
+    W->inc_off[0] = 0;
+    for (int b = 0; b < NBODY; ++b) W->inc_off[b + 1] = W->inc_off[b] + W->nb[b];
+    for (int b = 0; b < NBODY; ++b) {
+      int o = W->inc_off[b];
+      for (int i = 0; i < W->ncon; ++i) {
+        int a = W->con[i].word & 255, bb = (W->con[i].word >> 8) & 255;
+        if (a == b) W->inc[o++] = (unsigned short)(i << 1);
+        else if (bb == b) W->inc[o++] = (unsigned short)((i << 1) | 1);
+      }
+    }
+    for (int j = 0; j < SDX_ND; ++j) {
+      int n = 0;
+      for (int L = 0; L < SDX_NL; ++L) if (S->link_anc_mask[L] & (1u << j)) n += W->nb[NB + L];
+      W->nj[j] = n;
+    }
+    if (condump && sub == S->substeps - 1)
+      for (int i = 0; i < W->ncon; ++i) {
+        float* o = condump + 8 * i;
+        union { uint32_t u; float f; } cv; cv.u = W->con[i].word;
+        o[0] = cv.f; o[1] = W->con[i].w[0]; o[2] = W->con[i].w[1]; o[3] = W->con[i].w[2]; o[4] = W->con[i].den[0];
+        o[5] = W->con[i].bias; o[6] = 0.0f; o[7] = 0.0f;
+      }
+    for (int i = 0; i < W->ncon; ++i) {
+      contact_t* c = &W->con[i];
+      int a = c->word & 255, b = (c->word >> 8) & 255;
+      v3 n, t1, t2; contact_axes(W, c, &n, &t1, &t2);
+      v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
+      c->den[0] = body_k(S, W, a, wpt, n) + body_k(S, W, b, wpt, n);
+      c->den[1] = body_k(S, W, a, wpt, t1) + body_k(S, W, b, wpt, t1);
+      c->den[2] = body_k(S, W, a, wpt, t2) + body_k(S, W, b, wpt, t2);
+    }
+    /* 6. mass-splitting Jacobi iterations on the total impulses */
+    for (int it = 0; it < S->iters; ++it) {
+      for (int i = 0; i < W->ncon; ++i) { /* phase A: one contact each */
+        contact_t* c = &W->con[i];
+        int a = c->word & 255, b = (c->word >> 8) & 255;
+        v3 n, t1, t2; contact_axes(W, c, &n, &t1, &t2);
+        v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
+        v3 vrel = vadd(W->bv[a], vcross(W->bw[a], vsub(wpt, W->bx[a])));
+        if (b != STATIC_BODY) vrel = vsub(vrel, vadd(W->bv[b], vcross(W->bw[b], vsub(wpt, W->bx[b]))));
+        float ln = c->lam[0] + (c->bias - vdot(vrel, n)) / c->den[0];
+        ln = ln > 0.0f ? ln : 0.0f;
+        float lim = S->friction * ln;
+        float l1 = clampf(c->lam[1] - vdot(vrel, t1) / c->den[1], -lim, lim);
+        float l2 = clampf(c->lam[2] - vdot(vrel, t2) / c->den[2], -lim, lim);
+        c->lam[0] = ln; c->lam[1] = l1; c->lam[2] = l2;
+      }
+      for (int b = 0; b < NBODY; ++b) { /* phase B: one body each, incident contacts in order */
+        v3 F = V3(0, 0, 0), T = V3(0, 0, 0);
+        for (int e = W->inc_off[b]; e < W->inc_off[b + 1]; ++e) {
+          const contact_t* c = &W->con[W->inc[e] >> 1];
+          v3 n, t1, t2; contact_axes(W, c, &n, &t1, &t2);
+          v3 f = vadd(vadd(vscale(n, c->lam[0]), vscale(t1, c->lam[1])), vscale(t2, c->lam[2]));
+          if (W->inc[e] & 1) f = vneg(f);
+          v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
+          F = vadd(F, f);
+          if (b < NB) T = vadd(T, vcross(vsub(wpt, W->bx[b]), f));
+          else T = vadd(T, vcross(wpt, f));
+        }
+        if (b < NB) {
+          W->bv[b] = vadd(W->vfree[b], vscale(F, S->br_invm[b]));
+          W->bw[b] = vadd(W->wfree[b], brick_Iinv_mul(S, W, b, T));
+        } else { W->linkF[b - NB] = F; W->linkM[b - NB] = T; }
+      }
+      for (int j = 0; j < SDX_ND; ++j) {
+        v3 Fd = V3(0, 0, 0), Md = V3(0, 0, 0);
+        for (int L = 0; L < SDX_NL; ++L)
+          if (S->link_anc_mask[L] & (1u << j)) { Fd = vadd(Fd, W->linkF[L]); Md = vadd(Md, W->linkM[L]); }
+        float g = vdot(W->K.ja[j], vsub(Md, vcross(W->K.jo[j], Fd)));
+        W->qd[j] = W->qdfree[j] + g / W->ieff[j];
+      }
+      link_twists(S, W);
+    }
+    if (S->iters == 0) for (int L = 0; L < SDX_NL; ++L) { W->linkF[L] = V3(0, 0, 0); W->linkM[L] = V3(0, 0, 0); }
+    /* 7. integrate */
+    for (int b = 0; b < nbr; ++b) {
+      v3 w = W->bw[b], v = W->bv[b];
+      float w2 = vdot(w, w), mw = S->max_ang_vel;
+      if (w2 > mw * mw) { w = vscale(w, mw / sqrtf(w2)); W->bw[b] = w; }
+      float v2 = vdot(v, v), mv = S->max_lin_vel;
+      if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); W->bv[b] = v; }
+      W->bx[b] = vadd(W->bx[b], vscale(v, h));
+      q4 q = W->bq[b];
+      float hh = 0.5f * h;
+      q4 dq;
+      dq.x = hh * (w.x * q.w + w.y * q.z - w.z * q.y);
+      dq.y = hh * (w.y * q.w + w.z * q.x - w.x * q.z);
+      dq.z = hh * (w.z * q.w + w.x * q.y - w.y * q.x);
+      dq.w = hh * (-(w.x * q.x + w.y * q.y + w.z * q.z));
+      q.x = q.x + dq.x; q.y = q.y + dq.y; q.z = q.z + dq.z; q.w = q.w + dq.w;
+      float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+      q.x = q.x * inv; q.y = q.y * inv; q.z = q.z * inv; q.w = q.w * inv;
+      W->bq[b] = q;
+    }
+    for (int j = 0; j < SDX_ND; ++j) {
+      float qn = W->q[j] + h * W->qd[j];
+      if (qn < S->dof_lo[j]) { qn = S->dof_lo[j]; if (W->qd[j] < 0.0f) W->qd[j] = 0.0f; }
+      if (qn > S->dof_hi[j]) { qn = S->dof_hi[j]; if (W->qd[j] > 0.0f) W->qd[j] = 0.0f; }
+      W->q[j] = qn;
+    }
+  }
+  /* epilogue: state write-back + the rows the task reads */
+  for (int b = 0; b < NB; ++b) {
+    brick[0 * NB + b] = W->bx[b].x; brick[1 * NB + b] = W->bx[b].y; brick[2 * NB + b] = W->bx[b].z;
+    brick[3 * NB + b] = W->bq[b].x; brick[4 * NB + b] = W->bq[b].y; brick[5 * NB + b] = W->bq[b].z; brick[6 * NB + b] = W->bq[b].w;
+    brick[7 * NB + b] = W->bv[b].x; brick[8 * NB + b] = W->bv[b].y; brick[9 * NB + b] = W->bv[b].z;
+    brick[10 * NB + b] = W->bw[b].x; brick[11 * NB + b] = W->bw[b].y; brick[12 * NB + b] = W->bw[b].z;
+  }
+  for (int j = 0; j < SDX_ND; ++j) { dof[j] = W->q[j]; dof[24 + j] = W->qd[j]; }
+  robot_fk(S, W->q, &W->K);
+  link_twists(S, W);
+  for (int L = 0; L < SDX_NL; ++L) {
+    float* o = link_out + 13 * L;
+    o[0] = W->K.lx[L].x; o[1] = W->K.lx[L].y; o[2] = W->K.lx[L].z;
+    o[3] = W->K.lq[L].x; o[4] = W->K.lq[L].y; o[5] = W->K.lq[L].z; o[6] = W->K.lq[L].w;
+    o[7] = W->bv[NB + L].x; o[8] = W->bv[NB + L].y; o[9] = W->bv[NB + L].z;
+    o[10] = W->bw[NB + L].x; o[11] = W->bw[NB + L].y; o[12] = W->bw[NB + L].z;
+    float invh = 1.0f / h;
+    netf[3 * L] = W->linkF[L].x * invh; netf[3 * L + 1] = W->linkF[L].y * invh; netf[3 * L + 2] = W->linkF[L].z * invh;
+  }
+  for (int j = 0; j < 7; ++j) {
+    v3 lin = vcross(W->K.ja[j], vsub(W->K.lx[7], W->K.jo[j]));
+    jac7[0 * 7 + j] = lin.x; jac7[1 * 7 + j] = lin.y; jac7[2 * 7 + j] = lin.z;
+    jac7[3 * 7 + j] = W->K.ja[j].x; jac7[4 * 7 + j] = W->K.ja[j].y; jac7[5 * 7 + j] = W->K.ja[j].z;
+  }
+  ncontact[0] = W->ncon; ncontact[1] = W->ndropped;
+}
+
+typedef struct {
+  const sdx_scene_t* S; int n; float *brick, *dof, *link, *jac7, *netf; int* ncontact; float* condump;
+  int tid, nthreads;
+} sim_job_t;
+static void* sim_worker(void* arg) {
+  sim_job_t* J = (sim_job_t*)arg;
+  work_t* W = (work_t*)malloc(sizeof(work_t));
+  for (int e = J->tid; e < J->n; e += J->nthreads)
+    sim_env(J->S, J->brick + (size_t)e * 13 * NB, J->dof + (size_t)e * 72, J->link + (size_t)e * SDX_NL * 13,
+            J->jac7 + (size_t)e * 42, J->netf + (size_t)e * SDX_NL * 3, J->ncontact + 2 * e,
+            J->condump ? J->condump + (size_t)e * SDX_MAX_CONTACTS * 8 : 0, W);
+  free(W);
+  return 0;
+}
+static int g_threads = 0;
+void sdxo_set_threads(int t) { g_threads = t; }
+int sdxo_get_threads(void) {
+  if (g_threads > 0) return g_threads;
+  long c = sysconf(_SC_NPROCESSORS_ONLN);
+  return c > 0 ? (int)c : 1;
+}
+/* envs are independent: static round-robin over host threads (results do not depend on the thread count) */
+void sdxo_simulate(const sdx_scene_t* S, int n, float* brick, float* dof, float* link, float* jac7, float* netf,
+                   int* ncontact, float* condump) {
+  int nt = sdxo_get_threads();
+  if (nt > n) nt = n;
+  if (nt < 1) nt = 1;
+  if (nt > 256) nt = 256;
+  pthread_t th[256]; sim_job_t jobs[256];
+  for (int t = 0; t < nt; ++t) {
+    sim_job_t j = {S, n, brick, dof, link, jac7, netf, ncontact, condump, t, nt};
+    jobs[t] = j;
+    if (t > 0) pthread_create(&th[t], 0, sim_worker, &jobs[t]);
+  }
+  sim_worker(&jobs[0]);
+  for (int t = 1; t < nt; ++t) pthread_join(th[t], 0);
+}
+
+/* FK-only refresh of link rows / jacobian (used after resets and at creation) */
+void sdxo_refresh_links(const sdx_scene_t* S, int n, const float* dof, float* link, float* jac7) {
+  for (int e = 0; e < n; ++e) {
+    work_t* W = (work_t*)malloc(sizeof(work_t));
+    const float* d = dof + (size_t)e * 72;
+    for (int j = 0; j < SDX_ND; ++j) { W->q[j] = d[j]; W->qd[j] = d[24 + j]; }
+    robot_fk(S, W->q, &W->K);
+    link_twists(S, W);
+    for (int L = 0; L < SDX_NL; ++L) {
+      float* o = link + (size_t)e * SDX_NL * 13 + 13 * L;
+      o[0] = W->K.lx[L].x; o[1] = W->K.lx[L].y; o[2] = W->K.lx[L].z;
+      o[3] = W->K.lq[L].x; o[4] = W->K.lq[L].y; o[5] = W->K.lq[L].z; o[6] = W->K.lq[L].w;
+      o[7] = W->bv[NB + L].x; o[8] = W->bv[NB + L].y; o[9] = W->bv[NB + L].z;
+      o[10] = W->bw[NB + L].x; o[11] = W->bw[NB + L].y; o[12] = W->bw[NB + L].z;
+    }
+    float* J = jac7 + (size_t)e * 42;
+    for (int j = 0; j < 7; ++j) {
+      v3 lin = vcross(W->K.ja[j], vsub(W->K.lx[7], W->K.jo[j]));
+      J[0 * 7 + j] = lin.x; J[1 * 7 + j] = lin.y; J[2 * 7 + j] = lin.z;
+      J[3 * 7 + j] = W->K.ja[j].x; J[4 * 7 + j] = W->K.ja[j].y; J[5 * 7 + j] = W->K.ja[j].z;
+    }
+    free(W);
+  }
+}
+
+/* ------------------------------------------------------------------ task ops */
+static inline int target_brick(int env) { int s = env % 8; return (s == 3 || s == 4 || s == 7) ? 0 : s; } /* GS:962-975 */
+
+/* COM-frame brick block -> Isaac-Gym root row of brick b (pos = COM - R*coff, v_root = v + w x (root-COM)) */
+static void brick_root_row(const sdx_scene_t* S, const float* brick, int b, float* row) {
+  v3 x = V3(brick[0 * NB + b], brick[1 * NB + b], brick[2 * NB + b]);
+  q4 q = {brick[3 * NB + b], brick[4 * NB + b], brick[5 * NB + b], brick[6 * NB + b]};
+  v3 v = V3(brick[7 * NB + b], brick[8 * NB + b], brick[9 * NB + b]);
+  v3 w = V3(brick[10 * NB + b], brick[11 * NB + b], brick[12 * NB + b]);
+  v3 off = qrot(q, V3(S->br_coff[3 * b], S->br_coff[3 * b + 1], S->br_coff[3 * b + 2]));
+  v3 p = vsub(x, off);
+  v3 vr = vsub(v, vcross(w, off));
+  row[0] = p.x; row[1] = p.y; row[2] = p.z; row[3] = q.x; row[4] = q.y; row[5] = q.z; row[6] = q.w;
+  row[7] = vr.x; row[8] = vr.y; row[9] = vr.z; row[10] = w.x; row[11] = w.y; row[12] = w.z;
+}
+static void brick_from_root_row(const sdx_scene_t* S, float* brick, int b, const float* row) {
+  q4 q = {row[3], row[4], row[5], row[6]};
+  v3 off = qrot(q, V3(S->br_coff[3 * b], S->br_coff[3 * b + 1], S->br_coff[3 * b + 2]));
+  v3 w = V3(row[10], row[11], row[12]);
+  v3 x = vadd(V3(row[0], row[1], row[2]), off);
+  v3 v = vadd(V3(row[7], row[8], row[9]), vcross(w, off));
+  brick[0 * NB + b] = x.x; brick[1 * NB + b] = x.y; brick[2 * NB + b] = x.z;
+  brick[3 * NB + b] = q.x; brick[4 * NB + b] = q.y; brick[5 * NB + b] = q.z; brick[6 * NB + b] = q.w;
+  brick[7 * NB + b] = v.x; brick[8 * NB + b] = v.y; brick[9 * NB + b] = v.z;
+  brick[10 * NB + b] = w.x; brick[11 * NB + b] = w.y; brick[12 * NB + b] = w.z;
+}
+void sdxo_brick_root_rows(const sdx_scene_t* S, int n, const float* brick, float* rows /* [n][72][13] */) {
+  for (int e = 0; e < n; ++e)
+    for (int b = 0; b < NB; ++b) brick_root_row(S, brick + (size_t)e * 13 * NB, b, rows + ((size_t)e * NB + b) * 13);
+}
+void sdxo_brick_from_root_rows(const sdx_scene_t* S, int n, float* brick, const float* rows) {
+  for (int e = 0; e < n; ++e)
+    for (int b = 0; b < NB; ++b) brick_from_root_row(S, brick + (size_t)e * 13 * NB, b, rows + ((size_t)e * NB + b) * 13);
+}
+
+/* GraspInsertTValue forward (TVF:30-46) + sigmoid(.)[1] (GS:1200-1201).
+ * weights: W1[256][4] b1[256] W2[128][256] b2 W3[64][128] b3 W4[2][64] b4 */
+float sdxo_tvalue_one(const float* wts, const float* qin) {
+  const float* W1 = wts; const float* b1 = W1 + 256 * 4; const float* W2 = b1 + 256; const float* b2 = W2 + 128 * 256;
+  const float* W3 = b2 + 128; const float* b3 = W3 + 64 * 128; const float* W4 = b3 + 64; const float* b4 = W4 + 2 * 64;
+  float h1[256], h2[128], h3[64];
+  for (int o = 0; o < 256; ++o) { float a = b1[o]; for (int k = 0; k < 4; ++k) a = a + W1[o * 4 + k] * qin[k]; h1[o] = sdx_elu(a); }
+  for (int o = 0; o < 128; ++o) { float a = b2[o]; for (int k = 0; k < 256; ++k) a = a + W2[o * 256 + k] * h1[k]; h2[o] = sdx_elu(a); }
+  for (int o = 0; o < 64; ++o) { float a = b3[o]; for (int k = 0; k < 128; ++k) a = a + W3[o * 128 + k] * h2[k]; h3[o] = sdx_elu(a); }
+  float a = b4[1]; for (int k = 0; k < 64; ++k) a = a + W4[64 + k] * h3[k];
+  a = sdx_elu(a);
+  return 1.0f / (1.0f + sdx_exp(-a));
+}
+void sdxo_tvalue(const float* wts, int n, const float* qin, float* out) { for (int e = 0; e < n; ++e) out[e] = sdxo_tvalue_one(wts, qin + 4 * e); }
+
+/* control_ik (GS:1796-1804): u = J^T (J J^T + 0.05^2 I)^-1 dpose, 6x7 J, solved by Cholesky */
+static void control_ik(const float* J /*[6][7]*/, const float* dpose, float* u /*[7]*/) {
+  float A[6][6], y[6];
+  for (int r = 0; r < 6; ++r)
+    for (int c = 0; c < 6; ++c) {
+      float s = 0.0f;
+      for (int k = 0; k < 7; ++k) s = s + J[r * 7 + k] * J[c * 7 + k];
+      if (r == c) s = s + 0.05f * 0.05f;
+      A[r][c] = s;
+    }
+  for (int c = 0; c < 6; ++c) { /* A = L L^T, in place (lower) */
+    float d = A[c][c];
+    for (int k = 0; k < c; ++k) d = d - A[c][k] * A[c][k];
+    d = sqrtf(d);
+    A[c][c] = d;
+    for (int r = c + 1; r < 6; ++r) {
+      float s = A[r][c];
+      for (int k = 0; k < c; ++k) s = s - A[r][k] * A[c][k];
+      A[r][c] = s / d;
+    }
+  }
+  for (int r = 0; r < 6; ++r) { float s = dpose[r]; for (int k = 0; k < r; ++k) s = s - A[r][k] * y[k]; y[r] = s / A[r][r]; }
+  for (int r = 5; r >= 0; --r) { float s = y[r]; for (int k = r + 1; k < 6; ++k) s = s - A[k][r] * y[k]; y[r] = s / A[r][r]; }
+  for (int k = 0; k < 7; ++k) { float s = 0.0f; for (int r = 0; r < 6; ++r) s = s + J[r * 7 + k] * y[r]; u[k] = s; }
+}
+void sdxo_control_ik(int n, const float* J, const float* dpose, float* u) { for (int e = 0; e < n; ++e) control_ik(J + 42 * e, dpose + 6 * e, u + 7 * e); }
+
+/* reset_idx (GS:1361-1553) for the envs whose reset_buf is set.  Dead writes of the reference are
+ * not restated (DESIGN.md "reset"): the randomised target pose (GS:1488-1499) is overwritten by the
+ * banked heap row (GS:1508-1511) and perturb_* (GS:1460-1461) feed a disabled branch. */
+void sdxo_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* bank, int per_type, float* brick, float* dof,
+                float* target_init, int64_t* progress, int64_t* reset, float* successes, int* episode,
+                /* grasp terminal-state banking (GS:1399-1445) */
+                int do_bank, const float* finger_dist, const float* tvalue, float* gb_hand, float* gb_obj, int* gb_index) {
+  if (do_bank) {
+    for (int e = 0; e < n; ++e) {
+      if (!reset[e]) continue;
+      int ty = e % 8, tb = target_brick(e);
+      float row[13];
+      float* B = brick + (size_t)e * 13 * NB;
+      brick_root_row(S, B, tb, row);
+      if (row[1] < 0.0f && finger_dist[e] < 0.6f && tvalue[e] > 0.8f) {
+        int slot = gb_index[ty];
+        float* hd = gb_hand + ((size_t)ty * 11024 + slot) * 46;
+        const float* d = dof + (size_t)e * 72;
+        for (int j = 0; j < SDX_ND; ++j) { hd[2 * j] = d[j]; hd[2 * j + 1] = d[24 + j]; }
+        float* ob = gb_obj + ((size_t)ty * 11024 + slot) * 13;
+        for (int k = 0; k < 13; ++k) ob[k] = row[k];
+        gb_index[ty] = slot + 1;
+      }
+      if (gb_index[ty] > 5000) gb_index[ty] = 0;
+    }
+  }
+  for (int e = 0; e < n; ++e) {
+    if (!reset[e]) continue;
+    float* B = brick + (size_t)e * 13 * NB;
+    float* d = dof + (size_t)e * 72;
+    uint32_t r[4];
+    philox(seed, (uint32_t)e, (uint32_t)episode[e], 1u, r);
+    int slot = (int)(r[0] % (uint32_t)per_type);
+    const float* rows = bank + (((size_t)(e % 8)) * per_type + slot) * NB * 13;
+    for (int b = 0; b < NB; ++b) {
+      float row[13];
+      for (int k = 0; k < 7; ++k) row[k] = rows[b * 13 + k];
+      for (int k = 7; k < 13; ++k) row[k] = 0.0f; /* GS:1513 */
+      brick_from_root_row(S, B, b, row);
+    }
+    for (int j = 0; j < 7; ++j) { d[j] = S->prepare_arm[j]; d[24 + j] = 0.0f; d[48 + j] = S->prepare_arm[j]; }
+    for (int i = 0; i < 16; ++i) {
+      float v = scalef(S->finger_reset_unscaled[i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+      d[7 + i] = v; d[24 + 7 + i] = 0.0f; d[48 + 7 + i] = v;
+    }
+    int tb = target_brick(e);
+    for (int k = 0; k < 7; ++k) target_init[7 * e + k] = rows[tb * 13 + k]; /* GS:1547-1548 */
+    progress[e] = 0; reset[e] = 0; successes[e] = 0.0f; /* GS:1550-1552 */
+    episode[e] += 1;
+  }
+}
+
+/* pre_physics_step after resets (GS:1570-1638): actions -> DoF position targets */
+void sdxo_pre_physics(const sdx_scene_t* S, int n, const float* actions_in, float* actions, float* dof, const float* link,
+                      const float* jac7, const int64_t* progress, const float* target_init) {
+  for (int e = 0; e < n; ++e) {
+    const float* a = actions_in + 23 * e;
+    float* d = dof + (size_t)e * 72;
+    float cur[23];
+    for (int k = 0; k < 23; ++k) actions[23 * e + k] = a[k];
+    for (int i = 0; i < 16; ++i) {
+      float t = scalef(a[7 + i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+      cur[7 + i] = S->act_moving_average * t + (1.0f - S->act_moving_average) * d[48 + 7 + i];
+    }
+    float dpose[6] = {a[0] * 0.64f, a[1] * 0.64f, a[2] * 0.64f, a[3] * 0.2f, a[4] * 0.2f, a[5] * 0.2f};
+    int64_t pg = progress[e];
+    if (pg > 75) {
+      dpose[2] = 0.2f + 0.22f + (target_init[7 * e + 2] - link[((size_t)e * SDX_NL + 7) * 13 + 2]);
+      dpose[0] = 0.0f; dpose[1] = 0.0f;
+    }
+    float u[7];
+    control_ik(jac7 + 42 * (size_t)e, dpose, u);
+    for (int j = 0; j < 7; ++j) cur[j] = d[j] + u[j];
+    if (pg > 100) for (int j = 0; j < 7; ++j) cur[j] = S->insert_prep0[j];
+    if (pg > 125) for (int j = 0; j < 7; ++j) cur[j] = S->insert_prep1[j];
+    if (pg > 75) for (int i = 7; i < 23; ++i) cur[i] = d[48 + i];
+    for (int j = 0; j < 23; ++j) d[48 + j] = clampf(cur[j], S->dof_lo[j], S->dof_hi[j]);
+  }
+}
+
+/* post_physics_step (GS:1640-1645): progress += 1, compute_observations (GS:1090-1332),
+ * compute_hand_reward (GS:1706-1776).  obs [n][396], states [n][564] (UNCLAMPED task buffers). */
+void sdxo_post_physics(const sdx_scene_t* S, int n, const float* tv_wts, const float* brick, const float* dof,
+                       const float* link, const float* actions, const float* target_init, int64_t* progress,
+                       int64_t* reset, float* obs, float* states, float* rew, float* tvalue, float* finger_dist_out,
+                       const float* successes, float* consec) {
+  int64_t num_resets = 0; float finished = 0.0f;
+  for (int e = 0; e < n; ++e) {
+    progress[e] += 1;
+    const float* L = link + (size_t)e * SDX_NL * 13;
+    const float* d = dof + (size_t)e * 72;
+    const float* hb = L + 7 * 13; /* hand base = panda_link7 (GS:355,1110) */
+    const float* ff = L + 11 * 13; const float* mf = L + 19 * 13; const float* rf = L + 23 * 13; const float* th = L + 15 * 13; /* GS:183-186,1130-1152 */
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), tg);
+    v3 tp = V3(tg[0], tg[1], tg[2]); q4 tq = {tg[3], tg[4], tg[5], tg[6]};
+    v3 tip[4]; const float* fs[4] = {ff, mf, rf, th};
+    for (int i = 0; i < 4; ++i) { /* GS:1154-1157 */
+      q4 fq = {fs[i][3], fs[i][4], fs[i][5], fs[i][6]};
+      tip[i] = vadd(V3(fs[i][0], fs[i][1], fs[i][2]), qrot(fq, V3(0.0f, 0.0f, 1.0f * 0.04f)));
+    }
+    float nrm[4];
+    for (int i = 0; i < 4; ++i) { v3 dd = vsub(tp, tip[i]); nrm[i] = sqrtf(vdot(dd, dd)); }
+    float fdist = nrm[0] + nrm[1] + nrm[2] + nrm[3]; /* GS:1164-1165 (ff, mf, rf, th) */
+    finger_dist_out[e] = fdist;
+    /* hand in robot-base frame (GS:1172-1173) */
+    q4 bq = {S->base_quat[0], S->base_quat[1], S->base_quat[2], S->base_quat[3]};
+    q4 bqi = qconj(bq); v3 bpi = vneg(qrot(bqi, V3(S->base_pos[0], S->base_pos[1], S->base_pos[2])));
+    q4 hq = {hb[3], hb[4], hb[5], hb[6]}; v3 hp = V3(hb[0], hb[1], hb[2]);
+    q4 hvq = qmul(bqi, hq); v3 hvp = vadd(qrot(bqi, hp), bpi);
+    /* target in wrist-camera frame (GS:1176-1182) */
+    q4 cq0 = {S->cam_off_quat[0], S->cam_off_quat[1], S->cam_off_quat[2], S->cam_off_quat[3]};
+    q4 cq = qmul(hq, cq0); v3 cp = vadd(qrot(hq, V3(S->cam_off_pos[0], S->cam_off_pos[1], S->cam_off_pos[2])), hp);
+    q4 cqi = qconj(cq); v3 cpi = vneg(qrot(cqi, cp));
+    q4 cvq = qmul(cqi, tq); v3 cvp = vadd(qrot(cqi, tp), cpi);
+    float qin[4] = {cvq.x, cvq.y, cvq.z, cvq.w};
+    float tv = sdxo_tvalue_one(tv_wts, qin);
+    tvalue[e] = tv;
+    const float* ti = target_init + 7 * e;
+    /* ---- obs frame (GS:1299-1332) */
+    float* o = obs + (size_t)e * 3 * OBS_FRAME;
+    for (int k = 2 * OBS_FRAME - 1; k >= 0; --k) o[OBS_FRAME + k] = o[k]; /* history shift GS:1330-1332 */
+    for (int i = 0; i < 16; ++i) o[i] = unscalef(d[7 + i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+    o[16] = hvp.x; o[17] = hvp.y; o[18] = hvp.z; o[19] = hvq.x; o[20] = hvq.y; o[21] = hvq.z; o[22] = hvq.w;
+    o[23] = cvp.x; o[24] = cvp.y; o[25] = cvp.z; o[26] = cvq.x; o[27] = cvq.y; o[28] = cvq.z; o[29] = cvq.w;
+    for (int i = 0; i < 16; ++i) o[30 + i] = S->vel_obs_scale * d[24 + 7 + i];
+    for (int k = 0; k < 13; ++k) { o[46 + k] = ff[k]; o[59 + k] = rf[k]; o[72 + k] = mf[k]; o[85 + k] = th[k]; o[98 + k] = tg[k]; }
+    for (int k = 0; k < 7; ++k) o[111 + k] = hb[k];
+    for (int k = 0; k < 7; ++k) o[118 + k] = ti[k];
+    o[125] = tp.x - ti[0]; o[126] = tp.y - ti[1]; o[127] = tp.z - ti[2];
+    o[128] = hp.x - tp.x; o[129] = hp.y - tp.y; o[130] = hp.z - tp.z;
+    o[131] = 0.0f;
+    /* ---- privileged state frame (GS:1220-1280) */
+    float* s = states + (size_t)e * 3 * STATE_FRAME;
+    for (int k = 2 * STATE_FRAME - 1; k >= 0; --k) s[STATE_FRAME + k] = s[k];
+    for (int j = 0; j < 23; ++j) { s[j] = unscalef(d[j], S->dof_lo[j], S->dof_hi[j]); s[23 + j] = S->vel_obs_scale * d[24 + j]; }
+    s[46] = tip[0].x; s[47] = tip[0].y; s[48] = tip[0].z; /* ff */
+    s[49] = tip[2].x; s[50] = tip[2].y; s[51] = tip[2].z; /* rf */
+    s[52] = tip[1].x; s[53] = tip[1].y; s[54] = tip[1].z; /* mf */
+    s[55] = tip[3].x; s[56] = tip[3].y; s[57] = tip[3].z; /* th */
+    for (int k = 0; k < 23; ++k) s[58 + k] = actions[23 * e + k];
+    for (int k = 0; k < 7; ++k) { s[81 + k] = hb[k]; s[88 + k] = tg[k]; }
+    for (int k = 0; k < 6; ++k) s[95 + k] = hb[7 + k];
+    for (int k = 0; k < 4; ++k) { s[101 + k] = ff[3 + k]; s[111 + k] = mf[3 + k]; s[121 + k] = rf[3 + k]; s[131 + k] = th[3 + k]; }
+    for (int k = 0; k < 6; ++k) { s[105 + k] = ff[7 + k]; s[115 + k] = mf[7 + k]; s[125 + k] = rf[7 + k]; s[135 + k] = th[7 + k]; }
+    s[141] = 0.0f;
+    for (int k = 0; k < 6; ++k) s[142 + k] = tg[7 + k];
+    s[148] = ti[0]; s[149] = ti[1]; s[150] = ti[2];
+    s[151] = tp.x - ti[0]; s[152] = tp.y - ti[1]; s[153] = tp.z - ti[2];
+    s[154] = hp.x - tp.x; s[155] = hp.y - tp.y; s[156] = hp.z - tp.z;
+    q4 rel = qmul(hq, qconj(tq));
+    s[157] = rel.x; s[158] = rel.y; s[159] = rel.z; s[160] = rel.w;
+    { v3 a = vsub(tp, tip[0]), b = vsub(tp, tip[2]), c = vsub(tp, tip[1]), dd = vsub(tp, tip[3]);
+      s[161] = a.x; s[162] = a.y; s[163] = a.z; s[164] = b.x; s[165] = b.y; s[166] = b.z;
+      s[167] = c.x; s[168] = c.y; s[169] = c.z; s[170] = dd.x; s[171] = dd.y; s[172] = dd.z; }
+    s[173] = fdist;
+    s[174] = cvp.x; s[175] = cvp.y; s[176] = cvp.z; s[177] = cvq.x; s[178] = cvq.y; s[179] = cvq.z; s[180] = cvq.w;
+    s[181] = cvp.x; s[182] = cvp.y; s[183] = cvp.z; s[184] = cvq.x; s[185] = cvq.y; s[186] = cvq.z; s[187] = cvq.w;
+    /* ---- reward / reset (GS:1719-1755) */
+    float dist = nrm[0] + nrm[1] + nrm[2] + 3.0f * nrm[3];
+    int64_t rs = reset[e];
+    if (dist <= -1.0f) rs = 1;
+    if ((float)progress[e] >= (float)S->max_episode_length - 1.0f) rs = 1;
+    float cl = dist - 0.5f; if (cl < 0.0f) cl = 0.0f;
+    float dist_rew = sdx_exp(-2.0f * cl) * 0.1f;
+    float up = clampf(tp.z - ti[2], 0.0f, 0.2f) * 100.0f;
+    if (!(dist < 0.5f)) up = 0.0f;
+    if (up > 20.0f) up = 20.0f;
+    rew[e] = dist_rew + up;
+    if (progress[e] >= 75 && dist >= 0.6f) rs = 1;
+    reset[e] = rs;
+    num_resets += rs; finished = finished + successes[e] * (float)rs;
+  }
+  if (num_resets > 0) consec[0] = S->av_factor * finished / (float)num_resets + (1.0f - S->av_factor) * consec[0]; /* GS:1771-1774 */
+}
+
+/* rl_games discount_values (call sites RGC:1473-1478): [H][N] arrays */
+void sdxo_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
+              const float* last_dones, float* adv, float* returns, int H, int n, float gamma, float tau) {
+  for (int e = 0; e < n; ++e) {
+    float lastgaelam = 0.0f;
+    for (int t = H - 1; t >= 0; --t) {
+      float nnt, nv;
+      if (t == H - 1) { nnt = 1.0f - last_dones[e]; nv = last_values[e]; }
+      else { nnt = 1.0f - dones[(size_t)(t + 1) * n + e]; nv = values[(size_t)(t + 1) * n + e]; }
+      float delta = rewards[(size_t)t * n + e] + gamma * nv * nnt - values[(size_t)t * n + e];
+      lastgaelam = delta + gamma * tau * nnt * lastgaelam;
+      adv[(size_t)t * n + e] = lastgaelam;
+      returns[(size_t)t * n + e] = lastgaelam + values[(size_t)t * n + e];
+    }
+  }
+}
+
+int sdxo_scene_size(void) { return (int)sizeof(sdx_scene_t); }
+int sdxo_work_size(void) { return (int)sizeof(work_t); }
