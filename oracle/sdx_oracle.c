@@ -825,7 +825,7 @@ void sdxo_post_physics(const sdx_scene_t* S, int n, const float* tv_wts, const f
     for (int k = 0; k < 7; ++k) o[118 + k] = ti[k];
     o[125] = tp.x - ti[0]; o[126] = tp.y - ti[1]; o[127] = tp.z - ti[2];
     o[128] = hp.x - tp.x; o[129] = hp.y - tp.y; o[130] = hp.z - tp.z;
-    o[131] = 0.0f;
+    /* o[131] is never written by the reference (GS:1328 commented out): it keeps its value */
     /* ---- privileged state frame (GS:1220-1280) */
     float* s = states + (size_t)e * 3 * STATE_FRAME;
     for (int k = 2 * STATE_FRAME - 1; k >= 0; --k) s[STATE_FRAME + k] = s[k];
@@ -839,7 +839,7 @@ void sdxo_post_physics(const sdx_scene_t* S, int n, const float* tv_wts, const f
     for (int k = 0; k < 6; ++k) s[95 + k] = hb[7 + k];
     for (int k = 0; k < 4; ++k) { s[101 + k] = ff[3 + k]; s[111 + k] = mf[3 + k]; s[121 + k] = rf[3 + k]; s[131 + k] = th[3 + k]; }
     for (int k = 0; k < 6; ++k) { s[105 + k] = ff[7 + k]; s[115 + k] = mf[7 + k]; s[125 + k] = rf[7 + k]; s[135 + k] = th[7 + k]; }
-    s[141] = 0.0f;
+    /* s[141] likewise untouched (GS:1253-1255) */
     for (int k = 0; k < 6; ++k) s[142 + k] = tg[7 + k];
     s[148] = ti[0]; s[149] = ti[1]; s[150] = ti[2];
     s[151] = tp.x - ti[0]; s[152] = tp.y - ti[1]; s[153] = tp.z - ti[2];

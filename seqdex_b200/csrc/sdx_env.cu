@@ -1,0 +1,321 @@
+// sdx_env.cu -- C-ABI (include/seqdex_b200.h) over the contact-step and task kernels.
+// One sdx_env_t = one Isaac Gym "sim" with N envs on one GPU (BT:122-126).  No CPU fallback: every
+// entry point either launches CUDA work or fails with a message.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "sdx_sim.cuh"
+#include "sdx_task.cuh"
+
+static thread_local std::string g_err;
+extern "C" const char* sdx_last_error(void) { return g_err.c_str(); }
+static int fail(const char* what, cudaError_t e, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s:%d %s: %s", file, line, what, cudaGetErrorString(e));
+  g_err = buf;
+  return -1;
+}
+#define CK(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return fail(#x, _e, __FILE__, __LINE__); } while (0)
+#define CKL() do { cudaError_t _e = cudaGetLastError(); if (_e != cudaSuccess) return fail("kernel launch", _e, __FILE__, __LINE__); } while (0)
+
+struct sdx_env {
+  int n = 0, device = 0;
+  uint64_t seed = 0;
+  cudaStream_t stream = 0;
+  sdx_scene_t host_scene;
+  sdx_scene_t* scene = nullptr;
+  void* buf[SDX_T_COUNT] = {nullptr};
+  float *qcam = nullptr, *finger_dist = nullptr, *static_rows = nullptr, *bank = nullptr, *tvw = nullptr;
+  float *gb_hand = nullptr, *gb_obj = nullptr; int* gb_index = nullptr;
+  int* red_count = nullptr; float* red_sum = nullptr;
+  float *stage_obs = nullptr, *stage_states = nullptr, *stage_actions = nullptr;
+  int per_type = 0;
+  long long total_steps = 0, launches = 0;
+  bool dump_contacts = false;
+};
+
+static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim, int* dtype) {
+  int64_t n = E->n;
+  int64_t s[4] = {1, 1, 1, 1}; int nd = 1, dt = 0;
+  switch (kind) {
+    case SDX_T_BRICK: s[0] = n; s[1] = 13; s[2] = NB; nd = 3; break;
+    case SDX_T_DOF: s[0] = n; s[1] = 3; s[2] = 24; nd = 3; break;
+    case SDX_T_LINK: s[0] = n; s[1] = SDX_NL; s[2] = 13; nd = 3; break;
+    case SDX_T_JAC7: s[0] = n; s[1] = 6; s[2] = 7; nd = 3; break;
+    case SDX_T_NETF: s[0] = n; s[1] = SDX_NL; s[2] = 3; nd = 3; break;
+    case SDX_T_ACTIONS: s[0] = n; s[1] = 23; nd = 2; break;
+    case SDX_T_OBS: s[0] = n; s[1] = 3 * SDX_OBS_FRAME; nd = 2; break;
+    case SDX_T_STATES: s[0] = n; s[1] = 3 * SDX_STATE_FRAME; nd = 2; break;
+    case SDX_T_REW: case SDX_T_TVALUE: case SDX_T_SUCCESSES: s[0] = n; break;
+    case SDX_T_RESET: case SDX_T_PROGRESS: s[0] = n; dt = 1; break;
+    case SDX_T_TARGET_INIT: s[0] = n; s[1] = 7; nd = 2; break;
+    case SDX_T_CONSEC: s[0] = 1; break;
+    case SDX_T_NCONTACT: s[0] = n; s[1] = 2; nd = 2; dt = 2; break;
+    case SDX_T_ROOT: s[0] = n * SDX_ACTORS_PER_ENV; s[1] = 13; nd = 2; break;
+    case SDX_T_RB: s[0] = n * SDX_RB_PER_ENV; s[1] = 13; nd = 2; break;
+    case SDX_T_DOF_STATE: s[0] = n * SDX_ND; s[1] = 2; nd = 2; break;
+    case SDX_T_JACOBIAN: s[0] = n; s[1] = SDX_ND; s[2] = 6; s[3] = SDX_ND; nd = 4; break;
+    case SDX_T_EPISODE: s[0] = n; dt = 2; break;
+    case SDX_T_CONTACTS: s[0] = n; s[1] = SDX_MAX_CONTACTS; s[2] = 8; nd = 3; break;
+    default: return 0;
+  }
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = s[i];
+  if (ndim) *ndim = nd;
+  if (dtype) *dtype = dt;
+  return (size_t)(s[0] * s[1] * s[2] * s[3]);
+}
+static size_t dtype_size(int dt) { return dt == 1 ? 8 : 4; }
+
+extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, uint64_t seed, sdx_env_t** out) {
+  if (!scene || !out || num_envs <= 0) { g_err = "sdx_create: bad arguments"; return -1; }
+  if (scene->n_static > KSTAT || scene->n_rshapes > SDX_MAX_RSHAPES || scene->n_bricks > NB) { g_err = "sdx_create: scene exceeds kernel tables"; return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "sdx_create: no CUDA device (this library has no CPU path)"; return -1; }
+  CK(cudaSetDevice(device));
+  sdx_env* E = new sdx_env();
+  E->n = num_envs; E->device = device; E->seed = seed; E->host_scene = *scene;
+  CK(cudaMalloc(&E->scene, sizeof(sdx_scene_t)));
+  CK(cudaMemcpy(E->scene, scene, sizeof(sdx_scene_t), cudaMemcpyHostToDevice));
+  for (int k = 0; k < SDX_T_COUNT; ++k) {
+    int dt = 0;
+    size_t ne = kind_elems(E, k, nullptr, nullptr, &dt);
+    if (k == SDX_T_CONTACTS) continue;   // debug dump: allocated on demand
+    CK(cudaMalloc(&E->buf[k], ne * dtype_size(dt)));
+    CK(cudaMemset(E->buf[k], 0, ne * dtype_size(dt)));
+  }
+  size_t n = num_envs;
+  CK(cudaMalloc(&E->qcam, n * 4 * 4)); CK(cudaMemset(E->qcam, 0, n * 16));
+  CK(cudaMalloc(&E->finger_dist, n * 4)); CK(cudaMemset(E->finger_dist, 0, n * 4));
+  CK(cudaMalloc(&E->static_rows, SDX_ACTORS_PER_ENV * 13 * 4)); CK(cudaMemset(E->static_rows, 0, SDX_ACTORS_PER_ENV * 13 * 4));
+  CK(cudaMalloc(&E->tvw, SDX_TVALUE_PARAMS * 4)); CK(cudaMemset(E->tvw, 0, SDX_TVALUE_PARAMS * 4));
+  CK(cudaMalloc(&E->gb_hand, (size_t)8 * SDX_GRASP_BANK * 46 * 4)); CK(cudaMemset(E->gb_hand, 0, (size_t)8 * SDX_GRASP_BANK * 46 * 4));
+  CK(cudaMalloc(&E->gb_obj, (size_t)8 * SDX_GRASP_BANK * 13 * 4)); CK(cudaMemset(E->gb_obj, 0, (size_t)8 * SDX_GRASP_BANK * 13 * 4));
+  CK(cudaMalloc(&E->gb_index, 8 * 4)); CK(cudaMemset(E->gb_index, 0, 32));
+  CK(cudaMalloc(&E->red_count, 4)); CK(cudaMemset(E->red_count, 0, 4));
+  CK(cudaMalloc(&E->red_sum, 4)); CK(cudaMemset(E->red_sum, 0, 4));
+  CK(cudaMalloc(&E->stage_obs, n * 3 * SDX_OBS_FRAME * 4));
+  CK(cudaMalloc(&E->stage_states, n * 3 * SDX_STATE_FRAME * 4));
+  CK(cudaMalloc(&E->stage_actions, n * 23 * 4));
+  CK(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
+  *out = E;
+  return sdx_reset_all(E);
+}
+
+extern "C" void sdx_destroy(sdx_env_t* E) {
+  if (!E) return;
+  cudaSetDevice(E->device);
+  for (int k = 0; k < SDX_T_COUNT; ++k) cudaFree(E->buf[k]);
+  cudaFree(E->scene); cudaFree(E->qcam); cudaFree(E->finger_dist); cudaFree(E->static_rows); cudaFree(E->bank); cudaFree(E->tvw);
+  cudaFree(E->gb_hand); cudaFree(E->gb_obj); cudaFree(E->gb_index); cudaFree(E->red_count); cudaFree(E->red_sum);
+  cudaFree(E->stage_obs); cudaFree(E->stage_states); cudaFree(E->stage_actions);
+  delete E;
+}
+extern "C" int sdx_set_stream(sdx_env_t* E, void* stream) { E->stream = (cudaStream_t)stream; return 0; }
+extern "C" int sdx_num_envs(const sdx_env_t* E) { return E->n; }
+extern "C" int64_t sdx_launch_count(const sdx_env_t* E) { return E->launches; }
+extern "C" int sdx_scene_size(void) { return (int)sizeof(sdx_scene_t); }
+extern "C" int sdx_sim_smem_bytes(void) { return (int)sizeof(SimSmem); }
+
+extern "C" int sdx_tensor(sdx_env_t* E, int kind, void** dev_ptr, int64_t shape[4], int* ndim, int* dtype) {
+  if (kind < 0 || kind >= SDX_T_COUNT) { g_err = "sdx_tensor: bad kind"; return -1; }
+  int dt = 0;
+  size_t ne = kind_elems(E, kind, shape, ndim, &dt);
+  if (dtype) *dtype = dt;
+  if (kind == SDX_T_CONTACTS && !E->buf[kind]) {
+    CK(cudaSetDevice(E->device));
+    CK(cudaMalloc(&E->buf[kind], ne * 4));
+    CK(cudaMemset(E->buf[kind], 0, ne * 4));
+    E->dump_contacts = true;
+  }
+  *dev_ptr = E->buf[kind];
+  return 0;
+}
+
+#define F(k) ((float*)E->buf[k])
+#define I64(k) ((int64_t*)E->buf[k])
+#define I32(k) ((int*)E->buf[k])
+
+extern "C" int sdx_set_static_rows(sdx_env_t* E, const float* rows_host /*[142][13]*/) {
+  CK(cudaSetDevice(E->device));
+  CK(cudaMemcpy(E->static_rows, rows_host, SDX_ACTORS_PER_ENV * 13 * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int sdx_refresh(sdx_env_t* E, int kind) {
+  CK(cudaSetDevice(E->device));
+  const int n = E->n, T = 256;
+  switch (kind) {
+    case SDX_T_ROOT: k_refresh_root<<<(n * SDX_ACTORS_PER_ENV + T - 1) / T, T, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), E->static_rows, F(SDX_T_ROOT)); break;
+    case SDX_T_RB: k_refresh_rb<<<(n * SDX_RB_PER_ENV + T - 1) / T, T, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), F(SDX_T_LINK), E->static_rows, F(SDX_T_RB)); break;
+    case SDX_T_DOF_STATE: k_refresh_dof_state<<<(n * SDX_ND + T - 1) / T, T, 0, E->stream>>>(n, F(SDX_T_DOF), F(SDX_T_DOF_STATE)); break;
+    case SDX_T_JACOBIAN: k_refresh_jacobian<<<(n * SDX_ND * SDX_ND + T - 1) / T, T, 0, E->stream>>>(E->scene, n, F(SDX_T_LINK), F(SDX_T_JACOBIAN)); break;
+    case SDX_T_LINK: case SDX_T_JAC7: k_refresh_links<<<(n + 63) / 64, 64, 0, E->stream>>>(E->scene, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7), n); break;
+    case SDX_T_NETF: return 0;   // net contact forces are written by the step itself
+    default: g_err = "sdx_refresh: kind is not a refreshable tensor"; return -1;
+  }
+  E->launches++;
+  CKL();
+  return 0;
+}
+
+extern "C" int sdx_set_actor_root_state_indexed(sdx_env_t* E, const float* root_dev, const int32_t* idx_dev, int n) {
+  CK(cudaSetDevice(E->device));
+  if (n <= 0) return 0;
+  k_set_root_indexed<<<(n + 255) / 256, 256, 0, E->stream>>>(E->scene, E->n, F(SDX_T_BRICK), root_dev, idx_dev, n);
+  E->launches++; CKL(); return 0;
+}
+extern "C" int sdx_set_dof_state_indexed(sdx_env_t* E, const float* src, const int32_t* idx_dev, int n) {
+  CK(cudaSetDevice(E->device));
+  if (n <= 0) return 0;
+  k_set_dof_indexed<<<(n * SDX_ND + 255) / 256, 256, 0, E->stream>>>(E->n, F(SDX_T_DOF), src, idx_dev, n, 0);
+  E->launches++; CKL(); return 0;
+}
+extern "C" int sdx_set_dof_target_indexed(sdx_env_t* E, const float* src, const int32_t* idx_dev, int n) {
+  CK(cudaSetDevice(E->device));
+  if (n <= 0) return 0;
+  k_set_dof_indexed<<<(n * SDX_ND + 255) / 256, 256, 0, E->stream>>>(E->n, F(SDX_T_DOF), src, idx_dev, n, 1);
+  E->launches++; CKL(); return 0;
+}
+extern "C" int sdx_set_dof_targets(sdx_env_t* E, const float* src) {
+  CK(cudaSetDevice(E->device));
+  k_set_dof_targets<<<(E->n * SDX_ND + 255) / 256, 256, 0, E->stream>>>(E->n, F(SDX_T_DOF), src);
+  E->launches++; CKL(); return 0;
+}
+
+extern "C" int sdx_set_heap_bank(sdx_env_t* E, const float* bank_host, int per_type) {
+  CK(cudaSetDevice(E->device));
+  if (per_type <= 0) { g_err = "sdx_set_heap_bank: per_type must be positive"; return -1; }
+  CK(cudaStreamSynchronize(E->stream));
+  cudaFree(E->bank);
+  size_t bytes = (size_t)8 * per_type * NB * 13 * 4;
+  CK(cudaMalloc(&E->bank, bytes));
+  CK(cudaMemcpy(E->bank, bank_host, bytes, cudaMemcpyHostToDevice));
+  E->per_type = per_type;
+  return 0;
+}
+// same, from a device buffer (bank generated on the GPU by settling heaps)
+extern "C" int sdx_set_heap_bank_dev(sdx_env_t* E, const float* bank_dev, int per_type) {
+  CK(cudaSetDevice(E->device));
+  CK(cudaStreamSynchronize(E->stream));
+  cudaFree(E->bank);
+  size_t bytes = (size_t)8 * per_type * NB * 13 * 4;
+  CK(cudaMalloc(&E->bank, bytes));
+  CK(cudaMemcpy(E->bank, bank_dev, bytes, cudaMemcpyDeviceToDevice));
+  E->per_type = per_type;
+  return 0;
+}
+
+extern "C" int sdx_set_tvalue_weights(sdx_env_t* E, const float* w) {
+  CK(cudaSetDevice(E->device));
+  std::vector<float> d(SDX_TVALUE_PARAMS);
+  const float* W1 = w; const float* b1 = W1 + 1024; const float* W2 = b1 + 256; const float* b2 = W2 + 128 * 256;
+  const float* W3 = b2 + 128; const float* b3 = W3 + 64 * 128; const float* W4 = b3 + 64; const float* b4 = W4 + 128;
+  float* o = d.data();
+  memcpy(o, W1, 1024 * 4); o += 1024; memcpy(o, b1, 256 * 4); o += 256;
+  for (int k = 0; k < 256; ++k) for (int q = 0; q < 128; ++q) o[k * 128 + q] = W2[q * 256 + k];
+  o += 256 * 128; memcpy(o, b2, 128 * 4); o += 128;
+  for (int k = 0; k < 128; ++k) for (int q = 0; q < 64; ++q) o[k * 64 + q] = W3[q * 128 + k];
+  o += 128 * 64; memcpy(o, b3, 64 * 4); o += 64;
+  memcpy(o, W4, 128 * 4); o += 128; memcpy(o, b4, 2 * 4);
+  CK(cudaMemcpy(E->tvw, d.data(), SDX_TVALUE_PARAMS * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int sdx_reset_all(sdx_env_t* E) {
+  CK(cudaSetDevice(E->device));
+  k_reset_all<<<E->n, 128, 0, E->stream>>>(E->scene, E->n, F(SDX_T_BRICK), F(SDX_T_DOF), I64(SDX_T_PROGRESS), I64(SDX_T_RESET));
+  CKL();
+  k_refresh_links<<<(E->n + 63) / 64, 64, 0, E->stream>>>(E->scene, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7), E->n);
+  CKL();
+  E->launches += 2;
+  return 0;
+}
+
+extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
+  CK(cudaSetDevice(E->device));
+  const int n = E->n;
+  if (!E->bank) { g_err = "sdx_pre_physics: no heap bank set (reset_idx samples it, GS:1507-1511)"; return -1; }
+  if (E->total_steps > 0) {
+    k_bank_terminal<<<8, 256, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), I64(SDX_T_RESET), E->finger_dist,
+                                              F(SDX_T_TVALUE), E->gb_hand, E->gb_obj, E->gb_index);
+    E->launches++;
+  }
+  k_reset<<<n, 128, 0, E->stream>>>(E->scene, n, E->seed, E->bank, E->per_type, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_TARGET_INIT),
+                                    I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), I32(SDX_T_EPISODE));
+  k_pre_physics<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, actions_dev, F(SDX_T_ACTIONS), F(SDX_T_DOF), F(SDX_T_LINK),
+                                                        F(SDX_T_JAC7), I64(SDX_T_PROGRESS), F(SDX_T_TARGET_INIT));
+  E->launches += 2;
+  CKL();
+  return 0;
+}
+
+extern "C" int sdx_simulate(sdx_env_t* E) {
+  CK(cudaSetDevice(E->device));
+  k_simulate<<<E->n, SIM_THREADS, sizeof(SimSmem), E->stream>>>(E->scene, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+                                                              F(SDX_T_NETF), I32(SDX_T_NCONTACT),
+                                                              E->dump_contacts ? F(SDX_T_CONTACTS) : nullptr, E->n);
+  E->launches++;
+  CKL();
+  return 0;
+}
+extern "C" int sdx_simulate_n(sdx_env_t* E, int steps) {
+  for (int i = 0; i < steps; ++i) if (sdx_simulate(E)) return -1;
+  return 0;
+}
+
+extern "C" int sdx_post_physics(sdx_env_t* E) {
+  CK(cudaSetDevice(E->device));
+  const int n = E->n;
+  k_post_physics<<<(n + POST_WARPS - 1) / POST_WARPS, 32 * POST_WARPS, 0, E->stream>>>(
+      E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_ACTIONS), F(SDX_T_TARGET_INIT), I64(SDX_T_PROGRESS),
+      I64(SDX_T_RESET), F(SDX_T_OBS), F(SDX_T_STATES), F(SDX_T_REW), E->qcam, E->finger_dist, F(SDX_T_SUCCESSES), E->red_count, E->red_sum);
+  k_tvalue<<<(n + TV_ENVS * TV_WARPS - 1) / (TV_ENVS * TV_WARPS), 32 * TV_WARPS, 0, E->stream>>>(E->tvw, n, E->qcam, F(SDX_T_TVALUE));
+  k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
+  E->launches += 3;
+  E->total_steps++;
+  CKL();
+  return 0;
+}
+
+extern "C" int sdx_step(sdx_env_t* E, const float* actions_dev) {
+  if (sdx_pre_physics(E, actions_dev)) return -1;
+  if (sdx_simulate(E)) return -1;
+  return sdx_post_physics(E);
+}
+
+extern "C" int sdx_step_host(sdx_env_t* E, const float* actions_host, float* obs_host, float* states_host, float* rew_host,
+                             int64_t* reset_host) {
+  CK(cudaSetDevice(E->device));
+  const size_t n = E->n;
+  CK(cudaMemcpyAsync(E->stage_actions, actions_host, n * 23 * 4, cudaMemcpyHostToDevice, E->stream));
+  if (sdx_step(E, E->stage_actions)) return -1;
+  const size_t no = n * 3 * SDX_OBS_FRAME, ns = n * 3 * SDX_STATE_FRAME;
+  k_clamp_copy<<<(unsigned)((no + 255) / 256), 256, 0, E->stream>>>(F(SDX_T_OBS), E->stage_obs, no, 5.0f);
+  k_clamp_copy<<<(unsigned)((ns + 255) / 256), 256, 0, E->stream>>>(F(SDX_T_STATES), E->stage_states, ns, 5.0f);
+  E->launches += 2;
+  CKL();
+  if (obs_host) CK(cudaMemcpyAsync(obs_host, E->stage_obs, no * 4, cudaMemcpyDeviceToHost, E->stream));
+  if (states_host) CK(cudaMemcpyAsync(states_host, E->stage_states, ns * 4, cudaMemcpyDeviceToHost, E->stream));
+  if (rew_host) CK(cudaMemcpyAsync(rew_host, F(SDX_T_REW), n * 4, cudaMemcpyDeviceToHost, E->stream));
+  if (reset_host) CK(cudaMemcpyAsync(reset_host, I64(SDX_T_RESET), n * 8, cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));
+  return 0;
+}
+
+extern "C" int sdx_gae(const float* rewards, const float* values, const float* dones, const float* last_values,
+                       const float* last_dones, float* adv, float* returns, int horizon, int n, float gamma, float tau, void* stream) {
+  k_gae<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards, values, dones, last_values, last_dones, adv, returns, horizon, n, gamma, tau);
+  CKL();
+  return 0;
+}
+
+/* grasp terminal-state banks: device pointers for export */
+extern "C" int sdx_grasp_bank(sdx_env_t* E, void** hand_dev, void** obj_dev, void** index_dev) {
+  *hand_dev = E->gb_hand; *obj_dev = E->gb_obj; *index_dev = E->gb_index;
+  return 0;
+}
+extern "C" int sdx_aux(sdx_env_t* E, void** qcam_dev, void** finger_dist_dev) { *qcam_dev = E->qcam; *finger_dist_dev = E->finger_dist; return 0; }

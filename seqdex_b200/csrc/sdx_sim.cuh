@@ -1,0 +1,571 @@
+// sdx_sim.cuh -- the contact step (replaces gym.simulate(), BT:140) as ONE kernel launch per control
+// step: one CTA per environment, the whole per-env working set resident in shared memory for both
+// sub-steps and all 2 x 16 solver iterations; HBM is touched only to load / store the env's state tile.
+//
+//   load   : free-brick tile [13][72] f32 (3744 B, contiguous per env) by TMA bulk copy
+//            (cp.async.bulk -> mbarrier), DoF block [3][24] by plain loads
+//   per sub-step (h = dt/substeps):
+//     forward kinematics (quaternion chain), shape poses, free velocities (gravity, implicit PD)
+//     broad phase   : one thread per owner shape, world-AABB test against every target box
+//     narrow phase  : ordered pairs -> SAT reference face -> sample points -> contacts (two-pass,
+//                     deterministic compaction: owner, candidate, point order)
+//     CSR incidence : per body, contacts in index order (fixed summation order => reproducible)
+//     solver        : mass-splitting Jacobi on total impulses; phase A = 1 thread / contact,
+//                     phase B = 1 thread / body gathers its incident impulses; the articulation sees
+//                     contacts through per-link wrenches -> joint-space impulses (diag. inertia)
+//     integrate
+//   store  : brick tile by TMA bulk store, DoF block, and ONLY the rows the task reads
+//            (24 link rows, 6x7 Jacobian of link7, net contact force per link)
+#pragma once
+#include "sdx_math.cuh"
+#include "../../include/seqdex_b200.h"
+
+#define NB SDX_MAX_BRICKS
+#define NBODY (NB + SDX_NL)
+#define KSTAT 24                       /* static boxes the kernel keeps in shared memory */
+#define NOWN (NB + SDX_MAX_RSHAPES)    /* owner shapes: bricks + robot boxes */
+#define NT (NOWN + KSTAT)              /* target boxes */
+#define KC 32
+#define MAXC SDX_MAX_CONTACTS
+#define STATIC_BODY 255
+#define SIM_THREADS 128
+#define ROBOT_TID0 96                  /* warp 3 owns the articulation: lane j = DoF j, lane L = link L */
+#define PPMAX 24                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
+
+struct SimSmem {
+  float tile[13 * NB];                 // TMA landing / staging zone for the brick tile
+  unsigned long long mbar;
+  float sc[NT][3], sR[NT][9], sh[NT][3], sa[NT][3], spd[NT], srad[NOWN];
+  unsigned char sbody[NT];
+  float bx[NBODY][3], bv[NBODY][3], bw[NBODY][3];
+  float lq[SDX_NL][4], ja[SDX_ND][3], jo[SDX_ND][3];
+  float q[SDX_ND + 1], qd[SDX_ND + 1], tgt[SDX_ND + 1], qdfree[SDX_ND + 1], ieff[SDX_ND + 1];
+  float linkF[SDX_NL][3], linkM[SDX_NL][3];
+  int nb[NBODY], nj[SDX_ND + 1];
+  int inc_off[NBODY + 1];
+  unsigned short inc[2 * MAXC];
+  unsigned char cand[NOWN][KC];
+  int ncand[NOWN], poff[NOWN + 1];
+  int scan[SIM_THREADS];
+  int ncon, ndropped;
+  uint32_t cword[MAXC];
+  float cw[3][MAXC], cbias[MAXC], cden[3][MAXC], clam[3][MAXC];
+};
+
+__device__ __forceinline__ v3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(float* p, v3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+
+// forward kinematics of the collapsed Panda+Allegro tree, serial over the chain (one thread)
+__device__ void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M) {
+  st3(M.bx[NB], V3(S->base_pos[0], S->base_pos[1], S->base_pos[2]));
+  M.lq[0][0] = S->base_quat[0]; M.lq[0][1] = S->base_quat[1]; M.lq[0][2] = S->base_quat[2]; M.lq[0][3] = S->base_quat[3];
+  for (int j = 0; j < SDX_ND; ++j) {
+    int L = j + 1, P = S->body_parent[L];
+    q4 qP = Q4(M.lq[P][0], M.lq[P][1], M.lq[P][2], M.lq[P][3]);
+    q4 qf = Q4(S->joint_quat[4 * j], S->joint_quat[4 * j + 1], S->joint_quat[4 * j + 2], S->joint_quat[4 * j + 3]);
+    v3 ax = V3(S->joint_axis[3 * j], S->joint_axis[3 * j + 1], S->joint_axis[3 * j + 2]);
+    q4 qj = qmul(qP, qf);
+    v3 x = vadd(ld3(M.bx[NB + P]), qrot(qP, V3(S->joint_xyz[3 * j], S->joint_xyz[3 * j + 1], S->joint_xyz[3 * j + 2])));
+    float s, c;
+    sdx_sincos(0.5f * M.q[j], &s, &c);
+    q4 qr = Q4(ax.x * s, ax.y * s, ax.z * s, c);
+    q4 ql = qmul(qj, qr);
+    M.lq[L][0] = ql.x; M.lq[L][1] = ql.y; M.lq[L][2] = ql.z; M.lq[L][3] = ql.w;
+    st3(M.bx[NB + L], x);
+    st3(M.ja[j], qrot(qj, ax));
+    st3(M.jo[j], x);
+  }
+}
+
+__device__ __forceinline__ void link_twist(const sdx_scene_t* __restrict__ S, SimSmem& M, int L) {
+  v3 w = V3(0.0f, 0.0f, 0.0f), v = V3(0.0f, 0.0f, 0.0f);
+  unsigned m = S->link_anc_mask[L];
+  v3 xl = ld3(M.bx[NB + L]);
+  for (int j = 0; j < SDX_ND; ++j)
+    if (m & (1u << j)) {
+      v3 a = ld3(M.ja[j]);
+      w = vadd(w, vscale(a, M.qd[j]));
+      v = vadd(v, vscale(vcross(a, vsub(xl, ld3(M.jo[j]))), M.qd[j]));
+    }
+  st3(M.bv[NB + L], v); st3(M.bw[NB + L], w);
+}
+
+__device__ __forceinline__ v3 brick_Iinv_mul(const float* R, v3 invI, v3 u) {
+  v3 l = mtmul(R, u);
+  l.x = l.x * invI.x; l.y = l.y * invI.y; l.z = l.z * invI.z;
+  return mmul(R, l);
+}
+
+__device__ __forceinline__ void contact_axes(const SimSmem& M, uint32_t word, v3* n, v3* t1, v3* t2) {
+  int sh = (word >> 16) & 255, k = (word >> 24) & 3;
+  float sg = ((word >> 26) & 1) ? -1.0f : 1.0f;
+  *n = vscale(mcol(M.sR[sh], k), sg);
+  *t1 = mcol(M.sR[sh], (k + 1) % 3);
+  *t2 = mcol(M.sR[sh], (k + 2) % 3);
+}
+
+__device__ float body_k(const sdx_scene_t* __restrict__ S, const SimSmem& M, int body, v3 wpt, v3 d) {
+  if (body == STATIC_BODY) return 0.0f;
+  if (body < NB) {
+    v3 rxd = vcross(vsub(wpt, ld3(M.bx[body])), d);
+    v3 invI = V3(S->br_invI[3 * body], S->br_invI[3 * body + 1], S->br_invI[3 * body + 2]);
+    float k = S->br_invm[body] + vdot(rxd, brick_Iinv_mul(M.sR[body], invI, rxd));
+    return (float)M.nb[body] * k;
+  }
+  int L = body - NB;
+  unsigned m = S->link_anc_mask[L];
+  float k = 0.0f;
+  for (int j = 0; j < SDX_ND; ++j)
+    if (m & (1u << j)) {
+      float g = vdot(ld3(M.ja[j]), vcross(vsub(wpt, ld3(M.jo[j])), d));
+      k = k + (float)M.nj[j] * (g * g) / M.ieff[j];
+    }
+  return k;
+}
+
+// pair-level SAT: reference face of target t for owner a.  returns false if separated beyond m.
+struct PairGeom { v3 lc; float C[9]; int k; float sgf; uint32_t sg; float htk; v3 ha, ht; };
+__device__ __forceinline__ bool pair_geom(const SimSmem& M, int a, int t, float m, PairGeom& G) {
+  G.lc = mtmul(M.sR[t], vsub(ld3(M.sc[a]), ld3(M.sc[t])));
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c2 = 0; c2 < 3; ++c2)
+      G.C[3 * r + c2] = M.sR[t][r] * M.sR[a][c2] + M.sR[t][3 + r] * M.sR[a][3 + c2] + M.sR[t][6 + r] * M.sR[a][6 + c2];
+  G.ha = ld3(M.sh[a]); G.ht = ld3(M.sh[t]);
+  float o0 = G.ht.x + (fabsf(G.C[0]) * G.ha.x + fabsf(G.C[1]) * G.ha.y + fabsf(G.C[2]) * G.ha.z) - fabsf(G.lc.x);
+  float o1 = G.ht.y + (fabsf(G.C[3]) * G.ha.x + fabsf(G.C[4]) * G.ha.y + fabsf(G.C[5]) * G.ha.z) - fabsf(G.lc.y);
+  float o2 = G.ht.z + (fabsf(G.C[6]) * G.ha.x + fabsf(G.C[7]) * G.ha.y + fabsf(G.C[8]) * G.ha.z) - fabsf(G.lc.z);
+  int k = 0; float ov = o0;
+  if (o1 < ov) { k = 1; ov = o1; }
+  if (o2 < ov) { k = 2; ov = o2; }
+  if (ov < -m) return false;
+  float lck = k == 0 ? G.lc.x : (k == 1 ? G.lc.y : G.lc.z);
+  G.k = k;
+  G.sgf = lck >= 0.0f ? 1.0f : -1.0f;
+  G.sg = lck >= 0.0f ? 0u : 1u;
+  G.htk = k == 0 ? G.ht.x : (k == 1 ? G.ht.y : G.ht.z);
+  return true;
+}
+__device__ __forceinline__ v3 sample_point(v3 ha, int p) {
+  if (p < 8) return V3((p & 1) ? ha.x : -ha.x, (p & 2) ? ha.y : -ha.y, (p & 4) ? ha.z : -ha.z);
+  return V3(0.0f, (p & 1) ? ha.y : -ha.y, (p & 2) ? ha.z : -ha.z);
+}
+// does sample point p of the owner touch the reference face?  depth returned through *depth
+__device__ __forceinline__ bool point_hit(const PairGeom& G, int p, float m, float margin, float* depth) {
+  v3 pl = sample_point(G.ha, p);
+  v3 l = vadd(G.lc, mmul(G.C, pl));
+  int k = G.k;
+  float lk = k == 0 ? l.x : (k == 1 ? l.y : l.z);
+  float d = G.htk - G.sgf * lk;
+  if (!(d > -m)) return false;
+  bool inface = (k == 0 || fabsf(l.x) <= G.ht.x + margin) && (k == 1 || fabsf(l.y) <= G.ht.y + margin) &&
+                (k == 2 || fabsf(l.z) <= G.ht.z + margin);
+  *depth = d;
+  return inface;
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(SIM_THREADS)
+k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
+           float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
+           int* __restrict__ ncontact, float* __restrict__ condump, int n_envs) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SimSmem& M = *reinterpret_cast<SimSmem*>(smem_raw);
+  const int e = blockIdx.x, tid = threadIdx.x;
+  if (e >= n_envs) return;
+  const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;
+  const int n_owner = NB + nrs, n_target = NB + nrs + nst;
+  const int substeps = S->substeps, iters = S->iters;
+  const float h = S->dt / (float)substeps;
+  const float margin = S->contact_offset;
+  float* gbrick = brick + (size_t)e * 13 * NB;
+  float* gdof = dof + (size_t)e * 72;
+
+  // ---- TMA bulk load of the env's brick tile into shared memory
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&M.mbar);
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(M.tile);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(13 * NB * 4) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tile_s), "l"(gbrick), "r"(13 * NB * 4), "r"(bar) : "memory");
+  }
+  // robot state + static tables while the tile is in flight
+  if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) {
+    int j = tid - ROBOT_TID0;
+    M.q[j] = gdof[j]; M.qd[j] = gdof[24 + j]; M.tgt[j] = gdof[48 + j];
+  }
+  for (int s = tid; s < nst; s += SIM_THREADS) {
+    int t = NB + nrs + s;
+    st3(M.sc[t], V3(S->st_c[3 * s], S->st_c[3 * s + 1], S->st_c[3 * s + 2]));
+    st3(M.sh[t], V3(S->st_h[3 * s], S->st_h[3 * s + 1], S->st_h[3 * s + 2]));
+    st3(M.sa[t], V3(S->st_h[3 * s], S->st_h[3 * s + 1], S->st_h[3 * s + 2]));
+#pragma unroll
+    for (int i = 0; i < 9; ++i) M.sR[t][i] = (i % 4 == 0) ? 1.0f : 0.0f;
+    M.sbody[t] = STATIC_BODY;
+    M.spd[t] = 0.0f;
+  }
+  mbar_wait(&M.mbar, 0);
+
+  // brick threads keep their body in registers across the step
+  v3 bxr = V3(0, 0, 0), bvr = V3(0, 0, 0), bwr = V3(0, 0, 0), vfree = V3(0, 0, 0), wfree = V3(0, 0, 0);
+  q4 bqr = Q4(0, 0, 0, 1);
+  v3 invI = V3(0, 0, 0), halfb = V3(0, 0, 0);
+  float invm = 0.0f;
+  if (tid < NB) {
+    bxr = V3(M.tile[0 * NB + tid], M.tile[1 * NB + tid], M.tile[2 * NB + tid]);
+    bqr = Q4(M.tile[3 * NB + tid], M.tile[4 * NB + tid], M.tile[5 * NB + tid], M.tile[6 * NB + tid]);
+    bvr = V3(M.tile[7 * NB + tid], M.tile[8 * NB + tid], M.tile[9 * NB + tid]);
+    bwr = V3(M.tile[10 * NB + tid], M.tile[11 * NB + tid], M.tile[12 * NB + tid]);
+    invI = V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]);
+    invm = S->br_invm[tid];
+    halfb = V3(S->br_half[3 * tid], S->br_half[3 * tid + 1], S->br_half[3 * tid + 2]);
+    st3(M.sh[tid], halfb);
+    M.srad[tid] = sqrtf(vdot(halfb, halfb));
+    M.sbody[tid] = (unsigned char)tid;
+  }
+  if (tid < nrs) {
+    int t = NB + tid;
+    v3 hh = V3(S->rs_h[3 * tid], S->rs_h[3 * tid + 1], S->rs_h[3 * tid + 2]);
+    st3(M.sh[t], hh);
+    M.srad[t] = sqrtf(vdot(hh, hh));
+    M.sbody[t] = (unsigned char)(NB + S->rs_body[tid]);
+  }
+  __syncthreads();
+
+  for (int sub = 0; sub < substeps; ++sub) {
+    // 1. kinematics (one thread walks the chain) || brick poses + free velocities
+    if (tid == ROBOT_TID0) robot_fk(S, M);
+    if (tid < NB) {
+      qmat(bqr, M.sR[tid]);
+      st3(M.sc[tid], bxr); st3(M.bx[tid], bxr);
+      float damp = 1.0f - h * S->brick_ang_damp;
+      float ldamp = 1.0f - h * S->brick_lin_damp;
+      vfree = vscale(V3(bvr.x, bvr.y, bvr.z + h * S->gravity_z), ldamp);
+      wfree = vscale(bwr, damp);
+      if (tid >= nbr) { vfree = V3(0.0f, 0.0f, 0.0f); wfree = V3(0.0f, 0.0f, 0.0f); }
+      st3(M.bv[tid], vfree); st3(M.bw[tid], wfree);
+    }
+    __syncthreads();
+    // 2. robot shape poses || implicit PD free joint velocities
+    if (tid < nrs) {
+      int t = NB + tid, L = S->rs_body[tid];
+      q4 qL = Q4(M.lq[L][0], M.lq[L][1], M.lq[L][2], M.lq[L][3]);
+      q4 ql = Q4(S->rs_quat[4 * tid], S->rs_quat[4 * tid + 1], S->rs_quat[4 * tid + 2], S->rs_quat[4 * tid + 3]);
+      st3(M.sc[t], vadd(ld3(M.bx[NB + L]), qrot(qL, V3(S->rs_c[3 * tid], S->rs_c[3 * tid + 1], S->rs_c[3 * tid + 2]))));
+      qmat(qmul(qL, ql), M.sR[t]);
+    }
+    if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) {
+      int j = tid - ROBOT_TID0;
+      float I = S->dof_inertia[j], kp = S->dof_kp[j], kd = S->dof_kd[j];
+      float ieff = I + h * kd + (h * h) * kp;
+      float qdo = M.qd[j];
+      float qn = (I * qdo + h * kp * (M.tgt[j] - M.q[j])) / ieff;
+      float tau = I * (qn - qdo) / h;
+      if (tau > S->dof_effort[j]) qn = qdo + S->dof_effort[j] * h / I;
+      if (tau < -S->dof_effort[j]) qn = qdo - S->dof_effort[j] * h / I;
+      qn = clampf(qn, -S->dof_vmax[j], S->dof_vmax[j]);
+      M.ieff[j] = ieff; M.qdfree[j] = qn; M.qd[j] = qn;
+    }
+    __syncthreads();
+    // 3. link twists
+    if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0);
+    __syncthreads();
+    // 4. world AABBs + per-sub-step travel bound of every moving shape
+    if (tid < n_owner) {
+      int t = tid;
+      const float* R = M.sR[t];
+      v3 hh = ld3(M.sh[t]);
+      st3(M.sa[t], V3(fabsf(R[0]) * hh.x + fabsf(R[1]) * hh.y + fabsf(R[2]) * hh.z,
+                      fabsf(R[3]) * hh.x + fabsf(R[4]) * hh.y + fabsf(R[5]) * hh.z,
+                      fabsf(R[6]) * hh.x + fabsf(R[7]) * hh.y + fabsf(R[8]) * hh.z));
+      int bd = M.sbody[t];
+      v3 dc = vsub(ld3(M.sc[t]), ld3(M.bx[bd]));
+      float reach = sqrtf(vdot(dc, dc)) + M.srad[t];
+      v3 bv = ld3(M.bv[bd]), bw = ld3(M.bw[bd]);
+      M.spd[t] = h * (sqrtf(vdot(bv, bv)) + sqrtf(vdot(bw, bw)) * reach);
+    }
+    if (tid == 0) { M.ndropped = 0; }
+    __syncthreads();
+    // 5. broad phase: one thread per owner shape
+    if (tid < n_owner) {
+      int a = tid, k = 0, dropped = 0;
+      if (!(a < NB && a >= nbr)) {
+        v3 ca = ld3(M.sc[a]), aa = ld3(M.sa[a]);
+        float spa = M.spd[a];
+        for (int t = 0; t < n_target; ++t) {
+          if (t == a) continue;
+          if (t < NB && t >= nbr) continue;
+          if (a >= NB && t >= NB && t < NB + nrs) continue;   // robot-robot filtered (GS:906)
+          v3 d = vsub(ca, ld3(M.sc[t]));
+          v3 at = ld3(M.sa[t]);
+          float m = margin + spa + M.spd[t];
+          bool hit = fabsf(d.x) <= aa.x + at.x + m && fabsf(d.y) <= aa.y + at.y + m && fabsf(d.z) <= aa.z + at.z + m;
+          if (hit) { if (k < KC) M.cand[a][k++] = (unsigned char)t; else dropped++; }
+        }
+      }
+      M.ncand[a] = k;
+      if (dropped) atomicAdd(&M.ndropped, dropped);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int o = 0;
+      for (int a = 0; a < n_owner; ++a) { M.poff[a] = o; o += M.ncand[a]; }
+      M.poff[n_owner] = o;
+    }
+    __syncthreads();
+    // 6. narrow phase, pass 1: per-pair hit masks, kept in registers; contiguous pair chunks per thread
+    const int npairs = M.poff[n_owner];
+    const int PP = (npairs + SIM_THREADS - 1) / SIM_THREADS;   // <= KC*NOWN/128 = 26 > PPMAX only if every owner is full
+    const int p0 = tid * PP, p1 = min(npairs, p0 + PP);
+    unsigned short masks[PPMAX];
+    int mycount = 0, pairdrop = 0;
+    {
+      int a = 0;
+      for (int i = p0, s = 0; i < p1; ++i, ++s) {
+        if (s >= PPMAX) { pairdrop++; continue; }
+        while (M.poff[a + 1] <= i) ++a;
+        int t = M.cand[a][i - M.poff[a]];
+        float m = margin + M.spd[a] + M.spd[t];
+        unsigned short mk = 0;
+        PairGeom G;
+        if (pair_geom(M, a, t, m, G)) {
+          int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
+          for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, margin, &d)) mk |= (unsigned short)(1u << p); }
+        }
+        masks[s] = mk;
+        mycount += __popc((unsigned)mk);
+      }
+    }
+    // block-wide exclusive scan of per-thread contact counts (thread order == pair order)
+    M.scan[tid] = mycount;
+    __syncthreads();
+    if (tid == 0) {
+      int o = 0;
+      for (int i = 0; i < SIM_THREADS; ++i) { int c = M.scan[i]; M.scan[i] = o; o += c; }
+      M.ncon = o < MAXC ? o : MAXC;
+      if (o > MAXC) atomicAdd(&M.ndropped, o - MAXC);
+    }
+    __syncthreads();
+    // pass 2: regenerate the hits and write contacts at their global slots
+    {
+      int slot = M.scan[tid];
+      int a = 0;
+      for (int i = p0, s = 0; i < p1 && s < PPMAX; ++i, ++s) {
+        unsigned mk = masks[s];
+        if (!mk) continue;
+        while (M.poff[a + 1] <= i) ++a;
+        int t = M.cand[a][i - M.poff[a]];
+        float m = margin + M.spd[a] + M.spd[t];
+        PairGeom G;
+        pair_geom(M, a, t, m, G);
+        for (int p = 0; p < 12; ++p) {
+          if (!(mk & (1u << p))) continue;
+          float depth;
+          point_hit(G, p, m, margin, &depth);
+          if (slot < MAXC) {
+            v3 wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
+            M.cword[slot] = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
+            M.cw[0][slot] = wpt.x; M.cw[1][slot] = wpt.y; M.cw[2][slot] = wpt.z;
+            float bias = 0.0f;
+            if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
+            else if (depth < 0.0f) bias = depth / h;
+            M.cbias[slot] = bias;
+            M.clam[0][slot] = 0.0f; M.clam[1][slot] = 0.0f; M.clam[2][slot] = 0.0f;
+            M.cden[0][slot] = depth;
+          }
+          ++slot;
+        }
+      }
+      if (pairdrop) atomicAdd(&M.ndropped, pairdrop);
+    }
+    __syncthreads();
+    const int ncon = M.ncon;
+    // 7. incidence lists in contact order (every body thread scans the contact words; broadcast reads)
+    const int mybody = tid < NB ? tid : ((tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) ? NB + (tid - ROBOT_TID0) : -1);
+    if (mybody >= 0) {
+      int c = 0;
+      for (int i = 0; i < ncon; ++i) {
+        uint32_t wd = M.cword[i];
+        int a = wd & 255, b = (wd >> 8) & 255;
+        c += (a == mybody) + (b == mybody);
+      }
+      M.nb[mybody] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int o = 0;
+      for (int b = 0; b < NBODY; ++b) { M.inc_off[b] = o; o += M.nb[b]; }
+      M.inc_off[NBODY] = o;
+    }
+    __syncthreads();
+    if (mybody >= 0) {
+      int o = M.inc_off[mybody];
+      for (int i = 0; i < ncon; ++i) {
+        uint32_t wd = M.cword[i];
+        int a = wd & 255, b = (wd >> 8) & 255;
+        if (a == mybody) M.inc[o++] = (unsigned short)(i << 1);
+        else if (b == mybody) M.inc[o++] = (unsigned short)((i << 1) | 1);
+      }
+    }
+    if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) {
+      int j = tid - ROBOT_TID0, nn = 0;
+      for (int L = 0; L < SDX_NL; ++L) if (S->link_anc_mask[L] & (1u << j)) nn += M.nb[NB + L];
+      M.nj[j] = nn;
+    }
+    if (condump && sub == substeps - 1)
+      for (int i = tid; i < ncon; i += SIM_THREADS) {
+        float* o = condump + ((size_t)e * MAXC + i) * 8;
+        o[0] = __uint_as_float(M.cword[i]); o[1] = M.cw[0][i]; o[2] = M.cw[1][i]; o[3] = M.cw[2][i]; o[4] = M.cden[0][i];
+        o[5] = M.cbias[i]; o[6] = 0.0f; o[7] = 0.0f;
+      }
+    __syncthreads();
+    // 8. mass-split effective inverse masses along n, t1, t2
+    for (int i = tid; i < ncon; i += SIM_THREADS) {
+      uint32_t wd = M.cword[i];
+      int a = wd & 255, b = (wd >> 8) & 255;
+      v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
+      v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
+      M.cden[0][i] = body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n);
+      M.cden[1][i] = body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1);
+      M.cden[2][i] = body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2);
+    }
+    __syncthreads();
+    // 9. Jacobi iterations on total impulses
+    const float mu = S->friction;
+    for (int it = 0; it < iters; ++it) {
+      for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
+        uint32_t wd = M.cword[i];
+        int a = wd & 255, b = (wd >> 8) & 255;
+        v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
+        v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
+        v3 vrel = vadd(ld3(M.bv[a]), vcross(ld3(M.bw[a]), vsub(wpt, ld3(M.bx[a]))));
+        if (b != STATIC_BODY) vrel = vsub(vrel, vadd(ld3(M.bv[b]), vcross(ld3(M.bw[b]), vsub(wpt, ld3(M.bx[b])))));
+        float ln = M.clam[0][i] + (M.cbias[i] - vdot(vrel, n)) / M.cden[0][i];
+        ln = ln > 0.0f ? ln : 0.0f;
+        float lim = mu * ln;
+        float l1 = clampf(M.clam[1][i] - vdot(vrel, t1) / M.cden[1][i], -lim, lim);
+        float l2 = clampf(M.clam[2][i] - vdot(vrel, t2) / M.cden[2][i], -lim, lim);
+        M.clam[0][i] = ln; M.clam[1][i] = l1; M.clam[2][i] = l2;
+      }
+      __syncthreads();
+      if (mybody >= 0) {                                       // phase B: one thread per body
+        v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
+        const int e0 = M.inc_off[mybody], e1 = M.inc_off[mybody + 1];
+        const v3 xb = mybody < NB ? ld3(M.bx[mybody]) : V3(0.0f, 0.0f, 0.0f);
+        for (int ee = e0; ee < e1; ++ee) {
+          int ent = M.inc[ee], i = ent >> 1;
+          v3 n, t1, t2; contact_axes(M, M.cword[i], &n, &t1, &t2);
+          v3 f = vadd(vadd(vscale(n, M.clam[0][i]), vscale(t1, M.clam[1][i])), vscale(t2, M.clam[2][i]));
+          if (ent & 1) f = vneg(f);
+          v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
+          F = vadd(F, f);
+          if (mybody < NB) T = vadd(T, vcross(vsub(wpt, xb), f));
+          else T = vadd(T, vcross(wpt, f));
+        }
+        if (mybody < NB) {
+          st3(M.bv[mybody], vadd(vfree, vscale(F, invm)));
+          st3(M.bw[mybody], vadd(wfree, brick_Iinv_mul(M.sR[mybody], invI, T)));
+        } else { st3(M.linkF[mybody - NB], F); st3(M.linkM[mybody - NB], T); }
+      }
+      if (tid >= ROBOT_TID0) {                                 // the articulation lives in one warp
+        __syncwarp();
+        if (tid < ROBOT_TID0 + SDX_ND) {
+          int j = tid - ROBOT_TID0;
+          v3 Fd = V3(0.0f, 0.0f, 0.0f), Md = V3(0.0f, 0.0f, 0.0f);
+          for (int L = 0; L < SDX_NL; ++L)
+            if (S->link_anc_mask[L] & (1u << j)) { Fd = vadd(Fd, ld3(M.linkF[L])); Md = vadd(Md, ld3(M.linkM[L])); }
+          v3 aj = ld3(M.ja[j]);
+          float g = vdot(aj, vsub(Md, vcross(ld3(M.jo[j]), Fd)));
+          M.qd[j] = M.qdfree[j] + g / M.ieff[j];
+        }
+        __syncwarp();
+        if (tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0);
+      }
+      __syncthreads();
+    }
+    if (iters == 0 && tid < SDX_NL) { st3(M.linkF[tid], V3(0, 0, 0)); st3(M.linkM[tid], V3(0, 0, 0)); }
+    // 10. integrate
+    if (tid < nbr) {
+      v3 w = ld3(M.bw[tid]), v = ld3(M.bv[tid]);
+      float w2 = vdot(w, w), mw = S->max_ang_vel;
+      if (w2 > mw * mw) { w = vscale(w, mw / sqrtf(w2)); }
+      float v2 = vdot(v, v), mv = S->max_lin_vel;
+      if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); }
+      bvr = v; bwr = w;
+      bxr = vadd(bxr, vscale(v, h));
+      q4 q = bqr;
+      float hh = 0.5f * h;
+      q4 dq;
+      dq.x = hh * (w.x * q.w + w.y * q.z - w.z * q.y);
+      dq.y = hh * (w.y * q.w + w.z * q.x - w.x * q.z);
+      dq.z = hh * (w.z * q.w + w.x * q.y - w.y * q.x);
+      dq.w = hh * (-(w.x * q.x + w.y * q.y + w.z * q.z));
+      q.x = q.x + dq.x; q.y = q.y + dq.y; q.z = q.z + dq.z; q.w = q.w + dq.w;
+      float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+      q.x = q.x * inv; q.y = q.y * inv; q.z = q.z * inv; q.w = q.w * inv;
+      bqr = q;
+    } else if (tid < NB) { bvr = ld3(M.bv[tid]); bwr = ld3(M.bw[tid]); }
+    if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) {
+      int j = tid - ROBOT_TID0;
+      float qdj = M.qd[j];
+      float qn = M.q[j] + h * qdj;
+      if (qn < S->dof_lo[j]) { qn = S->dof_lo[j]; if (qdj < 0.0f) qdj = 0.0f; }
+      if (qn > S->dof_hi[j]) { qn = S->dof_hi[j]; if (qdj > 0.0f) qdj = 0.0f; }
+      M.q[j] = qn; M.qd[j] = qdj;
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: brick tile back through shared memory + TMA bulk store; task-visible robot rows
+  if (tid < NB) {
+    M.tile[0 * NB + tid] = bxr.x; M.tile[1 * NB + tid] = bxr.y; M.tile[2 * NB + tid] = bxr.z;
+    M.tile[3 * NB + tid] = bqr.x; M.tile[4 * NB + tid] = bqr.y; M.tile[5 * NB + tid] = bqr.z; M.tile[6 * NB + tid] = bqr.w;
+    M.tile[7 * NB + tid] = bvr.x; M.tile[8 * NB + tid] = bvr.y; M.tile[9 * NB + tid] = bvr.z;
+    M.tile[10 * NB + tid] = bwr.x; M.tile[11 * NB + tid] = bwr.y; M.tile[12 * NB + tid] = bwr.z;
+  }
+  if (tid == ROBOT_TID0) robot_fk(S, M);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gbrick), "r"(tile_s), "r"(13 * NB * 4) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0);
+  if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) { int j = tid - ROBOT_TID0; gdof[j] = M.q[j]; gdof[24 + j] = M.qd[j]; }
+  __syncthreads();
+  if (tid < SDX_NL) {
+    int L = tid;
+    float* o = link_out + ((size_t)e * SDX_NL + L) * 13;
+    o[0] = M.bx[NB + L][0]; o[1] = M.bx[NB + L][1]; o[2] = M.bx[NB + L][2];
+    o[3] = M.lq[L][0]; o[4] = M.lq[L][1]; o[5] = M.lq[L][2]; o[6] = M.lq[L][3];
+    o[7] = M.bv[NB + L][0]; o[8] = M.bv[NB + L][1]; o[9] = M.bv[NB + L][2];
+    o[10] = M.bw[NB + L][0]; o[11] = M.bw[NB + L][1]; o[12] = M.bw[NB + L][2];
+    float invh = 1.0f / h;
+    float* f = netf + ((size_t)e * SDX_NL + L) * 3;
+    f[0] = M.linkF[L][0] * invh; f[1] = M.linkF[L][1] * invh; f[2] = M.linkF[L][2] * invh;
+  }
+  if (tid >= 32 && tid < 39) {
+    int j = tid - 32;
+    v3 aj = ld3(M.ja[j]);
+    v3 lin = vcross(aj, vsub(ld3(M.bx[NB + 7]), ld3(M.jo[j])));
+    float* J = jac7 + (size_t)e * 42;
+    J[0 * 7 + j] = lin.x; J[1 * 7 + j] = lin.y; J[2 * 7 + j] = lin.z;
+    J[3 * 7 + j] = aj.x; J[4 * 7 + j] = aj.y; J[5 * 7 + j] = aj.z;
+  }
+  if (tid == 64) { ncontact[2 * e] = M.ncon; ncontact[2 * e + 1] = M.ndropped; }
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}

@@ -1,0 +1,153 @@
+"""Thin Python owner of one ``sdx_env_t`` (include/seqdex_b200.h): device buffers exposed as
+zero-copy torch views, the way ``gymtorch.wrap_tensor`` exposes PhysX buffers (GS:237-246)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .scene import Scene
+
+T = dict(BRICK=0, DOF=1, LINK=2, JAC7=3, NETF=4, ACTIONS=5, OBS=6, STATES=7, REW=8, RESET=9, PROGRESS=10, TVALUE=11,
+         TARGET_INIT=12, SUCCESSES=13, CONSEC=14, NCONTACT=15, ROOT=16, RB=17, DOF_STATE=18, JACOBIAN=19, EPISODE=20,
+         CONTACTS=21)
+_DT = {0: (torch.float32, "<f4"), 1: (torch.int64, "<i8"), 2: (torch.int32, "<i4")}
+
+
+class _DevView:
+    """``__cuda_array_interface__`` carrier so torch can alias a raw device pointer without copying."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class SdxEnv:
+    def __init__(self, scene: Scene, num_envs: int, device: int = 0, seed: int = 22):
+        if not torch.cuda.is_available():
+            raise RuntimeError("seqdex_b200 needs a CUDA device: there is no CPU path")
+        self.L = _lib.load()
+        assert self.L.sdx_scene_size() == ctypes.sizeof(scene.c), "scene struct ABI mismatch"
+        self.scene, self.n, self.device_index = scene, num_envs, device
+        self.device = torch.device("cuda", device)
+        self.h = ctypes.c_void_p()
+        _lib.check(self.L.sdx_create(ctypes.byref(scene.c), num_envs, device, ctypes.c_uint64(seed), ctypes.byref(self.h)))
+        rows = np.zeros((142, 13), np.float32)
+        for k, v in scene.static_actor_roots().items():
+            rows[k] = v
+        _lib.check(self.L.sdx_set_static_rows(self.h, rows.ctypes.data_as(ctypes.c_void_p)))
+        self._views = {}
+        self.set_stream(torch.cuda.current_stream(self.device))
+
+    def close(self):
+        if self.h:
+            self.L.sdx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream):
+        _lib.check(self.L.sdx_set_stream(self.h, ctypes.c_void_p(stream.cuda_stream)))
+
+    def tensor(self, name: str) -> torch.Tensor:
+        if name in self._views:
+            return self._views[name]
+        ptr = ctypes.c_void_p()
+        shape = (ctypes.c_int64 * 4)()
+        nd, dt = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.L.sdx_tensor(self.h, T[name], ctypes.byref(ptr), shape, ctypes.byref(nd), ctypes.byref(dt)))
+        shp = [int(shape[i]) for i in range(nd.value)]
+        with torch.cuda.device(self.device):
+            t = torch.as_tensor(_DevView(ptr.value, shp, _DT[dt.value][1]), device=self.device)
+        self._views[name] = t
+        return t
+
+    # ---- setup
+    def set_heap_bank(self, bank):
+        """bank: [8, per_type, 72, 13] root-frame rows (numpy or torch)."""
+        if isinstance(bank, torch.Tensor) and bank.is_cuda:
+            b = bank.contiguous().float()
+            _lib.check(self.L.sdx_set_heap_bank_dev(self.h, ctypes.c_void_p(b.data_ptr()), int(b.shape[1])))
+        else:
+            b = np.ascontiguousarray(bank.cpu().numpy() if isinstance(bank, torch.Tensor) else bank, np.float32)
+            _lib.check(self.L.sdx_set_heap_bank(self.h, b.ctypes.data_as(ctypes.c_void_p), int(b.shape[1])))
+
+    def set_tvalue_weights(self, w):
+        w = np.ascontiguousarray(w, np.float32)
+        assert w.size == 42562
+        _lib.check(self.L.sdx_set_tvalue_weights(self.h, w.ctypes.data_as(ctypes.c_void_p)))
+
+    def reset_all(self):
+        _lib.check(self.L.sdx_reset_all(self.h))
+
+    # ---- stepping (BT:130-150)
+    def pre_physics(self, actions: torch.Tensor):
+        a = actions.contiguous().float()
+        _lib.check(self.L.sdx_pre_physics(self.h, ctypes.c_void_p(a.data_ptr())))
+
+    def simulate(self, n=1):
+        _lib.check(self.L.sdx_simulate_n(self.h, n))
+
+    def post_physics(self):
+        _lib.check(self.L.sdx_post_physics(self.h))
+
+    def step(self, actions: torch.Tensor):
+        a = actions.contiguous().float()
+        _lib.check(self.L.sdx_step(self.h, ctypes.c_void_p(a.data_ptr())))
+
+    def step_host(self, actions, obs, states, rew, reset):
+        """pinned host tensors in/out (VecTask.step through the C-ABI with host buffers)."""
+        _lib.check(self.L.sdx_step_host(self.h, ctypes.c_void_p(actions.data_ptr()), ctypes.c_void_p(obs.data_ptr()),
+                                        ctypes.c_void_p(states.data_ptr()), ctypes.c_void_p(rew.data_ptr()),
+                                        ctypes.c_void_p(reset.data_ptr())))
+
+    def refresh(self, name):
+        _lib.check(self.L.sdx_refresh(self.h, T[name]))
+
+    def launch_count(self):
+        return int(self.L.sdx_launch_count(self.h))
+
+    def brick_roots(self):
+        """[N, 72, 13] Isaac-Gym root rows of the free bricks (actors 9..80 of the root tensor)."""
+        self.refresh("ROOT")
+        return self.tensor("ROOT").view(self.n, 142, 13)[:, 9:81]
+
+
+def make_heap_bank(scene: Scene, per_type: int, device: int = 0, settle_steps: int = 240, seed: int = 22):
+    """Synthesise the terminal-state heap bank the task samples on reset -- the stand-in for the
+    unshipped ``saved_searching_ternimal_states_*.pkl`` (GS:412-413): drop the 72 free
+    bricks from the staggered lattice (GS:737-742) under gravity and let them settle; per-heap variety comes
+    from a small Philox-free jitter of the lattice.  Runs on the GPU with the product kernel."""
+    n = 8 * per_type
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    env = SdxEnv(scene, n, device, seed)
+    brick = env.tensor("BRICK")
+    jit = (torch.rand(n, 3, 72, generator=g) * 2 - 1) * torch.tensor([0.01, 0.01, 0.0]).view(1, 3, 1)
+    brick[:, 0:3, :] += jit.to(brick.device)
+    old = scene.c.brick_lin_damp
+    # gentle settle: linear damping while the 9 layers come down, then free
+    import ctypes as _c
+    scene.c.brick_lin_damp = 10.0
+    env2 = env  # the device copy of the scene was taken at creation: recreate with damping
+    env.close()
+    env = SdxEnv(scene, n, device, seed)
+    env.tensor("BRICK")[:, 0:3, :] += jit.to(env.device)
+    env.simulate(settle_steps * 2 // 3)
+    rows_damped = env.brick_roots().clone()
+    scene.c.brick_lin_damp = old
+    env3 = SdxEnv(scene, n, device, seed)
+    idx = torch.arange(n * 142, dtype=torch.int32, device=env3.device)
+    root = env3.tensor("ROOT")
+    env3.refresh("ROOT")
+    root.view(n, 142, 13)[:, 9:81] = rows_damped
+    _lib.check(env3.L.sdx_set_actor_root_state_indexed(env3.h, ctypes.c_void_p(root.data_ptr()), ctypes.c_void_p(idx.data_ptr()), n * 142))
+    env3.simulate(settle_steps // 3)
+    rows = env3.brick_roots().clone()
+    rows[:, :, 7:13] = 0
+    env.close(); env3.close()
+    return rows.view(8, per_type, 72, 13).contiguous()
