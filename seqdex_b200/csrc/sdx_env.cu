@@ -13,6 +13,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* sdx_last_error(void) { return g_err.c_str(); }
+void sdx_set_error(const char* msg) { g_err = msg; }
 static int fail(const char* what, cudaError_t e, const char* file, int line) {
   char buf[512];
   snprintf(buf, sizeof buf, "%s:%d %s: %s", file, line, what, cudaGetErrorString(e));

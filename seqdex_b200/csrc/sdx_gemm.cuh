@@ -1,0 +1,209 @@
+// sdx_gemm.cuh -- bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), the dense
+// contraction of the PPO MLPs:   D[M,N] = A[M,K] . B[N,K]^T   (both K-major).
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B-swizzled 64-column K slabs, mbarrier tx)
+//   warp 1      : TMEM allocator + MMA issuer (one thread issues tcgen05.mma.cta_group::1.kind::f16,
+//                 UMMA 128 x BN x 16, accumulator in TMEM; tcgen05.commit frees smem stages)
+//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//
+// Fused epilogues (MODE):
+//   0  forward      out = ELU(acc + bias[n])               -> bf16 [M,ldo] (+ optional transposed bf16 [N,ldt])
+//   1  backward dX  out = acc * ELU'(h[m,n])  (h = the layer's own ELU output; ELU'(h) = h > 0 ? 1 : h + 1)
+//                                                          -> bf16 [M,ldo] (+ optional transposed bf16 [N,ldt])
+//   2  backward dW  out += acc   (fp32 red.global.add, split-K over blockIdx.z)  -> fp32 [M,ldf]
+//   3  plain        out = acc                                                   -> fp32 [M,ldf]
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define GEMM_BM 128
+#define GEMM_BK 64
+#define GEMM_THREADS 192
+
+struct GemmArgs {
+  int M, N, K;              // problem (K = total reduction length; split-K slices it by gridDim.z)
+  int kblocks_per_split;    // BK-blocks each z-slice reduces
+  const float* bias;        // MODE 0
+  const __nv_bfloat16* h; int ldh;          // MODE 1
+  __nv_bfloat16* out; int ldo;              // MODE 0/1 row-major
+  __nv_bfloat16* out_t; int ldt;            // MODE 0/1 transposed copy (may be null)
+  float* outf; int ldf;                     // MODE 2/3
+};
+
+namespace gemm {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(n)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t a = smem_u32(b), done = 0;
+  while (!done)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows 128 B apart, 8-row groups 1024 B apart (SBO), LBO = 1 (16 B), version 1
+__device__ __forceinline__ uint64_t umma_desc(const void* smem_tile) {
+  uint64_t d = (uint64_t)((smem_u32(smem_tile) & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+}  // namespace gemm
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  __nv_bfloat16 a[STAGES][GEMM_BM * GEMM_BK];
+  __nv_bfloat16 b[STAGES][BN * GEMM_BK];
+  uint64_t full[STAGES], empty[STAGES], tmem_full;
+  uint32_t tmem_base;
+};
+
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+  using namespace gemm;
+  extern __shared__ unsigned char gsm_raw[];
+  // 128B-swizzled TMA/UMMA tiles need 1024 B alignment: align by hand (the launcher over-allocates 1 KB)
+  auto& S = *reinterpret_cast<GemmSmem<BN, STAGES>*>(gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * BN;
+  const int kb0 = blockIdx.z * g.kblocks_per_split;
+  const int total_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
+  const int nkb = min(g.kblocks_per_split, total_kb - kb0);
+  constexpr uint32_t STAGE_BYTES = (GEMM_BM + BN) * GEMM_BK * 2;
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = S.tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&S.empty[s], ph ^ 1);
+        mbar_expect_tx(&S.full[s], STAGE_BYTES);
+        tma_load_2d(&mapA, S.a[s], &S.full[s], (kb0 + kb) * GEMM_BK, m0);
+        tma_load_2d(&mapB, S.b[s], &S.full[s], (kb0 + kb) * GEMM_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&S.full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da = umma_desc(S.a[s]), db = umma_desc(S.b[s]);
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k)   // +32 B (= 2 x 16 B) along K inside the 128 B swizzle row per UMMA_K
+          umma_f16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&S.empty[s]);
+      }
+      umma_commit(&S.tmem_full);
+    }
+  } else {
+    // ---------------- epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = output rows of the tile
+    mbar_wait(&S.tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int lg = warp & 3;
+    const int row = m0 + lg * 32 + lane;
+    const bool row_ok = row < g.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
+      const int col0 = n0 + c * 32;
+      if (col0 >= g.N) break;
+      if (MODE == 0 || MODE == 1) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float acc = __uint_as_float(r[j]);
+          const int col = col0 + j;
+          if (MODE == 0) {
+            acc += (col < g.N) ? g.bias[col] : 0.0f;
+            v[j] = acc > 0.0f ? acc : (__expf(acc) - 1.0f);
+          } else {
+            float hv = (row_ok && col < g.N) ? __bfloat162float(g.h[(size_t)row * g.ldh + col]) : 0.0f;
+            v[j] = acc * (hv > 0.0f ? 1.0f : hv + 1.0f);
+          }
+        }
+        if (row_ok) {
+          if (col0 + 32 <= g.N) {
+            uint4* dst = reinterpret_cast<uint4*>(g.out + (size_t)row * g.ldo + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+              u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+              dst[q] = u;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < g.N; ++j) g.out[(size_t)row * g.ldo + col0 + j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+        if (g.out_t) {   // transposed copy: for a fixed column the 32 lanes hold 32 consecutive rows -> coalesced
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (row_ok && col0 + j < g.N) g.out_t[(size_t)(col0 + j) * g.ldt + row] = __float2bfloat16_rn(v[j]);
+        }
+      } else {
+        if (row_ok) {
+          float* dst = g.outf + (size_t)row * g.ldf + col0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < g.N) {
+              if (MODE == 2) atomicAdd(dst + j, __uint_as_float(r[j]));
+              else dst[j] = __uint_as_float(r[j]);
+            }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+  }
+}
