@@ -12,6 +12,7 @@
 //                                                          -> bf16 [M,ldo] (+ optional transposed bf16 [N,ldt])
 //   2  backward dW  out += acc   (fp32 red.global.add, split-K over blockIdx.z)  -> fp32 [M,ldf]
 //   3  plain        out = acc                                                   -> fp32 [M,ldf]
+//   4  head         out = acc + bias[n]   (linear output layer: mu / value)      -> fp32 [M,ldf]
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -194,6 +195,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           for (int j = 0; j < 32; ++j)
             if (col0 + j < g.N) {
               if (MODE == 2) atomicAdd(dst + j, __uint_as_float(r[j]));
+              else if (MODE == 4) dst[j] = __uint_as_float(r[j]) + g.bias[col0 + j];
               else dst[j] = __uint_as_float(r[j]);
             }
         }

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
+#include <math.h>
 
 #include "sdx_gemm.cuh"
 
@@ -52,6 +54,7 @@ static int set_attrs() {
   PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   g_attr_set = true;
   return 0;
 }
@@ -83,8 +86,388 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
     case 1: k_gemm_tn<GEMM_BN, GEMM_STAGES, 1><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
     case 2: k_gemm_tn<GEMM_BN, GEMM_STAGES, 2><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
     case 3: k_gemm_tn<GEMM_BN, GEMM_STAGES, 3><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
+    case 4: k_gemm_tn<GEMM_BN, GEMM_STAGES, 4><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
     default: sdx_set_error("sdx_gemm_bf16_tn: bad mode"); return -1;
   }
   PCK(cudaGetLastError());
   return 0;
+}
+
+// =====================================================================================================
+// MLP object: fp32 master parameters + Adam state, bf16 compute copies (and their transposes), activation
+// and gradient staging buffers laid out so that EVERY contraction of forward and backward is the K-major
+// tcgen05 GEMM above:
+//   forward   a_{l+1} = ELU(a_l W_l^T + b_l)            A = a_l [M,d_l]          B = W_l  [d_{l+1}, d_l]
+//   head      out     = a_3 W_3^T + b_3   (fp32)        A = a_3 [M,256]          B = W_3  [out, 256]
+//   dX        dz_l    = (dz_{l+1} W_l) * ELU'(a_l)      A = dz_{l+1} [M,d_{l+1}] B = W_l^T [d_l, d_{l+1}]
+//   dW,db     [dW_l | db_l] = dz_{l+1}^T [a_l | 1]      A = dz_{l+1}^T [d_{l+1},M] B = [a_l | 1]^T [d_l+16, M]
+// (the "ones" row appended to the transposed activations makes the bias gradient one more output column).
+// Parameter vector order = torch state_dict of rl_games' network: W0,b0,W1,b1,W2,b2,W3(mu / value),b3[,sigma].
+// =====================================================================================================
+struct sdx_mlp {
+  int in_dim, in_pad, out_dim, max_rows, has_sigma;
+  int d[5];
+  size_t nparams, w_off[4], b_off[4], sigma_off;
+  float *params, *grads, *adam_m, *adam_v, *out, *scal, *gW[4];
+  __nv_bfloat16 *W[4], *Wt[4], *A[4], *At[4], *dZ[5], *dZt[5];
+  long long adam_t;
+};
+static inline int pad64(int x) { return (x + 63) / 64 * 64; }
+
+__global__ void k_fill_bf16(__nv_bfloat16* p, size_t n, float v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = __float2bfloat16_rn(v);
+}
+// fp32 [R, C] (ld) -> bf16 row-major [R, ldo] (cols [C, Cpad) zero-filled) and/or transposed bf16 [Cpad.., ldt];
+// optional per-column normalisation (x - mean) / sqrt(var + 1e-5) clamped to +-5 (rl_games RunningMeanStd)
+__global__ void k_cvt_2way(const float* __restrict__ src, int R, int C, int ld, int Cpad, __nv_bfloat16* __restrict__ dst, int ldo,
+                           __nv_bfloat16* __restrict__ dst_t, int ldt, const float* __restrict__ mean, const float* __restrict__ var) {
+  __shared__ float tile[32][33];
+  int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.0f;
+    if (r < R && c < C) {
+      v = src[(size_t)r * ld + c];
+      if (mean) { v = (v - mean[c]) / sqrtf(var[c] + 1e-5f); v = fminf(fmaxf(v, -5.0f), 5.0f); }
+    }
+    tile[i][threadIdx.x] = v;
+    if (dst && r < R && c < Cpad) dst[(size_t)r * ldo + c] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  if (dst_t)
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      int c = c0 + i, r = r0 + threadIdx.x;
+      if (c < Cpad && r < R) dst_t[(size_t)c * ldt + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+}
+__global__ void k_unpack_grads(const float* __restrict__ gW, int rows, int kreal, int kones, int ldg, float* __restrict__ gw, float* __restrict__ gb) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (kreal + 1)) return;
+  int r = i / (kreal + 1), c = i % (kreal + 1);
+  if (c < kreal) gw[(size_t)r * kreal + c] = gW[(size_t)r * ldg + c];
+  else gb[r] = gW[(size_t)r * ldg + kones];
+}
+__global__ void k_sumsq(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += g[i] * g[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0f;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+// torch.optim.Adam (eps 1e-8, no weight decay; RGC:1102) with rl_games' global grad-norm clip folded in (RGC:1866-1872)
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
+                       float lr, float b1, float b2, float eps, float bc1, float bc2, float max_norm, const float* __restrict__ sumsq) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float scale = 1.0f;
+  if (max_norm > 0.0f) { float nrm = sqrtf(*sumsq); scale = fminf(1.0f, max_norm / (nrm + 1e-6f)); }
+  float gi = g[i] * scale;
+  float mi = b1 * m[i] + (1.0f - b1) * gi;
+  float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+}
+__global__ void k_sync_w(const float* __restrict__ w, int N, int Kreal, __nv_bfloat16* __restrict__ W, int ldw, int Kpad,
+                         __nv_bfloat16* __restrict__ Wt, int ldwt, int Npad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int tot = max(N * Kpad, Wt ? Kreal * Npad : 0);
+  if (i >= tot) return;
+  if (i < N * Kpad) { int n = i / Kpad, k = i % Kpad; W[(size_t)n * ldw + k] = __float2bfloat16_rn(k < Kreal ? w[(size_t)n * Kreal + k] : 0.0f); }
+  if (Wt && i < Kreal * Npad) { int k = i / Npad, n = i % Npad; Wt[(size_t)k * ldwt + n] = __float2bfloat16_rn(n < N ? w[(size_t)n * Kreal + k] : 0.0f); }
+}
+
+extern "C" int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sigma, sdx_mlp** out) {
+  sdx_mlp* m = new sdx_mlp();
+  memset(m, 0, sizeof(*m));
+  m->in_dim = in_dim; m->in_pad = pad64(in_dim); m->out_dim = out_dim; m->max_rows = max_rows; m->has_sigma = has_sigma;
+  m->d[0] = m->in_pad; m->d[1] = 1024; m->d[2] = 512; m->d[3] = 256; m->d[4] = out_dim;
+  if (max_rows % 8) { sdx_set_error("sdx_mlp_create: max_rows must be a multiple of 8"); return -1; }
+  size_t off = 0;
+  for (int l = 0; l < 4; ++l) {
+    int kreal = l == 0 ? in_dim : m->d[l];
+    m->w_off[l] = off; off += (size_t)m->d[l + 1] * kreal;
+    m->b_off[l] = off; off += m->d[l + 1];
+  }
+  m->sigma_off = off; if (has_sigma) off += out_dim;
+  m->nparams = off;
+  PCK(cudaMalloc(&m->params, off * 4)); PCK(cudaMemset(m->params, 0, off * 4));
+  PCK(cudaMalloc(&m->grads, off * 4)); PCK(cudaMemset(m->grads, 0, off * 4));
+  PCK(cudaMalloc(&m->adam_m, off * 4)); PCK(cudaMemset(m->adam_m, 0, off * 4));
+  PCK(cudaMalloc(&m->adam_v, off * 4)); PCK(cudaMemset(m->adam_v, 0, off * 4));
+  PCK(cudaMalloc(&m->out, (size_t)max_rows * out_dim * 4));
+  PCK(cudaMalloc(&m->scal, 64)); PCK(cudaMemset(m->scal, 0, 64));
+  size_t R = max_rows;
+  for (int l = 0; l < 4; ++l) {
+    int K = m->d[l], N = m->d[l + 1], Npad = pad64(N);
+    PCK(cudaMalloc(&m->W[l], (size_t)N * K * 2)); PCK(cudaMemset(m->W[l], 0, (size_t)N * K * 2));
+    if (l > 0) { PCK(cudaMalloc(&m->Wt[l], (size_t)K * Npad * 2)); PCK(cudaMemset(m->Wt[l], 0, (size_t)K * Npad * 2)); }
+    PCK(cudaMalloc(&m->A[l], R * K * 2)); PCK(cudaMemset(m->A[l], 0, R * K * 2));
+    PCK(cudaMalloc(&m->At[l], (size_t)(K + 16) * R * 2)); PCK(cudaMemset(m->At[l], 0, (size_t)(K + 16) * R * 2));
+    k_fill_bf16<<<(unsigned)((R + 255) / 256), 256>>>(m->At[l] + (size_t)K * R, R, 1.0f);   // the "ones" row -> bias gradients
+    PCK(cudaMalloc(&m->gW[l], (size_t)N * (K + 16) * 4));
+    PCK(cudaMalloc(&m->dZ[l + 1], R * Npad * 2)); PCK(cudaMemset(m->dZ[l + 1], 0, R * Npad * 2));
+    PCK(cudaMalloc(&m->dZt[l + 1], (size_t)Npad * R * 2)); PCK(cudaMemset(m->dZt[l + 1], 0, (size_t)Npad * R * 2));
+  }
+  PCK(cudaDeviceSynchronize());
+  *out = m;
+  return 0;
+}
+extern "C" void sdx_mlp_destroy(sdx_mlp* m) {
+  if (!m) return;
+  cudaFree(m->params); cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->out); cudaFree(m->scal);
+  for (int l = 0; l < 4; ++l) { cudaFree(m->W[l]); cudaFree(m->Wt[l]); cudaFree(m->A[l]); cudaFree(m->At[l]); cudaFree(m->gW[l]); cudaFree(m->dZ[l + 1]); cudaFree(m->dZt[l + 1]); }
+  delete m;
+}
+extern "C" int sdx_mlp_info(sdx_mlp* m, int64_t* nparams, void** params, void** grads, void** out, void** adam_m, void** adam_v) {
+  *nparams = (int64_t)m->nparams; *params = m->params; *grads = m->grads; *out = m->out;
+  if (adam_m) *adam_m = m->adam_m;
+  if (adam_v) *adam_v = m->adam_v;
+  return 0;
+}
+// refresh the bf16 compute copies from the fp32 master parameters (after load / optimiser step)
+extern "C" int sdx_mlp_sync(sdx_mlp* m, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int l = 0; l < 4; ++l) {
+    int N = m->d[l + 1], Kpad = m->d[l], Kreal = l == 0 ? m->in_dim : m->d[l], Npad = pad64(N);
+    int tot = N * Kpad; if (l > 0 && Kreal * Npad > tot) tot = Kreal * Npad;
+    k_sync_w<<<(tot + 255) / 256, 256, 0, st>>>(m->params + m->w_off[l], N, Kreal, m->W[l], Kpad, Kpad, l > 0 ? m->Wt[l] : nullptr, Npad, Npad);
+  }
+  PCK(cudaGetLastError());
+  return 0;
+}
+// x: fp32 [M, in_dim] (device).  mean/var (nullable): RunningMeanStd input normalisation.  train != 0 keeps the
+// transposed activations the backward pass needs.  Result: m->out fp32 [M, out_dim].
+extern "C" int sdx_mlp_forward(sdx_mlp* m, const float* x, int M, const float* mean, const float* var, int train, void* stream) {
+  if (M > m->max_rows || M <= 0) { sdx_set_error("sdx_mlp_forward: M exceeds max_rows"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 blk(32, 8), grd((m->in_pad + 31) / 32, (M + 31) / 32);
+  k_cvt_2way<<<grd, blk, 0, st>>>(x, M, m->in_dim, m->in_dim, m->in_pad, m->A[0], m->in_pad, train ? m->At[0] : nullptr, m->max_rows, mean, var);
+  PCK(cudaGetLastError());
+  for (int l = 0; l < 3; ++l)
+    if (sdx_gemm_bf16_tn(0, m->A[l], M, m->d[l], m->d[l], m->W[l], m->d[l + 1], m->d[l], m->params + m->b_off[l], nullptr, 0, m->A[l + 1], m->d[l + 1],
+                         train ? m->At[l + 1] : nullptr, m->max_rows, nullptr, 0, 1, stream)) return -1;
+  return sdx_gemm_bf16_tn(4, m->A[3], M, m->d[3], m->d[3], m->W[3], m->out_dim, m->d[3], m->params + m->b_off[3], nullptr, 0, nullptr, 0, nullptr, 0,
+                          m->out, m->out_dim, 1, stream);
+}
+// dout: fp32 [M, out_dim] = dLoss/d(out).  Fills m->grads (W and b of every layer; sigma is the loss kernel's job).
+extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stream) {
+  if (M > m->max_rows || M <= 0) { sdx_set_error("sdx_mlp_backward: M exceeds max_rows"); return -1; }
+  cudaStream_t st = (cudaStream_t)stream;
+  int opad = pad64(m->out_dim);
+  dim3 blk(32, 8), grd((opad + 31) / 32, (M + 31) / 32);
+  k_cvt_2way<<<grd, blk, 0, st>>>(dout, M, m->out_dim, m->out_dim, opad, m->dZ[4], opad, m->dZt[4], m->max_rows, nullptr, nullptr);
+  PCK(cudaGetLastError());
+  for (int l = 3; l >= 0; --l) {
+    int N = m->d[l + 1], K = m->d[l], ldg = K + 16;
+    PCK(cudaMemsetAsync(m->gW[l], 0, (size_t)N * ldg * 4, st));
+    int tiles = ((N + 127) / 128) * ((K + 16 + 127) / 128);
+    int splits = (296 + tiles - 1) / tiles; if (splits < 1) splits = 1;
+    if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, m->At[l], K + 16, m->max_rows, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
+    int kreal = l == 0 ? m->in_dim : K;
+    k_unpack_grads<<<(N * (kreal + 1) + 255) / 256, 256, 0, st>>>(m->gW[l], N, kreal, K, ldg, m->grads + m->w_off[l], m->grads + m->b_off[l]);
+    if (l > 0) {
+      int Kd = pad64(N);
+      if (sdx_gemm_bf16_tn(1, m->dZ[l + 1], M, Kd, Kd, m->Wt[l], K, Kd, nullptr, m->A[l], K, m->dZ[l], K, m->dZt[l], m->max_rows, nullptr, 0, 1, stream)) return -1;
+    }
+  }
+  PCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int sdx_mlp_adam(sdx_mlp* m, float lr, float b1, float b2, float eps, float max_norm, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  m->adam_t++;
+  PCK(cudaMemsetAsync(m->scal, 0, 4, st));
+  if (max_norm > 0.0f) k_sumsq<<<296, 256, 0, st>>>(m->grads, m->nparams, m->scal);
+  float bc1 = 1.0f - powf(b1, (float)m->adam_t), bc2 = 1.0f - powf(b2, (float)m->adam_t);
+  k_adam<<<(unsigned)((m->nparams + 255) / 256), 256, 0, st>>>(m->params, m->grads, m->adam_m, m->adam_v, m->nparams, lr, b1, b2, eps, bc1, bc2, max_norm, m->scal);
+  PCK(cudaGetLastError());
+  return sdx_mlp_sync(m, stream);
+}
+
+// =====================================================================================================
+// PPO elementwise kernels (rl_games 1.5.2 semantics)
+// =====================================================================================================
+__device__ __forceinline__ void philox4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t out[4]) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c[4] = {c0, c1, c2, 0u};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+// a = mu + exp(logstd) * N(0,1);  neglogp = 0.5 sum((a-mu)/sigma)^2 + 0.5 A ln(2 pi) + sum(logstd)   (RGC:2115-2127)
+__global__ void k_ppo_sample(const float* __restrict__ mu, const float* __restrict__ logstd, int M, int A, uint64_t seed, uint32_t counter,
+                             float* __restrict__ actions, float* __restrict__ neglogp) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= M) return;
+  float nlp = 0.0f, sls = 0.0f;
+  for (int i = 0; i < A; i += 4) {
+    uint32_t r[4];
+    philox4(seed, (uint32_t)e, counter, (uint32_t)(i >> 2), r);
+    float u0 = ((r[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u1 = (r[1] >> 8) * (1.0f / 16777216.0f);
+    float u2 = ((r[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u3 = (r[3] >> 8) * (1.0f / 16777216.0f);
+    float ra = sqrtf(-2.0f * logf(u0)), rb = sqrtf(-2.0f * logf(u2));
+    float z[4] = {ra * cosf(6.283185307f * u1), ra * sinf(6.283185307f * u1), rb * cosf(6.283185307f * u3), rb * sinf(6.283185307f * u3)};
+    for (int j = 0; j < 4 && i + j < A; ++j) {
+      float ls = logstd[i + j];
+      actions[(size_t)e * A + i + j] = mu[(size_t)e * A + i + j] + expf(ls) * z[j];
+      nlp += 0.5f * z[j] * z[j];
+      sls += ls;
+    }
+  }
+  neglogp[e] = nlp + 0.5f * (float)A * 1.8378770664093453f + sls;
+}
+// stats: [0] sum a_loss, [1] sum b_loss, [2] sum kl, [3] sum clipped indicator
+__global__ void k_ppo_actor_loss(const float* __restrict__ mu, const float* __restrict__ logstd, const float* __restrict__ actions,
+                                 const float* __restrict__ old_mu, const float* __restrict__ old_logstd, const float* __restrict__ old_neglogp,
+                                 const float* __restrict__ adv, int M, int A, float e_clip, float bounds_coef, float inv_batch,
+                                 float* __restrict__ dmu, float* __restrict__ dlogstd, float* __restrict__ stats) {
+  __shared__ float s_dl[32], s_st[4];
+  if (threadIdx.x < 32) s_dl[threadIdx.x] = 0.0f;
+  if (threadIdx.x < 4) s_st[threadIdx.x] = 0.0f;
+  __syncthreads();
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < M) {
+    float nlp = 0.0f, sls = 0.0f, bl = 0.0f, kl = 0.0f;
+    for (int i = 0; i < A; ++i) {
+      float ls = logstd[i], sg = expf(ls), m_ = mu[(size_t)e * A + i];
+      float z = (actions[(size_t)e * A + i] - m_) / sg;
+      nlp += 0.5f * z * z; sls += ls;
+      float hi = fmaxf(m_ - 1.1f, 0.0f), lo = fminf(m_ + 1.1f, 0.0f);
+      bl += hi * hi + lo * lo;
+      float so = expf(old_logstd[i]), dm = old_mu[(size_t)e * A + i] - m_;
+      kl += logf(sg / so + 1e-5f) + (so * so + dm * dm) / (2.0f * (sg * sg + 1e-5f)) - 0.5f;
+    }
+    nlp += 0.5f * (float)A * 1.8378770664093453f + sls;
+    float ratio = expf(old_neglogp[e] - nlp), a = adv[e];
+    float s1 = -a * ratio, s2 = -a * fminf(fmaxf(ratio, 1.0f - e_clip), 1.0f + e_clip);
+    bool inside = ratio > 1.0f - e_clip && ratio < 1.0f + e_clip;
+    float al = fmaxf(s1, s2);
+    // d a_loss / d neglogp: branch s1 -> a * ratio; branch s2 -> a * ratio inside the clip range, else 0
+    float g = (s1 >= s2 || inside) ? a * ratio : 0.0f;
+    for (int i = 0; i < A; ++i) {
+      float ls = logstd[i], sg = expf(ls), m_ = mu[(size_t)e * A + i];
+      float z = (actions[(size_t)e * A + i] - m_) / sg;
+      float db = 2.0f * fmaxf(m_ - 1.1f, 0.0f) + 2.0f * fminf(m_ + 1.1f, 0.0f);
+      dmu[(size_t)e * A + i] = (g * (-z / sg) + bounds_coef * db) * inv_batch;
+      atomicAdd(&s_dl[i], g * (1.0f - z * z) * inv_batch);
+    }
+    atomicAdd(&s_st[0], al); atomicAdd(&s_st[1], bl); atomicAdd(&s_st[2], kl); atomicAdd(&s_st[3], inside ? 0.0f : 1.0f);
+  }
+  __syncthreads();
+  if (threadIdx.x < A) atomicAdd(&dlogstd[threadIdx.x], s_dl[threadIdx.x]);
+  if (threadIdx.x < 4) atomicAdd(&stats[threadIdx.x], s_st[threadIdx.x]);
+}
+// clipped value loss: c = max((v-R)^2, (v_old + clip(v - v_old, +-e) - R)^2); dv = scale * dc/dv.  stats[0] += sum c
+__global__ void k_ppo_value_loss(const float* __restrict__ v, const float* __restrict__ v_old, const float* __restrict__ ret, int M,
+                                 float e_clip, int clip_value, float scale, float* __restrict__ dv, float* __restrict__ stats) {
+  __shared__ float s;
+  if (threadIdx.x == 0) s = 0.0f;
+  __syncthreads();
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < M) {
+    float vn = v[e], vo = v_old[e], r = ret[e];
+    float l1 = (vn - r) * (vn - r), g = 2.0f * (vn - r), c = l1;
+    if (clip_value) {
+      float d = vn - vo, dc = fminf(fmaxf(d, -e_clip), e_clip);
+      float vc = vo + dc, l2 = (vc - r) * (vc - r);
+      if (l2 > l1) { c = l2; g = (d > -e_clip && d < e_clip) ? 2.0f * (vc - r) : 0.0f; }
+    }
+    dv[e] = g * scale;
+    atomicAdd(&s, c);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(&stats[0], s);
+}
+__global__ void k_moments(const float* __restrict__ x, size_t n, double* __restrict__ out) {
+  __shared__ double sh[2][32];
+  double s = 0.0, q = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { double v = x[i]; s += v; q += v * v; }
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[0][threadIdx.x] : 0.0; q = threadIdx.x < (blockDim.x >> 5) ? sh[1][threadIdx.x] : 0.0;
+    for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (threadIdx.x == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], q); }
+  }
+}
+// (x - mean) / (std + 1e-8) with mean/std from sums over `count` samples (unbiased std like torch.std; RGC:1651)
+__global__ void k_normalize(float* __restrict__ x, size_t n, const double* __restrict__ mom, double count) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double mean = mom[0] / count, var = (mom[1] - count * mean * mean) / (count - 1.0);
+  float sd = (float)sqrt(var > 0.0 ? var : 0.0);
+  x[i] = (x[i] - (float)mean) / (sd + 1e-8f);
+}
+// per-column sum / sum of squares of x [B, D] into colmom [2][D] (double)
+__global__ void k_col_moments(const float* __restrict__ x, int B, int D, double* __restrict__ colmom) {
+  int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  int lane_r = threadIdx.x >> 5, nr = blockDim.x >> 5;
+  double s = 0.0, q = 0.0;
+  if (c < D)
+    for (int r = blockIdx.y * nr + lane_r; r < B; r += gridDim.y * nr) { double v = x[(size_t)r * D + c]; s += v; q += v * v; }
+  if (c < D) { atomicAdd(&colmom[c], s); atomicAdd(&colmom[D + c], q); }
+}
+// rl_games RunningMeanStd merge (parallel-variance): running (mean, var, count) with the batch moments
+__global__ void k_rms_merge(float* __restrict__ mean, float* __restrict__ var, double* __restrict__ count, const double* __restrict__ colmom,
+                            int D, double bcount) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  double bm = colmom[c] / bcount, bv = (colmom[D + c] - bcount * bm * bm) / (bcount - 1.0);
+  double cnt = *count, tot = cnt + bcount, delta = bm - (double)mean[c];
+  double m2 = (double)var[c] * cnt + bv * bcount + delta * delta * cnt * bcount / tot;
+  mean[c] = (float)((double)mean[c] + delta * bcount / tot);
+  var[c] = (float)(m2 / tot);
+}
+__global__ void k_add_count(double* count, double b) { *count += b; }
+
+extern "C" int sdx_ppo_sample(const float* mu, const float* logstd, int M, int A, uint64_t seed, uint32_t counter, float* actions, float* neglogp, void* stream) {
+  k_ppo_sample<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, logstd, M, A, seed, counter, actions, neglogp);
+  PCK(cudaGetLastError()); return 0;
+}
+extern "C" int sdx_ppo_actor_loss(const float* mu, const float* logstd, const float* actions, const float* old_mu, const float* old_logstd,
+                                  const float* old_neglogp, const float* adv, int M, int A, float e_clip, float bounds_coef, float inv_batch,
+                                  float* dmu, float* dlogstd, float* stats, void* stream) {
+  if (A > 32) { sdx_set_error("sdx_ppo_actor_loss: at most 32 actions"); return -1; }
+  k_ppo_actor_loss<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, logstd, actions, old_mu, old_logstd, old_neglogp, adv, M, A, e_clip, bounds_coef,
+                                                                         inv_batch, dmu, dlogstd, stats);
+  PCK(cudaGetLastError()); return 0;
+}
+extern "C" int sdx_ppo_value_loss(const float* v, const float* v_old, const float* ret, int M, float e_clip, int clip_value, float scale, float* dv,
+                                  float* stats, void* stream) {
+  k_ppo_value_loss<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, v_old, ret, M, e_clip, clip_value, scale, dv, stats);
+  PCK(cudaGetLastError()); return 0;
+}
+// mom: double[2] device scratch (zeroed here).  After the call x is normalised in place (count = n unless n_total given for DP).
+extern "C" int sdx_moments(const float* x, int64_t n, double* mom, void* stream) {
+  PCK(cudaMemsetAsync(mom, 0, 16, (cudaStream_t)stream));
+  k_moments<<<296, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, mom);
+  PCK(cudaGetLastError()); return 0;
+}
+extern "C" int sdx_normalize(float* x, int64_t n, const double* mom, double count, void* stream) {
+  k_normalize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, mom, count);
+  PCK(cudaGetLastError()); return 0;
+}
+extern "C" int sdx_col_moments(const float* x, int B, int D, double* colmom, void* stream) {
+  PCK(cudaMemsetAsync(colmom, 0, (size_t)2 * D * 8, (cudaStream_t)stream));
+  dim3 grd((D + 31) / 32, 64);
+  k_col_moments<<<grd, 256, 0, (cudaStream_t)stream>>>(x, B, D, colmom);
+  PCK(cudaGetLastError()); return 0;
+}
+extern "C" int sdx_rms_merge(float* mean, float* var, double* count, const double* colmom, int D, double bcount, void* stream) {
+  k_rms_merge<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, var, count, colmom, D, bcount);
+  k_add_count<<<1, 1, 0, (cudaStream_t)stream>>>(count, bcount);
+  PCK(cudaGetLastError()); return 0;
 }

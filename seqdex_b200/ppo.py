@@ -1,0 +1,299 @@
+"""PPO with rl_games 1.5.2 semantics (continuous_a2c_logstd + asymmetric central value;
+cfg/lego/ppo_continuous_grasp.yaml) on top of the CUDA kernels of csrc/sdx_ppo.cu:
+every dense contraction is the tcgen05 GEMM, every elementwise PPO op a fused kernel.  This module only
+sequences launches (the role rl_games' A2CAgent.play_steps / train_epoch plays; restated in-tree at
+utils/rl_games_custom.py RGC:1394-1483, 1621-1683, 1767-1911) and owns no math of its own.
+
+Multi-GPU: envs are sharded over ranks; the ONLY data-path collectives are one all-reduce of the flat fp32
+gradient vector per optimiser step, one of the advantage moments per iteration, one of the RunningMeanStd
+column moments per iteration and one scalar (KL) per mini-epoch, all through torch.distributed (NCCL).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _View:
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class MLP:
+    """in -> 1024 -> 512 -> 256 -> out, ELU (cfg/lego/ppo_continuous_grasp.yaml:21-23): fp32 master params,
+    bf16 tensor-core compute.  ``params`` / ``grads`` are flat fp32 views in torch state_dict order."""
+
+    def __init__(self, in_dim, out_dim, max_rows, has_sigma=False, device=0, seed=0):
+        self.L = _lib.load()
+        self.in_dim, self.out_dim, self.max_rows, self.has_sigma = in_dim, out_dim, max_rows, has_sigma
+        self.device = torch.device("cuda", device)
+        self.h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.sdx_mlp_create(in_dim, out_dim, max_rows, int(has_sigma), ctypes.byref(self.h)))
+            n = ctypes.c_int64()
+            pp, pg, po, pm, pv = (ctypes.c_void_p() for _ in range(5))
+            _lib.check(self.L.sdx_mlp_info(self.h, ctypes.byref(n), ctypes.byref(pp), ctypes.byref(pg), ctypes.byref(po),
+                                           ctypes.byref(pm), ctypes.byref(pv)))
+            self.nparams = n.value
+            mk = lambda p, shp: torch.as_tensor(_View(p.value, shp), device=self.device)
+            self.params, self.grads = mk(pp, [self.nparams]), mk(pg, [self.nparams])
+            self.adam_m, self.adam_v = mk(pm, [self.nparams]), mk(pv, [self.nparams])
+            self.out = mk(po, [max_rows, out_dim])
+        self.dims = [in_dim, 1024, 512, 256, out_dim]
+        self.init_default(seed)
+
+    def close(self):
+        if self.h:
+            self.L.sdx_mlp_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def slices(self):
+        """[(name, offset, shape)] of the flat parameter vector (torch state_dict order)"""
+        out, off = [], 0
+        for l in range(4):
+            o, i = self.dims[l + 1], self.dims[l]
+            out.append((f"W{l}", off, (o, i))); off += o * i
+            out.append((f"b{l}", off, (o,))); off += o
+        if self.has_sigma:
+            out.append(("sigma", off, (self.out_dim,))); off += self.out_dim
+        assert off == self.nparams
+        return out
+
+    def init_default(self, seed=0):
+        """rl_games 'default' initialiser = torch.nn.Linear's (U(-1/sqrt(in), 1/sqrt(in)) for W and b); sigma const 0"""
+        g = torch.Generator().manual_seed(seed)
+        flat = torch.zeros(self.nparams)
+        for name, off, shp in self.slices():
+            if name == "sigma":
+                continue
+            fan_in = self.dims[int(name[1])]
+            n = int(torch.tensor(shp).prod())
+            flat[off:off + n] = (torch.rand(n, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        self.load_flat(flat)
+
+    def load_flat(self, flat):
+        self.params.copy_(flat.to(self.device, torch.float32))
+        self.sync()
+
+    def sync(self):
+        _lib.check(self.L.sdx_mlp_sync(self.h, _stream()))
+
+    def forward(self, x, mean=None, var=None, train=False):
+        M = x.shape[0]
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.in_dim
+        _lib.check(self.L.sdx_mlp_forward(self.h, _p(x), M, _p(mean), _p(var), int(train), _stream()))
+        return self.out[:M]
+
+    def backward(self, dout):
+        assert dout.is_contiguous() and dout.dtype == torch.float32
+        _lib.check(self.L.sdx_mlp_backward(self.h, _p(dout), dout.shape[0], _stream()))
+
+    def adam(self, lr, max_norm=1.0, b1=0.9, b2=0.999, eps=1e-8):
+        _lib.check(self.L.sdx_mlp_adam(self.h, ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
+                                       ctypes.c_float(max_norm), _stream()))
+
+    def torch_reference(self):
+        """plain fp32 torch modules holding the same parameters (tests / checkpoint export)"""
+        layers = []
+        sl = {n: (o, s) for n, o, s in self.slices()}
+        for l in range(4):
+            lin = torch.nn.Linear(self.dims[l], self.dims[l + 1]).to(self.device)
+            o, s = sl[f"W{l}"]
+            lin.weight.data.copy_(self.params[o:o + s[0] * s[1]].view(s))
+            o, s = sl[f"b{l}"]
+            lin.bias.data.copy_(self.params[o:o + s[0]])
+            layers.append(lin)
+            if l < 3:
+                layers.append(torch.nn.ELU())
+        return torch.nn.Sequential(*layers)
+
+
+class PPOConfig:
+    """cfg/lego/ppo_continuous_grasp.yaml:30-95 (minibatch_size defaults to a sane value instead of the yaml's 4,
+    SURVEY.md section 7 'hard parts'; pass minibatch_size=4 to honour the yaml literally)"""
+
+    def __init__(self, **kw):
+        self.gamma, self.tau = 0.99, 0.95
+        self.learning_rate, self.cv_learning_rate = 3e-4, 1e-3
+        self.grad_norm, self.e_clip, self.clip_value = 1.0, 0.1, True
+        self.horizon_length, self.mini_epochs, self.cv_mini_epochs = 8, 5, 5
+        self.minibatch_size = 16384
+        self.kl_threshold, self.bounds_loss_coef = 0.02, 0.001
+        self.normalize_advantage, self.cv_normalize_input = True, True
+        self.lr_schedule = "adaptive"
+        self.seed = 22
+        for k, v in kw.items():
+            if not hasattr(self, k):
+                raise KeyError(k)
+            setattr(self, k, v)
+
+
+class A2CAgent:
+    """the calls rl_games' Runner makes on its agent: play_steps() + train_epoch() (= train() loop body)."""
+
+    def __init__(self, vec_env, cfg: PPOConfig | None = None, device=0, dist_group=None):
+        self.env, self.cfg = vec_env, cfg or PPOConfig()
+        c = self.cfg
+        self.device = torch.device("cuda", device)
+        self.N = vec_env.num_envs
+        self.H = c.horizon_length
+        self.B = self.N * self.H
+        self.mb = min(c.minibatch_size, self.B)
+        assert self.B % self.mb == 0, "batch must be a multiple of the minibatch"
+        self.A, self.obs_dim, self.state_dim = vec_env.num_actions, vec_env.num_obs, vec_env.num_states
+        rows = max(self.N, self.mb)
+        self.L = _lib.load()
+        self.actor = MLP(self.obs_dim, self.A, rows, has_sigma=True, device=device, seed=c.seed)
+        self.cv = MLP(self.state_dim, 1, rows, has_sigma=False, device=device, seed=c.seed + 1)
+        self.dist = dist_group
+        self.world = torch.distributed.get_world_size() if dist_group is not None else 1
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=self.device, dtype=dt)
+        H, N, A = self.H, self.N, self.A
+        self.b_obs, self.b_states = z(H, N, self.obs_dim), z(H, N, self.state_dim)
+        self.b_actions, self.b_mu = z(H, N, A), z(H, N, A)
+        self.b_neglogp, self.b_values, self.b_rewards, self.b_dones = z(H, N), z(H, N), z(H, N), z(H, N)
+        self.b_adv, self.b_returns = z(H, N), z(H, N)
+        self.old_logstd = z(self.B // self.mb, A)
+        self.dmu, self.dv = z(self.mb, A), z(self.mb, 1)
+        self.stats, self.cv_stats = z(4), z(4)
+        self.mom = torch.zeros(2, device=self.device, dtype=torch.float64)
+        self.colmom = torch.zeros(2 * self.state_dim, device=self.device, dtype=torch.float64)
+        self.rms_mean, self.rms_var = z(self.state_dim), torch.ones(self.state_dim, device=self.device)
+        self.rms_count = torch.full((1,), 1e-4, device=self.device, dtype=torch.float64)
+        self.last_lr = c.learning_rate
+        self.dones = torch.zeros(N, device=self.device)
+        self.obs = None
+        self.sample_counter = 0
+        self.epoch_num = 0
+        self.last_kl = 0.0
+
+    @property
+    def logstd(self):
+        return self.actor.params[self.actor.nparams - self.A:]
+
+    # ---- rollout (RGC:1394-1483)
+    def get_action_values(self, obs, states):
+        mu = self.actor.forward(obs)
+        t = self.sample_counter
+        self.sample_counter += 1
+        return mu, t
+
+    def play_steps(self):
+        if self.obs is None:
+            self.obs = self.env.reset()
+        L, A, N = self.L, self.A, self.N
+        for t in range(self.H):
+            obs, states = self.obs["obs"], self.obs["states"]
+            self.b_obs[t].copy_(obs)
+            self.b_states[t].copy_(states)
+            self.b_dones[t].copy_(self.dones)
+            mu = self.actor.forward(self.b_obs[t])
+            self.b_mu[t].copy_(mu)
+            _lib.check(L.sdx_ppo_sample(_p(self.b_mu[t]), _p(self.logstd), N, A, ctypes.c_uint64(self.cfg.seed), self.sample_counter,
+                                        _p(self.b_actions[t]), _p(self.b_neglogp[t]), _stream()))
+            self.sample_counter += 1
+            v = self.cv.forward(self.b_states[t], self.rms_mean if self.cfg.cv_normalize_input else None,
+                                self.rms_var if self.cfg.cv_normalize_input else None)
+            self.b_values[t].copy_(v.view(-1))
+            self.obs, rew, dones, _ = self.env.step(self.b_actions[t])
+            self.b_rewards[t].copy_(rew)
+            self.dones = dones.float()
+        v = self.cv.forward(self.obs["states"].contiguous(), self.rms_mean if self.cfg.cv_normalize_input else None,
+                            self.rms_var if self.cfg.cv_normalize_input else None)
+        last_values = v.view(-1).clone()
+        _lib.check(L.sdx_gae(_p(self.b_rewards), _p(self.b_values), _p(self.b_dones), _p(last_values), _p(self.dones), _p(self.b_adv),
+                             _p(self.b_returns), self.H, N, ctypes.c_float(self.cfg.gamma), ctypes.c_float(self.cfg.tau), _stream()))
+
+    def _allreduce(self, t, avg=True):
+        if self.dist is not None and self.world > 1:
+            torch.distributed.all_reduce(t, group=self.dist)
+            if avg:
+                t.div_(self.world)
+
+    # ---- update (RGC:1621-1683, 1339-1375, 1767-1911)
+    def train_epoch(self):
+        c, L, A, B, mb = self.cfg, self.L, self.A, self.B, self.mb
+        self.play_steps()
+        Btot = B * self.world
+        obs, states = self.b_obs.view(B, -1), self.b_states.view(B, -1)
+        actions, mu_old, nlp_old = self.b_actions.view(B, A), self.b_mu.view(B, A), self.b_neglogp.view(B)
+        values, returns = self.b_values.view(B), self.b_returns.view(B)
+        adv = (self.b_returns - self.b_values).view(B).contiguous()
+        if c.normalize_advantage:                       # (adv - mean) / (std + 1e-8) over the GLOBAL batch (RGC:1651)
+            _lib.check(L.sdx_moments(_p(adv), B, _p(self.mom), _stream()))
+            self._allreduce(self.mom, avg=False)
+            _lib.check(L.sdx_normalize(_p(adv), B, _p(self.mom), ctypes.c_double(Btot), _stream()))
+        if c.cv_normalize_input:                        # RunningMeanStd of the critic state, merged once per iteration
+            _lib.check(L.sdx_col_moments(_p(states), B, self.state_dim, _p(self.colmom), _stream()))
+            self._allreduce(self.colmom, avg=False)
+            _lib.check(L.sdx_rms_merge(_p(self.rms_mean), _p(self.rms_var), _p(self.rms_count), _p(self.colmom), self.state_dim,
+                                       ctypes.c_double(Btot), _stream()))
+        nmb = B // mb
+        inv = 1.0 / float(mb)
+        # central value network (asymmetric critic), own optimiser lr 1e-3
+        for _ in range(c.cv_mini_epochs):
+            for i in range(nmb):
+                s = slice(i * mb, (i + 1) * mb)
+                v = self.cv.forward(states[s], self.rms_mean if c.cv_normalize_input else None,
+                                    self.rms_var if c.cv_normalize_input else None, train=True)
+                _lib.check(L.sdx_ppo_value_loss(_p(v), _p(values[s]), _p(returns[s]), mb, ctypes.c_float(c.e_clip), int(c.clip_value),
+                                                ctypes.c_float(inv), _p(self.dv), _p(self.cv_stats), _stream()))
+                self.cv.backward(self.dv)
+                self._allreduce(self.cv.grads)
+                self.cv.adam(c.cv_learning_rate, c.grad_norm)
+        # actor
+        self.old_logstd.copy_(self.logstd.unsqueeze(0).expand(nmb, A))
+        for ep in range(c.mini_epochs):
+            self.stats.zero_()
+            for i in range(nmb):
+                s = slice(i * mb, (i + 1) * mb)
+                mu = self.actor.forward(obs[s], train=True)
+                self.actor.grads[self.actor.nparams - A:].zero_()
+                _lib.check(L.sdx_ppo_actor_loss(_p(mu), _p(self.logstd), _p(actions[s]), _p(mu_old[s]), _p(self.old_logstd[i]), _p(nlp_old[s]),
+                                                _p(adv[s]), mb, A, ctypes.c_float(c.e_clip), ctypes.c_float(c.bounds_loss_coef),
+                                                ctypes.c_float(inv), _p(self.dmu), _p(self.actor.grads[self.actor.nparams - A:]),
+                                                _p(self.stats), _stream()))
+                mu_old[s].copy_(mu)                                  # dataset.update_mu_sigma (RGC:1358)
+                self.old_logstd[i].copy_(self.logstd)
+                self.actor.backward(self.dmu)
+                self._allreduce(self.actor.grads)
+                self.actor.adam(self.last_lr, c.grad_norm)
+            st = self.stats.clone()
+            self._allreduce(st)
+            kl = float(st[2]) / B                                     # one host sync per mini-epoch, like rl_games' av_kls
+            self.last_kl = kl
+            if c.lr_schedule == "adaptive":                          # RGC:1369-1374
+                if kl > 2.0 * c.kl_threshold:
+                    self.last_lr = max(self.last_lr / 1.5, 1e-6)
+                if kl < 0.5 * c.kl_threshold:
+                    self.last_lr = min(self.last_lr * 1.5, 1e-2)
+        self.epoch_num += 1
+        return {"kl": self.last_kl, "lr": self.last_lr, "a_loss": float(st[0]) / B, "b_loss": float(st[1]) / B,
+                "mean_reward": float(self.b_rewards.mean())}
+
+    # ---- checkpoint (rl_games .pth layout: {'model': state_dict, ...}; RGC:1913-1933)
+    def state_dict(self):
+        sd = {}
+        for name, off, shp in self.actor.slices():
+            n = int(torch.tensor(shp).prod())
+            key = {"W": "a2c_network.actor_mlp.{}.weight", "b": "a2c_network.actor_mlp.{}.bias"}.get(name[0])
+            if name == "sigma":
+                sd["a2c_network.sigma"] = self.actor.params[off:off + n].clone()
+            elif int(name[1]) < 3:
+                sd[key.format(2 * int(name[1]))] = self.actor.params[off:off + n].view(shp).clone()
+            else:
+                sd["a2c_network.mu." + ("weight" if name[0] == "W" else "bias")] = self.actor.params[off:off + n].view(shp).clone()
+        return {"model": sd, "epoch": self.epoch_num, "last_lr": self.last_lr,
+                "central_val": self.cv.params.clone(), "running_mean_std": (self.rms_mean.clone(), self.rms_var.clone(), self.rms_count.clone())}

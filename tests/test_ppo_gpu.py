@@ -1,0 +1,194 @@
+"""PPO tensor path (csrc/sdx_ppo.cu via seqdex_b200.ppo) against plain PyTorch fp32 references of the same ops
+(rl_games 1.5.2 formulas).  bf16 tensor-core compute -> tolerances: forward 2e-2 relative to the
+output scale, gradients: relative Frobenius error < 3e-2 and cosine > 0.999; fp32 elementwise kernels: 1e-5."""
+import ctypes
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _relerr(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+@pytest.mark.parametrize("in_dim,out_dim,M", [(396, 23, 1024), (564, 1, 640)])
+def test_mlp_forward_backward_vs_torch(in_dim, out_dim, M):
+    from seqdex_b200.ppo import MLP
+    torch.manual_seed(0)
+    m = MLP(in_dim, out_dim, 2048, has_sigma=(out_dim > 1), seed=3)
+    ref = m.torch_reference()
+    x = torch.randn(M, in_dim, device="cuda").clamp(-5, 5)
+    out = m.forward(x, train=True).clone()
+    xr = x.clone().requires_grad_(False)
+    out_ref = ref(xr)
+    scale = float(out_ref.abs().mean())
+    assert float((out - out_ref).abs().max()) < 3e-2 * max(scale, 1.0), (float((out - out_ref).abs().max()), scale)
+    dout = torch.randn(M, out_dim, device="cuda") / M
+    m.backward(dout.contiguous())
+    torch.cuda.synchronize()
+    out_ref.backward(dout)
+    gref = torch.cat([p.grad.reshape(-1) for lin in ref if isinstance(lin, torch.nn.Linear) for p in (lin.weight, lin.bias)])
+    n = gref.numel()
+    g = m.grads[:n]
+    assert torch.isfinite(g).all()
+    cos = float(torch.nn.functional.cosine_similarity(g, gref, dim=0))
+    assert cos > 0.999 and _relerr(g, gref) < 3e-2, (cos, _relerr(g, gref))
+    for name, off, shp in m.slices():     # every layer individually (a wrong bias column would hide in the global norm)
+        if name == "sigma":
+            continue
+        k = int(torch.tensor(shp).prod())
+        assert _relerr(g[off:off + k], gref[off:off + k]) < 6e-2, (name, _relerr(g[off:off + k], gref[off:off + k]))
+
+
+def test_mlp_input_normalisation():
+    from seqdex_b200.ppo import MLP
+    torch.manual_seed(1)
+    m = MLP(564, 1, 512, seed=5)
+    x = torch.randn(256, 564, device="cuda") * 3 + 1
+    mean, var = torch.randn(564, device="cuda"), torch.rand(564, device="cuda") + 0.5
+    out = m.forward(x, mean, var).clone()
+    xn = ((x - mean) / torch.sqrt(var + 1e-5)).clamp(-5, 5)
+    ref = m.torch_reference()(xn)
+    assert float((out - ref).abs().max()) < 3e-2 * max(float(ref.abs().mean()), 1.0)
+
+
+def test_adam_matches_torch():
+    from seqdex_b200.ppo import MLP
+    m = MLP(396, 23, 256, has_sigma=True, seed=7)
+    p0 = m.params.clone()
+    tp = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([tp], lr=3e-4, eps=1e-8)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for _ in range(3):
+        grad = torch.randn(m.nparams, device="cuda", generator=g) * 0.01
+        m.grads.copy_(grad)
+        m.adam(3e-4, max_norm=1.0)
+        tp.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([tp], 1.0)
+        opt.step()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(m.params, tp.data, rtol=1e-5, atol=1e-7)
+
+
+def test_actor_loss_kernel_vs_torch():
+    from seqdex_b200 import _lib
+    L = _lib.load()
+    torch.manual_seed(2)
+    M, A, eclip, bc = 1000, 23, 0.1, 0.001
+    mu = (torch.randn(M, A, device="cuda") * 0.8).requires_grad_(True)
+    logstd = (torch.randn(A, device="cuda") * 0.1).requires_grad_(True)
+    old_mu = mu.detach() + torch.randn(M, A, device="cuda") * 0.05
+    old_logstd = logstd.detach() + 0.02
+    actions = old_mu + torch.exp(old_logstd) * torch.randn(M, A, device="cuda")
+    adv = torch.randn(M, device="cuda")
+
+    def neglogp(a, m_, ls):
+        return 0.5 * (((a - m_) / torch.exp(ls)) ** 2).sum(-1) + 0.5 * A * math.log(2 * math.pi) + ls.sum()
+    old_nlp = neglogp(actions, old_mu, old_logstd)
+    nlp = neglogp(actions, mu, logstd)
+    ratio = torch.exp(old_nlp - nlp)
+    a_loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 1 - eclip, 1 + eclip))
+    b_loss = (torch.clamp_min(mu - 1.1, 0) ** 2 + torch.clamp_max(mu + 1.1, 0) ** 2).sum(-1)
+    loss = a_loss.mean() + bc * b_loss.mean()
+    loss.backward()
+    sig, so = torch.exp(logstd.detach()), torch.exp(old_logstd)
+    kl = (torch.log(sig / so + 1e-5) + (so ** 2 + (old_mu - mu.detach()) ** 2) / (2 * (sig ** 2 + 1e-5)) - 0.5).sum(-1)
+    dmu, dls, stats = torch.zeros(M, A, device="cuda"), torch.zeros(A, device="cuda"), torch.zeros(4, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(L.sdx_ppo_actor_loss(p(mu.detach().contiguous()), p(logstd.detach()), p(actions), p(old_mu), p(old_logstd), p(old_nlp), p(adv), M, A,
+                                    ctypes.c_float(eclip), ctypes.c_float(bc), ctypes.c_float(1.0 / M), p(dmu), p(dls), p(stats),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dmu, mu.grad, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(dls, logstd.grad, rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(stats[0] / M, a_loss.mean().detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(stats[1] / M, b_loss.mean().detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(stats[2] / M, kl.mean(), rtol=1e-3, atol=1e-6)
+
+
+def test_value_loss_kernel_vs_torch():
+    from seqdex_b200 import _lib
+    L = _lib.load()
+    torch.manual_seed(3)
+    M, eclip = 777, 0.1
+    v = torch.randn(M, device="cuda").requires_grad_(True)
+    vo, r = v.detach() + torch.randn(M, device="cuda") * 0.15, torch.randn(M, device="cuda")
+    vc = vo + (v - vo).clamp(-eclip, eclip)
+    loss = torch.max((v - r) ** 2, (vc - r) ** 2).mean()
+    loss.backward()
+    dv, stats = torch.zeros(M, device="cuda"), torch.zeros(4, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(L.sdx_ppo_value_loss(p(v.detach()), p(vo), p(r), M, ctypes.c_float(eclip), 1, ctypes.c_float(1.0 / M), p(dv), p(stats),
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dv, v.grad, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(stats[0] / M, loss.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_sampling_and_moments():
+    from seqdex_b200 import _lib
+    L = _lib.load()
+    M, A = 20000, 23
+    mu = torch.randn(M, A, device="cuda")
+    logstd = torch.full((A,), -0.3, device="cuda")
+    act, nlp = torch.zeros(M, A, device="cuda"), torch.zeros(M, device="cuda")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(L.sdx_ppo_sample(p(mu), p(logstd), M, A, ctypes.c_uint64(5), 11, p(act), p(nlp), st))
+    z = (act - mu) / math.exp(-0.3)
+    assert abs(float(z.mean())) < 0.01 and abs(float(z.std()) - 1.0) < 0.01
+    ref = 0.5 * (z ** 2).sum(-1) + 0.5 * A * math.log(2 * math.pi) + float(logstd.sum())
+    torch.testing.assert_close(nlp, ref, rtol=1e-5, atol=1e-4)
+    x = torch.randn(100000, device="cuda") * 3 + 2
+    mom = torch.zeros(2, device="cuda", dtype=torch.float64)
+    xr = (x - x.mean()) / (x.std() + 1e-8)
+    _lib.check(L.sdx_moments(p(x), x.numel(), p(mom), st))
+    _lib.check(L.sdx_normalize(p(x), x.numel(), p(mom), ctypes.c_double(x.numel()), st))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(x, xr, rtol=1e-4, atol=1e-5)
+
+
+def test_running_mean_std_merge():
+    from seqdex_b200 import _lib
+    L = _lib.load()
+    D = 564
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    mean, var = torch.zeros(D, device="cuda"), torch.ones(D, device="cuda")
+    cnt = torch.full((1,), 1e-4, device="cuda", dtype=torch.float64)
+    col = torch.zeros(2 * D, device="cuda", dtype=torch.float64)
+    rm, rv, rc = torch.zeros(D, dtype=torch.float64), torch.ones(D, dtype=torch.float64), 1e-4
+    for i in range(3):
+        x = torch.randn(4096, D, device="cuda") * (i + 1) + i
+        _lib.check(L.sdx_col_moments(p(x), 4096, D, p(col), st))
+        _lib.check(L.sdx_rms_merge(p(mean), p(var), p(cnt), p(col), D, ctypes.c_double(4096), st))
+        xb = x.double().cpu()
+        bm, bv, bc = xb.mean(0), xb.var(0), 4096
+        delta, tot = bm - rm, rc + bc
+        m2 = rv * rc + bv * bc + delta ** 2 * rc * bc / tot
+        rm, rv, rc = rm + delta * bc / tot, m2 / tot, tot
+    torch.cuda.synchronize()
+    torch.testing.assert_close(mean.double().cpu(), rm, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(var.double().cpu(), rv, rtol=1e-4, atol=1e-5)
+
+
+def test_agent_trains_end_to_end(scene):
+    """two PPO iterations on 512 envs through VecTask: finite losses, parameters move, KL small and positive"""
+    from seqdex_b200.ppo import A2CAgent, PPOConfig
+    from seqdex_b200.tasks import BlockAssemblyGraspSim
+    from seqdex_b200.vec_task import RLgamesVecTaskPython
+    from tests.util import lattice_bank
+    cfg = {"env": {"numEnvs": 512, "episodeLength": 150, "actionsMovingAverage": 1.0}, "sim": {"substeps": 2, "physx": {}}, "task": {"randomize": False}}
+    task = BlockAssemblyGraspSim(cfg, heap_bank=lattice_bank(scene, 4))
+    env = RLgamesVecTaskPython(task, "cuda:0")
+    agent = A2CAgent(env, PPOConfig(minibatch_size=2048))
+    p0 = agent.actor.params.clone()
+    for _ in range(2):
+        info = agent.train_epoch()
+        assert all(math.isfinite(v) for v in info.values()), info
+    assert float((agent.actor.params - p0).abs().max()) > 0
+    assert 0 <= info["kl"] < 0.5
+    assert torch.isfinite(agent.b_adv).all() and torch.isfinite(agent.cv.params).all()
