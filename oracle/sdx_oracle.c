@@ -74,8 +74,12 @@ static inline v3 V3(float x, float y, float z) { v3 r = {x, y, z}; return r; }
 static inline v3 vadd(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
 static inline v3 vsub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 vscale(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
-static inline float vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-static inline v3 vcross(v3 a, v3 b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+/* explicit single-rounding FMAs (the CUDA side uses the same fmaf() calls; nothing else is contracted) */
+static inline float vdot(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+static inline v3 vcross(v3 a, v3 b) {
+  return V3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
+}
+static inline v3 vmad(v3 a, float s, v3 b) { return V3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); } /* a*s + b */
 static inline v3 vneg(v3 a) { return V3(-a.x, -a.y, -a.z); }
 
 /* isaacgym.torch_utils.quat_mul (xyzw), same operation order as the public
@@ -99,7 +103,7 @@ static inline q4 qconj(q4 a) { q4 r = {-a.x, -a.y, -a.z, a.w}; return r; }
 static inline v3 qrot(q4 q, v3 b) {
   v3 xyz = V3(q.x, q.y, q.z);
   v3 t = vscale(vcross(xyz, b), 2.0f);
-  return vadd(vadd(b, vscale(t, q.w)), vcross(xyz, t));
+  return vadd(vmad(t, q.w, b), vcross(xyz, t));
 }
 /* rotation matrix (row-major) of a unit quaternion */
 static inline void qmat(q4 q, float* R) {
@@ -111,12 +115,12 @@ static inline void qmat(q4 q, float* R) {
 }
 static inline v3 mcol(const float* R, int k) { return V3(R[k], R[3 + k], R[6 + k]); }
 static inline v3 mmul(const float* R, v3 a) {
-  return V3(R[0] * a.x + R[1] * a.y + R[2] * a.z, R[3] * a.x + R[4] * a.y + R[5] * a.z,
-            R[6] * a.x + R[7] * a.y + R[8] * a.z);
+  return V3(fmaf(R[2], a.z, fmaf(R[1], a.y, R[0] * a.x)), fmaf(R[5], a.z, fmaf(R[4], a.y, R[3] * a.x)),
+            fmaf(R[8], a.z, fmaf(R[7], a.y, R[6] * a.x)));
 }
 static inline v3 mtmul(const float* R, v3 a) {
-  return V3(R[0] * a.x + R[3] * a.y + R[6] * a.z, R[1] * a.x + R[4] * a.y + R[7] * a.z,
-            R[2] * a.x + R[5] * a.y + R[8] * a.z);
+  return V3(fmaf(R[6], a.z, fmaf(R[3], a.y, R[0] * a.x)), fmaf(R[7], a.z, fmaf(R[4], a.y, R[1] * a.x)),
+            fmaf(R[8], a.z, fmaf(R[5], a.y, R[2] * a.x)));
 }
 
 /* sin/cos for |x| < ~100: Cody-Waite reduction by pi/2, cephes sinf/cosf minimax kernels */
@@ -203,8 +207,8 @@ typedef struct {
   uint32_t word;   /* a_body | b_body<<8 | b_shape<<16 | axis<<24 | sign<<26 */
   float w[3];      /* contact point, world */
   float bias;      /* target normal velocity */
-  float den[3];    /* mass-split effective inverse mass along n, t1, t2 */
-  float lam[3];
+  float inv[3];    /* 1 / (mass-split effective inverse mass) along n, t1, t2 */
+  float f[3];      /* total impulse of the contact, world frame: lam_n n + lam_1 t1 + lam_2 t2 */
 } contact_t;
 
 typedef struct {
@@ -220,7 +224,8 @@ typedef struct {
   unsigned char cand[NB + SDX_MAX_RSHAPES][KC]; int ncand[NB + SDX_MAX_RSHAPES];
   contact_t con[SDX_MAX_CONTACTS]; int ncon, ndropped;
   int nb[NBODY]; int nj[SDX_ND];
-  int inc_off[NBODY + 1]; unsigned short inc[2 * SDX_MAX_CONTACTS];
+  /* incidence of body b, in summation order: owner-side contacts [astart,aend) then target-side list (ascending) */
+  int astart[NBODY], aend[NBODY], boff[NBODY + 1]; unsigned short blist[SDX_MAX_CONTACTS];
   v3 linkF[SDX_NL], linkM[SDX_NL];
 } work_t;
 
@@ -236,8 +241,8 @@ static void link_twists(const sdx_scene_t* S, work_t* W) {
     unsigned m = S->link_anc_mask[L];
     for (int j = 0; j < SDX_ND; ++j)
       if (m & (1u << j)) {
-        w = vadd(w, vscale(W->K.ja[j], W->qd[j]));
-        v = vadd(v, vscale(vcross(W->K.ja[j], vsub(W->K.lx[L], W->K.jo[j])), W->qd[j]));
+        w = vmad(W->K.ja[j], W->qd[j], w);
+        v = vmad(vcross(W->K.ja[j], vsub(W->K.lx[L], W->K.jo[j])), W->qd[j], v);
       }
     W->bv[NB + L] = v; W->bw[NB + L] = w;
   }
@@ -415,26 +420,26 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
           else if (depth < 0.0f) bias = depth / h;
           c->bias = bias;
-          c->lam[0] = c->lam[1] = c->lam[2] = 0.0f;
-          c->den[0] = depth; /* scratch: kept for the debug dump, overwritten below */
+          c->f[0] = c->f[1] = c->f[2] = 0.0f;
+          c->inv[0] = depth; /* scratch: kept for the debug dump, overwritten below */
         }
       }
     }
-    /* 5. incidence (CSR in contact order) + mass-splitting counts */
-    for (int b = 0; b < NBODY; ++b) W->nb[b] = 0;
+    /* 5. incidence + mass-splitting counts.  Contacts are generated owner-major, so the contacts a body OWNS
+     *    are one contiguous range; the contacts in which it is the TARGET are listed in ascending order. */
+    for (int b = 0; b < NBODY; ++b) { W->astart[b] = 0; W->aend[b] = 0; W->nb[b] = 0; }
     for (int i = 0; i < W->ncon; ++i) {
       int a = W->con[i].word & 255, b = (W->con[i].word >> 8) & 255;
-      W->nb[a]++; if (b != STATIC_BODY) W->nb[b]++;
+      if (i == 0 || (int)(W->con[i - 1].word & 255) != a) W->astart[a] = i;
+      W->aend[a] = i + 1;
+      if (b != STATIC_BODY) W->nb[b]++;
     }
-    W->inc_off[0] = 0;
-    for (int b = 0; b < NBODY; ++b) W->inc_off[b + 1] = W->inc_off[b] + W->nb[b];
+    W->boff[0] = 0;
+    for (int b = 0; b < NBODY; ++b) W->boff[b + 1] = W->boff[b] + W->nb[b];
     for (int b = 0; b < NBODY; ++b) {
-      int o = W->inc_off[b];
-      for (int i = 0; i < W->ncon; ++i) {
-        int a = W->con[i].word & 255, bb = (W->con[i].word >> 8) & 255;
-        if (a == b) W->inc[o++] = (unsigned short)(i << 1);
-        else if (bb == b) W->inc[o++] = (unsigned short)((i << 1) | 1);
-      }
+      int o = W->boff[b];
+      for (int i = 0; i < W->ncon; ++i) if ((int)((W->con[i].word >> 8) & 255) == b) W->blist[o++] = (unsigned short)i;
+      W->nb[b] = (W->aend[b] - W->astart[b]) + (W->boff[b + 1] - W->boff[b]);
     }
     for (int j = 0; j < SDX_ND; ++j) {
       int n = 0;
@@ -445,7 +450,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       for (int i = 0; i < W->ncon; ++i) {
         float* o = condump + 8 * i;
         union { uint32_t u; float f; } cv; cv.u = W->con[i].word;
-        o[0] = cv.f; o[1] = W->con[i].w[0]; o[2] = W->con[i].w[1]; o[3] = W->con[i].w[2]; o[4] = W->con[i].den[0];
+        o[0] = cv.f; o[1] = W->con[i].w[0]; o[2] = W->con[i].w[1]; o[3] = W->con[i].w[2]; o[4] = W->con[i].inv[0];
         o[5] = W->con[i].bias; o[6] = 0.0f; o[7] = 0.0f;
       }
     for (int i = 0; i < W->ncon; ++i) {
@@ -453,9 +458,9 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       int a = c->word & 255, b = (c->word >> 8) & 255;
       v3 n, t1, t2; contact_axes(W, c, &n, &t1, &t2);
       v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
-      c->den[0] = body_k(S, W, a, wpt, n) + body_k(S, W, b, wpt, n);
-      c->den[1] = body_k(S, W, a, wpt, t1) + body_k(S, W, b, wpt, t1);
-      c->den[2] = body_k(S, W, a, wpt, t2) + body_k(S, W, b, wpt, t2);
+      c->inv[0] = 1.0f / (body_k(S, W, a, wpt, n) + body_k(S, W, b, wpt, n));
+      c->inv[1] = 1.0f / (body_k(S, W, a, wpt, t1) + body_k(S, W, b, wpt, t1));
+      c->inv[2] = 1.0f / (body_k(S, W, a, wpt, t2) + body_k(S, W, b, wpt, t2));
     }
     /* 6. mass-splitting Jacobi iterations on the total impulses */
     for (int it = 0; it < S->iters; ++it) {
@@ -464,29 +469,36 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         int a = c->word & 255, b = (c->word >> 8) & 255;
         v3 n, t1, t2; contact_axes(W, c, &n, &t1, &t2);
         v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
+        v3 f = V3(c->f[0], c->f[1], c->f[2]);
         v3 vrel = vadd(W->bv[a], vcross(W->bw[a], vsub(wpt, W->bx[a])));
         if (b != STATIC_BODY) vrel = vsub(vrel, vadd(W->bv[b], vcross(W->bw[b], vsub(wpt, W->bx[b]))));
-        float ln = c->lam[0] + (c->bias - vdot(vrel, n)) / c->den[0];
+        float ln = fmaf(c->bias - vdot(vrel, n), c->inv[0], vdot(f, n));
         ln = ln > 0.0f ? ln : 0.0f;
         float lim = S->friction * ln;
-        float l1 = clampf(c->lam[1] - vdot(vrel, t1) / c->den[1], -lim, lim);
-        float l2 = clampf(c->lam[2] - vdot(vrel, t2) / c->den[2], -lim, lim);
-        c->lam[0] = ln; c->lam[1] = l1; c->lam[2] = l2;
+        float l1 = clampf(fmaf(-vdot(vrel, t1), c->inv[1], vdot(f, t1)), -lim, lim);
+        float l2 = clampf(fmaf(-vdot(vrel, t2), c->inv[2], vdot(f, t2)), -lim, lim);
+        f = vmad(t2, l2, vmad(t1, l1, vscale(n, ln)));
+        c->f[0] = f.x; c->f[1] = f.y; c->f[2] = f.z;
       }
-      for (int b = 0; b < NBODY; ++b) { /* phase B: one body each, incident contacts in order */
-        v3 F = V3(0, 0, 0), T = V3(0, 0, 0);
-        for (int e = W->inc_off[b]; e < W->inc_off[b + 1]; ++e) {
-          const contact_t* c = &W->con[W->inc[e] >> 1];
-          v3 n, t1, t2; contact_axes(W, c, &n, &t1, &t2);
-          v3 f = vadd(vadd(vscale(n, c->lam[0]), vscale(t1, c->lam[1])), vscale(t2, c->lam[2]));
-          if (W->inc[e] & 1) f = vneg(f);
+      for (int b = 0; b < NBODY; ++b) { /* phase B: one body each; 4 strided partial sums, combined (0+1)+(2+3) */
+        v3 Fk[4], Tk[4];
+        for (int k = 0; k < 4; ++k) { Fk[k] = V3(0, 0, 0); Tk[k] = V3(0, 0, 0); }
+        int na = W->aend[b] - W->astart[b], nbl = W->boff[b + 1] - W->boff[b];
+        v3 xb = b < NB ? W->bx[b] : V3(0, 0, 0);
+        for (int e = 0; e < na + nbl; ++e) {
+          int i = e < na ? W->astart[b] + e : W->blist[W->boff[b] + (e - na)];
+          const contact_t* c = &W->con[i];
+          v3 f = V3(c->f[0], c->f[1], c->f[2]);
+          if (e >= na) f = vneg(f);
           v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
-          F = vadd(F, f);
-          if (b < NB) T = vadd(T, vcross(vsub(wpt, W->bx[b]), f));
-          else T = vadd(T, vcross(wpt, f));
+          int k = e & 3;
+          Fk[k] = vadd(Fk[k], f);
+          Tk[k] = vadd(Tk[k], vcross(vsub(wpt, xb), f));
         }
+        v3 F = vadd(vadd(Fk[0], Fk[1]), vadd(Fk[2], Fk[3]));
+        v3 T = vadd(vadd(Tk[0], Tk[1]), vadd(Tk[2], Tk[3]));
         if (b < NB) {
-          W->bv[b] = vadd(W->vfree[b], vscale(F, S->br_invm[b]));
+          W->bv[b] = vmad(F, S->br_invm[b], W->vfree[b]);
           W->bw[b] = vadd(W->wfree[b], brick_Iinv_mul(S, W, b, T));
         } else { W->linkF[b - NB] = F; W->linkM[b - NB] = T; }
       }
@@ -507,7 +519,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       if (w2 > mw * mw) { w = vscale(w, mw / sqrtf(w2)); W->bw[b] = w; }
       float v2 = vdot(v, v), mv = S->max_lin_vel;
       if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); W->bv[b] = v; }
-      W->bx[b] = vadd(W->bx[b], vscale(v, h));
+      W->bx[b] = vmad(v, h, W->bx[b]);
       q4 q = W->bq[b];
       float hh = 0.5f * h;
       q4 dq;

@@ -16,10 +16,12 @@ __device__ __forceinline__ v3 V3(float x, float y, float z) { v3 r; r.x = x; r.y
 __device__ __forceinline__ v3 vadd(v3 a, v3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
 __device__ __forceinline__ v3 vsub(v3 a, v3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
 __device__ __forceinline__ v3 vscale(v3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float vdot(v3 a, v3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+// explicit single-rounding FMAs: with -fmad=false these are the ONLY fused operations in the kernels
+__device__ __forceinline__ float vdot(v3 a, v3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
 __device__ __forceinline__ v3 vcross(v3 a, v3 b) {
-  return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+  return V3(fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)));
 }
+__device__ __forceinline__ v3 vmad(v3 a, float s, v3 b) { return V3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }  // a*s + b
 __device__ __forceinline__ v3 vneg(v3 a) { return V3(-a.x, -a.y, -a.z); }
 
 // quaternion product, xyzw (same operation order as isaacgym.torch_utils.quat_mul)
@@ -43,7 +45,7 @@ __device__ __forceinline__ q4 Q4(float x, float y, float z, float w) { q4 r; r.x
 __device__ __forceinline__ v3 qrot(q4 q, v3 b) {
   v3 xyz = V3(q.x, q.y, q.z);
   v3 t = vscale(vcross(xyz, b), 2.0f);
-  return vadd(vadd(b, vscale(t, q.w)), vcross(xyz, t));
+  return vadd(vmad(t, q.w, b), vcross(xyz, t));
 }
 __device__ __forceinline__ void qmat(q4 q, float* R) {
   float xx = q.x * q.x, yy = q.y * q.y, zz = q.z * q.z, xy = q.x * q.y, xz = q.x * q.z, yz = q.y * q.z,
@@ -54,12 +56,12 @@ __device__ __forceinline__ void qmat(q4 q, float* R) {
 }
 __device__ __forceinline__ v3 mcol(const float* R, int k) { return V3(R[k], R[3 + k], R[6 + k]); }
 __device__ __forceinline__ v3 mmul(const float* R, v3 a) {
-  return V3(R[0] * a.x + R[1] * a.y + R[2] * a.z, R[3] * a.x + R[4] * a.y + R[5] * a.z,
-            R[6] * a.x + R[7] * a.y + R[8] * a.z);
+  return V3(fmaf(R[2], a.z, fmaf(R[1], a.y, R[0] * a.x)), fmaf(R[5], a.z, fmaf(R[4], a.y, R[3] * a.x)),
+            fmaf(R[8], a.z, fmaf(R[7], a.y, R[6] * a.x)));
 }
 __device__ __forceinline__ v3 mtmul(const float* R, v3 a) {
-  return V3(R[0] * a.x + R[3] * a.y + R[6] * a.z, R[1] * a.x + R[4] * a.y + R[7] * a.z,
-            R[2] * a.x + R[5] * a.y + R[8] * a.z);
+  return V3(fmaf(R[6], a.z, fmaf(R[3], a.y, R[0] * a.x)), fmaf(R[7], a.z, fmaf(R[4], a.y, R[1] * a.x)),
+            fmaf(R[8], a.z, fmaf(R[5], a.y, R[2] * a.x)));
 }
 
 // sin/cos: Cody-Waite reduction by pi/2 + cephes minimax kernels (|x| < ~100)

@@ -30,7 +30,7 @@
 #define STATIC_BODY 255
 #define SIM_THREADS 128
 #define ROBOT_TID0 96                  /* warp 3 owns the articulation: lane j = DoF j, lane L = link L */
-#define PPMAX 24                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
+#define PPMAX 26                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
 
 struct SimSmem {
   float tile[13 * NB];                 // TMA landing / staging zone for the brick tile
@@ -38,19 +38,35 @@ struct SimSmem {
   float sc[NT][3], sR[NT][9], sh[NT][3], sa[NT][3], spd[NT], srad[NOWN];
   unsigned char sbody[NT];
   float bx[NBODY][3], bv[NBODY][3], bw[NBODY][3];
+  float vfree[NB][3], wfree[NB][3], binvm[NB], binvI[NB][3];
   float lq[SDX_NL][4], ja[SDX_ND][3], jo[SDX_ND][3];
   float q[SDX_ND + 1], qd[SDX_ND + 1], tgt[SDX_ND + 1], qdfree[SDX_ND + 1], ieff[SDX_ND + 1];
   float linkF[SDX_NL][3], linkM[SDX_NL][3];
   int nb[NBODY], nj[SDX_ND + 1];
-  int inc_off[NBODY + 1];
-  unsigned short inc[2 * MAXC];
+  // incidence of body b in summation order: owned contacts [astart, aend) then the target-side list (ascending)
+  int astart[NBODY], aend[NBODY], boff[NBODY + 1], bcur[NBODY];
+  unsigned short blist[MAXC];
   unsigned char cand[NOWN][KC];
   int ncand[NOWN], poff[NOWN + 1];
   int scan[SIM_THREADS];
   int ncon, ndropped;
   uint32_t cword[MAXC];
-  float cw[3][MAXC], cbias[MAXC], cden[3][MAXC], clam[3][MAXC];
+  float cw[3][MAXC], cbias[MAXC], cinv[3][MAXC], cf[3][MAXC];
 };
+
+// exclusive prefix sum of arr[0..n) (n <= 128) by ONE warp, in place; returns the total to every lane
+__device__ __forceinline__ int warp_excl_scan(int* arr, int n, int lane) {
+  int v[4], s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { int k = lane * 4 + i; v[i] = k < n ? arr[k] : 0; s += v[i]; }
+  int incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  int run = incl - s;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { int k = lane * 4 + i; if (k < n) arr[k] = run; run += v[i]; }
+  return __shfl_sync(0xffffffffu, incl, 31);
+}
 
 __device__ __forceinline__ v3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
 __device__ __forceinline__ void st3(float* p, v3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
@@ -77,16 +93,16 @@ __device__ void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M) {
   }
 }
 
-__device__ __forceinline__ void link_twist(const sdx_scene_t* __restrict__ S, SimSmem& M, int L) {
+__device__ __forceinline__ void link_twist(const sdx_scene_t* __restrict__ S, SimSmem& M, int L, unsigned m) {
   v3 w = V3(0.0f, 0.0f, 0.0f), v = V3(0.0f, 0.0f, 0.0f);
-  unsigned m = S->link_anc_mask[L];
   v3 xl = ld3(M.bx[NB + L]);
-  for (int j = 0; j < SDX_ND; ++j)
-    if (m & (1u << j)) {
-      v3 a = ld3(M.ja[j]);
-      w = vadd(w, vscale(a, M.qd[j]));
-      v = vadd(v, vscale(vcross(a, vsub(xl, ld3(M.jo[j]))), M.qd[j]));
-    }
+  while (m) {                       // ancestors in ascending DoF order
+    int j = __ffs(m) - 1; m &= m - 1;
+    v3 a = ld3(M.ja[j]);
+    float qd = M.qd[j];
+    w = vmad(a, qd, w);
+    v = vmad(vcross(a, vsub(xl, ld3(M.jo[j]))), qd, v);
+  }
   st3(M.bv[NB + L], v); st3(M.bw[NB + L], w);
 }
 
@@ -108,18 +124,16 @@ __device__ float body_k(const sdx_scene_t* __restrict__ S, const SimSmem& M, int
   if (body == STATIC_BODY) return 0.0f;
   if (body < NB) {
     v3 rxd = vcross(vsub(wpt, ld3(M.bx[body])), d);
-    v3 invI = V3(S->br_invI[3 * body], S->br_invI[3 * body + 1], S->br_invI[3 * body + 2]);
-    float k = S->br_invm[body] + vdot(rxd, brick_Iinv_mul(M.sR[body], invI, rxd));
+    float k = M.binvm[body] + vdot(rxd, brick_Iinv_mul(M.sR[body], ld3(M.binvI[body]), rxd));
     return (float)M.nb[body] * k;
   }
-  int L = body - NB;
-  unsigned m = S->link_anc_mask[L];
+  unsigned m = S->link_anc_mask[body - NB];
   float k = 0.0f;
-  for (int j = 0; j < SDX_ND; ++j)
-    if (m & (1u << j)) {
-      float g = vdot(ld3(M.ja[j]), vcross(vsub(wpt, ld3(M.jo[j])), d));
-      k = k + (float)M.nj[j] * (g * g) / M.ieff[j];
-    }
+  while (m) {
+    int j = __ffs(m) - 1; m &= m - 1;
+    float g = vdot(ld3(M.ja[j]), vcross(vsub(wpt, ld3(M.jo[j])), d));
+    k = k + (float)M.nj[j] * (g * g) / M.ieff[j];
+  }
   return k;
 }
 
@@ -221,17 +235,20 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   mbar_wait(&M.mbar, 0);
 
   // brick threads keep their body in registers across the step
-  v3 bxr = V3(0, 0, 0), bvr = V3(0, 0, 0), bwr = V3(0, 0, 0), vfree = V3(0, 0, 0), wfree = V3(0, 0, 0);
+  v3 bxr = V3(0, 0, 0), bvr = V3(0, 0, 0), bwr = V3(0, 0, 0);
   q4 bqr = Q4(0, 0, 0, 1);
-  v3 invI = V3(0, 0, 0), halfb = V3(0, 0, 0);
-  float invm = 0.0f;
+  v3 halfb = V3(0, 0, 0);
+  const unsigned my_anc = (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) ? S->link_anc_mask[tid - ROBOT_TID0] : 0u;
+  unsigned my_desc = 0u;   // DoF threads: links moved by this DoF
+  if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND)
+    for (int L = 0; L < SDX_NL; ++L) if (S->link_anc_mask[L] & (1u << (tid - ROBOT_TID0))) my_desc |= 1u << L;
   if (tid < NB) {
     bxr = V3(M.tile[0 * NB + tid], M.tile[1 * NB + tid], M.tile[2 * NB + tid]);
     bqr = Q4(M.tile[3 * NB + tid], M.tile[4 * NB + tid], M.tile[5 * NB + tid], M.tile[6 * NB + tid]);
     bvr = V3(M.tile[7 * NB + tid], M.tile[8 * NB + tid], M.tile[9 * NB + tid]);
     bwr = V3(M.tile[10 * NB + tid], M.tile[11 * NB + tid], M.tile[12 * NB + tid]);
-    invI = V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]);
-    invm = S->br_invm[tid];
+    st3(M.binvI[tid], V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]));
+    M.binvm[tid] = S->br_invm[tid];
     halfb = V3(S->br_half[3 * tid], S->br_half[3 * tid + 1], S->br_half[3 * tid + 2]);
     st3(M.sh[tid], halfb);
     M.srad[tid] = sqrtf(vdot(halfb, halfb));
@@ -254,10 +271,11 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       st3(M.sc[tid], bxr); st3(M.bx[tid], bxr);
       float damp = 1.0f - h * S->brick_ang_damp;
       float ldamp = 1.0f - h * S->brick_lin_damp;
-      vfree = vscale(V3(bvr.x, bvr.y, bvr.z + h * S->gravity_z), ldamp);
-      wfree = vscale(bwr, damp);
+      v3 vfree = vscale(V3(bvr.x, bvr.y, bvr.z + h * S->gravity_z), ldamp);
+      v3 wfree = vscale(bwr, damp);
       if (tid >= nbr) { vfree = V3(0.0f, 0.0f, 0.0f); wfree = V3(0.0f, 0.0f, 0.0f); }
       st3(M.bv[tid], vfree); st3(M.bw[tid], wfree);
+      st3(M.vfree[tid], vfree); st3(M.wfree[tid], wfree);
     }
     __syncthreads();
     // 2. robot shape poses || implicit PD free joint velocities
@@ -282,7 +300,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     }
     __syncthreads();
     // 3. link twists
-    if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0);
+    if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0, my_anc);
     __syncthreads();
     // 4. world AABBs + per-sub-step travel bound of every moving shape
     if (tid < n_owner) {
@@ -321,10 +339,11 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       if (dropped) atomicAdd(&M.ndropped, dropped);
     }
     __syncthreads();
-    if (tid == 0) {
-      int o = 0;
-      for (int a = 0; a < n_owner; ++a) { M.poff[a] = o; o += M.ncand[a]; }
-      M.poff[n_owner] = o;
+    if (tid < 32) {
+      for (int a = tid; a < n_owner; a += 32) M.poff[a] = M.ncand[a];
+      __syncwarp();
+      int tot = warp_excl_scan(M.poff, n_owner, tid);
+      if (tid == 0) M.poff[n_owner] = tot;
     }
     __syncthreads();
     // 6. narrow phase, pass 1: per-pair hit masks, kept in registers; contiguous pair chunks per thread
@@ -353,12 +372,11 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     // block-wide exclusive scan of per-thread contact counts (thread order == pair order)
     M.scan[tid] = mycount;
     __syncthreads();
-    if (tid == 0) {
-      int o = 0;
-      for (int i = 0; i < SIM_THREADS; ++i) { int c = M.scan[i]; M.scan[i] = o; o += c; }
-      M.ncon = o < MAXC ? o : MAXC;
-      if (o > MAXC) atomicAdd(&M.ndropped, o - MAXC);
+    if (tid < 32) {
+      int o = warp_excl_scan(M.scan, SIM_THREADS, tid);
+      if (tid == 0) { M.ncon = o < MAXC ? o : MAXC; if (o > MAXC) atomicAdd(&M.ndropped, o - MAXC); }
     }
+    if (tid < NBODY) { M.astart[tid] = 0; M.aend[tid] = 0; M.nb[tid] = 0; }
     __syncthreads();
     // pass 2: regenerate the hits and write contacts at their global slots
     {
@@ -384,8 +402,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
             if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
             else if (depth < 0.0f) bias = depth / h;
             M.cbias[slot] = bias;
-            M.clam[0][slot] = 0.0f; M.clam[1][slot] = 0.0f; M.clam[2][slot] = 0.0f;
-            M.cden[0][slot] = depth;
+            M.cf[0][slot] = 0.0f; M.cf[1][slot] = 0.0f; M.cf[2][slot] = 0.0f;
+            M.cinv[0][slot] = depth;
           }
           ++slot;
         }
@@ -394,54 +412,64 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     }
     __syncthreads();
     const int ncon = M.ncon;
-    // 7. incidence lists in contact order (every body thread scans the contact words; broadcast reads)
-    const int mybody = tid < NB ? tid : ((tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) ? NB + (tid - ROBOT_TID0) : -1);
-    if (mybody >= 0) {
-      int c = 0;
-      for (int i = 0; i < ncon; ++i) {
-        uint32_t wd = M.cword[i];
-        int a = wd & 255, b = (wd >> 8) & 255;
-        c += (a == mybody) + (b == mybody);
-      }
-      M.nb[mybody] = c;
+    // 7. incidence: owned contacts of a body are one contiguous range (contacts are generated owner-major);
+    //    target-side contacts go to a per-body list, filled with atomics and then sorted ascending
+    //    (=> the summation order of phase B is fixed, whatever the fill order was)
+    for (int i = tid; i < ncon; i += SIM_THREADS) {
+      uint32_t wd = M.cword[i];
+      int a = wd & 255, b = (wd >> 8) & 255;
+      if (i == 0 || (int)(M.cword[i - 1] & 255) != a) M.astart[a] = i;
+      if (i == ncon - 1 || (int)(M.cword[i + 1] & 255) != a) M.aend[a] = i + 1;
+      if (b != STATIC_BODY) atomicAdd(&M.nb[b], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int o = 0;
-      for (int b = 0; b < NBODY; ++b) { M.inc_off[b] = o; o += M.nb[b]; }
-      M.inc_off[NBODY] = o;
+    if (tid < 32) {
+      for (int b = tid; b < NBODY; b += 32) M.boff[b] = M.nb[b];
+      __syncwarp();
+      int tot = warp_excl_scan(M.boff, NBODY, tid);
+      if (tid == 0) M.boff[NBODY] = tot;
     }
     __syncthreads();
-    if (mybody >= 0) {
-      int o = M.inc_off[mybody];
-      for (int i = 0; i < ncon; ++i) {
-        uint32_t wd = M.cword[i];
-        int a = wd & 255, b = (wd >> 8) & 255;
-        if (a == mybody) M.inc[o++] = (unsigned short)(i << 1);
-        else if (b == mybody) M.inc[o++] = (unsigned short)((i << 1) | 1);
-      }
+    if (tid < NBODY) M.bcur[tid] = M.boff[tid];
+    __syncthreads();
+    for (int i = tid; i < ncon; i += SIM_THREADS) {
+      int b = (M.cword[i] >> 8) & 255;
+      if (b != STATIC_BODY) M.blist[atomicAdd(&M.bcur[b], 1)] = (unsigned short)i;
     }
+    __syncthreads();
+    if (tid < NBODY) {
+      const int o0 = M.boff[tid], o1 = M.boff[tid + 1];
+      for (int i = o0 + 1; i < o1; ++i) {      // insertion sort (lists are short)
+        unsigned short key = M.blist[i];
+        int j = i - 1;
+        while (j >= o0 && M.blist[j] > key) { M.blist[j + 1] = M.blist[j]; --j; }
+        M.blist[j + 1] = key;
+      }
+      M.nb[tid] = (M.aend[tid] - M.astart[tid]) + (o1 - o0);
+    }
+    __syncthreads();
     if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) {
-      int j = tid - ROBOT_TID0, nn = 0;
-      for (int L = 0; L < SDX_NL; ++L) if (S->link_anc_mask[L] & (1u << j)) nn += M.nb[NB + L];
-      M.nj[j] = nn;
+      int nn = 0;
+      unsigned m = my_desc;
+      while (m) { int L = __ffs(m) - 1; m &= m - 1; nn += M.nb[NB + L]; }
+      M.nj[tid - ROBOT_TID0] = nn;
     }
     if (condump && sub == substeps - 1)
       for (int i = tid; i < ncon; i += SIM_THREADS) {
         float* o = condump + ((size_t)e * MAXC + i) * 8;
-        o[0] = __uint_as_float(M.cword[i]); o[1] = M.cw[0][i]; o[2] = M.cw[1][i]; o[3] = M.cw[2][i]; o[4] = M.cden[0][i];
+        o[0] = __uint_as_float(M.cword[i]); o[1] = M.cw[0][i]; o[2] = M.cw[1][i]; o[3] = M.cw[2][i]; o[4] = M.cinv[0][i];
         o[5] = M.cbias[i]; o[6] = 0.0f; o[7] = 0.0f;
       }
     __syncthreads();
-    // 8. mass-split effective inverse masses along n, t1, t2
+    // 8. inverse mass-split effective masses along n, t1, t2
     for (int i = tid; i < ncon; i += SIM_THREADS) {
       uint32_t wd = M.cword[i];
       int a = wd & 255, b = (wd >> 8) & 255;
       v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
       v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
-      M.cden[0][i] = body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n);
-      M.cden[1][i] = body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1);
-      M.cden[2][i] = body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2);
+      M.cinv[0][i] = 1.0f / (body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n));
+      M.cinv[1][i] = 1.0f / (body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1));
+      M.cinv[2][i] = 1.0f / (body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2));
     }
     __syncthreads();
     // 9. Jacobi iterations on total impulses
@@ -452,48 +480,61 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         int a = wd & 255, b = (wd >> 8) & 255;
         v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
         v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
+        v3 f = V3(M.cf[0][i], M.cf[1][i], M.cf[2][i]);
         v3 vrel = vadd(ld3(M.bv[a]), vcross(ld3(M.bw[a]), vsub(wpt, ld3(M.bx[a]))));
         if (b != STATIC_BODY) vrel = vsub(vrel, vadd(ld3(M.bv[b]), vcross(ld3(M.bw[b]), vsub(wpt, ld3(M.bx[b])))));
-        float ln = M.clam[0][i] + (M.cbias[i] - vdot(vrel, n)) / M.cden[0][i];
+        float ln = fmaf(M.cbias[i] - vdot(vrel, n), M.cinv[0][i], vdot(f, n));
         ln = ln > 0.0f ? ln : 0.0f;
         float lim = mu * ln;
-        float l1 = clampf(M.clam[1][i] - vdot(vrel, t1) / M.cden[1][i], -lim, lim);
-        float l2 = clampf(M.clam[2][i] - vdot(vrel, t2) / M.cden[2][i], -lim, lim);
-        M.clam[0][i] = ln; M.clam[1][i] = l1; M.clam[2][i] = l2;
+        float l1 = clampf(fmaf(-vdot(vrel, t1), M.cinv[1][i], vdot(f, t1)), -lim, lim);
+        float l2 = clampf(fmaf(-vdot(vrel, t2), M.cinv[2][i], vdot(f, t2)), -lim, lim);
+        f = vmad(t2, l2, vmad(t1, l1, vscale(n, ln)));
+        M.cf[0][i] = f.x; M.cf[1][i] = f.y; M.cf[2][i] = f.z;
       }
       __syncthreads();
-      if (mybody >= 0) {                                       // phase B: one thread per body
+      // phase B: FOUR lanes per body, lane k sums incidences e = k (mod 4); partials combined (0+1)+(2+3).
+      // warps 0-2: 72 bricks x 4 lanes = 3 passes of 96 threads; warp 3: 24 links x 4 lanes = 3 passes of 32.
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const int item = tid < ROBOT_TID0 ? pass * ROBOT_TID0 + tid : pass * 32 + (tid - ROBOT_TID0);
+        const int body = tid < ROBOT_TID0 ? (item >> 2) : NB + (item >> 2);
+        const int k = item & 3;
+        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = na + (M.boff[body + 1] - b0);
+        const v3 xb = body < NB ? ld3(M.bx[body]) : V3(0.0f, 0.0f, 0.0f);
         v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
-        const int e0 = M.inc_off[mybody], e1 = M.inc_off[mybody + 1];
-        const v3 xb = mybody < NB ? ld3(M.bx[mybody]) : V3(0.0f, 0.0f, 0.0f);
-        for (int ee = e0; ee < e1; ++ee) {
-          int ent = M.inc[ee], i = ent >> 1;
-          v3 n, t1, t2; contact_axes(M, M.cword[i], &n, &t1, &t2);
-          v3 f = vadd(vadd(vscale(n, M.clam[0][i]), vscale(t1, M.clam[1][i])), vscale(t2, M.clam[2][i]));
-          if (ent & 1) f = vneg(f);
+        for (int ee = k; ee < ntot; ee += 4) {
+          const bool own = ee < na;
+          const int i = own ? a0 + ee : (int)M.blist[b0 + (ee - na)];
+          v3 f = V3(M.cf[0][i], M.cf[1][i], M.cf[2][i]);
+          if (!own) f = vneg(f);
           v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
           F = vadd(F, f);
-          if (mybody < NB) T = vadd(T, vcross(vsub(wpt, xb), f));
-          else T = vadd(T, vcross(wpt, f));
+          T = vadd(T, vcross(vsub(wpt, xb), f));
         }
-        if (mybody < NB) {
-          st3(M.bv[mybody], vadd(vfree, vscale(F, invm)));
-          st3(M.bw[mybody], vadd(wfree, brick_Iinv_mul(M.sR[mybody], invI, T)));
-        } else { st3(M.linkF[mybody - NB], F); st3(M.linkM[mybody - NB], T); }
+        F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
+        T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
+        F.x += __shfl_xor_sync(0xffffffffu, F.x, 2); F.y += __shfl_xor_sync(0xffffffffu, F.y, 2); F.z += __shfl_xor_sync(0xffffffffu, F.z, 2);
+        T.x += __shfl_xor_sync(0xffffffffu, T.x, 2); T.y += __shfl_xor_sync(0xffffffffu, T.y, 2); T.z += __shfl_xor_sync(0xffffffffu, T.z, 2);
+        if (k == 0) {
+          if (body < NB) {
+            st3(M.bv[body], vmad(F, M.binvm[body], ld3(M.vfree[body])));
+            st3(M.bw[body], vadd(ld3(M.wfree[body]), brick_Iinv_mul(M.sR[body], ld3(M.binvI[body]), T)));
+          } else { st3(M.linkF[body - NB], F); st3(M.linkM[body - NB], T); }
+        }
       }
       if (tid >= ROBOT_TID0) {                                 // the articulation lives in one warp
         __syncwarp();
         if (tid < ROBOT_TID0 + SDX_ND) {
           int j = tid - ROBOT_TID0;
           v3 Fd = V3(0.0f, 0.0f, 0.0f), Md = V3(0.0f, 0.0f, 0.0f);
-          for (int L = 0; L < SDX_NL; ++L)
-            if (S->link_anc_mask[L] & (1u << j)) { Fd = vadd(Fd, ld3(M.linkF[L])); Md = vadd(Md, ld3(M.linkM[L])); }
+          unsigned m = my_desc;
+          while (m) { int L = __ffs(m) - 1; m &= m - 1; Fd = vadd(Fd, ld3(M.linkF[L])); Md = vadd(Md, ld3(M.linkM[L])); }
           v3 aj = ld3(M.ja[j]);
           float g = vdot(aj, vsub(Md, vcross(ld3(M.jo[j]), Fd)));
           M.qd[j] = M.qdfree[j] + g / M.ieff[j];
         }
         __syncwarp();
-        if (tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0);
+        if (tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0, my_anc);
       }
       __syncthreads();
     }
@@ -506,7 +547,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       float v2 = vdot(v, v), mv = S->max_lin_vel;
       if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); }
       bvr = v; bwr = w;
-      bxr = vadd(bxr, vscale(v, h));
+      bxr = vmad(v, h, bxr);
       q4 q = bqr;
       float hh = 0.5f * h;
       q4 dq;
@@ -544,7 +585,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gbrick), "r"(tile_s), "r"(13 * NB * 4) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
-  if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0);
+  if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0, my_anc);
   if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) { int j = tid - ROBOT_TID0; gdof[j] = M.q[j]; gdof[24 + j] = M.qd[j]; }
   __syncthreads();
   if (tid < SDX_NL) {
