@@ -146,6 +146,10 @@ def main():
     ap.add_argument("--bank-per-type", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
+                    help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
+                         "rollout: VecTask.step only with U(-1,1) actions")
+    ap.add_argument("--minibatch", type=int, default=16384)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -179,16 +183,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    import ctypes
+    from seqdex_b200 import _lib
+    ppo_launch = lambda: int(_lib.load().sdx_ppo_launch_count())
     for i in range(W):
         env.step(acts[i])
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    # ---- (1) rollout only: VecTask.step with actions resident in HBM; per-launch events around the contact step
+    KR = min(K, 64)
     l0 = env.launch_count()
-    sim_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sim_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KR)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(K):
+    for i in range(KR):
         env.pre_physics(acts[W + i])
         sim_ev[i][0].record()
         env.simulate()
@@ -196,9 +205,38 @@ def main():
         env.post_physics()
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
-    launches = env.launch_count() - l0
+    ro_ms = e0.elapsed_time(e1)
+    ro_launches = env.launch_count() - l0
     sim_ms = float(np.mean([a.elapsed_time(b) for a, b in sim_ev]))
+    ms, launches, ppo_info = ro_ms * K / KR, ro_launches * K // KR, None
+    if args.mode == "ppo":
+        # ---- (2) PPO in the loop: the headline.  K env steps = K/8 iterations of play_steps + train_epoch
+        from seqdex_b200.ppo import A2CAgent, PPOConfig
+        from seqdex_b200.vec_task import RLgamesVecTaskPython
+
+        class _Task:      # the task surface VecTask needs, over the SAME env (no second simulation state)
+            pass
+        task = _Task()
+        task.env, task.num_envs, task.num_obs, task.num_states, task.num_actions, task.device = env, n, 396, 564, 23, f"cuda:{local}"
+        task.obs_buf, task.states_buf, task.rew_buf, task.reset_buf = (env.tensor(k) for k in ("OBS", "STATES", "REW", "RESET"))
+        task.extras = {}
+        task.step = env.step
+        venv = RLgamesVecTaskPython(task, task.device)
+        agent = A2CAgent(venv, PPOConfig(minibatch_size=min(args.minibatch, 8 * n)), device=local,
+                         dist_group=dist.group.WORLD if world > 1 else None)
+        H = agent.H
+        iters, witers = max(K // H, 1), max(W // H, 1)
+        for _ in range(witers):
+            ppo_info = agent.train_epoch()
+        barrier()
+        l0, p0 = env.launch_count(), ppo_launch()
+        e0.record()
+        for _ in range(iters):
+            ppo_info = agent.train_epoch()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) * K / (iters * H)
+        launches = (env.launch_count() - l0 + ppo_launch() - p0) * K // (iters * H)
     # ---- end to end through the C-ABI with HOST buffers (sdx_step_host): H2D actions, D2H obs/states/rew/reset
     E = args.e2e_steps
     h_act = torch.empty(n, 23, dtype=torch.float32).pin_memory()
@@ -220,10 +258,10 @@ def main():
     e2e_ms = max(g0.elapsed_time(g1), 1000 * (time.perf_counter() - t0) * 0.0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    tms = torch.tensor([ms, e2e_ms, sim_ms], device=dev, dtype=torch.float64)
+    tms = torch.tensor([ms, e2e_ms, sim_ms, ro_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, sim_ms = (float(x) for x in tms.tolist())
+    ms, e2e_ms, sim_ms, ro_ms = (float(x) for x in tms.tolist())
     nc = env.tensor("NCONTACT").cpu().numpy()
     if rank == 0:
         peak, which = measured_peaks()
@@ -232,18 +270,24 @@ def main():
             "metric": "env-steps/sec at num_envs=16384 (BlockAssemblyGraspSim)", "value": world * n * K / (ms * 1e-3),
             "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BlockAssemblyGraspSim num_envs={n} per GPU, rollout: VecTask.step = reset_idx + pre_physics(IK) + "
-                                   "contact step (2 sub-steps x 16 iterations) + observations/reward/t-value; U(-1,1) actions",
+            "config": {"workload": (f"BlockAssemblyGraspSim num_envs={n} per GPU, PPO bf16: every 8 env steps (policy + central-value forward, "
+                                    "VecTask.step = reset_idx + IK + contact step 2x16 + obs/reward/t-value) then GAE and "
+                                    f"5 mini-epochs x {8 * n // min(args.minibatch, 8 * n)} minibatches for actor and central value"
+                                    if args.mode == "ppo" else
+                                    f"BlockAssemblyGraspSim num_envs={n} per GPU, rollout only: VecTask.step, U(-1,1) actions"),
+                       "mode": args.mode, "minibatch": min(args.minibatch, 8 * n),
                        "num_envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "env state (260 MB at 16384 envs) exceeds the 126 MB L2; no explicit flush",
                        "heap_bank_per_type": args.bank_per_type},
             "e2e": {"value": world * n * E / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 23 * 4,
                     "d2h_bytes_per_step": n * (396 + 564 + 1) * 4 + n * 8, "steps": E},
             "gpu_launches": int(launches),
+            "rollout_only": {"value": world * n * KR / (ro_ms * 1e-3), "unit": "env-steps/s", "steps": KR, "ms_per_step": ro_ms / KR},
+            "ppo": ppo_info,
             "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": None,
                          "ms_per_launch": sim_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
-                         "share_of_step": sim_ms * K / ms,
+                         "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
                          "note": "state-streaming bound is loose: the kernel is fp32-ALU / shared-memory bound (DESIGN.md section 6)"},
             "clocks": sampler.summary(),
             "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "dropped_max": int(nc[:, 1].max())},

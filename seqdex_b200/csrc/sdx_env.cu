@@ -314,6 +314,18 @@ extern "C" int sdx_gae(const float* rewards, const float* values, const float* d
   return 0;
 }
 
+/* VecTask clamp of a task buffer into caller memory (VR:174-175): dst = clamp(tensor(kind), -lim, lim) */
+extern "C" int sdx_clamped_copy(sdx_env_t* E, int kind, float* dst_dev, float lim) {
+  CK(cudaSetDevice(E->device));
+  int dt = 0;
+  size_t ne = kind_elems(E, kind, nullptr, nullptr, &dt);
+  if (dt != 0 || !E->buf[kind]) { g_err = "sdx_clamped_copy: not a float tensor"; return -1; }
+  k_clamp_copy<<<(unsigned)((ne + 255) / 256), 256, 0, E->stream>>>((const float*)E->buf[kind], dst_dev, ne, lim);
+  E->launches++;
+  CKL();
+  return 0;
+}
+
 /* grasp terminal-state banks: device pointers for export */
 extern "C" int sdx_grasp_bank(sdx_env_t* E, void** hand_dev, void** obj_dev, void** index_dev) {
   *hand_dev = E->gb_hand; *obj_dev = E->gb_obj; *index_dev = E->gb_index;

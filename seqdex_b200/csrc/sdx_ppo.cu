@@ -18,6 +18,8 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static encode_tiled_fn g_encode = nullptr;
+static long long g_ppo_launches = 0;   // kernels launched by this translation unit
+extern "C" long long sdx_ppo_launch_count(void) { return g_ppo_launches; }
 
 static int get_encode() {
   if (g_encode) return 0;
@@ -89,6 +91,7 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
     case 4: k_gemm_tn<GEMM_BN, GEMM_STAGES, 4><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
     default: sdx_set_error("sdx_gemm_bf16_tn: bad mode"); return -1;
   }
+  g_ppo_launches++;
   PCK(cudaGetLastError());
   return 0;
 }
@@ -238,6 +241,7 @@ extern "C" int sdx_mlp_sync(sdx_mlp* m, void* stream) {
     int N = m->d[l + 1], Kpad = m->d[l], Kreal = l == 0 ? m->in_dim : m->d[l], Npad = pad64(N);
     int tot = N * Kpad; if (l > 0 && Kreal * Npad > tot) tot = Kreal * Npad;
     k_sync_w<<<(tot + 255) / 256, 256, 0, st>>>(m->params + m->w_off[l], N, Kreal, m->W[l], Kpad, Kpad, l > 0 ? m->Wt[l] : nullptr, Npad, Npad);
+    g_ppo_launches++;
   }
   PCK(cudaGetLastError());
   return 0;
@@ -249,6 +253,7 @@ extern "C" int sdx_mlp_forward(sdx_mlp* m, const float* x, int M, const float* m
   cudaStream_t st = (cudaStream_t)stream;
   dim3 blk(32, 8), grd((m->in_pad + 31) / 32, (M + 31) / 32);
   k_cvt_2way<<<grd, blk, 0, st>>>(x, M, m->in_dim, m->in_dim, m->in_pad, m->A[0], m->in_pad, train ? m->At[0] : nullptr, m->max_rows, mean, var);
+  g_ppo_launches++;
   PCK(cudaGetLastError());
   for (int l = 0; l < 3; ++l)
     if (sdx_gemm_bf16_tn(0, m->A[l], M, m->d[l], m->d[l], m->W[l], m->d[l + 1], m->d[l], m->params + m->b_off[l], nullptr, 0, m->A[l + 1], m->d[l + 1],
@@ -263,6 +268,7 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
   int opad = pad64(m->out_dim);
   dim3 blk(32, 8), grd((opad + 31) / 32, (M + 31) / 32);
   k_cvt_2way<<<grd, blk, 0, st>>>(dout, M, m->out_dim, m->out_dim, opad, m->dZ[4], opad, m->dZt[4], m->max_rows, nullptr, nullptr);
+  g_ppo_launches++;
   PCK(cudaGetLastError());
   for (int l = 3; l >= 0; --l) {
     int N = m->d[l + 1], K = m->d[l], ldg = K + 16;
@@ -272,6 +278,7 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
     if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, m->At[l], K + 16, m->max_rows, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
     int kreal = l == 0 ? m->in_dim : K;
     k_unpack_grads<<<(N * (kreal + 1) + 255) / 256, 256, 0, st>>>(m->gW[l], N, kreal, K, ldg, m->grads + m->w_off[l], m->grads + m->b_off[l]);
+    g_ppo_launches++;
     if (l > 0) {
       int Kd = pad64(N);
       if (sdx_gemm_bf16_tn(1, m->dZ[l + 1], M, Kd, Kd, m->Wt[l], K, Kd, nullptr, m->A[l], K, m->dZ[l], K, m->dZt[l], m->max_rows, nullptr, 0, 1, stream)) return -1;
@@ -285,8 +292,10 @@ extern "C" int sdx_mlp_adam(sdx_mlp* m, float lr, float b1, float b2, float eps,
   m->adam_t++;
   PCK(cudaMemsetAsync(m->scal, 0, 4, st));
   if (max_norm > 0.0f) k_sumsq<<<296, 256, 0, st>>>(m->grads, m->nparams, m->scal);
+  g_ppo_launches++;
   float bc1 = 1.0f - powf(b1, (float)m->adam_t), bc2 = 1.0f - powf(b2, (float)m->adam_t);
   k_adam<<<(unsigned)((m->nparams + 255) / 256), 256, 0, st>>>(m->params, m->grads, m->adam_m, m->adam_v, m->nparams, lr, b1, b2, eps, bc1, bc2, max_norm, m->scal);
+  g_ppo_launches++;
   PCK(cudaGetLastError());
   return sdx_mlp_sync(m, stream);
 }
@@ -435,6 +444,7 @@ __global__ void k_add_count(double* count, double b) { *count += b; }
 
 extern "C" int sdx_ppo_sample(const float* mu, const float* logstd, int M, int A, uint64_t seed, uint32_t counter, float* actions, float* neglogp, void* stream) {
   k_ppo_sample<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, logstd, M, A, seed, counter, actions, neglogp);
+  g_ppo_launches++;
   PCK(cudaGetLastError()); return 0;
 }
 extern "C" int sdx_ppo_actor_loss(const float* mu, const float* logstd, const float* actions, const float* old_mu, const float* old_logstd,
@@ -448,26 +458,32 @@ extern "C" int sdx_ppo_actor_loss(const float* mu, const float* logstd, const fl
 extern "C" int sdx_ppo_value_loss(const float* v, const float* v_old, const float* ret, int M, float e_clip, int clip_value, float scale, float* dv,
                                   float* stats, void* stream) {
   k_ppo_value_loss<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(v, v_old, ret, M, e_clip, clip_value, scale, dv, stats);
+  g_ppo_launches++;
   PCK(cudaGetLastError()); return 0;
 }
 // mom: double[2] device scratch (zeroed here).  After the call x is normalised in place (count = n unless n_total given for DP).
 extern "C" int sdx_moments(const float* x, int64_t n, double* mom, void* stream) {
   PCK(cudaMemsetAsync(mom, 0, 16, (cudaStream_t)stream));
   k_moments<<<296, 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, mom);
+  g_ppo_launches++;
   PCK(cudaGetLastError()); return 0;
 }
 extern "C" int sdx_normalize(float* x, int64_t n, const double* mom, double count, void* stream) {
   k_normalize<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, (size_t)n, mom, count);
+  g_ppo_launches++;
   PCK(cudaGetLastError()); return 0;
 }
 extern "C" int sdx_col_moments(const float* x, int B, int D, double* colmom, void* stream) {
   PCK(cudaMemsetAsync(colmom, 0, (size_t)2 * D * 8, (cudaStream_t)stream));
   dim3 grd((D + 31) / 32, 64);
   k_col_moments<<<grd, 256, 0, (cudaStream_t)stream>>>(x, B, D, colmom);
+  g_ppo_launches++;
   PCK(cudaGetLastError()); return 0;
 }
 extern "C" int sdx_rms_merge(float* mean, float* var, double* count, const double* colmom, int D, double bcount, void* stream) {
   k_rms_merge<<<(D + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean, var, count, colmom, D, bcount);
+  g_ppo_launches++;
   k_add_count<<<1, 1, 0, (cudaStream_t)stream>>>(count, bcount);
+  g_ppo_launches++;
   PCK(cudaGetLastError()); return 0;
 }

@@ -106,6 +106,10 @@ class SdxEnv:
                                         ctypes.c_void_p(states.data_ptr()), ctypes.c_void_p(rew.data_ptr()),
                                         ctypes.c_void_p(reset.data_ptr())))
 
+    def clamped_copy(self, name, dst, lim=5.0):
+        """dst <- clamp(tensor(name), -lim, lim) in one kernel (VecTask's clip_obs, VR:174-175)"""
+        _lib.check(self.L.sdx_clamped_copy(self.h, T[name], ctypes.c_void_p(dst.data_ptr()), ctypes.c_float(lim)))
+
     def refresh(self, name):
         _lib.check(self.L.sdx_refresh(self.h, T[name]))
 

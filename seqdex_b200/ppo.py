@@ -174,6 +174,7 @@ class A2CAgent:
         self.rms_count = torch.full((1,), 1e-4, device=self.device, dtype=torch.float64)
         self.last_lr = c.learning_rate
         self.dones = torch.zeros(N, device=self.device)
+        self.last_values = torch.zeros(N, device=self.device)
         self.obs = None
         self.sample_counter = 0
         self.epoch_num = 0
@@ -191,30 +192,37 @@ class A2CAgent:
         return mu, t
 
     def play_steps(self):
+        """horizon_length env steps (RGC:1394-1483): obs/dones stored pre-step, values from the central value net"""
+        L, A, N, H = self.L, self.A, self.N, self.H
+        fast = hasattr(self.env, "step_into")
         if self.obs is None:
-            self.obs = self.env.reset()
-        L, A, N = self.L, self.A, self.N
-        for t in range(self.H):
-            obs, states = self.obs["obs"], self.obs["states"]
-            self.b_obs[t].copy_(obs)
-            self.b_states[t].copy_(states)
+            first = self.env.reset()
+            self.next_obs, self.next_states = first["obs"].clone(), first["states"].clone()
+            self.obs = True
+        mean = self.rms_mean if self.cfg.cv_normalize_input else None
+        var = self.rms_var if self.cfg.cv_normalize_input else None
+        for t in range(H):
+            self.b_obs[t].copy_(self.next_obs)
+            self.b_states[t].copy_(self.next_states)
             self.b_dones[t].copy_(self.dones)
             mu = self.actor.forward(self.b_obs[t])
             self.b_mu[t].copy_(mu)
             _lib.check(L.sdx_ppo_sample(_p(self.b_mu[t]), _p(self.logstd), N, A, ctypes.c_uint64(self.cfg.seed), self.sample_counter,
                                         _p(self.b_actions[t]), _p(self.b_neglogp[t]), _stream()))
             self.sample_counter += 1
-            v = self.cv.forward(self.b_states[t], self.rms_mean if self.cfg.cv_normalize_input else None,
-                                self.rms_var if self.cfg.cv_normalize_input else None)
+            v = self.cv.forward(self.b_states[t], mean, var)
             self.b_values[t].copy_(v.view(-1))
-            self.obs, rew, dones, _ = self.env.step(self.b_actions[t])
+            if fast:
+                rew, dones, _ = self.env.step_into(self.b_actions[t], self.next_obs, self.next_states)
+            else:
+                o, rew, dones, _ = self.env.step(self.b_actions[t])
+                self.next_obs.copy_(o["obs"]); self.next_states.copy_(o["states"])
             self.b_rewards[t].copy_(rew)
-            self.dones = dones.float()
-        v = self.cv.forward(self.obs["states"].contiguous(), self.rms_mean if self.cfg.cv_normalize_input else None,
-                            self.rms_var if self.cfg.cv_normalize_input else None)
-        last_values = v.view(-1).clone()
-        _lib.check(L.sdx_gae(_p(self.b_rewards), _p(self.b_values), _p(self.b_dones), _p(last_values), _p(self.dones), _p(self.b_adv),
-                             _p(self.b_returns), self.H, N, ctypes.c_float(self.cfg.gamma), ctypes.c_float(self.cfg.tau), _stream()))
+            self.dones.copy_(dones)
+        v = self.cv.forward(self.next_states, mean, var)
+        self.last_values.copy_(v.view(-1))
+        _lib.check(L.sdx_gae(_p(self.b_rewards), _p(self.b_values), _p(self.b_dones), _p(self.last_values), _p(self.dones), _p(self.b_adv),
+                             _p(self.b_returns), H, N, ctypes.c_float(self.cfg.gamma), ctypes.c_float(self.cfg.tau), _stream()))
 
     def _allreduce(self, t, avg=True):
         if self.dist is not None and self.world > 1:

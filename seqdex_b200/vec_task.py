@@ -86,6 +86,14 @@ class RLgamesVecTaskPython(VecTask):
                     "states": torch.clamp(self.task.states_buf, -self.clip_obs, self.clip_obs)}
         return obs_dict, self.task.rew_buf, self.task.reset_buf, self.task.extras
 
+    def step_into(self, actions, obs_out, states_out):
+        """step() writing the clamped observations straight into caller buffers (same values as step(); saves the two
+        temporaries torch.clamp allocates every step).  Actions are clamped inside the pre-physics kernel."""
+        self.task.step(actions)
+        self.task.env.clamped_copy("OBS", obs_out, self.clip_obs)
+        self.task.env.clamped_copy("STATES", states_out, self.clip_obs)
+        return self.task.rew_buf, self.task.reset_buf, self.task.extras
+
     def reset(self):                                                                 # VR:179-192
         actions = 0.01 * (1 - 2 * torch.rand([self.task.num_envs, self.task.num_actions], dtype=torch.float32, device=self.rl_device))
         self.task.step(actions)
