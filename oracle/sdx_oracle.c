@@ -399,6 +399,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         float lck = k == 0 ? lc.x : (k == 1 ? lc.y : lc.z);
         float sgf = lck >= 0.0f ? 1.0f : -1.0f;
         uint32_t sg = lck >= 0.0f ? 0u : 1u;
+        if (t >= NB + nrs && k == 2) { sgf = 1.0f; sg = 0u; } /* statics rest on each other: their z faces only push UP */
         float htk = k == 0 ? ht.x : (k == 1 ? ht.y : ht.z);
         for (int p = 0; p < npts; ++p) {
           v3 pl;

@@ -86,7 +86,7 @@ struct GemmSmem {
 };
 
 template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
   using namespace gemm;
   extern __shared__ unsigned char gsm_raw[];
@@ -191,13 +191,20 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       } else {
         if (row_ok) {
           float* dst = g.outf + (size_t)row * g.ldf + col0;
+          if (MODE == 2 && col0 + 32 <= g.N && (g.ldf & 3) == 0) {      // split-K accumulation: 16-byte vector reductions
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < g.N) {
-              if (MODE == 2) atomicAdd(dst + j, __uint_as_float(r[j]));
-              else if (MODE == 4) dst[j] = __uint_as_float(r[j]) + g.bias[col0 + j];
-              else dst[j] = __uint_as_float(r[j]);
-            }
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(dst + j),
+                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < g.N) {
+                if (MODE == 2) atomicAdd(dst + j, __uint_as_float(r[j]));
+                else if (MODE == 4) dst[j] = __uint_as_float(r[j]) + g.bias[col0 + j];
+                else dst[j] = __uint_as_float(r[j]);
+              }
+          }
         }
       }
     }

@@ -46,7 +46,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
 }
 
 #define GEMM_BN 128
-#define GEMM_STAGES 5
+#define GEMM_STAGES 3   /* 3 x 32 KB stages -> two CTAs per SM: one tile's epilogue overlaps the other's main loop */
 typedef GemmSmem<GEMM_BN, GEMM_STAGES> GSm;
 static bool g_attr_set = false;
 static int set_attrs() {
@@ -274,7 +274,7 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
     int N = m->d[l + 1], K = m->d[l], ldg = K + 16;
     PCK(cudaMemsetAsync(m->gW[l], 0, (size_t)N * ldg * 4, st));
     int tiles = ((N + 127) / 128) * ((K + 16 + 127) / 128);
-    int splits = (296 + tiles - 1) / tiles; if (splits < 1) splits = 1;
+    int splits = (148 + tiles - 1) / tiles; if (splits < 1) splits = 1;   // ~one wave of CTAs; fewer splits = fewer fp32 reductions
     if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, m->At[l], K + 16, m->max_rows, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
     int kreal = l == 0 ? m->in_dim : K;
     k_unpack_grads<<<(N * (kreal + 1) + 255) / 256, 256, 0, st>>>(m->gW[l], N, kreal, K, ldg, m->grads + m->w_off[l], m->grads + m->b_off[l]);

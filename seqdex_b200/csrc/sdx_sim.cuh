@@ -28,8 +28,11 @@
 #define KC 32
 #define MAXC SDX_MAX_CONTACTS
 #define STATIC_BODY 255
-#define SIM_THREADS 128
-#define ROBOT_TID0 96                  /* warp 3 owns the articulation: lane j = DoF j, lane L = link L */
+#ifndef SIM_THREADS
+#define SIM_THREADS 256
+#endif
+#define SIM_MIN_CTAS 3                 /* CTAs per SM the register budget is sized for */
+#define ROBOT_TID0 (SIM_THREADS - 32)  /* the LAST warp owns the articulation: lane j = DoF j, lane L = link L */
 #define PPMAX 26                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
 
 struct SimSmem {
@@ -54,43 +57,51 @@ struct SimSmem {
   float cw[3][MAXC], cbias[MAXC], cinv[3][MAXC], cf[3][MAXC];
 };
 
-// exclusive prefix sum of arr[0..n) (n <= 128) by ONE warp, in place; returns the total to every lane
+// exclusive prefix sum of arr[0..n) (n <= 256) by ONE warp, in place; returns the total to every lane
 __device__ __forceinline__ int warp_excl_scan(int* arr, int n, int lane) {
-  int v[4], s = 0;
+  constexpr int PER = 8;
+  int v[PER], s = 0;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { int k = lane * 4 + i; v[i] = k < n ? arr[k] : 0; s += v[i]; }
+  for (int i = 0; i < PER; ++i) { int k = lane * PER + i; v[i] = k < n ? arr[k] : 0; s += v[i]; }
   int incl = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
   int run = incl - s;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { int k = lane * 4 + i; if (k < n) arr[k] = run; run += v[i]; }
+  for (int i = 0; i < PER; ++i) { int k = lane * PER + i; if (k < n) arr[k] = run; run += v[i]; }
   return __shfl_sync(0xffffffffu, incl, 31);
 }
 
 __device__ __forceinline__ v3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
 __device__ __forceinline__ void st3(float* p, v3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
 
-// forward kinematics of the collapsed Panda+Allegro tree, serial over the chain (one thread)
-__device__ void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M) {
-  st3(M.bx[NB], V3(S->base_pos[0], S->base_pos[1], S->base_pos[2]));
-  M.lq[0][0] = S->base_quat[0]; M.lq[0][1] = S->base_quat[1]; M.lq[0][2] = S->base_quat[2]; M.lq[0][3] = S->base_quat[3];
-  for (int j = 0; j < SDX_ND; ++j) {
-    int L = j + 1, P = S->body_parent[L];
-    q4 qP = Q4(M.lq[P][0], M.lq[P][1], M.lq[P][2], M.lq[P][3]);
-    q4 qf = Q4(S->joint_quat[4 * j], S->joint_quat[4 * j + 1], S->joint_quat[4 * j + 2], S->joint_quat[4 * j + 3]);
-    v3 ax = V3(S->joint_axis[3 * j], S->joint_axis[3 * j + 1], S->joint_axis[3 * j + 2]);
-    q4 qj = qmul(qP, qf);
-    v3 x = vadd(ld3(M.bx[NB + P]), qrot(qP, V3(S->joint_xyz[3 * j], S->joint_xyz[3 * j + 1], S->joint_xyz[3 * j + 2])));
-    float s, c;
-    sdx_sincos(0.5f * M.q[j], &s, &c);
-    q4 qr = Q4(ax.x * s, ax.y * s, ax.z * s, c);
-    q4 ql = qmul(qj, qr);
-    M.lq[L][0] = ql.x; M.lq[L][1] = ql.y; M.lq[L][2] = ql.z; M.lq[L][3] = ql.w;
-    st3(M.bx[NB + L], x);
-    st3(M.ja[j], qrot(qj, ax));
-    st3(M.jo[j], x);
+// forward kinematics of the collapsed Panda+Allegro tree by ONE WARP: lane 0 walks the 7 arm joints, then lanes 0-3
+// walk the four finger chains (DoFs 7+4f .. 10+4f) concurrently -> dependency depth 11 instead of 23
+__device__ __forceinline__ void fk_joint(const sdx_scene_t* __restrict__ S, SimSmem& M, int j) {
+  int L = j + 1, P = S->body_parent[L];
+  q4 qP = Q4(M.lq[P][0], M.lq[P][1], M.lq[P][2], M.lq[P][3]);
+  q4 qf = Q4(S->joint_quat[4 * j], S->joint_quat[4 * j + 1], S->joint_quat[4 * j + 2], S->joint_quat[4 * j + 3]);
+  v3 ax = V3(S->joint_axis[3 * j], S->joint_axis[3 * j + 1], S->joint_axis[3 * j + 2]);
+  q4 qj = qmul(qP, qf);
+  v3 x = vadd(ld3(M.bx[NB + P]), qrot(qP, V3(S->joint_xyz[3 * j], S->joint_xyz[3 * j + 1], S->joint_xyz[3 * j + 2])));
+  float s, c;
+  sdx_sincos(0.5f * M.q[j], &s, &c);
+  q4 qr = Q4(ax.x * s, ax.y * s, ax.z * s, c);
+  q4 ql = qmul(qj, qr);
+  M.lq[L][0] = ql.x; M.lq[L][1] = ql.y; M.lq[L][2] = ql.z; M.lq[L][3] = ql.w;
+  st3(M.bx[NB + L], x);
+  st3(M.ja[j], qrot(qj, ax));
+  st3(M.jo[j], x);
+}
+__device__ void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M, int lane) {
+  if (lane == 0) {
+    st3(M.bx[NB], V3(S->base_pos[0], S->base_pos[1], S->base_pos[2]));
+    M.lq[0][0] = S->base_quat[0]; M.lq[0][1] = S->base_quat[1]; M.lq[0][2] = S->base_quat[2]; M.lq[0][3] = S->base_quat[3];
+    for (int j = 0; j < 7; ++j) fk_joint(S, M, j);
   }
+  __syncwarp();
+  if (lane < 4) for (int j = 7 + 4 * lane; j < 11 + 4 * lane; ++j) fk_joint(S, M, j);
+  __syncwarp();
 }
 
 __device__ __forceinline__ void link_twist(const sdx_scene_t* __restrict__ S, SimSmem& M, int L, unsigned m) {
@@ -139,7 +150,7 @@ __device__ float body_k(const sdx_scene_t* __restrict__ S, const SimSmem& M, int
 
 // pair-level SAT: reference face of target t for owner a.  returns false if separated beyond m.
 struct PairGeom { v3 lc; float C[9]; int k; float sgf; uint32_t sg; float htk; v3 ha, ht; };
-__device__ __forceinline__ bool pair_geom(const SimSmem& M, int a, int t, float m, PairGeom& G) {
+__device__ __forceinline__ bool pair_geom(const SimSmem& M, int a, int t, float m, PairGeom& G, bool t_static) {
   G.lc = mtmul(M.sR[t], vsub(ld3(M.sc[a]), ld3(M.sc[t])));
 #pragma unroll
   for (int r = 0; r < 3; ++r)
@@ -158,6 +169,7 @@ __device__ __forceinline__ bool pair_geom(const SimSmem& M, int a, int t, float 
   G.k = k;
   G.sgf = lck >= 0.0f ? 1.0f : -1.0f;
   G.sg = lck >= 0.0f ? 0u : 1u;
+  if (t_static && k == 2) { G.sgf = 1.0f; G.sg = 0u; }   // statics rest on each other: their z faces only push UP
   G.htk = k == 0 ? G.ht.x : (k == 1 ? G.ht.y : G.ht.z);
   return true;
 }
@@ -188,7 +200,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   }
 }
 
-__global__ void __launch_bounds__(SIM_THREADS)
+__global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
            int* __restrict__ ncontact, float* __restrict__ condump, int n_envs) {
@@ -265,7 +277,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
 
   for (int sub = 0; sub < substeps; ++sub) {
     // 1. kinematics (one thread walks the chain) || brick poses + free velocities
-    if (tid == ROBOT_TID0) robot_fk(S, M);
+    if (tid >= ROBOT_TID0) robot_fk(S, M, tid - ROBOT_TID0);
     if (tid < NB) {
       qmat(bqr, M.sR[tid]);
       st3(M.sc[tid], bxr); st3(M.bx[tid], bxr);
@@ -346,30 +358,30 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       if (tid == 0) M.poff[n_owner] = tot;
     }
     __syncthreads();
-    // 6. narrow phase, pass 1: per-pair hit masks, kept in registers; contiguous pair chunks per thread
+    // 6. narrow phase, pass 1 (pair-parallel): per-pair hit masks + running contact offsets.  The pair tables live in
+    //    the (still unused) impulse / inverse-mass arrays.  Contiguous pair chunks per thread => offsets are in pair order.
     const int npairs = M.poff[n_owner];
-    const int PP = (npairs + SIM_THREADS - 1) / SIM_THREADS;   // <= KC*NOWN/128 = 26 > PPMAX only if every owner is full
+    const int PP = (npairs + SIM_THREADS - 1) / SIM_THREADS;
     const int p0 = tid * PP, p1 = min(npairs, p0 + PP);
-    unsigned short masks[PPMAX];
-    int mycount = 0, pairdrop = 0;
+    unsigned short* pmask = reinterpret_cast<unsigned short*>(&M.cf[0][0]);     // [npairs] <= 3328 * 2 B < 12 KB
+    unsigned short* pstart = reinterpret_cast<unsigned short*>(&M.cinv[0][0]);  // [npairs]
+    int mycount = 0;
     {
       int a = 0;
-      for (int i = p0, s = 0; i < p1; ++i, ++s) {
-        if (s >= PPMAX) { pairdrop++; continue; }
+      for (int i = p0; i < p1; ++i) {
         while (M.poff[a + 1] <= i) ++a;
         int t = M.cand[a][i - M.poff[a]];
         float m = margin + M.spd[a] + M.spd[t];
         unsigned short mk = 0;
         PairGeom G;
-        if (pair_geom(M, a, t, m, G)) {
+        if (pair_geom(M, a, t, m, G, t >= NB + nrs)) {
           int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
           for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, margin, &d)) mk |= (unsigned short)(1u << p); }
         }
-        masks[s] = mk;
+        pmask[i] = mk;
         mycount += __popc((unsigned)mk);
       }
     }
-    // block-wide exclusive scan of per-thread contact counts (thread order == pair order)
     M.scan[tid] = mycount;
     __syncthreads();
     if (tid < 32) {
@@ -378,37 +390,53 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     }
     if (tid < NBODY) { M.astart[tid] = 0; M.aend[tid] = 0; M.nb[tid] = 0; }
     __syncthreads();
-    // pass 2: regenerate the hits and write contacts at their global slots
     {
-      int slot = M.scan[tid];
-      int a = 0;
-      for (int i = p0, s = 0; i < p1 && s < PPMAX; ++i, ++s) {
-        unsigned mk = masks[s];
-        if (!mk) continue;
-        while (M.poff[a + 1] <= i) ++a;
-        int t = M.cand[a][i - M.poff[a]];
-        float m = margin + M.spd[a] + M.spd[t];
-        PairGeom G;
-        pair_geom(M, a, t, m, G);
-        for (int p = 0; p < 12; ++p) {
-          if (!(mk & (1u << p))) continue;
-          float depth;
-          point_hit(G, p, m, margin, &depth);
-          if (slot < MAXC) {
-            v3 wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
-            M.cword[slot] = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
-            M.cw[0][slot] = wpt.x; M.cw[1][slot] = wpt.y; M.cw[2][slot] = wpt.z;
-            float bias = 0.0f;
-            if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
-            else if (depth < 0.0f) bias = depth / h;
-            M.cbias[slot] = bias;
-            M.cf[0][slot] = 0.0f; M.cf[1][slot] = 0.0f; M.cf[2][slot] = 0.0f;
-            M.cinv[0][slot] = depth;
-          }
-          ++slot;
+      int run = M.scan[tid];
+      for (int i = p0; i < p1; ++i) { pstart[i] = (unsigned short)min(run, 65535); run += __popc((unsigned)pmask[i]); }
+    }
+    __syncthreads();
+    // pass 2 (contact-parallel): slot -> (pair, point) by binary search over the pair offsets, then regenerate the hit
+    {
+      const int ncon_w = M.ncon;
+      unsigned short stash_mask[MAXC / SIM_THREADS], stash_pair[MAXC / SIM_THREADS];   // read the tables BEFORE they are overwritten
+      unsigned char stash_j[MAXC / SIM_THREADS];
+#pragma unroll
+      for (int r = 0; r < MAXC / SIM_THREADS; ++r) {
+        int slot = r * SIM_THREADS + tid;
+        stash_pair[r] = 0; stash_mask[r] = 0; stash_j[r] = 0;
+        if (slot < ncon_w) {
+          int lo = 0, hi = npairs - 1;                 // largest i with pstart[i] <= slot (that pair is non-empty)
+          while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)pstart[mid] <= slot) lo = mid; else hi = mid - 1; }
+          stash_pair[r] = (unsigned short)lo; stash_mask[r] = pmask[lo]; stash_j[r] = (unsigned char)(slot - (int)pstart[lo]);
         }
       }
-      if (pairdrop) atomicAdd(&M.ndropped, pairdrop);
+      __syncthreads();
+#pragma unroll 1
+      for (int r = 0; r < MAXC / SIM_THREADS; ++r) {
+        int slot = r * SIM_THREADS + tid;
+        if (slot >= ncon_w) break;
+        int i = stash_pair[r];
+        unsigned mk = stash_mask[r];
+        int j = stash_j[r], p = 0;
+        for (;; ++p) { if (mk & (1u << p)) { if (j == 0) break; --j; } }
+        int lo = 0, hi = n_owner - 1;                  // owner a with poff[a] <= i < poff[a+1]
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (M.poff[mid] <= i) lo = mid; else hi = mid - 1; }
+        const int a = lo, t = M.cand[a][i - M.poff[a]];
+        float m = margin + M.spd[a] + M.spd[t];
+        PairGeom G;
+        pair_geom(M, a, t, m, G, t >= NB + nrs);
+        float depth;
+        point_hit(G, p, m, margin, &depth);
+        v3 wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
+        M.cword[slot] = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
+        M.cw[0][slot] = wpt.x; M.cw[1][slot] = wpt.y; M.cw[2][slot] = wpt.z;
+        float bias = 0.0f;
+        if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
+        else if (depth < 0.0f) bias = depth / h;
+        M.cbias[slot] = bias;
+        M.cf[0][slot] = 0.0f; M.cf[1][slot] = 0.0f; M.cf[2][slot] = 0.0f;
+        M.cinv[0][slot] = depth;
+      }
     }
     __syncthreads();
     const int ncon = M.ncon;
@@ -493,10 +521,11 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       }
       __syncthreads();
       // phase B: FOUR lanes per body, lane k sums incidences e = k (mod 4); partials combined (0+1)+(2+3).
-      // warps 0-2: 72 bricks x 4 lanes = 3 passes of 96 threads; warp 3: 24 links x 4 lanes = 3 passes of 32.
+      // brick warps (all but the last): 72 bricks x 4 lanes = 288 items, ROBOT_TID0 per pass; last warp: 24 links x 4 lanes.
 #pragma unroll 1
       for (int pass = 0; pass < 3; ++pass) {
         const int item = tid < ROBOT_TID0 ? pass * ROBOT_TID0 + tid : pass * 32 + (tid - ROBOT_TID0);
+        if (tid < ROBOT_TID0 && item >= 4 * NB) continue;       // warp-uniform (288 and ROBOT_TID0 are multiples of 32)
         const int body = tid < ROBOT_TID0 ? (item >> 2) : NB + (item >> 2);
         const int k = item & 3;
         const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = na + (M.boff[body + 1] - b0);
@@ -578,7 +607,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     M.tile[7 * NB + tid] = bvr.x; M.tile[8 * NB + tid] = bvr.y; M.tile[9 * NB + tid] = bvr.z;
     M.tile[10 * NB + tid] = bwr.x; M.tile[11 * NB + tid] = bwr.y; M.tile[12 * NB + tid] = bwr.z;
   }
-  if (tid == ROBOT_TID0) robot_fk(S, M);
+  if (tid >= ROBOT_TID0) robot_fk(S, M, tid - ROBOT_TID0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   if (tid == 0) {

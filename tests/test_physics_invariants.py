@@ -1,0 +1,120 @@
+"""Physics invariants of the contact step, checked on the CPU oracle (the CUDA kernel is bit-identical to it,
+tests/test_parity_gpu.py).  PhysX itself cannot be run here (closed binary) -- these stand in for a reference
+trajectory: free fall, momentum exchange, rest stability / bounded penetration, joint limits,
+PD tracking, no NaNs from a violent start."""
+import numpy as np
+import pytest
+
+from seqdex_b200.scene import Scene
+
+
+def _env(oracle_lib, n_bricks, n=1, **kw):
+    s = Scene(**kw)
+    s.c.n_bricks = n_bricks
+    return s, oracle_lib.OracleEnv(s, n)
+
+
+def _rows(pos, quat=(0, 0, 0, 1), vel=(0, 0, 0), ang=(0, 0, 0)):
+    return list(pos) + list(quat) + list(vel) + list(ang)
+
+
+def test_free_fall_matches_semi_implicit_euler(oracle_lib):
+    s, e = _env(oracle_lib, 1)
+    rows = e.brick_roots()
+    rows[0, 0] = _rows((0.25, 0.19, 2.0))          # far above everything: no contacts
+    e.set_brick_roots(rows)
+    h, g = 1.0 / 120.0, -9.81
+    z, v = 2.0, 0.0
+    for _ in range(10):
+        e.simulate()
+        for _ in range(2):
+            v += h * g
+            z += h * v
+    r = e.brick_roots()[0, 0]
+    assert e.ncontact[0, 0] == 0
+    np.testing.assert_allclose(r[2], z, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(r[9], v, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(r[[0, 1]], [0.25, 0.19], atol=1e-6)
+
+
+def test_head_on_collision_conserves_momentum(oracle_lib):
+    s, e = _env(oracle_lib, 2)
+    s.c.gravity_z = 0.0
+    s.c.brick_ang_damp = 0.0
+    rows = e.brick_roots()
+    rows[0, 0] = _rows((0.00, 0.0, 3.0), vel=(0.5, 0, 0))     # brick 0 (1x2) moving +x
+    rows[0, 1] = _rows((0.09, 0.0, 3.0), vel=(-0.2, 0, 0))    # brick 1 (1x2_curve) moving -x, 3 cm gap
+    e.set_brick_roots(rows)
+    m = 1.0 / np.ctypeslib.as_array(s.c.br_invm)[:2]
+    p0 = (m[:, None] * e.brick[0, 7:10, :2].T).sum(0)
+    touched = 0
+    for _ in range(30):
+        e.simulate()
+        touched = max(touched, int(e.ncontact[0, 0]))
+    p1 = (m[:, None] * e.brick[0, 7:10, :2].T).sum(0)
+    assert touched > 0, "bricks never met"
+    np.testing.assert_allclose(p1, p0, rtol=0, atol=2e-6)      # equal and opposite impulses
+    assert e.brick[0, 7, 0] < 0.5 and e.brick[0, 7, 1] > -0.2  # they did exchange momentum
+    assert e.brick[0, 7, 1] - e.brick[0, 7, 0] > -1e-4         # and no longer approach each other
+
+
+def test_bricks_come_to_rest_with_bounded_penetration(oracle_lib):
+    s, e = _env(oracle_lib, 8)
+    rows = e.brick_roots()
+    rng = np.random.default_rng(0)
+    for b in range(8):        # one layer, just above the fixed floor bricks (top at z = 0.6637), no initial overlap
+        rows[0, b] = _rows((0.10 + 0.09 * (b % 4), 0.10 + 0.12 * (b // 4), 0.70), quat=(0, 0, np.sin(0.3 * b), np.cos(0.3 * b)))
+    rows[0, :8, 0:2] += rng.uniform(-0.005, 0.005, size=(8, 2))
+    e.set_brick_roots(rows.astype(np.float32))
+    for _ in range(150):
+        e.simulate(dump=True)
+    n = e.ncontact[0, 0]
+    depth = e.condump[0, :n, 4]
+    v = np.linalg.norm(e.brick[0, 7:10, :8], axis=0)
+    w = np.linalg.norm(e.brick[0, 10:13, :8], axis=0)
+    z = e.brick_roots()[0, :8, 2]
+    assert n >= 8 * 3, "every resting brick needs at least 3 support points"
+    assert depth.max() < 0.004, f"penetration {depth.max():.4f} m"
+    assert v.max() < 0.03 and w.max() < 0.5, (v.max(), w.max())
+    assert np.all(np.abs(z - (0.6637 + 0.01875)) < 0.006), z      # resting on the floor bricks' tops
+    ke0 = (v ** 2).sum()
+    for _ in range(100):
+        e.simulate()
+    ke1 = (np.linalg.norm(e.brick[0, 7:10, :8], axis=0) ** 2).sum()
+    assert ke1 <= ke0 + 1e-3, "resting heap must not gain energy"
+
+
+def test_joint_limits_and_pd_tracking(oracle_lib):
+    s, e = _env(oracle_lib, 0)
+    lo, hi = s.dof_lo, s.dof_hi
+    e.dof[0, 2, :23] = hi + 1.0                    # targets beyond the upper limits
+    e.dof[0, 2, 3] = lo[3] - 1.0                   # and one beyond the lower limit
+    for _ in range(240):
+        e.simulate()
+    q = e.dof[0, 0, :23]
+    assert np.all(q <= hi + 1e-6) and np.all(q >= lo - 1e-6)
+    assert np.all(np.abs(q[7:] - hi[7:]) < 1e-3), "fingers (k=50, d=1) reach the limit within 4 s"
+    assert abs(q[3] - lo[3]) < 0.05
+    # PD tracking of an in-range target: critically over-damped arm joint converges monotonically
+    s2, e2 = _env(oracle_lib, 0)
+    q0 = e2.dof[0, 0, 1]
+    e2.dof[0, 2, 1] = q0 - 0.3           # lifts the arm (the other direction pushes the hand into the bin)
+    prev, hist = q0, []
+    for _ in range(180):
+        e2.simulate()
+        hist.append(e2.dof[0, 0, 1])
+    assert all(b <= a + 1e-6 for a, b in zip(hist, hist[1:])), "no overshoot oscillation"
+    assert abs(hist[-1] - (q0 - 0.3)) < 1e-3
+    assert e2.ncontact[0, 0] == 0
+
+
+def test_violent_start_stays_finite(oracle_lib):
+    """the reference's own initial condition: 9 layers dropped from up to 1.1 m, first layer overlapping the floor bricks"""
+    s, e = _env(oracle_lib, 72, n=2)
+    for _ in range(200):
+        e.simulate()
+    assert np.isfinite(e.brick).all() and np.isfinite(e.dof).all()
+    r = e.brick_roots()
+    assert r[..., 2].min() > -0.1, "nothing tunnels through the ground plane"
+    inside = (np.abs(r[..., 0] - 0.25) < 0.35) & (np.abs(r[..., 1] - 0.19) < 0.26)
+    assert inside.mean() > 0.8, "most bricks end up in or next to the bin"
