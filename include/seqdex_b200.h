@@ -137,11 +137,58 @@ int sdx_simulate_n(sdx_env_t* env, int n);
 /* number of kernels this library has launched on behalf of env since creation */
 int64_t sdx_launch_count(const sdx_env_t* env);
 
+/* dst = clamp(tensor(kind), -lim, lim): VecTask's clip_obs into caller memory (VR:174-175) */
+int sdx_clamped_copy(sdx_env_t* env, int kind, float* dst_dev, float lim);
+/* rows [142][13] of the actors that carry no simulation state (hand base, table, bin, fixed bricks, ...) for the facade */
+int sdx_set_static_rows(sdx_env_t* env, const float* rows_host);
+/* sdx_set_heap_bank from a device buffer (bank synthesised on the GPU) */
+int sdx_set_heap_bank_dev(sdx_env_t* env, const float* bank_dev, int per_type);
+/* device pointers of the grasp terminal-state rings reset_idx fills (GS:1399-1445): hand [8][11024][23][2], obj [8][11024][13], index [8] */
+int sdx_grasp_bank(sdx_env_t* env, void** hand_dev, void** obj_dev, void** index_dev);
+int sdx_aux(sdx_env_t* env, void** qcam_dev, void** finger_dist_dev);
+int sdx_scene_size(void);
+int sdx_sim_smem_bytes(void);
+
 /* ---- PPO (rl_games 1.5.2 semantics; RGC:1394-1483, 1767-1911, 2115-2132) ---- */
 /* discount_values: GAE sweep. rewards/values/dones [H][N], last_values/last_dones [N] -> advantages [H][N]. */
 int sdx_gae(const float* rewards_dev, const float* values_dev, const float* dones_dev, const float* last_values_dev,
             const float* last_dones_dev, float* adv_dev, float* returns_dev, int horizon, int n, float gamma,
             float tau, void* stream);
+
+/* bf16 tensor-core GEMM D[M,N] = A[M,K] . B[N,K]^T (both K-major); fused epilogues by `mode` (csrc/sdx_gemm.cuh):
+ * 0 ELU(acc+bias)->bf16 (+transposed copy)  1 acc*ELU'(h)->bf16 (+transposed)  2 fp32 += acc (split-K)  3 fp32 = acc
+ * 4 fp32 = acc + bias.  Replaces the cuBLAS calls under rl_games' network forward/backward (RGC:1697-1723, 1767-1911). */
+int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, const void* B, int N, int ldb, const float* bias,
+                     const void* h, int ldh, void* out, int ldo, void* out_t, int ldt, float* outf, int ldf, int splits,
+                     void* stream);
+
+/* MLP in -> 1024 -> 512 -> 256 -> out (ELU), fp32 master parameters in torch state_dict order, bf16 compute
+ * (cfg/lego/ppo_continuous_grasp.yaml:21-23, 74-95).  has_sigma appends the logstd vector (fixed_sigma: True). */
+typedef struct sdx_mlp sdx_mlp_t;
+int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sigma, sdx_mlp_t** out);
+void sdx_mlp_destroy(sdx_mlp_t* m);
+int sdx_mlp_info(sdx_mlp_t* m, int64_t* nparams, void** params, void** grads, void** out, void** adam_m, void** adam_v);
+int sdx_mlp_sync(sdx_mlp_t* m, void* stream);
+int sdx_mlp_forward(sdx_mlp_t* m, const float* x_dev, int M, const float* mean, const float* var, int train, void* stream);
+int sdx_mlp_backward(sdx_mlp_t* m, const float* dout_dev, int M, void* stream);
+int sdx_mlp_adam(sdx_mlp_t* m, float lr, float b1, float b2, float eps, float max_norm, void* stream);   /* RGC:1102, 1866-1872 */
+long long sdx_ppo_launch_count(void);
+
+/* a = mu + exp(logstd) N(0,1) (Philox), neglogp (RGC:2115-2127) */
+int sdx_ppo_sample(const float* mu, const float* logstd, int M, int A, uint64_t seed, uint32_t counter, float* actions,
+                   float* neglogp, void* stream);
+/* clipped surrogate + bounds loss + KL (RGC:1767-1911, 2130-2132): dmu [M,A], dlogstd [A] (+=), stats[4] (+=) */
+int sdx_ppo_actor_loss(const float* mu, const float* logstd, const float* actions, const float* old_mu,
+                       const float* old_logstd, const float* old_neglogp, const float* adv, int M, int A, float e_clip,
+                       float bounds_coef, float inv_batch, float* dmu, float* dlogstd, float* stats, void* stream);
+int sdx_ppo_value_loss(const float* v, const float* v_old, const float* ret, int M, float e_clip, int clip_value,
+                       float scale, float* dv, float* stats, void* stream);
+/* advantage normalisation (RGC:1651): moments -> (x - mean) / (std + 1e-8) */
+int sdx_moments(const float* x, int64_t n, double* mom, void* stream);
+int sdx_normalize(float* x, int64_t n, const double* mom, double count, void* stream);
+/* RunningMeanStd of the central-value input (yaml:80 normalize_input) */
+int sdx_col_moments(const float* x, int B, int D, double* colmom, void* stream);
+int sdx_rms_merge(float* mean, float* var, double* count, const double* colmom, int D, double bcount, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,10 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -87,7 +91,8 @@ struct GemmSmem {
 
 template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
-k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const GemmArgs g) {
+k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
+          const __grid_constant__ CUtensorMap mapT, const GemmArgs g) {
   using namespace gemm;
   extern __shared__ unsigned char gsm_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment: align by hand (the launcher over-allocates 1 KB)
@@ -155,38 +160,63 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       if (col0 >= g.N) break;
       if (MODE == 0 || MODE == 1) {
         float v[32];
+        const bool full = col0 + 32 <= g.N;
+        if (MODE == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float acc = __uint_as_float(r[j]);
-          const int col = col0 + j;
-          if (MODE == 0) {
-            acc += (col < g.N) ? g.bias[col] : 0.0f;
-            v[j] = acc > 0.0f ? acc : (__expf(acc) - 1.0f);
-          } else {
-            float hv = (row_ok && col < g.N) ? __bfloat162float(g.h[(size_t)row * g.ldh + col]) : 0.0f;
-            v[j] = acc * (hv > 0.0f ? 1.0f : hv + 1.0f);
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = full ? *reinterpret_cast<const float4*>(g.bias + col0 + j)
+                             : make_float4(col0 + j < g.N ? g.bias[col0 + j] : 0.f, col0 + j + 1 < g.N ? g.bias[col0 + j + 1] : 0.f,
+                                           col0 + j + 2 < g.N ? g.bias[col0 + j + 2] : 0.f, col0 + j + 3 < g.N ? g.bias[col0 + j + 3] : 0.f);
+            float a0 = __uint_as_float(r[j]) + b4.x, a1 = __uint_as_float(r[j + 1]) + b4.y, a2 = __uint_as_float(r[j + 2]) + b4.z,
+                  a3 = __uint_as_float(r[j + 3]) + b4.w;
+            v[j] = a0 > 0.0f ? a0 : (__expf(a0) - 1.0f); v[j + 1] = a1 > 0.0f ? a1 : (__expf(a1) - 1.0f);
+            v[j + 2] = a2 > 0.0f ? a2 : (__expf(a2) - 1.0f); v[j + 3] = a3 > 0.0f ? a3 : (__expf(a3) - 1.0f);
           }
-        }
-        if (row_ok) {
-          if (col0 + 32 <= g.N) {
-            uint4* dst = reinterpret_cast<uint4*>(g.out + (size_t)row * g.ldo + col0);
+        } else {
+          if (row_ok && full && (g.ldh & 7) == 0) {     // 4 x 16-byte loads of the layer's own activations
+            const uint4* hp = reinterpret_cast<const uint4*>(g.h + (size_t)row * g.ldh + col0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-              u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-              dst[q] = u;
+              uint4 u = hp[q];
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e2 = 0; e2 < 4; ++e2) {
+                float2 hv = __bfloat1622float2(h2[e2]);
+                int j = 8 * q + 2 * e2;
+                v[j] = __uint_as_float(r[j]) * (hv.x > 0.0f ? 1.0f : hv.x + 1.0f);
+                v[j + 1] = __uint_as_float(r[j + 1]) * (hv.y > 0.0f ? 1.0f : hv.y + 1.0f);
+              }
             }
           } else {
-            for (int j = 0; j < 32 && col0 + j < g.N; ++j) g.out[(size_t)row * g.ldo + col0 + j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float hv = (row_ok && col0 + j < g.N) ? __bfloat162float(g.h[(size_t)row * g.ldh + col0 + j]) : 0.0f;
+              v[j] = __uint_as_float(r[j]) * (hv > 0.0f ? 1.0f : hv + 1.0f);
+            }
           }
         }
-        if (g.out_t) {   // transposed copy: for a fixed column the 32 lanes hold 32 consecutive rows -> coalesced
+        // stage the bf16 results in shared memory (the pipeline stages are free once tmem_full has fired) in the layouts
+        // of 128B- / 64B-swizzled TMA boxes; one TMA store per box writes full, coalesced lines
+        {
+          unsigned char* rm = reinterpret_cast<unsigned char*>(&S.a[0][0]) + lg * 8192 + (c >> 1) * 4096;   // [32 rows][64 cols] box
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (row_ok && col0 + j < g.N) g.out_t[(size_t)(col0 + j) * g.ldt + row] = __float2bfloat16_rn(v[j]);
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+            const int cc = (c & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(rm + lane * 128 + ((cc ^ (lane & 7)) << 4)) = u;
+          }
+          if (g.out_t) {
+            unsigned char* tb = reinterpret_cast<unsigned char*>(&S.b[0][0]) + lg * 8192;                  // [128 n][32 m] box, 64 B rows
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int nl = c * 32 + j;
+              *reinterpret_cast<__nv_bfloat16*>(tb + nl * 64 + ((((lane >> 3) ^ ((nl >> 1) & 3))) << 4) + (lane & 7) * 2) = __float2bfloat16_rn(v[j]);
+            }
+          }
         }
       } else {
         if (row_ok) {
@@ -206,6 +236,18 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
               }
           }
         }
+      }
+    }
+    if (MODE == 0 || MODE == 1) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        const unsigned char* rm = reinterpret_cast<const unsigned char*>(&S.a[0][0]) + lg * 8192;
+        tma_store_2d(&mapO, rm, n0, m0 + lg * 32);
+        if (n0 + 64 < g.N) tma_store_2d(&mapO, rm + 4096, n0 + 64, m0 + lg * 32);
+        if (g.out_t) tma_store_2d(&mapT, reinterpret_cast<const unsigned char*>(&S.b[0][0]) + lg * 8192, m0 + lg * 32, n0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       }
     }
   }

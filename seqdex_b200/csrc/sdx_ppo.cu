@@ -31,16 +31,16 @@ static int get_encode() {
   return 0;
 }
 
-// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64 cols], 128B swizzle
-static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x box_cols], 128B or 64B swizzle
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = GEMM_BK,
+                    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B) {
   if (get_encode()) return -1;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {GEMM_BK, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { char b[160]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld); sdx_set_error(b); return -1; }
   return 0;
 }
@@ -68,9 +68,15 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
                                 int splits, void* stream) {
   if (set_attrs()) return -1;
   if ((lda % 8) || (ldb % 8) || M <= 0 || N <= 0 || K <= 0) { sdx_set_error("sdx_gemm_bf16_tn: bad shape (ld must be a multiple of 8)"); return -1; }
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mo, mt;
   if (make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1;
   if (make_map(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, GEMM_BN)) return -1;
+  mo = ma; mt = ma;   // placeholders when the mode has no bf16 output
+  if (mode == 0 || mode == 1) {
+    if (!out || (ldo % 8) || (out_t && (ldt % 8))) { sdx_set_error("sdx_gemm_bf16_tn: bf16 outputs need ld % 8 == 0"); return -1; }
+    if (make_map(&mo, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;                   // [32 rows x 64 cols] boxes
+    if (out_t && make_map(&mt, out_t, (uint64_t)N, (uint64_t)M, (uint64_t)ldt, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;         // [128 n x 32 m] boxes
+  }
   GemmArgs g;
   g.M = M; g.N = N; g.K = K;
   int total_kb = (K + GEMM_BK - 1) / GEMM_BK;
@@ -84,11 +90,11 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
   size_t smem = sizeof(GSm) + 1024;
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {
-    case 0: k_gemm_tn<GEMM_BN, GEMM_STAGES, 0><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
-    case 1: k_gemm_tn<GEMM_BN, GEMM_STAGES, 1><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
-    case 2: k_gemm_tn<GEMM_BN, GEMM_STAGES, 2><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
-    case 3: k_gemm_tn<GEMM_BN, GEMM_STAGES, 3><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
-    case 4: k_gemm_tn<GEMM_BN, GEMM_STAGES, 4><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, g); break;
+    case 0: k_gemm_tn<GEMM_BN, GEMM_STAGES, 0><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
+    case 1: k_gemm_tn<GEMM_BN, GEMM_STAGES, 1><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
+    case 2: k_gemm_tn<GEMM_BN, GEMM_STAGES, 2><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
+    case 3: k_gemm_tn<GEMM_BN, GEMM_STAGES, 3><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
+    case 4: k_gemm_tn<GEMM_BN, GEMM_STAGES, 4><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
     default: sdx_set_error("sdx_gemm_bf16_tn: bad mode"); return -1;
   }
   g_ppo_launches++;

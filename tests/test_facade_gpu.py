@@ -20,7 +20,9 @@ def test_refresh_root_rb_dof_jacobian(scene, oracle_lib):
         g.refresh(name)
     torch.cuda.synchronize()
     root = g.tensor("ROOT").view(n, 142, 13).cpu().numpy()
-    assert np.array_equal(root[:, 9:81], o.brick_roots())                       # 72 free bricks, actor slots 9..80
+    ref = o.brick_roots()
+    assert np.array_equal(g.tensor('BRICK').cpu().numpy(), o.brick), 'internal state differs'
+    assert np.array_equal(root[:, 9:81], ref), f'max diff {np.abs(root[:, 9:81] - ref).max()} at {np.argwhere(root[:, 9:81] != ref)[:4]}'   # 72 free bricks, actor slots 9..80
     fixed = np.ctypeslib.as_array(scene.c.fixed_root).reshape(60, 13)
     assert np.allclose(root[:, 81:141], fixed[None])                            # 60 fixed bricks
     assert np.allclose(root[:, 0, :7], [-0.35, 0, 0.6, 0, 0, 0, 1])             # hand actor root (GS:625)
