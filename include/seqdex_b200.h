@@ -58,7 +58,7 @@ typedef struct sdx_scene_t {
   float brick_init[SDX_MAX_BRICKS * 13];
   float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
   float cam_off_pos[3], cam_off_quat[4];
-  float act_moving_average, av_factor, vel_obs_scale, pad3[2];
+  float act_moving_average, av_factor, vel_obs_scale, warm_start, pad3;
 } sdx_scene_t;
 
 /* Tensor kinds for sdx_tensor(): device buffers owned by the env. dtype 0=f32 1=i64 2=i32 */
@@ -85,7 +85,9 @@ enum {
   SDX_T_JACOBIAN = 19,  /* f32 [N][23][6][23] jacobian tensor, filled by sdx_refresh                  */
   SDX_T_EPISODE = 20,   /* i32 [N]       per-env episode counter (keys the reset RNG)                */
   SDX_T_CONTACTS = 21,  /* f32 [N][SDX_MAX_CONTACTS][8] debug dump of the last sub-step's contacts   */
-  SDX_T_COUNT = 22
+  SDX_T_WS = 22,        /* f32 [N][2][SDX_MAX_CONTACTS][4] contact-impulse cache (key bits, f.xyz), double buffered  */
+  SDX_T_WSN = 23,       /* i32 [N][2]    entries in each cache buffer                                           */
+  SDX_T_COUNT = 24
 };
 
 typedef struct sdx_env sdx_env_t;

@@ -88,6 +88,9 @@ class OracleEnv:
         self.ncontact = np.zeros((n, 2), np.int32)
         self.episode = np.zeros(n, np.int32)
         self.condump = np.zeros((n, MAXC, 8), np.float32)
+        self.ws = np.zeros((n, 2, MAXC, 4), np.float32)
+        self.wsn = np.zeros((n, 2), np.int32)
+        self.ws_cur = 0
         self.gb_hand = np.zeros((8, 11024, 23, 2), np.float32)
         self.gb_obj = np.zeros((8, 11024, 13), np.float32)
         self.gb_index = np.zeros(8, np.int32)
@@ -112,6 +115,7 @@ class OracleEnv:
         self.dof[:, 2, :] = q
         self.progress[:] = 0
         self.reset[:] = 1
+        self.wsn[:] = 0
         self.refresh_links()
 
     def set_brick_roots(self, rows):
@@ -133,14 +137,15 @@ class OracleEnv:
     # ---- BaseTask.step phases
     def simulate(self, dump=False):
         self.L.sdxo_simulate(self.S, self.n, fp(self.brick), fp(self.dof), fp(self.link), fp(self.jac7), fp(self.netf),
-                             ip(self.ncontact), fp(self.condump) if dump else None)
+                             ip(self.ncontact), fp(self.condump) if dump else None, fp(self.ws), ip(self.wsn), self.ws_cur)
+        self.ws_cur ^= self.scene.c.substeps & 1
 
     def pre_physics(self, actions):
         if self.reset.any():
             assert self.bank is not None, "reset needs a heap bank (GS:412-413)"
             self.L.sdxo_reset(self.S, self.n, ctypes.c_uint64(self.seed), fp(self.bank), self.per_type, fp(self.brick),
                               fp(self.dof), fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.successes),
-                              ip(self.episode), int(self.total_steps > 0), fp(self.finger_dist), fp(self.tvalue),
+                              ip(self.episode), ip(self.wsn), int(self.total_steps > 0), fp(self.finger_dist), fp(self.tvalue),
                               fp(self.gb_hand), fp(self.gb_obj), ip(self.gb_index))
         a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)   # VR:166
         self.L.sdxo_pre_physics(self.S, self.n, fp(a), fp(self.actions), fp(self.dof), fp(self.link), fp(self.jac7),

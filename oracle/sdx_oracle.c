@@ -63,7 +63,7 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   float brick_init[SDX_MAX_BRICKS * 13];
   float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
   float cam_off_pos[3], cam_off_quat[4];
-  float act_moving_average, av_factor, vel_obs_scale, pad3[2];
+  float act_moving_average, av_factor, vel_obs_scale, warm_start, pad3;
 } sdx_scene_t;
 
 /* ------------------------------------------------------------------ math */
@@ -227,6 +227,7 @@ typedef struct {
   /* incidence of body b, in summation order: owner-side contacts [astart,aend) then target-side list (ascending) */
   int astart[NBODY], aend[NBODY], boff[NBODY + 1]; unsigned short blist[SDX_MAX_CONTACTS];
   v3 linkF[SDX_NL], linkM[SDX_NL];
+  uint32_t ckey[SDX_MAX_CONTACTS];
 } work_t;
 
 static inline v3 brick_Iinv_mul(const sdx_scene_t* S, const work_t* W, int b, v3 u) {
@@ -277,8 +278,9 @@ static float body_k(const sdx_scene_t* S, const work_t* W, int body, v3 wpt, v3 
 /* one env, one control step = `substeps` sub-steps (gym.simulate, BT:140; yaml sim: substeps 2,
  * 16 position iterations).  brick: [13][72]; dof: [3][24]; link_out: [24][13]; jac7: [6][7];
  * netf: [24][3]; ncontact: [2]; condump: [MAXC][8] or NULL */
+/* ws: [2][MAXC][4] impulse cache of this env (key bits, f.xyz), wsn: [2] entry counts, ws_cur: buffer holding the latest list */
 static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_out, float* jac7, float* netf,
-                    int* ncontact, float* condump, work_t* W) {
+                    int* ncontact, float* condump, float* ws, int* wsn, int ws_cur, work_t* W) {
   const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;
   const int n_owner = NB + nrs, n_target = NB + nrs + nst;
   const float h = S->dt / (float)S->substeps;
@@ -299,7 +301,11 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     W->sbody[t] = STATIC_BODY;
     W->srad[t] = 0.0f;
   }
+  int rb = ws_cur;
   for (int sub = 0; sub < S->substeps; ++sub) {
+    const float* wsr = ws + (size_t)rb * SDX_MAX_CONTACTS * 4;
+    float* wsw = ws + (size_t)(1 - rb) * SDX_MAX_CONTACTS * 4;
+    const int nprev = wsn[rb];
     /* 1. kinematics + shape poses */
     robot_fk(S, W->q, &W->K);
     for (int L = 0; L < SDX_NL; ++L) { W->bx[NB + L] = W->K.lx[L]; W->bq[NB + L] = W->K.lq[L]; qmat(W->K.lq[L], W->bR[NB + L]); }
@@ -422,6 +428,20 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           else if (depth < 0.0f) bias = depth / h;
           c->bias = bias;
           c->f[0] = c->f[1] = c->f[2] = 0.0f;
+          {   /* warm start: a contact is identified by (owner shape, target shape, sample point); keys ascend with the contact order */
+            uint32_t key = ((uint32_t)a << 12) | ((uint32_t)t << 4) | (uint32_t)p;
+            W->ckey[W->ncon - 1] = key;
+            if (S->warm_start > 0.0f) {
+              int lo = 0, hi = nprev - 1;
+              while (lo <= hi) {
+                int mid = (lo + hi) >> 1;
+                union { float f; uint32_t u; } kv; kv.f = wsr[4 * mid];
+                if (kv.u < key) lo = mid + 1;
+                else if (kv.u > key) hi = mid - 1;
+                else { c->f[0] = S->warm_start * wsr[4 * mid + 1]; c->f[1] = S->warm_start * wsr[4 * mid + 2]; c->f[2] = S->warm_start * wsr[4 * mid + 3]; break; }
+              }
+            }
+          }
           c->inv[0] = depth; /* scratch: kept for the debug dump, overwritten below */
         }
       }
@@ -464,8 +484,8 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       c->inv[2] = 1.0f / (body_k(S, W, a, wpt, t2) + body_k(S, W, b, wpt, t2));
     }
     /* 6. mass-splitting Jacobi iterations on the total impulses */
-    for (int it = 0; it < S->iters; ++it) {
-      for (int i = 0; i < W->ncon; ++i) { /* phase A: one contact each */
+    for (int it = -1; it < S->iters; ++it) { /* it = -1: only phase B, i.e. apply the warm-start impulses */
+      if (it >= 0) for (int i = 0; i < W->ncon; ++i) { /* phase A: one contact each */
         contact_t* c = &W->con[i];
         int a = c->word & 255, b = (c->word >> 8) & 255;
         v3 n, t1, t2; contact_axes(W, c, &n, &t1, &t2);
@@ -512,6 +532,12 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       }
       link_twists(S, W);
     }
+    for (int i = 0; i < W->ncon; ++i) {
+      union { float f; uint32_t u; } kv; kv.u = W->ckey[i];
+      wsw[4 * i] = kv.f; wsw[4 * i + 1] = W->con[i].f[0]; wsw[4 * i + 2] = W->con[i].f[1]; wsw[4 * i + 3] = W->con[i].f[2];
+    }
+    wsn[1 - rb] = W->ncon;
+    rb = 1 - rb;
     if (S->iters == 0) for (int L = 0; L < SDX_NL; ++L) { W->linkF[L] = V3(0, 0, 0); W->linkM[L] = V3(0, 0, 0); }
     /* 7. integrate */
     for (int b = 0; b < nbr; ++b) {
@@ -568,7 +594,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
 }
 
 typedef struct {
-  const sdx_scene_t* S; int n; float *brick, *dof, *link, *jac7, *netf; int* ncontact; float* condump;
+  const sdx_scene_t* S; int n; float *brick, *dof, *link, *jac7, *netf; int* ncontact; float* condump; float* ws; int* wsn; int ws_cur;
   int tid, nthreads;
 } sim_job_t;
 static void* sim_worker(void* arg) {
@@ -577,7 +603,8 @@ static void* sim_worker(void* arg) {
   for (int e = J->tid; e < J->n; e += J->nthreads)
     sim_env(J->S, J->brick + (size_t)e * 13 * NB, J->dof + (size_t)e * 72, J->link + (size_t)e * SDX_NL * 13,
             J->jac7 + (size_t)e * 42, J->netf + (size_t)e * SDX_NL * 3, J->ncontact + 2 * e,
-            J->condump ? J->condump + (size_t)e * SDX_MAX_CONTACTS * 8 : 0, W);
+            J->condump ? J->condump + (size_t)e * SDX_MAX_CONTACTS * 8 : 0, J->ws + (size_t)e * 2 * SDX_MAX_CONTACTS * 4, J->wsn + 2 * e,
+            J->ws_cur, W);
   free(W);
   return 0;
 }
@@ -590,14 +617,14 @@ int sdxo_get_threads(void) {
 }
 /* envs are independent: static round-robin over host threads (results do not depend on the thread count) */
 void sdxo_simulate(const sdx_scene_t* S, int n, float* brick, float* dof, float* link, float* jac7, float* netf,
-                   int* ncontact, float* condump) {
+                   int* ncontact, float* condump, float* ws, int* wsn, int ws_cur) {
   int nt = sdxo_get_threads();
   if (nt > n) nt = n;
   if (nt < 1) nt = 1;
   if (nt > 256) nt = 256;
   pthread_t th[256]; sim_job_t jobs[256];
   for (int t = 0; t < nt; ++t) {
-    sim_job_t j = {S, n, brick, dof, link, jac7, netf, ncontact, condump, t, nt};
+    sim_job_t j = {S, n, brick, dof, link, jac7, netf, ncontact, condump, ws, wsn, ws_cur, t, nt};
     jobs[t] = j;
     if (t > 0) pthread_create(&th[t], 0, sim_worker, &jobs[t]);
   }
@@ -711,7 +738,7 @@ void sdxo_control_ik(int n, const float* J, const float* dpose, float* u) { for 
  * not restated (DESIGN.md "reset"): the randomised target pose (GS:1488-1499) is overwritten by the
  * banked heap row (GS:1508-1511) and perturb_* (GS:1460-1461) feed a disabled branch. */
 void sdxo_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* bank, int per_type, float* brick, float* dof,
-                float* target_init, int64_t* progress, int64_t* reset, float* successes, int* episode,
+                float* target_init, int64_t* progress, int64_t* reset, float* successes, int* episode, int* wsn,
                 /* grasp terminal-state banking (GS:1399-1445) */
                 int do_bank, const float* finger_dist, const float* tvalue, float* gb_hand, float* gb_obj, int* gb_index) {
   if (do_bank) {
@@ -755,6 +782,7 @@ void sdxo_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* bank, i
     int tb = target_brick(e);
     for (int k = 0; k < 7; ++k) target_init[7 * e + k] = rows[tb * 13 + k]; /* GS:1547-1548 */
     progress[e] = 0; reset[e] = 0; successes[e] = 0.0f; /* GS:1550-1552 */
+    wsn[2 * e] = 0; wsn[2 * e + 1] = 0; /* a new heap: no contact persists */
     episode[e] += 1;
   }
 }

@@ -36,6 +36,7 @@ struct sdx_env {
   float *stage_obs = nullptr, *stage_states = nullptr, *stage_actions = nullptr;
   int per_type = 0;
   long long total_steps = 0, launches = 0;
+  int ws_cur = 0;          // which impulse-cache buffer holds the latest contact list
   bool dump_contacts = false;
 };
 
@@ -62,6 +63,8 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
     case SDX_T_JACOBIAN: s[0] = n; s[1] = SDX_ND; s[2] = 6; s[3] = SDX_ND; nd = 4; break;
     case SDX_T_EPISODE: s[0] = n; dt = 2; break;
     case SDX_T_CONTACTS: s[0] = n; s[1] = SDX_MAX_CONTACTS; s[2] = 8; nd = 3; break;
+    case SDX_T_WS: s[0] = n; s[1] = 2; s[2] = SDX_MAX_CONTACTS; s[3] = 4; nd = 4; break;
+    case SDX_T_WSN: s[0] = n; s[1] = 2; nd = 2; dt = 2; break;
     default: return 0;
   }
   if (shape) for (int i = 0; i < 4; ++i) shape[i] = s[i];
@@ -228,6 +231,7 @@ extern "C" int sdx_set_tvalue_weights(sdx_env_t* E, const float* w) {
 
 extern "C" int sdx_reset_all(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
+  CK(cudaMemsetAsync(E->buf[SDX_T_WSN], 0, (size_t)E->n * 2 * 4, E->stream));
   k_reset_all<<<E->n, 128, 0, E->stream>>>(E->scene, E->n, F(SDX_T_BRICK), F(SDX_T_DOF), I64(SDX_T_PROGRESS), I64(SDX_T_RESET));
   CKL();
   k_refresh_links<<<(E->n + 63) / 64, 64, 0, E->stream>>>(E->scene, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7), E->n);
@@ -246,7 +250,7 @@ extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
     E->launches++;
   }
   k_reset<<<n, 128, 0, E->stream>>>(E->scene, n, E->seed, E->bank, E->per_type, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_TARGET_INIT),
-                                    I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), I32(SDX_T_EPISODE));
+                                    I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), I32(SDX_T_EPISODE), I32(SDX_T_WSN));
   k_pre_physics<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, actions_dev, F(SDX_T_ACTIONS), F(SDX_T_DOF), F(SDX_T_LINK),
                                                         F(SDX_T_JAC7), I64(SDX_T_PROGRESS), F(SDX_T_TARGET_INIT));
   E->launches += 2;
@@ -258,7 +262,9 @@ extern "C" int sdx_simulate(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
   k_simulate<<<E->n, SIM_THREADS, sizeof(SimSmem), E->stream>>>(E->scene, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
                                                               F(SDX_T_NETF), I32(SDX_T_NCONTACT),
-                                                              E->dump_contacts ? F(SDX_T_CONTACTS) : nullptr, E->n);
+                                                              E->dump_contacts ? F(SDX_T_CONTACTS) : nullptr, F(SDX_T_WS), I32(SDX_T_WSN),
+                                                              E->ws_cur, E->n);
+  E->ws_cur ^= (E->host_scene.substeps & 1);
   E->launches++;
   CKL();
   return 0;

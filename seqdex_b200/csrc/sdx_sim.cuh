@@ -203,7 +203,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 __global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
-           int* __restrict__ ncontact, float* __restrict__ condump, int n_envs) {
+           int* __restrict__ ncontact, float* __restrict__ condump, float* ws, int* wsn, int ws_cur, int n_envs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SimSmem& M = *reinterpret_cast<SimSmem*>(smem_raw);
   const int e = blockIdx.x, tid = threadIdx.x;
@@ -275,7 +275,14 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   }
   __syncthreads();
 
+  float* gws = ws + (size_t)e * 2 * MAXC * 4;
+  int* gwsn = wsn + 2 * e;
+  const float warm = S->warm_start;
+  int rb = ws_cur;
   for (int sub = 0; sub < substeps; ++sub) {
+    const float* wsr = gws + (size_t)rb * MAXC * 4;        // impulse cache of the previous sub-step / step
+    float* wsw = gws + (size_t)(1 - rb) * MAXC * 4;
+    const int nprev = gwsn[rb];
     // 1. kinematics (one thread walks the chain) || brick poses + free velocities
     if (tid >= ROBOT_TID0) robot_fk(S, M, tid - ROBOT_TID0);
     if (tid < NB) {
@@ -434,7 +441,22 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
         else if (depth < 0.0f) bias = depth / h;
         M.cbias[slot] = bias;
-        M.cf[0][slot] = 0.0f; M.cf[1][slot] = 0.0f; M.cf[2][slot] = 0.0f;
+        {   // warm start from the cached impulse of the same (owner shape, target shape, sample point), if it persisted
+          const uint32_t key = ((uint32_t)a << 12) | ((uint32_t)t << 4) | (uint32_t)p;
+          wsw[4 * slot] = __uint_as_float(key);
+          v3 f0 = V3(0.0f, 0.0f, 0.0f);
+          if (warm > 0.0f) {
+            int lo2 = 0, hi2 = nprev - 1;
+            while (lo2 <= hi2) {
+              int mid = (lo2 + hi2) >> 1;
+              uint32_t kv = __float_as_uint(wsr[4 * mid]);
+              if (kv < key) lo2 = mid + 1;
+              else if (kv > key) hi2 = mid - 1;
+              else { f0 = V3(warm * wsr[4 * mid + 1], warm * wsr[4 * mid + 2], warm * wsr[4 * mid + 3]); break; }
+            }
+          }
+          M.cf[0][slot] = f0.x; M.cf[1][slot] = f0.y; M.cf[2][slot] = f0.z;
+        }
         M.cinv[0][slot] = depth;
       }
     }
@@ -502,7 +524,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     __syncthreads();
     // 9. Jacobi iterations on total impulses
     const float mu = S->friction;
-    for (int it = 0; it < iters; ++it) {
+    for (int it = -1; it < iters; ++it) {                      // it = -1: phase B only = apply the warm-start impulses
+      if (it >= 0)
       for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
         uint32_t wd = M.cword[i];
         int a = wd & 255, b = (wd >> 8) & 255;
@@ -567,6 +590,9 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       }
       __syncthreads();
     }
+    for (int i = tid; i < ncon; i += SIM_THREADS) { wsw[4 * i + 1] = M.cf[0][i]; wsw[4 * i + 2] = M.cf[1][i]; wsw[4 * i + 3] = M.cf[2][i]; }
+    if (tid == 0) gwsn[1 - rb] = ncon;
+    rb = 1 - rb;
     if (iters == 0 && tid < SDX_NL) { st3(M.linkF[tid], V3(0, 0, 0)); st3(M.linkM[tid], V3(0, 0, 0)); }
     // 10. integrate
     if (tid < nbr) {

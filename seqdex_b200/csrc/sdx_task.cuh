@@ -135,7 +135,7 @@ k_bank_terminal(const sdx_scene_t* __restrict__ S, int n, const float* __restric
 __global__ void __launch_bounds__(128)
 k_reset(const sdx_scene_t* __restrict__ S, int n, uint64_t seed, const float* __restrict__ bank, int per_type,
         float* __restrict__ brick, float* __restrict__ dof, float* __restrict__ target_init, int64_t* __restrict__ progress,
-        int64_t* __restrict__ reset, float* __restrict__ successes, int* __restrict__ episode) {
+        int64_t* __restrict__ reset, float* __restrict__ successes, int* __restrict__ episode, int* __restrict__ wsn) {
   const int e = blockIdx.x, tid = threadIdx.x;
   if (e >= n || !reset[e]) return;
   const int ep = episode[e];
@@ -163,6 +163,7 @@ k_reset(const sdx_scene_t* __restrict__ S, int n, uint64_t seed, const float* __
     int tb = target_brick(e);
     for (int k = 0; k < 7; ++k) target_init[7 * e + k] = rows[tb * 13 + k];         // GS:1547-1548
     progress[e] = 0; reset[e] = 0; successes[e] = 0.0f; episode[e] = ep + 1;        // GS:1550-1552
+    wsn[2 * e] = 0; wsn[2 * e + 1] = 0;                                             // a new heap: no contact persists
   }
 }
 

@@ -63,7 +63,12 @@ def test_contact_step_bit_exact(scene, oracle_lib, steps):
     _cmp("link", g.tensor("LINK"), o.link)
     _cmp("jac7", g.tensor("JAC7"), o.jac7)
     _cmp("netf", g.tensor("NETF"), o.netf)
+    _cmp("impulse-cache counts", g.tensor("WSN"), o.wsn)
+    gws = g.tensor("WS").cpu().numpy()
+    for e in range(o.n):     # warm-start cache: same keys, same impulses (latest buffer)
+        _cmp(f"impulse cache env{e}", gws[e, o.ws_cur, :nc[e]], o.ws[e, o.ws_cur, :nc[e]])
     assert o.ncontact[:, 0].max() > 100, "test must exercise contacts"
+    assert (np.abs(o.ws[:, o.ws_cur, :, 1:]).sum() > 0), "impulses must be cached"
 
 
 def test_robot_contacts_exercised(scene, oracle_lib):
