@@ -498,11 +498,18 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       M.nb[tid] = (M.aend[tid] - M.astart[tid]) + (o1 - o0);
     }
     __syncthreads();
-    if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND) {
-      int nn = 0;
-      unsigned m = my_desc;
-      while (m) { int L = __ffs(m) - 1; m &= m - 1; nn += M.nb[NB + L]; }
-      M.nj[tid - ROBOT_TID0] = nn;
+    unsigned ract = 0u;                                        // robot warp: links with at least one contact
+    if (tid >= ROBOT_TID0) {
+      const int L = tid - ROBOT_TID0;
+      const bool has = L < SDX_NL && M.nb[NB + L] > 0;
+      ract = __ballot_sync(0xffffffffu, has);
+      if (L < SDX_NL && !has) { st3(M.linkF[L], V3(0.0f, 0.0f, 0.0f)); st3(M.linkM[L], V3(0.0f, 0.0f, 0.0f)); }
+      if (L < SDX_ND) {
+        int nn = 0;
+        unsigned m = my_desc;
+        while (m) { int L2 = __ffs(m) - 1; m &= m - 1; nn += M.nb[NB + L2]; }
+        M.nj[L] = nn;
+      }
     }
     if (condump && sub == substeps - 1)
       for (int i = tid; i < ncon; i += SIM_THREADS) {
@@ -544,14 +551,20 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       }
       __syncthreads();
       // phase B: FOUR lanes per body, lane k sums incidences e = k (mod 4); partials combined (0+1)+(2+3).
-      // brick warps (all but the last): 72 bricks x 4 lanes = 288 items, ROBOT_TID0 per pass; last warp: 24 links x 4 lanes.
+      // brick warps (all but the last): 72 bricks x 4 lanes = 288 items, ROBOT_TID0 per pass.
+      // last warp: the articulation -- only links that HAVE contacts are gathered (their wrenches are zero otherwise, set
+      // once per sub-step), and the joint-space update is skipped entirely while the robot touches nothing.
+      const bool robot_warp = tid >= ROBOT_TID0;
+      const int n_items = robot_warp ? 4 * __popc(ract) : 4 * NB;
+      const int per_pass = robot_warp ? 32 : ROBOT_TID0;
 #pragma unroll 1
-      for (int pass = 0; pass < 3; ++pass) {
-        const int item = tid < ROBOT_TID0 ? pass * ROBOT_TID0 + tid : pass * 32 + (tid - ROBOT_TID0);
-        if (tid < ROBOT_TID0 && item >= 4 * NB) continue;       // warp-uniform (288 and ROBOT_TID0 are multiples of 32)
-        const int body = tid < ROBOT_TID0 ? (item >> 2) : NB + (item >> 2);
+      for (int base = 0; base < n_items; base += per_pass) {
+        const int item = base + (robot_warp ? tid - ROBOT_TID0 : tid);
+        if (!robot_warp && item >= n_items) continue;           // warp-uniform (288 and ROBOT_TID0 are multiples of 32)
+        const bool live = item < n_items;
+        const int body = !robot_warp ? (item >> 2) : NB + (live ? (int)__fns(ract, 0, (item >> 2) + 1) : 0);
         const int k = item & 3;
-        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = na + (M.boff[body + 1] - b0);
+        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
         const v3 xb = body < NB ? ld3(M.bx[body]) : V3(0.0f, 0.0f, 0.0f);
         v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
         for (int ee = k; ee < ntot; ee += 4) {
@@ -567,14 +580,14 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
         F.x += __shfl_xor_sync(0xffffffffu, F.x, 2); F.y += __shfl_xor_sync(0xffffffffu, F.y, 2); F.z += __shfl_xor_sync(0xffffffffu, F.z, 2);
         T.x += __shfl_xor_sync(0xffffffffu, T.x, 2); T.y += __shfl_xor_sync(0xffffffffu, T.y, 2); T.z += __shfl_xor_sync(0xffffffffu, T.z, 2);
-        if (k == 0) {
+        if (k == 0 && live) {
           if (body < NB) {
             st3(M.bv[body], vmad(F, M.binvm[body], ld3(M.vfree[body])));
             st3(M.bw[body], vadd(ld3(M.wfree[body]), brick_Iinv_mul(M.sR[body], ld3(M.binvI[body]), T)));
           } else { st3(M.linkF[body - NB], F); st3(M.linkM[body - NB], T); }
         }
       }
-      if (tid >= ROBOT_TID0) {                                 // the articulation lives in one warp
+      if (robot_warp && ract != 0u) {                          // joint-space impulse + link twists (one warp)
         __syncwarp();
         if (tid < ROBOT_TID0 + SDX_ND) {
           int j = tid - ROBOT_TID0;
