@@ -501,9 +501,9 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         f = vmad(t2, l2, vmad(t1, l1, vscale(n, ln)));
         c->f[0] = f.x; c->f[1] = f.y; c->f[2] = f.z;
       }
-      for (int b = 0; b < NBODY; ++b) { /* phase B: one body each; 4 strided partial sums, combined (0+1)+(2+3) */
-        v3 Fk[4], Tk[4];
-        for (int k = 0; k < 4; ++k) { Fk[k] = V3(0, 0, 0); Tk[k] = V3(0, 0, 0); }
+      for (int b = 0; b < NBODY; ++b) { /* phase B: one body each; TWO interleaved partial sums (even / odd incidences), combined 0+1 */
+        v3 Fk[2], Tk[2];
+        for (int k = 0; k < 2; ++k) { Fk[k] = V3(0, 0, 0); Tk[k] = V3(0, 0, 0); }
         int na = W->aend[b] - W->astart[b], nbl = W->boff[b + 1] - W->boff[b];
         v3 xb = b < NB ? W->bx[b] : V3(0, 0, 0);
         for (int e = 0; e < na + nbl; ++e) {
@@ -512,12 +512,12 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           v3 f = V3(c->f[0], c->f[1], c->f[2]);
           if (e >= na) f = vneg(f);
           v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
-          int k = e & 3;
+          int k = e & 1;
           Fk[k] = vadd(Fk[k], f);
           Tk[k] = vadd(Tk[k], vcross(vsub(wpt, xb), f));
         }
-        v3 F = vadd(vadd(Fk[0], Fk[1]), vadd(Fk[2], Fk[3]));
-        v3 T = vadd(vadd(Tk[0], Tk[1]), vadd(Tk[2], Tk[3]));
+        v3 F = vadd(Fk[0], Fk[1]);
+        v3 T = vadd(Tk[0], Tk[1]);
         if (b < NB) {
           W->bv[b] = vmad(F, S->br_invm[b], W->vfree[b]);
           W->bw[b] = vadd(W->wfree[b], brick_Iinv_mul(S, W, b, T));

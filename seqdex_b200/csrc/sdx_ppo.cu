@@ -192,6 +192,29 @@ __global__ void k_sync_w(const float* __restrict__ w, int N, int Kreal, __nv_bfl
   if (Wt && i < Kreal * Npad) { int k = i / Npad, n = i % Npad; Wt[(size_t)k * ldwt + n] = __float2bfloat16_rn(n < N ? w[(size_t)n * Kreal + k] : 0.0f); }
 }
 
+struct LayerTab {
+  const float* w[4]; __nv_bfloat16* W[4]; __nv_bfloat16* Wt[4]; int N[4], Kreal[4], Kpad[4], Npad[4];
+  const float* gW[4]; float* gw[4]; float* gb[4]; int kones[4], ldg[4];
+};
+// all four layers in one launch (blockIdx.y = layer): fp32 master -> bf16 W [N][Kpad] and W^T [Kreal][Npad]
+__global__ void k_sync_all(LayerTab t) {
+  int l = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  int N = t.N[l], Kreal = t.Kreal[l], Kpad = t.Kpad[l], Npad = t.Npad[l];
+  const float* w = t.w[l];
+  if (i < N * Kpad) { int n = i / Kpad, k = i % Kpad; t.W[l][(size_t)n * Kpad + k] = __float2bfloat16_rn(k < Kreal ? w[(size_t)n * Kreal + k] : 0.0f); }
+  if (t.Wt[l] && i < Kreal * Npad) { int k = i / Npad, n = i % Npad; t.Wt[l][(size_t)k * Npad + n] = __float2bfloat16_rn(n < N ? w[(size_t)n * Kreal + k] : 0.0f); }
+}
+// all four layers in one launch: split-K scratch [N][K+16] -> flat gradient vector (weights, then the bias column)
+__global__ void k_unpack_all(LayerTab t) {
+  int l = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  int rows = t.N[l], kreal = t.Kreal[l];
+  if (i >= rows * (kreal + 1)) return;
+  int r = i / (kreal + 1), c = i % (kreal + 1);
+  if (c < kreal) t.gw[l][(size_t)r * kreal + c] = t.gW[l][(size_t)r * t.ldg[l] + c];
+  else t.gb[l][r] = t.gW[l][(size_t)r * t.ldg[l] + t.kones[l]];
+}
+static LayerTab make_tab(sdx_mlp* m);
+
 extern "C" int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sigma, sdx_mlp** out) {
   sdx_mlp* m = new sdx_mlp();
   memset(m, 0, sizeof(*m));
@@ -240,17 +263,27 @@ extern "C" int sdx_mlp_info(sdx_mlp* m, int64_t* nparams, void** params, void** 
   if (adam_v) *adam_v = m->adam_v;
   return 0;
 }
+static LayerTab make_tab(sdx_mlp* m) {
+  LayerTab t;
+  for (int l = 0; l < 4; ++l) {
+    t.w[l] = m->params + m->w_off[l]; t.W[l] = m->W[l]; t.Wt[l] = l > 0 ? m->Wt[l] : nullptr;
+    t.N[l] = m->d[l + 1]; t.Kreal[l] = l == 0 ? m->in_dim : m->d[l]; t.Kpad[l] = m->d[l]; t.Npad[l] = pad64(m->d[l + 1]);
+    t.gW[l] = m->gW[l]; t.gw[l] = m->grads + m->w_off[l]; t.gb[l] = m->grads + m->b_off[l]; t.kones[l] = m->d[l]; t.ldg[l] = m->d[l] + 16;
+  }
+  return t;
+}
 // refresh the bf16 compute copies from the fp32 master parameters (after load / optimiser step)
 extern "C" int sdx_mlp_sync(sdx_mlp* m, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  for (int l = 0; l < 4; ++l) {
-    int N = m->d[l + 1], Kpad = m->d[l], Kreal = l == 0 ? m->in_dim : m->d[l], Npad = pad64(N);
-    int tot = N * Kpad; if (l > 0 && Kreal * Npad > tot) tot = Kreal * Npad;
-    k_sync_w<<<(tot + 255) / 256, 256, 0, st>>>(m->params + m->w_off[l], N, Kreal, m->W[l], Kpad, Kpad, l > 0 ? m->Wt[l] : nullptr, Npad, Npad);
+  {
+    int mx = 0;
+    for (int l = 0; l < 4; ++l) { int a = m->d[l + 1] * m->d[l], b = (l == 0 ? m->in_dim : m->d[l]) * pad64(m->d[l + 1]); mx = a > mx ? a : mx; mx = b > mx ? b : mx; }
+    dim3 grd((mx + 255) / 256, 4);
+    k_sync_all<<<grd, 256, 0, st>>>(make_tab(m));
     g_ppo_launches++;
+    PCK(cudaGetLastError());
+    return 0;
   }
-  PCK(cudaGetLastError());
-  return 0;
 }
 // x: fp32 [M, in_dim] (device).  mean/var (nullable): RunningMeanStd input normalisation.  train != 0 keeps the
 // transposed activations the backward pass needs.  Result: m->out fp32 [M, out_dim].
@@ -282,13 +315,17 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
     int tiles = ((N + 127) / 128) * ((K + 16 + 127) / 128);
     int splits = (148 + tiles - 1) / tiles; if (splits < 1) splits = 1;   // ~one wave of CTAs; fewer splits = fewer fp32 reductions
     if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, m->At[l], K + 16, m->max_rows, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
-    int kreal = l == 0 ? m->in_dim : K;
-    k_unpack_grads<<<(N * (kreal + 1) + 255) / 256, 256, 0, st>>>(m->gW[l], N, kreal, K, ldg, m->grads + m->w_off[l], m->grads + m->b_off[l]);
-    g_ppo_launches++;
     if (l > 0) {
       int Kd = pad64(N);
       if (sdx_gemm_bf16_tn(1, m->dZ[l + 1], M, Kd, Kd, m->Wt[l], K, Kd, nullptr, m->A[l], K, m->dZ[l], K, m->dZt[l], m->max_rows, nullptr, 0, 1, stream)) return -1;
     }
+  }
+  {
+    int mx = 0;
+    for (int l = 0; l < 4; ++l) { int a = m->d[l + 1] * ((l == 0 ? m->in_dim : m->d[l]) + 1); mx = a > mx ? a : mx; }
+    dim3 grd((mx + 255) / 256, 4);
+    k_unpack_all<<<grd, 256, 0, st>>>(make_tab(m));
+    g_ppo_launches++;
   }
   PCK(cudaGetLastError());
   return 0;
@@ -353,6 +390,7 @@ __global__ void k_ppo_actor_loss(const float* __restrict__ mu, const float* __re
   if (threadIdx.x < 4) s_st[threadIdx.x] = 0.0f;
   __syncthreads();
   int e = blockIdx.x * blockDim.x + threadIdx.x;
+  float gk = 0.0f, st0 = 0.0f, st1 = 0.0f, st2 = 0.0f, st3 = 0.0f;
   if (e < M) {
     float nlp = 0.0f, sls = 0.0f, bl = 0.0f, kl = 0.0f;
     for (int i = 0; i < A; ++i) {
@@ -371,15 +409,26 @@ __global__ void k_ppo_actor_loss(const float* __restrict__ mu, const float* __re
     float al = fmaxf(s1, s2);
     // d a_loss / d neglogp: branch s1 -> a * ratio; branch s2 -> a * ratio inside the clip range, else 0
     float g = (s1 >= s2 || inside) ? a * ratio : 0.0f;
-    for (int i = 0; i < A; ++i) {
+    gk = g; st0 = al; st1 = bl; st2 = kl; st3 = inside ? 0.0f : 1.0f;
+  }
+  // per-action pass: every lane takes part in the reductions (inactive rows contribute zeros)
+  for (int i = 0; i < A; ++i) {
+    float contrib = 0.0f;
+    if (e < M) {
       float ls = logstd[i], sg = expf(ls), m_ = mu[(size_t)e * A + i];
       float z = (actions[(size_t)e * A + i] - m_) / sg;
       float db = 2.0f * fmaxf(m_ - 1.1f, 0.0f) + 2.0f * fminf(m_ + 1.1f, 0.0f);
-      dmu[(size_t)e * A + i] = (g * (-z / sg) + bounds_coef * db) * inv_batch;
-      atomicAdd(&s_dl[i], g * (1.0f - z * z) * inv_batch);
+      dmu[(size_t)e * A + i] = (gk * (-z / sg) + bounds_coef * db) * inv_batch;
+      contrib = gk * (1.0f - z * z) * inv_batch;
     }
-    atomicAdd(&s_st[0], al); atomicAdd(&s_st[1], bl); atomicAdd(&s_st[2], kl); atomicAdd(&s_st[3], inside ? 0.0f : 1.0f);
+    for (int o = 16; o; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_dl[i], contrib);
   }
+  for (int o = 16; o; o >>= 1) {
+    st0 += __shfl_xor_sync(0xffffffffu, st0, o); st1 += __shfl_xor_sync(0xffffffffu, st1, o);
+    st2 += __shfl_xor_sync(0xffffffffu, st2, o); st3 += __shfl_xor_sync(0xffffffffu, st3, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&s_st[0], st0); atomicAdd(&s_st[1], st1); atomicAdd(&s_st[2], st2); atomicAdd(&s_st[3], st3); }
   __syncthreads();
   if (threadIdx.x < A) atomicAdd(&dlogstd[threadIdx.x], s_dl[threadIdx.x]);
   if (threadIdx.x < 4) atomicAdd(&stats[threadIdx.x], s_st[threadIdx.x]);

@@ -36,11 +36,18 @@
 #define PPMAX 26                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
 
 struct SimSmem {
-  float tile[13 * NB];                 // TMA landing / staging zone for the brick tile
+  union {                              // lifetimes do not overlap: tile = kernel prologue / epilogue, candidates = broad..narrow phase
+    float tile[13 * NB];               // TMA landing / staging zone for the brick tile
+    struct { unsigned char cand[NOWN][KC]; int ncand[NOWN]; };
+  };
   unsigned long long mbar;
-  float sc[NT][3], sR[NT][9], sh[NT][3], sa[NT][3], spd[NT], srad[NOWN];
+  float sc[NT][3], sR[NT][9], sh[NT][3], srad[NOWN];
+  union {                              // world AABBs + travel bounds live until the narrow phase; the target-side lists after it
+    struct { float sa[NT][3], spd[NT]; };
+    unsigned short blist[MAXC];
+  };
   unsigned char sbody[NT];
-  float bx[NBODY][3], bv[NBODY][3], bw[NBODY][3];
+  float4 bx[NBODY], bv[NBODY], bw[NBODY];      // body origin, linear, angular velocity (16-byte records)
   float vfree[NB][3], wfree[NB][3], binvm[NB], binvI[NB][3];
   float lq[SDX_NL][4], ja[SDX_ND][3], jo[SDX_ND][3];
   float q[SDX_ND + 1], qd[SDX_ND + 1], tgt[SDX_ND + 1], qdfree[SDX_ND + 1], ieff[SDX_ND + 1];
@@ -48,13 +55,13 @@ struct SimSmem {
   int nb[NBODY], nj[SDX_ND + 1];
   // incidence of body b in summation order: owned contacts [astart, aend) then the target-side list (ascending)
   int astart[NBODY], aend[NBODY], boff[NBODY + 1], bcur[NBODY];
-  unsigned short blist[MAXC];
-  unsigned char cand[NOWN][KC];
-  int ncand[NOWN], poff[NOWN + 1];
+  int poff[NOWN + 1];
   int scan[SIM_THREADS];
   int ncon, ndropped;
-  uint32_t cword[MAXC];
-  float cw[3][MAXC], cbias[MAXC], cinv[3][MAXC], cf[3][MAXC];
+  // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
+  float4 ca[MAXC];    // contact point w.xyz | bias
+  float4 cb[MAXC];    // 1/den along n, t1, t2 | packed word (bodies, target shape, face axis, sign)
+  float4 cf4[MAXC];   // total impulse f.xyz | unused
 };
 
 // exclusive prefix sum of arr[0..n) (n <= 256) by ONE warp, in place; returns the total to every lane
@@ -74,6 +81,9 @@ __device__ __forceinline__ int warp_excl_scan(int* arr, int n, int lane) {
 
 __device__ __forceinline__ v3 ld3(const float* p) { return V3(p[0], p[1], p[2]); }
 __device__ __forceinline__ void st3(float* p, v3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ v3 ldv(const float4& p) { float4 t = p; return V3(t.x, t.y, t.z); }          // one LDS.128
+__device__ __forceinline__ v3 ld3(const float4& p) { return ldv(p); }
+__device__ __forceinline__ void st3(float4& p, v3 a) { p = make_float4(a.x, a.y, a.z, 0.0f); }   // one STS.128
 
 // forward kinematics of the collapsed Panda+Allegro tree by ONE WARP: lane 0 walks the 7 arm joints, then lanes 0-3
 // walk the four finger chains (DoFs 7+4f .. 10+4f) concurrently -> dependency depth 11 instead of 23
@@ -238,11 +248,9 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     int t = NB + nrs + s;
     st3(M.sc[t], V3(S->st_c[3 * s], S->st_c[3 * s + 1], S->st_c[3 * s + 2]));
     st3(M.sh[t], V3(S->st_h[3 * s], S->st_h[3 * s + 1], S->st_h[3 * s + 2]));
-    st3(M.sa[t], V3(S->st_h[3 * s], S->st_h[3 * s + 1], S->st_h[3 * s + 2]));
 #pragma unroll
     for (int i = 0; i < 9; ++i) M.sR[t][i] = (i % 4 == 0) ? 1.0f : 0.0f;
     M.sbody[t] = STATIC_BODY;
-    M.spd[t] = 0.0f;
   }
   mbar_wait(&M.mbar, 0);
 
@@ -335,6 +343,11 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       v3 bv = ld3(M.bv[bd]), bw = ld3(M.bw[bd]);
       M.spd[t] = h * (sqrtf(vdot(bv, bv)) + sqrtf(vdot(bw, bw)) * reach);
     }
+    for (int s2 = tid; s2 < nst; s2 += SIM_THREADS) {          // statics: AABB = the box itself, no travel (rewritten each sub-step: aliased storage)
+      int t = NB + nrs + s2;
+      st3(M.sa[t], ld3(M.sh[t]));
+      M.spd[t] = 0.0f;
+    }
     if (tid == 0) { M.ndropped = 0; }
     __syncthreads();
     // 5. broad phase: one thread per owner shape
@@ -370,8 +383,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     const int npairs = M.poff[n_owner];
     const int PP = (npairs + SIM_THREADS - 1) / SIM_THREADS;
     const int p0 = tid * PP, p1 = min(npairs, p0 + PP);
-    unsigned short* pmask = reinterpret_cast<unsigned short*>(&M.cf[0][0]);     // [npairs] <= 3328 * 2 B < 12 KB
-    unsigned short* pstart = reinterpret_cast<unsigned short*>(&M.cinv[0][0]);  // [npairs]
+    unsigned short* pmask = reinterpret_cast<unsigned short*>(&M.cf4[0]);     // [npairs] <= 3328 * 2 B < 16 KB
+    unsigned short* pstart = reinterpret_cast<unsigned short*>(&M.cb[0]);     // [npairs]
     int mycount = 0;
     {
       int a = 0;
@@ -435,12 +448,12 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         float depth;
         point_hit(G, p, m, margin, &depth);
         v3 wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
-        M.cword[slot] = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
-        M.cw[0][slot] = wpt.x; M.cw[1][slot] = wpt.y; M.cw[2][slot] = wpt.z;
+        const uint32_t wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
         float bias = 0.0f;
         if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
         else if (depth < 0.0f) bias = depth / h;
-        M.cbias[slot] = bias;
+        M.ca[slot] = make_float4(wpt.x, wpt.y, wpt.z, bias);
+        M.cb[slot] = make_float4(depth, 0.0f, 0.0f, __uint_as_float(wdn));   // .x carries the depth until the inverse masses are computed
         {   // warm start from the cached impulse of the same (owner shape, target shape, sample point), if it persisted
           const uint32_t key = ((uint32_t)a << 12) | ((uint32_t)t << 4) | (uint32_t)p;
           wsw[4 * slot] = __uint_as_float(key);
@@ -455,9 +468,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
               else { f0 = V3(warm * wsr[4 * mid + 1], warm * wsr[4 * mid + 2], warm * wsr[4 * mid + 3]); break; }
             }
           }
-          M.cf[0][slot] = f0.x; M.cf[1][slot] = f0.y; M.cf[2][slot] = f0.z;
+          M.cf4[slot] = make_float4(f0.x, f0.y, f0.z, 0.0f);
         }
-        M.cinv[0][slot] = depth;
       }
     }
     __syncthreads();
@@ -466,10 +478,10 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     //    target-side contacts go to a per-body list, filled with atomics and then sorted ascending
     //    (=> the summation order of phase B is fixed, whatever the fill order was)
     for (int i = tid; i < ncon; i += SIM_THREADS) {
-      uint32_t wd = M.cword[i];
+      uint32_t wd = __float_as_uint(M.cb[i].w);
       int a = wd & 255, b = (wd >> 8) & 255;
-      if (i == 0 || (int)(M.cword[i - 1] & 255) != a) M.astart[a] = i;
-      if (i == ncon - 1 || (int)(M.cword[i + 1] & 255) != a) M.aend[a] = i + 1;
+      if (i == 0 || (int)(__float_as_uint(M.cb[i - 1].w) & 255) != a) M.astart[a] = i;
+      if (i == ncon - 1 || (int)(__float_as_uint(M.cb[i + 1].w) & 255) != a) M.aend[a] = i + 1;
       if (b != STATIC_BODY) atomicAdd(&M.nb[b], 1);
     }
     __syncthreads();
@@ -483,7 +495,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     if (tid < NBODY) M.bcur[tid] = M.boff[tid];
     __syncthreads();
     for (int i = tid; i < ncon; i += SIM_THREADS) {
-      int b = (M.cword[i] >> 8) & 255;
+      int b = (__float_as_uint(M.cb[i].w) >> 8) & 255;
       if (b != STATIC_BODY) M.blist[atomicAdd(&M.bcur[b], 1)] = (unsigned short)i;
     }
     __syncthreads();
@@ -514,19 +526,22 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     if (condump && sub == substeps - 1)
       for (int i = tid; i < ncon; i += SIM_THREADS) {
         float* o = condump + ((size_t)e * MAXC + i) * 8;
-        o[0] = __uint_as_float(M.cword[i]); o[1] = M.cw[0][i]; o[2] = M.cw[1][i]; o[3] = M.cw[2][i]; o[4] = M.cinv[0][i];
-        o[5] = M.cbias[i]; o[6] = 0.0f; o[7] = 0.0f;
+        float4 A4 = M.ca[i], B4 = M.cb[i];
+        o[0] = B4.w; o[1] = A4.x; o[2] = A4.y; o[3] = A4.z; o[4] = B4.x;
+        o[5] = A4.w; o[6] = 0.0f; o[7] = 0.0f;
       }
     __syncthreads();
     // 8. inverse mass-split effective masses along n, t1, t2
     for (int i = tid; i < ncon; i += SIM_THREADS) {
-      uint32_t wd = M.cword[i];
+      const float4 A4 = M.ca[i];
+      uint32_t wd = __float_as_uint(M.cb[i].w);
       int a = wd & 255, b = (wd >> 8) & 255;
       v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
-      v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
-      M.cinv[0][i] = 1.0f / (body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n));
-      M.cinv[1][i] = 1.0f / (body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1));
-      M.cinv[2][i] = 1.0f / (body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2));
+      v3 wpt = V3(A4.x, A4.y, A4.z);
+      float i0 = 1.0f / (body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n));
+      float i1 = 1.0f / (body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1));
+      float i2 = 1.0f / (body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2));
+      M.cb[i] = make_float4(i0, i1, i2, __uint_as_float(wd));
     }
     __syncthreads();
     // 9. Jacobi iterations on total impulses
@@ -534,52 +549,52 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     for (int it = -1; it < iters; ++it) {                      // it = -1: phase B only = apply the warm-start impulses
       if (it >= 0)
       for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
-        uint32_t wd = M.cword[i];
+        const float4 A4 = M.ca[i], B4 = M.cb[i], F4 = M.cf4[i];
+        uint32_t wd = __float_as_uint(B4.w);
         int a = wd & 255, b = (wd >> 8) & 255;
         v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
-        v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
-        v3 f = V3(M.cf[0][i], M.cf[1][i], M.cf[2][i]);
-        v3 vrel = vadd(ld3(M.bv[a]), vcross(ld3(M.bw[a]), vsub(wpt, ld3(M.bx[a]))));
-        if (b != STATIC_BODY) vrel = vsub(vrel, vadd(ld3(M.bv[b]), vcross(ld3(M.bw[b]), vsub(wpt, ld3(M.bx[b])))));
-        float ln = fmaf(M.cbias[i] - vdot(vrel, n), M.cinv[0][i], vdot(f, n));
+        v3 wpt = V3(A4.x, A4.y, A4.z);
+        v3 f = V3(F4.x, F4.y, F4.z);
+        v3 vrel = vadd(ldv(M.bv[a]), vcross(ldv(M.bw[a]), vsub(wpt, ldv(M.bx[a]))));
+        if (b != STATIC_BODY) vrel = vsub(vrel, vadd(ldv(M.bv[b]), vcross(ldv(M.bw[b]), vsub(wpt, ldv(M.bx[b])))));
+        float ln = fmaf(A4.w - vdot(vrel, n), B4.x, vdot(f, n));
         ln = ln > 0.0f ? ln : 0.0f;
         float lim = mu * ln;
-        float l1 = clampf(fmaf(-vdot(vrel, t1), M.cinv[1][i], vdot(f, t1)), -lim, lim);
-        float l2 = clampf(fmaf(-vdot(vrel, t2), M.cinv[2][i], vdot(f, t2)), -lim, lim);
+        float l1 = clampf(fmaf(-vdot(vrel, t1), B4.y, vdot(f, t1)), -lim, lim);
+        float l2 = clampf(fmaf(-vdot(vrel, t2), B4.z, vdot(f, t2)), -lim, lim);
         f = vmad(t2, l2, vmad(t1, l1, vscale(n, ln)));
-        M.cf[0][i] = f.x; M.cf[1][i] = f.y; M.cf[2][i] = f.z;
+        M.cf4[i] = make_float4(f.x, f.y, f.z, 0.0f);
       }
       __syncthreads();
-      // phase B: FOUR lanes per body, lane k sums incidences e = k (mod 4); partials combined (0+1)+(2+3).
-      // brick warps (all but the last): 72 bricks x 4 lanes = 288 items, ROBOT_TID0 per pass.
+      // phase B: TWO lanes per body, lane k sums incidences e = k (mod 2); partials combined 0+1.
+      // brick warps (all but the last): 72 bricks x 2 lanes = 144 items in ONE pass.
       // last warp: the articulation -- only links that HAVE contacts are gathered (their wrenches are zero otherwise, set
       // once per sub-step), and the joint-space update is skipped entirely while the robot touches nothing.
       const bool robot_warp = tid >= ROBOT_TID0;
-      const int n_items = robot_warp ? 4 * __popc(ract) : 4 * NB;
+      const int n_items = robot_warp ? 2 * __popc(ract) : 2 * NB;
       const int per_pass = robot_warp ? 32 : ROBOT_TID0;
 #pragma unroll 1
       for (int base = 0; base < n_items; base += per_pass) {
         const int item = base + (robot_warp ? tid - ROBOT_TID0 : tid);
-        if (!robot_warp && item >= n_items) continue;           // warp-uniform (288 and ROBOT_TID0 are multiples of 32)
+        if (!robot_warp && (item & ~31) >= n_items) continue;   // whole warp beyond the item range
         const bool live = item < n_items;
-        const int body = !robot_warp ? (item >> 2) : NB + (live ? (int)__fns(ract, 0, (item >> 2) + 1) : 0);
-        const int k = item & 3;
+        const int body = !robot_warp ? (live ? (item >> 1) : 0) : NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
+        const int k = item & 1;
         const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
         const v3 xb = body < NB ? ld3(M.bx[body]) : V3(0.0f, 0.0f, 0.0f);
         v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
-        for (int ee = k; ee < ntot; ee += 4) {
+        for (int ee = k; ee < ntot; ee += 2) {
           const bool own = ee < na;
           const int i = own ? a0 + ee : (int)M.blist[b0 + (ee - na)];
-          v3 f = V3(M.cf[0][i], M.cf[1][i], M.cf[2][i]);
+          const float4 F4 = M.cf4[i], A4 = M.ca[i];
+          v3 f = V3(F4.x, F4.y, F4.z);
           if (!own) f = vneg(f);
-          v3 wpt = V3(M.cw[0][i], M.cw[1][i], M.cw[2][i]);
+          v3 wpt = V3(A4.x, A4.y, A4.z);
           F = vadd(F, f);
           T = vadd(T, vcross(vsub(wpt, xb), f));
         }
         F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
         T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
-        F.x += __shfl_xor_sync(0xffffffffu, F.x, 2); F.y += __shfl_xor_sync(0xffffffffu, F.y, 2); F.z += __shfl_xor_sync(0xffffffffu, F.z, 2);
-        T.x += __shfl_xor_sync(0xffffffffu, T.x, 2); T.y += __shfl_xor_sync(0xffffffffu, T.y, 2); T.z += __shfl_xor_sync(0xffffffffu, T.z, 2);
         if (k == 0 && live) {
           if (body < NB) {
             st3(M.bv[body], vmad(F, M.binvm[body], ld3(M.vfree[body])));
@@ -603,7 +618,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       }
       __syncthreads();
     }
-    for (int i = tid; i < ncon; i += SIM_THREADS) { wsw[4 * i + 1] = M.cf[0][i]; wsw[4 * i + 2] = M.cf[1][i]; wsw[4 * i + 3] = M.cf[2][i]; }
+    for (int i = tid; i < ncon; i += SIM_THREADS) { const float4 F4 = M.cf4[i]; wsw[4 * i + 1] = F4.x; wsw[4 * i + 2] = F4.y; wsw[4 * i + 3] = F4.z; }
     if (tid == 0) gwsn[1 - rb] = ncon;
     rb = 1 - rb;
     if (iters == 0 && tid < SDX_NL) { st3(M.linkF[tid], V3(0, 0, 0)); st3(M.linkM[tid], V3(0, 0, 0)); }
@@ -659,10 +674,10 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   if (tid < SDX_NL) {
     int L = tid;
     float* o = link_out + ((size_t)e * SDX_NL + L) * 13;
-    o[0] = M.bx[NB + L][0]; o[1] = M.bx[NB + L][1]; o[2] = M.bx[NB + L][2];
+    o[0] = M.bx[NB + L].x; o[1] = M.bx[NB + L].y; o[2] = M.bx[NB + L].z;
     o[3] = M.lq[L][0]; o[4] = M.lq[L][1]; o[5] = M.lq[L][2]; o[6] = M.lq[L][3];
-    o[7] = M.bv[NB + L][0]; o[8] = M.bv[NB + L][1]; o[9] = M.bv[NB + L][2];
-    o[10] = M.bw[NB + L][0]; o[11] = M.bw[NB + L][1]; o[12] = M.bw[NB + L][2];
+    o[7] = M.bv[NB + L].x; o[8] = M.bv[NB + L].y; o[9] = M.bv[NB + L].z;
+    o[10] = M.bw[NB + L].x; o[11] = M.bw[NB + L].y; o[12] = M.bw[NB + L].z;
     float invh = 1.0f / h;
     float* f = netf + ((size_t)e * SDX_NL + L) * 3;
     f[0] = M.linkF[L][0] * invh; f[1] = M.linkF[L][1] * invh; f[2] = M.linkF[L][2] * invh;
