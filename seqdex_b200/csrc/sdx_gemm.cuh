@@ -85,33 +85,37 @@ template <int BN, int STAGES>
 struct GemmSmem {
   __nv_bfloat16 a[STAGES][GEMM_BM * GEMM_BK];
   __nv_bfloat16 b[STAGES][BN * GEMM_BK];
-  uint64_t full[STAGES], empty[STAGES], tmem_full;
+  unsigned char stage_rm[4 * 8192];      // epilogue staging, row-major boxes: per warp [32 rows][2 x 64 cols], 128B-swizzled
+  unsigned char stage_t[4 * 8192];       // epilogue staging, transposed box: per warp [128 n][32 m], 64B-swizzled
+  uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
 };
 
 template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
           const __grid_constant__ CUtensorMap mapT, const GemmArgs g) {
+  // PERSISTENT: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA ring and the MMA issuer run ahead
+  // into the next tile while the epilogue warps drain the previous accumulator (two TMEM accumulators of BN columns).
   using namespace gemm;
   extern __shared__ unsigned char gsm_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment: align by hand (the launcher over-allocates 1 KB)
   auto& S = *reinterpret_cast<GemmSmem<BN, STAGES>*>(gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * BN;
-  const int kb0 = blockIdx.z * g.kblocks_per_split;
+  const int tiles_n = (g.N + BN - 1) / BN, tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
   const int total_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
-  const int nkb = min(g.kblocks_per_split, total_kb - kb0);
+  const int splits = (total_kb + g.kblocks_per_split - 1) / g.kblocks_per_split;
+  const int n_tiles = tiles_n * tiles_m * splits;
   constexpr uint32_t STAGE_BYTES = (GEMM_BM + BN) * GEMM_BK * 2;
   constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    mbar_init(&S.tmem_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -121,140 +125,168 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&S.empty[s], ph ^ 1);
-        mbar_expect_tx(&S.full[s], STAGE_BYTES);
-        tma_load_2d(&mapA, S.a[s], &S.full[s], (kb0 + kb) * GEMM_BK, m0);
-        tma_load_2d(&mapB, S.b[s], &S.full[s], (kb0 + kb) * GEMM_BK, n0);
+      uint32_t kbg = 0;                                  // k-block counter across all tiles of this CTA (stage ring position)
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int nx = t % tiles_n, my = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
+        const int m0 = my * GEMM_BM, n0 = nx * BN, kb0 = z * g.kblocks_per_split;
+        const int nkb = min(g.kblocks_per_split, total_kb - kb0);
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&S.empty[s], ph ^ 1);
+          mbar_expect_tx(&S.full[s], STAGE_BYTES);
+          tma_load_2d(&mapA, S.a[s], &S.full[s], (kb0 + kb) * GEMM_BK, m0);
+          tma_load_2d(&mapB, S.b[s], &S.full[s], (kb0 + kb) * GEMM_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&S.full[s], ph);
+      uint32_t kbg = 0, it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int z = t / (tiles_n * tiles_m), kb0 = z * g.kblocks_per_split;
+        const int nkb = min(g.kblocks_per_split, total_kb - kb0);
+        const uint32_t acc = it & 1;
+        mbar_wait(&S.tmem_empty[acc], ((it >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da = umma_desc(S.a[s]), db = umma_desc(S.b[s]);
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&S.full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t da = umma_desc(S.a[s]), db = umma_desc(S.b[s]);
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k)   // +32 B (= 2 x 16 B) along K inside the 128 B swizzle row per UMMA_K
-          umma_f16(tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&S.empty[s]);
+          for (int k = 0; k < GEMM_BK / 16; ++k)   // +32 B (= 2 x 16 B) along K inside the 128 B swizzle row per UMMA_K
+            umma_f16(tmem + acc * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&S.empty[s]);
+        }
+        umma_commit(&S.tmem_full[acc]);
       }
-      umma_commit(&S.tmem_full);
     }
   } else {
     // ---------------- epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = output rows of the tile
-    mbar_wait(&S.tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int lg = warp & 3;
-    const int row = m0 + lg * 32 + lane;
-    const bool row_ok = row < g.M;
+    unsigned char* const rm0 = S.stage_rm + lg * 8192;
+    unsigned char* const tb = S.stage_t + lg * 8192;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      const int nx = t % tiles_n, my = (t / tiles_n) % tiles_m;
+      const int m0 = my * GEMM_BM, n0 = nx * BN;
+      const uint32_t acc = it & 1;
+      mbar_wait(&S.tmem_full[acc], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = m0 + lg * 32 + lane;
+      const bool row_ok = row < g.M;
+      if (MODE == 0 || MODE == 1) {                        // the previous tile's TMA stores must have read the staging area
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
-      const int col0 = n0 + c * 32;
-      if (col0 >= g.N) break;
-      if (MODE == 0 || MODE == 1) {
-        float v[32];
-        const bool full = col0 + 32 <= g.N;
-        if (MODE == 0) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + acc * BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
+        const int col0 = n0 + c * 32;
+        if (col0 >= g.N) continue;
+        if (MODE == 0 || MODE == 1) {
+          float v[32];
+          const bool full = col0 + 32 <= g.N;
+          if (MODE == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 b4 = full ? *reinterpret_cast<const float4*>(g.bias + col0 + j)
-                             : make_float4(col0 + j < g.N ? g.bias[col0 + j] : 0.f, col0 + j + 1 < g.N ? g.bias[col0 + j + 1] : 0.f,
-                                           col0 + j + 2 < g.N ? g.bias[col0 + j + 2] : 0.f, col0 + j + 3 < g.N ? g.bias[col0 + j + 3] : 0.f);
-            float a0 = __uint_as_float(r[j]) + b4.x, a1 = __uint_as_float(r[j + 1]) + b4.y, a2 = __uint_as_float(r[j + 2]) + b4.z,
-                  a3 = __uint_as_float(r[j + 3]) + b4.w;
-            v[j] = a0 > 0.0f ? a0 : (__expf(a0) - 1.0f); v[j + 1] = a1 > 0.0f ? a1 : (__expf(a1) - 1.0f);
-            v[j + 2] = a2 > 0.0f ? a2 : (__expf(a2) - 1.0f); v[j + 3] = a3 > 0.0f ? a3 : (__expf(a3) - 1.0f);
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = full ? *reinterpret_cast<const float4*>(g.bias + col0 + j)
+                               : make_float4(col0 + j < g.N ? g.bias[col0 + j] : 0.f, col0 + j + 1 < g.N ? g.bias[col0 + j + 1] : 0.f,
+                                             col0 + j + 2 < g.N ? g.bias[col0 + j + 2] : 0.f, col0 + j + 3 < g.N ? g.bias[col0 + j + 3] : 0.f);
+              float a0 = __uint_as_float(r[j]) + b4.x, a1 = __uint_as_float(r[j + 1]) + b4.y, a2 = __uint_as_float(r[j + 2]) + b4.z,
+                    a3 = __uint_as_float(r[j + 3]) + b4.w;
+              v[j] = a0 > 0.0f ? a0 : (__expf(a0) - 1.0f); v[j + 1] = a1 > 0.0f ? a1 : (__expf(a1) - 1.0f);
+              v[j + 2] = a2 > 0.0f ? a2 : (__expf(a2) - 1.0f); v[j + 3] = a3 > 0.0f ? a3 : (__expf(a3) - 1.0f);
+            }
+          } else {
+            if (row_ok && full && (g.ldh & 7) == 0) {     // 4 x 16-byte loads of the layer's own activations
+              const uint4* hp = reinterpret_cast<const uint4*>(g.h + (size_t)row * g.ldh + col0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                uint4 u = hp[q];
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                for (int e2 = 0; e2 < 4; ++e2) {
+                  float2 hv = __bfloat1622float2(h2[e2]);
+                  int j = 8 * q + 2 * e2;
+                  v[j] = __uint_as_float(r[j]) * (hv.x > 0.0f ? 1.0f : hv.x + 1.0f);
+                  v[j + 1] = __uint_as_float(r[j + 1]) * (hv.y > 0.0f ? 1.0f : hv.y + 1.0f);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                float hv = (row_ok && col0 + j < g.N) ? __bfloat162float(g.h[(size_t)row * g.ldh + col0 + j]) : 0.0f;
+                v[j] = __uint_as_float(r[j]) * (hv > 0.0f ? 1.0f : hv + 1.0f);
+              }
+            }
           }
-        } else {
-          if (row_ok && full && (g.ldh & 7) == 0) {     // 4 x 16-byte loads of the layer's own activations
-            const uint4* hp = reinterpret_cast<const uint4*>(g.h + (size_t)row * g.ldh + col0);
+          // stage the bf16 results in shared memory in the layouts of 128B- / 64B-swizzled TMA boxes;
+          // one TMA store per box then writes full, coalesced lines
+          {
+            unsigned char* rm = rm0 + (c >> 1) * 4096;                                   // [32 rows][64 cols] box
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 u = hp[q];
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+              u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+              const int cc = (c & 1) * 4 + q;
+              *reinterpret_cast<uint4*>(rm + lane * 128 + ((cc ^ (lane & 7)) << 4)) = u;
+            }
+            if (g.out_t) {
 #pragma unroll
-              for (int e2 = 0; e2 < 4; ++e2) {
-                float2 hv = __bfloat1622float2(h2[e2]);
-                int j = 8 * q + 2 * e2;
-                v[j] = __uint_as_float(r[j]) * (hv.x > 0.0f ? 1.0f : hv.x + 1.0f);
-                v[j + 1] = __uint_as_float(r[j + 1]) * (hv.y > 0.0f ? 1.0f : hv.y + 1.0f);
+              for (int j = 0; j < 32; ++j) {
+                const int nl = c * 32 + j;
+                *reinterpret_cast<__nv_bfloat16*>(tb + nl * 64 + ((((lane >> 3) ^ ((nl >> 1) & 3))) << 4) + (lane & 7) * 2) = __float2bfloat16_rn(v[j]);
               }
             }
-          } else {
+          }
+        } else {
+          if (row_ok) {
+            float* dst = g.outf + (size_t)row * g.ldf + col0;
+            if (MODE == 2 && col0 + 32 <= g.N && (g.ldf & 3) == 0) {      // split-K accumulation: 16-byte vector reductions
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float hv = (row_ok && col0 + j < g.N) ? __bfloat162float(g.h[(size_t)row * g.ldh + col0 + j]) : 0.0f;
-              v[j] = __uint_as_float(r[j]) * (hv > 0.0f ? 1.0f : hv + 1.0f);
+              for (int j = 0; j < 32; j += 4)
+                atomicAdd(reinterpret_cast<float4*>(dst + j),
+                          make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < g.N) {
+                  if (MODE == 2) atomicAdd(dst + j, __uint_as_float(r[j]));
+                  else if (MODE == 4) dst[j] = __uint_as_float(r[j]) + g.bias[col0 + j];
+                  else dst[j] = __uint_as_float(r[j]);
+                }
             }
-          }
-        }
-        // stage the bf16 results in shared memory (the pipeline stages are free once tmem_full has fired) in the layouts
-        // of 128B- / 64B-swizzled TMA boxes; one TMA store per box writes full, coalesced lines
-        {
-          unsigned char* rm = reinterpret_cast<unsigned char*>(&S.a[0][0]) + lg * 8192 + (c >> 1) * 4096;   // [32 rows][64 cols] box
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * q + 4], v[8 * q + 5]), p3 = __floats2bfloat162_rn(v[8 * q + 6], v[8 * q + 7]);
-            uint4 u;
-            u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-            u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-            const int cc = (c & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(rm + lane * 128 + ((cc ^ (lane & 7)) << 4)) = u;
-          }
-          if (g.out_t) {
-            unsigned char* tb = reinterpret_cast<unsigned char*>(&S.b[0][0]) + lg * 8192;                  // [128 n][32 m] box, 64 B rows
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int nl = c * 32 + j;
-              *reinterpret_cast<__nv_bfloat16*>(tb + nl * 64 + ((((lane >> 3) ^ ((nl >> 1) & 3))) << 4) + (lane & 7) * 2) = __float2bfloat16_rn(v[j]);
-            }
-          }
-        }
-      } else {
-        if (row_ok) {
-          float* dst = g.outf + (size_t)row * g.ldf + col0;
-          if (MODE == 2 && col0 + 32 <= g.N && (g.ldf & 3) == 0) {      // split-K accumulation: 16-byte vector reductions
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              atomicAdd(reinterpret_cast<float4*>(dst + j),
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) {
-                if (MODE == 2) atomicAdd(dst + j, __uint_as_float(r[j]));
-                else if (MODE == 4) dst[j] = __uint_as_float(r[j]) + g.bias[col0 + j];
-                else dst[j] = __uint_as_float(r[j]);
-              }
           }
         }
       }
-    }
-    if (MODE == 0 || MODE == 1) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      // this warp has read its TMEM lanes of the accumulator: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
-        const unsigned char* rm = reinterpret_cast<const unsigned char*>(&S.a[0][0]) + lg * 8192;
-        tma_store_2d(&mapO, rm, n0, m0 + lg * 32);
-        if (n0 + 64 < g.N) tma_store_2d(&mapO, rm + 4096, n0 + 64, m0 + lg * 32);
-        if (g.out_t) tma_store_2d(&mapT, reinterpret_cast<const unsigned char*>(&S.b[0][0]) + lg * 8192, m0 + lg * 32, n0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.tmem_empty[acc])) : "memory");
+      if (MODE == 0 || MODE == 1) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&mapO, rm0, n0, m0 + lg * 32);
+          if (n0 + 64 < g.N) tma_store_2d(&mapO, rm0 + 4096, n0 + 64, m0 + lg * 32);
+          if (g.out_t) tma_store_2d(&mapT, tb, m0 + lg * 32, n0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
+    if ((MODE == 0 || MODE == 1) && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
   }
 }

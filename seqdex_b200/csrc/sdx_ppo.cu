@@ -46,7 +46,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
 }
 
 #define GEMM_BN 128
-#define GEMM_STAGES 3   /* 3 x 32 KB stages -> two CTAs per SM: one tile's epilogue overlaps the other's main loop */
+#define GEMM_STAGES 4   /* 4 x 32 KB TMA stages + 64 KB epilogue staging: one persistent CTA per SM */
 typedef GemmSmem<GEMM_BN, GEMM_STAGES> GSm;
 static bool g_attr_set = false;
 static int set_attrs() {
@@ -86,7 +86,10 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
   splits = (total_kb + g.kblocks_per_split - 1) / g.kblocks_per_split;
   g.bias = bias; g.h = (const __nv_bfloat16*)h; g.ldh = ldh; g.out = (__nv_bfloat16*)out; g.ldo = ldo;
   g.out_t = (__nv_bfloat16*)out_t; g.ldt = ldt; g.outf = outf; g.ldf = ldf;
-  dim3 grid((N + GEMM_BN - 1) / GEMM_BN, (M + GEMM_BM - 1) / GEMM_BM, splits);
+  int n_tiles = ((N + GEMM_BN - 1) / GEMM_BN) * ((M + GEMM_BM - 1) / GEMM_BM) * splits;
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  dim3 grid(n_tiles < n_sm ? n_tiles : n_sm);   // persistent: one CTA per SM walks the tiles
   size_t smem = sizeof(GSm) + 1024;
   cudaStream_t st = (cudaStream_t)stream;
   switch (mode) {
@@ -313,7 +316,7 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
     int N = m->d[l + 1], K = m->d[l], ldg = K + 16;
     PCK(cudaMemsetAsync(m->gW[l], 0, (size_t)N * ldg * 4, st));
     int tiles = ((N + 127) / 128) * ((K + 16 + 127) / 128);
-    int splits = (148 + tiles - 1) / tiles; if (splits < 1) splits = 1;   // ~one wave of CTAs; fewer splits = fewer fp32 reductions
+    int splits = 296 / tiles; if (splits < 1) splits = 1;   // two tiles per persistent CTA: the second one's main loop hides the first one's reduction epilogue
     if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, m->At[l], K + 16, m->max_rows, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
     if (l > 0) {
       int Kd = pad64(N);

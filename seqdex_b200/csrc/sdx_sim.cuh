@@ -187,14 +187,19 @@ __device__ __forceinline__ v3 sample_point(v3 ha, int p) {
   if (p < 8) return V3((p & 1) ? ha.x : -ha.x, (p & 2) ? ha.y : -ha.y, (p & 4) ? ha.z : -ha.z);
   return V3(0.0f, (p & 1) ? ha.y : -ha.y, (p & 2) ? ha.z : -ha.z);
 }
-// does sample point p of the owner touch the reference face?  depth returned through *depth
+// does sample point p of the owner touch the reference face?  depth returned through *depth.
+// The coordinate along the face axis is evaluated first (most points fail the depth test); the values are the same
+// as evaluating the full point l = lc + C pl.
 __device__ __forceinline__ bool point_hit(const PairGeom& G, int p, float m, float margin, float* depth) {
   v3 pl = sample_point(G.ha, p);
-  v3 l = vadd(G.lc, mmul(G.C, pl));
-  int k = G.k;
-  float lk = k == 0 ? l.x : (k == 1 ? l.y : l.z);
+  const int k = G.k;
+  const float c0 = k == 0 ? G.C[0] : (k == 1 ? G.C[3] : G.C[6]), c1 = k == 0 ? G.C[1] : (k == 1 ? G.C[4] : G.C[7]),
+              c2 = k == 0 ? G.C[2] : (k == 1 ? G.C[5] : G.C[8]);
+  const float lck = k == 0 ? G.lc.x : (k == 1 ? G.lc.y : G.lc.z);
+  float lk = lck + fmaf(c2, pl.z, fmaf(c1, pl.y, c0 * pl.x));
   float d = G.htk - G.sgf * lk;
   if (!(d > -m)) return false;
+  v3 l = vadd(G.lc, mmul(G.C, pl));
   bool inface = (k == 0 || fabsf(l.x) <= G.ht.x + margin) && (k == 1 || fabsf(l.y) <= G.ht.y + margin) &&
                 (k == 2 || fabsf(l.z) <= G.ht.z + margin);
   *depth = d;
@@ -548,6 +553,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     const float mu = S->friction;
     for (int it = -1; it < iters; ++it) {                      // it = -1: phase B only = apply the warm-start impulses
       if (it >= 0)
+#pragma unroll 2
       for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
         const float4 A4 = M.ca[i], B4 = M.cb[i], F4 = M.cf4[i];
         uint32_t wd = __float_as_uint(B4.w);
