@@ -172,6 +172,9 @@ void sdx_mlp_destroy(sdx_mlp_t* m);
 int sdx_mlp_info(sdx_mlp_t* m, int64_t* nparams, void** params, void** grads, void** out, void** adam_m, void** adam_v);
 int sdx_mlp_sync(sdx_mlp_t* m, void* stream);
 int sdx_mlp_forward(sdx_mlp_t* m, const float* x_dev, int M, const float* mean, const float* var, int train, void* stream);
+/* whole-batch input conversion (once per PPO iteration) and forward on a row range of it */
+int sdx_mlp_convert_batch(sdx_mlp_t* m, const float* x_dev, int B, const float* mean, const float* var, void* xb_bf16, void* xt_bf16, void* stream);
+int sdx_mlp_forward_pre(sdx_mlp_t* m, const void* xb_bf16, const void* xt_bf16, int B, int row0, int M, int train, void* stream);
 int sdx_mlp_backward(sdx_mlp_t* m, const float* dout_dev, int M, void* stream);
 int sdx_mlp_adam(sdx_mlp_t* m, float lr, float b1, float b2, float eps, float max_norm, void* stream);   /* RGC:1102, 1866-1872 */
 long long sdx_ppo_launch_count(void);

@@ -122,6 +122,7 @@ struct sdx_mlp {
   size_t nparams, w_off[4], b_off[4], sigma_off;
   float *params, *grads, *adam_m, *adam_v, *out, *scal, *gW[4];
   __nv_bfloat16 *W[4], *Wt[4], *A[4], *At[4], *dZ[5], *dZt[5];
+  const __nv_bfloat16 *a0, *at0; int ldt0;   // layer-0 input of the last forward (own staging buffers or a caller-converted batch)
   long long adam_t;
 };
 static inline int pad64(int x) { return (x + 63) / 64 * 64; }
@@ -290,6 +291,13 @@ extern "C" int sdx_mlp_sync(sdx_mlp* m, void* stream) {
 }
 // x: fp32 [M, in_dim] (device).  mean/var (nullable): RunningMeanStd input normalisation.  train != 0 keeps the
 // transposed activations the backward pass needs.  Result: m->out fp32 [M, out_dim].
+static int mlp_forward_core(sdx_mlp* m, int M, int train, void* stream) {
+  for (int l = 0; l < 3; ++l)
+    if (sdx_gemm_bf16_tn(0, l == 0 ? (const void*)m->a0 : (const void*)m->A[l], M, m->d[l], m->d[l], m->W[l], m->d[l + 1], m->d[l], m->params + m->b_off[l], nullptr, 0,
+                         m->A[l + 1], m->d[l + 1], train ? m->At[l + 1] : nullptr, m->max_rows, nullptr, 0, 1, stream)) return -1;
+  return sdx_gemm_bf16_tn(4, m->A[3], M, m->d[3], m->d[3], m->W[3], m->out_dim, m->d[3], m->params + m->b_off[3], nullptr, 0, nullptr, 0, nullptr, 0,
+                          m->out, m->out_dim, 1, stream);
+}
 extern "C" int sdx_mlp_forward(sdx_mlp* m, const float* x, int M, const float* mean, const float* var, int train, void* stream) {
   if (M > m->max_rows || M <= 0) { sdx_set_error("sdx_mlp_forward: M exceeds max_rows"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -297,11 +305,29 @@ extern "C" int sdx_mlp_forward(sdx_mlp* m, const float* x, int M, const float* m
   k_cvt_2way<<<grd, blk, 0, st>>>(x, M, m->in_dim, m->in_dim, m->in_pad, m->A[0], m->in_pad, train ? m->At[0] : nullptr, m->max_rows, mean, var);
   g_ppo_launches++;
   PCK(cudaGetLastError());
-  for (int l = 0; l < 3; ++l)
-    if (sdx_gemm_bf16_tn(0, m->A[l], M, m->d[l], m->d[l], m->W[l], m->d[l + 1], m->d[l], m->params + m->b_off[l], nullptr, 0, m->A[l + 1], m->d[l + 1],
-                         train ? m->At[l + 1] : nullptr, m->max_rows, nullptr, 0, 1, stream)) return -1;
-  return sdx_gemm_bf16_tn(4, m->A[3], M, m->d[3], m->d[3], m->W[3], m->out_dim, m->d[3], m->params + m->b_off[3], nullptr, 0, nullptr, 0, nullptr, 0,
-                          m->out, m->out_dim, 1, stream);
+  m->a0 = m->A[0]; m->at0 = m->At[0]; m->ldt0 = m->max_rows;
+  return mlp_forward_core(m, M, train, stream);
+}
+// Convert a whole rollout batch ONCE per iteration: x fp32 [B, in_dim] -> xb bf16 [B, in_pad] and xt bf16 [in_pad + 16, B]
+// (row in_pad = ones, for the bias gradient).  Minibatches are then row ranges of xb / column ranges of xt.
+extern "C" int sdx_mlp_convert_batch(sdx_mlp* m, const float* x, int B, const float* mean, const float* var, void* xb, void* xt, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B % 8) { sdx_set_error("sdx_mlp_convert_batch: B must be a multiple of 8"); return -1; }
+  dim3 blk(32, 8), grd((m->in_pad + 31) / 32, (B + 31) / 32);
+  k_cvt_2way<<<grd, blk, 0, st>>>(x, B, m->in_dim, m->in_dim, m->in_pad, (__nv_bfloat16*)xb, m->in_pad, (__nv_bfloat16*)xt, B, mean, var);
+  PCK(cudaMemsetAsync((__nv_bfloat16*)xt + (size_t)m->in_pad * B, 0, (size_t)16 * B * 2, st));
+  k_fill_bf16<<<(unsigned)((B + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)xt + (size_t)m->in_pad * B, (size_t)B, 1.0f);
+  g_ppo_launches += 2;
+  PCK(cudaGetLastError());
+  return 0;
+}
+// forward on rows [row0, row0 + M) of a converted batch (xb [B, in_pad], xt [in_pad + 16, B])
+extern "C" int sdx_mlp_forward_pre(sdx_mlp* m, const void* xb, const void* xt, int B, int row0, int M, int train, void* stream) {
+  if (M > m->max_rows || M <= 0 || row0 % 8) { sdx_set_error("sdx_mlp_forward_pre: bad row range"); return -1; }
+  m->a0 = (const __nv_bfloat16*)xb + (size_t)row0 * m->in_pad;
+  m->at0 = (const __nv_bfloat16*)xt + row0;
+  m->ldt0 = B;
+  return mlp_forward_core(m, M, train, stream);
 }
 // dout: fp32 [M, out_dim] = dLoss/d(out).  Fills m->grads (W and b of every layer; sigma is the loss kernel's job).
 extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stream) {
@@ -317,7 +343,8 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
     PCK(cudaMemsetAsync(m->gW[l], 0, (size_t)N * ldg * 4, st));
     int tiles = ((N + 127) / 128) * ((K + 16 + 127) / 128);
     int splits = 296 / tiles; if (splits < 1) splits = 1;   // two tiles per persistent CTA: the second one's main loop hides the first one's reduction epilogue
-    if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, m->At[l], K + 16, m->max_rows, nullptr, nullptr, 0, nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
+    if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, l == 0 ? (const void*)m->at0 : (const void*)m->At[l], K + 16, l == 0 ? m->ldt0 : m->max_rows, nullptr, nullptr, 0,
+                         nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
     if (l > 0) {
       int Kd = pad64(N);
       if (sdx_gemm_bf16_tn(1, m->dZ[l + 1], M, Kd, Kd, m->Wt[l], K, Kd, nullptr, m->A[l], K, m->dZ[l], K, m->dZt[l], m->max_rows, nullptr, 0, 1, stream)) return -1;

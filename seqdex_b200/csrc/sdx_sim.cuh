@@ -553,7 +553,6 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     const float mu = S->friction;
     for (int it = -1; it < iters; ++it) {                      // it = -1: phase B only = apply the warm-start impulses
       if (it >= 0)
-#pragma unroll 2
       for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
         const float4 A4 = M.ca[i], B4 = M.cb[i], F4 = M.cf4[i];
         uint32_t wd = __float_as_uint(B4.w);

@@ -38,6 +38,7 @@ class MLP:
     def __init__(self, in_dim, out_dim, max_rows, has_sigma=False, device=0, seed=0):
         self.L = _lib.load()
         self.in_dim, self.out_dim, self.max_rows, self.has_sigma = in_dim, out_dim, max_rows, has_sigma
+        self.in_pad = (in_dim + 63) // 64 * 64
         self.device = torch.device("cuda", device)
         self.h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
@@ -94,6 +95,14 @@ class MLP:
         M = x.shape[0]
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == self.in_dim
         _lib.check(self.L.sdx_mlp_forward(self.h, _p(x), M, _p(mean), _p(var), int(train), _stream()))
+        return self.out[:M]
+
+    def convert_batch(self, x, xb, xt, mean=None, var=None):
+        """fp32 [B, in] -> bf16 [B, in_pad] + transposed bf16 [in_pad + 16, B] (ones row appended), once per iteration"""
+        _lib.check(self.L.sdx_mlp_convert_batch(self.h, _p(x), x.shape[0], _p(mean), _p(var), _p(xb), _p(xt), _stream()))
+
+    def forward_pre(self, xb, xt, row0, M, train=True):
+        _lib.check(self.L.sdx_mlp_forward_pre(self.h, _p(xb), _p(xt), xb.shape[0], row0, M, int(train), _stream()))
         return self.out[:M]
 
     def backward(self, dout):
@@ -166,6 +175,9 @@ class A2CAgent:
         self.b_neglogp, self.b_values, self.b_rewards, self.b_dones = z(H, N), z(H, N), z(H, N), z(H, N)
         self.b_adv, self.b_returns = z(H, N), z(H, N)
         self.old_logstd = z(self.B // self.mb, A)
+        bf = lambda r, c: torch.zeros(r, c, device=self.device, dtype=torch.bfloat16)
+        self.xb_obs, self.xt_obs = bf(self.B, self.actor.in_pad), bf(self.actor.in_pad + 16, self.B)
+        self.xb_st, self.xt_st = bf(self.B, self.cv.in_pad), bf(self.cv.in_pad + 16, self.B)
         self.dmu, self.dv = z(self.mb, A), z(self.mb, 1)
         self.stats, self.cv_stats = z(4), z(4)
         self.mom = torch.zeros(2, device=self.device, dtype=torch.float64)
@@ -250,12 +262,15 @@ class A2CAgent:
                                        ctypes.c_double(Btot), _stream()))
         nmb = B // mb
         inv = 1.0 / float(mb)
+        # inputs of both networks -> bf16 (row-major + transposed) ONCE per iteration; minibatches are slices of these
+        self.actor.convert_batch(obs, self.xb_obs, self.xt_obs)
+        self.cv.convert_batch(states, self.xb_st, self.xt_st, self.rms_mean if c.cv_normalize_input else None,
+                              self.rms_var if c.cv_normalize_input else None)
         # central value network (asymmetric critic), own optimiser lr 1e-3
         for _ in range(c.cv_mini_epochs):
             for i in range(nmb):
                 s = slice(i * mb, (i + 1) * mb)
-                v = self.cv.forward(states[s], self.rms_mean if c.cv_normalize_input else None,
-                                    self.rms_var if c.cv_normalize_input else None, train=True)
+                v = self.cv.forward_pre(self.xb_st, self.xt_st, i * mb, mb)
                 _lib.check(L.sdx_ppo_value_loss(_p(v), _p(values[s]), _p(returns[s]), mb, ctypes.c_float(c.e_clip), int(c.clip_value),
                                                 ctypes.c_float(inv), _p(self.dv), _p(self.cv_stats), _stream()))
                 self.cv.backward(self.dv)
@@ -267,7 +282,7 @@ class A2CAgent:
             self.stats.zero_()
             for i in range(nmb):
                 s = slice(i * mb, (i + 1) * mb)
-                mu = self.actor.forward(obs[s], train=True)
+                mu = self.actor.forward_pre(self.xb_obs, self.xt_obs, i * mb, mb)
                 self.actor.grads[self.actor.nparams - A:].zero_()
                 _lib.check(L.sdx_ppo_actor_loss(_p(mu), _p(self.logstd), _p(actions[s]), _p(mu_old[s]), _p(self.old_logstd[i]), _p(nlp_old[s]),
                                                 _p(adv[s]), mb, A, ctypes.c_float(c.e_clip), ctypes.c_float(c.bounds_loss_coef),

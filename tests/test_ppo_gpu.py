@@ -192,3 +192,26 @@ def test_agent_trains_end_to_end(scene):
     assert float((agent.actor.params - p0).abs().max()) > 0
     assert 0 <= info["kl"] < 0.5
     assert torch.isfinite(agent.b_adv).all() and torch.isfinite(agent.cv.params).all()
+
+
+def test_preconverted_batch_path_matches_direct_path():
+    """forward/backward on a row range of a batch converted once per iteration == forward/backward on that slice"""
+    from seqdex_b200.ppo import MLP
+    torch.manual_seed(4)
+    B, M, row0 = 2048, 512, 1024
+    m = MLP(564, 1, 1024, seed=9)
+    x = torch.randn(B, 564, device="cuda") * 2
+    mean, var = torch.randn(564, device="cuda") * 0.1, torch.rand(564, device="cuda") + 0.5
+    out_a = m.forward(x[row0:row0 + M].contiguous(), mean, var, train=True).clone()
+    dout = torch.randn(M, 1, device="cuda") / M
+    m.backward(dout)
+    g_a = m.grads.clone()
+    xb = torch.zeros(B, m.in_pad, device="cuda", dtype=torch.bfloat16)
+    xt = torch.zeros(m.in_pad + 16, B, device="cuda", dtype=torch.bfloat16)
+    m.convert_batch(x, xb, xt, mean, var)
+    out_b = m.forward_pre(xb, xt, row0, M).clone()
+    m.backward(dout)
+    torch.cuda.synchronize()
+    assert torch.equal(out_a, out_b)
+    torch.testing.assert_close(m.grads, g_a, rtol=1e-4, atol=1e-6)     # split-K atomics: order-dependent last bits
+    assert float(xt[m.in_pad].float().min()) == 1.0 and float(xt[m.in_pad + 1:].abs().max()) == 0.0
