@@ -168,6 +168,9 @@ int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, const void*
  * (cfg/lego/ppo_continuous_grasp.yaml:21-23, 74-95).  has_sigma appends the logstd vector (fixed_sigma: True). */
 typedef struct sdx_mlp sdx_mlp_t;
 int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sigma, sdx_mlp_t** out);
+int sdx_mlp_create_ex(int in_dim, int out_dim, int h1, int h2, int h3, int max_rows, int has_sigma, sdx_mlp_t** out);
+/* t-value trainer loss (TVT:199-201,226): BCEWithLogits(ELU(z), onehot(label)), mean over M x 2; dz through the ELU */
+int sdx_tvalue_bce(const float* z, const int* label, int M, float* dz, float* stats, void* stream);
 void sdx_mlp_destroy(sdx_mlp_t* m);
 int sdx_mlp_info(sdx_mlp_t* m, int64_t* nparams, void** params, void** grads, void** out, void** adam_m, void** adam_v);
 int sdx_mlp_sync(sdx_mlp_t* m, void* stream);

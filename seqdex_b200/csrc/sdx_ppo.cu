@@ -219,11 +219,13 @@ __global__ void k_unpack_all(LayerTab t) {
 }
 static LayerTab make_tab(sdx_mlp* m);
 
-extern "C" int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sigma, sdx_mlp** out) {
+// hidden widths h1,h2,h3 must be multiples of 64 (K dimensions of the tensor-core tiles)
+extern "C" int sdx_mlp_create_ex(int in_dim, int out_dim, int h1, int h2, int h3, int max_rows, int has_sigma, sdx_mlp** out) {
+  if ((h1 % 64) || (h2 % 64) || (h3 % 64) || out_dim < 1 || out_dim > 64) { sdx_set_error("sdx_mlp_create_ex: hidden widths must be multiples of 64, out_dim <= 64"); return -1; }
   sdx_mlp* m = new sdx_mlp();
   memset(m, 0, sizeof(*m));
   m->in_dim = in_dim; m->in_pad = pad64(in_dim); m->out_dim = out_dim; m->max_rows = max_rows; m->has_sigma = has_sigma;
-  m->d[0] = m->in_pad; m->d[1] = 1024; m->d[2] = 512; m->d[3] = 256; m->d[4] = out_dim;
+  m->d[0] = m->in_pad; m->d[1] = h1; m->d[2] = h2; m->d[3] = h3; m->d[4] = out_dim;
   if (max_rows % 8) { sdx_set_error("sdx_mlp_create: max_rows must be a multiple of 8"); return -1; }
   size_t off = 0;
   for (int l = 0; l < 4; ++l) {
@@ -254,6 +256,9 @@ extern "C" int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sig
   PCK(cudaDeviceSynchronize());
   *out = m;
   return 0;
+}
+extern "C" int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sigma, sdx_mlp** out) {
+  return sdx_mlp_create_ex(in_dim, out_dim, 1024, 512, 256, max_rows, has_sigma, out);   // cfg/lego/ppo_continuous_grasp.yaml:21-23
 }
 extern "C" void sdx_mlp_destroy(sdx_mlp* m) {
   if (!m) return;
@@ -527,6 +532,27 @@ __global__ void k_rms_merge(float* __restrict__ mean, float* __restrict__ var, d
 }
 __global__ void k_add_count(double* count, double b) { *count += b; }
 
+// t-value trainer loss (TVT:199-201,226): y = ELU(z) (the network ends in an ELU, TVF:44), BCEWithLogits(y, onehot(label)) with
+// mean reduction over M x 2 elements.  dz = dL/dz (through the ELU), stats[0] += sum of the element losses.
+__global__ void k_tvalue_bce(const float* __restrict__ z, const int* __restrict__ label, int M, float* __restrict__ dz, float* __restrict__ stats) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.0f;
+  if (e < M) {
+    for (int c = 0; c < 2; ++c) {
+      float zz = z[2 * e + c], y = zz > 0.0f ? zz : (expf(zz) - 1.0f), t = (label[e] == c) ? 1.0f : 0.0f;
+      float sg = 1.0f / (1.0f + expf(-y));
+      l += fmaxf(y, 0.0f) - y * t + log1pf(expf(-fabsf(y)));
+      dz[2 * e + c] = (sg - t) * (zz > 0.0f ? 1.0f : y + 1.0f) / (2.0f * (float)M);
+    }
+  }
+  for (int o = 16; o; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(stats, l);
+}
+extern "C" int sdx_tvalue_bce(const float* z, const int* label, int M, float* dz, float* stats, void* stream) {
+  k_tvalue_bce<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(z, label, M, dz, stats);
+  g_ppo_launches++;
+  PCK(cudaGetLastError()); return 0;
+}
 extern "C" int sdx_ppo_sample(const float* mu, const float* logstd, int M, int A, uint64_t seed, uint32_t counter, float* actions, float* neglogp, void* stream) {
   k_ppo_sample<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mu, logstd, M, A, seed, counter, actions, neglogp);
   g_ppo_launches++;

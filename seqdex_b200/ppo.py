@@ -35,14 +35,14 @@ class MLP:
     """in -> 1024 -> 512 -> 256 -> out, ELU (cfg/lego/ppo_continuous_grasp.yaml:21-23): fp32 master params,
     bf16 tensor-core compute.  ``params`` / ``grads`` are flat fp32 views in torch state_dict order."""
 
-    def __init__(self, in_dim, out_dim, max_rows, has_sigma=False, device=0, seed=0):
+    def __init__(self, in_dim, out_dim, max_rows, has_sigma=False, device=0, seed=0, hidden=(1024, 512, 256)):
         self.L = _lib.load()
         self.in_dim, self.out_dim, self.max_rows, self.has_sigma = in_dim, out_dim, max_rows, has_sigma
         self.in_pad = (in_dim + 63) // 64 * 64
         self.device = torch.device("cuda", device)
         self.h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(self.L.sdx_mlp_create(in_dim, out_dim, max_rows, int(has_sigma), ctypes.byref(self.h)))
+            _lib.check(self.L.sdx_mlp_create_ex(in_dim, out_dim, hidden[0], hidden[1], hidden[2], max_rows, int(has_sigma), ctypes.byref(self.h)))
             n = ctypes.c_int64()
             pp, pg, po, pm, pv = (ctypes.c_void_p() for _ in range(5))
             _lib.check(self.L.sdx_mlp_info(self.h, ctypes.byref(n), ctypes.byref(pp), ctypes.byref(pg), ctypes.byref(po),
@@ -52,7 +52,7 @@ class MLP:
             self.params, self.grads = mk(pp, [self.nparams]), mk(pg, [self.nparams])
             self.adam_m, self.adam_v = mk(pm, [self.nparams]), mk(pv, [self.nparams])
             self.out = mk(po, [max_rows, out_dim])
-        self.dims = [in_dim, 1024, 512, 256, out_dim]
+        self.dims = [in_dim, hidden[0], hidden[1], hidden[2], out_dim]
         self.init_default(seed)
 
     def close(self):
