@@ -161,7 +161,9 @@ __global__ void k_unpack_grads(const float* __restrict__ gW, int rows, int kreal
   if (c < kreal) gw[(size_t)r * kreal + c] = gW[(size_t)r * ldg + c];
   else gb[r] = gW[(size_t)r * ldg + kones];
 }
-__global__ void k_sumsq(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+// sum of squares in TWO deterministic stages (per-block partials, then one block in fixed order): data-parallel replicas
+// must compute bit-identical clip factors from their bit-identical all-reduced gradients, or they drift apart
+__global__ void k_sumsq(const float* __restrict__ g, size_t n, float* __restrict__ partial) {
   __shared__ float sh[32];
   float s = 0.0f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += g[i] * g[i];
@@ -171,7 +173,20 @@ __global__ void k_sumsq(const float* __restrict__ g, size_t n, float* __restrict
   if (threadIdx.x < 32) {
     s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0f;
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+  }
+}
+__global__ void k_sumsq_final(const float* __restrict__ partial, int nb, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s += partial[i];
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0f;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = s;
   }
 }
 // torch.optim.Adam (eps 1e-8, no weight decay; RGC:1102) with rl_games' global grad-norm clip folded in (RGC:1866-1872)
@@ -240,7 +255,7 @@ extern "C" int sdx_mlp_create_ex(int in_dim, int out_dim, int h1, int h2, int h3
   PCK(cudaMalloc(&m->adam_m, off * 4)); PCK(cudaMemset(m->adam_m, 0, off * 4));
   PCK(cudaMalloc(&m->adam_v, off * 4)); PCK(cudaMemset(m->adam_v, 0, off * 4));
   PCK(cudaMalloc(&m->out, (size_t)max_rows * out_dim * 4));
-  PCK(cudaMalloc(&m->scal, 64)); PCK(cudaMemset(m->scal, 0, 64));
+  PCK(cudaMalloc(&m->scal, 2048)); PCK(cudaMemset(m->scal, 0, 2048));   // [0] grad norm^2, [16..16+296) per-block partials
   size_t R = max_rows;
   for (int l = 0; l < 4; ++l) {
     int K = m->d[l], N = m->d[l + 1], Npad = pad64(N);
@@ -368,8 +383,11 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
 extern "C" int sdx_mlp_adam(sdx_mlp* m, float lr, float b1, float b2, float eps, float max_norm, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   m->adam_t++;
-  PCK(cudaMemsetAsync(m->scal, 0, 4, st));
-  if (max_norm > 0.0f) k_sumsq<<<296, 256, 0, st>>>(m->grads, m->nparams, m->scal);
+  if (max_norm > 0.0f) {
+    k_sumsq<<<296, 256, 0, st>>>(m->grads, m->nparams, m->scal + 16);
+    k_sumsq_final<<<1, 256, 0, st>>>(m->scal + 16, 296, m->scal);
+    g_ppo_launches++;
+  }
   g_ppo_launches++;
   float bc1 = 1.0f - powf(b1, (float)m->adam_t), bc2 = 1.0f - powf(b2, (float)m->adam_t);
   k_adam<<<(unsigned)((m->nparams + 255) / 256), 256, 0, st>>>(m->params, m->grads, m->adam_m, m->adam_v, m->nparams, lr, b1, b2, eps, bc1, bc2, max_norm, m->scal);
