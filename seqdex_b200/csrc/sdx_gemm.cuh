@@ -4,7 +4,8 @@
 //   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, 128B-swizzled 64-column K slabs, mbarrier tx)
 //   warp 1      : TMEM allocator + MMA issuer (one thread issues tcgen05.mma.cta_group::1.kind::f16,
 //                 UMMA 128 x BN x 16, accumulator in TMEM; tcgen05.commit frees smem stages)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 2..9  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> smem boxes -> TMA store);
+//                 two warps per TMEM lane group, each owning a 64-column slice (latency-bound otherwise)
 //
 // Fused epilogues (MODE):
 //   0  forward      out = ELU(acc + bias[n])               -> bf16 [M,ldo] (+ optional transposed bf16 [N,ldt])
@@ -21,7 +22,7 @@
 
 #define GEMM_BM 128
 #define GEMM_BK 64
-#define GEMM_THREADS 192
+#define GEMM_THREADS 320   // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue
 
 struct GemmArgs {
   int M, N, K;              // problem (K = total reduction length; split-K slices it by gridDim.z)
@@ -69,6 +70,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
+// ELU without branches or denormal fix-ups: exp only ever sees min(a, 0), so ex2.approx.ftz is exact enough for a bf16 result
+__device__ __forceinline__ float elu_fast(float a) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(a, 0.0f) * 1.4426950408889634f));
+  return a > 0.0f ? a : e - 1.0f;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -85,16 +92,17 @@ template <int BN, int STAGES>
 struct GemmSmem {
   __nv_bfloat16 a[STAGES][GEMM_BM * GEMM_BK];
   __nv_bfloat16 b[STAGES][BN * GEMM_BK];
-  unsigned char stage_rm[4 * 8192];      // epilogue staging, row-major boxes: per warp [32 rows][2 x 64 cols], 128B-swizzled
-  unsigned char stage_t[4 * 8192];       // epilogue staging, transposed box: per warp [128 n][32 m], 64B-swizzled
-  uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+  unsigned char stage_rm[8 * 4096];      // epilogue staging, row-major box per warp: [32 rows][64 cols], 128B-swizzled
+  unsigned char stage_t[8 * 4096];       // epilogue staging, transposed box per warp: [64 n][32 m], 64B-swizzled
+  float bias[8][BN / 2];                 // per-warp copy of its bias slices (MODE 0)
+  uint64_t full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], hbar[8];
   uint32_t tmem_base;
 };
 
 template <int BN, int STAGES, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
-          const __grid_constant__ CUtensorMap mapT, const GemmArgs g) {
+          const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapH, const GemmArgs g) {
   // PERSISTENT: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA ring and the MMA issuer run ahead
   // into the next tile while the epilogue warps drain the previous accumulator (two TMEM accumulators of BN columns).
   using namespace gemm;
@@ -111,7 +119,8 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 8); }
+    for (int a = 0; a < 8; ++a) mbar_init(&S.hbar[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -164,49 +173,71 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       }
     }
   } else {
-    // ---------------- epilogue: warp w reads TMEM lanes [32 (w % 4), +32) = output rows of the tile
-    const int lg = warp & 3;
-    unsigned char* const rm0 = S.stage_rm + lg * 8192;
-    unsigned char* const tb = S.stage_t + lg * 8192;
+    // ---------------- epilogue: 8 warps.  Warp w reads TMEM lanes [32 (w % 4), +32) (= 32 output rows of the tile) and,
+    // of every 128-column span of the tile, the 64-column slice ch = (w - 2) / 4: two 32-column TMEM loads per slice.
+    const int lg = warp & 3, ch = (warp - 2) >> 2, ew = ch * 4 + lg;
+    unsigned char* const rm = S.stage_rm + ew * 4096;      // [32 rows][64 cols] box, 128B-swizzled
+    unsigned char* const tb = S.stage_t + ew * 4096;       // [64 n][32 m] box, 64B-swizzled
     uint32_t it = 0;
+    [[maybe_unused]] uint32_t hph = 0;                     // uses of this warp's h barrier so far
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
       const int nx = t % tiles_n, my = (t / tiles_n) % tiles_m;
       const int m0 = my * GEMM_BM, n0 = nx * BN;
       const uint32_t acc = it & 1;
+      if (MODE == 0) {                                     // this warp's copy of its bias slices
+#pragma unroll
+        for (int q = lane; q < BN / 2; q += 32) {
+          const int col = n0 + (q >> 6) * 128 + ch * 64 + (q & 63);
+          S.bias[ew][q] = col < g.N ? g.bias[col] : 0.0f;
+        }
+        __syncwarp();
+      }
+      // MODE 1 reads the layer's own activations h through the SAME staging box the results leave by: one TMA load
+      // (full, coalesced lines), each thread then reads and overwrites exactly its own 16-byte units.
+      auto stage_slice = [&](int ns) {
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // earlier TMA stores have read the staging area
+          if (MODE == 1) {
+            mbar_expect_tx(&S.hbar[ew], 4096u);
+            tma_load_2d(&mapH, rm, &S.hbar[ew], ns, m0 + lg * 32);
+          }
+        }
+        __syncwarp();
+      };
+      if ((MODE == 0 || MODE == 1) && n0 + ch * 64 < g.N) stage_slice(n0 + ch * 64);
       mbar_wait(&S.tmem_full[acc], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row = m0 + lg * 32 + lane;
       const bool row_ok = row < g.M;
-      if (MODE == 0 || MODE == 1) {                        // the previous tile's TMA stores must have read the staging area
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncwarp();
-      }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem + acc * BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
-        const int col0 = n0 + c * 32;
-        if (col0 >= g.N) continue;
+      for (int sp = 0; sp < BN / 128; ++sp) {
+        const int ns = n0 + sp * 128 + ch * 64;             // first column of this warp's slice
+        if (ns >= g.N) break;
         if (MODE == 0 || MODE == 1) {
-          float v[32];
-          const bool full = col0 + 32 <= g.N;
-          if (MODE == 0) {
+          if (sp > 0) stage_slice(ns);
+          if (MODE == 1) { mbar_wait(&S.hbar[ew], hph & 1); ++hph; }
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int col0 = ns + cc * 32;
+          if (col0 >= g.N) break;
+          uint32_t r[32];
+          tmem_ld32(tmem + acc * BN + ((uint32_t)(lg * 32) << 16) + (uint32_t)(sp * 128 + ch * 64 + cc * 32), r);
+          if (MODE == 0 || MODE == 1) {
+            float v[32];
+            if (MODE == 0) {
+              const float4* bq = reinterpret_cast<const float4*>(&S.bias[ew][sp * 64 + cc * 32]);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = full ? *reinterpret_cast<const float4*>(g.bias + col0 + j)
-                               : make_float4(col0 + j < g.N ? g.bias[col0 + j] : 0.f, col0 + j + 1 < g.N ? g.bias[col0 + j + 1] : 0.f,
-                                             col0 + j + 2 < g.N ? g.bias[col0 + j + 2] : 0.f, col0 + j + 3 < g.N ? g.bias[col0 + j + 3] : 0.f);
-              float a0 = __uint_as_float(r[j]) + b4.x, a1 = __uint_as_float(r[j + 1]) + b4.y, a2 = __uint_as_float(r[j + 2]) + b4.z,
-                    a3 = __uint_as_float(r[j + 3]) + b4.w;
-              v[j] = a0 > 0.0f ? a0 : (__expf(a0) - 1.0f); v[j + 1] = a1 > 0.0f ? a1 : (__expf(a1) - 1.0f);
-              v[j + 2] = a2 > 0.0f ? a2 : (__expf(a2) - 1.0f); v[j + 3] = a3 > 0.0f ? a3 : (__expf(a3) - 1.0f);
-            }
-          } else {
-            if (row_ok && full && (g.ldh & 7) == 0) {     // 4 x 16-byte loads of the layer's own activations
-              const uint4* hp = reinterpret_cast<const uint4*>(g.h + (size_t)row * g.ldh + col0);
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = bq[j >> 2];                // broadcast read
+                v[j] = elu_fast(__uint_as_float(r[j]) + b4.x); v[j + 1] = elu_fast(__uint_as_float(r[j + 1]) + b4.y);
+                v[j + 2] = elu_fast(__uint_as_float(r[j + 2]) + b4.z); v[j + 3] = elu_fast(__uint_as_float(r[j + 3]) + b4.w);
+              }
+            } else {
+              const unsigned char* hb = rm + lane * 128;
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
-                uint4 u = hp[q];
+                const uint4 u = *reinterpret_cast<const uint4*>(hb + (((cc * 4 + q) ^ (lane & 7)) << 4));
                 const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
                 for (int e2 = 0; e2 < 4; ++e2) {
@@ -216,18 +247,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                   v[j + 1] = __uint_as_float(r[j + 1]) * (hv.y > 0.0f ? 1.0f : hv.y + 1.0f);
                 }
               }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float hv = (row_ok && col0 + j < g.N) ? __bfloat162float(g.h[(size_t)row * g.ldh + col0 + j]) : 0.0f;
-                v[j] = __uint_as_float(r[j]) * (hv > 0.0f ? 1.0f : hv + 1.0f);
-              }
             }
-          }
-          // stage the bf16 results in shared memory in the layouts of 128B- / 64B-swizzled TMA boxes;
-          // one TMA store per box then writes full, coalesced lines
-          {
-            unsigned char* rm = rm0 + (c >> 1) * 4096;                                   // [32 rows][64 cols] box
+            // stage the bf16 results in shared memory in the layouts of 128B- / 64B-swizzled TMA boxes;
+            // one TMA store per box then writes full, coalesced lines
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * q + 0], v[8 * q + 1]), p1 = __floats2bfloat162_rn(v[8 * q + 2], v[8 * q + 3]);
@@ -235,19 +257,16 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
               uint4 u;
               u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
               u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-              const int cc = (c & 1) * 4 + q;
-              *reinterpret_cast<uint4*>(rm + lane * 128 + ((cc ^ (lane & 7)) << 4)) = u;
+              *reinterpret_cast<uint4*>(rm + lane * 128 + (((cc * 4 + q) ^ (lane & 7)) << 4)) = u;
             }
             if (g.out_t) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                const int nl = c * 32 + j;
+                const int nl = cc * 32 + j;
                 *reinterpret_cast<__nv_bfloat16*>(tb + nl * 64 + ((((lane >> 3) ^ ((nl >> 1) & 3))) << 4) + (lane & 7) * 2) = __float2bfloat16_rn(v[j]);
               }
             }
-          }
-        } else {
-          if (row_ok) {
+          } else if (row_ok) {
             float* dst = g.outf + (size_t)row * g.ldf + col0;
             if (MODE == 2 && col0 + 32 <= g.N && (g.ldf & 3) == 0) {      // split-K accumulation: 16-byte vector reductions
 #pragma unroll
@@ -265,21 +284,20 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
           }
         }
+        if (MODE == 0 || MODE == 1) {                        // slice complete: one TMA store per staged box
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapO, rm, ns, m0 + lg * 32);
+            if (g.out_t) tma_store_2d(&mapT, tb, m0 + lg * 32, ns);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       }
       // this warp has read its TMEM lanes of the accumulator: hand it back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.tmem_empty[acc])) : "memory");
-      if (MODE == 0 || MODE == 1) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&mapO, rm0, n0, m0 + lg * 32);
-          if (n0 + 64 < g.N) tma_store_2d(&mapO, rm0 + 4096, n0 + 64, m0 + lg * 32);
-          if (g.out_t) tma_store_2d(&mapT, tb, m0 + lg * 32, n0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
     }
     if ((MODE == 0 || MODE == 1) && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }

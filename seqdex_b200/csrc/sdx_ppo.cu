@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <string.h>
 #include <math.h>
@@ -48,6 +49,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
 #define GEMM_BN 128
 #define GEMM_STAGES 4   /* 4 x 32 KB TMA stages + 64 KB epilogue staging: one persistent CTA per SM */
 typedef GemmSmem<GEMM_BN, GEMM_STAGES> GSm;
+typedef GemmSmem<256, 3> GSmW;   // wide tiles: 128 x 256, 3 x 48 KB stages + 64 KB staging (higher flop/byte against the L2 bound)
 static bool g_attr_set = false;
 static int set_attrs() {
   if (g_attr_set) return 0;
@@ -57,6 +59,8 @@ static int set_attrs() {
   PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PCK(cudaFuncSetAttribute(k_gemm_tn<256, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmW) + 1024));
+  PCK(cudaFuncSetAttribute(k_gemm_tn<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmW) + 1024));
   g_attr_set = true;
   return 0;
 }
@@ -68,14 +72,23 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
                                 int splits, void* stream) {
   if (set_attrs()) return -1;
   if ((lda % 8) || (ldb % 8) || M <= 0 || N <= 0 || K <= 0) { sdx_set_error("sdx_gemm_bf16_tn: bad shape (ld must be a multiple of 8)"); return -1; }
-  CUtensorMap ma, mb, mo, mt;
+  CUtensorMap ma, mb, mo, mt, mh;
+  static int wide_ok = -1;
+  if (wide_ok < 0) { const char* e = getenv("SDX_GEMM_WIDE"); wide_ok = e ? atoi(e) : 1; }
+  // 128 x 256 tiles for the large bf16-output GEMMs: twice the flops per byte pulled from L2 into the SM
+  const bool wide = wide_ok && mode == 0 && N >= 256 && (long long)M * N >= (long long)GEMM_BM * 256 * 148;
+  const int BNsel = wide ? 256 : GEMM_BN;
   if (make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1;
-  if (make_map(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, GEMM_BN)) return -1;
-  mo = ma; mt = ma;   // placeholders when the mode has no bf16 output
+  if (make_map(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BNsel)) return -1;
+  mo = ma; mt = ma; mh = ma;   // placeholders when the mode has no bf16 output / no h input
   if (mode == 0 || mode == 1) {
     if (!out || (ldo % 8) || (out_t && (ldt % 8))) { sdx_set_error("sdx_gemm_bf16_tn: bf16 outputs need ld % 8 == 0"); return -1; }
     if (make_map(&mo, out, (uint64_t)M, (uint64_t)N, (uint64_t)ldo, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;                   // [32 rows x 64 cols] boxes
-    if (out_t && make_map(&mt, out_t, (uint64_t)N, (uint64_t)M, (uint64_t)ldt, 128, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;         // [128 n x 32 m] boxes
+    if (mode == 1) {
+      if (!h || (ldh % 8)) { sdx_set_error("sdx_gemm_bf16_tn: mode 1 needs h with ldh % 8 == 0"); return -1; }
+      if (make_map(&mh, h, (uint64_t)M, (uint64_t)N, (uint64_t)ldh, 32, 64, CU_TENSOR_MAP_SWIZZLE_128B)) return -1;
+    }
+    if (out_t && make_map(&mt, out_t, (uint64_t)N, (uint64_t)M, (uint64_t)ldt, 64, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;          // [64 n x 32 m] boxes
   }
   GemmArgs g;
   g.M = M; g.N = N; g.K = K;
@@ -86,18 +99,22 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
   splits = (total_kb + g.kblocks_per_split - 1) / g.kblocks_per_split;
   g.bias = bias; g.h = (const __nv_bfloat16*)h; g.ldh = ldh; g.out = (__nv_bfloat16*)out; g.ldo = ldo;
   g.out_t = (__nv_bfloat16*)out_t; g.ldt = ldt; g.outf = outf; g.ldf = ldf;
-  int n_tiles = ((N + GEMM_BN - 1) / GEMM_BN) * ((M + GEMM_BM - 1) / GEMM_BM) * splits;
+  int n_tiles = ((N + BNsel - 1) / BNsel) * ((M + GEMM_BM - 1) / GEMM_BM) * splits;
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   dim3 grid(n_tiles < n_sm ? n_tiles : n_sm);   // persistent: one CTA per SM walks the tiles
   size_t smem = sizeof(GSm) + 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (mode) {
-    case 0: k_gemm_tn<GEMM_BN, GEMM_STAGES, 0><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
-    case 1: k_gemm_tn<GEMM_BN, GEMM_STAGES, 1><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
-    case 2: k_gemm_tn<GEMM_BN, GEMM_STAGES, 2><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
-    case 3: k_gemm_tn<GEMM_BN, GEMM_STAGES, 3><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
-    case 4: k_gemm_tn<GEMM_BN, GEMM_STAGES, 4><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, g); break;
+  if (wide) {
+    const size_t smw = sizeof(GSmW) + 1024;
+    if (mode == 0) k_gemm_tn<256, 3, 0><<<grid, GEMM_THREADS, smw, st>>>(ma, mb, mo, mt, mh, g);
+    else k_gemm_tn<256, 3, 1><<<grid, GEMM_THREADS, smw, st>>>(ma, mb, mo, mt, mh, g);
+  } else switch (mode) {
+    case 0: k_gemm_tn<GEMM_BN, GEMM_STAGES, 0><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, mh, g); break;
+    case 1: k_gemm_tn<GEMM_BN, GEMM_STAGES, 1><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, mh, g); break;
+    case 2: k_gemm_tn<GEMM_BN, GEMM_STAGES, 2><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, mh, g); break;
+    case 3: k_gemm_tn<GEMM_BN, GEMM_STAGES, 3><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, mh, g); break;
+    case 4: k_gemm_tn<GEMM_BN, GEMM_STAGES, 4><<<grid, GEMM_THREADS, smem, st>>>(ma, mb, mo, mt, mh, g); break;
     default: sdx_set_error("sdx_gemm_bf16_tn: bad mode"); return -1;
   }
   g_ppo_launches++;

@@ -73,3 +73,28 @@ def test_backward_dw_split_k(splits):
     _gemm(2, A, B, outf=out, splits=splits)
     ref = A.float() @ B.float().T
     torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(32768, 512, 256), (20000 + 8, 328, 192)])
+def test_wide_tiles_forward_and_dx(M, N, K):
+    """large outputs take the 128 x 256 tile path (sdx_ppo.cu: `wide`); ragged M and N exercise the clipped TMA boxes"""
+    torch.manual_seed(4)
+    A = (torch.randn(M, K, device="cuda") * 0.2).bfloat16()
+    B = (torch.randn(N, K, device="cuda") * 0.2).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    out_t = torch.zeros(N + 16, M, device="cuda", dtype=torch.bfloat16)
+    _gemm(0, A, B, bias=bias, out=out, out_t=out_t)
+    acc = A.float() @ B.float().T
+    ref = torch.nn.functional.elu(acc + bias)
+    torch.testing.assert_close(out.float(), ref, rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(out_t[:N].float(), ref.T.contiguous(), rtol=1e-2, atol=1e-2)
+    assert (out_t[N:] == 0).all()
+    h = torch.nn.functional.elu(torch.randn(M, N, device="cuda")).bfloat16()
+    out2 = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    out2_t = torch.zeros(N, M, device="cuda", dtype=torch.bfloat16)
+    _gemm(1, A, B, h=h, out=out2, out_t=out2_t)
+    hf = h.float()
+    ref2 = acc * torch.where(hf > 0, torch.ones_like(hf), hf + 1)
+    torch.testing.assert_close(out2.float(), ref2, rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(out2_t.float(), ref2.T.contiguous(), rtol=1e-2, atol=2e-2)
