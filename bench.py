@@ -67,6 +67,19 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+PRE_STEPS = 80          # untimed steps after staggering: every env has been through a reset, the episode-phase mix is stationary
+STAGGER = 75            # an untrained policy's episodes end at progress 75 (GS:1751: far from the target after 75 steps)
+
+
+def precondition_cpu(env, rng):
+    """same episode-phase mix as the GPU arm: first step resets every env, then progress ~ U[0, 75), then PRE_STEPS steps"""
+    n = env.n
+    env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
+    env.progress[:] = rng.integers(0, STAGGER, size=n)
+    for _ in range(PRE_STEPS):
+        env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
+
+
 def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None):
     """the oracle (CPU port of the same hot path) on the host cores, bounded sample of the same workload"""
     from oracle import oracle
@@ -76,14 +89,15 @@ def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None):
     env = oracle.OracleEnv(scene, n)
     env.set_heap_bank(bank)
     rng = np.random.default_rng(0)
-    env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))   # warm-up (includes the reset of every env)
+    precondition_cpu(env, rng)
     t0, steps = time.time(), 0
     while time.time() - t0 < seconds or steps < 2:
         env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
         steps += 1
     dt = time.time() - t0
     return {"value": n * steps / dt, "unit": "env-steps/s", "cores": int(cores), "kind": "port",
-            "sample": f"{n} envs x {steps} VecTask.step() calls of the C oracle (oracle/sdx_oracle.c), {dt:.1f} s"}
+            "sample": f"{n} envs x {steps} VecTask.step() calls of the C oracle (oracle/sdx_oracle.c), {dt:.1f} s, after the same "
+                      f"episode staggering + {PRE_STEPS} untimed steps as the GPU arm"}
 
 
 def host_bank(scene, per_type=2, settle=150):
@@ -120,6 +134,7 @@ def run_reference(args):
     env = oracle.OracleEnv(scene, n)
     env.set_heap_bank(bank)
     rng = np.random.default_rng(0)
+    precondition_cpu(env, rng)
     for _ in range(max(args.warmup, 1)):
         env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
     t0 = time.time()
@@ -127,7 +142,8 @@ def run_reference(args):
         env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
     dt = time.time() - t0
     val = n * args.steps / dt
-    sample = f"{n} envs per step (bounded sample of the {args.num_envs}-env workload), C oracle on {cores} host threads"
+    sample = (f"{n} envs per step (bounded sample of the {args.num_envs}-env workload), C oracle on {cores} host threads, "
+              f"episodes staggered + {PRE_STEPS} untimed steps first")
     print(json.dumps({
         "impl": "reference", "metric": "env-steps/sec at num_envs=16384 (BlockAssemblyGraspSim)", "value": val, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
@@ -189,6 +205,13 @@ def main():
     import ctypes
     from seqdex_b200 import _lib
     ppo_launch = lambda: int(_lib.load().sdx_ppo_launch_count())
+    # stationary episode-phase mix (untimed set-up): the first step resets every env, then progress ~ U[0, 75) and
+    # PRE_STEPS steps, so that resets -- and with them the waking / falling asleep of the heaps -- are spread over time
+    # as they are in a long training run instead of all envs marching through one episode in lockstep
+    env.step(acts[0])
+    env.tensor("PROGRESS").copy_(torch.randint(0, STAGGER, (n,), device=dev, generator=gen))
+    for i in range(PRE_STEPS):
+        env.step(torch.rand(n, 23, device=dev, generator=gen) * 2 - 1)
     for i in range(W):
         env.step(acts[i])
     barrier()
@@ -223,7 +246,13 @@ def main():
         task.env, task.num_envs, task.num_obs, task.num_states, task.num_actions, task.device = env, n, 396, 564, 23, f"cuda:{local}"
         task.obs_buf, task.states_buf, task.rew_buf, task.reset_buf = (env.tensor(k) for k in ("OBS", "STATES", "REW", "RESET"))
         task.extras = {}
-        task.step = env.step
+        step_ev = []                    # CUDA events around every VecTask.step of the timed PPO iterations
+        def _timed_step(a):
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(); r = env.step(a); ev[1].record()
+            step_ev.append(ev)
+            return r
+        task.step = _timed_step
         venv = RLgamesVecTaskPython(task, task.device)
         agent = A2CAgent(venv, PPOConfig(minibatch_size=min(args.minibatch, 8 * n)), device=local,
                          dist_group=dist.group.WORLD if world > 1 else None)
@@ -233,12 +262,17 @@ def main():
             ppo_info = agent.train_epoch()
         barrier()
         l0, p0 = env.launch_count(), ppo_launch()
+        step_ev.clear()
+        asleep0 = float((env.tensor("SLEEP") >= max(scene.c.sleep_substeps, 1)).float().mean())
         e0.record()
         for _ in range(iters):
             ppo_info = agent.train_epoch()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1) * K / (iters * H)
+        ppo_info = dict(ppo_info or {})
+        ppo_info["env_step_ms_in_loop"] = float(np.mean([a.elapsed_time(b) for a, b in step_ev]))
+        ppo_info["bricks_asleep_frac_start_end"] = [asleep0, float((env.tensor("SLEEP") >= max(scene.c.sleep_substeps, 1)).float().mean())]
         launches = (env.launch_count() - l0 + ppo_launch() - p0) * K // (iters * H)
     # ---- end to end through the C-ABI with HOST buffers (sdx_step_host): H2D actions, D2H obs/states/rew/reset
     E = args.e2e_steps
@@ -281,7 +315,9 @@ def main():
                        "mode": args.mode, "minibatch": min(args.minibatch, 8 * n),
                        "num_envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "env state (260 MB at 16384 envs) exceeds the 126 MB L2; no explicit flush",
-                       "heap_bank_per_type": args.bank_per_type},
+                       "heap_bank_per_type": args.bank_per_type,
+                       "episodes": f"staggered: progress ~ U[0,{STAGGER}) then {PRE_STEPS} untimed steps before warm-up (stationary mix of "
+                                   "fresh and settled heaps; resting bricks sleep with PhysX's default threshold and 0.4 s timer)"},
             "e2e": {"value": world * n * E / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 23 * 4,
                     "d2h_bytes_per_step": n * (396 + 564 + 1) * 4 + n * 8, "steps": E},
             "gpu_launches": int(launches),
@@ -295,6 +331,7 @@ def main():
                          "note": "state-streaming bound is loose: the kernel is fp32-ALU / shared-memory bound (DESIGN.md section 6)"},
             "clocks": sampler.summary(),
             "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "dropped_max": int(nc[:, 1].max())},
+            "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
         }
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(scene, bank=bank[:, :2].cpu().numpy())

@@ -40,9 +40,9 @@ extern "C" {
 /* Constant scene tables (seqdex_b200/scene.py builds them; layout is ABI). */
 typedef struct sdx_scene_t {
   int n_bricks, n_fixed, n_rshapes, n_static;
-  int substeps, iters, max_episode_length, pad0;
+  int substeps, iters, max_episode_length, sleep_substeps;   /* sleep_substeps: quiet sub-steps before a brick sleeps; 0 = never */
   float dt, gravity_z, contact_offset, friction, baumgarte, slop, max_depen_vel, brick_ang_damp, max_ang_vel,
-      max_lin_vel, brick_lin_damp, pad1;
+      max_lin_vel, brick_lin_damp, sleep_energy;   /* sleep_energy: mass-normalised kinetic energy below which a brick is quiet */
   float base_pos[3], base_quat[4], pad2;
   int body_parent[SDX_NL];
   unsigned link_anc_mask[SDX_NL];            /* bit j: DoF j moves link */
@@ -58,10 +58,10 @@ typedef struct sdx_scene_t {
   float brick_init[SDX_MAX_BRICKS * 13];
   float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
   float cam_off_pos[3], cam_off_quat[4];
-  float act_moving_average, av_factor, vel_obs_scale, warm_start, pad3;
+  float act_moving_average, av_factor, vel_obs_scale, warm_start, wake_energy;   /* wake_energy: energy above which a brick wakes what it touches */
 } sdx_scene_t;
 
-/* Tensor kinds for sdx_tensor(): device buffers owned by the env. dtype 0=f32 1=i64 2=i32 */
+/* Tensor kinds for sdx_tensor(): device buffers owned by the env. dtype 0=f32 1=i64 2=i32 3=u8 */
 enum {
   SDX_T_BRICK = 0,      /* f32 [N][13][72]  free-brick COM state, SoA inside an env block            */
   SDX_T_DOF = 1,        /* f32 [N][3][24]   q | qd | position target (GS:313-316, 328-329)           */
@@ -87,7 +87,8 @@ enum {
   SDX_T_CONTACTS = 21,  /* f32 [N][SDX_MAX_CONTACTS][8] debug dump of the last sub-step's contacts   */
   SDX_T_WS = 22,        /* f32 [N][2][SDX_MAX_CONTACTS][4] contact-impulse cache (key bits, f.xyz), double buffered  */
   SDX_T_WSN = 23,       /* i32 [N][2]    entries in each cache buffer                                           */
-  SDX_T_COUNT = 24
+  SDX_T_SLEEP = 24,     /* u8  [N][72]   sub-steps since each free brick was last hot (0 = hot; >= sleep_substeps = asleep)  */
+  SDX_T_COUNT = 25
 };
 
 typedef struct sdx_env sdx_env_t;

@@ -90,6 +90,7 @@ class OracleEnv:
         self.condump = np.zeros((n, MAXC, 8), np.float32)
         self.ws = np.zeros((n, 2, MAXC, 4), np.float32)
         self.wsn = np.zeros((n, 2), np.int32)
+        self.slp = np.zeros((n, NB), np.uint8)      # sleep counters (sub-steps since last hot)
         self.ws_cur = 0
         self.gb_hand = np.zeros((8, 11024, 23, 2), np.float32)
         self.gb_obj = np.zeros((8, 11024, 13), np.float32)
@@ -116,11 +117,13 @@ class OracleEnv:
         self.progress[:] = 0
         self.reset[:] = 1
         self.wsn[:] = 0
+        self.slp[:] = 0
         self.refresh_links()
 
     def set_brick_roots(self, rows):
         rows = np.ascontiguousarray(rows, np.float32)
         self.L.sdxo_brick_from_root_rows(self.S, self.n, fp(self.brick), fp(rows))
+        self.slp[:] = 0      # setting a pose wakes the actor (sdx_set_actor_root_state_indexed does the same)
 
     def brick_roots(self):
         rows = np.zeros((self.n, NB, 13), np.float32)
@@ -137,7 +140,8 @@ class OracleEnv:
     # ---- BaseTask.step phases
     def simulate(self, dump=False):
         self.L.sdxo_simulate(self.S, self.n, fp(self.brick), fp(self.dof), fp(self.link), fp(self.jac7), fp(self.netf),
-                             ip(self.ncontact), fp(self.condump) if dump else None, fp(self.ws), ip(self.wsn), self.ws_cur)
+                             ip(self.ncontact), fp(self.condump) if dump else None, fp(self.ws), ip(self.wsn), self.ws_cur,
+                             self.slp.ctypes.data_as(ctypes.c_void_p))
         self.ws_cur ^= self.scene.c.substeps & 1
 
     def pre_physics(self, actions):
@@ -145,7 +149,7 @@ class OracleEnv:
             assert self.bank is not None, "reset needs a heap bank (GS:412-413)"
             self.L.sdxo_reset(self.S, self.n, ctypes.c_uint64(self.seed), fp(self.bank), self.per_type, fp(self.brick),
                               fp(self.dof), fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.successes),
-                              ip(self.episode), ip(self.wsn), int(self.total_steps > 0), fp(self.finger_dist), fp(self.tvalue),
+                              ip(self.episode), ip(self.wsn), self.slp.ctypes.data_as(ctypes.c_void_p), int(self.total_steps > 0), fp(self.finger_dist), fp(self.tvalue),
                               fp(self.gb_hand), fp(self.gb_obj), ip(self.gb_index))
         a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)   # VR:166
         self.L.sdxo_pre_physics(self.S, self.n, fp(a), fp(self.actions), fp(self.dof), fp(self.link), fp(self.jac7),

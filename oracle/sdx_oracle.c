@@ -45,9 +45,9 @@
 
 typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   int n_bricks, n_fixed, n_rshapes, n_static;
-  int substeps, iters, max_episode_length, pad0;
+  int substeps, iters, max_episode_length, sleep_substeps;
   float dt, gravity_z, contact_offset, friction, baumgarte, slop, max_depen_vel, brick_ang_damp, max_ang_vel,
-      max_lin_vel, brick_lin_damp, pad1;
+      max_lin_vel, brick_lin_damp, sleep_energy;
   float base_pos[3], base_quat[4], pad2;
   int body_parent[SDX_NL];
   unsigned link_anc_mask[SDX_NL];
@@ -63,7 +63,7 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   float brick_init[SDX_MAX_BRICKS * 13];
   float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
   float cam_off_pos[3], cam_off_quat[4];
-  float act_moving_average, av_factor, vel_obs_scale, warm_start, pad3;
+  float act_moving_average, av_factor, vel_obs_scale, warm_start, wake_energy;
 } sdx_scene_t;
 
 /* ------------------------------------------------------------------ math */
@@ -228,6 +228,7 @@ typedef struct {
   int astart[NBODY], aend[NBODY], boff[NBODY + 1]; unsigned short blist[SDX_MAX_CONTACTS];
   v3 linkF[SDX_NL], linkM[SDX_NL];
   uint32_t ckey[SDX_MAX_CONTACTS];
+  unsigned char asleep[NB], hot[NB], touch[NB];   /* sleeping (see sim_env): touch bit0 = robot, bit1 = hot brick */
 } work_t;
 
 static inline v3 brick_Iinv_mul(const sdx_scene_t* S, const work_t* W, int b, v3 u) {
@@ -260,6 +261,7 @@ static void contact_axes(const work_t* W, const contact_t* c, v3* n, v3* t1, v3*
 static float body_k(const sdx_scene_t* S, const work_t* W, int body, v3 wpt, v3 d) {
   if (body == STATIC_BODY) return 0.0f;
   if (body < NB) {
+    if (W->asleep[body]) return 0.0f;   /* a sleeping brick is immovable for this sub-step */
     v3 rxd = vcross(vsub(wpt, W->bx[body]), d);
     float k = S->br_invm[body] + vdot(rxd, brick_Iinv_mul(S, W, body, rxd));
     return (float)W->nb[body] * k;
@@ -278,9 +280,21 @@ static float body_k(const sdx_scene_t* S, const work_t* W, int body, v3 wpt, v3 
 /* one env, one control step = `substeps` sub-steps (gym.simulate, BT:140; yaml sim: substeps 2,
  * 16 position iterations).  brick: [13][72]; dof: [3][24]; link_out: [24][13]; jac7: [6][7];
  * netf: [24][3]; ncontact: [2]; condump: [MAXC][8] or NULL */
-/* ws: [2][MAXC][4] impulse cache of this env (key bits, f.xyz), wsn: [2] entry counts, ws_cur: buffer holding the latest list */
+/* ws: [2][MAXC][4] impulse cache of this env (key bits, f.xyz), wsn: [2] entry counts, ws_cur: buffer holding the latest list
+ *
+ * SLEEPING (what PhysX does to resting actors; its defaults apply to the reference because the yaml sets none):
+ * slp[b] counts the sub-steps since brick b was last energetic; 0 = HOT.  A brick with slp >= sleep_substeps is ASLEEP
+ * for the sub-step: zero velocity, no gravity, infinite mass, not integrated, and pairs of two non-awake boxes (asleep
+ * brick vs asleep brick / static) are dropped in the broad phase.  With E = (|v|^2 + |w|^2 r^2 / 3) / 2 (r = half diagonal
+ * of the box) of the solved velocities, at the end of the sub-step
+ *     asleep: touched by a robot link -> 0 (hot); touched by a brick that was hot at the sub-step start -> 1 (woken);
+ *             otherwise unchanged
+ *     awake : touched by a robot link or E >= wake_energy  -> 0   (hot: it wakes / keeps awake what it touches)
+ *             else E >= sleep_energy or touched by a hot brick -> 1   (awake, timer restarted)
+ *             else                                            -> slp + 1 (saturating at 255)
+ * sleep_substeps = 0 disables the mechanism. */
 static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_out, float* jac7, float* netf,
-                    int* ncontact, float* condump, float* ws, int* wsn, int ws_cur, work_t* W) {
+                    int* ncontact, float* condump, float* ws, int* wsn, int ws_cur, unsigned char* slp, work_t* W) {
   const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;
   const int n_owner = NB + nrs, n_target = NB + nrs + nst;
   const float h = S->dt / (float)S->substeps;
@@ -306,6 +320,11 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     const float* wsr = ws + (size_t)rb * SDX_MAX_CONTACTS * 4;
     float* wsw = ws + (size_t)(1 - rb) * SDX_MAX_CONTACTS * 4;
     const int nprev = wsn[rb];
+    for (int b = 0; b < NB; ++b) {
+      W->asleep[b] = (unsigned char)(b < nbr && S->sleep_substeps > 0 && (int)slp[b] >= S->sleep_substeps);
+      W->hot[b] = (unsigned char)(b < nbr && slp[b] == 0);
+      W->touch[b] = 0;
+    }
     /* 1. kinematics + shape poses */
     robot_fk(S, W->q, &W->K);
     for (int L = 0; L < SDX_NL; ++L) { W->bx[NB + L] = W->K.lx[L]; W->bq[NB + L] = W->K.lq[L]; qmat(W->K.lq[L], W->bR[NB + L]); }
@@ -333,7 +352,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       for (int b = 0; b < NB; ++b) {
         W->vfree[b] = vscale(V3(W->bv[b].x, W->bv[b].y, W->bv[b].z + h * S->gravity_z), ldamp);
         W->wfree[b] = vscale(W->bw[b], damp);
-        if (b >= nbr) { W->vfree[b] = V3(0, 0, 0); W->wfree[b] = V3(0, 0, 0); }
+        if (b >= nbr || W->asleep[b]) { W->vfree[b] = V3(0, 0, 0); W->wfree[b] = V3(0, 0, 0); }
         W->bv[b] = W->vfree[b]; W->bw[b] = W->wfree[b];
       }
       for (int j = 0; j < SDX_ND; ++j) {
@@ -372,6 +391,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         if (t == a) continue;
         if (t < NB && t >= nbr) continue;
         if (a >= NB && t >= NB && t < NB + nrs) continue; /* robot-robot filtered (GS:906 filter -1) */
+        if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue; /* neither box can move */
         v3 d = vsub(W->sc[a], W->sc[t]);
         float m = margin + W->spd[a] + W->spd[t];
         int hit = fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
@@ -454,6 +474,8 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       if (i == 0 || (int)(W->con[i - 1].word & 255) != a) W->astart[a] = i;
       W->aend[a] = i + 1;
       if (b != STATIC_BODY) W->nb[b]++;
+      if (a < NB && b != STATIC_BODY) { if (b >= NB) W->touch[a] |= 1; else if (W->hot[b]) W->touch[a] |= 2; }
+      if (b < NB) { if (a >= NB) W->touch[b] |= 1; else if (W->hot[a]) W->touch[b] |= 2; }
     }
     W->boff[0] = 0;
     for (int b = 0; b < NBODY; ++b) W->boff[b + 1] = W->boff[b] + W->nb[b];
@@ -502,6 +524,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         c->f[0] = f.x; c->f[1] = f.y; c->f[2] = f.z;
       }
       for (int b = 0; b < NBODY; ++b) { /* phase B: one body each; TWO interleaved partial sums (even / odd incidences), combined 0+1 */
+        if (b < NB && W->asleep[b]) continue; /* stays at rest */
         v3 Fk[2], Tk[2];
         for (int k = 0; k < 2; ++k) { Fk[k] = V3(0, 0, 0); Tk[k] = V3(0, 0, 0); }
         int na = W->aend[b] - W->astart[b], nbl = W->boff[b + 1] - W->boff[b];
@@ -541,11 +564,23 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     if (S->iters == 0) for (int L = 0; L < SDX_NL; ++L) { W->linkF[L] = V3(0, 0, 0); W->linkM[L] = V3(0, 0, 0); }
     /* 7. integrate */
     for (int b = 0; b < nbr; ++b) {
+      if (W->asleep[b]) {   /* pose and (zero) velocity unchanged; only a touch can restart the counter */
+        if (W->touch[b] & 1) slp[b] = 0; else if (W->touch[b] & 2) slp[b] = 1;
+        continue;
+      }
       v3 w = W->bw[b], v = W->bv[b];
       float w2 = vdot(w, w), mw = S->max_ang_vel;
       if (w2 > mw * mw) { w = vscale(w, mw / sqrtf(w2)); W->bw[b] = w; }
       float v2 = vdot(v, v), mv = S->max_lin_vel;
       if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); W->bv[b] = v; }
+      {
+        float E = 0.5f * (vdot(v, v) + vdot(w, w) * (W->srad[b] * W->srad[b] * (1.0f / 3.0f)));
+        int c = slp[b];
+        if ((W->touch[b] & 1) || E >= S->wake_energy) c = 0;
+        else if ((W->touch[b] & 2) || E >= S->sleep_energy) c = 1;
+        else c = c + 1 > 255 ? 255 : c + 1;
+        slp[b] = (unsigned char)c;
+      }
       W->bx[b] = vmad(v, h, W->bx[b]);
       q4 q = W->bq[b];
       float hh = 0.5f * h;
@@ -594,7 +629,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
 }
 
 typedef struct {
-  const sdx_scene_t* S; int n; float *brick, *dof, *link, *jac7, *netf; int* ncontact; float* condump; float* ws; int* wsn; int ws_cur;
+  const sdx_scene_t* S; int n; float *brick, *dof, *link, *jac7, *netf; int* ncontact; float* condump; float* ws; int* wsn; int ws_cur; unsigned char* slp;
   int tid, nthreads;
 } sim_job_t;
 static void* sim_worker(void* arg) {
@@ -604,7 +639,7 @@ static void* sim_worker(void* arg) {
     sim_env(J->S, J->brick + (size_t)e * 13 * NB, J->dof + (size_t)e * 72, J->link + (size_t)e * SDX_NL * 13,
             J->jac7 + (size_t)e * 42, J->netf + (size_t)e * SDX_NL * 3, J->ncontact + 2 * e,
             J->condump ? J->condump + (size_t)e * SDX_MAX_CONTACTS * 8 : 0, J->ws + (size_t)e * 2 * SDX_MAX_CONTACTS * 4, J->wsn + 2 * e,
-            J->ws_cur, W);
+            J->ws_cur, J->slp + (size_t)e * NB, W);
   free(W);
   return 0;
 }
@@ -617,14 +652,14 @@ int sdxo_get_threads(void) {
 }
 /* envs are independent: static round-robin over host threads (results do not depend on the thread count) */
 void sdxo_simulate(const sdx_scene_t* S, int n, float* brick, float* dof, float* link, float* jac7, float* netf,
-                   int* ncontact, float* condump, float* ws, int* wsn, int ws_cur) {
+                   int* ncontact, float* condump, float* ws, int* wsn, int ws_cur, unsigned char* slp) {
   int nt = sdxo_get_threads();
   if (nt > n) nt = n;
   if (nt < 1) nt = 1;
   if (nt > 256) nt = 256;
   pthread_t th[256]; sim_job_t jobs[256];
   for (int t = 0; t < nt; ++t) {
-    sim_job_t j = {S, n, brick, dof, link, jac7, netf, ncontact, condump, ws, wsn, ws_cur, t, nt};
+    sim_job_t j = {S, n, brick, dof, link, jac7, netf, ncontact, condump, ws, wsn, ws_cur, slp, t, nt};
     jobs[t] = j;
     if (t > 0) pthread_create(&th[t], 0, sim_worker, &jobs[t]);
   }
@@ -738,7 +773,7 @@ void sdxo_control_ik(int n, const float* J, const float* dpose, float* u) { for 
  * not restated (DESIGN.md "reset"): the randomised target pose (GS:1488-1499) is overwritten by the
  * banked heap row (GS:1508-1511) and perturb_* (GS:1460-1461) feed a disabled branch. */
 void sdxo_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* bank, int per_type, float* brick, float* dof,
-                float* target_init, int64_t* progress, int64_t* reset, float* successes, int* episode, int* wsn,
+                float* target_init, int64_t* progress, int64_t* reset, float* successes, int* episode, int* wsn, unsigned char* slp,
                 /* grasp terminal-state banking (GS:1399-1445) */
                 int do_bank, const float* finger_dist, const float* tvalue, float* gb_hand, float* gb_obj, int* gb_index) {
   if (do_bank) {
@@ -783,6 +818,7 @@ void sdxo_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* bank, i
     for (int k = 0; k < 7; ++k) target_init[7 * e + k] = rows[tb * 13 + k]; /* GS:1547-1548 */
     progress[e] = 0; reset[e] = 0; successes[e] = 0.0f; /* GS:1550-1552 */
     wsn[2 * e] = 0; wsn[2 * e + 1] = 0; /* a new heap: no contact persists */
+    for (int b = 0; b < NB; ++b) slp[(size_t)e * NB + b] = 0; /* setting a pose wakes the actor */
     episode[e] += 1;
   }
 }

@@ -65,6 +65,7 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
     case SDX_T_CONTACTS: s[0] = n; s[1] = SDX_MAX_CONTACTS; s[2] = 8; nd = 3; break;
     case SDX_T_WS: s[0] = n; s[1] = 2; s[2] = SDX_MAX_CONTACTS; s[3] = 4; nd = 4; break;
     case SDX_T_WSN: s[0] = n; s[1] = 2; nd = 2; dt = 2; break;
+    case SDX_T_SLEEP: s[0] = n; s[1] = NB; nd = 2; dt = 3; break;
     default: return 0;
   }
   if (shape) for (int i = 0; i < 4; ++i) shape[i] = s[i];
@@ -72,7 +73,7 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
   if (dtype) *dtype = dt;
   return (size_t)(s[0] * s[1] * s[2] * s[3]);
 }
-static size_t dtype_size(int dt) { return dt == 1 ? 8 : 4; }
+static size_t dtype_size(int dt) { return dt == 1 ? 8 : (dt == 3 ? 1 : 4); }
 
 extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, uint64_t seed, sdx_env_t** out) {
   if (!scene || !out || num_envs <= 0) { g_err = "sdx_create: bad arguments"; return -1; }
@@ -169,7 +170,7 @@ extern "C" int sdx_refresh(sdx_env_t* E, int kind) {
 extern "C" int sdx_set_actor_root_state_indexed(sdx_env_t* E, const float* root_dev, const int32_t* idx_dev, int n) {
   CK(cudaSetDevice(E->device));
   if (n <= 0) return 0;
-  k_set_root_indexed<<<(n + 255) / 256, 256, 0, E->stream>>>(E->scene, E->n, F(SDX_T_BRICK), root_dev, idx_dev, n);
+  k_set_root_indexed<<<(n + 255) / 256, 256, 0, E->stream>>>(E->scene, E->n, F(SDX_T_BRICK), root_dev, idx_dev, n, (unsigned char*)E->buf[SDX_T_SLEEP]);
   E->launches++; CKL(); return 0;
 }
 extern "C" int sdx_set_dof_state_indexed(sdx_env_t* E, const float* src, const int32_t* idx_dev, int n) {
@@ -232,6 +233,7 @@ extern "C" int sdx_set_tvalue_weights(sdx_env_t* E, const float* w) {
 extern "C" int sdx_reset_all(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
   CK(cudaMemsetAsync(E->buf[SDX_T_WSN], 0, (size_t)E->n * 2 * 4, E->stream));
+  CK(cudaMemsetAsync(E->buf[SDX_T_SLEEP], 0, (size_t)E->n * NB, E->stream));
   k_reset_all<<<E->n, 128, 0, E->stream>>>(E->scene, E->n, F(SDX_T_BRICK), F(SDX_T_DOF), I64(SDX_T_PROGRESS), I64(SDX_T_RESET));
   CKL();
   k_refresh_links<<<(E->n + 63) / 64, 64, 0, E->stream>>>(E->scene, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7), E->n);
@@ -250,7 +252,8 @@ extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
     E->launches++;
   }
   k_reset<<<n, 128, 0, E->stream>>>(E->scene, n, E->seed, E->bank, E->per_type, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_TARGET_INIT),
-                                    I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), I32(SDX_T_EPISODE), I32(SDX_T_WSN));
+                                    I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), I32(SDX_T_EPISODE), I32(SDX_T_WSN),
+                                    (unsigned char*)E->buf[SDX_T_SLEEP]);
   k_pre_physics<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, actions_dev, F(SDX_T_ACTIONS), F(SDX_T_DOF), F(SDX_T_LINK),
                                                         F(SDX_T_JAC7), I64(SDX_T_PROGRESS), F(SDX_T_TARGET_INIT));
   E->launches += 2;
@@ -263,7 +266,7 @@ extern "C" int sdx_simulate(sdx_env_t* E) {
   k_simulate<<<E->n, SIM_THREADS, sizeof(SimSmem), E->stream>>>(E->scene, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
                                                               F(SDX_T_NETF), I32(SDX_T_NCONTACT),
                                                               E->dump_contacts ? F(SDX_T_CONTACTS) : nullptr, F(SDX_T_WS), I32(SDX_T_WSN),
-                                                              E->ws_cur, E->n);
+                                                              E->ws_cur, (unsigned char*)E->buf[SDX_T_SLEEP], E->n);
   E->ws_cur ^= (E->host_scene.substeps & 1);
   E->launches++;
   CKL();

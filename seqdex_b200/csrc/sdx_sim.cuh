@@ -58,6 +58,7 @@ struct SimSmem {
   int poff[NOWN + 1];
   int scan[SIM_THREADS];
   int ncon, ndropped;
+  unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
   // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
   float4 ca[MAXC];    // contact point w.xyz | bias
   float4 cb[MAXC];    // 1/den along n, t1, t2 | packed word (bodies, target shape, face axis, sign)
@@ -206,6 +207,9 @@ __device__ __forceinline__ bool point_hit(const PairGeom& G, int p, float m, flo
   return inface;
 }
 
+__device__ __forceinline__ void touch_or(unsigned char* flags, int i, unsigned bits) {
+  atomicOr(reinterpret_cast<unsigned*>(flags) + (i >> 2), bits << (8 * (i & 3)));
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
   uint32_t done = 0;
@@ -218,7 +222,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 __global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
-           int* __restrict__ ncontact, float* __restrict__ condump, float* ws, int* wsn, int ws_cur, int n_envs) {
+           int* __restrict__ ncontact, float* __restrict__ condump, float* ws, int* wsn, int ws_cur,
+           unsigned char* __restrict__ slp, int n_envs) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SimSmem& M = *reinterpret_cast<SimSmem*>(smem_raw);
   const int e = blockIdx.x, tid = threadIdx.x;
@@ -263,6 +268,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   v3 bxr = V3(0, 0, 0), bvr = V3(0, 0, 0), bwr = V3(0, 0, 0);
   q4 bqr = Q4(0, 0, 0, 1);
   v3 halfb = V3(0, 0, 0);
+  int slpc = (tid < NB) ? (int)slp[(size_t)e * NB + tid] : 0;   // sub-steps since this brick was last hot (oracle: sim_env SLEEPING)
+  const int sleep_n = S->sleep_substeps;
   const unsigned my_anc = (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) ? S->link_anc_mask[tid - ROBOT_TID0] : 0u;
   unsigned my_desc = 0u;   // DoF threads: links moved by this DoF
   if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_ND)
@@ -272,8 +279,6 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     bqr = Q4(M.tile[3 * NB + tid], M.tile[4 * NB + tid], M.tile[5 * NB + tid], M.tile[6 * NB + tid]);
     bvr = V3(M.tile[7 * NB + tid], M.tile[8 * NB + tid], M.tile[9 * NB + tid]);
     bwr = V3(M.tile[10 * NB + tid], M.tile[11 * NB + tid], M.tile[12 * NB + tid]);
-    st3(M.binvI[tid], V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]));
-    M.binvm[tid] = S->br_invm[tid];
     halfb = V3(S->br_half[3 * tid], S->br_half[3 * tid + 1], S->br_half[3 * tid + 2]);
     st3(M.sh[tid], halfb);
     M.srad[tid] = sqrtf(vdot(halfb, halfb));
@@ -298,14 +303,20 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     const int nprev = gwsn[rb];
     // 1. kinematics (one thread walks the chain) || brick poses + free velocities
     if (tid >= ROBOT_TID0) robot_fk(S, M, tid - ROBOT_TID0);
+    bool asleep = false;
     if (tid < NB) {
+      asleep = tid < nbr && sleep_n > 0 && slpc >= sleep_n;
+      M.sflag[tid] = (unsigned char)((asleep ? 1 : 0) | ((tid < nbr && slpc == 0) ? 2 : 0));
+      M.touch[tid] = 0;
+      M.binvm[tid] = asleep ? 0.0f : S->br_invm[tid];        // a sleeping brick is immovable for this sub-step
+      st3(M.binvI[tid], asleep ? V3(0.0f, 0.0f, 0.0f) : V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]));
       qmat(bqr, M.sR[tid]);
       st3(M.sc[tid], bxr); st3(M.bx[tid], bxr);
       float damp = 1.0f - h * S->brick_ang_damp;
       float ldamp = 1.0f - h * S->brick_lin_damp;
       v3 vfree = vscale(V3(bvr.x, bvr.y, bvr.z + h * S->gravity_z), ldamp);
       v3 wfree = vscale(bwr, damp);
-      if (tid >= nbr) { vfree = V3(0.0f, 0.0f, 0.0f); wfree = V3(0.0f, 0.0f, 0.0f); }
+      if (tid >= nbr || asleep) { vfree = V3(0.0f, 0.0f, 0.0f); wfree = V3(0.0f, 0.0f, 0.0f); }
       st3(M.bv[tid], vfree); st3(M.bw[tid], wfree);
       st3(M.vfree[tid], vfree); st3(M.wfree[tid], wfree);
     }
@@ -361,10 +372,12 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       if (!(a < NB && a >= nbr)) {
         v3 ca = ld3(M.sc[a]), aa = ld3(M.sa[a]);
         float spa = M.spd[a];
+        const bool a_sl = a < NB && (M.sflag[a] & 1);
         for (int t = 0; t < n_target; ++t) {
           if (t == a) continue;
           if (t < NB && t >= nbr) continue;
           if (a >= NB && t >= NB && t < NB + nrs) continue;   // robot-robot filtered (GS:906)
+          if (a_sl && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)))) continue;   // neither box can move
           v3 d = vsub(ca, ld3(M.sc[t]));
           v3 at = ld3(M.sa[t]);
           float m = margin + spa + M.spd[t];
@@ -488,6 +501,9 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       if (i == 0 || (int)(__float_as_uint(M.cb[i - 1].w) & 255) != a) M.astart[a] = i;
       if (i == ncon - 1 || (int)(__float_as_uint(M.cb[i + 1].w) & 255) != a) M.aend[a] = i + 1;
       if (b != STATIC_BODY) atomicAdd(&M.nb[b], 1);
+      // sleeping: who touched whom (all writers of a flag byte OR in bits => atomicOr on the containing word)
+      if (a < NB && b != STATIC_BODY) { if (b >= NB) touch_or(M.touch, a, 1u); else if (M.sflag[b] & 2) touch_or(M.touch, a, 2u); }
+      if (b < NB) { if (a >= NB) touch_or(M.touch, b, 1u); else if (M.sflag[a] & 2) touch_or(M.touch, b, 2u); }
     }
     __syncthreads();
     if (tid < 32) {
@@ -585,7 +601,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         const bool live = item < n_items;
         const int body = !robot_warp ? (live ? (item >> 1) : 0) : NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
         const int k = item & 1;
-        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
+        const bool b_sl = body < NB && (M.sflag[body] & 1);       // sleeping bricks stay at rest
+        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = (live && !b_sl) ? na + (M.boff[body + 1] - b0) : 0;
         const v3 xb = body < NB ? ld3(M.bx[body]) : V3(0.0f, 0.0f, 0.0f);
         v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
         for (int ee = k; ee < ntot; ee += 2) {
@@ -600,7 +617,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         }
         F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
         T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
-        if (k == 0 && live) {
+        if (k == 0 && live && !b_sl) {
           if (body < NB) {
             st3(M.bv[body], vmad(F, M.binvm[body], ld3(M.vfree[body])));
             st3(M.bw[body], vadd(ld3(M.wfree[body]), brick_Iinv_mul(M.sR[body], ld3(M.binvI[body]), T)));
@@ -628,12 +645,24 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     rb = 1 - rb;
     if (iters == 0 && tid < SDX_NL) { st3(M.linkF[tid], V3(0, 0, 0)); st3(M.linkM[tid], V3(0, 0, 0)); }
     // 10. integrate
-    if (tid < nbr) {
+    if (tid < nbr && asleep) {                                 // pose unchanged; only a touch restarts the counter
+      const unsigned tc = M.touch[tid];
+      if (tc & 1) slpc = 0; else if (tc & 2) slpc = 1;
+      bvr = V3(0.0f, 0.0f, 0.0f); bwr = V3(0.0f, 0.0f, 0.0f);
+    } else if (tid < nbr) {
       v3 w = ld3(M.bw[tid]), v = ld3(M.bv[tid]);
       float w2 = vdot(w, w), mw = S->max_ang_vel;
       if (w2 > mw * mw) { w = vscale(w, mw / sqrtf(w2)); }
       float v2 = vdot(v, v), mv = S->max_lin_vel;
       if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); }
+      {
+        const float rad = M.srad[tid];
+        const float E = 0.5f * (vdot(v, v) + vdot(w, w) * (rad * rad * (1.0f / 3.0f)));
+        const unsigned tc = M.touch[tid];
+        if ((tc & 1) || E >= S->wake_energy) slpc = 0;
+        else if ((tc & 2) || E >= S->sleep_energy) slpc = 1;
+        else slpc = slpc + 1 > 255 ? 255 : slpc + 1;
+      }
       bvr = v; bwr = w;
       bxr = vmad(v, h, bxr);
       q4 q = bqr;
@@ -696,5 +725,6 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     J[3 * 7 + j] = aj.x; J[4 * 7 + j] = aj.y; J[5 * 7 + j] = aj.z;
   }
   if (tid == 64) { ncontact[2 * e] = M.ncon; ncontact[2 * e + 1] = M.ndropped; }
+  if (tid < NB) slp[(size_t)e * NB + tid] = (unsigned char)slpc;
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }

@@ -135,7 +135,8 @@ k_bank_terminal(const sdx_scene_t* __restrict__ S, int n, const float* __restric
 __global__ void __launch_bounds__(128)
 k_reset(const sdx_scene_t* __restrict__ S, int n, uint64_t seed, const float* __restrict__ bank, int per_type,
         float* __restrict__ brick, float* __restrict__ dof, float* __restrict__ target_init, int64_t* __restrict__ progress,
-        int64_t* __restrict__ reset, float* __restrict__ successes, int* __restrict__ episode, int* __restrict__ wsn) {
+        int64_t* __restrict__ reset, float* __restrict__ successes, int* __restrict__ episode, int* __restrict__ wsn,
+        unsigned char* __restrict__ slp) {
   const int e = blockIdx.x, tid = threadIdx.x;
   if (e >= n || !reset[e]) return;
   const int ep = episode[e];
@@ -151,6 +152,7 @@ k_reset(const sdx_scene_t* __restrict__ S, int n, uint64_t seed, const float* __
     for (int k = 0; k < 7; ++k) row[k] = rows[tid * 13 + k];
     for (int k = 7; k < 13; ++k) row[k] = 0.0f;                                   // GS:1513
     brick_from_root_row(S, B, tid, row);
+    slp[(size_t)e * NB + tid] = 0;                                                // setting a pose wakes the actor
   } else if (tid >= 96 && tid < 96 + 7) {
     int j = tid - 96;
     d[j] = S->prepare_arm[j]; d[24 + j] = 0.0f; d[48 + j] = S->prepare_arm[j];     // GS:1526-1529
@@ -465,12 +467,13 @@ __global__ void k_refresh_jacobian(const sdx_scene_t* __restrict__ S, int n, con
   o[0 * SDX_ND] = lin.x; o[1 * SDX_ND] = lin.y; o[2 * SDX_ND] = lin.z; o[3 * SDX_ND] = ang.x; o[4 * SDX_ND] = ang.y; o[5 * SDX_ND] = ang.z;
 }
 __global__ void k_set_root_indexed(const sdx_scene_t* __restrict__ S, int n_envs, float* __restrict__ brick, const float* __restrict__ root,
-                                   const int32_t* __restrict__ idx, int n) {
+                                   const int32_t* __restrict__ idx, int n, unsigned char* __restrict__ slp) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int ai = idx[i], e = ai / SDX_ACTORS_PER_ENV, a = ai % SDX_ACTORS_PER_ENV;
   if (e >= n_envs || a < 9 || a >= 9 + NB) return;   // only free bricks carry simulation state; the rest are fixed actors
   brick_from_root_row(S, brick + (size_t)e * 13 * NB, a - 9, root + (size_t)ai * 13);
+  slp[(size_t)e * NB + (a - 9)] = 0;                  // setting a pose wakes the actor (PhysX does the same)
 }
 __global__ void k_set_dof_indexed(int n_envs, float* __restrict__ dof, const float* __restrict__ src, const int32_t* __restrict__ idx, int n, int mode) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

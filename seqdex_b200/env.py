@@ -12,8 +12,8 @@ from .scene import Scene
 
 T = dict(BRICK=0, DOF=1, LINK=2, JAC7=3, NETF=4, ACTIONS=5, OBS=6, STATES=7, REW=8, RESET=9, PROGRESS=10, TVALUE=11,
          TARGET_INIT=12, SUCCESSES=13, CONSEC=14, NCONTACT=15, ROOT=16, RB=17, DOF_STATE=18, JACOBIAN=19, EPISODE=20,
-         CONTACTS=21, WS=22, WSN=23)
-_DT = {0: (torch.float32, "<f4"), 1: (torch.int64, "<i8"), 2: (torch.int32, "<i4")}
+         CONTACTS=21, WS=22, WSN=23, SLEEP=24)
+_DT = {0: (torch.float32, "<f4"), 1: (torch.int64, "<i8"), 2: (torch.int32, "<i4"), 3: (torch.uint8, "|u1")}
 
 
 class _DevView:

@@ -63,6 +63,7 @@ def test_contact_step_bit_exact(scene, oracle_lib, steps):
     _cmp("link", g.tensor("LINK"), o.link)
     _cmp("jac7", g.tensor("JAC7"), o.jac7)
     _cmp("netf", g.tensor("NETF"), o.netf)
+    _cmp("sleep counters", g.tensor("SLEEP"), o.slp)
     _cmp("impulse-cache counts", g.tensor("WSN"), o.wsn)
     gws = g.tensor("WS").cpu().numpy()
     for e in range(o.n):     # warm-start cache: same keys, same impulses (latest buffer)
@@ -92,6 +93,35 @@ def test_robot_contacts_exercised(scene, oracle_lib):
     assert robot_seen > 0, "hand never touched the heap: test does not cover robot contacts"
 
 
+def test_sleeping_and_waking_bit_exact(oracle_lib):
+    """bricks dropped into the bin fall asleep (short timer so it happens within the test), the hand then ploughs into
+    the heap and wakes some of them: counters, poses and contact counts must follow the oracle bit for bit"""
+    from seqdex_b200.scene import Scene
+    sc = Scene(sleep_time=0.1)
+    ns = sc.c.sleep_substeps
+    assert ns == 12
+    g, o = _mk(sc, oracle_lib, 4)
+    slept = woken = 0
+    for t in range(150):
+        if t == 70:                                    # now send the hand down into the heap
+            tgt = o.dof[:, 2, :].copy()
+            tgt[:, 1] += 0.9; tgt[:, 3] += 0.6
+            o.dof[:, 2, :] = tgt
+            g.tensor("DOF")[:, 2, :] = torch.from_numpy(tgt).cuda()
+        before = o.slp.copy()
+        g.simulate(); o.simulate()
+        slept = max(slept, int((o.slp >= ns).sum()))
+        woken += int(((before >= ns) & (o.slp < ns)).sum())
+        if t % 10 == 9 or t in (70, 71, 72):
+            torch.cuda.synchronize()
+            _cmp(f"sleep@{t}", g.tensor("SLEEP"), o.slp)
+            _cmp(f"ncontact@{t}", g.tensor("NCONTACT"), o.ncontact)
+            _cmp(f"brick@{t}", g.tensor("BRICK"), o.brick)
+            _cmp(f"dof@{t}", g.tensor("DOF"), o.dof)
+    assert slept > 4 * 36, f"only {slept} brick-states ever asleep: the test does not cover sleeping"
+    assert woken > 0, "nothing was ever woken: the test does not cover waking"
+
+
 def test_full_step_bit_exact(scene, oracle_lib):
     """VecTask.step semantics end to end: reset_idx -> pre_physics -> simulate -> post_physics, 160 steps
     (crosses an episode boundary at progress 149, so resets, banking and the scripted lift are covered)."""
@@ -108,7 +138,7 @@ def test_full_step_bit_exact(scene, oracle_lib):
             torch.cuda.synchronize()
             for name, ov in (("OBS", o.obs), ("STATES", o.states), ("REW", o.rew), ("RESET", o.reset), ("PROGRESS", o.progress),
                              ("TVALUE", o.tvalue), ("TARGET_INIT", o.target_init), ("DOF", o.dof), ("BRICK", o.brick),
-                             ("EPISODE", o.episode), ("CONSEC", o.consec)):
+                             ("EPISODE", o.episode), ("CONSEC", o.consec), ("SLEEP", o.slp)):
                 _cmp(f"{name}@{t}", g.tensor(name), ov)
     assert o.episode.min() >= 2
 

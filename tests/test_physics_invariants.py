@@ -59,7 +59,7 @@ def test_head_on_collision_conserves_momentum(oracle_lib):
 
 
 def test_bricks_come_to_rest_with_bounded_penetration(oracle_lib):
-    s, e = _env(oracle_lib, 8)
+    s, e = _env(oracle_lib, 8, sleep_time=0.0)       # sleeping off: the solver itself has to hold the bricks still
     rows = e.brick_roots()
     rng = np.random.default_rng(0)
     for b in range(8):        # one layer, just above the fixed floor bricks (top at z = 0.6637), no initial overlap
@@ -118,3 +118,81 @@ def test_violent_start_stays_finite(oracle_lib):
     assert r[..., 2].min() > -0.1, "nothing tunnels through the ground plane"
     inside = (np.abs(r[..., 0] - 0.25) < 0.35) & (np.abs(r[..., 1] - 0.19) < 0.26)
     assert inside.mean() > 0.8, "most bricks end up in or next to the bin"
+
+
+def _layer(e, n_bricks=8, z=0.70):
+    rows = e.brick_roots()
+    rng = np.random.default_rng(0)
+    for b in range(n_bricks):
+        rows[0, b] = _rows((0.10 + 0.09 * (b % 4), 0.10 + 0.12 * (b // 4), z), quat=(0, 0, np.sin(0.3 * b), np.cos(0.3 * b)))
+    rows[0, :n_bricks, 0:2] += rng.uniform(-0.005, 0.005, size=(n_bricks, 2))
+    return rows.astype(np.float32)
+
+
+def test_resting_bricks_fall_asleep_and_stay_put(oracle_lib):
+    """PhysX puts resting actors to sleep (scene.py: sleep_energy / sleep_time); ours: oracle sim_env 'SLEEPING'."""
+    s, e = _env(oracle_lib, 8)
+    ns = s.c.sleep_substeps
+    assert ns == 48 and s.c.sleep_energy > 0
+    e.set_brick_roots(_layer(e))
+    for _ in range(20):
+        e.simulate()
+    assert e.ncontact[0, 0] >= 8 * 3 and (e.slp[0, :8] < ns).all()      # landed, supported, still awake (0.4 s not over)
+    for _ in range(130):
+        e.simulate()
+    assert (e.slp[0, :8] >= ns).all(), e.slp[0, :8]
+    assert e.ncontact[0, 0] == 0                                       # asleep-vs-static pairs are not even generated
+    assert (e.brick[0, 7:13, :8] == 0).all()
+    z = e.brick_roots()[0, :8, 2]
+    assert np.all(np.abs(z - (0.6637 + 0.01875)) < 0.006), z
+    before = e.brick.copy()
+    for _ in range(50):
+        e.simulate()
+    np.testing.assert_array_equal(e.brick, before)                     # bit-stable while asleep
+
+
+def test_sleeping_brick_wakes_when_hit_and_carries_the_load(oracle_lib):
+    s, e = _env(oracle_lib, 9)
+    ns = s.c.sleep_substeps
+    rows = _layer(e)
+    rows[0, 8] = _rows((0.45, 0.10, 0.70))                             # brick 8 parked away from the layer
+    e.set_brick_roots(rows)
+    for _ in range(150):
+        e.simulate()
+    assert (e.slp[0, :9] >= ns).all()
+    z0 = float(e.brick[0, 2, 0])
+    # teleport brick 8 to 12 cm above brick 0 (the facade's indexed root write wakes exactly the actors it touches)
+    e.brick[0, 0:3, 8] = e.brick[0, 0:3, 0] + np.array([0, 0, 0.12], np.float32)
+    e.brick[0, 7:13, 8] = 0
+    e.slp[0, 8] = 0
+    woke = False
+    for _ in range(60):
+        e.simulate()
+        woke |= bool(e.slp[0, 0] < ns)
+        assert e.brick[0, 2, 0] > z0 - 0.004, "the sleeping brick was pushed into its support"
+    assert woke, "the impact did not wake the sleeping brick"
+    for _ in range(120):
+        e.simulate()
+    assert (e.slp[0, :9] >= ns).all(), e.slp[0, :9]                    # everything is quiet again ...
+    assert e.brick[0, 2, 8] > z0 + 0.015                               # ... with brick 8 resting ON brick 0, not inside it
+    assert np.isfinite(e.brick).all()
+
+
+def test_sleeping_brick_wakes_when_its_support_is_knocked_away(oracle_lib):
+    s, e = _env(oracle_lib, 2)
+    ns = s.c.sleep_substeps
+    rows = e.brick_roots()
+    rows[0, 0] = _rows((0.25, 0.19, 0.70))
+    rows[0, 1] = _rows((0.25, 0.19, 0.75))                             # brick 1 stacked on brick 0
+    e.set_brick_roots(rows)
+    for _ in range(150):
+        e.simulate()
+    assert (e.slp[0, :2] >= ns).all()
+    z1 = float(e.brick[0, 2, 1])
+    assert z1 > e.brick[0, 2, 0] + 0.015
+    e.brick[0, 7, 0] = 1.5                                             # kick the lower brick out sideways
+    e.slp[0, 0] = 0
+    for _ in range(120):
+        e.simulate()
+    assert e.brick[0, 2, 1] < z1 - 0.01, "the upper brick kept floating on a support that is gone"
+    assert np.isfinite(e.brick).all()
