@@ -524,10 +524,10 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         c->f[0] = f.x; c->f[1] = f.y; c->f[2] = f.z;
       }
       for (int b = 0; b < NBODY; ++b) { /* phase B: one body each; TWO interleaved partial sums (even / odd incidences), combined 0+1 */
-        if (b < NB && W->asleep[b]) continue; /* stays at rest */
+        int na = W->aend[b] - W->astart[b], nbl = W->boff[b + 1] - W->boff[b];
+        if (b < NB && (W->asleep[b] || na + nbl == 0)) continue; /* asleep: stays at rest; untouched: keeps its free velocity */
         v3 Fk[2], Tk[2];
         for (int k = 0; k < 2; ++k) { Fk[k] = V3(0, 0, 0); Tk[k] = V3(0, 0, 0); }
-        int na = W->aend[b] - W->astart[b], nbl = W->boff[b + 1] - W->boff[b];
         v3 xb = b < NB ? W->bx[b] : V3(0, 0, 0);
         for (int e = 0; e < na + nbl; ++e) {
           int i = e < na ? W->astart[b] + e : W->blist[W->boff[b] + (e - na)];

@@ -58,6 +58,7 @@ struct SimSmem {
   int poff[NOWN + 1];
   int scan[SIM_THREADS];
   int ncon, ndropped;
+  unsigned char alist[NB]; int nact;   // bricks phase B has to visit: awake AND touched by at least one contact (ascending)
   unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
   // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
   float4 ca[MAXC];    // contact point w.xyz | bias
@@ -366,27 +367,45 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     }
     if (tid == 0) { M.ndropped = 0; }
     __syncthreads();
-    // 5. broad phase: one thread per owner shape
-    if (tid < n_owner) {
-      int a = tid, k = 0, dropped = 0;
-      if (!(a < NB && a >= nbr)) {
-        v3 ca = ld3(M.sc[a]), aa = ld3(M.sa[a]);
-        float spa = M.spd[a];
-        const bool a_sl = a < NB && (M.sflag[a] & 1);
-        for (int t = 0; t < n_target; ++t) {
-          if (t == a) continue;
-          if (t < NB && t >= nbr) continue;
-          if (a >= NB && t >= NB && t < NB + nrs) continue;   // robot-robot filtered (GS:906)
-          if (a_sl && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)))) continue;   // neither box can move
-          v3 d = vsub(ca, ld3(M.sc[t]));
-          v3 at = ld3(M.sa[t]);
-          float m = margin + spa + M.spd[t];
-          bool hit = fabsf(d.x) <= aa.x + at.x + m && fabsf(d.y) <= aa.y + at.y + m && fabsf(d.z) <= aa.z + at.z + m;
-          if (hit) { if (k < KC) M.cand[a][k++] = (unsigned char)t; else dropped++; }
+    // 5. broad phase: TWO threads per owner shape (thread tid: owner tid & 127, target-range half tid >> 7); the second
+    //    half's hits go to a scratch list (in the idle impulse array) and are appended in target order, so the candidate
+    //    lists -- including what overflows KC -- are the ones a single ascending sweep produces
+    {
+      unsigned char* tmpc = reinterpret_cast<unsigned char*>(&M.cf4[0]);   // [NOWN][KC]
+      int* tmpn = reinterpret_cast<int*>(&M.cb[0]);                         // [NOWN]
+      const int a = tid & 127, half = tid >> 7;
+      if (a < n_owner) {
+        int k = 0, dropped = 0;
+        if (!(a < NB && a >= nbr)) {
+          v3 ca = ld3(M.sc[a]), aa = ld3(M.sa[a]);
+          float spa = M.spd[a];
+          const bool a_sl = a < NB && (M.sflag[a] & 1);
+          const int tmid = n_target >> 1;
+          const int t1 = half ? n_target : tmid;
+          unsigned char* dst = half ? tmpc + a * KC : M.cand[a];
+          for (int t = half ? tmid : 0; t < t1; ++t) {
+            if (t == a) continue;
+            if (t < NB && t >= nbr) continue;
+            if (a >= NB && t >= NB && t < NB + nrs) continue;   // robot-robot filtered (GS:906)
+            if (a_sl && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)))) continue;   // neither box can move
+            v3 d = vsub(ca, ld3(M.sc[t]));
+            v3 at = ld3(M.sa[t]);
+            float m = margin + spa + M.spd[t];
+            bool hit = fabsf(d.x) <= aa.x + at.x + m && fabsf(d.y) <= aa.y + at.y + m && fabsf(d.z) <= aa.z + at.z + m;
+            if (hit) { if (k < KC) dst[k++] = (unsigned char)t; else dropped++; }
+          }
         }
+        if (half) tmpn[a] = k; else M.ncand[a] = k;
+        if (dropped) atomicAdd(&M.ndropped, dropped);
       }
-      M.ncand[a] = k;
-      if (dropped) atomicAdd(&M.ndropped, dropped);
+      __syncthreads();
+      if (tid < n_owner) {
+        int k = M.ncand[tid], dropped = 0;
+        const int n1 = tmpn[tid];
+        for (int i = 0; i < n1; ++i) { if (k < KC) M.cand[tid][k++] = tmpc[tid * KC + i]; else dropped++; }
+        M.ncand[tid] = k;
+        if (dropped) atomicAdd(&M.ndropped, dropped);
+      }
     }
     __syncthreads();
     if (tid < 32) {
@@ -531,6 +550,18 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       M.nb[tid] = (M.aend[tid] - M.astart[tid]) + (o1 - o0);
     }
     __syncthreads();
+    if (tid < 32) {                                            // warp 0: compact the bricks phase B has to visit
+      int base = 0;
+#pragma unroll
+      for (int r = 0; r < (NB + 31) / 32; ++r) {
+        const int b = r * 32 + tid;
+        const bool act = b < NB && !(M.sflag[b] & 1) && M.nb[b] > 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, act);
+        if (act) M.alist[base + __popc(bal & ((1u << tid) - 1u))] = (unsigned char)b;
+        base += __popc(bal);
+      }
+      if (tid == 0) M.nact = base;
+    }
     unsigned ract = 0u;                                        // robot warp: links with at least one contact
     if (tid >= ROBOT_TID0) {
       const int L = tid - ROBOT_TID0;
@@ -588,21 +619,21 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       }
       __syncthreads();
       // phase B: TWO lanes per body, lane k sums incidences e = k (mod 2); partials combined 0+1.
-      // brick warps (all but the last): 72 bricks x 2 lanes = 144 items in ONE pass.
+      // brick warps (all but the last): only bricks that are awake and in contact (alist) x 2 lanes; the others keep
+      // their free velocity (zero when asleep).
       // last warp: the articulation -- only links that HAVE contacts are gathered (their wrenches are zero otherwise, set
       // once per sub-step), and the joint-space update is skipped entirely while the robot touches nothing.
       const bool robot_warp = tid >= ROBOT_TID0;
-      const int n_items = robot_warp ? 2 * __popc(ract) : 2 * NB;
+      const int n_items = robot_warp ? 2 * __popc(ract) : 2 * M.nact;
       const int per_pass = robot_warp ? 32 : ROBOT_TID0;
 #pragma unroll 1
       for (int base = 0; base < n_items; base += per_pass) {
         const int item = base + (robot_warp ? tid - ROBOT_TID0 : tid);
         if (!robot_warp && (item & ~31) >= n_items) continue;   // whole warp beyond the item range
         const bool live = item < n_items;
-        const int body = !robot_warp ? (live ? (item >> 1) : 0) : NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
+        const int body = !robot_warp ? (live ? (int)M.alist[item >> 1] : 0) : NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
         const int k = item & 1;
-        const bool b_sl = body < NB && (M.sflag[body] & 1);       // sleeping bricks stay at rest
-        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = (live && !b_sl) ? na + (M.boff[body + 1] - b0) : 0;
+        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
         const v3 xb = body < NB ? ld3(M.bx[body]) : V3(0.0f, 0.0f, 0.0f);
         v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
         for (int ee = k; ee < ntot; ee += 2) {
@@ -617,7 +648,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         }
         F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
         T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
-        if (k == 0 && live && !b_sl) {
+        if (k == 0 && live) {
           if (body < NB) {
             st3(M.bv[body], vmad(F, M.binvm[body], ld3(M.vfree[body])));
             st3(M.bw[body], vadd(ld3(M.wfree[body]), brick_Iinv_mul(M.sR[body], ld3(M.binvI[body]), T)));
