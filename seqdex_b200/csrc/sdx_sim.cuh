@@ -43,7 +43,7 @@ struct SimSmem {
   unsigned long long mbar;
   float sc[NT][3], sR[NT][9], sh[NT][3], srad[NOWN];
   union {                              // world AABBs + travel bounds live until the narrow phase; the target-side lists after it
-    struct { float sa[NT][3], spd[NT]; };
+    float4 sab[NT];                    // world-AABB half extents .xyz | per-sub-step travel bound .w
     unsigned short blist[MAXC];
   };
   unsigned char sbody[NT];
@@ -351,19 +351,19 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       int t = tid;
       const float* R = M.sR[t];
       v3 hh = ld3(M.sh[t]);
-      st3(M.sa[t], V3(fabsf(R[0]) * hh.x + fabsf(R[1]) * hh.y + fabsf(R[2]) * hh.z,
-                      fabsf(R[3]) * hh.x + fabsf(R[4]) * hh.y + fabsf(R[5]) * hh.z,
-                      fabsf(R[6]) * hh.x + fabsf(R[7]) * hh.y + fabsf(R[8]) * hh.z));
+      const v3 ext = V3(fabsf(R[0]) * hh.x + fabsf(R[1]) * hh.y + fabsf(R[2]) * hh.z,
+                        fabsf(R[3]) * hh.x + fabsf(R[4]) * hh.y + fabsf(R[5]) * hh.z,
+                        fabsf(R[6]) * hh.x + fabsf(R[7]) * hh.y + fabsf(R[8]) * hh.z);
       int bd = M.sbody[t];
       v3 dc = vsub(ld3(M.sc[t]), ld3(M.bx[bd]));
       float reach = sqrtf(vdot(dc, dc)) + M.srad[t];
       v3 bv = ld3(M.bv[bd]), bw = ld3(M.bw[bd]);
-      M.spd[t] = h * (sqrtf(vdot(bv, bv)) + sqrtf(vdot(bw, bw)) * reach);
+      M.sab[t] = make_float4(ext.x, ext.y, ext.z, h * (sqrtf(vdot(bv, bv)) + sqrtf(vdot(bw, bw)) * reach));
     }
     for (int s2 = tid; s2 < nst; s2 += SIM_THREADS) {          // statics: AABB = the box itself, no travel (rewritten each sub-step: aliased storage)
       int t = NB + nrs + s2;
-      st3(M.sa[t], ld3(M.sh[t]));
-      M.spd[t] = 0.0f;
+      const v3 hs = ld3(M.sh[t]);
+      M.sab[t] = make_float4(hs.x, hs.y, hs.z, 0.0f);
     }
     if (tid == 0) { M.ndropped = 0; }
     __syncthreads();
@@ -377,23 +377,30 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       if (a < n_owner) {
         int k = 0, dropped = 0;
         if (!(a < NB && a >= nbr)) {
-          v3 ca = ld3(M.sc[a]), aa = ld3(M.sa[a]);
-          float spa = M.spd[a];
+          const v3 ca = ld3(M.sc[a]);
+          const float4 A4 = M.sab[a];
           const bool a_sl = a < NB && (M.sflag[a] & 1);
           const int tmid = n_target >> 1;
-          const int t1 = half ? n_target : tmid;
+          const int tlo = half ? tmid : 0, thi = half ? n_target : tmid;
           unsigned char* dst = half ? tmpc + a * KC : M.cand[a];
-          for (int t = half ? tmid : 0; t < t1; ++t) {
-            if (t == a) continue;
-            if (t < NB && t >= nbr) continue;
-            if (a >= NB && t >= NB && t < NB + nrs) continue;   // robot-robot filtered (GS:906)
-            if (a_sl && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)))) continue;   // neither box can move
-            v3 d = vsub(ca, ld3(M.sc[t]));
-            v3 at = ld3(M.sa[t]);
-            float m = margin + spa + M.spd[t];
-            bool hit = fabsf(d.x) <= aa.x + at.x + m && fabsf(d.y) <= aa.y + at.y + m && fabsf(d.z) <= aa.z + at.z + m;
+          auto test = [&](int t) {
+            const v3 d = vsub(ca, ld3(M.sc[t]));
+            const float4 T4 = M.sab[t];
+            const float m = margin + A4.w + T4.w;
+            const bool hit = fabsf(d.x) <= A4.x + T4.x + m && fabsf(d.y) <= A4.y + T4.y + m && fabsf(d.z) <= A4.z + T4.z + m;
             if (hit) { if (k < KC) dst[k++] = (unsigned char)t; else dropped++; }
+          };
+          // the target index space is bricks [0, nbr) | robot shapes [NB, NB+nrs) | statics [NB+nrs, n_target): one loop per
+          // class with the class-level filters hoisted (same ascending order as one sweep over t)
+          for (int t = max(tlo, 0); t < min(thi, nbr); ++t) {
+            if (t == a) continue;
+            if (a_sl && (M.sflag[t] & 1)) continue;              // neither box can move
+            test(t);
           }
+          if (a < NB)                                            // robot-robot pairs are filtered (GS:906)
+            for (int t = max(tlo, NB); t < min(thi, NB + nrs); ++t) test(t);
+          if (!a_sl)                                             // a sleeping brick against a static: neither box can move
+            for (int t = max(tlo, NB + nrs); t < thi; ++t) test(t);
         }
         if (half) tmpn[a] = k; else M.ncand[a] = k;
         if (dropped) atomicAdd(&M.ndropped, dropped);
@@ -428,7 +435,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       for (int i = p0; i < p1; ++i) {
         while (M.poff[a + 1] <= i) ++a;
         int t = M.cand[a][i - M.poff[a]];
-        float m = margin + M.spd[a] + M.spd[t];
+        float m = margin + M.sab[a].w + M.sab[t].w;
         unsigned short mk = 0;
         PairGeom G;
         if (pair_geom(M, a, t, m, G, t >= NB + nrs)) {
@@ -479,7 +486,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         int lo = 0, hi = n_owner - 1;                  // owner a with poff[a] <= i < poff[a+1]
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (M.poff[mid] <= i) lo = mid; else hi = mid - 1; }
         const int a = lo, t = M.cand[a][i - M.poff[a]];
-        float m = margin + M.spd[a] + M.spd[t];
+        float m = margin + M.sab[a].w + M.sab[t].w;
         PairGeom G;
         pair_geom(M, a, t, m, G, t >= NB + nrs);
         float depth;
