@@ -168,7 +168,8 @@ def main():
     ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
                     help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
                          "rollout: VecTask.step only with U(-1,1) actions")
-    ap.add_argument("--minibatch", type=int, default=16384)
+    ap.add_argument("--minibatch", type=int, default=32768,
+                    help="PPO minibatch; the yaml's 4 is a 4-env smoke value (SURVEY.md section 7): default = batch/4 at 16384 envs x horizon 8")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
