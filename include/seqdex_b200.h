@@ -148,6 +148,9 @@ int sdx_set_static_rows(sdx_env_t* env, const float* rows_host);
 int sdx_set_heap_bank_dev(sdx_env_t* env, const float* bank_dev, int per_type);
 /* device pointers of the grasp terminal-state rings reset_idx fills (GS:1399-1445): hand [8][11024][23][2], obj [8][11024][13], index [8] */
 int sdx_grasp_bank(sdx_env_t* env, void** hand_dev, void** obj_dev, void** index_dev);
+/* t-value training data (GS:1402-1438 under save_hdf5; read back by TVT:132-168): capacity > 0 allocates two device rings
+ * succ/fail [capacity][4] f32 + counts i64[2] (rows ever written) and records from the next reset on; 0 stops recording */
+int sdx_tvalue_dataset(sdx_env_t* env, int capacity, void** succ_dev, void** fail_dev, void** counts_dev);
 int sdx_aux(sdx_env_t* env, void** qcam_dev, void** finger_dist_dev);
 int sdx_scene_size(void);
 int sdx_sim_smem_bytes(void);

@@ -144,9 +144,18 @@ class OracleEnv:
                              self.slp.ctypes.data_as(ctypes.c_void_p))
         self.ws_cur ^= self.scene.c.substeps & 1
 
+    def enable_tvalue_dataset(self, cap):
+        self.tvd_cap = int(cap)
+        self.tvd_succ = np.zeros((cap, 4), np.float32)
+        self.tvd_fail = np.zeros((cap, 4), np.float32)
+        self.tvd_counts = np.zeros(2, np.int64)
+
     def pre_physics(self, actions):
         if self.reset.any():
             assert self.bank is not None, "reset needs a heap bank (GS:412-413)"
+            if getattr(self, "tvd_cap", 0) and self.total_steps > 0:
+                self.L.sdxo_tv_dataset(self.S, self.n, lp(self.reset), fp(self.brick), fp(self.finger_dist), fp(self.tvalue),
+                                       fp(self.states), fp(self.tvd_succ), fp(self.tvd_fail), lp(self.tvd_counts), self.tvd_cap)
             self.L.sdxo_reset(self.S, self.n, ctypes.c_uint64(self.seed), fp(self.bank), self.per_type, fp(self.brick),
                               fp(self.dof), fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.successes),
                               ip(self.episode), ip(self.wsn), self.slp.ctypes.data_as(ctypes.c_void_p), int(self.total_steps > 0), fp(self.finger_dist), fp(self.tvalue),

@@ -667,6 +667,13 @@ void sdxo_simulate(const sdx_scene_t* S, int n, float* brick, float* dof, float*
   for (int t = 1; t < nt; ++t) pthread_join(th[t], 0);
 }
 
+/* t-value training data (GS:1402-1438, save_hdf5): every env that resets (after the first step) contributes its
+ * camera-frame target quaternion -- states[177:181] of the newest frame, the gate's input (GS:1200) -- to the SUCCESS set
+ * when the grasp is banked (target y < 0, finger_dist < 0.6, tvalue > 0.8) and to the FAILURE set otherwise; env order,
+ * rings of `cap` rows, counts[0/1] = rows ever written (the reference's success_v_count / failure_v_count). */
+void sdxo_tv_dataset(const sdx_scene_t* S, int n, const int64_t* reset, const float* brick, const float* finger_dist,
+                     const float* tvalue, const float* states, float* succ, float* fail, int64_t* counts, int cap);
+
 /* FK-only refresh of link rows / jacobian (used after resets and at creation) */
 void sdxo_refresh_links(const sdx_scene_t* S, int n, const float* dof, float* link, float* jac7) {
   for (int e = 0; e < n; ++e) {
@@ -961,6 +968,19 @@ void sdxo_gae(const float* rewards, const float* values, const float* dones, con
       adv[(size_t)t * n + e] = lastgaelam;
       returns[(size_t)t * n + e] = lastgaelam + values[(size_t)t * n + e];
     }
+  }
+}
+
+void sdxo_tv_dataset(const sdx_scene_t* S, int n, const int64_t* reset, const float* brick, const float* finger_dist,
+                     const float* tvalue, const float* states, float* succ, float* fail, int64_t* counts, int cap) {
+  for (int e = 0; e < n; ++e) {
+    if (!reset[e]) continue;
+    float row[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), row);
+    int ok = row[1] < 0.0f && finger_dist[e] < 0.6f && tvalue[e] > 0.8f;
+    float* dst = (ok ? succ : fail) + 4 * (size_t)(counts[ok ? 0 : 1] % cap);
+    for (int k = 0; k < 4; ++k) dst[k] = states[(size_t)e * 3 * STATE_FRAME + 177 + k];
+    counts[ok ? 0 : 1] += 1;
   }
 }
 

@@ -32,6 +32,7 @@ struct sdx_env {
   void* buf[SDX_T_COUNT] = {nullptr};
   float *qcam = nullptr, *finger_dist = nullptr, *static_rows = nullptr, *bank = nullptr, *tvw = nullptr;
   float *gb_hand = nullptr, *gb_obj = nullptr; int* gb_index = nullptr;
+  float *tvd_succ = nullptr, *tvd_fail = nullptr; long long* tvd_counts = nullptr; int tvd_cap = 0;   // t-value dataset rings
   int* red_count = nullptr; float* red_sum = nullptr;
   float *stage_obs = nullptr, *stage_states = nullptr, *stage_actions = nullptr;
   int per_type = 0;
@@ -114,6 +115,7 @@ extern "C" void sdx_destroy(sdx_env_t* E) {
   if (!E) return;
   cudaSetDevice(E->device);
   for (int k = 0; k < SDX_T_COUNT; ++k) cudaFree(E->buf[k]);
+  cudaFree(E->tvd_succ); cudaFree(E->tvd_fail); cudaFree(E->tvd_counts);
   cudaFree(E->scene); cudaFree(E->qcam); cudaFree(E->finger_dist); cudaFree(E->static_rows); cudaFree(E->bank); cudaFree(E->tvw);
   cudaFree(E->gb_hand); cudaFree(E->gb_obj); cudaFree(E->gb_index); cudaFree(E->red_count); cudaFree(E->red_sum);
   cudaFree(E->stage_obs); cudaFree(E->stage_states); cudaFree(E->stage_actions);
@@ -250,6 +252,11 @@ extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
     k_bank_terminal<<<8, 256, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), I64(SDX_T_RESET), E->finger_dist,
                                               F(SDX_T_TVALUE), E->gb_hand, E->gb_obj, E->gb_index);
     E->launches++;
+    if (E->tvd_cap > 0) {
+      k_tv_dataset<<<1, 1024, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), I64(SDX_T_RESET), E->finger_dist, F(SDX_T_TVALUE), E->qcam,
+                                              E->tvd_succ, E->tvd_fail, E->tvd_counts, E->tvd_cap);
+      E->launches++;
+    }
   }
   k_reset<<<n, 128, 0, E->stream>>>(E->scene, n, E->seed, E->bank, E->per_type, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_TARGET_INIT),
                                     I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), I32(SDX_T_EPISODE), I32(SDX_T_WSN),
@@ -338,6 +345,23 @@ extern "C" int sdx_clamped_copy(sdx_env_t* E, int kind, float* dst_dev, float li
 /* grasp terminal-state banks: device pointers for export */
 extern "C" int sdx_grasp_bank(sdx_env_t* E, void** hand_dev, void** obj_dev, void** index_dev) {
   *hand_dev = E->gb_hand; *obj_dev = E->gb_obj; *index_dev = E->gb_index;
+  return 0;
+}
+/* t-value training data rings (GS:1402-1438 save_hdf5 / TVT:132-168): capacity > 0 (re)allocates and switches recording on */
+extern "C" int sdx_tvalue_dataset(sdx_env_t* E, int capacity, void** succ_dev, void** fail_dev, void** counts_dev) {
+  CK(cudaSetDevice(E->device));
+  if (capacity > 0 && capacity != E->tvd_cap) {
+    CK(cudaStreamSynchronize(E->stream));
+    cudaFree(E->tvd_succ); cudaFree(E->tvd_fail); cudaFree(E->tvd_counts);
+    CK(cudaMalloc(&E->tvd_succ, (size_t)capacity * 16)); CK(cudaMemset(E->tvd_succ, 0, (size_t)capacity * 16));
+    CK(cudaMalloc(&E->tvd_fail, (size_t)capacity * 16)); CK(cudaMemset(E->tvd_fail, 0, (size_t)capacity * 16));
+    CK(cudaMalloc(&E->tvd_counts, 16)); CK(cudaMemset(E->tvd_counts, 0, 16));
+    E->tvd_cap = capacity;
+  }
+  if (capacity == 0) E->tvd_cap = 0;   // recording off (buffers kept until destroy)
+  if (succ_dev) *succ_dev = E->tvd_succ;
+  if (fail_dev) *fail_dev = E->tvd_fail;
+  if (counts_dev) *counts_dev = E->tvd_counts;
   return 0;
 }
 extern "C" int sdx_aux(sdx_env_t* E, void** qcam_dev, void** finger_dist_dev) { *qcam_dev = E->qcam; *finger_dist_dev = E->finger_dist; return 0; }

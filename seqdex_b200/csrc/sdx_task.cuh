@@ -132,6 +132,45 @@ k_bank_terminal(const sdx_scene_t* __restrict__ S, int n, const float* __restric
   if (tid == 0) gb_index[ty] = (base + total) % 5001;
 }
 
+// t-value training data (GS:1402-1438 with save_hdf5): every resetting env appends its gate input (camera-frame target
+// quaternion) to the success ring when the grasp is banked, to the failure ring otherwise -- in ENV ORDER (block scan).
+__global__ void __launch_bounds__(1024)
+k_tv_dataset(const sdx_scene_t* __restrict__ S, int n, const float* __restrict__ brick, const int64_t* __restrict__ reset,
+             const float* __restrict__ finger_dist, const float* __restrict__ tvalue, const float* __restrict__ qcam,
+             float* __restrict__ succ, float* __restrict__ fail, long long* __restrict__ counts, int cap) {
+  __shared__ int cs[1024], cf[1024];
+  __shared__ long long base[2], endc[2];
+  const int tid = threadIdx.x, per = (n + 1023) / 1024;
+  const int i0 = tid * per, i1 = min(n, i0 + per);
+  int ns = 0, nf = 0;
+  for (int e = i0; e < i1; ++e) {
+    if (!reset[e]) continue;
+    float row[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), row);
+    if (row[1] < 0.0f && finger_dist[e] < 0.6f && tvalue[e] > 0.8f) ns++; else nf++;
+  }
+  cs[tid] = ns; cf[tid] = nf;
+  __syncthreads();
+  if (tid == 0) {
+    int os = 0, of = 0;
+    for (int t = 0; t < 1024; ++t) { int a = cs[t], b = cf[t]; cs[t] = os; cf[t] = of; os += a; of += b; }
+    base[0] = counts[0]; base[1] = counts[1];
+    counts[0] = endc[0] = base[0] + os; counts[1] = endc[1] = base[1] + of;
+  }
+  __syncthreads();
+  long long ks = base[0] + cs[tid], kf = base[1] + cf[tid];
+  for (int e = i0; e < i1; ++e) {
+    if (!reset[e]) continue;
+    float row[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), row);
+    const bool ok = row[1] < 0.0f && finger_dist[e] < 0.6f && tvalue[e] > 0.8f;
+    const long long idx = ok ? ks++ : kf++;
+    if (idx < endc[ok ? 0 : 1] - cap) continue;            // overwritten by a later row of this very call: the sequential loop's last writer wins
+    float* dst = (ok ? succ : fail) + 4 * (size_t)(idx % cap);
+    for (int k = 0; k < 4; ++k) dst[k] = qcam[4 * e + k];
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k_reset(const sdx_scene_t* __restrict__ S, int n, uint64_t seed, const float* __restrict__ bank, int per_type,
         float* __restrict__ brick, float* __restrict__ dof, float* __restrict__ target_init, int64_t* __restrict__ progress,

@@ -116,6 +116,30 @@ class SdxEnv:
     def launch_count(self):
         return int(self.L.sdx_launch_count(self.h))
 
+    def _view(self, ptr, shape, typestr="<f4"):
+        with torch.cuda.device(self.device):
+            return torch.as_tensor(_DevView(ptr, shape, typestr), device=self.device)
+
+    def grasp_bank(self):
+        """the grasp terminal-state rings reset_idx fills (GS:1399-1445): (hand [8,11024,23,2], obj [8,11024,13], index [8])"""
+        h, o, i = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self.L.sdx_grasp_bank(self.h, ctypes.byref(h), ctypes.byref(o), ctypes.byref(i)))
+        return self._view(h.value, (8, 11024, 23, 2)), self._view(o.value, (8, 11024, 13)), self._view(i.value, (8,), "<i4")
+
+    def enable_tvalue_dataset(self, capacity=65536):
+        """record the t-value training rows on the device (the reference's save_hdf5 branch, GS:1402-1438)"""
+        _lib.check(self.L.sdx_tvalue_dataset(self.h, int(capacity), None, None, None))
+        self._tvd_cap = int(capacity)
+
+    def tvalue_dataset(self):
+        """(success [ns,4], failure [nf,4], counts [2] i64): rows recorded so far (ring order once a ring has wrapped)"""
+        s, f, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self.L.sdx_tvalue_dataset(self.h, self._tvd_cap, ctypes.byref(s), ctypes.byref(f), ctypes.byref(c)))
+        counts = self._view(c.value, (2,), "<i8")
+        torch.cuda.synchronize(self.device)
+        ns, nf = (min(int(x), self._tvd_cap) for x in counts.tolist())
+        return self._view(s.value, (self._tvd_cap, 4))[:ns], self._view(f.value, (self._tvd_cap, 4))[:nf], counts
+
     def brick_roots(self):
         """[N, 72, 13] Isaac-Gym root rows of the free bricks (actors 9..80 of the root tensor)."""
         self.refresh("ROOT")

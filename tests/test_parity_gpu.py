@@ -122,6 +122,40 @@ def test_sleeping_and_waking_bit_exact(oracle_lib):
     assert woken > 0, "nothing was ever woken: the test does not cover waking"
 
 
+def test_tvalue_dataset_and_grasp_bank_bit_exact(scene, oracle_lib, tmp_path):
+    """the device rings of SURVEY 8f.1 (t-value training rows, grasp terminal states) against the oracle's sequential
+    loops, and their export in the reference's pickle layout"""
+    from seqdex_b200 import bank_io
+    n = 64
+    g, o = _mk(scene, oracle_lib, n, jitter=False)
+    bank = lattice_bank(scene, 4)
+    g.set_heap_bank(bank); o.set_heap_bank(bank)
+    w = oracle_lib.default_tvalue_weights(1).copy()
+    w[-2:] = [-4.0, 4.0]                                   # bias the gate open so that SOME grasps bank (sigmoid(z1) > 0.8)
+    g.set_tvalue_weights(w); o.tv = w
+    g.enable_tvalue_dataset(32); o.enable_tvalue_dataset(32)   # small rings: they wrap
+    rng = np.random.default_rng(9)
+    for t in range(160):
+        a = rng.uniform(-1.2, 1.2, size=(n, 23)).astype(np.float32)
+        g.step(torch.from_numpy(a).cuda()); o.step(a)
+    gs, gf, gc = g.tvalue_dataset()
+    _cmp("dataset counts", gc, o.tvd_counts)
+    assert o.tvd_counts.sum() >= n and o.tvd_counts.min() >= 0
+    _cmp("failure rows", gf, o.tvd_fail[: gf.shape[0]])
+    _cmp("success rows", gs, o.tvd_succ[: gs.shape[0]])
+    hand, obj, idx = g.grasp_bank()
+    _cmp("grasp bank index", idx, o.gb_index)
+    _cmp("grasp bank hand", hand, o.gb_hand)
+    _cmp("grasp bank obj", obj, o.gb_obj)
+    bank_io.save_grasp_bank(g, tmp_path / "hand.pkl", tmp_path / "obj.pkl")
+    import pickle
+    with open(tmp_path / "hand.pkl", "rb") as f:
+        hl = pickle.load(f)
+    with open(tmp_path / "obj.pkl", "rb") as f:
+        ol = pickle.load(f)
+    assert len(hl) == len(ol) == 8 and tuple(hl[0].shape) == (11024, 23, 2) and tuple(ol[0].shape) == (11024, 1, 13)   # GS:390-395
+
+
 def test_full_step_bit_exact(scene, oracle_lib):
     """VecTask.step semantics end to end: reset_idx -> pre_physics -> simulate -> post_physics, 160 steps
     (crosses an episode boundary at progress 149, so resets, banking and the scripted lift are covered)."""
