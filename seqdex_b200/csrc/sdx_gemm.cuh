@@ -70,6 +70,31 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the leader CTA (rank 0) issues one M = 256 MMA over both SMs' shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER's mbarrier (peer bit of the barrier address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+// MMA-completion arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+               ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
 // ELU without branches or denormal fix-ups: exp only ever sees min(a, 0), so ex2.approx.ftz is exact enough for a bf16 result
 __device__ __forceinline__ float elu_fast(float a) {
   float e;
@@ -88,10 +113,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 }  // namespace gemm
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BROWS = BN>
 struct GemmSmem {
   __nv_bfloat16 a[STAGES][GEMM_BM * GEMM_BK];
-  __nv_bfloat16 b[STAGES][BN * GEMM_BK];
+  __nv_bfloat16 b[STAGES][BROWS * GEMM_BK];   // BROWS = BN, or BN / 2 when a CTA pair shares the B tile
   unsigned char stage_rm[8 * 4096];      // epilogue staging, row-major box per warp: [32 rows][64 cols], 128B-swizzled
   unsigned char stage_t[8 * 4096];       // epilogue staging, transposed box per warp: [64 n][32 m], 64B-swizzled
   float bias[8][BN / 2];                 // per-warp copy of its bias slices (MODE 0)
@@ -99,33 +124,46 @@ struct GemmSmem {
   uint32_t tmem_base;
 };
 
-template <int BN, int STAGES, int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
-          const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapH, const GemmArgs g) {
-  // PERSISTENT: each CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA ring and the MMA issuer run ahead
-  // into the next tile while the epilogue warps drain the previous accumulator (two TMEM accumulators of BN columns).
+extern __shared__ unsigned char gsm_raw[];
+
+// PERSISTENT: each CTA (CTA2: each CTA PAIR) walks tiles t = first, first + stride, ...  The TMA ring and the MMA issuer run
+// ahead into the next tile while the epilogue warps drain the previous accumulator (two TMEM accumulators of BN columns).
+// CTA2: a cluster of two CTAs owns a 256 x BN tile.  Each CTA loads its own 128 rows of A and HALF of the B tile; the leader
+// issues tcgen05.mma.cta_group::2 (M = 256), which reads both halves of B across the pair -- per output element each SM
+// pulls half as many operand bytes out of L2 (the bound of the single-CTA kernel); each CTA drains its own 128 TMEM lanes.
+template <int BN, int STAGES, int MODE, bool CTA2>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& mapA, const CUtensorMap& mapB, const CUtensorMap& mapO, const CUtensorMap& mapT,
+                                          const CUtensorMap& mapH, const GemmArgs& g) {
   using namespace gemm;
-  extern __shared__ unsigned char gsm_raw[];
+  constexpr int BROWS = CTA2 ? BN / 2 : BN;
+  constexpr int TILE_M = CTA2 ? 2 * GEMM_BM : GEMM_BM;
   // 128B-swizzled TMA/UMMA tiles need 1024 B alignment: align by hand (the launcher over-allocates 1 KB)
-  auto& S = *reinterpret_cast<GemmSmem<BN, STAGES>*>(gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u));
+  auto& S = *reinterpret_cast<GemmSmem<BN, STAGES, BROWS>*>(gsm_raw + ((1024u - (smem_u32(gsm_raw) & 1023u)) & 1023u));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (g.N + BN - 1) / BN, tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;           // 0 = leader
+  const int first = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, stride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tiles_n = (g.N + BN - 1) / BN, tiles_m = (g.M + TILE_M - 1) / TILE_M;
   const int total_kb = (g.K + GEMM_BK - 1) / GEMM_BK;
   const int splits = (total_kb + g.kblocks_per_split - 1) / g.kblocks_per_split;
   const int n_tiles = tiles_n * tiles_m * splits;
-  constexpr uint32_t STAGE_BYTES = (GEMM_BM + BN) * GEMM_BK * 2;
-  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+  constexpr uint32_t STAGE_BYTES = (CTA2 ? 2u : 1u) * (GEMM_BM + BROWS) * GEMM_BK * 2;      // bytes landing per stage (both CTAs)
+  constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&S.tmem_full[a], 1); mbar_init(&S.tmem_empty[a], CTA2 ? 16 : 8); }
     for (int a = 0; a < 8; ++a) mbar_init(&S.hbar[a], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (CTA2) { __syncthreads(); cluster_sync_all(); }             // barriers of both CTAs exist before anything remote touches them
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(2 * BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "n"(2 * BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -135,24 +173,30 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
   if (warp == 0) {
     if (lane == 0) {
       uint32_t kbg = 0;                                  // k-block counter across all tiles of this CTA (stage ring position)
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = first; t < n_tiles; t += stride) {
         const int nx = t % tiles_n, my = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
-        const int m0 = my * GEMM_BM, n0 = nx * BN, kb0 = z * g.kblocks_per_split;
+        const int m0 = my * TILE_M + (int)rank * GEMM_BM, n0 = nx * BN + (int)rank * BROWS, kb0 = z * g.kblocks_per_split;
         const int nkb = min(g.kblocks_per_split, total_kb - kb0);
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (kbg / STAGES) & 1;
           mbar_wait(&S.empty[s], ph ^ 1);
-          mbar_expect_tx(&S.full[s], STAGE_BYTES);
-          tma_load_2d(&mapA, S.a[s], &S.full[s], (kb0 + kb) * GEMM_BK, m0);
-          tma_load_2d(&mapB, S.b[s], &S.full[s], (kb0 + kb) * GEMM_BK, n0);
+          if (CTA2) {                                      // both CTAs load; the bytes of both are expected on the leader's barrier
+            if (rank == 0) mbar_expect_tx(&S.full[s], STAGE_BYTES);
+            tma_load_2d_pair(&mapA, S.a[s], &S.full[s], (kb0 + kb) * GEMM_BK, m0);
+            tma_load_2d_pair(&mapB, S.b[s], &S.full[s], (kb0 + kb) * GEMM_BK, n0);
+          } else {
+            mbar_expect_tx(&S.full[s], STAGE_BYTES);
+            tma_load_2d(&mapA, S.a[s], &S.full[s], (kb0 + kb) * GEMM_BK, m0);
+            tma_load_2d(&mapB, S.b[s], &S.full[s], (kb0 + kb) * GEMM_BK, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t kbg = 0, it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+      for (int t = first; t < n_tiles; t += stride, ++it) {
         const int z = t / (tiles_n * tiles_m), kb0 = z * g.kblocks_per_split;
         const int nkb = min(g.kblocks_per_split, total_kb - kb0);
         const uint32_t acc = it & 1;
@@ -166,10 +210,11 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
           const uint64_t da = umma_desc(S.a[s]), db = umma_desc(S.b[s]);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k)   // +32 B (= 2 x 16 B) along K inside the 128 B swizzle row per UMMA_K
-            umma_f16(tmem + acc * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&S.empty[s]);
+            if (CTA2) umma_f16_pair(tmem + acc * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(tmem + acc * BN, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+          if (CTA2) umma_commit_pair(&S.empty[s]); else umma_commit(&S.empty[s]);
         }
-        umma_commit(&S.tmem_full[acc]);
+        if (CTA2) umma_commit_pair(&S.tmem_full[acc]); else umma_commit(&S.tmem_full[acc]);
       }
     }
   } else {
@@ -180,9 +225,9 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     unsigned char* const tb = S.stage_t + ew * 4096;       // [64 n][32 m] box, 64B-swizzled
     uint32_t it = 0;
     [[maybe_unused]] uint32_t hph = 0;                     // uses of this warp's h barrier so far
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    for (int t = first; t < n_tiles; t += stride, ++it) {
       const int nx = t % tiles_n, my = (t / tiles_n) % tiles_m;
-      const int m0 = my * GEMM_BM, n0 = nx * BN;
+      const int m0 = my * TILE_M + (int)rank * GEMM_BM, n0 = nx * BN;
       const uint32_t acc = it & 1;
       if (MODE == 0) {                                     // this warp's copy of its bias slices
 #pragma unroll
@@ -297,14 +342,33 @@ k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
       // this warp has read its TMEM lanes of the accumulator: hand it back to the MMA issuer
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.tmem_empty[acc])) : "memory");
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(&S.tmem_empty[acc], 0u);   // the leader issues the MMAs of both CTAs
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&S.tmem_empty[acc])) : "memory");
+      }
     }
     if ((MODE == 0 || MODE == 1) && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CTA2) cluster_sync_all();                                  // the peer may still be reading this CTA's half of B / signalling its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
   }
+}
+
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tn(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
+          const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapH, const GemmArgs g) {
+  gemm_body<BN, STAGES, MODE, false>(mapA, mapB, mapO, mapT, mapH, g);
+}
+// CTA-pair launch: grid = 2 x pairs, cluster (2,1,1)
+template <int BN, int STAGES, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_tn2(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
+           const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapH, const GemmArgs g) {
+  gemm_body<BN, STAGES, MODE, true>(mapA, mapB, mapO, mapT, mapH, g);
 }

@@ -49,7 +49,8 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t col
 #define GEMM_BN 128
 #define GEMM_STAGES 4   /* 4 x 32 KB TMA stages + 64 KB epilogue staging: one persistent CTA per SM */
 typedef GemmSmem<GEMM_BN, GEMM_STAGES> GSm;
-typedef GemmSmem<256, 3> GSmW;   // wide tiles: 128 x 256, 3 x 48 KB stages + 64 KB staging (higher flop/byte against the L2 bound)
+typedef GemmSmem<256, 3> GSmW;
+typedef GemmSmem<256, 4, 128> GSmP;   // CTA pair: 256 x 256 tile per pair, each CTA stages A 128 x 64 + half of B 128 x 64 per stage   // wide tiles: 128 x 256, 3 x 48 KB stages + 64 KB staging (higher flop/byte against the L2 bound)
 static bool g_attr_set = false;
 static int set_attrs() {
   if (g_attr_set) return 0;
@@ -61,6 +62,8 @@ static int set_attrs() {
   PCK(cudaFuncSetAttribute(k_gemm_tn<GEMM_BN, GEMM_STAGES, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
   PCK(cudaFuncSetAttribute(k_gemm_tn<256, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmW) + 1024));
   PCK(cudaFuncSetAttribute(k_gemm_tn<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmW) + 1024));
+  PCK(cudaFuncSetAttribute(k_gemm_tn2<256, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmP) + 1024));
+  PCK(cudaFuncSetAttribute(k_gemm_tn2<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmP) + 1024));
   g_attr_set = true;
   return 0;
 }
@@ -76,10 +79,14 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
   static int wide_ok = -1;
   if (wide_ok < 0) { const char* e = getenv("SDX_GEMM_WIDE"); wide_ok = e ? atoi(e) : 1; }
   // 128 x 256 tiles for the large bf16-output GEMMs: twice the flops per byte pulled from L2 into the SM
-  const bool wide = wide_ok && mode == 0 && N >= 256 && (long long)M * N >= (long long)GEMM_BM * 256 * 148;
-  const int BNsel = wide ? 256 : GEMM_BN;
+  static int pair_ok = -1;
+  if (pair_ok < 0) { const char* e = getenv("SDX_GEMM_PAIR"); pair_ok = e ? atoi(e) : 1; }
+  // CTA pairs (cta_group::2, 256 x 256 tile per pair) for the large bf16-output GEMMs: half the operand bytes per SM
+  const bool pair = pair_ok && ((mode == 0 && N >= 256) || (mode == 1 && N >= 1024)) && (long long)M * N >= (long long)256 * 256 * 74;
+  const bool wide = !pair && wide_ok && mode == 0 && N >= 256 && (long long)M * N >= (long long)GEMM_BM * 256 * 148;
+  const int BNsel = (wide || pair) ? 256 : GEMM_BN;
   if (make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1;
-  if (make_map(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BNsel)) return -1;
+  if (make_map(&mb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, pair ? 128 : BNsel)) return -1;
   mo = ma; mt = ma; mh = ma;   // placeholders when the mode has no bf16 output / no h input
   if (mode == 0 || mode == 1) {
     if (!out || (ldo % 8) || (out_t && (ldt % 8))) { sdx_set_error("sdx_gemm_bf16_tn: bf16 outputs need ld % 8 == 0"); return -1; }
@@ -99,13 +106,19 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
   splits = (total_kb + g.kblocks_per_split - 1) / g.kblocks_per_split;
   g.bias = bias; g.h = (const __nv_bfloat16*)h; g.ldh = ldh; g.out = (__nv_bfloat16*)out; g.ldo = ldo;
   g.out_t = (__nv_bfloat16*)out_t; g.ldt = ldt; g.outf = outf; g.ldf = ldf;
-  int n_tiles = ((N + BNsel - 1) / BNsel) * ((M + GEMM_BM - 1) / GEMM_BM) * splits;
+  const int tile_m = pair ? 2 * GEMM_BM : GEMM_BM;
+  int n_tiles = ((N + BNsel - 1) / BNsel) * ((M + tile_m - 1) / tile_m) * splits;
   static int n_sm = 0;
   if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   dim3 grid(n_tiles < n_sm ? n_tiles : n_sm);   // persistent: one CTA per SM walks the tiles
   size_t smem = sizeof(GSm) + 1024;
   cudaStream_t st = (cudaStream_t)stream;
-  if (wide) {
+  if (pair) {
+    const size_t smp = sizeof(GSmP) + 1024;
+    const int pairs = n_tiles < n_sm / 2 ? n_tiles : n_sm / 2;
+    if (mode == 0) k_gemm_tn2<256, 4, 0><<<2 * pairs, GEMM_THREADS, smp, st>>>(ma, mb, mo, mt, mh, g);
+    else k_gemm_tn2<256, 4, 1><<<2 * pairs, GEMM_THREADS, smp, st>>>(ma, mb, mo, mt, mh, g);
+  } else if (wide) {
     const size_t smw = sizeof(GSmW) + 1024;
     if (mode == 0) k_gemm_tn<256, 3, 0><<<grid, GEMM_THREADS, smw, st>>>(ma, mb, mo, mt, mh, g);
     else k_gemm_tn<256, 3, 1><<<grid, GEMM_THREADS, smw, st>>>(ma, mb, mo, mt, mh, g);
