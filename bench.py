@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_ENV_STEP = 15956   # algorithmic HBM bytes / env-step (fp32 rollout)
 # dram__bytes_read.sum + dram__bytes_write.sum of k_simulate per env, from the committed ncu --set full capture
 # (profiles/r01_ncu_k_simulate_v6.txt: 47.85 MB + 33.69 MB over 4096 envs; includes the warm-start impulse cache)
-NCU_TRAFFIC_BYTES_PER_ENV = (47.854848e6 + 33.688832e6) / 4096
+NCU_TRAFFIC_BYTES_PER_ENV = (124.820480e6 + 154.421504e6) / 16384   # dram read + write of ONE k_simulate launch at 16 384 envs
 
 
 def measured_peaks():
@@ -326,7 +326,7 @@ def main():
             "ppo": ppo_info,
             "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": NCU_TRAFFIC_BYTES_PER_ENV * n,
-                         "traffic_source": "ncu --set full, profiles/r01_ncu_k_simulate_v6.txt (per env x envs per launch)",
+                         "traffic_source": "ncu --set full at 16384 envs, profiles/r01_ncu_k_simulate_v9_16384envs.txt (scaled by envs per launch)",
                          "ms_per_launch": sim_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
                          "note": "state-streaming bound is loose: the kernel is fp32-ALU / shared-memory bound (DESIGN.md section 6)"},
