@@ -184,6 +184,9 @@ int sdx_mlp_convert_batch(sdx_mlp_t* m, const float* x_dev, int B, const float* 
 int sdx_mlp_forward_pre(sdx_mlp_t* m, const void* xb_bf16, const void* xt_bf16, int B, int row0, int M, int train, void* stream);
 int sdx_mlp_backward(sdx_mlp_t* m, const float* dout_dev, int M, void* stream);
 int sdx_mlp_adam(sdx_mlp_t* m, float lr, float b1, float b2, float eps, float max_norm, void* stream);   /* RGC:1102, 1866-1872 */
+/* Adam step counter of the MLP's optimiser (torch.optim.Adam state['step'], saved in rl_games checkpoints under 'optimizer',
+ * RGC:1913-1933): set < 0 reads it, set >= 0 overwrites it (restore) */
+long long sdx_mlp_adam_step(sdx_mlp_t* m, long long set);
 long long sdx_ppo_launch_count(void);
 
 /* a = mu + exp(logstd) N(0,1) (Philox), neglogp (RGC:2115-2127) */

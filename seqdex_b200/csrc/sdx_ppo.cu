@@ -410,6 +410,8 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
   PCK(cudaGetLastError());
   return 0;
 }
+/* optimiser step counter (the `step` of torch.optim.Adam's state): read with set < 0, overwritten otherwise (checkpoint restore) */
+extern "C" long long sdx_mlp_adam_step(sdx_mlp* m, long long set) { if (set >= 0) m->adam_t = set; return m->adam_t; }
 extern "C" int sdx_mlp_adam(sdx_mlp* m, float lr, float b1, float b2, float eps, float max_norm, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   m->adam_t++;

@@ -203,38 +203,61 @@ class A2CAgent:
         self.sample_counter += 1
         return mu, t
 
+    # the three pieces of one rollout step, so that a sequencing runner (PSR:220-275) can interleave two agents on one env
+    def act(self, t):
+        """store obs / states / dones of step t (RGC:1403-1410, PSR:338-346), sample the action, evaluate the central value"""
+        L, A, N = self.L, self.A, self.N
+        mean = self.rms_mean if self.cfg.cv_normalize_input else None
+        var = self.rms_var if self.cfg.cv_normalize_input else None
+        self.b_obs[t].copy_(self.next_obs)
+        self.b_states[t].copy_(self.next_states)
+        self.b_dones[t].copy_(self.dones)
+        mu = self.actor.forward(self.b_obs[t])
+        self.b_mu[t].copy_(mu)
+        _lib.check(L.sdx_ppo_sample(_p(self.b_mu[t]), _p(self.logstd), N, A, ctypes.c_uint64(self.cfg.seed), self.sample_counter,
+                                    _p(self.b_actions[t]), _p(self.b_neglogp[t]), _stream()))
+        self.sample_counter += 1
+        v = self.cv.forward(self.b_states[t], mean, var)
+        self.b_values[t].copy_(v.view(-1))
+        return self.b_actions[t]
+
+    def record(self, t, rew, dones):
+        """rewards / dones after the env step (RGC:1420-1440, PSR:348-354; reward_shaper scale 1, no time-out bootstrap)"""
+        self.b_rewards[t].copy_(rew)
+        self.dones.copy_(dones)
+
+    def finish_rollout(self):
+        """bootstrap value + GAE (RGC:1465-1478, PSR:322-336)"""
+        mean = self.rms_mean if self.cfg.cv_normalize_input else None
+        var = self.rms_var if self.cfg.cv_normalize_input else None
+        v = self.cv.forward(self.next_states, mean, var)
+        self.last_values.copy_(v.view(-1))
+        _lib.check(self.L.sdx_gae(_p(self.b_rewards), _p(self.b_values), _p(self.b_dones), _p(self.last_values), _p(self.dones), _p(self.b_adv),
+                                  _p(self.b_returns), self.H, self.N, ctypes.c_float(self.cfg.gamma), ctypes.c_float(self.cfg.tau), _stream()))
+
+    def set_obs(self, obs, states):
+        """the observation the next act() consumes (``agent.obs`` in rl_games)"""
+        if self.obs is None:
+            self.next_obs, self.next_states = obs.clone(), states.clone()
+            self.obs = True
+        else:
+            self.next_obs.copy_(obs); self.next_states.copy_(states)
+
     def play_steps(self):
         """horizon_length env steps (RGC:1394-1483): obs/dones stored pre-step, values from the central value net"""
-        L, A, N, H = self.L, self.A, self.N, self.H
         fast = hasattr(self.env, "step_into")
         if self.obs is None:
             first = self.env.reset()
-            self.next_obs, self.next_states = first["obs"].clone(), first["states"].clone()
-            self.obs = True
-        mean = self.rms_mean if self.cfg.cv_normalize_input else None
-        var = self.rms_var if self.cfg.cv_normalize_input else None
-        for t in range(H):
-            self.b_obs[t].copy_(self.next_obs)
-            self.b_states[t].copy_(self.next_states)
-            self.b_dones[t].copy_(self.dones)
-            mu = self.actor.forward(self.b_obs[t])
-            self.b_mu[t].copy_(mu)
-            _lib.check(L.sdx_ppo_sample(_p(self.b_mu[t]), _p(self.logstd), N, A, ctypes.c_uint64(self.cfg.seed), self.sample_counter,
-                                        _p(self.b_actions[t]), _p(self.b_neglogp[t]), _stream()))
-            self.sample_counter += 1
-            v = self.cv.forward(self.b_states[t], mean, var)
-            self.b_values[t].copy_(v.view(-1))
+            self.set_obs(first["obs"], first["states"])
+        for t in range(self.H):
+            a = self.act(t)
             if fast:
-                rew, dones, _ = self.env.step_into(self.b_actions[t], self.next_obs, self.next_states)
+                rew, dones, _ = self.env.step_into(a, self.next_obs, self.next_states)
             else:
-                o, rew, dones, _ = self.env.step(self.b_actions[t])
+                o, rew, dones, _ = self.env.step(a)
                 self.next_obs.copy_(o["obs"]); self.next_states.copy_(o["states"])
-            self.b_rewards[t].copy_(rew)
-            self.dones.copy_(dones)
-        v = self.cv.forward(self.next_states, mean, var)
-        self.last_values.copy_(v.view(-1))
-        _lib.check(L.sdx_gae(_p(self.b_rewards), _p(self.b_values), _p(self.b_dones), _p(self.last_values), _p(self.dones), _p(self.b_adv),
-                             _p(self.b_returns), H, N, ctypes.c_float(self.cfg.gamma), ctypes.c_float(self.cfg.tau), _stream()))
+            self.record(t, rew, dones)
+        self.finish_rollout()
 
     def _allreduce(self, t, avg=True):
         if self.dist is not None and self.world > 1:
@@ -244,8 +267,12 @@ class A2CAgent:
 
     # ---- update (RGC:1621-1683, 1339-1375, 1767-1911)
     def train_epoch(self):
-        c, L, A, B, mb = self.cfg, self.L, self.A, self.B, self.mb
         self.play_steps()
+        return self.update()
+
+    def update(self):
+        """prepare_dataset + central-value and actor mini-epochs on the rollout the buffers hold (RGC:1621-1683, PSR:277-319)"""
+        c, L, A, B, mb = self.cfg, self.L, self.A, self.B, self.mb
         Btot = B * self.world
         obs, states = self.b_obs.view(B, -1), self.b_states.view(B, -1)
         actions, mu_old, nlp_old = self.b_actions.view(B, A), self.b_mu.view(B, A), self.b_neglogp.view(B)
@@ -306,17 +333,70 @@ class A2CAgent:
         return {"kl": self.last_kl, "lr": self.last_lr, "a_loss": float(st[0]) / B, "b_loss": float(st[1]) / B,
                 "mean_reward": float(self.b_rewards.mean())}
 
-    # ---- checkpoint (rl_games .pth layout: {'model': state_dict, ...}; RGC:1913-1933)
+    # ---- checkpoint (rl_games .pth layout, seqdex_b200/checkpoint.py; RGC:1913-1933, 2098-2106)
+    def _adam_step(self, mlp, set_to=-1):
+        self.L.sdx_mlp_adam_step.restype = ctypes.c_longlong
+        return int(self.L.sdx_mlp_adam_step(mlp.h, ctypes.c_longlong(set_to)))
+
+    def get_weights(self):
+        from . import checkpoint as ck
+        return {"model": ck.actor_state_dict(self.actor.params, self.obs_dim, self.A, critic=getattr(self, "_a2c_critic", None), seed=self.cfg.seed)}
+
+    def get_full_state_weights(self):
+        """what rl_games' ``A2CBase.save`` writes (restated at RGC:1913-1933): weights + optimiser + central value + counters"""
+        from . import checkpoint as ck
+        state = self.get_weights()
+        state["epoch"] = self.epoch_num
+        state["optimizer"] = ck.adam_state_dict(self.actor.adam_m, self.actor.adam_v, self._adam_step(self.actor), self.actor.slices(),
+                                                self.last_lr, ck.actor_param_order())
+        state["assymetric_vf_nets"] = ck.central_value_state_dict(
+            self.cv.params, self.state_dim, rms=(self.rms_mean, self.rms_var, self.rms_count) if self.cfg.cv_normalize_input else None)
+        cvo = [n for n, _, _ in self.cv.slices()]
+        state["assymetric_vf_optimizer"] = ck.adam_state_dict(self.cv.adam_m, self.cv.adam_v, self._adam_step(self.cv), self.cv.slices(),
+                                                              self.cfg.cv_learning_rate, cvo)
+        state["frame"] = self.epoch_num * self.B * self.world
+        state["last_mean_rewards"] = getattr(self, "last_mean_rewards", -100500)
+        state["env_state"] = self.env.get_env_state() if hasattr(self.env, "get_env_state") else None
+        return state
+
+    def set_weights(self, weights):
+        from . import checkpoint as ck
+        flat, critic = ck.actor_flat(weights["model"], self.obs_dim, self.A)
+        self._a2c_critic = critic
+        self.actor.load_flat(flat)
+
+    def set_full_state_weights(self, weights, load_optimizer_state=True):
+        from . import checkpoint as ck
+        self.set_weights(weights)
+        self.epoch_num = int(weights.get("epoch", 0))
+        self.last_mean_rewards = weights.get("last_mean_rewards", -100500)
+        if "assymetric_vf_nets" in weights:
+            flat, rms = ck.central_value_flat(weights["assymetric_vf_nets"], self.state_dim)
+            self.cv.load_flat(flat)
+            if rms is not None:
+                self.rms_mean.copy_(rms[0]); self.rms_var.copy_(rms[1]); self.rms_count.copy_(rms[2])
+        if load_optimizer_state:
+            for mlp, key, order in ((self.actor, "optimizer", ck.actor_param_order()), (self.cv, "assymetric_vf_optimizer", [n for n, _, _ in self.cv.slices()])):
+                opt = weights.get(key)
+                if not opt or len(opt["state"]) != len(order):
+                    continue        # e.g. a file written by rl_games itself: its optimizer also holds the unused critic trunk
+                by = {n: (o, s) for n, o, s in mlp.slices()}
+                for i, name in enumerate(order):
+                    o, shp = by[name]
+                    k = opt["state"][i]["exp_avg"].numel()
+                    mlp.adam_m[o:o + k].copy_(opt["state"][i]["exp_avg"].reshape(-1))
+                    mlp.adam_v[o:o + k].copy_(opt["state"][i]["exp_avg_sq"].reshape(-1))
+                self._adam_step(mlp, int(float(opt["state"][0]["step"])))
+                if key == "optimizer":
+                    self.last_lr = float(opt["param_groups"][0]["lr"])
+
+    def save(self, fn):
+        from . import checkpoint as ck
+        return ck.save_checkpoint(fn, self.get_full_state_weights())
+
+    def restore(self, fn):
+        from . import checkpoint as ck
+        self.set_full_state_weights(ck.load_checkpoint(fn))
+
     def state_dict(self):
-        sd = {}
-        for name, off, shp in self.actor.slices():
-            n = int(torch.tensor(shp).prod())
-            key = {"W": "a2c_network.actor_mlp.{}.weight", "b": "a2c_network.actor_mlp.{}.bias"}.get(name[0])
-            if name == "sigma":
-                sd["a2c_network.sigma"] = self.actor.params[off:off + n].clone()
-            elif int(name[1]) < 3:
-                sd[key.format(2 * int(name[1]))] = self.actor.params[off:off + n].view(shp).clone()
-            else:
-                sd["a2c_network.mu." + ("weight" if name[0] == "W" else "bias")] = self.actor.params[off:off + n].view(shp).clone()
-        return {"model": sd, "epoch": self.epoch_num, "last_lr": self.last_lr,
-                "central_val": self.cv.params.clone(), "running_mean_std": (self.rms_mean.clone(), self.rms_var.clone(), self.rms_count.clone())}
+        return self.get_full_state_weights()
