@@ -59,7 +59,18 @@ typedef struct sdx_scene_t {
   float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
   float cam_off_pos[3], cam_off_quat[4];
   float act_moving_average, av_factor, vel_obs_scale, warm_start, wake_energy;   /* wake_energy: energy above which a brick wakes what it touches */
+  int task;                   /* SDX_TASK_*: which task's pre-physics / observation / reward / reset ops run around the contact step */
+  float hand_target_quat[4];  /* Orient: quat_from_euler_xyz(target_euler = (0, 3.1415, 1.571)) the arm IK tracks (OR:484, 1738) */
+  int bank_sample_range;      /* Orient: reset samples heap rows [0, range) of the bank (OR:1564 env_rand_range = range(0, 500)) */
+  int pad3[2];
 } sdx_scene_t;
+
+/* tasks sharing the scene, the contact step and the PPO engine (SURVEY.md section 8a "per-task dimensions"):
+ *   OR = tasks/block_assembly/allegro_hand_block_assembly_orient.py */
+#define SDX_TASK_GRASP_SIM 0   /* BlockAssemblyGraspSim: obs 132 x 3, states 188 x 3, episode 150 (GS:191-211) */
+#define SDX_TASK_ORIENT 1      /* BlockAssemblyOrient:   obs  62 x 3, states 188 x 3, episode  75 (OR:189-214)  */
+#define SDX_ORIENT_OBS_FRAME 62
+#define SDX_ORIENT_BANK_WRAP 10000   /* OR:1478-1479: ring index returns to 0 after slot 10000 */
 
 /* Tensor kinds for sdx_tensor(): device buffers owned by the env. dtype 0=f32 1=i64 2=i32 3=u8 */
 enum {
@@ -69,7 +80,7 @@ enum {
   SDX_T_JAC7 = 3,       /* f32 [N][6][7]    jacobian_tensor[:, link7-1, :, :7] (GS:1601)             */
   SDX_T_NETF = 4,       /* f32 [N][24][3]   net contact force on robot links (GS:1159)               */
   SDX_T_ACTIONS = 5,    /* f32 [N][23]                                                              */
-  SDX_T_OBS = 6,        /* f32 [N][396]  obs_buf (BT:57)                                             */
+  SDX_T_OBS = 6,        /* f32 [N][396]  obs_buf (BT:57); [N][186] for SDX_TASK_ORIENT                */
   SDX_T_STATES = 7,     /* f32 [N][564]  states_buf (BT:59)                                          */
   SDX_T_REW = 8,        /* f32 [N]       rew_buf                                                     */
   SDX_T_RESET = 9,      /* i64 [N]       reset_buf (BT:63)                                           */
@@ -152,6 +163,16 @@ int sdx_grasp_bank(sdx_env_t* env, void** hand_dev, void** obj_dev, void** index
  * succ/fail [capacity][4] f32 + counts i64[2] (rows ever written) and records from the next reset on; 0 stops recording */
 int sdx_tvalue_dataset(sdx_env_t* env, int capacity, void** succ_dev, void** fail_dev, void** counts_dev);
 int sdx_aux(sdx_env_t* env, void** qcam_dev, void** finger_dist_dev);
+/* Orient (OR:1390-1695).  reset_idx there is not a per-env scatter: it drives the WHOLE sim through a scripted sequence --
+ * 50 steps lifting the hand above the target (OR:1430-1458), one extra compute_observations + banking of the re-oriented heaps
+ * (OR:1460-1511), the state reset (OR:1523-1605) and post_reset's 2 + 1 + 50 settle / approach steps (OR:1612-1695).
+ * sdx_pre_physics runs that sequence itself when any reset flag is set (one 4-byte device->host read per step, the
+ * reference's reset_buf.nonzero()).  The entry points below expose its two data products:
+ * terminal heaps of envs whose brick ended face up (saved_digging_ternimal_states_list -> ..._good_mo_tvalue.pkl, OR:1465-1513):
+ * capacity > 0 allocates rings [8][capacity + 1][72][13] f32 (free-brick root rows) + index i32[8] and records from then on */
+int sdx_orient_heap_bank(sdx_env_t* env, int capacity, void** rows_dev, void** index_dev);
+/* number of contact steps the last sdx_pre_physics spent inside reset_idx (0 when nobody reset; 103 for a full Orient reset) */
+int sdx_last_reset_sim_steps(const sdx_env_t* env);
 int sdx_scene_size(void);
 int sdx_sim_smem_bytes(void);
 

@@ -75,7 +75,8 @@ class OracleEnv:
         self.jac7 = np.zeros((n, 6, 7), np.float32)
         self.netf = np.zeros((n, NL, 3), np.float32)
         self.actions = np.zeros((n, 23), np.float32)
-        self.obs = np.zeros((n, 396), np.float32)
+        self.task = int(scene.c.task)               # 0 BlockAssemblyGraspSim, 1 BlockAssemblyOrient
+        self.obs = np.zeros((n, 396 if self.task == 0 else 186), np.float32)
         self.states = np.zeros((n, 564), np.float32)
         self.rew = np.zeros(n, np.float32)
         self.reset = np.ones(n, np.int64)           # BT:63
@@ -150,7 +151,53 @@ class OracleEnv:
         self.tvd_fail = np.zeros((cap, 4), np.float32)
         self.tvd_counts = np.zeros(2, np.int64)
 
+    def enable_orient_heap_bank(self, cap):
+        self.ob_wrap = int(cap)
+        self.ob_rows = np.zeros((8, cap + 1, NB, 13), np.float32)
+        self.ob_index = np.zeros(8, np.int32)
+
+    def _orient_reset_idx(self):
+        """OR:1390-1695: the scripted reset (lift 50, observe + bank, state reset, settle 2 + 1, approach 50)"""
+        L, vp = self.L, self.slp.ctypes.data_as(ctypes.c_void_p)
+        script = lambda mode, i: L.sdxo_orient_arm_script(self.S, self.n, lp(self.reset), mode, i, fp(self.dof), fp(self.link),
+                                                          fp(self.jac7), fp(self.brick), fp(self.target_init))
+        state = lambda phase: L.sdxo_orient_reset(self.S, self.n, ctypes.c_uint64(self.seed), fp(self.bank), self.per_type, phase,
+                                                  fp(self.brick), fp(self.dof), fp(self.target_init), lp(self.progress), lp(self.reset),
+                                                  fp(self.successes), ip(self.episode), ip(self.wsn), vp)
+        self.last_reset_sim_steps = 0
+        def sim():
+            self.simulate(); self.last_reset_sim_steps += 1
+        if self.total_steps > 0:
+            for i in range(50):
+                script(0, i); sim()
+            self._orient_post(0)
+            if getattr(self, "ob_wrap", 0):
+                L.sdxo_orient_bank(self.S, self.n, fp(self.brick), fp(self.finger_dist), fp(self.tvalue), fp(self.ob_rows),
+                                   ip(self.ob_index), self.ob_wrap)
+        state(0)
+        sim(); sim()                  # OR:1617-1619 (every reader of the link rows below comes after a contact step, which rewrites them)
+        state(1)
+        sim()                         # OR:1657
+        for i in range(50):
+            script(1, i); sim()
+        state(2)
+
+    def _orient_post(self, count_step):
+        self.L.sdxo_orient_post_physics(self.S, self.n, fp(self.tv), fp(self.brick), fp(self.dof), fp(self.link), fp(self.actions),
+                                        fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.obs), fp(self.states),
+                                        fp(self.rew), fp(self.tvalue), fp(self.finger_dist), fp(self.successes), fp(self.consec),
+                                        int(count_step))
+
     def pre_physics(self, actions):
+        if self.task == 1:
+            self.last_reset_sim_steps = 0
+            if self.reset.any():
+                assert self.bank is not None, "reset needs a heap bank (OR:419-420)"
+                self._orient_reset_idx()
+            a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)   # VR:166
+            self.L.sdxo_orient_pre_physics(self.S, self.n, fp(a), fp(self.actions), fp(self.dof), fp(self.link), fp(self.jac7),
+                                           fp(self.brick), lp(self.progress), fp(self.target_init))
+            return
         if self.reset.any():
             assert self.bank is not None, "reset needs a heap bank (GS:412-413)"
             if getattr(self, "tvd_cap", 0) and self.total_steps > 0:
@@ -165,6 +212,10 @@ class OracleEnv:
                                 lp(self.progress), fp(self.target_init))
 
     def post_physics(self):
+        if self.task == 1:
+            self._orient_post(1)
+            self.total_steps += 1
+            return
         self.L.sdxo_post_physics(self.S, self.n, fp(self.tv), fp(self.brick), fp(self.dof), fp(self.link), fp(self.actions),
                                  fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.obs), fp(self.states),
                                  fp(self.rew), fp(self.tvalue), fp(self.finger_dist), fp(self.successes), fp(self.consec))

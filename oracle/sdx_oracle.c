@@ -64,7 +64,13 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   float prepare_arm[7], insert_prep0[7], insert_prep1[7], finger_reset_unscaled[16];
   float cam_off_pos[3], cam_off_quat[4];
   float act_moving_average, av_factor, vel_obs_scale, warm_start, wake_energy;
+  int task;
+  float hand_target_quat[4];
+  int bank_sample_range;
+  int pad3[2];
 } sdx_scene_t;
+#define ORIENT_OBS_FRAME 62
+#define ORIENT_BANK_WRAP 10000
 
 /* ------------------------------------------------------------------ math */
 typedef struct { float x, y, z; } v3;
@@ -981,6 +987,249 @@ void sdxo_tv_dataset(const sdx_scene_t* S, int n, const int64_t* reset, const fl
     float* dst = (ok ? succ : fail) + 4 * (size_t)(counts[ok ? 0 : 1] % cap);
     for (int k = 0; k < 4; ++k) dst[k] = states[(size_t)e * 3 * STATE_FRAME + 177 + k];
     counts[ok ? 0 : 1] += 1;
+  }
+}
+
+
+/* ================================================================== BlockAssemblyOrient (SDX_TASK_ORIENT)
+ * OR = tasks/block_assembly/allegro_hand_block_assembly_orient.py.  Same scene, contact step, t-value gate and privileged
+ * state frame as GraspSim; its own action mapping (object-centric arm IK, OR:1697-1778), observation frame (62 slots, of
+ * which compute_real_observations writes 48, OR:1308-1326), reward (OR:1843-1907) and a scripted reset (OR:1390-1695).
+ * PARITY: pre-physics, observations, reward / reset flags PINNED to the reference's own Python (oracle/gen_golden_orient.py
+ * -> tests/golden/orient_*.npz); the reset script is sequencing of those pieces around the (unpinned) contact step. */
+static inline float sgnf(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); } /* torch.sign */
+/* orientation_error (OR:1922-1925): xyz of desired * conj(current), flipped to the short way round */
+static inline v3 orientation_error(q4 desired, q4 current) {
+  q4 r = qmul(desired, qconj(current));
+  float sg = sgnf(r.w);
+  return V3(r.x * sg, r.y * sg, r.z * sg);
+}
+static inline float z_align(q4 q) { /* sign(d) d^2 with d = (R(q) z) . z  (OR:1198-1201, 1857-1860) */
+  float d = qrot(q, V3(0.0f, 0.0f, 1.0f)).z;
+  return sgnf(d) * (d * d);
+}
+
+/* pre_physics_step, after any reset (OR:1711-1778): fingers = EMA of the scaled actions; arm = IK towards the pose 22 cm
+ * above / 18 cm behind the target brick with the fixed wrist orientation hand_target_quat */
+void sdxo_orient_pre_physics(const sdx_scene_t* S, int n, const float* actions_in, float* actions, float* dof, const float* link,
+                             const float* jac7, const float* brick, const int64_t* progress, const float* target_init) {
+  for (int e = 0; e < n; ++e) {
+    const float* a = actions_in + 23 * e;
+    float* d = dof + (size_t)e * 72;
+    float cur[23];
+    for (int k = 0; k < 23; ++k) actions[23 * e + k] = a[k];
+    for (int i = 0; i < 16; ++i) {
+      float t = scalef(a[7 + i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+      cur[7 + i] = S->act_moving_average * t + (1.0f - S->act_moving_average) * d[48 + 7 + i];
+    }
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), tg);
+    const float* hb = link + ((size_t)e * SDX_NL + 7) * 13;
+    float dpose[6];
+    dpose[0] = (tg[0] - hb[0]) - 0.18f; dpose[1] = tg[1] - hb[1]; dpose[2] = (tg[2] - hb[2]) + 0.22f;
+    int64_t pg = progress[e];
+    if (pg > 75) dpose[2] = ((target_init[7 * e + 2] - hb[2]) + 0.15f) + 0.24f; /* OR:1735 */
+    q4 want = {S->hand_target_quat[0], S->hand_target_quat[1], S->hand_target_quat[2], S->hand_target_quat[3]};
+    q4 hq = {hb[3], hb[4], hb[5], hb[6]};
+    v3 re = orientation_error(want, hq);
+    dpose[3] = re.x; dpose[4] = re.y; dpose[5] = re.z;
+    float u[7];
+    control_ik(jac7 + 42 * (size_t)e, dpose, u);
+    for (int j = 0; j < 7; ++j) cur[j] = d[j] + u[j];
+    if (pg > 75) for (int i = 7; i < 23; ++i) cur[i] = d[48 + i]; /* OR:1743 */
+    for (int j = 0; j < 23; ++j) d[48 + j] = clampf(cur[j], S->dof_lo[j], S->dof_hi[j]);
+  }
+}
+
+/* post_physics_step (OR:1780-1784) when count_step != 0: progress += 1, compute_observations (OR:1087-1242 ->
+ * compute_real_observations OR:1308-1326 + compute_contact_asymmetric_observations OR:1244-1306), compute_hand_reward
+ * (OR:1843-1907).  count_step == 0 is the bare compute_observations() call inside reset_idx (OR:1461): observations,
+ * finger distance and gate value only.  obs [n][186], states [n][564]. */
+void sdxo_orient_post_physics(const sdx_scene_t* S, int n, const float* tv_wts, const float* brick, const float* dof,
+                              const float* link, const float* actions, const float* target_init, int64_t* progress,
+                              int64_t* reset, float* obs, float* states, float* rew, float* tvalue, float* finger_dist_out,
+                              const float* successes, float* consec, int count_step) {
+  int64_t num_resets = 0; float finished = 0.0f;
+  for (int e = 0; e < n; ++e) {
+    if (count_step) progress[e] += 1;
+    const float* L = link + (size_t)e * SDX_NL * 13;
+    const float* d = dof + (size_t)e * 72;
+    const float* hb = L + 7 * 13;
+    const float* ff = L + 11 * 13; const float* mf = L + 19 * 13; const float* rf = L + 23 * 13; const float* th = L + 15 * 13; /* OR:183-186 */
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), tg);
+    v3 tp = V3(tg[0], tg[1], tg[2]); q4 tq = {tg[3], tg[4], tg[5], tg[6]};
+    v3 tip[4]; const float* fs[4] = {ff, mf, rf, th};
+    float nrm[4];
+    for (int i = 0; i < 4; ++i) { /* OR:1158-1161 */
+      q4 fq = {fs[i][3], fs[i][4], fs[i][5], fs[i][6]};
+      tip[i] = vadd(V3(fs[i][0], fs[i][1], fs[i][2]), qrot(fq, V3(0.0f, 0.0f, 1.0f * 0.04f)));
+      v3 dd = vsub(tp, tip[i]); nrm[i] = sqrtf(vdot(dd, dd));
+    }
+    float fdist = nrm[0] + nrm[1] + nrm[2] + nrm[3]; /* OR:1174-1175 */
+    finger_dist_out[e] = fdist;
+    q4 hq = {hb[3], hb[4], hb[5], hb[6]}; v3 hp = V3(hb[0], hb[1], hb[2]);
+    q4 cq0 = {S->cam_off_quat[0], S->cam_off_quat[1], S->cam_off_quat[2], S->cam_off_quat[3]};
+    q4 cq = qmul(hq, cq0); v3 cp = vadd(qrot(hq, V3(S->cam_off_pos[0], S->cam_off_pos[1], S->cam_off_pos[2])), hp); /* OR:1181-1187 */
+    q4 cqi = qconj(cq); v3 cpi = vneg(qrot(cqi, cp));
+    q4 cvq = qmul(cqi, tq); v3 cvp = vadd(qrot(cqi, tp), cpi);
+    float qin[4] = {cvq.x, cvq.y, cvq.z, cvq.w};
+    float tv = sdxo_tvalue_one(tv_wts, qin);
+    tvalue[e] = tv > 0.99f ? 1.0f : 0.0f; /* OR:1203-1205 */
+    const float* ti = target_init + 7 * e;
+    /* ---- obs frame 0 (OR:1308-1326); slots 16..29 and frames 1, 2 are never written by the reference */
+    float* o = obs + (size_t)e * 3 * ORIENT_OBS_FRAME;
+    for (int i = 0; i < 16; ++i) {
+      float us = unscalef(d[7 + i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+      o[i] = us;
+      o[30 + i] = actions[23 * e + 7 + i] - us;
+      o[46 + i] = actions[23 * e + 7 + i];
+    }
+    /* ---- privileged state frame (OR:1244-1306): the GraspSim layout */
+    float* s = states + (size_t)e * 3 * STATE_FRAME;
+    for (int k = 2 * STATE_FRAME - 1; k >= 0; --k) s[STATE_FRAME + k] = s[k];
+    for (int j = 0; j < 23; ++j) { s[j] = unscalef(d[j], S->dof_lo[j], S->dof_hi[j]); s[23 + j] = S->vel_obs_scale * d[24 + j]; }
+    s[46] = tip[0].x; s[47] = tip[0].y; s[48] = tip[0].z;
+    s[49] = tip[2].x; s[50] = tip[2].y; s[51] = tip[2].z;
+    s[52] = tip[1].x; s[53] = tip[1].y; s[54] = tip[1].z;
+    s[55] = tip[3].x; s[56] = tip[3].y; s[57] = tip[3].z;
+    for (int k = 0; k < 23; ++k) s[58 + k] = actions[23 * e + k];
+    for (int k = 0; k < 7; ++k) { s[81 + k] = hb[k]; s[88 + k] = tg[k]; }
+    for (int k = 0; k < 6; ++k) s[95 + k] = hb[7 + k];
+    for (int k = 0; k < 4; ++k) { s[101 + k] = ff[3 + k]; s[111 + k] = mf[3 + k]; s[121 + k] = rf[3 + k]; s[131 + k] = th[3 + k]; }
+    for (int k = 0; k < 6; ++k) { s[105 + k] = ff[7 + k]; s[115 + k] = mf[7 + k]; s[125 + k] = rf[7 + k]; s[135 + k] = th[7 + k]; }
+    for (int k = 0; k < 6; ++k) s[142 + k] = tg[7 + k];
+    s[148] = ti[0]; s[149] = ti[1]; s[150] = ti[2];
+    s[151] = tp.x - ti[0]; s[152] = tp.y - ti[1]; s[153] = tp.z - ti[2];
+    s[154] = hp.x - tp.x; s[155] = hp.y - tp.y; s[156] = hp.z - tp.z;
+    q4 rel = qmul(hq, qconj(tq));
+    s[157] = rel.x; s[158] = rel.y; s[159] = rel.z; s[160] = rel.w;
+    { v3 a = vsub(tp, tip[0]), b = vsub(tp, tip[2]), c = vsub(tp, tip[1]), dd = vsub(tp, tip[3]);
+      s[161] = a.x; s[162] = a.y; s[163] = a.z; s[164] = b.x; s[165] = b.y; s[166] = b.z;
+      s[167] = c.x; s[168] = c.y; s[169] = c.z; s[170] = dd.x; s[171] = dd.y; s[172] = dd.z; }
+    s[173] = fdist;
+    s[174] = cvp.x; s[175] = cvp.y; s[176] = cvp.z; s[177] = cvq.x; s[178] = cvq.y; s[179] = cvq.z; s[180] = cvq.w;
+    s[181] = cvp.x; s[182] = cvp.y; s[183] = cvp.z; s[184] = cvq.x; s[185] = cvq.y; s[186] = cvq.z; s[187] = cvq.w;
+    if (!count_step) continue;
+    /* ---- reward / reset flags (OR:1852-1907) */
+    float dist = nrm[0] + nrm[1] + nrm[2] + 3.0f * nrm[3];
+    int64_t rs = reset[e];
+    if (dist <= -1.0f) rs = 1;
+    if ((float)progress[e] >= (float)S->max_episode_length - 1.0f) rs = 1;
+    float drew = dist - 0.4f; if (drew < 0.0f) drew = 0.0f;
+    if (progress[e] > 175) drew = 0.0f;
+    float zrew = 1.0f - ((z_align(tq) + 1.0f) / 2.0f);
+    rew[e] = sdx_exp(-(5.0f * zrew + 5.0f * drew));
+    reset[e] = rs;
+    num_resets += rs; finished = finished + successes[e] * (float)rs;
+  }
+  if (count_step && num_resets > 0) consec[0] = S->av_factor * finished / (float)num_resets + (1.0f - S->av_factor) * consec[0];
+}
+
+/* the two scripted arm motions of reset_idx, for the envs whose reset flag is set:
+ * mode 0 (OR:1430-1455, before the banking): lift the hand to 42 cm above / 18 cm behind the CURRENT target pose; the arm
+ *   target is clamped; the finger targets open by 0.01 rad ONCE (cur_targets_clone - 0.01 is the same every iteration)
+ * mode 1 (OR:1659-1690, post_reset): teleport the arm along the IK solution towards 22 cm (+20 cm for the first 20
+ *   iterations) above the INITIAL target pose -- joint positions, targets (unclamped) and zero velocities are written into
+ *   the sim; the fingers are held at their reset pose */
+void sdxo_orient_arm_script(const sdx_scene_t* S, int n, const int64_t* reset, int mode, int iter, float* dof, const float* link,
+                            const float* jac7, const float* brick, const float* target_init) {
+  for (int e = 0; e < n; ++e) {
+    if (!reset[e]) continue;
+    float* d = dof + (size_t)e * 72;
+    const float* hb = link + ((size_t)e * SDX_NL + 7) * 13;
+    float dpose[6];
+    if (mode == 0) {
+      float tg[13];
+      brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), tg);
+      dpose[0] = (tg[0] - hb[0]) - 0.18f; dpose[1] = tg[1] - hb[1]; dpose[2] = (tg[2] - hb[2]) + 0.42f;
+    } else {
+      const float* ti = target_init + 7 * e;
+      float z = (ti[2] - hb[2]) + 0.22f;
+      if (iter < 20) z = z + 0.2f;
+      dpose[0] = (ti[0] - hb[0]) - 0.18f; dpose[1] = ti[1] - hb[1]; dpose[2] = z;
+    }
+    q4 want = {S->hand_target_quat[0], S->hand_target_quat[1], S->hand_target_quat[2], S->hand_target_quat[3]};
+    q4 hq = {hb[3], hb[4], hb[5], hb[6]};
+    v3 re = orientation_error(want, hq);
+    dpose[3] = re.x; dpose[4] = re.y; dpose[5] = re.z;
+    float u[7];
+    control_ik(jac7 + 42 * (size_t)e, dpose, u);
+    if (mode == 0) {
+      for (int j = 0; j < 7; ++j) d[48 + j] = clampf(d[j] + u[j], S->dof_lo[j], S->dof_hi[j]);
+      if (iter == 0) for (int i = 7; i < 23; ++i) d[48 + i] = d[48 + i] - 0.01f;
+    } else {
+      for (int j = 0; j < 7; ++j) { float t = d[j] + u[j]; d[j] = t; d[48 + j] = t; d[24 + j] = 0.0f; }
+      for (int i = 0; i < 16; ++i) {
+        float v = scalef(S->finger_reset_unscaled[i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+        d[7 + i] = v; d[24 + 7 + i] = 0.0f; d[48 + 7 + i] = v;
+      }
+    }
+  }
+}
+
+/* banking of the re-oriented heaps (OR:1465-1481), EVERY env in env order (the reference loops over range(num_envs), not
+ * env_ids): fingers away from the brick (> 0.3), brick inside the bin's near half (0 < y < 0.5), gate passed (tvalue, already
+ * thresholded to {0, 1}, > 0.6) -> the env's 72 free-brick root rows go to ring[type][index]; the index returns to 0 after
+ * slot `wrap`.  rows_out [8][wrap + 1][72][13].  (The reference's .view(num_envs, 108, 13) at OR:1465 cannot hold the 132
+ * bricks it indexes; the intent -- the whole heap, as Search banks it, SE:1348-1352 -- is what is restated.) */
+void sdxo_orient_bank(const sdx_scene_t* S, int n, const float* brick, const float* finger_dist, const float* tvalue,
+                      float* rows_out, int* index, int wrap) {
+  for (int e = 0; e < n; ++e) {
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), tg);
+    if (!(finger_dist[e] > 0.3f)) continue;
+    if (!(0.5f > tg[1] && tg[1] > 0.0f)) continue;
+    if (!(tvalue[e] > 0.6f)) continue;
+    int ty = e % 8;
+    float* dst = rows_out + (((size_t)ty * (wrap + 1)) + index[ty]) * NB * 13;
+    for (int b = 0; b < NB; ++b) brick_root_row(S, brick + (size_t)e * 13 * NB, b, dst + b * 13);
+    index[ty] += 1;
+    if (index[ty] > wrap) index[ty] = 0;
+  }
+}
+
+/* state writes of reset_idx / post_reset for the envs whose reset flag is set.
+ * phase 0 (OR:1541-1605): heap <- bank row Philox(seed, env, episode) % min(per_type, bank_sample_range), velocities 0;
+ *          hand at the prepare pose with the finger reset pose, velocities 0, targets = positions
+ * phase 1 (OR:1623-1645, after 2 settle steps): remember the target's pose as its initial pose; hand written again
+ * phase 2 (OR:1607-1610): progress, reset flag, successes cleared */
+void sdxo_orient_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* bank, int per_type, int phase, float* brick,
+                       float* dof, float* target_init, int64_t* progress, int64_t* reset, float* successes, int* episode,
+                       int* wsn, unsigned char* slp) {
+  for (int e = 0; e < n; ++e) {
+    if (!reset[e]) continue;
+    float* B = brick + (size_t)e * 13 * NB;
+    float* d = dof + (size_t)e * 72;
+    if (phase == 0) {
+      uint32_t r[4];
+      philox(seed, (uint32_t)e, (uint32_t)episode[e], 1u, r);
+      int range = per_type < S->bank_sample_range ? per_type : S->bank_sample_range;
+      int slot = (int)(r[0] % (uint32_t)range);
+      const float* rows = bank + (((size_t)(e % 8)) * per_type + slot) * NB * 13;
+      for (int b = 0; b < NB; ++b) {
+        float row[13];
+        for (int k = 0; k < 7; ++k) row[k] = rows[b * 13 + k];
+        for (int k = 7; k < 13; ++k) row[k] = 0.0f; /* OR:1570 */
+        brick_from_root_row(S, B, b, row);
+        slp[(size_t)e * NB + b] = 0;
+      }
+      wsn[2 * e] = 0; wsn[2 * e + 1] = 0;
+      episode[e] += 1;
+    }
+    if (phase == 1) {
+      float tg[13];
+      brick_root_row(S, B, target_brick(e), tg);
+      for (int k = 0; k < 7; ++k) target_init[7 * e + k] = tg[k]; /* OR:1623-1624 */
+    }
+    if (phase == 0 || phase == 1) {
+      for (int j = 0; j < 7; ++j) { d[j] = S->prepare_arm[j]; d[24 + j] = 0.0f; d[48 + j] = S->prepare_arm[j]; }
+      for (int i = 0; i < 16; ++i) {
+        float v = scalef(S->finger_reset_unscaled[i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+        d[7 + i] = v; d[24 + 7 + i] = 0.0f; d[48 + 7 + i] = v;
+      }
+    }
+    if (phase == 2) { progress[e] = 0; reset[e] = 0; successes[e] = 0.0f; }
   }
 }
 

@@ -10,6 +10,7 @@
 
 #include "sdx_sim.cuh"
 #include "sdx_task.cuh"
+#include "sdx_task_orient.cuh"
 
 static thread_local std::string g_err;
 extern "C" const char* sdx_last_error(void) { return g_err.c_str(); }
@@ -39,7 +40,15 @@ struct sdx_env {
   long long total_steps = 0, launches = 0;
   int ws_cur = 0;          // which impulse-cache buffer holds the latest contact list
   bool dump_contacts = false;
+  // BlockAssemblyOrient
+  int task = 0;
+  int* flag_count = nullptr;       // device: number of reset flags set
+  int* flag_count_host = nullptr;  // pinned mirror
+  int* ob_slot = nullptr;          // [n] ring slot of each env in the current banking call
+  float* ob_rows = nullptr; int* ob_index = nullptr; int ob_wrap = 0;   // re-oriented heap rings (sdx_orient_heap_bank)
+  int last_reset_sim_steps = 0;
 };
+static int obs_frame(const sdx_env* E) { return E->task == SDX_TASK_ORIENT ? SDX_ORIENT_OBS_FRAME : SDX_OBS_FRAME; }
 
 static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim, int* dtype) {
   int64_t n = E->n;
@@ -51,7 +60,7 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
     case SDX_T_JAC7: s[0] = n; s[1] = 6; s[2] = 7; nd = 3; break;
     case SDX_T_NETF: s[0] = n; s[1] = SDX_NL; s[2] = 3; nd = 3; break;
     case SDX_T_ACTIONS: s[0] = n; s[1] = 23; nd = 2; break;
-    case SDX_T_OBS: s[0] = n; s[1] = 3 * SDX_OBS_FRAME; nd = 2; break;
+    case SDX_T_OBS: s[0] = n; s[1] = 3 * obs_frame(E); nd = 2; break;
     case SDX_T_STATES: s[0] = n; s[1] = 3 * SDX_STATE_FRAME; nd = 2; break;
     case SDX_T_REW: case SDX_T_TVALUE: case SDX_T_SUCCESSES: s[0] = n; break;
     case SDX_T_RESET: case SDX_T_PROGRESS: s[0] = n; dt = 1; break;
@@ -84,6 +93,8 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaSetDevice(device));
   sdx_env* E = new sdx_env();
   E->n = num_envs; E->device = device; E->seed = seed; E->host_scene = *scene;
+  if (scene->task != SDX_TASK_GRASP_SIM && scene->task != SDX_TASK_ORIENT) { g_err = "sdx_create: unknown scene.task"; delete E; return -1; }
+  E->task = scene->task;
   CK(cudaMalloc(&E->scene, sizeof(sdx_scene_t)));
   CK(cudaMemcpy(E->scene, scene, sizeof(sdx_scene_t), cudaMemcpyHostToDevice));
   for (int k = 0; k < SDX_T_COUNT; ++k) {
@@ -103,7 +114,10 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaMalloc(&E->gb_index, 8 * 4)); CK(cudaMemset(E->gb_index, 0, 32));
   CK(cudaMalloc(&E->red_count, 4)); CK(cudaMemset(E->red_count, 0, 4));
   CK(cudaMalloc(&E->red_sum, 4)); CK(cudaMemset(E->red_sum, 0, 4));
-  CK(cudaMalloc(&E->stage_obs, n * 3 * SDX_OBS_FRAME * 4));
+  CK(cudaMalloc(&E->flag_count, 4)); CK(cudaMemset(E->flag_count, 0, 4));
+  CK(cudaMallocHost(&E->flag_count_host, 4)); *E->flag_count_host = 0;
+  CK(cudaMalloc(&E->ob_slot, n * 4));
+  CK(cudaMalloc(&E->stage_obs, n * 3 * obs_frame(E) * 4));
   CK(cudaMalloc(&E->stage_states, n * 3 * SDX_STATE_FRAME * 4));
   CK(cudaMalloc(&E->stage_actions, n * 23 * 4));
   CK(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
@@ -119,6 +133,7 @@ extern "C" void sdx_destroy(sdx_env_t* E) {
   cudaFree(E->scene); cudaFree(E->qcam); cudaFree(E->finger_dist); cudaFree(E->static_rows); cudaFree(E->bank); cudaFree(E->tvw);
   cudaFree(E->gb_hand); cudaFree(E->gb_obj); cudaFree(E->gb_index); cudaFree(E->red_count); cudaFree(E->red_sum);
   cudaFree(E->stage_obs); cudaFree(E->stage_states); cudaFree(E->stage_actions);
+  cudaFree(E->flag_count); cudaFreeHost(E->flag_count_host); cudaFree(E->ob_slot); cudaFree(E->ob_rows); cudaFree(E->ob_index);
   delete E;
 }
 extern "C" int sdx_set_stream(sdx_env_t* E, void* stream) { E->stream = (cudaStream_t)stream; return 0; }
@@ -244,10 +259,12 @@ extern "C" int sdx_reset_all(sdx_env_t* E) {
   return 0;
 }
 
+static int orient_pre_physics(sdx_env_t* E, const float* actions_dev);
 extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
   CK(cudaSetDevice(E->device));
   const int n = E->n;
   if (!E->bank) { g_err = "sdx_pre_physics: no heap bank set (reset_idx samples it, GS:1507-1511)"; return -1; }
+  if (E->task == SDX_TASK_ORIENT) return orient_pre_physics(E, actions_dev);
   if (E->total_steps > 0) {
     k_bank_terminal<<<8, 256, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), I64(SDX_T_RESET), E->finger_dist,
                                               F(SDX_T_TVALUE), E->gb_hand, E->gb_obj, E->gb_index);
@@ -284,13 +301,98 @@ extern "C" int sdx_simulate_n(sdx_env_t* E, int steps) {
   return 0;
 }
 
+static int orient_observe(sdx_env_t* E, int count_step) {
+  const int n = E->n;
+  k_orient_post_physics<<<(n + POST_WARPS - 1) / POST_WARPS, 32 * POST_WARPS, 0, E->stream>>>(
+      E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_ACTIONS), F(SDX_T_TARGET_INIT), I64(SDX_T_PROGRESS),
+      I64(SDX_T_RESET), F(SDX_T_OBS), F(SDX_T_STATES), F(SDX_T_REW), E->qcam, E->finger_dist, F(SDX_T_SUCCESSES), E->red_count, E->red_sum,
+      count_step);
+  k_tvalue<<<(n + TV_ENVS * TV_WARPS - 1) / (TV_ENVS * TV_WARPS), 32 * TV_WARPS, 0, E->stream>>>(E->tvw, n, E->qcam, F(SDX_T_TVALUE), 0.99f);
+  E->launches += 2;
+  CKL();
+  return 0;
+}
+
+// BlockAssemblyOrient.pre_physics_step (OR:1697-1778).  reset_idx (OR:1390-1695) is a script over the whole sim, run here when
+// any reset flag is set: [lift 50 steps, observe, bank]* (* skipped before the first step), state reset, 2 + 1 settle steps,
+// 50 approach steps, flags cleared.
+static int orient_pre_physics(sdx_env_t* E, const float* actions_dev) {
+  const int n = E->n, T = 128, G = (n + T - 1) / T;
+  CK(cudaMemsetAsync(E->flag_count, 0, 4, E->stream));
+  k_count_flags<<<(n + 255) / 256, 256, 0, E->stream>>>(I64(SDX_T_RESET), n, E->flag_count);
+  E->launches++;
+  CK(cudaMemcpyAsync(E->flag_count_host, E->flag_count, 4, cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));                       // the reference's reset_buf.nonzero() is the same host sync
+  E->last_reset_sim_steps = 0;
+  if (*E->flag_count_host > 0) {
+    auto script = [&](int mode, int it) {
+      k_orient_arm_script<<<G, T, 0, E->stream>>>(E->scene, n, I64(SDX_T_RESET), mode, it, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+                                                  F(SDX_T_BRICK), F(SDX_T_TARGET_INIT));
+      E->launches++;
+    };
+    auto state = [&](int phase) {
+      k_orient_reset<<<n, 128, 0, E->stream>>>(E->scene, n, E->seed, E->bank, E->per_type, phase, F(SDX_T_BRICK), F(SDX_T_DOF),
+                                               F(SDX_T_TARGET_INIT), I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES),
+                                               I32(SDX_T_EPISODE), I32(SDX_T_WSN), (unsigned char*)E->buf[SDX_T_SLEEP]);
+      E->launches++;
+    };
+    auto sim = [&]() -> int { E->last_reset_sim_steps++; return sdx_simulate(E); };
+    if (E->total_steps > 0) {
+      for (int i = 0; i < 50; ++i) { script(0, i); if (sim()) return -1; }
+      if (orient_observe(E, 0)) return -1;
+      if (E->ob_wrap > 0) {
+        k_orient_bank_slots<<<8, 256, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), E->finger_dist, F(SDX_T_TVALUE), E->ob_index, E->ob_wrap, E->ob_slot);
+        k_orient_bank_write<<<n, 96, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), E->ob_slot, E->ob_rows, E->ob_wrap);
+        E->launches += 2;
+      }
+    }
+    state(0);
+    if (sim() || sim()) return -1;
+    state(1);
+    if (sim()) return -1;
+    for (int i = 0; i < 50; ++i) { script(1, i); if (sim()) return -1; }
+    state(2);
+  }
+  k_orient_pre_physics<<<G, T, 0, E->stream>>>(E->scene, n, actions_dev, F(SDX_T_ACTIONS), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+                                               F(SDX_T_BRICK), I64(SDX_T_PROGRESS), F(SDX_T_TARGET_INIT));
+  E->launches++;
+  CKL();
+  return 0;
+}
+
+extern "C" int sdx_orient_heap_bank(sdx_env_t* E, int capacity, void** rows_dev, void** index_dev) {
+  CK(cudaSetDevice(E->device));
+  if (E->task != SDX_TASK_ORIENT) { g_err = "sdx_orient_heap_bank: the env does not run BlockAssemblyOrient"; return -1; }
+  if (capacity > 0 && capacity != E->ob_wrap) {
+    CK(cudaStreamSynchronize(E->stream));
+    cudaFree(E->ob_rows); cudaFree(E->ob_index);
+    size_t bytes = (size_t)8 * (capacity + 1) * NB * 13 * 4;
+    CK(cudaMalloc(&E->ob_rows, bytes)); CK(cudaMemset(E->ob_rows, 0, bytes));
+    CK(cudaMalloc(&E->ob_index, 32)); CK(cudaMemset(E->ob_index, 0, 32));
+    E->ob_wrap = capacity;
+  }
+  if (capacity == 0) E->ob_wrap = 0;
+  if (rows_dev) *rows_dev = E->ob_rows;
+  if (index_dev) *index_dev = E->ob_index;
+  return 0;
+}
+extern "C" int sdx_last_reset_sim_steps(const sdx_env_t* E) { return E->last_reset_sim_steps; }
+
 extern "C" int sdx_post_physics(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
   const int n = E->n;
+  if (E->task == SDX_TASK_ORIENT) {
+    if (orient_observe(E, 1)) return -1;
+    k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
+    E->launches++;
+    E->total_steps++;
+    CKL();
+    return 0;
+  }
   k_post_physics<<<(n + POST_WARPS - 1) / POST_WARPS, 32 * POST_WARPS, 0, E->stream>>>(
       E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_ACTIONS), F(SDX_T_TARGET_INIT), I64(SDX_T_PROGRESS),
       I64(SDX_T_RESET), F(SDX_T_OBS), F(SDX_T_STATES), F(SDX_T_REW), E->qcam, E->finger_dist, F(SDX_T_SUCCESSES), E->red_count, E->red_sum);
-  k_tvalue<<<(n + TV_ENVS * TV_WARPS - 1) / (TV_ENVS * TV_WARPS), 32 * TV_WARPS, 0, E->stream>>>(E->tvw, n, E->qcam, F(SDX_T_TVALUE));
+  k_tvalue<<<(n + TV_ENVS * TV_WARPS - 1) / (TV_ENVS * TV_WARPS), 32 * TV_WARPS, 0, E->stream>>>(E->tvw, n, E->qcam, F(SDX_T_TVALUE), 0.0f);
   k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
   E->launches += 3;
   E->total_steps++;
@@ -310,7 +412,7 @@ extern "C" int sdx_step_host(sdx_env_t* E, const float* actions_host, float* obs
   const size_t n = E->n;
   CK(cudaMemcpyAsync(E->stage_actions, actions_host, n * 23 * 4, cudaMemcpyHostToDevice, E->stream));
   if (sdx_step(E, E->stage_actions)) return -1;
-  const size_t no = n * 3 * SDX_OBS_FRAME, ns = n * 3 * SDX_STATE_FRAME;
+  const size_t no = n * 3 * obs_frame(E), ns = n * 3 * SDX_STATE_FRAME;
   k_clamp_copy<<<(unsigned)((no + 255) / 256), 256, 0, E->stream>>>(F(SDX_T_OBS), E->stage_obs, no, 5.0f);
   k_clamp_copy<<<(unsigned)((ns + 255) / 256), 256, 0, E->stream>>>(F(SDX_T_STATES), E->stage_states, ns, 5.0f);
   E->launches += 2;

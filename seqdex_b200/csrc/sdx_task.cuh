@@ -382,7 +382,7 @@ __global__ void k_finalize(const sdx_scene_t* __restrict__ S, int* __restrict__ 
 #define TV_ENVS 4
 #define TV_WARPS 4
 __global__ void __launch_bounds__(32 * TV_WARPS)
-k_tvalue(const float* __restrict__ wts, int n, const float* __restrict__ qcam, float* __restrict__ tvalue) {
+k_tvalue(const float* __restrict__ wts, int n, const float* __restrict__ qcam, float* __restrict__ tvalue, float thresh) {
   __shared__ float h1[TV_WARPS][TV_ENVS][256];
   __shared__ float h2[TV_WARPS][TV_ENVS][128];
   __shared__ float h3[TV_WARPS][TV_ENVS][64];
@@ -455,7 +455,8 @@ k_tvalue(const float* __restrict__ wts, int n, const float* __restrict__ qcam, f
     float a = b4[1];
     for (int k = 0; k < 64; ++k) a = a + W4[64 + k] * h3[wid][lane][k];
     a = sdx_elu(a);
-    tvalue[e0 + lane] = 1.0f / (1.0f + sdx_exp(-a));
+    const float v = 1.0f / (1.0f + sdx_exp(-a));
+    tvalue[e0 + lane] = thresh > 0.0f ? (v > thresh ? 1.0f : 0.0f) : v;   // Orient keeps only the thresholded gate (OR:1203-1205)
   }
 }
 

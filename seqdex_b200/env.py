@@ -140,6 +140,21 @@ class SdxEnv:
         ns, nf = (min(int(x), self._tvd_cap) for x in counts.tolist())
         return self._view(s.value, (self._tvd_cap, 4))[:ns], self._view(f.value, (self._tvd_cap, 4))[:nf], counts
 
+    def enable_orient_heap_bank(self, capacity=10000):
+        """record the heaps BlockAssemblyOrient leaves face up (saved_digging_ternimal_states_list, OR:1465-1481); capacity is the
+        slot after which the ring index returns to 0 (10000 in the reference)"""
+        _lib.check(self.L.sdx_orient_heap_bank(self.h, int(capacity), None, None))
+        self._ob_wrap = int(capacity)
+
+    def orient_heap_bank(self):
+        """(rows [8, capacity + 1, 72, 13], index [8] i32) of the re-oriented heap rings"""
+        r, i = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self.L.sdx_orient_heap_bank(self.h, self._ob_wrap, ctypes.byref(r), ctypes.byref(i)))
+        return self._view(r.value, (8, self._ob_wrap + 1, 72, 13)), self._view(i.value, (8,), "<i4")
+
+    def last_reset_sim_steps(self):
+        return int(self.L.sdx_last_reset_sim_steps(self.h))
+
     def brick_roots(self):
         """[N, 72, 13] Isaac-Gym root rows of the free bricks (actors 9..80 of the root tensor)."""
         self.refresh("ROOT")

@@ -1,1 +1,2 @@
 from .block_assembly_grasp_sim import BlockAssemblyGraspSim  # noqa: F401
+from .block_assembly_orient import BlockAssemblyOrient  # noqa: F401
