@@ -173,6 +173,14 @@ int sdx_aux(sdx_env_t* env, void** qcam_dev, void** finger_dist_dev);
 int sdx_orient_heap_bank(sdx_env_t* env, int capacity, void** rows_dev, void** index_dev);
 /* number of contact steps the last sdx_pre_physics spent inside reset_idx (0 when nobody reset; 103 for a full Orient reset) */
 int sdx_last_reset_sim_steps(const sdx_env_t* env);
+/* BlockAssemblySearch's camera features (SE = tasks/block_assembly/allegro_hand_block_assembly_search.py): the reference renders
+ * a 128x128 segmentation image per env (gym.create_camera_sensor / set_camera_location / get_camera_image_gpu_tensor
+ * IMAGE_SEGMENTATION, SE:755-758, 873-878) and keeps three integers of it -- the number of pixels that show the target brick
+ * and the centroid (row, column) of those pixels (SE:1231-1241, 1640-1646).  sdx_segmentation_features computes exactly those
+ * by ray casting against the scene's boxes.  The camera is a pinhole: unit vectors fwd / right / up (right = fwd x world-up,
+ * up = right x fwd), inv_focal = tan(horizontal_fov / 2) / (width / 2) (Isaac Gym's default horizontal_fov is 90 degrees). */
+typedef struct sdx_camera_t { float pos[3], fwd[3], right[3], up[3]; float inv_focal; int width, height; } sdx_camera_t;
+int sdx_segmentation_features(sdx_env_t* env, const sdx_camera_t* cam, int32_t* out_dev /* [N][3]: pixels, centre row, centre column */);
 int sdx_scene_size(void);
 int sdx_sim_smem_bytes(void);
 

@@ -138,6 +138,12 @@ class OracleEnv:
         self.bank = np.ascontiguousarray(bank, np.float32)
         self.per_type = bank.shape[1]
 
+    def segmentation_features(self, cam):
+        """[n, 3] int32: pixels showing the target brick, int(mean row), int(mean column) (SE:1231-1241)"""
+        out = np.zeros((self.n, 3), np.int32)
+        self.L.sdxo_segmentation_features(self.S, self.n, ctypes.byref(cam), fp(self.brick), fp(self.link), ip(out))
+        return out
+
     # ---- BaseTask.step phases
     def simulate(self, dump=False):
         self.L.sdxo_simulate(self.S, self.n, fp(self.brick), fp(self.dof), fp(self.link), fp(self.jac7), fp(self.netf),

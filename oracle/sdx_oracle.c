@@ -1233,5 +1233,87 @@ void sdxo_orient_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* 
   }
 }
 
+
+/* ================================================================== Search's camera features
+ * SE = tasks/block_assembly/allegro_hand_block_assembly_search.py.  The reference renders a 128 x 128 segmentation image per env
+ * (Isaac Gym camera sensor, SE:755-758, 873-878) and keeps the number of pixels showing the target brick and the centroid
+ * (row, column) of those pixels (SE:1231-1241, 1640-1646).  Restated as ray casting against the scene's oriented boxes:
+ * a pixel shows the target iff its ray hits the target box and no other box earlier.  PARITY UNPINNED against the reference
+ * (Isaac Gym's rasteriser is a closed binary and renders the brick MESHES, we render their bounding boxes); pinned by the
+ * analytic cases in tests/test_camera_cpu.py.  out [n][3] = pixels, int(mean row), int(mean column). */
+typedef struct sdx_camera_t { float pos[3], fwd[3], right[3], up[3]; float inv_focal; int width, height; } sdx_camera_t;
+static int ray_box(v3 o, v3 d, v3 c, const float* R, v3 h, float* t_entry) {
+  v3 ol = mtmul(R, vsub(o, c));
+  v3 dl = mtmul(R, d);
+  float tmin = -3.0e38f, tmax = 3.0e38f;
+  const float oa[3] = {ol.x, ol.y, ol.z}, da[3] = {dl.x, dl.y, dl.z}, ha[3] = {h.x, h.y, h.z};
+  for (int a = 0; a < 3; ++a) {
+    if (da[a] == 0.0f) { if (oa[a] < -ha[a] || oa[a] > ha[a]) return 0; }
+    else {
+      float inv = 1.0f / da[a];
+      float t1 = (-ha[a] - oa[a]) * inv, t2 = (ha[a] - oa[a]) * inv;
+      if (t1 > t2) { float s = t1; t1 = t2; t2 = s; }
+      if (t1 > tmin) tmin = t1;
+      if (t2 < tmax) tmax = t2;
+    }
+  }
+  if (tmax < tmin || tmax < 0.0f) return 0;
+  *t_entry = tmin;
+  return 1;
+}
+void sdxo_segmentation_features(const sdx_scene_t* S, int n, const sdx_camera_t* cam, const float* brick, const float* link, int* out) {
+  enum { MAXS = SDX_MAX_BRICKS + SDX_MAX_RSHAPES + SDX_MAX_STATIC };
+  static __thread float sc[MAXS][3], sR[MAXS][9], sh[MAXS][3];
+  const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static, nshape = nbr + nrs + nst;
+  const v3 o = V3(cam->pos[0], cam->pos[1], cam->pos[2]), fw = V3(cam->fwd[0], cam->fwd[1], cam->fwd[2]);
+  const v3 rt = V3(cam->right[0], cam->right[1], cam->right[2]), up = V3(cam->up[0], cam->up[1], cam->up[2]);
+  const int W = cam->width, H = cam->height;
+  for (int e = 0; e < n; ++e) {
+    const float* B = brick + (size_t)e * 13 * NB;
+    const int tb = target_brick(e);
+    for (int b = 0; b < nbr; ++b) {
+      sc[b][0] = B[0 * NB + b]; sc[b][1] = B[1 * NB + b]; sc[b][2] = B[2 * NB + b];
+      q4 q = {B[3 * NB + b], B[4 * NB + b], B[5 * NB + b], B[6 * NB + b]};
+      qmat(q, sR[b]);
+      for (int k = 0; k < 3; ++k) sh[b][k] = S->br_half[3 * b + k];
+    }
+    for (int i = 0; i < nrs; ++i) {
+      int t = nbr + i, L = S->rs_body[i];
+      const float* lr = link + ((size_t)e * SDX_NL + L) * 13;
+      q4 qL = {lr[3], lr[4], lr[5], lr[6]};
+      v3 x = vadd(V3(lr[0], lr[1], lr[2]), qrot(qL, V3(S->rs_c[3 * i], S->rs_c[3 * i + 1], S->rs_c[3 * i + 2])));
+      sc[t][0] = x.x; sc[t][1] = x.y; sc[t][2] = x.z;
+      q4 ql = {S->rs_quat[4 * i], S->rs_quat[4 * i + 1], S->rs_quat[4 * i + 2], S->rs_quat[4 * i + 3]};
+      qmat(qmul(qL, ql), sR[t]);
+      for (int k = 0; k < 3; ++k) sh[t][k] = S->rs_h[3 * i + k];
+    }
+    for (int i = 0; i < nst; ++i) {
+      int t = nbr + nrs + i;
+      for (int k = 0; k < 3; ++k) { sc[t][k] = S->st_c[3 * i + k]; sh[t][k] = S->st_h[3 * i + k]; }
+      for (int k = 0; k < 9; ++k) sR[t][k] = (k % 4 == 0) ? 1.0f : 0.0f;
+    }
+    int cnt = 0, sr = 0, scol = 0;
+    const v3 tc = V3(sc[tb][0], sc[tb][1], sc[tb][2]), th = V3(sh[tb][0], sh[tb][1], sh[tb][2]);
+    for (int r = 0; r < H; ++r)      /* every pixel: the kernel's bounding-rectangle pruning cannot change the result */
+      for (int c = 0; c < W; ++c) {
+        const float sx = (((float)c + 0.5f) - 0.5f * (float)W) * cam->inv_focal;
+        const float sy = -((((float)r + 0.5f) - 0.5f * (float)H) * cam->inv_focal);
+        const v3 d = vadd(vadd(fw, vscale(rt, sx)), vscale(up, sy));
+        float tt;
+        if (!ray_box(o, d, tc, sR[tb], th, &tt)) continue;
+        int occluded = 0;
+        for (int s2 = 0; s2 < nshape && !occluded; ++s2) {
+          if (s2 == tb) continue;
+          float ts;
+          if (ray_box(o, d, V3(sc[s2][0], sc[s2][1], sc[s2][2]), sR[s2], V3(sh[s2][0], sh[s2][1], sh[s2][2]), &ts) && ts < tt) occluded = 1;
+        }
+        if (!occluded) { cnt++; sr += r; scol += c; }
+      }
+    out[3 * e] = cnt;
+    out[3 * e + 1] = cnt > 0 ? (int)((float)sr / (float)cnt) : 0;
+    out[3 * e + 2] = cnt > 0 ? (int)((float)scol / (float)cnt) : 0;
+  }
+}
+
 int sdxo_scene_size(void) { return (int)sizeof(sdx_scene_t); }
 int sdxo_work_size(void) { return (int)sizeof(work_t); }

@@ -11,6 +11,7 @@
 #include "sdx_sim.cuh"
 #include "sdx_task.cuh"
 #include "sdx_task_orient.cuh"
+#include "sdx_camera.cuh"
 
 static thread_local std::string g_err;
 extern "C" const char* sdx_last_error(void) { return g_err.c_str(); }
@@ -464,6 +465,15 @@ extern "C" int sdx_tvalue_dataset(sdx_env_t* E, int capacity, void** succ_dev, v
   if (succ_dev) *succ_dev = E->tvd_succ;
   if (fail_dev) *fail_dev = E->tvd_fail;
   if (counts_dev) *counts_dev = E->tvd_counts;
+  return 0;
+}
+extern "C" int sdx_segmentation_features(sdx_env_t* E, const sdx_camera_t* cam, int32_t* out_dev) {
+  CK(cudaSetDevice(E->device));
+  if (!cam || !out_dev || cam->width <= 0 || cam->height <= 0 || cam->width > 4096 || cam->height > 4096) { g_err = "sdx_segmentation_features: bad camera"; return -1; }
+  if (E->host_scene.n_bricks + E->host_scene.n_rshapes + E->host_scene.n_static > CAM_MAX_SHAPES) { g_err = "sdx_segmentation_features: scene exceeds the shape table"; return -1; }
+  k_seg_features<<<E->n, 128, 0, E->stream>>>(E->scene, E->n, *cam, F(SDX_T_BRICK), F(SDX_T_LINK), out_dev);
+  E->launches++;
+  CKL();
   return 0;
 }
 extern "C" int sdx_aux(sdx_env_t* E, void** qcam_dev, void** finger_dist_dev) { *qcam_dev = E->qcam; *finger_dist_dev = E->finger_dist; return 0; }

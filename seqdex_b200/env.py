@@ -155,6 +155,14 @@ class SdxEnv:
     def last_reset_sim_steps(self):
         return int(self.L.sdx_last_reset_sim_steps(self.h))
 
+    def segmentation_features(self, cam, out=None):
+        """Search's camera features (SE:1231-1241, 1640-1646) for the camera ``cam`` (seqdex_b200.camera.look_at):
+        int32 [N, 3] = pixels that show the target brick, int(mean row), int(mean column)"""
+        if out is None:
+            out = torch.zeros(self.n, 3, dtype=torch.int32, device=self.device)
+        _lib.check(self.L.sdx_segmentation_features(self.h, ctypes.byref(cam), ctypes.c_void_p(out.data_ptr())))
+        return out
+
     def brick_roots(self):
         """[N, 72, 13] Isaac-Gym root rows of the free bricks (actors 9..80 of the root tensor)."""
         self.refresh("ROOT")
