@@ -50,6 +50,46 @@ def load_heap_bank(path):
         return heap_bank_from_reference(pickle.load(f))
 
 
+def orient_bank_valid(env):
+    """the heaps BlockAssemblyOrient banked so far as ``[8, K, 72, 13]`` on the device (K = the fewest any type holds; a ring
+    that has wrapped counts as full) -- what the NEXT stage of the chain samples on reset (GS:412-413, 1507-1511)"""
+    rows, index = env.orient_heap_bank()
+    torch.cuda.synchronize(env.device)
+    idx = index.cpu().tolist()
+    ring = rows.shape[1]
+    filled = [ring if bool(rows[t, ring - 1].abs().sum() > 0) else idx[t] for t in range(8)]     # last slot written <=> wrapped
+    k = min(filled)
+    if k == 0:
+        raise RuntimeError(f"BlockAssemblyOrient has banked no heap yet for some brick type (per-type counts {filled})")
+    out = rows[:, :k].clone()
+    out[..., 7:13] = 0
+    return out.contiguous()
+
+
+def orient_bank_to_reference(env, scene, rows_per_type=10000 + 1024):
+    """``saved_digging_ternimal_states_list`` as the reference pickles it (OR:1510-1512 ->
+    ``saved_searching_ternimal_states_good_mo_tvalue.pkl``, loaded by GraspSim GS:412-413): ``list[8]`` of
+    ``Tensor[11024, 132, 13]``, rows beyond what has been banked left at zero (OR:404-411 preallocates them)"""
+    rows, _ = env.orient_heap_bank()
+    torch.cuda.synchronize(env.device)
+    rows = rows.cpu()
+    fixed = torch.from_numpy(np.ctypeslib.as_array(scene.c.fixed_root).reshape(N_FIXED, 13).astype(np.float32))
+    out = []
+    for ty in range(8):
+        t = torch.zeros(rows_per_type, N_FREE + N_FIXED, 13)
+        k = min(rows.shape[1], rows_per_type)
+        t[:k, :N_FREE] = rows[ty, :k]
+        written = rows[ty, :k].abs().sum(dim=(1, 2)) > 0
+        t[:k, N_FREE:][written] = fixed
+        out.append(t)
+    return out
+
+
+def save_orient_heap_bank(env, scene, path):
+    with open(path, "wb") as f:
+        pickle.dump(orient_bank_to_reference(env, scene), f)
+
+
 def grasp_bank_to_reference(env):
     """device rings of an ``SdxEnv`` -> (hand list[8] of [11024, 23, 2], object list[8] of [11024, 1, 13]) on the CPU"""
     hand, obj, _ = env.grasp_bank()

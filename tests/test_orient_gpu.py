@@ -190,3 +190,48 @@ def test_orient_task_and_ppo_smoke(oscene):
     assert all(math.isfinite(v) for v in info.values()), info
     assert 0.0 < info["mean_reward"] <= 1.0                  # exp(-(5 z + 5 d)) (OR:1893)
     assert int(task.progress_buf[0]) == 9                    # reset() step + 8 rollout steps
+
+
+def test_chain_hand_off_orient_to_grasp_sim(oscene, scene, tmp_path):
+    """the link of the chain GraspSim depends on (GS:412-413): the heaps Orient leaves face up, in the reference's pickle layout
+    (list[8] of Tensor[11024, 132, 13]) and directly on the device, become the bank GraspSim samples on reset"""
+    import pickle
+    from seqdex_b200 import bank_io
+    from seqdex_b200.env import SdxEnv
+    from seqdex_b200.tasks.block_assembly_grasp_sim import default_tvalue_weights
+    n = 32
+    w = default_tvalue_weights(1)
+    w[-1] += 50.0                                            # gate open: every heap with the brick in the near half is banked
+    g = SdxEnv(oscene, n)
+    g.set_tvalue_weights(w)
+    g.set_heap_bank(lattice_bank(oscene, 2))
+    g.enable_orient_heap_bank(16)
+    a = torch.zeros(n, 23, device="cuda")
+    g.step(a)
+    for _ in range(2):                                       # two lockstep resets -> up to 8 heaps per brick type
+        g.tensor("RESET").fill_(1)
+        g.step(a)
+    bank = bank_io.orient_bank_valid(g)
+    assert bank.shape[0] == 8 and bank.shape[2:] == (72, 13) and bank.shape[1] >= 2 and float(bank[..., 7:13].abs().max()) == 0
+    p = tmp_path / "saved_searching_ternimal_states_good_mo_tvalue.pkl"
+    bank_io.save_orient_heap_bank(g, oscene, p)
+    with open(p, "rb") as f:
+        ref = pickle.load(f)
+    assert len(ref) == 8 and all(tuple(t.shape) == (11024, 132, 13) for t in ref)
+    k = bank.shape[1]
+    for ty in range(8):
+        assert torch.equal(ref[ty][:k, :72, 0:7], bank[ty].cpu()[..., 0:7])
+        assert torch.equal(ref[ty][0, 72:], torch.from_numpy(np.ctypeslib.as_array(oscene.c.fixed_root).reshape(60, 13).copy()))
+    back = bank_io.load_heap_bank(p)                         # what GraspSim's loader makes of the file: K = 11024 rows, zeros beyond
+    assert torch.equal(back[:, :k], bank.cpu())
+    # next stage: GraspSim resets from exactly these heaps
+    gs = SdxEnv(scene, n)
+    gs.set_tvalue_weights(default_tvalue_weights(1))
+    gs.set_heap_bank(bank)
+    gs.pre_physics(a)                                        # reset_idx (all reset flags start at 1, BT:63)
+    roots = gs.brick_roots().cpu()
+    for e in range(n):
+        match = [torch.equal(roots[e, :, 0:7], bank[e % 8, s].cpu()[:, 0:7]) for s in range(k)]
+        # root row -> COM block -> root row round-trips to the last bit only for axis-aligned bricks; allow 1e-6
+        close = [float((roots[e, :, 0:7] - bank[e % 8, s].cpu()[:, 0:7]).abs().max()) < 1e-6 for s in range(k)]
+        assert any(match) or any(close), e
