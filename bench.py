@@ -71,16 +71,17 @@ PRE_STEPS = 80          # untimed steps after staggering: every env has been thr
 STAGGER = 75            # an untrained policy's episodes end at progress 75 (GS:1751: far from the target after 75 steps)
 
 
-def precondition_cpu(env, rng):
+def precondition_cpu(env, rng, stagger=True):
     """same episode-phase mix as the GPU arm: first step resets every env, then progress ~ U[0, 75), then PRE_STEPS steps"""
     n = env.n
     env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
-    env.progress[:] = rng.integers(0, STAGGER, size=n)
+    if stagger:
+        env.progress[:] = rng.integers(0, STAGGER, size=n)
     for _ in range(PRE_STEPS):
         env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
 
 
-def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None):
+def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None, stagger=True):
     """the oracle (CPU port of the same hot path) on the host cores, bounded sample of the same workload"""
     from oracle import oracle
     oracle.build()
@@ -89,7 +90,7 @@ def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None):
     env = oracle.OracleEnv(scene, n)
     env.set_heap_bank(bank)
     rng = np.random.default_rng(0)
-    precondition_cpu(env, rng)
+    precondition_cpu(env, rng, stagger)
     t0, steps = time.time(), 0
     while time.time() - t0 < seconds or steps < 2:
         env.step(rng.uniform(-1, 1, size=(n, 23)).astype(np.float32))
@@ -144,7 +145,7 @@ def run_reference(args):
     val = n * args.steps / dt
     sample = (f"{n} envs per step (bounded sample of the {args.num_envs}-env workload), C oracle on {cores} host threads, "
               f"episodes staggered + {PRE_STEPS} untimed steps first")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "env-steps/sec at num_envs=16384 (BlockAssemblyGraspSim)", "value": val, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -152,10 +153,33 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": int(cores), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Isaac Gym (closed binary) is not installable here; this arm times the repo's CPU oracle of the same path",
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """the contract is ONE JSON line on stdout: anything libraries print there (NCCL's version banner, torchrun notices) is
+    routed to stderr by pointing fd 1 at fd 2; emit() writes the line to the saved descriptor"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.write(line + "\n")
+        _REAL_STDOUT.flush()
+    else:
+        print(line)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=160)
@@ -168,6 +192,9 @@ def main():
     ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
                     help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
                          "rollout: VecTask.step only with U(-1,1) actions")
+    ap.add_argument("--task", default="grasp_sim", choices=["grasp_sim", "orient"],
+                    help="grasp_sim: BlockAssemblyGraspSim, the BASELINE.json metric (configs[1]); orient: BlockAssemblyOrient (configs[2]: "
+                         "32768 envs over 2 GPUs = --gpus 2 with the default 16384 envs per GPU)")
     ap.add_argument("--minibatch", type=int, default=32768,
                     help="PPO minibatch; the yaml's 4 is a 4-env smoke value (SURVEY.md section 7): default = batch/4 at 16384 envs x horizon 8")
     args = ap.parse_args()
@@ -188,7 +215,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = args.num_envs
-    scene = Scene()
+    orient = args.task == "orient"
+    # Orient's reset_idx is a script over the WHOLE sim (103 extra contact steps whenever any env resets, OR:1390-1695), so its
+    # episodes run in lockstep as in the reference (time-outs only); GraspSim's per-env resets are staggered (see below)
+    scene = Scene(task="BlockAssemblyOrient", episode_length=75, act_moving_average=0.2) if orient else Scene()
+    task_name = "BlockAssemblyOrient" if orient else "BlockAssemblyGraspSim"
+    obs_dim = 186 if orient else 396
     bank = make_heap_bank(scene, args.bank_per_type, local, seed=22 + rank)
     env = SdxEnv(scene, n, local, seed=22 + rank)
     env.set_heap_bank(bank)
@@ -210,7 +242,8 @@ def main():
     # PRE_STEPS steps, so that resets -- and with them the waking / falling asleep of the heaps -- are spread over time
     # as they are in a long training run instead of all envs marching through one episode in lockstep
     env.step(acts[0])
-    env.tensor("PROGRESS").copy_(torch.randint(0, STAGGER, (n,), device=dev, generator=gen))
+    if not orient:
+        env.tensor("PROGRESS").copy_(torch.randint(0, STAGGER, (n,), device=dev, generator=gen))
     for i in range(PRE_STEPS):
         env.step(torch.rand(n, 23, device=dev, generator=gen) * 2 - 1)
     for i in range(W):
@@ -244,7 +277,7 @@ def main():
         class _Task:      # the task surface VecTask needs, over the SAME env (no second simulation state)
             pass
         task = _Task()
-        task.env, task.num_envs, task.num_obs, task.num_states, task.num_actions, task.device = env, n, 396, 564, 23, f"cuda:{local}"
+        task.env, task.num_envs, task.num_obs, task.num_states, task.num_actions, task.device = env, n, obs_dim, 564, 23, f"cuda:{local}"
         task.obs_buf, task.states_buf, task.rew_buf, task.reset_buf = (env.tensor(k) for k in ("OBS", "STATES", "REW", "RESET"))
         task.extras = {}
         step_ev = []                    # CUDA events around every VecTask.step of the timed PPO iterations
@@ -279,7 +312,7 @@ def main():
     E = args.e2e_steps
     h_act = torch.empty(n, 23, dtype=torch.float32).pin_memory()
     h_act.copy_(acts[0].cpu())
-    h_obs = torch.empty(n, 396, dtype=torch.float32).pin_memory()
+    h_obs = torch.empty(n, obs_dim, dtype=torch.float32).pin_memory()
     h_st = torch.empty(n, 564, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
     h_rs = torch.empty(n, dtype=torch.int64).pin_memory()
@@ -305,22 +338,24 @@ def main():
         peak, which = measured_peaks()
         achieved = ALGO_BYTES_PER_ENV_STEP * n / (sim_ms * 1e-3) / 1e9
         out = {
-            "metric": "env-steps/sec at num_envs=16384 (BlockAssemblyGraspSim)", "value": world * n * K / (ms * 1e-3),
+            "metric": f"env-steps/sec at num_envs=16384 ({task_name})", "value": world * n * K / (ms * 1e-3),
             "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"BlockAssemblyGraspSim num_envs={n} per GPU, PPO bf16: every 8 env steps (policy + central-value forward, "
+            "config": {"workload": (f"{task_name} num_envs={n} per GPU, PPO bf16: every 8 env steps (policy + central-value forward, "
                                     "VecTask.step = reset_idx + IK + contact step 2x16 + obs/reward/t-value) then GAE and "
                                     f"5 mini-epochs x {8 * n // min(args.minibatch, 8 * n)} minibatches for actor and central value"
                                     if args.mode == "ppo" else
-                                    f"BlockAssemblyGraspSim num_envs={n} per GPU, rollout only: VecTask.step, U(-1,1) actions"),
+                                    f"{task_name} num_envs={n} per GPU, rollout only: VecTask.step, U(-1,1) actions"),
                        "mode": args.mode, "minibatch": min(args.minibatch, 8 * n),
                        "num_envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "env state (260 MB at 16384 envs) exceeds the 126 MB L2; no explicit flush",
                        "heap_bank_per_type": args.bank_per_type,
-                       "episodes": f"staggered: progress ~ U[0,{STAGGER}) then {PRE_STEPS} untimed steps before warm-up (stationary mix of "
-                                   "fresh and settled heaps; resting bricks sleep with PhysX's default threshold and 0.4 s timer)"},
+                       "episodes": (f"lockstep as in the reference (time-outs every 75 steps; each reset runs the 103-step scripted reset_idx "
+                                    f"of OR:1390-1695 inside the timed region); {PRE_STEPS} untimed steps before warm-up" if orient else
+                                    f"staggered: progress ~ U[0,{STAGGER}) then {PRE_STEPS} untimed steps before warm-up (stationary mix of "
+                                    "fresh and settled heaps; resting bricks sleep with PhysX's default threshold and 0.4 s timer)")},
             "e2e": {"value": world * n * E / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 23 * 4,
-                    "d2h_bytes_per_step": n * (396 + 564 + 1) * 4 + n * 8, "steps": E},
+                    "d2h_bytes_per_step": n * (obs_dim + 564 + 1) * 4 + n * 8, "steps": E},
             "gpu_launches": int(launches),
             "rollout_only": {"value": world * n * KR / (ro_ms * 1e-3), "unit": "env-steps/s", "steps": KR, "ms_per_step": ro_ms / KR},
             "ppo": ppo_info,
@@ -335,8 +370,8 @@ def main():
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
         }
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(scene, bank=bank[:, :2].cpu().numpy())
-        print(json.dumps(out))
+            out["cpu_baseline"] = cpu_baseline(scene, bank=bank[:, :2].cpu().numpy(), stagger=not orient, n_envs=1024 if orient else None)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
