@@ -309,7 +309,7 @@ def main():
         ppo_info["bricks_asleep_frac_start_end"] = [asleep0, float((env.tensor("SLEEP") >= max(scene.c.sleep_substeps, 1)).float().mean())]
         launches = (env.launch_count() - l0 + ppo_launch() - p0) * K // (iters * H)
     # ---- end to end through the C-ABI with HOST buffers (sdx_step_host): H2D actions, D2H obs/states/rew/reset
-    E = args.e2e_steps
+    E = 75 if orient and args.e2e_steps >= 32 else args.e2e_steps   # Orient: one whole episode, so one scripted reset is inside
     h_act = torch.empty(n, 23, dtype=torch.float32).pin_memory()
     h_act.copy_(acts[0].cpu())
     h_obs = torch.empty(n, obs_dim, dtype=torch.float32).pin_memory()
