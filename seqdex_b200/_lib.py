@@ -7,7 +7,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libseqdex_b200.so")
+SO_PATH = os.environ.get("SEQDEX_B200_LIB") or os.path.join(_HERE, "libseqdex_b200.so")   # override: A/B builds of the same sources
 CSRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-fmad=false",            # rounding contract of the contact step (csrc/sdx_math.cuh)

@@ -48,6 +48,7 @@ struct sdx_env {
   int* ob_slot = nullptr;          // [n] ring slot of each env in the current banking call
   float* ob_rows = nullptr; int* ob_index = nullptr; int ob_wrap = 0;   // re-oriented heap rings (sdx_orient_heap_bank)
   int last_reset_sim_steps = 0;
+  float4* cscratch = nullptr;      // [n][2][MAXC] contact records of k_simulate (SIM_GLOBAL_CONTACTS)
 };
 static int obs_frame(const sdx_env* E) { return E->task == SDX_TASK_ORIENT ? SDX_ORIENT_OBS_FRAME : SDX_OBS_FRAME; }
 
@@ -121,6 +122,9 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaMalloc(&E->stage_obs, n * 3 * obs_frame(E) * 4));
   CK(cudaMalloc(&E->stage_states, n * 3 * SDX_STATE_FRAME * 4));
   CK(cudaMalloc(&E->stage_actions, n * 23 * 4));
+#if SIM_GLOBAL_CONTACTS
+  CK(cudaMalloc(&E->cscratch, n * 2 * MAXC * sizeof(float4)));
+#endif
   CK(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
   *out = E;
   return sdx_reset_all(E);
@@ -134,6 +138,7 @@ extern "C" void sdx_destroy(sdx_env_t* E) {
   cudaFree(E->scene); cudaFree(E->qcam); cudaFree(E->finger_dist); cudaFree(E->static_rows); cudaFree(E->bank); cudaFree(E->tvw);
   cudaFree(E->gb_hand); cudaFree(E->gb_obj); cudaFree(E->gb_index); cudaFree(E->red_count); cudaFree(E->red_sum);
   cudaFree(E->stage_obs); cudaFree(E->stage_states); cudaFree(E->stage_actions);
+  cudaFree(E->cscratch);
   cudaFree(E->flag_count); cudaFreeHost(E->flag_count_host); cudaFree(E->ob_slot); cudaFree(E->ob_rows); cudaFree(E->ob_index);
   delete E;
 }
@@ -291,7 +296,7 @@ extern "C" int sdx_simulate(sdx_env_t* E) {
   k_simulate<<<E->n, SIM_THREADS, sizeof(SimSmem), E->stream>>>(E->scene, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
                                                               F(SDX_T_NETF), I32(SDX_T_NCONTACT),
                                                               E->dump_contacts ? F(SDX_T_CONTACTS) : nullptr, F(SDX_T_WS), I32(SDX_T_WSN),
-                                                              E->ws_cur, (unsigned char*)E->buf[SDX_T_SLEEP], E->n);
+                                                              E->ws_cur, (unsigned char*)E->buf[SDX_T_SLEEP], E->n, E->cscratch);
   E->ws_cur ^= (E->host_scene.substeps & 1);
   E->launches++;
   CKL();

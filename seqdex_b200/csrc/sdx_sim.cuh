@@ -31,7 +31,17 @@
 #ifndef SIM_THREADS
 #define SIM_THREADS 256
 #endif
-#define SIM_MIN_CTAS 3                 /* CTAs per SM the register budget is sized for */
+// SIM_GLOBAL_CONTACTS: the two contact-record arrays that are READ-ONLY during the solver iterations (point | bias and
+// inverse masses | packed word, 32 KB per env at MAXC = 1024) live in global memory behind L1 instead of shared memory:
+// 42.6 KB of shared memory per CTA instead of 74.6 KB and a 64-register budget put FOUR CTAs on an SM instead of three.
+// (line-level ncu: 45 % of the warp stall samples are block-barrier waits, the issue slots are busy 42 % of the time --
+// resident warps are the lever)  Same arithmetic, same results.
+#ifndef SIM_GLOBAL_CONTACTS
+#define SIM_GLOBAL_CONTACTS 1
+#endif
+#ifndef SIM_MIN_CTAS
+#define SIM_MIN_CTAS (SIM_GLOBAL_CONTACTS ? 4 : 3)   /* CTAs per SM the register budget is sized for */
+#endif
 #define ROBOT_TID0 (SIM_THREADS - 32)  /* the LAST warp owns the articulation: lane j = DoF j, lane L = link L */
 #define PPMAX 26                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
 
@@ -61,10 +71,15 @@ struct SimSmem {
   unsigned char alist[NB]; int nact;   // bricks phase B has to visit: awake AND touched by at least one contact (ascending)
   unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
   // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
+#if !SIM_GLOBAL_CONTACTS
   float4 ca[MAXC];    // contact point w.xyz | bias
   float4 cb[MAXC];    // 1/den along n, t1, t2 | packed word (bodies, target shape, face axis, sign)
-  float4 cf4[MAXC];   // total impulse f.xyz | unused
+#endif
+  float4 cf4[MAXC];   // total impulse f.xyz | unused          (also scratch: candidate overflow lists, pair tables)
 };
+
+static_assert(NOWN * KC * 2 <= 8192 && 8192 + NOWN * KC * 2 <= MAXC * 16 && NOWN * KC + NOWN * 4 <= MAXC * 16,
+              "the pair tables / candidate overflow lists are laid out inside the impulse array (cf4)");
 
 // exclusive prefix sum of arr[0..n) (n <= 256) by ONE warp, in place; returns the total to every lane
 __device__ __forceinline__ int warp_excl_scan(int* arr, int n, int lane) {
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
            int* __restrict__ ncontact, float* __restrict__ condump, float* ws, int* wsn, int ws_cur,
-           unsigned char* __restrict__ slp, int n_envs) {
+           unsigned char* __restrict__ slp, int n_envs, float4* cscratch /* [n_envs][2][MAXC] when SIM_GLOBAL_CONTACTS */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SimSmem& M = *reinterpret_cast<SimSmem*>(smem_raw);
   const int e = blockIdx.x, tid = threadIdx.x;
@@ -236,6 +251,14 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   const float margin = S->contact_offset;
   float* gbrick = brick + (size_t)e * 13 * NB;
   float* gdof = dof + (size_t)e * 72;
+#if SIM_GLOBAL_CONTACTS
+  float4* const CA = cscratch + (size_t)e * 2 * MAXC;   // plain (coherent, L1-cached) loads / stores: written and read by this CTA only
+  float4* const CB = CA + MAXC;
+#else
+  float4* const CA = M.ca;
+  float4* const CB = M.cb;
+#endif
+  unsigned char* const cf_bytes = reinterpret_cast<unsigned char*>(&M.cf4[0]);   // 16 KB of scratch while the impulses are not live
 
   // ---- TMA bulk load of the env's brick tile into shared memory
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&M.mbar);
@@ -371,8 +394,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     //    half's hits go to a scratch list (in the idle impulse array) and are appended in target order, so the candidate
     //    lists -- including what overflows KC -- are the ones a single ascending sweep produces
     {
-      unsigned char* tmpc = reinterpret_cast<unsigned char*>(&M.cf4[0]);   // [NOWN][KC]
-      int* tmpn = reinterpret_cast<int*>(&M.cb[0]);                         // [NOWN]
+      unsigned char* tmpc = cf_bytes;                                       // [NOWN][KC]
+      int* tmpn = reinterpret_cast<int*>(cf_bytes + NOWN * KC);             // [NOWN]
       const int a = tid & 127, half = tid >> 7;
       if (a < n_owner) {
         int k = 0, dropped = 0;
@@ -427,8 +450,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     const int npairs = M.poff[n_owner];
     const int PP = (npairs + SIM_THREADS - 1) / SIM_THREADS;
     const int p0 = tid * PP, p1 = min(npairs, p0 + PP);
-    unsigned short* pmask = reinterpret_cast<unsigned short*>(&M.cf4[0]);     // [npairs] <= 3328 * 2 B < 16 KB
-    unsigned short* pstart = reinterpret_cast<unsigned short*>(&M.cb[0]);     // [npairs]
+    unsigned short* pmask = reinterpret_cast<unsigned short*>(cf_bytes);          // [npairs] <= 3328 * 2 B < 8 KB
+    unsigned short* pstart = reinterpret_cast<unsigned short*>(cf_bytes + 8192);  // [npairs]
     int mycount = 0;
     {
       int a = 0;
@@ -496,8 +519,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         float bias = 0.0f;
         if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
         else if (depth < 0.0f) bias = depth / h;
-        M.ca[slot] = make_float4(wpt.x, wpt.y, wpt.z, bias);
-        M.cb[slot] = make_float4(depth, 0.0f, 0.0f, __uint_as_float(wdn));   // .x carries the depth until the inverse masses are computed
+        CA[slot] = make_float4(wpt.x, wpt.y, wpt.z, bias);
+        CB[slot] = make_float4(depth, 0.0f, 0.0f, __uint_as_float(wdn));   // .x carries the depth until the inverse masses are computed
         {   // warm start from the cached impulse of the same (owner shape, target shape, sample point), if it persisted
           const uint32_t key = ((uint32_t)a << 12) | ((uint32_t)t << 4) | (uint32_t)p;
           wsw[4 * slot] = __uint_as_float(key);
@@ -522,10 +545,10 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     //    target-side contacts go to a per-body list, filled with atomics and then sorted ascending
     //    (=> the summation order of phase B is fixed, whatever the fill order was)
     for (int i = tid; i < ncon; i += SIM_THREADS) {
-      uint32_t wd = __float_as_uint(M.cb[i].w);
+      uint32_t wd = __float_as_uint(CB[i].w);
       int a = wd & 255, b = (wd >> 8) & 255;
-      if (i == 0 || (int)(__float_as_uint(M.cb[i - 1].w) & 255) != a) M.astart[a] = i;
-      if (i == ncon - 1 || (int)(__float_as_uint(M.cb[i + 1].w) & 255) != a) M.aend[a] = i + 1;
+      if (i == 0 || (int)(__float_as_uint(CB[i - 1].w) & 255) != a) M.astart[a] = i;
+      if (i == ncon - 1 || (int)(__float_as_uint(CB[i + 1].w) & 255) != a) M.aend[a] = i + 1;
       if (b != STATIC_BODY) atomicAdd(&M.nb[b], 1);
       // sleeping: who touched whom (all writers of a flag byte OR in bits => atomicOr on the containing word)
       if (a < NB && b != STATIC_BODY) { if (b >= NB) touch_or(M.touch, a, 1u); else if (M.sflag[b] & 2) touch_or(M.touch, a, 2u); }
@@ -542,7 +565,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     if (tid < NBODY) M.bcur[tid] = M.boff[tid];
     __syncthreads();
     for (int i = tid; i < ncon; i += SIM_THREADS) {
-      int b = (__float_as_uint(M.cb[i].w) >> 8) & 255;
+      int b = (__float_as_uint(CB[i].w) >> 8) & 255;
       if (b != STATIC_BODY) M.blist[atomicAdd(&M.bcur[b], 1)] = (unsigned short)i;
     }
     __syncthreads();
@@ -585,22 +608,22 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     if (condump && sub == substeps - 1)
       for (int i = tid; i < ncon; i += SIM_THREADS) {
         float* o = condump + ((size_t)e * MAXC + i) * 8;
-        float4 A4 = M.ca[i], B4 = M.cb[i];
+        float4 A4 = CA[i], B4 = CB[i];
         o[0] = B4.w; o[1] = A4.x; o[2] = A4.y; o[3] = A4.z; o[4] = B4.x;
         o[5] = A4.w; o[6] = 0.0f; o[7] = 0.0f;
       }
     __syncthreads();
     // 8. inverse mass-split effective masses along n, t1, t2
     for (int i = tid; i < ncon; i += SIM_THREADS) {
-      const float4 A4 = M.ca[i];
-      uint32_t wd = __float_as_uint(M.cb[i].w);
+      const float4 A4 = CA[i];
+      uint32_t wd = __float_as_uint(CB[i].w);
       int a = wd & 255, b = (wd >> 8) & 255;
       v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
       v3 wpt = V3(A4.x, A4.y, A4.z);
       float i0 = 1.0f / (body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n));
       float i1 = 1.0f / (body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1));
       float i2 = 1.0f / (body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2));
-      M.cb[i] = make_float4(i0, i1, i2, __uint_as_float(wd));
+      CB[i] = make_float4(i0, i1, i2, __uint_as_float(wd));
     }
     __syncthreads();
     // 9. Jacobi iterations on total impulses
@@ -608,7 +631,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     for (int it = -1; it < iters; ++it) {                      // it = -1: phase B only = apply the warm-start impulses
       if (it >= 0)
       for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
-        const float4 A4 = M.ca[i], B4 = M.cb[i], F4 = M.cf4[i];
+        const float4 A4 = CA[i], B4 = CB[i], F4 = M.cf4[i];
         uint32_t wd = __float_as_uint(B4.w);
         int a = wd & 255, b = (wd >> 8) & 255;
         v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
@@ -646,7 +669,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         for (int ee = k; ee < ntot; ee += 2) {
           const bool own = ee < na;
           const int i = own ? a0 + ee : (int)M.blist[b0 + (ee - na)];
-          const float4 F4 = M.cf4[i], A4 = M.ca[i];
+          const float4 F4 = M.cf4[i], A4 = CA[i];
           v3 f = V3(F4.x, F4.y, F4.z);
           if (!own) f = vneg(f);
           v3 wpt = V3(A4.x, A4.y, A4.z);
