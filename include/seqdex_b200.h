@@ -63,12 +63,16 @@ typedef struct sdx_scene_t {
   float hand_target_quat[4];  /* Orient: quat_from_euler_xyz(target_euler = (0, 3.1415, 1.571)) the arm IK tracks (OR:484, 1738) */
   int bank_sample_range;      /* Orient: reset samples heap rows [0, range) of the bank (OR:1564 env_rand_range = range(0, 500)) */
   int pad3[2];
+  float default_dof[SDX_ND];  /* Search: arm_hand_default_dof_pos, the pose that parks the hand beside the bin (SE:207-211) */
+  float prepare_dof[SDX_ND];  /* Search: arm_hand_prepare_dof_pos_list[0], where an episode starts (SE:220-223, 316) */
+  float pad4[2];
 } sdx_scene_t;
 
 /* tasks sharing the scene, the contact step and the PPO engine (SURVEY.md section 8a "per-task dimensions"):
  *   OR = tasks/block_assembly/allegro_hand_block_assembly_orient.py */
 #define SDX_TASK_GRASP_SIM 0   /* BlockAssemblyGraspSim: obs 132 x 3, states 188 x 3, episode 150 (GS:191-211) */
 #define SDX_TASK_ORIENT 1      /* BlockAssemblyOrient:   obs  62 x 3, states 188 x 3, episode  75 (OR:189-214)  */
+#define SDX_TASK_SEARCH 2      /* BlockAssemblySearch:   obs  62 x 3, states 188 x 3, episode  75 (SE:149-175); BASELINE configs[0] */
 #define SDX_ORIENT_OBS_FRAME 62
 #define SDX_ORIENT_BANK_WRAP 10000   /* OR:1478-1479: ring index returns to 0 after slot 10000 */
 
@@ -99,9 +103,14 @@ enum {
   SDX_T_WS = 22,        /* f32 [N][2][SDX_MAX_CONTACTS][4] contact-impulse cache (key bits, f.xyz), double buffered  */
   SDX_T_WSN = 23,       /* i32 [N][2]    entries in each cache buffer                                           */
   SDX_T_SLEEP = 24,     /* u8  [N][72]   sub-steps since each free brick was last hot (0 = hot; >= sleep_substeps = asleep)  */
-  SDX_T_COUNT = 25
+  SDX_T_SEG = 25,       /* i32 [N][3]    Search: pixels showing the target | centre row | centre column of the last render (SE:1231-1241) */
+  SDX_T_EMERGENCE = 26, /* f32 [N]       Search: emergence reward = 5 x (pixels now - pixels at the last render) (SE:1640-1646)   */
+  SDX_T_TVOBS = 27,     /* f32 [N][650]  Search: the transition-feasibility gate's input, 10 frames x 65 (SE:400, 1154-1166)      */
+  SDX_T_COUNT = 28
 };
 
+/* pinhole camera of the segmentation features (see sdx_segmentation_features) */
+typedef struct sdx_camera_t { float pos[3], fwd[3], right[3], up[3]; float inv_focal; int width, height; } sdx_camera_t;
 typedef struct sdx_env sdx_env_t;
 
 const char* sdx_last_error(void);
@@ -171,6 +180,14 @@ int sdx_aux(sdx_env_t* env, void** qcam_dev, void** finger_dist_dev);
  * terminal heaps of envs whose brick ended face up (saved_digging_ternimal_states_list -> ..._good_mo_tvalue.pkl, OR:1465-1513):
  * capacity > 0 allocates rings [8][capacity + 1][72][13] f32 (free-brick root rows) + index i32[8] and records from then on */
 int sdx_orient_heap_bank(sdx_env_t* env, int capacity, void** rows_dev, void** index_dev);
+/* Search (SE = tasks/block_assembly/allegro_hand_block_assembly_search.py).  Its reset_idx settles the freshly dropped heap for 60
+ * contact steps and renders the overview camera (SE:1435-1455); at the end of an episode compute_observations parks the hand,
+ * steps once and renders again (SE:989-1019).  sdx_pre_physics / sdx_post_physics run both; the camera is set here
+ * (gym.create_camera_sensor + set_camera_location, SE:873-875).  sdx_search_bank: the heaps whose target brick became visible
+ * enough, with the hand's DoF state (saved_searching_{,hand_}ternimal_states_list -> ..._medium_mo_tvalue.pkl, SE:1305-1352):
+ * capacity > 0 allocates rings rows [8][capacity + 1][72][13], hand [8][capacity + 1][23][2] f32, index i32[8] */
+int sdx_set_camera(sdx_env_t* env, const sdx_camera_t* cam);
+int sdx_search_bank(sdx_env_t* env, int capacity, void** rows_dev, void** hand_dev, void** index_dev);
 /* number of contact steps the last sdx_pre_physics spent inside reset_idx (0 when nobody reset; 103 for a full Orient reset) */
 int sdx_last_reset_sim_steps(const sdx_env_t* env);
 /* BlockAssemblySearch's camera features (SE = tasks/block_assembly/allegro_hand_block_assembly_search.py): the reference renders
@@ -179,7 +196,6 @@ int sdx_last_reset_sim_steps(const sdx_env_t* env);
  * and the centroid (row, column) of those pixels (SE:1231-1241, 1640-1646).  sdx_segmentation_features computes exactly those
  * by ray casting against the scene's boxes.  The camera is a pinhole: unit vectors fwd / right / up (right = fwd x world-up,
  * up = right x fwd), inv_focal = tan(horizontal_fov / 2) / (width / 2) (Isaac Gym's default horizontal_fov is 90 degrees). */
-typedef struct sdx_camera_t { float pos[3], fwd[3], right[3], up[3]; float inv_focal; int width, height; } sdx_camera_t;
 int sdx_segmentation_features(sdx_env_t* env, const sdx_camera_t* cam, int32_t* out_dev /* [N][3]: pixels, centre row, centre column */);
 int sdx_scene_size(void);
 int sdx_sim_smem_bytes(void);

@@ -77,6 +77,13 @@ class OracleEnv:
         self.actions = np.zeros((n, 23), np.float32)
         self.task = int(scene.c.task)               # 0 BlockAssemblyGraspSim, 1 BlockAssemblyOrient
         self.obs = np.zeros((n, 396 if self.task == 0 else 186), np.float32)
+        if self.task == 2:                          # BlockAssemblySearch: camera features, emergence reward, the gate's 10-frame input
+            self.seg = np.zeros((n, 3), np.int32)
+            self.emergence = np.zeros(n, np.float32)
+            self.last_pixels = np.zeros(n, np.float32)
+            self.tvobs = np.zeros((n, 650), np.float32)
+            self.cam = None
+            self.sb_wrap = 0
         self.states = np.zeros((n, 564), np.float32)
         self.rew = np.zeros(n, np.float32)
         self.reset = np.ones(n, np.int64)           # BT:63
@@ -162,6 +169,49 @@ class OracleEnv:
         self.ob_rows = np.zeros((8, cap + 1, NB, 13), np.float32)
         self.ob_index = np.zeros(8, np.int32)
 
+    # ---- BlockAssemblySearch (SE:1274-1537)
+    def set_camera(self, cam):
+        self.cam = cam
+
+    def enable_search_bank(self, cap):
+        self.sb_wrap = int(cap)
+        self.sb_rows = np.zeros((8, cap + 1, NB, 13), np.float32)
+        self.sb_hand = np.zeros((8, cap + 1, 23, 2), np.float32)
+        self.sb_index = np.zeros(8, np.int32)
+
+    def _search_render(self, baseline):
+        """render_all_camera_sensors + compute_emergence_reward (SE:1446-1455 / 1010-1019)"""
+        assert self.cam is not None, "BlockAssemblySearch needs its overview camera (SE:873-878)"
+        self.seg[:] = self.segmentation_features(self.cam)
+        self.L.sdxo_search_emergence(self.n, ip(self.seg), fp(self.last_pixels), fp(self.emergence), int(baseline))
+
+    def _search_reset_idx(self):
+        L, vp = self.L, self.slp.ctypes.data_as(ctypes.c_void_p)
+        state = lambda phase: L.sdxo_search_reset(self.S, self.n, ctypes.c_uint64(self.seed), phase, fp(self.brick), fp(self.dof),
+                                                  fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.successes),
+                                                  ip(self.episode), ip(self.wsn), vp)
+        self.last_reset_sim_steps = 0
+        if self.total_steps > 0 and self.sb_wrap:
+            L.sdxo_search_bank(self.S, self.n, fp(self.brick), fp(self.dof), ip(self.seg), fp(self.sb_rows), fp(self.sb_hand),
+                               ip(self.sb_index), self.sb_wrap)
+        state(0)
+        for _ in range(60):                       # SE:1437-1439: the heap falls into the bin
+            self.simulate(); self.last_reset_sim_steps += 1
+        self._search_render(True)
+        state(1)
+        self.refresh_links()                      # the hand was teleported and the next reader (pre_physics) comes before any contact step
+        state(2)
+
+    def _search_post(self):
+        if self.progress[0] + 1 >= self.scene.c.max_episode_length - 1:      # SE:989: env 0's clock stands for all (lockstep)
+            self.L.sdxo_search_hand_pose(self.S, self.n, None, 0, fp(self.dof))
+            self.simulate()
+            self._search_render(False)
+        self.L.sdxo_search_post_physics(self.S, self.n, fp(self.brick), fp(self.dof), fp(self.link), fp(self.netf), fp(self.actions),
+                                        fp(self.target_init), ip(self.seg), lp(self.progress), lp(self.reset), fp(self.obs),
+                                        fp(self.states), fp(self.tvobs), fp(self.rew), fp(self.finger_dist), fp(self.successes),
+                                        fp(self.consec))
+
     def _orient_reset_idx(self):
         """OR:1390-1695: the scripted reset (lift 50, observe + bank, state reset, settle 2 + 1, approach 50)"""
         L, vp = self.L, self.slp.ctypes.data_as(ctypes.c_void_p)
@@ -195,6 +245,14 @@ class OracleEnv:
                                         int(count_step))
 
     def pre_physics(self, actions):
+        if self.task == 2:
+            self.last_reset_sim_steps = 0
+            if self.reset.any():
+                self._search_reset_idx()
+            a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)   # VR:166
+            self.L.sdxo_search_pre_physics(self.S, self.n, fp(a), fp(self.actions), fp(self.dof), fp(self.link), fp(self.jac7),
+                                           fp(self.brick))
+            return
         if self.task == 1:
             self.last_reset_sim_steps = 0
             if self.reset.any():
@@ -218,6 +276,10 @@ class OracleEnv:
                                 lp(self.progress), fp(self.target_init))
 
     def post_physics(self):
+        if self.task == 2:
+            self._search_post()
+            self.total_steps += 1
+            return
         if self.task == 1:
             self._orient_post(1)
             self.total_steps += 1

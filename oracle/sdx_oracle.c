@@ -68,6 +68,9 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   float hand_target_quat[4];
   int bank_sample_range;
   int pad3[2];
+  float default_dof[SDX_ND];  /* Search: arm_hand_default_dof_pos, the pose that parks the hand beside the bin (SE:207-211) */
+  float prepare_dof[SDX_ND];  /* Search: arm_hand_prepare_dof_pos_list[0], where an episode starts (SE:220-223, 316) */
+  float pad4[2];
 } sdx_scene_t;
 #define ORIENT_OBS_FRAME 62
 #define ORIENT_BANK_WRAP 10000
@@ -1313,6 +1316,231 @@ void sdxo_segmentation_features(const sdx_scene_t* S, int n, const sdx_camera_t*
     out[3 * e + 1] = cnt > 0 ? (int)((float)sr / (float)cnt) : 0;
     out[3 * e + 2] = cnt > 0 ? (int)((float)scol / (float)cnt) : 0;
   }
+}
+
+
+/* ================================================================== BlockAssemblySearch (SDX_TASK_SEARCH; BASELINE configs[0])
+ * SE = tasks/block_assembly/allegro_hand_block_assembly_search.py.  Scene = GraspSim's with the drop lattice 6 cm higher, the
+ * floor bricks 5 mm higher and a 12x12 base-plate (seqdex_b200/scene.py); Orient's finger drives.  The hand digs through the
+ * heap until the overview camera sees enough of the target brick.
+ * PARITY: pre-physics, observations, privileged state, reward / reset flags PINNED to the reference's own Python
+ * (oracle/gen_golden_search.py -> tests/golden/search_*.npz).  The camera features come from sdxo_segmentation_features
+ * (unpinned: closed rasteriser); the reset is sequencing around the (unpinned) contact step. */
+#define SEARCH_TVOBS 650 /* 10 frames x 65 (SE:400) */
+static inline float u11(uint32_t r) { return (float)(r >> 8) * (2.0f / 16777216.0f) - 1.0f; } /* U[-1, 1) from 24 random bits */
+static const int SEARCH_PIXEL_THRESHOLD[8] = {20, 20, 15, 20, 20, 30, 30, 20}; /* SE:1290 */
+
+/* pre_physics_step after any reset (SE:1546-1596): fingers = clamped EMA of the scaled actions, arm = IK towards 24 cm above /
+ * 18 cm behind the target brick with the wrist orientation quat_from_euler_xyz(0, 3.14, 1.57).  (The reference tracks the
+ * target position cached by the last compute_observations; ours reads the current one -- they differ only in the first
+ * step after a reset.) */
+void sdxo_search_pre_physics(const sdx_scene_t* S, int n, const float* actions_in, float* actions, float* dof, const float* link,
+                             const float* jac7, const float* brick) {
+  for (int e = 0; e < n; ++e) {
+    const float* a = actions_in + 23 * e;
+    float* d = dof + (size_t)e * 72;
+    float cur[23];
+    for (int k = 0; k < 23; ++k) actions[23 * e + k] = a[k];
+    for (int i = 0; i < 16; ++i) {
+      float t = scalef(a[7 + i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+      float c = S->act_moving_average * t + (1.0f - S->act_moving_average) * d[48 + 7 + i];
+      cur[7 + i] = clampf(c, S->dof_lo[7 + i], S->dof_hi[7 + i]);
+    }
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), tg);
+    const float* hb = link + ((size_t)e * SDX_NL + 7) * 13;
+    float dpose[6];
+    dpose[0] = (tg[0] - hb[0]) - 0.18f; dpose[1] = tg[1] - hb[1]; dpose[2] = (tg[2] - hb[2]) + 0.24f;
+    q4 want = {S->hand_target_quat[0], S->hand_target_quat[1], S->hand_target_quat[2], S->hand_target_quat[3]};
+    q4 hq = {hb[3], hb[4], hb[5], hb[6]};
+    v3 re = orientation_error(want, hq);
+    dpose[3] = re.x; dpose[4] = re.y; dpose[5] = re.z;
+    float u[7];
+    control_ik(jac7 + 42 * (size_t)e, dpose, u);
+    for (int j = 0; j < 7; ++j) cur[j] = d[j] + u[j];
+    for (int j = 0; j < 23; ++j) d[48 + j] = clampf(cur[j], S->dof_lo[j], S->dof_hi[j]);
+  }
+}
+
+/* post_physics_step (SE:1598-1602) after the end-of-episode camera branch (handled by the caller): progress += 1,
+ * compute_observations (SE:1036-1166 -> compute_contact_observations SE:1220-1245, compute_contact_asymmetric_observations
+ * SE:1168-1218, the 10-frame gate input SE:1154-1166), compute_hand_reward (SE:1660-1712).
+ * seg [n][3] = pixels / centre row / centre column of the LAST rendered segmentation image.  obs [n][186], states [n][564],
+ * tvobs [n][650]. */
+void sdxo_search_post_physics(const sdx_scene_t* S, int n, const float* brick, const float* dof, const float* link, const float* netf,
+                              const float* actions, const float* target_init, const int* seg, int64_t* progress, int64_t* reset,
+                              float* obs, float* states, float* tvobs, float* rew, float* finger_dist_out, const float* successes,
+                              float* consec) {
+  int64_t num_resets = 0; float finished = 0.0f;
+  for (int e = 0; e < n; ++e) {
+    progress[e] += 1;
+    const float* L = link + (size_t)e * SDX_NL * 13;
+    const float* d = dof + (size_t)e * 72;
+    const float* hb = L + 7 * 13;
+    const float* ff = L + 11 * 13; const float* mf = L + 19 * 13; const float* rf = L + 23 * 13; const float* th = L + 15 * 13;
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, target_brick(e), tg);
+    v3 tp = V3(tg[0], tg[1], tg[2]); q4 tq = {tg[3], tg[4], tg[5], tg[6]};
+    v3 tip[4]; const float* fs[4] = {ff, mf, rf, th};
+    float nrm[4];
+    for (int i = 0; i < 4; ++i) { /* SE:1086-1089 */
+      q4 fq = {fs[i][3], fs[i][4], fs[i][5], fs[i][6]};
+      tip[i] = vadd(V3(fs[i][0], fs[i][1], fs[i][2]), qrot(fq, V3(0.0f, 0.0f, 1.0f * 0.04f)));
+      v3 dd = vsub(tp, tip[i]); nrm[i] = sqrtf(vdot(dd, dd));
+    }
+    float fdist = nrm[0] + nrm[1] + nrm[2] + nrm[3];
+    finger_dist_out[e] = fdist;
+    q4 hq = {hb[3], hb[4], hb[5], hb[6]}; v3 hp = V3(hb[0], hb[1], hb[2]);
+    q4 cq0 = {S->cam_off_quat[0], S->cam_off_quat[1], S->cam_off_quat[2], S->cam_off_quat[3]};
+    q4 cq = qmul(hq, cq0); v3 cp = vadd(qrot(hq, V3(S->cam_off_pos[0], S->cam_off_pos[1], S->cam_off_pos[2])), hp); /* SE:1104-1108 */
+    q4 cqi = qconj(cq);
+    q4 cvq = qmul(cqi, tq);
+    (void)cp;
+    float contacts = 0.0f; /* arm links 0..6 whose net contact force reaches 0.1 N (SE:919, 1111-1115) */
+    for (int k = 0; k < 7; ++k) {
+      const float* f = netf + ((size_t)e * SDX_NL + k) * 3;
+      float nf = sqrtf(vdot(V3(f[0], f[1], f[2]), V3(f[0], f[1], f[2])));
+      contacts = contacts + (nf >= 0.1f ? 1.0f : 0.0f);
+    }
+    const float* ti = target_init + 7 * e;
+    const float sx = (float)seg[3 * e + 1] / 128.0f, sy = (float)seg[3 * e + 2] / 128.0f, sn = (float)seg[3 * e] / 100.0f;
+    /* ---- obs frame 0 (SE:1220-1229) */
+    float* o = obs + (size_t)e * 3 * ORIENT_OBS_FRAME;
+    for (int i = 0; i < 16; ++i) {
+      float us = unscalef(d[7 + i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+      o[i] = us;
+      o[30 + i] = actions[23 * e + 7 + i] - us;
+      o[46 + i] = actions[23 * e + 7 + i];
+    }
+    /* ---- privileged state, frame 0 only: Search never shifts a history (SE:1168-1218) */
+    float* s = states + (size_t)e * 3 * STATE_FRAME;
+    for (int j = 0; j < 23; ++j) { s[j] = unscalef(d[j], S->dof_lo[j], S->dof_hi[j]); s[23 + j] = S->vel_obs_scale * d[24 + j]; }
+    s[46] = tip[0].x; s[47] = tip[0].y; s[48] = tip[0].z;
+    s[49] = tip[2].x; s[50] = tip[2].y; s[51] = tip[2].z;
+    s[52] = tip[1].x; s[53] = tip[1].y; s[54] = tip[1].z;
+    s[55] = tip[3].x; s[56] = tip[3].y; s[57] = tip[3].z;
+    for (int k = 0; k < 23; ++k) s[58 + k] = actions[23 * e + k];
+    for (int k = 0; k < 7; ++k) { s[81 + k] = hb[k]; s[88 + k] = tg[k]; }
+    for (int k = 96; k < 120; ++k) s[k] = 0.0f; /* hand_pos_history_0..7 are means of a zeroed buffer (SE:1457-1465) */
+    s[120] = sx; s[121] = sy; s[122] = sn;
+    for (int k = 0; k < 6; ++k) s[123 + k] = hb[7 + k];
+    for (int k = 0; k < 4; ++k) { s[129 + k] = ff[3 + k]; s[139 + k] = mf[3 + k]; s[149 + k] = rf[3 + k]; s[159 + k] = th[3 + k]; }
+    for (int k = 0; k < 6; ++k) { s[133 + k] = ff[7 + k]; s[143 + k] = mf[7 + k]; s[153 + k] = rf[7 + k]; s[163 + k] = th[7 + k]; }
+    for (int k = 0; k < 6; ++k) s[169 + k] = tg[7 + k];
+    /* ---- the gate's 10-frame input (SE:1154-1166): oldest frame out, newest = obs[0:62] with slots 26..29 = camera-frame
+     * target quaternion, then centre / 128, centre / 128, pixels / 100 */
+    float* tvo = tvobs + (size_t)e * SEARCH_TVOBS;
+    for (int k = 0; k < 9 * 65; ++k) tvo[k] = tvo[k + 65];
+    float* fr = tvo + 9 * 65;
+    for (int k = 0; k < 62; ++k) fr[k] = o[k];
+    fr[26] = cvq.x; fr[27] = cvq.y; fr[28] = cvq.z; fr[29] = cvq.w;
+    fr[62] = sx; fr[63] = sy; fr[64] = sn;
+    /* ---- reward / reset flags (SE:1668-1712) */
+    float dist_rew = -0.2f * fdist; if (dist_rew > -0.06f) dist_rew = -0.06f;
+    float asq = 0.0f;
+    for (int k = 0; k < 23; ++k) asq = asq + actions[23 * e + k] * actions[23 * e + k];
+    float action_penalty = asq * 0.005f;
+    float up = clampf(tp.z - ti[2], 0.0f, 0.1f) * 1000.0f - clampf(tp.x - ti[0], 0.0f, 0.1f) * 1000.0f - clampf(tp.y - ti[1], 0.0f, 0.1f) * 1000.0f;
+    rew[e] = (((dist_rew - contacts) + 0.0f) - action_penalty) + up;
+    int64_t rs = reset[e];
+    if (fdist <= -1.0f) rs = 1;
+    if ((float)progress[e] >= (float)S->max_episode_length - 1.0f) rs = 1;
+    reset[e] = rs;
+    num_resets += rs; finished = finished + successes[e] * (float)rs;
+  }
+  if (num_resets > 0) consec[0] = S->av_factor * finished / (float)num_resets + (1.0f - S->av_factor) * consec[0];
+}
+
+/* every env's hand (or the flagged ones) teleported to a stored pose: which = 0 arm_hand_default_dof_pos (SE:990-998, 1405-1410),
+ * 1 arm_hand_prepare_dof_poses (SE:1483-1493); positions = targets = pose, velocities 0 */
+void sdxo_search_hand_pose(const sdx_scene_t* S, int n, const int64_t* mask, int which, float* dof) {
+  const float* pose = which ? S->prepare_dof : S->default_dof;
+  for (int e = 0; e < n; ++e) {
+    if (mask && !mask[e]) continue;
+    float* d = dof + (size_t)e * 72;
+    for (int j = 0; j < SDX_ND; ++j) { d[j] = pose[j]; d[24 + j] = 0.0f; d[48 + j] = pose[j]; }
+  }
+}
+
+/* compute_emergence_reward (SE:1640-1646): 5 x (pixels now - pixels at the last render); baseline != 0 only records */
+void sdxo_search_emergence(int n, const int* seg, float* last_pixels, float* emergence, int baseline) {
+  for (int e = 0; e < n; ++e) {
+    float pix = (float)seg[3 * e];
+    if (!baseline) emergence[e] = (pix - last_pixels[e]) * 5.0f;
+    last_pixels[e] = pix;
+  }
+}
+
+/* banking of the dug-out heaps (SE:1305-1340), EVERY env in env order: enough pixels of the target visible -> the 72 free-brick
+ * root rows and the hand's DoF state go to ring[type][index]; the index returns to 0 after slot `wrap` (10000) */
+void sdxo_search_bank(const sdx_scene_t* S, int n, const float* brick, const float* dof, const int* seg, float* rows_out,
+                      float* hand_out, int* index, int wrap) {
+  for (int e = 0; e < n; ++e) {
+    int ty = e % 8;
+    if (!(seg[3 * e] > SEARCH_PIXEL_THRESHOLD[ty])) continue;
+    float* dst = rows_out + (((size_t)ty * (wrap + 1)) + index[ty]) * NB * 13;
+    for (int b = 0; b < NB; ++b) brick_root_row(S, brick + (size_t)e * 13 * NB, b, dst + b * 13);
+    float* hd = hand_out + (((size_t)ty * (wrap + 1)) + index[ty]) * 46;
+    const float* d = dof + (size_t)e * 72;
+    for (int j = 0; j < SDX_ND; ++j) { hd[2 * j] = d[j]; hd[2 * j + 1] = d[24 + j]; }
+    index[ty] += 1;
+    if (index[ty] > wrap) index[ty] = 0;
+  }
+}
+
+/* state writes of reset_idx / post_reset for the flagged envs.
+ * phase 0 (SE:1388-1411): free bricks back on the drop lattice with 2 cm xy jitter, velocities 0; the target brick at
+ *          (0.25 + 0.2 r, 0.19 + 0.15 r, 0.9) with ONE r per env (SE:1392-1394 index the same random column twice); hand at the
+ *          default pose.  Own Philox stream instead of torch's generator.
+ * phase 1 (SE:1483-1496, after the 60 settle steps): hand at the prepare pose; the target's pose becomes its initial pose
+ * phase 2 (SE:1430-1433): progress, reset flag, successes cleared */
+void sdxo_search_reset(const sdx_scene_t* S, int n, uint64_t seed, int phase, float* brick, float* dof, float* target_init,
+                       int64_t* progress, int64_t* reset, float* successes, int* episode, int* wsn, unsigned char* slp) {
+  for (int e = 0; e < n; ++e) {
+    if (!reset[e]) continue;
+    float* B = brick + (size_t)e * 13 * NB;
+    float* d = dof + (size_t)e * 72;
+    if (phase == 0) {
+      const int tb = target_brick(e);
+      for (int b = 0; b < NB; ++b) {
+        uint32_t r[4];
+        philox(seed, (uint32_t)e, (uint32_t)episode[e], 16u + (uint32_t)b, r);
+        float row[13];
+        for (int k = 0; k < 7; ++k) row[k] = S->brick_init[b * 13 + k];
+        for (int k = 7; k < 13; ++k) row[k] = 0.0f;
+        row[0] = row[0] + u11(r[0]) * 0.02f;
+        row[1] = row[1] + u11(r[1]) * 0.02f;
+        if (b == tb) {
+          uint32_t q[4];
+          philox(seed, (uint32_t)e, (uint32_t)episode[e], 2u, q);
+          float rr = u11(q[0]);
+          row[0] = 0.25f + rr * 0.2f; row[1] = 0.19f + rr * 0.15f; row[2] = 0.9f;
+        }
+        brick_from_root_row(S, B, b, row);
+        slp[(size_t)e * NB + b] = 0;
+      }
+      wsn[2 * e] = 0; wsn[2 * e + 1] = 0;
+      episode[e] += 1;
+      for (int j = 0; j < SDX_ND; ++j) { d[j] = S->default_dof[j]; d[24 + j] = 0.0f; d[48 + j] = S->default_dof[j]; }
+    }
+    if (phase == 1) {
+      for (int j = 0; j < SDX_ND; ++j) { d[j] = S->prepare_dof[j]; d[24 + j] = 0.0f; d[48 + j] = S->prepare_dof[j]; }
+      float tg[13];
+      brick_root_row(S, B, target_brick(e), tg);
+      for (int k = 0; k < 7; ++k) target_init[7 * e + k] = tg[k]; /* SE:1495-1496 */
+    }
+    if (phase == 2) { progress[e] = 0; reset[e] = 0; successes[e] = 0.0f; }
+  }
+}
+
+/* the reduction the reference applies to a rendered segmentation image (SE:1231-1241): mask [h][w] of the pixels that carry the
+ * target's id -> pixels, int(mean row), int(mean column).  Exposed so the golden test can pin the arithmetic on real images. */
+void sdxo_mask_features(const unsigned char* mask, int h, int w, int* out) {
+  int cnt = 0, sr = 0, sc2 = 0;
+  for (int r = 0; r < h; ++r) for (int c = 0; c < w; ++c) if (mask[r * w + c]) { cnt++; sr += r; sc2 += c; }
+  out[0] = cnt;
+  out[1] = cnt > 0 ? (int)((float)sr / (float)cnt) : 0;
+  out[2] = cnt > 0 ? (int)((float)sc2 / (float)cnt) : 0;
 }
 
 int sdxo_scene_size(void) { return (int)sizeof(sdx_scene_t); }

@@ -50,6 +50,49 @@ def load_heap_bank(path):
         return heap_bank_from_reference(pickle.load(f))
 
 
+def search_bank_valid(env):
+    """the heaps BlockAssemblySearch banked so far as ``[8, K, 72, 13]`` on the device: what Orient samples on reset (OR:419-420, 1564-1568)"""
+    rows, _, index = env.search_bank()
+    torch.cuda.synchronize(env.device)
+    idx = index.cpu().tolist()
+    ring = rows.shape[1]
+    filled = [ring if bool(rows[t, ring - 1].abs().sum() > 0) else idx[t] for t in range(8)]
+    k = min(filled)
+    if k == 0:
+        raise RuntimeError(f"BlockAssemblySearch has banked no heap yet for some brick type (per-type counts {filled})")
+    out = rows[:, :k].clone()
+    out[..., 7:13] = 0
+    return out.contiguous()
+
+
+def search_bank_to_reference(env, scene, rows_per_type=10000 + 1024):
+    """(``saved_searching_ternimal_states_list``, ``saved_searching_hand_ternimal_states_list``) as Search pickles them
+    (SE:1348-1352): ``list[8]`` of ``Tensor[11024, 132, 13]`` and of ``Tensor[11024, 23, 2]``"""
+    rows, hand, _ = env.search_bank()
+    torch.cuda.synchronize(env.device)
+    rows, hand = rows.cpu(), hand.cpu()
+    fixed = torch.from_numpy(np.ctypeslib.as_array(scene.c.fixed_root).reshape(N_FIXED, 13).astype(np.float32))
+    heaps, hands = [], []
+    for ty in range(8):
+        t = torch.zeros(rows_per_type, N_FREE + N_FIXED, 13)
+        h = torch.zeros(rows_per_type, 23, 2)
+        k = min(rows.shape[1], rows_per_type)
+        t[:k, :N_FREE] = rows[ty, :k]
+        written = rows[ty, :k].abs().sum(dim=(1, 2)) > 0
+        t[:k, N_FREE:][written] = fixed
+        h[:k] = hand[ty, :k]
+        heaps.append(t); hands.append(h)
+    return heaps, hands
+
+
+def save_search_bank(env, scene, heap_path, hand_path):
+    heaps, hands = search_bank_to_reference(env, scene)
+    with open(heap_path, "wb") as f:
+        pickle.dump(heaps, f)
+    with open(hand_path, "wb") as f:
+        pickle.dump(hands, f)
+
+
 def orient_bank_valid(env):
     """the heaps BlockAssemblyOrient banked so far as ``[8, K, 72, 13]`` on the device (K = the fewest any type holds; a ring
     that has wrapped counts as full) -- what the NEXT stage of the chain samples on reset (GS:412-413, 1507-1511)"""

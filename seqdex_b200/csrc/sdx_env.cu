@@ -12,6 +12,7 @@
 #include "sdx_task.cuh"
 #include "sdx_task_orient.cuh"
 #include "sdx_camera.cuh"
+#include "sdx_task_search.cuh"
 
 static thread_local std::string g_err;
 extern "C" const char* sdx_last_error(void) { return g_err.c_str(); }
@@ -48,9 +49,14 @@ struct sdx_env {
   int* ob_slot = nullptr;          // [n] ring slot of each env in the current banking call
   float* ob_rows = nullptr; int* ob_index = nullptr; int ob_wrap = 0;   // re-oriented heap rings (sdx_orient_heap_bank)
   int last_reset_sim_steps = 0;
+  // BlockAssemblySearch
+  sdx_camera_t cam; bool has_cam = false;
+  float* last_pixels = nullptr;
+  float *sb_rows = nullptr, *sb_hand = nullptr; int* sb_index = nullptr; int sb_wrap = 0;
+  int64_t* progress0_host = nullptr;   // pinned: progress_buf[0] (SE:989 reads it on the host every step)
   float4* cscratch = nullptr;      // [n][2][MAXC] contact records of k_simulate (SIM_GLOBAL_CONTACTS)
 };
-static int obs_frame(const sdx_env* E) { return E->task == SDX_TASK_ORIENT ? SDX_ORIENT_OBS_FRAME : SDX_OBS_FRAME; }
+static int obs_frame(const sdx_env* E) { return E->task == SDX_TASK_GRASP_SIM ? SDX_OBS_FRAME : SDX_ORIENT_OBS_FRAME; }
 
 static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim, int* dtype) {
   int64_t n = E->n;
@@ -78,6 +84,9 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
     case SDX_T_WS: s[0] = n; s[1] = 2; s[2] = SDX_MAX_CONTACTS; s[3] = 4; nd = 4; break;
     case SDX_T_WSN: s[0] = n; s[1] = 2; nd = 2; dt = 2; break;
     case SDX_T_SLEEP: s[0] = n; s[1] = NB; nd = 2; dt = 3; break;
+    case SDX_T_SEG: s[0] = n; s[1] = 3; nd = 2; dt = 2; break;
+    case SDX_T_EMERGENCE: s[0] = n; break;
+    case SDX_T_TVOBS: s[0] = E->task == SDX_TASK_SEARCH ? n : 1; s[1] = SEARCH_TVOBS; nd = 2; break;
     default: return 0;
   }
   if (shape) for (int i = 0; i < 4; ++i) shape[i] = s[i];
@@ -95,7 +104,7 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaSetDevice(device));
   sdx_env* E = new sdx_env();
   E->n = num_envs; E->device = device; E->seed = seed; E->host_scene = *scene;
-  if (scene->task != SDX_TASK_GRASP_SIM && scene->task != SDX_TASK_ORIENT) { g_err = "sdx_create: unknown scene.task"; delete E; return -1; }
+  if (scene->task != SDX_TASK_GRASP_SIM && scene->task != SDX_TASK_ORIENT && scene->task != SDX_TASK_SEARCH) { g_err = "sdx_create: unknown scene.task"; delete E; return -1; }
   E->task = scene->task;
   CK(cudaMalloc(&E->scene, sizeof(sdx_scene_t)));
   CK(cudaMemcpy(E->scene, scene, sizeof(sdx_scene_t), cudaMemcpyHostToDevice));
@@ -119,6 +128,8 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaMalloc(&E->flag_count, 4)); CK(cudaMemset(E->flag_count, 0, 4));
   CK(cudaMallocHost(&E->flag_count_host, 4)); *E->flag_count_host = 0;
   CK(cudaMalloc(&E->ob_slot, n * 4));
+  CK(cudaMalloc(&E->last_pixels, n * 4)); CK(cudaMemset(E->last_pixels, 0, n * 4));
+  CK(cudaMallocHost(&E->progress0_host, 8)); *E->progress0_host = 0;
   CK(cudaMalloc(&E->stage_obs, n * 3 * obs_frame(E) * 4));
   CK(cudaMalloc(&E->stage_states, n * 3 * SDX_STATE_FRAME * 4));
   CK(cudaMalloc(&E->stage_actions, n * 23 * 4));
@@ -139,6 +150,7 @@ extern "C" void sdx_destroy(sdx_env_t* E) {
   cudaFree(E->gb_hand); cudaFree(E->gb_obj); cudaFree(E->gb_index); cudaFree(E->red_count); cudaFree(E->red_sum);
   cudaFree(E->stage_obs); cudaFree(E->stage_states); cudaFree(E->stage_actions);
   cudaFree(E->cscratch);
+  cudaFree(E->last_pixels); cudaFree(E->sb_rows); cudaFree(E->sb_hand); cudaFree(E->sb_index); cudaFreeHost(E->progress0_host);
   cudaFree(E->flag_count); cudaFreeHost(E->flag_count_host); cudaFree(E->ob_slot); cudaFree(E->ob_rows); cudaFree(E->ob_index);
   delete E;
 }
@@ -266,9 +278,11 @@ extern "C" int sdx_reset_all(sdx_env_t* E) {
 }
 
 static int orient_pre_physics(sdx_env_t* E, const float* actions_dev);
+static int search_pre_physics(sdx_env_t* E, const float* actions_dev);
 extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
   CK(cudaSetDevice(E->device));
   const int n = E->n;
+  if (E->task == SDX_TASK_SEARCH) return search_pre_physics(E, actions_dev);     // Search resets from the drop lattice: no bank
   if (!E->bank) { g_err = "sdx_pre_physics: no heap bank set (reset_idx samples it, GS:1507-1511)"; return -1; }
   if (E->task == SDX_TASK_ORIENT) return orient_pre_physics(E, actions_dev);
   if (E->total_steps > 0) {
@@ -366,6 +380,93 @@ static int orient_pre_physics(sdx_env_t* E, const float* actions_dev) {
   return 0;
 }
 
+// ---- BlockAssemblySearch
+static int search_render(sdx_env_t* E, int baseline) {     // render_all_camera_sensors + compute_emergence_reward (SE:1446-1455 / 1010-1019)
+  if (!E->has_cam) { g_err = "BlockAssemblySearch needs its overview camera: call sdx_set_camera (SE:873-878)"; return -1; }
+  if (sdx_segmentation_features(E, &E->cam, I32(SDX_T_SEG))) return -1;
+  k_search_emergence<<<(E->n + 255) / 256, 256, 0, E->stream>>>(E->n, I32(SDX_T_SEG), E->last_pixels, F(SDX_T_EMERGENCE), baseline);
+  E->launches++;
+  CKL();
+  return 0;
+}
+static int search_pre_physics(sdx_env_t* E, const float* actions_dev) {
+  const int n = E->n, T = 128, G = (n + T - 1) / T;
+  CK(cudaMemsetAsync(E->flag_count, 0, 4, E->stream));
+  k_count_flags<<<(n + 255) / 256, 256, 0, E->stream>>>(I64(SDX_T_RESET), n, E->flag_count);
+  E->launches++;
+  CK(cudaMemcpyAsync(E->flag_count_host, E->flag_count, 4, cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));                       // reset_buf.nonzero() (SE:1540)
+  E->last_reset_sim_steps = 0;
+  if (*E->flag_count_host > 0) {
+    auto state = [&](int phase) {
+      k_search_reset<<<n, 128, 0, E->stream>>>(E->scene, n, E->seed, phase, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_TARGET_INIT),
+                                               I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), I32(SDX_T_EPISODE),
+                                               I32(SDX_T_WSN), (unsigned char*)E->buf[SDX_T_SLEEP]);
+      E->launches++;
+    };
+    if (E->total_steps > 0 && E->sb_wrap > 0) {
+      k_search_bank_slots<<<8, 256, 0, E->stream>>>(n, I32(SDX_T_SEG), E->sb_index, E->sb_wrap, E->ob_slot);
+      k_search_bank_write<<<n, 96, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), E->ob_slot, E->sb_rows, E->sb_hand, E->sb_wrap);
+      E->launches += 2;
+    }
+    state(0);
+    for (int i = 0; i < 60; ++i) { E->last_reset_sim_steps++; if (sdx_simulate(E)) return -1; }     // SE:1437-1439
+    if (search_render(E, 1)) return -1;
+    state(1);
+    k_refresh_links<<<(n + 63) / 64, 64, 0, E->stream>>>(E->scene, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7), n);   // teleported hand
+    E->launches++;
+    state(2);
+  }
+  k_search_pre_physics<<<G, T, 0, E->stream>>>(E->scene, n, actions_dev, F(SDX_T_ACTIONS), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+                                               F(SDX_T_BRICK));
+  E->launches++;
+  CKL();
+  return 0;
+}
+static int search_post_physics(sdx_env_t* E) {
+  const int n = E->n;
+  CK(cudaMemcpyAsync(E->progress0_host, I64(SDX_T_PROGRESS), 8, cudaMemcpyDeviceToHost, E->stream));
+  CK(cudaStreamSynchronize(E->stream));                       // `if ... self.progress_buf[0] >= self.max_episode_length - 1` (SE:989)
+  if (*E->progress0_host + 1 >= E->host_scene.max_episode_length - 1) {
+    k_search_hand_pose<<<(n * SDX_ND + 255) / 256, 256, 0, E->stream>>>(E->scene, n, nullptr, 0, F(SDX_T_DOF));
+    E->launches++;
+    if (sdx_simulate(E)) return -1;
+    if (search_render(E, 0)) return -1;
+  }
+  k_search_post_physics<<<(n + POST_WARPS - 1) / POST_WARPS, 32 * POST_WARPS, 0, E->stream>>>(
+      E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_NETF), F(SDX_T_ACTIONS), F(SDX_T_TARGET_INIT), I32(SDX_T_SEG),
+      I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_OBS), F(SDX_T_STATES), F(SDX_T_TVOBS), F(SDX_T_REW), E->finger_dist,
+      F(SDX_T_SUCCESSES), E->red_count, E->red_sum);
+  k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
+  E->launches += 2;
+  E->total_steps++;
+  CKL();
+  return 0;
+}
+extern "C" int sdx_set_camera(sdx_env_t* E, const sdx_camera_t* cam) {
+  if (!cam || cam->width <= 0 || cam->height <= 0) { g_err = "sdx_set_camera: bad camera"; return -1; }
+  E->cam = *cam; E->has_cam = true;
+  return 0;
+}
+extern "C" int sdx_search_bank(sdx_env_t* E, int capacity, void** rows_dev, void** hand_dev, void** index_dev) {
+  CK(cudaSetDevice(E->device));
+  if (E->task != SDX_TASK_SEARCH) { g_err = "sdx_search_bank: the env does not run BlockAssemblySearch"; return -1; }
+  if (capacity > 0 && capacity != E->sb_wrap) {
+    CK(cudaStreamSynchronize(E->stream));
+    cudaFree(E->sb_rows); cudaFree(E->sb_hand); cudaFree(E->sb_index);
+    size_t slots = (size_t)8 * (capacity + 1);
+    CK(cudaMalloc(&E->sb_rows, slots * NB * 13 * 4)); CK(cudaMemset(E->sb_rows, 0, slots * NB * 13 * 4));
+    CK(cudaMalloc(&E->sb_hand, slots * 46 * 4)); CK(cudaMemset(E->sb_hand, 0, slots * 46 * 4));
+    CK(cudaMalloc(&E->sb_index, 32)); CK(cudaMemset(E->sb_index, 0, 32));
+    E->sb_wrap = capacity;
+  }
+  if (capacity == 0) E->sb_wrap = 0;
+  if (rows_dev) *rows_dev = E->sb_rows;
+  if (hand_dev) *hand_dev = E->sb_hand;
+  if (index_dev) *index_dev = E->sb_index;
+  return 0;
+}
+
 extern "C" int sdx_orient_heap_bank(sdx_env_t* E, int capacity, void** rows_dev, void** index_dev) {
   CK(cudaSetDevice(E->device));
   if (E->task != SDX_TASK_ORIENT) { g_err = "sdx_orient_heap_bank: the env does not run BlockAssemblyOrient"; return -1; }
@@ -387,6 +488,7 @@ extern "C" int sdx_last_reset_sim_steps(const sdx_env_t* E) { return E->last_res
 extern "C" int sdx_post_physics(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
   const int n = E->n;
+  if (E->task == SDX_TASK_SEARCH) return search_post_physics(E);
   if (E->task == SDX_TASK_ORIENT) {
     if (orient_observe(E, 1)) return -1;
     k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));

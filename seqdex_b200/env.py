@@ -12,7 +12,7 @@ from .scene import Scene
 
 T = dict(BRICK=0, DOF=1, LINK=2, JAC7=3, NETF=4, ACTIONS=5, OBS=6, STATES=7, REW=8, RESET=9, PROGRESS=10, TVALUE=11,
          TARGET_INIT=12, SUCCESSES=13, CONSEC=14, NCONTACT=15, ROOT=16, RB=17, DOF_STATE=18, JACOBIAN=19, EPISODE=20,
-         CONTACTS=21, WS=22, WSN=23, SLEEP=24)
+         CONTACTS=21, WS=22, WSN=23, SLEEP=24, SEG=25, EMERGENCE=26, TVOBS=27)
 _DT = {0: (torch.float32, "<f4"), 1: (torch.int64, "<i8"), 2: (torch.int32, "<i4"), 3: (torch.uint8, "|u1")}
 
 
@@ -151,6 +151,23 @@ class SdxEnv:
         r, i = ctypes.c_void_p(), ctypes.c_void_p()
         _lib.check(self.L.sdx_orient_heap_bank(self.h, self._ob_wrap, ctypes.byref(r), ctypes.byref(i)))
         return self._view(r.value, (8, self._ob_wrap + 1, 72, 13)), self._view(i.value, (8,), "<i4")
+
+    # ---- BlockAssemblySearch
+    def set_camera(self, cam):
+        """the overview camera Search renders after every reset and at the end of every episode (SE:873-878)"""
+        _lib.check(self.L.sdx_set_camera(self.h, ctypes.byref(cam)))
+
+    def enable_search_bank(self, capacity=10000):
+        """record the heaps (and hand states) Search digs the target out of (saved_searching_*_ternimal_states_list, SE:1305-1352)"""
+        _lib.check(self.L.sdx_search_bank(self.h, int(capacity), None, None, None))
+        self._sb_wrap = int(capacity)
+
+    def search_bank(self):
+        """(rows [8, capacity + 1, 72, 13], hand [8, capacity + 1, 23, 2], index [8] i32)"""
+        r, h, i = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self.L.sdx_search_bank(self.h, self._sb_wrap, ctypes.byref(r), ctypes.byref(h), ctypes.byref(i)))
+        return (self._view(r.value, (8, self._sb_wrap + 1, 72, 13)), self._view(h.value, (8, self._sb_wrap + 1, 23, 2)),
+                self._view(i.value, (8,), "<i4"))
 
     def last_reset_sim_steps(self):
         return int(self.L.sdx_last_reset_sim_steps(self.h))
