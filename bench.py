@@ -88,7 +88,11 @@ def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None, stagger=True):
     cores = oracle.lib().sdxo_get_threads()
     n = n_envs or 32 * cores
     env = oracle.OracleEnv(scene, n)
-    env.set_heap_bank(bank)
+    if bank is not None:
+        env.set_heap_bank(bank)
+    if int(scene.c.task) == 2:
+        from seqdex_b200.camera import SEARCH_CAMERA, look_at
+        env.set_camera(look_at(**SEARCH_CAMERA))
     rng = np.random.default_rng(0)
     precondition_cpu(env, rng, stagger)
     t0, steps = time.time(), 0
@@ -192,7 +196,7 @@ def main():
     ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
                     help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
                          "rollout: VecTask.step only with U(-1,1) actions")
-    ap.add_argument("--task", default="grasp_sim", choices=["grasp_sim", "orient"],
+    ap.add_argument("--task", default="grasp_sim", choices=["grasp_sim", "orient", "search"],
                     help="grasp_sim: BlockAssemblyGraspSim, the BASELINE.json metric (configs[1]); orient: BlockAssemblyOrient (configs[2]: "
                          "32768 envs over 2 GPUs = --gpus 2 with the default 16384 envs per GPU)")
     ap.add_argument("--minibatch", type=int, default=32768,
@@ -215,15 +219,22 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = args.num_envs
-    orient = args.task == "orient"
+    orient = args.task in ("orient", "search")      # lockstep episodes (both tasks' resets are scripts over the whole sim)
+    search = args.task == "search"
     # Orient's reset_idx is a script over the WHOLE sim (103 extra contact steps whenever any env resets, OR:1390-1695), so its
     # episodes run in lockstep as in the reference (time-outs only); GraspSim's per-env resets are staggered (see below)
-    scene = Scene(task="BlockAssemblyOrient", episode_length=75, act_moving_average=0.2) if orient else Scene()
-    task_name = "BlockAssemblyOrient" if orient else "BlockAssemblyGraspSim"
+    scene = (Scene(task="BlockAssemblySearch", episode_length=75, act_moving_average=0.6) if search else
+             Scene(task="BlockAssemblyOrient", episode_length=75, act_moving_average=0.2) if orient else Scene())
+    task_name = "BlockAssemblySearch" if search else "BlockAssemblyOrient" if orient else "BlockAssemblyGraspSim"
     obs_dim = 186 if orient else 396
-    bank = make_heap_bank(scene, args.bank_per_type, local, seed=22 + rank)
     env = SdxEnv(scene, n, local, seed=22 + rank)
-    env.set_heap_bank(bank)
+    if search:                                      # Search resets from the drop lattice and renders its overview camera
+        from seqdex_b200.camera import SEARCH_CAMERA, look_at
+        env.set_camera(look_at(**SEARCH_CAMERA))
+        bank = None
+    else:
+        bank = make_heap_bank(scene, args.bank_per_type, local, seed=22 + rank)
+        env.set_heap_bank(bank)
     env.set_tvalue_weights(default_tvalue_weights(22))
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     K, W = args.steps, max(args.warmup, 3)
@@ -350,8 +361,9 @@ def main():
                        "num_envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-sharded x{world}, no data-path collective",
                        "l2": "env state (260 MB at 16384 envs) exceeds the 126 MB L2; no explicit flush",
                        "heap_bank_per_type": args.bank_per_type,
-                       "episodes": (f"lockstep as in the reference (time-outs every 75 steps; each reset runs the 103-step scripted reset_idx "
-                                    f"of OR:1390-1695 inside the timed region); {PRE_STEPS} untimed steps before warm-up" if orient else
+                       "episodes": (f"lockstep as in the reference (time-outs every 75 steps; each reset runs the scripted reset_idx inside the "
+                                    f"timed region: 103 contact steps for Orient OR:1390-1695, 60 + render + 1 + render for Search "
+                                    f"SE:1274-1537, 989-1019); {PRE_STEPS} untimed steps before warm-up" if orient else
                                     f"staggered: progress ~ U[0,{STAGGER}) then {PRE_STEPS} untimed steps before warm-up (stationary mix of "
                                     "fresh and settled heaps; resting bricks sleep with PhysX's default threshold and 0.4 s timer)")},
             "e2e": {"value": world * n * E / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 23 * 4,
@@ -370,7 +382,7 @@ def main():
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
         }
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(scene, bank=bank[:, :2].cpu().numpy(), stagger=not orient, n_envs=1024 if orient else None)
+            out["cpu_baseline"] = cpu_baseline(scene, bank=None if search else bank[:, :2].cpu().numpy(), stagger=not orient, n_envs=1024 if orient else None)
         emit(out)
     if world > 1:
         dist.barrier()
