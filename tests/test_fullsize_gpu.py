@@ -1,0 +1,94 @@
+"""BASELINE.json's full size (16 384 envs on one GPU) through size-independent properties (the oracle cannot run that many envs in
+seconds): BATCH INVARIANCE -- env e of the 16 384-env run is bit-identical to env e of a 64-env run that the oracle parity tests
+cover, so parity at full size follows --, run-to-run determinism, and physical / bookkeeping invariants over every env."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import lattice_bank
+
+pytestmark = pytest.mark.gpu
+FULL = 16384
+
+
+def _run(scene, n, steps, seed=22, bank=None, act_seed=7, hook=None):
+    from seqdex_b200.env import SdxEnv
+    from seqdex_b200.tasks.block_assembly_grasp_sim import default_tvalue_weights
+    g = SdxEnv(scene, n, 0, seed)
+    g.set_tvalue_weights(default_tvalue_weights(1))
+    if bank is not None:
+        g.set_heap_bank(bank)
+    if hook:
+        hook(g)
+    gen = torch.Generator(device="cuda").manual_seed(act_seed)
+    acts = torch.rand(steps, FULL, 23, device="cuda", generator=gen) * 2.4 - 1.2     # the same action rows whatever n is
+    for t in range(steps):
+        if t == 3:                                     # a wave of resets in the middle: envs 0, 5, 10, ... time out
+            g.tensor("PROGRESS")[::5] = 148
+        g.step(acts[t, :n].contiguous())
+    torch.cuda.synchronize()
+    return g
+
+
+NAMES = ("BRICK", "DOF", "LINK", "JAC7", "NETF", "OBS", "STATES", "REW", "RESET", "PROGRESS", "TVALUE", "TARGET_INIT", "EPISODE", "SLEEP",
+         "NCONTACT", "WSN")
+
+
+def test_grasp_sim_full_size_batch_invariance_determinism_and_invariants(scene):
+    bank = lattice_bank(scene, 4)
+    big = _run(scene, FULL, 12, bank=bank)
+    small = _run(scene, 64, 12, bank=bank)
+    for name in NAMES:
+        a, b = big.tensor(name)[:64], small.tensor(name)
+        assert torch.equal(a, b), f"{name}: env e of the {FULL}-env run differs from env e of the 64-env run"
+    again = _run(scene, FULL, 12, bank=bank)
+    for name in NAMES + ("CONSEC",):
+        assert torch.equal(big.tensor(name), again.tensor(name)), f"{name}: two identical runs differ (non-deterministic kernel)"
+    # invariants over all 16 384 envs
+    brick = big.tensor("BRICK")
+    assert torch.isfinite(brick).all() and torch.isfinite(big.tensor("OBS")).all() and torch.isfinite(big.tensor("STATES")).all()
+    qn = brick[:, 3:7, :].norm(dim=1)
+    assert float((qn - 1).abs().max()) < 1e-4                      # unit quaternions after 24 sub-steps of integration
+    assert float(brick[:, 2, :].min()) > 0.55                      # nothing sank through the bin floor / table
+    assert float(brick[:, 7:10, :].abs().max()) < 20.0             # no exploding velocities
+    prog, ep = big.tensor("PROGRESS"), big.tensor("EPISODE")
+    assert int(prog.min()) >= 1 and int(prog.max()) <= 150
+    assert set(ep.unique().tolist()) == {1, 2}                     # exactly the envs of the reset wave went through a second reset_idx
+    assert bool((ep[::5] == 2).all()) and int((ep == 2).sum()) == len(ep[::5])
+    nc = big.tensor("NCONTACT")
+    assert int(nc[:, 0].max()) <= 1024 and int(nc[:, 0].min()) > 0
+    dof = big.tensor("DOF")
+    lo, hi = torch.from_numpy(scene.dof_lo).cuda(), torch.from_numpy(scene.dof_hi).cuda()
+    assert bool(((dof[:, 0, :23] >= lo - 1e-6) & (dof[:, 0, :23] <= hi + 1e-6)).all())     # joint limits
+    assert bool(((dof[:, 2, :23] >= lo) & (dof[:, 2, :23] <= hi)).all())                   # targets are clamped (GS:1636)
+
+
+def test_orient_and_search_batch_invariance_across_scripted_resets():
+    """4096 envs vs 32 envs through the first scripted reset and a few steps (Orient: 53 contact steps inside reset_idx; Search: 60 +
+    the ray-cast render): the first 32 envs agree bit for bit"""
+    from seqdex_b200.camera import SEARCH_CAMERA, look_at
+    from seqdex_b200.scene import Scene
+    for task, kw, extra in (("BlockAssemblyOrient", dict(episode_length=75, act_moving_average=0.2), ()),
+                            ("BlockAssemblySearch", dict(episode_length=75, act_moving_average=0.6), ("SEG", "EMERGENCE", "TVOBS"))):
+        sc = Scene(task=task, **kw)
+        hook = (lambda g: g.set_camera(look_at(**SEARCH_CAMERA))) if task.endswith("Search") else None
+        bank = None if task.endswith("Search") else lattice_bank(sc, 2)
+        outs = []
+        for n in (4096, 32):
+            from seqdex_b200.env import SdxEnv
+            from seqdex_b200.tasks.block_assembly_grasp_sim import default_tvalue_weights
+            g = SdxEnv(sc, n, 0, 22)
+            g.set_tvalue_weights(default_tvalue_weights(1))
+            if bank is not None:
+                g.set_heap_bank(bank)
+            if hook:
+                hook(g)
+            gen = torch.Generator(device="cuda").manual_seed(3)
+            acts = torch.rand(4, 4096, 23, device="cuda", generator=gen) * 2 - 1
+            for t in range(4):
+                g.step(acts[t, :n].contiguous())
+            torch.cuda.synchronize()
+            outs.append(g)
+        for name in ("BRICK", "DOF", "LINK", "OBS", "STATES", "REW", "RESET", "PROGRESS", "TARGET_INIT", "EPISODE", "SLEEP") + extra:
+            assert torch.equal(outs[0].tensor(name)[:32], outs[1].tensor(name)), (task, name)
+        assert torch.isfinite(outs[0].tensor("BRICK")).all() and float(outs[0].tensor("BRICK")[:, 2, :].min()) > 0.0
