@@ -10,8 +10,10 @@ column moments per iteration and one scalar (KL) per mini-epoch, all through tor
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import math
+import os
 
 import torch
 
@@ -192,6 +194,14 @@ class A2CAgent:
         self.epoch_num = 0
         self.last_kl = 0.0
 
+    def _side_stream(self):
+        """second stream for the central-value update (SEQDEX_PPO_STREAMS=0 keeps everything on one stream)"""
+        if os.environ.get("SEQDEX_PPO_STREAMS", "1") == "0":
+            return None
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     @property
     def logstd(self):
         return self.actor.params[self.actor.nparams - self.A:]
@@ -293,33 +303,53 @@ class A2CAgent:
         self.actor.convert_batch(obs, self.xb_obs, self.xt_obs)
         self.cv.convert_batch(states, self.xb_st, self.xt_st, self.rms_mean if c.cv_normalize_input else None,
                               self.rms_var if c.cv_normalize_input else None)
-        # central value network (asymmetric critic), own optimiser lr 1e-3
-        for _ in range(c.cv_mini_epochs):
-            for i in range(nmb):
-                s = slice(i * mb, (i + 1) * mb)
-                v = self.cv.forward_pre(self.xb_st, self.xt_st, i * mb, mb)
-                _lib.check(L.sdx_ppo_value_loss(_p(v), _p(values[s]), _p(returns[s]), mb, ctypes.c_float(c.e_clip), int(c.clip_value),
-                                                ctypes.c_float(inv), _p(self.dv), _p(self.cv_stats), _stream()))
-                self.cv.backward(self.dv)
-                self._allreduce(self.cv.grads)
-                self.cv.adam(c.cv_learning_rate, c.grad_norm)
-        # actor
+        # The two networks' updates are independent once the rollout is in the buffers: the central-value chain goes to a side
+        # stream so that its small kernels (loss, norm, Adam, unpack) and GEMM tails overlap the actor chain's GEMMs and vice
+        # versa.  The steps of the two chains are ISSUED alternately (so that, with several GPUs, their all-reduces enter the
+        # communicator interleaved instead of one chain queueing behind the other); each chain runs in program order on its
+        # own stream and the results do not depend on the interleaving.
+        side = self._side_stream()
+        main = torch.cuda.current_stream()
+        if side is not None:
+            side.wait_stream(main)
+        side_ctx = (lambda: torch.cuda.stream(side)) if side is not None else contextlib.nullcontext
+
+        def cv_step(i):       # central value network (asymmetric critic), own optimiser lr 1e-3
+            s = slice(i * mb, (i + 1) * mb)
+            v = self.cv.forward_pre(self.xb_st, self.xt_st, i * mb, mb)
+            _lib.check(L.sdx_ppo_value_loss(_p(v), _p(values[s]), _p(returns[s]), mb, ctypes.c_float(c.e_clip), int(c.clip_value),
+                                            ctypes.c_float(inv), _p(self.dv), _p(self.cv_stats), _stream()))
+            self.cv.backward(self.dv)
+            self._allreduce(self.cv.grads)
+            self.cv.adam(c.cv_learning_rate, c.grad_norm)
+
+        def actor_step(i):
+            s = slice(i * mb, (i + 1) * mb)
+            mu = self.actor.forward_pre(self.xb_obs, self.xt_obs, i * mb, mb)
+            self.actor.grads[self.actor.nparams - A:].zero_()
+            _lib.check(L.sdx_ppo_actor_loss(_p(mu), _p(self.logstd), _p(actions[s]), _p(mu_old[s]), _p(self.old_logstd[i]), _p(nlp_old[s]),
+                                            _p(adv[s]), mb, A, ctypes.c_float(c.e_clip), ctypes.c_float(c.bounds_loss_coef),
+                                            ctypes.c_float(inv), _p(self.dmu), _p(self.actor.grads[self.actor.nparams - A:]),
+                                            _p(self.stats), _stream()))
+            mu_old[s].copy_(mu)                                  # dataset.update_mu_sigma (RGC:1358)
+            self.old_logstd[i].copy_(self.logstd)
+            self.actor.backward(self.dmu)
+            self._allreduce(self.actor.grads)
+            self.actor.adam(self.last_lr, c.grad_norm)
+
         self.old_logstd.copy_(self.logstd.unsqueeze(0).expand(nmb, A))
-        for ep in range(c.mini_epochs):
-            self.stats.zero_()
+        st = self.stats
+        for ep in range(max(c.mini_epochs, c.cv_mini_epochs)):
+            if ep < c.mini_epochs:
+                self.stats.zero_()
             for i in range(nmb):
-                s = slice(i * mb, (i + 1) * mb)
-                mu = self.actor.forward_pre(self.xb_obs, self.xt_obs, i * mb, mb)
-                self.actor.grads[self.actor.nparams - A:].zero_()
-                _lib.check(L.sdx_ppo_actor_loss(_p(mu), _p(self.logstd), _p(actions[s]), _p(mu_old[s]), _p(self.old_logstd[i]), _p(nlp_old[s]),
-                                                _p(adv[s]), mb, A, ctypes.c_float(c.e_clip), ctypes.c_float(c.bounds_loss_coef),
-                                                ctypes.c_float(inv), _p(self.dmu), _p(self.actor.grads[self.actor.nparams - A:]),
-                                                _p(self.stats), _stream()))
-                mu_old[s].copy_(mu)                                  # dataset.update_mu_sigma (RGC:1358)
-                self.old_logstd[i].copy_(self.logstd)
-                self.actor.backward(self.dmu)
-                self._allreduce(self.actor.grads)
-                self.actor.adam(self.last_lr, c.grad_norm)
+                if ep < c.cv_mini_epochs:
+                    with side_ctx():
+                        cv_step(i)
+                if ep < c.mini_epochs:
+                    actor_step(i)
+            if ep >= c.mini_epochs:
+                continue
             st = self.stats.clone()
             self._allreduce(st)
             kl = float(st[2]) / B                                     # one host sync per mini-epoch, like rl_games' av_kls
@@ -329,6 +359,8 @@ class A2CAgent:
                     self.last_lr = max(self.last_lr / 1.5, 1e-6)
                 if kl < 0.5 * c.kl_threshold:
                     self.last_lr = min(self.last_lr * 1.5, 1e-2)
+        if side is not None:
+            main.wait_stream(side)
         self.epoch_num += 1
         return {"kl": self.last_kl, "lr": self.last_lr, "a_loss": float(st[0]) / B, "b_loss": float(st[1]) / B,
                 "mean_reward": float(self.b_rewards.mean())}
