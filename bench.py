@@ -25,9 +25,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = 15956   # algorithmic HBM bytes / env-step (fp32 rollout)
-# dram__bytes_read.sum + dram__bytes_write.sum of k_simulate per env, from the committed ncu --set full capture
-# (profiles/r01_ncu_k_simulate_v6.txt: 47.85 MB + 33.69 MB over 4096 envs; includes the warm-start impulse cache)
-NCU_TRAFFIC_BYTES_PER_ENV = (124.820480e6 + 154.421504e6) / 16384   # dram read + write of ONE k_simulate launch at 16 384 envs
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_simulate launch at 16 384 envs, from the committed ncu --set full capture
+# (profiles/r01_ncu_k_simulate_v10_16384envs.txt: 127.1 MB read + 280.2 MB written; the writes include the contact records that
+# live in global memory behind L1 since SIM_GLOBAL_CONTACTS and the warm-start impulse cache)
+NCU_TRAFFIC_BYTES_PER_ENV = (127.120896e6 + 280.205056e6) / 16384
+NCU_ISSUE_ACTIVE = 0.4649            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
 
 
 def measured_peaks():
@@ -373,10 +375,12 @@ def main():
             "ppo": ppo_info,
             "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": NCU_TRAFFIC_BYTES_PER_ENV * n,
-                         "traffic_source": "ncu --set full at 16384 envs, profiles/r01_ncu_k_simulate_v9_16384envs.txt (scaled by envs per launch)",
+                         "traffic_source": "ncu --set full at 16384 envs, profiles/r01_ncu_k_simulate_v10_16384envs.txt (scaled by envs per launch)",
+                         "issue_slots_busy_ncu": NCU_ISSUE_ACTIVE,
                          "ms_per_launch": sim_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
-                         "note": "state-streaming bound is loose: the kernel is fp32-ALU / shared-memory bound (DESIGN.md section 6)"},
+                         "note": "state-streaming bound is loose: the kernel is bound by block-barrier waits between ~40 phases per sub-step "
+                                 "(45 % of warp stall samples, DESIGN.md section 11), not by HBM"},
             "clocks": sampler.summary(),
             "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "dropped_max": int(nc[:, 1].max())},
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
