@@ -225,6 +225,7 @@ typedef struct {
   v3 bx[NBODY]; q4 bq[NBODY]; float bR[NBODY][9];
   v3 bv[NBODY], bw[NBODY];
   v3 vfree[NB], wfree[NB];
+  float wI[NB][6];   /* world-frame inverse inertia R diag(1/I) R^T of a brick: xx xy xz yy yz zz, once per sub-step */
   float q[SDX_ND], qd[SDX_ND], tgt[SDX_ND], qdfree[SDX_ND], ieff[SDX_ND];
   fk_t K;
   /* target boxes: bricks, robot shapes, statics */
@@ -240,10 +241,23 @@ typedef struct {
   unsigned char asleep[NB], hot[NB], touch[NB];   /* sleeping (see sim_env): touch bit0 = robot, bit1 = hot brick */
 } work_t;
 
-static inline v3 brick_Iinv_mul(const sdx_scene_t* S, const work_t* W, int b, v3 u) {
-  v3 l = mtmul(W->bR[b], u);
-  l.x = l.x * S->br_invI[3 * b]; l.y = l.y * S->br_invI[3 * b + 1]; l.z = l.z * S->br_invI[3 * b + 2];
-  return mmul(W->bR[b], l);
+/* W = R diag(1/I) R^T (symmetric, six numbers), formed ONCE per sub-step and brick -- the kernel keeps it as two 16-byte
+   shared-memory records -- so that every later product with a vector is nine multiply-adds and no rotation matrix */
+static inline void brick_world_invI(const float* R, const float* invI, float* w) {
+  const float a0x = R[0] * invI[0], a0y = R[1] * invI[1], a0z = R[2] * invI[2];
+  const float a1x = R[3] * invI[0], a1y = R[4] * invI[1], a1z = R[5] * invI[2];
+  const float a2x = R[6] * invI[0], a2y = R[7] * invI[1], a2z = R[8] * invI[2];
+  w[0] = fmaf(a0z, R[2], fmaf(a0y, R[1], a0x * R[0]));
+  w[1] = fmaf(a0z, R[5], fmaf(a0y, R[4], a0x * R[3]));
+  w[2] = fmaf(a0z, R[8], fmaf(a0y, R[7], a0x * R[6]));
+  w[3] = fmaf(a1z, R[5], fmaf(a1y, R[4], a1x * R[3]));
+  w[4] = fmaf(a1z, R[8], fmaf(a1y, R[7], a1x * R[6]));
+  w[5] = fmaf(a2z, R[8], fmaf(a2y, R[7], a2x * R[6]));
+}
+static inline v3 brick_Iinv_mul(const work_t* W, int b, v3 u) {
+  const float* w = W->wI[b];
+  return V3(fmaf(w[2], u.z, fmaf(w[1], u.y, w[0] * u.x)), fmaf(w[4], u.z, fmaf(w[3], u.y, w[1] * u.x)),
+            fmaf(w[5], u.z, fmaf(w[4], u.y, w[2] * u.x)));
 }
 
 static void link_twists(const sdx_scene_t* S, work_t* W) {
@@ -272,7 +286,7 @@ static float body_k(const sdx_scene_t* S, const work_t* W, int body, v3 wpt, v3 
   if (body < NB) {
     if (W->asleep[body]) return 0.0f;   /* a sleeping brick is immovable for this sub-step */
     v3 rxd = vcross(vsub(wpt, W->bx[body]), d);
-    float k = S->br_invm[body] + vdot(rxd, brick_Iinv_mul(S, W, body, rxd));
+    float k = S->br_invm[body] + vdot(rxd, brick_Iinv_mul(W, body, rxd));
     return (float)W->nb[body] * k;
   }
   int L = body - NB;
@@ -363,6 +377,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         W->wfree[b] = vscale(W->bw[b], damp);
         if (b >= nbr || W->asleep[b]) { W->vfree[b] = V3(0, 0, 0); W->wfree[b] = V3(0, 0, 0); }
         W->bv[b] = W->vfree[b]; W->bw[b] = W->wfree[b];
+        brick_world_invI(W->bR[b], &S->br_invI[3 * b], W->wI[b]);
       }
       for (int j = 0; j < SDX_ND; ++j) {
         float I = S->dof_inertia[j], kp = S->dof_kp[j], kd = S->dof_kd[j];
@@ -552,7 +567,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         v3 T = vadd(Tk[0], Tk[1]);
         if (b < NB) {
           W->bv[b] = vmad(F, S->br_invm[b], W->vfree[b]);
-          W->bw[b] = vadd(W->wfree[b], brick_Iinv_mul(S, W, b, T));
+          W->bw[b] = vadd(W->wfree[b], brick_Iinv_mul(W, b, T));
         } else { W->linkF[b - NB] = F; W->linkM[b - NB] = T; }
       }
       for (int j = 0; j < SDX_ND; ++j) {

@@ -167,8 +167,13 @@ extern "C" int sdx_tensor(sdx_env_t* E, int kind, void** dev_ptr, int64_t shape[
   if (dtype) *dtype = dt;
   if (kind == SDX_T_CONTACTS && !E->buf[kind]) {
     CK(cudaSetDevice(E->device));
-    CK(cudaMalloc(&E->buf[kind], ne * 4));
-    CK(cudaMemset(E->buf[kind], 0, ne * 4));
+#ifdef SIM_PROFILE
+    const size_t extra = (size_t)E->n * 2 * SIM_PROF_REC * 8;   // per-warp cycle counters behind the contact rows (tools/sim_phase_cycles.py)
+#else
+    const size_t extra = 0;
+#endif
+    CK(cudaMalloc(&E->buf[kind], ne * 4 + extra));
+    CK(cudaMemset(E->buf[kind], 0, ne * 4 + extra));
     E->dump_contacts = true;
   }
   *dev_ptr = E->buf[kind];

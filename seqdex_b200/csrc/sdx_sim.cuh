@@ -43,6 +43,15 @@
 #define SIM_MIN_CTAS (SIM_GLOBAL_CONTACTS ? 4 : 3)   /* CTAs per SM the register budget is sized for */
 #endif
 #define ROBOT_TID0 (SIM_THREADS - 32)  /* the LAST warp owns the articulation: lane j = DoF j, lane L = link L */
+#define NBW (ROBOT_TID0 / 32)          /* brick warps */
+#define SIM_PROF_REC (18 * 2 * 8 + 16)  /* SIM_PROFILE builds: int64 counters per env and sub-step */
+#ifndef SIM_DEAL_RR
+#define SIM_DEAL_RR 0                  /* phase B: 16 consecutive work items per warp (1: dealt round-robin over the brick warps -- measured SLOWER,
+                                          5.40 vs 5.18 ms per launch: every warp then runs the loop for about the same maximal trip count) */
+#endif
+#ifndef SIM_GATHER_U
+#define SIM_GATHER_U 1                 /* incidences whose loads phase B issues together per lane (2 / 4 measured slower: 5.56 / 5.87 vs 5.18 ms) */
+#endif
 #define PPMAX 26                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
 
 struct SimSmem {
@@ -58,7 +67,12 @@ struct SimSmem {
   };
   unsigned char sbody[NT];
   float4 bx[NBODY], bv[NBODY], bw[NBODY];      // body origin, linear, angular velocity (16-byte records)
-  float vfree[NB][3], wfree[NB][3], binvm[NB], binvI[NB][3];
+  // per-brick records of phase B's tail, written once per sub-step (16-byte vectors: one LDS.128 each)
+  float4 bfv[NB];   // free linear velocity .xyz | inverse mass (0 while asleep)
+  float4 bfw[NB];   // free angular velocity .xyz
+  float4 bI0[NB];   // world-frame inverse inertia R diag(1/I) R^T: xx xy xz yy
+  float4 bI1[NB];   //                                              yz zz
+  int4 irec[NB];    // phase-B work items (one per awake, touched brick): a0 | na | b0 | body + (ntot << 8)
   float lq[SDX_NL][4], ja[SDX_ND][3], jo[SDX_ND][3];
   float q[SDX_ND + 1], qd[SDX_ND + 1], tgt[SDX_ND + 1], qdfree[SDX_ND + 1], ieff[SDX_ND + 1];
   float linkF[SDX_NL][3], linkM[SDX_NL][3];
@@ -68,7 +82,7 @@ struct SimSmem {
   int poff[NOWN + 1];
   int scan[SIM_THREADS];
   int ncon, ndropped;
-  unsigned char alist[NB]; int nact;   // bricks phase B has to visit: awake AND touched by at least one contact (ascending)
+  int nact;                            // bricks phase B has to visit: awake AND touched by at least one contact (irec, ascending)
   unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
   // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
 #if !SIM_GLOBAL_CONTACTS
@@ -144,10 +158,52 @@ __device__ __forceinline__ void link_twist(const sdx_scene_t* __restrict__ S, Si
   st3(M.bv[NB + L], v); st3(M.bw[NB + L], w);
 }
 
-__device__ __forceinline__ v3 brick_Iinv_mul(const float* R, v3 invI, v3 u) {
-  v3 l = mtmul(R, u);
-  l.x = l.x * invI.x; l.y = l.y * invI.y; l.z = l.z * invI.z;
-  return mmul(R, l);
+// world-frame inverse inertia of a brick, W = R diag(invI) R^T, as six numbers (xx xy xz yy | yz zz) computed ONCE per sub-step
+// (the oracle's brick_world_invI, operation for operation), and its product with a vector
+__device__ __forceinline__ void brick_world_invI(const float* R, v3 invI, float4* w0, float4* w1) {
+  const float a0x = R[0] * invI.x, a0y = R[1] * invI.y, a0z = R[2] * invI.z;
+  const float a1x = R[3] * invI.x, a1y = R[4] * invI.y, a1z = R[5] * invI.z;
+  const float a2x = R[6] * invI.x, a2y = R[7] * invI.y, a2z = R[8] * invI.z;
+  *w0 = make_float4(fmaf(a0z, R[2], fmaf(a0y, R[1], a0x * R[0])), fmaf(a0z, R[5], fmaf(a0y, R[4], a0x * R[3])),
+                    fmaf(a0z, R[8], fmaf(a0y, R[7], a0x * R[6])), fmaf(a1z, R[5], fmaf(a1y, R[4], a1x * R[3])));
+  *w1 = make_float4(fmaf(a1z, R[8], fmaf(a1y, R[7], a1x * R[6])), fmaf(a2z, R[8], fmaf(a2y, R[7], a2x * R[6])), 0.0f, 0.0f);
+}
+__device__ __forceinline__ v3 brick_Iinv_mul(const float4 w0, const float4 w1, v3 u) {
+  return V3(fmaf(w0.z, u.z, fmaf(w0.y, u.y, w0.x * u.x)), fmaf(w1.x, u.z, fmaf(w0.w, u.y, w0.y * u.x)),
+            fmaf(w1.y, u.z, fmaf(w1.x, u.y, w0.z * u.x)));
+}
+
+// phase B's inner loop: lane k of a body's lane pair sums the impulses (and their moments about xb) of the incidences
+// e = k, k + 2, k + 4, ... of that body -- owned contacts [a0, a0 + na) first, then the ascending target-side list at b0 --
+// strictly in that order (the oracle's Fk[k] / Tk[k]).  The loads of U consecutive incidences are issued together before
+// the first add, so a lane waits for one shared-memory + one L1 round trip per U incidences instead of per incidence.
+template <int U>
+__device__ __forceinline__ void gather_incident(const SimSmem& M, const float4* CA, int a0, int na, int b0, int ntot,
+                                                int k, v3 xb, v3* Fo, v3* To) {
+  v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
+#pragma unroll 1
+  for (int e0 = k; e0 < ntot; e0 += 2 * U) {
+    int idx[U];
+    float4 F4[U], A4[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ee = e0 + 2 * u;
+      idx[u] = ee < na ? a0 + ee : (ee < ntot ? (int)M.blist[b0 + (ee - na)] : 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) { F4[u] = M.cf4[idx[u]]; A4[u] = CA[idx[u]]; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ee = e0 + 2 * u;
+      if (ee < ntot) {
+        v3 f = V3(F4[u].x, F4[u].y, F4[u].z);
+        if (ee >= na) f = vneg(f);
+        F = vadd(F, f);
+        T = vadd(T, vcross(vsub(V3(A4[u].x, A4[u].y, A4[u].z), xb), f));
+      }
+    }
+  }
+  *Fo = F; *To = T;
 }
 
 __device__ __forceinline__ void contact_axes(const SimSmem& M, uint32_t word, v3* n, v3* t1, v3* t2) {
@@ -162,7 +218,7 @@ __device__ float body_k(const sdx_scene_t* __restrict__ S, const SimSmem& M, int
   if (body == STATIC_BODY) return 0.0f;
   if (body < NB) {
     v3 rxd = vcross(vsub(wpt, ld3(M.bx[body])), d);
-    float k = M.binvm[body] + vdot(rxd, brick_Iinv_mul(M.sR[body], ld3(M.binvI[body]), rxd));
+    float k = M.bfv[body].w + vdot(rxd, brick_Iinv_mul(M.bI0[body], M.bI1[body], rxd));
     return (float)M.nb[body] * k;
   }
   unsigned m = S->link_anc_mask[body - NB];
@@ -325,6 +381,16 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     const float* wsr = gws + (size_t)rb * MAXC * 4;        // impulse cache of the previous sub-step / step
     float* wsw = gws + (size_t)(1 - rb) * MAXC * 4;
     const int nprev = gwsn[rb];
+#ifdef SIM_PROFILE
+    // per pass and warp: clock64 when the warp ARRIVES at the barrier after phase A and at the one after phase B (arrival times
+    // are exact; a read placed after a BAR.SYNC.DEFER_BLOCKING is not); PMARK(k): thread 0's clock after the barrier that ends
+    // stage k of the sub-step.  Sink: behind the contact rows of the debug dump (tools/sim_phase_cycles.py).
+    long long* const prof = condump ? reinterpret_cast<long long*>(condump + ((size_t)n_envs * MAXC) * 8) + ((size_t)e * 2 + sub) * SIM_PROF_REC : nullptr;
+#define PMARK(k) do { if (prof && tid == 0) prof[18 * 2 * 8 + 4 + (k)] = clock64(); } while (0)
+#else
+#define PMARK(k) do { } while (0)
+#endif
+    PMARK(0);
     // 1. kinematics (one thread walks the chain) || brick poses + free velocities
     if (tid >= ROBOT_TID0) robot_fk(S, M, tid - ROBOT_TID0);
     bool asleep = false;
@@ -332,8 +398,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       asleep = tid < nbr && sleep_n > 0 && slpc >= sleep_n;
       M.sflag[tid] = (unsigned char)((asleep ? 1 : 0) | ((tid < nbr && slpc == 0) ? 2 : 0));
       M.touch[tid] = 0;
-      M.binvm[tid] = asleep ? 0.0f : S->br_invm[tid];        // a sleeping brick is immovable for this sub-step
-      st3(M.binvI[tid], asleep ? V3(0.0f, 0.0f, 0.0f) : V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]));
+      const float invm = asleep ? 0.0f : S->br_invm[tid];    // a sleeping brick is immovable for this sub-step
+      const v3 invI = asleep ? V3(0.0f, 0.0f, 0.0f) : V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]);
       qmat(bqr, M.sR[tid]);
       st3(M.sc[tid], bxr); st3(M.bx[tid], bxr);
       float damp = 1.0f - h * S->brick_ang_damp;
@@ -342,7 +408,9 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       v3 wfree = vscale(bwr, damp);
       if (tid >= nbr || asleep) { vfree = V3(0.0f, 0.0f, 0.0f); wfree = V3(0.0f, 0.0f, 0.0f); }
       st3(M.bv[tid], vfree); st3(M.bw[tid], wfree);
-      st3(M.vfree[tid], vfree); st3(M.wfree[tid], wfree);
+      M.bfv[tid] = make_float4(vfree.x, vfree.y, vfree.z, invm);
+      M.bfw[tid] = make_float4(wfree.x, wfree.y, wfree.z, 0.0f);
+      brick_world_invI(M.sR[tid], invI, &M.bI0[tid], &M.bI1[tid]);
     }
     __syncthreads();
     // 2. robot shape poses || implicit PD free joint velocities
@@ -369,6 +437,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     // 3. link twists
     if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0, my_anc);
     __syncthreads();
+    PMARK(1);
     // 4. world AABBs + per-sub-step travel bound of every moving shape
     if (tid < n_owner) {
       int t = tid;
@@ -390,6 +459,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     }
     if (tid == 0) { M.ndropped = 0; }
     __syncthreads();
+    PMARK(2);
     // 5. broad phase: TWO threads per owner shape (thread tid: owner tid & 127, target-range half tid >> 7); the second
     //    half's hits go to a scratch list (in the idle impulse array) and are appended in target order, so the candidate
     //    lists -- including what overflows KC -- are the ones a single ascending sweep produces
@@ -438,6 +508,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       }
     }
     __syncthreads();
+    PMARK(3);
     if (tid < 32) {
       for (int a = tid; a < n_owner; a += 32) M.poff[a] = M.ncand[a];
       __syncwarp();
@@ -445,6 +516,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       if (tid == 0) M.poff[n_owner] = tot;
     }
     __syncthreads();
+    PMARK(4);
     // 6. narrow phase, pass 1 (pair-parallel): per-pair hit masks + running contact offsets.  The pair tables live in
     //    the (still unused) impulse / inverse-mass arrays.  Contiguous pair chunks per thread => offsets are in pair order.
     const int npairs = M.poff[n_owner];
@@ -471,6 +543,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     }
     M.scan[tid] = mycount;
     __syncthreads();
+    PMARK(5);
     if (tid < 32) {
       int o = warp_excl_scan(M.scan, SIM_THREADS, tid);
       if (tid == 0) { M.ncon = o < MAXC ? o : MAXC; if (o > MAXC) atomicAdd(&M.ndropped, o - MAXC); }
@@ -482,6 +555,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       for (int i = p0; i < p1; ++i) { pstart[i] = (unsigned short)min(run, 65535); run += __popc((unsigned)pmask[i]); }
     }
     __syncthreads();
+    PMARK(6);
     // pass 2 (contact-parallel): slot -> (pair, point) by binary search over the pair offsets, then regenerate the hit
     {
       const int ncon_w = M.ncon;
@@ -540,6 +614,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       }
     }
     __syncthreads();
+    PMARK(7);
     const int ncon = M.ncon;
     // 7. incidence: owned contacts of a body are one contiguous range (contacts are generated owner-major);
     //    target-side contacts go to a per-body list, filled with atomics and then sorted ascending
@@ -587,7 +662,10 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         const int b = r * 32 + tid;
         const bool act = b < NB && !(M.sflag[b] & 1) && M.nb[b] > 0;
         const unsigned bal = __ballot_sync(0xffffffffu, act);
-        if (act) M.alist[base + __popc(bal & ((1u << tid) - 1u))] = (unsigned char)b;
+        if (act) {                                             // phase B's work item: everything a lane pair needs in one LDS.128
+          const int a0 = M.astart[b];
+          M.irec[base + __popc(bal & ((1u << tid) - 1u))] = make_int4(a0, M.aend[b] - a0, M.boff[b], b | (M.nb[b] << 8));
+        }
         base += __popc(bal);
       }
       if (tid == 0) M.nact = base;
@@ -613,6 +691,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         o[5] = A4.w; o[6] = 0.0f; o[7] = 0.0f;
       }
     __syncthreads();
+    PMARK(8);
     // 8. inverse mass-split effective masses along n, t1, t2
     for (int i = tid; i < ncon; i += SIM_THREADS) {
       const float4 A4 = CA[i];
@@ -628,6 +707,11 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     __syncthreads();
     // 9. Jacobi iterations on total impulses
     const float mu = S->friction;
+    PMARK(9);
+#ifdef SIM_PROFILE
+    if (prof && tid == 0) { prof[18 * 2 * 8] = clock64(); prof[18 * 2 * 8 + 1] = ncon; prof[18 * 2 * 8 + 2] = M.nact; }
+    if (prof && tid == ROBOT_TID0) prof[18 * 2 * 8 + 3] = (long long)__popc(ract);
+#endif
     for (int it = -1; it < iters; ++it) {                      // it = -1: phase B only = apply the warm-start impulses
       if (it >= 0)
       for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
@@ -647,42 +731,52 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         f = vmad(t2, l2, vmad(t1, l1, vscale(n, ln)));
         M.cf4[i] = make_float4(f.x, f.y, f.z, 0.0f);
       }
+#ifdef SIM_PROFILE
+      if (prof && (tid & 31) == 0) prof[((it + 1) * 2 + 0) * 8 + (tid >> 5)] = clock64();
+#endif
       __syncthreads();
       // phase B: TWO lanes per body, lane k sums incidences e = k (mod 2); partials combined 0+1.
-      // brick warps (all but the last): only bricks that are awake and in contact (alist) x 2 lanes; the others keep
-      // their free velocity (zero when asleep).
+      // brick warps (all but the last): only bricks that are awake and in contact (irec, built once per sub-step: one LDS.128
+      // per lane and pass instead of a chain of five), 16 per warp; the other bricks keep their free velocity (zero when asleep).
       // last warp: the articulation -- only links that HAVE contacts are gathered (their wrenches are zero otherwise, set
       // once per sub-step), and the joint-space update is skipped entirely while the robot touches nothing.
       const bool robot_warp = tid >= ROBOT_TID0;
-      const int n_items = robot_warp ? 2 * __popc(ract) : 2 * M.nact;
-      const int per_pass = robot_warp ? 32 : ROBOT_TID0;
+      if (!robot_warp) {
+        const int nact = M.nact;
 #pragma unroll 1
-      for (int base = 0; base < n_items; base += per_pass) {
-        const int item = base + (robot_warp ? tid - ROBOT_TID0 : tid);
-        if (!robot_warp && (item & ~31) >= n_items) continue;   // whole warp beyond the item range
-        const bool live = item < n_items;
-        const int body = !robot_warp ? (live ? (int)M.alist[item >> 1] : 0) : NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
-        const int k = item & 1;
-        const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
-        const v3 xb = body < NB ? ld3(M.bx[body]) : V3(0.0f, 0.0f, 0.0f);
-        v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
-        for (int ee = k; ee < ntot; ee += 2) {
-          const bool own = ee < na;
-          const int i = own ? a0 + ee : (int)M.blist[b0 + (ee - na)];
-          const float4 F4 = M.cf4[i], A4 = CA[i];
-          v3 f = V3(F4.x, F4.y, F4.z);
-          if (!own) f = vneg(f);
-          v3 wpt = V3(A4.x, A4.y, A4.z);
-          F = vadd(F, f);
-          T = vadd(T, vcross(vsub(wpt, xb), f));
+#if SIM_DEAL_RR
+        for (int base = (tid >> 5); base < nact; base += 16 * NBW) {      // warp-uniform: the warp's first item
+          const int item = base + ((tid & 31) >> 1) * NBW;
+#else
+        for (int base = (tid >> 5) * 16; base < nact; base += 16 * NBW) {
+          const int item = base + ((tid & 31) >> 1);
+#endif
+          const bool live = item < nact;
+          const int4 r = M.irec[live ? item : 0];
+          const int body = r.w & 255;
+          v3 F, T;
+          gather_incident<SIM_GATHER_U>(M, CA, r.x, r.y, r.z, live ? (r.w >> 8) : 0, tid & 1, ld3(M.bx[body]), &F, &T);
+          F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
+          T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
+          if (!(tid & 1) && live) {
+            const float4 fv = M.bfv[body], fw = M.bfw[body];
+            st3(M.bv[body], vmad(F, fv.w, V3(fv.x, fv.y, fv.z)));
+            st3(M.bw[body], vadd(V3(fw.x, fw.y, fw.z), brick_Iinv_mul(M.bI0[body], M.bI1[body], T)));
+          }
         }
-        F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
-        T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
-        if (k == 0 && live) {
-          if (body < NB) {
-            st3(M.bv[body], vmad(F, M.binvm[body], ld3(M.vfree[body])));
-            st3(M.bw[body], vadd(ld3(M.wfree[body]), brick_Iinv_mul(M.sR[body], ld3(M.binvI[body]), T)));
-          } else { st3(M.linkF[body - NB], F); st3(M.linkM[body - NB], T); }
+      } else {
+        const int n_items = 2 * __popc(ract);
+#pragma unroll 1
+        for (int base = 0; base < n_items; base += 32) {
+          const int item = base + tid - ROBOT_TID0;
+          const bool live = item < n_items;
+          const int body = NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
+          const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
+          v3 F, T;
+          gather_incident<SIM_GATHER_U>(M, CA, a0, na, b0, ntot, item & 1, V3(0.0f, 0.0f, 0.0f), &F, &T);
+          F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
+          T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
+          if (!(item & 1) && live) { st3(M.linkF[body - NB], F); st3(M.linkM[body - NB], T); }
         }
       }
       if (robot_warp && ract != 0u) {                          // joint-space impulse + link twists (one warp)
@@ -699,8 +793,12 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
         __syncwarp();
         if (tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0, my_anc);
       }
+#ifdef SIM_PROFILE
+      if (prof && (tid & 31) == 0) prof[((it + 1) * 2 + 1) * 8 + (tid >> 5)] = clock64();
+#endif
       __syncthreads();
     }
+    PMARK(10);
     for (int i = tid; i < ncon; i += SIM_THREADS) { const float4 F4 = M.cf4[i]; wsw[4 * i + 1] = F4.x; wsw[4 * i + 2] = F4.y; wsw[4 * i + 3] = F4.z; }
     if (tid == 0) gwsn[1 - rb] = ncon;
     rb = 1 - rb;
@@ -747,6 +845,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       M.q[j] = qn; M.qd[j] = qdj;
     }
     __syncthreads();
+    PMARK(11);
   }
 
   // ---- epilogue: brick tile back through shared memory + TMA bulk store; task-visible robot rows
