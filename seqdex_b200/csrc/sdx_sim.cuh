@@ -49,6 +49,30 @@
 #define SIM_DEAL_RR 0                  /* phase B: 16 consecutive work items per warp (1: dealt round-robin over the brick warps -- measured SLOWER,
                                           5.40 vs 5.18 ms per launch: every warp then runs the loop for about the same maximal trip count) */
 #endif
+#ifndef SIM_SMALL_CODE
+#define SIM_SMALL_CODE 1               /* out-of-line FK, rolled joint / axis loops (see robot_fk) */
+#endif
+#if SIM_SMALL_CODE
+#define SIM_FK_INLINE __noinline__
+#else
+#define SIM_FK_INLINE
+#endif
+#ifndef SIM_BROAD_ROLLED
+#define SIM_BROAD_ROLLED 1             /* broad-phase target loops kept rolled (code size; A/B profiles/r01_ab_code_size.txt) */
+#endif
+#if SIM_BROAD_ROLLED
+#define SIM_BROAD_UNROLL _Pragma("unroll 1")
+#else
+#define SIM_BROAD_UNROLL
+#endif
+#ifndef SIM_SCAN_OUTLINE
+#define SIM_SCAN_OUTLINE 1             /* one out-of-line copy of the warp scan */
+#endif
+#if SIM_SCAN_OUTLINE
+#define SIM_SCAN_INLINE __noinline__
+#else
+#define SIM_SCAN_INLINE __forceinline__
+#endif
 #ifndef SIM_GATHER_U
 #define SIM_GATHER_U 1                 /* incidences whose loads phase B issues together per lane (2 / 4 measured slower: 5.56 / 5.87 vs 5.18 ms) */
 #endif
@@ -96,7 +120,7 @@ static_assert(NOWN * KC * 2 <= 8192 && 8192 + NOWN * KC * 2 <= MAXC * 16 && NOWN
               "the pair tables / candidate overflow lists are laid out inside the impulse array (cf4)");
 
 // exclusive prefix sum of arr[0..n) (n <= 256) by ONE warp, in place; returns the total to every lane
-__device__ __forceinline__ int warp_excl_scan(int* arr, int n, int lane) {
+__device__ SIM_SCAN_INLINE int warp_excl_scan(int* arr, int n, int lane) {
   constexpr int PER = 8;
   int v[PER], s = 0;
 #pragma unroll
@@ -134,14 +158,20 @@ __device__ __forceinline__ void fk_joint(const sdx_scene_t* __restrict__ S, SimS
   st3(M.ja[j], qrot(qj, ax));
   st3(M.jo[j], x);
 }
-__device__ void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M, int lane) {
+// Code size is a performance number in this kernel (128 KB of SASS against the SM's instruction cache, four CTAs in different
+// phases: sm__icc_request_hit_rate 83 %): ONE out-of-line copy, joint loops kept rolled -- the chain is serial anyway.
+__device__ SIM_FK_INLINE void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M, int lane) {
   if (lane == 0) {
     st3(M.bx[NB], V3(S->base_pos[0], S->base_pos[1], S->base_pos[2]));
     M.lq[0][0] = S->base_quat[0]; M.lq[0][1] = S->base_quat[1]; M.lq[0][2] = S->base_quat[2]; M.lq[0][3] = S->base_quat[3];
+#pragma unroll 1
     for (int j = 0; j < 7; ++j) fk_joint(S, M, j);
   }
   __syncwarp();
-  if (lane < 4) for (int j = 7 + 4 * lane; j < 11 + 4 * lane; ++j) fk_joint(S, M, j);
+  if (lane < 4) {
+#pragma unroll 1
+    for (int j = 7 + 4 * lane; j < 11 + 4 * lane; ++j) fk_joint(S, M, j);
+  }
   __syncwarp();
 }
 
@@ -485,15 +515,20 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
           };
           // the target index space is bricks [0, nbr) | robot shapes [NB, NB+nrs) | statics [NB+nrs, n_target): one loop per
           // class with the class-level filters hoisted (same ascending order as one sweep over t)
+SIM_BROAD_UNROLL
           for (int t = max(tlo, 0); t < min(thi, nbr); ++t) {
             if (t == a) continue;
             if (a_sl && (M.sflag[t] & 1)) continue;              // neither box can move
             test(t);
           }
-          if (a < NB)                                            // robot-robot pairs are filtered (GS:906)
+          if (a < NB) {                                          // robot-robot pairs are filtered (GS:906)
+SIM_BROAD_UNROLL
             for (int t = max(tlo, NB); t < min(thi, NB + nrs); ++t) test(t);
-          if (!a_sl)                                             // a sleeping brick against a static: neither box can move
+          }
+          if (!a_sl) {                                           // a sleeping brick against a static: neither box can move
+SIM_BROAD_UNROLL
             for (int t = max(tlo, NB + nrs); t < thi; ++t) test(t);
+          }
         }
         if (half) tmpn[a] = k; else M.ncand[a] = k;
         if (dropped) atomicAdd(&M.ndropped, dropped);
@@ -697,12 +732,26 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       const float4 A4 = CA[i];
       uint32_t wd = __float_as_uint(CB[i].w);
       int a = wd & 255, b = (wd >> 8) & 255;
-      v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
       v3 wpt = V3(A4.x, A4.y, A4.z);
+#if SIM_SMALL_CODE
+      float inv[3];
+      const int sh = (wd >> 16) & 255, k = (wd >> 24) & 3;
+#pragma unroll 1
+      for (int ax = 0; ax < 3; ++ax) {                        // n, t1, t2 in turn (contact_axes), one copy of body_k x 2
+        const int col = k + ax >= 3 ? k + ax - 3 : k + ax;
+        v3 d = mcol(M.sR[sh], col);
+        if (ax == 0) d = vscale(d, ((wd >> 26) & 1) ? -1.0f : 1.0f);
+        const float iv = 1.0f / (body_k(S, M, a, wpt, d) + body_k(S, M, b, wpt, d));
+        if (ax == 0) inv[0] = iv; else if (ax == 1) inv[1] = iv; else inv[2] = iv;
+      }
+      CB[i] = make_float4(inv[0], inv[1], inv[2], __uint_as_float(wd));
+#else
+      v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
       float i0 = 1.0f / (body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n));
       float i1 = 1.0f / (body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1));
       float i2 = 1.0f / (body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2));
       CB[i] = make_float4(i0, i1, i2, __uint_as_float(wd));
+#endif
     }
     __syncthreads();
     // 9. Jacobi iterations on total impulses
