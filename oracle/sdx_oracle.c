@@ -239,6 +239,7 @@ typedef struct {
   v3 linkF[SDX_NL], linkM[SDX_NL];
   uint32_t ckey[SDX_MAX_CONTACTS];
   unsigned char asleep[NB], hot[NB], touch[NB];   /* sleeping (see sim_env): touch bit0 = robot, bit1 = hot brick */
+  unsigned char built_asleep[NB]; int cand_dropped; /* candidate lists are kept over the sub-steps of a step (see sim_env 3.) */
 } work_t;
 
 /* W = R diag(1/I) R^T (symmetric, six numbers), formed ONCE per sub-step and brick -- the kernel keeps it as two 16-byte
@@ -407,31 +408,42 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       }
       W->spd[t] = spd;
     }
-    int cand_dropped = 0;
-    for (int a = 0; a < n_owner; ++a) {
-      int k = 0;
-      if (a < NB && a >= nbr) { W->ncand[a] = 0; continue; }
-      for (int t = 0; t < n_target; ++t) {
-        if (t == a) continue;
-        if (t < NB && t >= nbr) continue;
-        if (a >= NB && t >= NB && t < NB + nrs) continue; /* robot-robot filtered (GS:906 filter -1) */
-        if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue; /* neither box can move */
-        v3 d = vsub(W->sc[a], W->sc[t]);
-        float m = margin + W->spd[a] + W->spd[t];
-        int hit = fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
-                  fabsf(d.z) <= W->sa[a].z + W->sa[t].z + m;
-        if (hit) { if (k < KC) W->cand[a][k++] = (unsigned char)t; else cand_dropped++; }
+    /* The candidate lists are built in the FIRST sub-step of a step for ALL its sub-steps -- the travel bounds scaled by the
+     * number of sub-steps left, plus the speed gravity adds in between -- and rebuilt in a later sub-step only if a brick that
+     * was asleep when they were built has been woken since (its pairs with sleeping bricks and statics were filtered). */
+    int rebuild = sub == 0;
+    if (sub > 0) for (int b = 0; b < NB; ++b) if (W->built_asleep[b] && !W->asleep[b]) rebuild = 1;
+    if (rebuild) {
+      const int left = S->substeps - sub;
+      const float infl = (float)left, slack = (float)(left - 1) * ((h * h) * fabsf(S->gravity_z));
+      for (int b = 0; b < NB; ++b) W->built_asleep[b] = W->asleep[b];
+      W->cand_dropped = 0;
+      for (int a = 0; a < n_owner; ++a) {
+        int k = 0;
+        if (a < NB && a >= nbr) { W->ncand[a] = 0; continue; }
+        for (int t = 0; t < n_target; ++t) {
+          if (t == a) continue;
+          if (t < NB && t >= nbr) continue;
+          if (a >= NB && t >= NB && t < NB + nrs) continue; /* robot-robot filtered (GS:906 filter -1) */
+          if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue; /* neither box can move */
+          v3 d = vsub(W->sc[a], W->sc[t]);
+          float m = margin + infl * (W->spd[a] + W->spd[t]) + slack;
+          int hit = fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
+                    fabsf(d.z) <= W->sa[a].z + W->sa[t].z + m;
+          if (hit) { if (k < KC) W->cand[a][k++] = (unsigned char)t; else W->cand_dropped++; }
+        }
+        W->ncand[a] = k;
       }
-      W->ncand[a] = k;
     }
     /* 4. narrow phase, per ordered pair (owner a, target t): reference face of t = its axis of least
      *    overlap with a (SAT over t's three face axes); a's sample points that lie over that face and
      *    within the speculative margin below/above it become contacts.  Order: owner, candidate, point. */
-    W->ncon = 0; W->ndropped = cand_dropped;
+    W->ncon = 0; W->ndropped = W->cand_dropped;
     for (int a = 0; a < n_owner; ++a) {
       int npts = (a < NB && W->sh[a].x > 0.04f) ? 12 : 8; /* long bricks add 4 mid-edge points */
       for (int ci = 0; ci < W->ncand[a]; ++ci) {
         int t = W->cand[a][ci];
+        if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue; /* kept list, both asleep by now */
         float m = margin + W->spd[a] + W->spd[t];
         v3 lc = mtmul(W->sR[t], vsub(W->sc[a], W->sc[t]));
         float C[9]; /* C = R_t^T R_a */

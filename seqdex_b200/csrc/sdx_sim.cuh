@@ -105,7 +105,7 @@ struct SimSmem {
   int astart[NBODY], aend[NBODY], boff[NBODY + 1], bcur[NBODY];
   int poff[NOWN + 1];
   int scan[SIM_THREADS];
-  int ncon, ndropped;
+  int ncon, ndropped, ndrop_cand;      // ndrop_cand: candidates beyond KC when the lists were last built
   int nact;                            // bricks phase B has to visit: awake AND touched by at least one contact (irec, ascending)
   unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
   // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
@@ -378,6 +378,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   v3 bxr = V3(0, 0, 0), bvr = V3(0, 0, 0), bwr = V3(0, 0, 0);
   q4 bqr = Q4(0, 0, 0, 1);
   v3 halfb = V3(0, 0, 0);
+  bool built_asleep = false;                                     // was this brick asleep when the candidate lists were built?
   int slpc = (tid < NB) ? (int)slp[(size_t)e * NB + tid] : 0;   // sub-steps since this brick was last hot (oracle: sim_env SLEEPING)
   const int sleep_n = S->sleep_substeps;
   const unsigned my_anc = (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) ? S->link_anc_mask[tid - ROBOT_TID0] : 0u;
@@ -488,12 +489,18 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       M.sab[t] = make_float4(hs.x, hs.y, hs.z, 0.0f);
     }
     if (tid == 0) { M.ndropped = 0; }
-    __syncthreads();
+    // The candidate lists are built in the FIRST sub-step of a step for ALL its sub-steps (travel bounds scaled by the number of
+    // sub-steps left, plus the speed gravity adds in between) and rebuilt later only if a brick that was asleep when they were
+    // built has been woken since: its pairs with sleeping bricks and statics were filtered (oracle: sim_env 3.)
+    const int rebuild = __syncthreads_or(sub == 0 || (tid < NB && built_asleep && !asleep));
     PMARK(2);
     // 5. broad phase: TWO threads per owner shape (thread tid: owner tid & 127, target-range half tid >> 7); the second
     //    half's hits go to a scratch list (in the idle impulse array) and are appended in target order, so the candidate
     //    lists -- including what overflows KC -- are the ones a single ascending sweep produces
-    {
+    if (rebuild) {
+      const int left = substeps - sub;
+      const float infl = (float)left, slack = (float)(left - 1) * ((h * h) * fabsf(S->gravity_z));
+      built_asleep = asleep;
       unsigned char* tmpc = cf_bytes;                                       // [NOWN][KC]
       int* tmpn = reinterpret_cast<int*>(cf_bytes + NOWN * KC);             // [NOWN]
       const int a = tid & 127, half = tid >> 7;
@@ -509,7 +516,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
           auto test = [&](int t) {
             const v3 d = vsub(ca, ld3(M.sc[t]));
             const float4 T4 = M.sab[t];
-            const float m = margin + A4.w + T4.w;
+            const float m = margin + infl * (A4.w + T4.w) + slack;
             const bool hit = fabsf(d.x) <= A4.x + T4.x + m && fabsf(d.y) <= A4.y + T4.y + m && fabsf(d.z) <= A4.z + T4.z + m;
             if (hit) { if (k < KC) dst[k++] = (unsigned char)t; else dropped++; }
           };
@@ -541,16 +548,19 @@ SIM_BROAD_UNROLL
         M.ncand[tid] = k;
         if (dropped) atomicAdd(&M.ndropped, dropped);
       }
+      __syncthreads();
+      PMARK(3);
+      if (tid < 32) {
+        for (int a = tid; a < n_owner; a += 32) M.poff[a] = M.ncand[a];
+        __syncwarp();
+        int tot = warp_excl_scan(M.poff, n_owner, tid);
+        if (tid == 0) { M.poff[n_owner] = tot; M.ndrop_cand = M.ndropped; }
+      }
+      __syncthreads();
+    } else {
+      if (tid == 0) M.ndropped = M.ndrop_cand;                 // lists, pair offsets and their drop count stand
+      PMARK(3);
     }
-    __syncthreads();
-    PMARK(3);
-    if (tid < 32) {
-      for (int a = tid; a < n_owner; a += 32) M.poff[a] = M.ncand[a];
-      __syncwarp();
-      int tot = warp_excl_scan(M.poff, n_owner, tid);
-      if (tid == 0) M.poff[n_owner] = tot;
-    }
-    __syncthreads();
     PMARK(4);
     // 6. narrow phase, pass 1 (pair-parallel): per-pair hit masks + running contact offsets.  The pair tables live in
     //    the (still unused) impulse / inverse-mass arrays.  Contiguous pair chunks per thread => offsets are in pair order.
@@ -568,7 +578,8 @@ SIM_BROAD_UNROLL
         float m = margin + M.sab[a].w + M.sab[t].w;
         unsigned short mk = 0;
         PairGeom G;
-        if (pair_geom(M, a, t, m, G, t >= NB + nrs)) {
+        const bool dead = a < NB && (M.sflag[a] & 1) && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)));   // kept list, both asleep by now
+        if (!dead && pair_geom(M, a, t, m, G, t >= NB + nrs)) {
           int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
           for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, margin, &d)) mk |= (unsigned short)(1u << p); }
         }
