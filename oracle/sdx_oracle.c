@@ -585,7 +585,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       for (int j = 0; j < SDX_ND; ++j) {
         v3 Fd = V3(0, 0, 0), Md = V3(0, 0, 0);
         for (int L = 0; L < SDX_NL; ++L)
-          if (S->link_anc_mask[L] & (1u << j)) { Fd = vadd(Fd, W->linkF[L]); Md = vadd(Md, W->linkM[L]); }
+          if ((S->link_anc_mask[L] & (1u << j)) && W->nb[NB + L] > 0) { Fd = vadd(Fd, W->linkF[L]); Md = vadd(Md, W->linkM[L]); } /* links in contact only */
         float g = vdot(W->K.ja[j], vsub(Md, vcross(W->K.jo[j], Fd)));
         W->qd[j] = W->qdfree[j] + g / W->ieff[j];
       }

@@ -73,6 +73,9 @@
 #else
 #define SIM_SCAN_INLINE __forceinline__
 #endif
+#ifndef SIM_FK_WARP
+#define SIM_FK_WARP 1                  /* forward kinematics by the whole robot warp in lockstep (0: one lane per chain) */
+#endif
 #ifndef SIM_GATHER_U
 #define SIM_GATHER_U 1                 /* incidences whose loads phase B issues together per lane (2 / 4 measured slower: 5.56 / 5.87 vs 5.18 ms) */
 #endif
@@ -160,6 +163,49 @@ __device__ __forceinline__ void fk_joint(const sdx_scene_t* __restrict__ S, SimS
 }
 // Code size is a performance number in this kernel (128 KB of SASS against the SM's instruction cache, four CTAs in different
 // phases: sm__icc_request_hit_rate 83 %): ONE out-of-line copy, joint loops kept rolled -- the chain is serial anyway.
+#if SIM_FK_WARP
+// The whole warp walks the tree in lockstep.  What a joint needs that does NOT depend on its parent -- its constants, the sine
+// and cosine of its angle -- is prepared by lane j for all 23 joints at once and handed to the chain by shuffle; the chain
+// itself carries only what is serial: two quaternion products per joint for the link frames (7 arm steps, then the four
+// finger chains side by side in lanes 0-3), and later one vector add per joint for the origins.  Joint axes and offsets are
+// again one joint per lane.  Every product is the one fk_joint forms, operand for operand: same bits, a third of the
+// instructions on the critical path (a lone lane used to issue all ~150 instructions of each of 11 chained joints).
+__device__ __forceinline__ q4 shfl_q4(q4 a, int src) {
+  return Q4(__shfl_sync(0xffffffffu, a.x, src), __shfl_sync(0xffffffffu, a.y, src), __shfl_sync(0xffffffffu, a.z, src),
+            __shfl_sync(0xffffffffu, a.w, src));
+}
+__device__ SIM_FK_INLINE void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M, int lane) {
+  const int j = lane < SDX_ND ? lane : 0;
+  const q4 qf = Q4(S->joint_quat[4 * j], S->joint_quat[4 * j + 1], S->joint_quat[4 * j + 2], S->joint_quat[4 * j + 3]);
+  const v3 ax = V3(S->joint_axis[3 * j], S->joint_axis[3 * j + 1], S->joint_axis[3 * j + 2]);
+  float sn, cs;
+  sdx_sincos(0.5f * M.q[j], &sn, &cs);
+  const q4 qr = Q4(ax.x * sn, ax.y * sn, ax.z * sn, cs);
+  q4 qP = Q4(S->base_quat[0], S->base_quat[1], S->base_quat[2], S->base_quat[3]);
+  if (lane == 0) { M.lq[0][0] = qP.x; M.lq[0][1] = qP.y; M.lq[0][2] = qP.z; M.lq[0][3] = qP.w; }
+#pragma unroll 1
+  for (int i = 0; i < 11; ++i) {                               // steps 0-6: the arm (all lanes alike); 7-10: finger (lane & 3)
+    const int src = i < 7 ? i : 4 * (lane & 3) + i;            // = 7 + 4 f + (i - 7)
+    const q4 ql = qmul(qmul(qP, shfl_q4(qf, src)), shfl_q4(qr, src));
+    if (lane == 0 || (i >= 7 && lane < 4)) { M.lq[src + 1][0] = ql.x; M.lq[src + 1][1] = ql.y; M.lq[src + 1][2] = ql.z; M.lq[src + 1][3] = ql.w; }
+    qP = ql;
+  }
+  __syncwarp();
+  const int P = S->body_parent[j + 1];
+  const q4 qPj = Q4(M.lq[P][0], M.lq[P][1], M.lq[P][2], M.lq[P][3]);
+  const v3 d = qrot(qPj, V3(S->joint_xyz[3 * j], S->joint_xyz[3 * j + 1], S->joint_xyz[3 * j + 2]));
+  if (lane < SDX_ND) st3(M.ja[j], qrot(qmul(qPj, qf), ax));
+  v3 x = V3(S->base_pos[0], S->base_pos[1], S->base_pos[2]);
+  if (lane == 0) st3(M.bx[NB], x);
+#pragma unroll 1
+  for (int i = 0; i < 11; ++i) {
+    const int src = i < 7 ? i : 4 * (lane & 3) + i;
+    x = vadd(x, V3(__shfl_sync(0xffffffffu, d.x, src), __shfl_sync(0xffffffffu, d.y, src), __shfl_sync(0xffffffffu, d.z, src)));
+    if (lane == 0 || (i >= 7 && lane < 4)) { st3(M.bx[NB + src + 1], x); st3(M.jo[src], x); }
+  }
+  __syncwarp();
+}
+#else
 __device__ SIM_FK_INLINE void robot_fk(const sdx_scene_t* __restrict__ S, SimSmem& M, int lane) {
   if (lane == 0) {
     st3(M.bx[NB], V3(S->base_pos[0], S->base_pos[1], S->base_pos[2]));
@@ -174,6 +220,8 @@ __device__ SIM_FK_INLINE void robot_fk(const sdx_scene_t* __restrict__ S, SimSme
   }
   __syncwarp();
 }
+
+#endif
 
 __device__ __forceinline__ void link_twist(const sdx_scene_t* __restrict__ S, SimSmem& M, int L, unsigned m) {
   v3 w = V3(0.0f, 0.0f, 0.0f), v = V3(0.0f, 0.0f, 0.0f);
@@ -587,17 +635,19 @@ SIM_BROAD_UNROLL
         mycount += __popc((unsigned)mk);
       }
     }
-    M.scan[tid] = mycount;
-    __syncthreads();
-    PMARK(5);
-    if (tid < 32) {
-      int o = warp_excl_scan(M.scan, SIM_THREADS, tid);
-      if (tid == 0) { M.ncon = o < MAXC ? o : MAXC; if (o > MAXC) atomicAdd(&M.ndropped, o - MAXC); }
-    }
+    // running contact offsets: warp-level inclusive scan of the per-thread counts + the totals of the warps before (one barrier)
+    int incl = mycount;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+    if ((tid & 31) == 31) M.scan[tid >> 5] = incl;
     if (tid < NBODY) { M.astart[tid] = 0; M.aend[tid] = 0; M.nb[tid] = 0; }
     __syncthreads();
+    PMARK(5);
     {
-      int run = M.scan[tid];
+      int run = incl - mycount, total = 0;
+#pragma unroll
+      for (int w = 0; w < SIM_THREADS / 32; ++w) { const int v = M.scan[w]; if (w < (tid >> 5)) run += v; total += v; }
+      if (tid == 0) { M.ncon = total < MAXC ? total : MAXC; if (total > MAXC) atomicAdd(&M.ndropped, total - MAXC); }
       for (int i = p0; i < p1; ++i) { pstart[i] = (unsigned short)min(run, 65535); run += __popc((unsigned)pmask[i]); }
     }
     __syncthreads();
@@ -646,13 +696,18 @@ SIM_BROAD_UNROLL
           wsw[4 * slot] = __uint_as_float(key);
           v3 f0 = V3(0.0f, 0.0f, 0.0f);
           if (warm > 0.0f) {
-            int lo2 = 0, hi2 = nprev - 1;
+            // the keys of both sub-steps ascend with the contact order and most contacts persist in place: look at the same
+            // slot first, gallop away from it, then bisect the bracket (finds what a plain bisection finds, in 1-3 probes
+            // for a settled heap instead of 10 dependent global loads)
+            int lo2 = 0, hi2 = nprev - 1, mid = slot < hi2 ? slot : hi2, step = 1, dir = 0;
             while (lo2 <= hi2) {
-              int mid = (lo2 + hi2) >> 1;
-              uint32_t kv = __float_as_uint(wsr[4 * mid]);
-              if (kv < key) lo2 = mid + 1;
-              else if (kv > key) hi2 = mid - 1;
-              else { f0 = V3(warm * wsr[4 * mid + 1], warm * wsr[4 * mid + 2], warm * wsr[4 * mid + 3]); break; }
+              const uint32_t kv = __float_as_uint(wsr[4 * mid]);
+              if (kv == key) { f0 = V3(warm * wsr[4 * mid + 1], warm * wsr[4 * mid + 2], warm * wsr[4 * mid + 3]); break; }
+              const int d = kv < key ? 1 : -1;
+              if (d > 0) lo2 = mid + 1; else hi2 = mid - 1;
+              if (dir == 0) dir = d;
+              if (dir == d) { mid += d * step; step <<= 1; if (mid < lo2 || mid > hi2) { dir = 2; mid = (lo2 + hi2) >> 1; } }
+              else { dir = 2; mid = (lo2 + hi2) >> 1; }
             }
           }
           M.cf4[slot] = make_float4(f0.x, f0.y, f0.z, 0.0f);
@@ -681,9 +736,9 @@ SIM_BROAD_UNROLL
       __syncwarp();
       int tot = warp_excl_scan(M.boff, NBODY, tid);
       if (tid == 0) M.boff[NBODY] = tot;
+      __syncwarp();
+      for (int b = tid; b < NBODY; b += 32) M.bcur[b] = M.boff[b];
     }
-    __syncthreads();
-    if (tid < NBODY) M.bcur[tid] = M.boff[tid];
     __syncthreads();
     for (int i = tid; i < ncon; i += SIM_THREADS) {
       int b = (__float_as_uint(CB[i].w) >> 8) & 255;
@@ -844,14 +899,14 @@ SIM_BROAD_UNROLL
         if (tid < ROBOT_TID0 + SDX_ND) {
           int j = tid - ROBOT_TID0;
           v3 Fd = V3(0.0f, 0.0f, 0.0f), Md = V3(0.0f, 0.0f, 0.0f);
-          unsigned m = my_desc;
+          unsigned m = my_desc & ract;                         // descendant links IN CONTACT (the others carry no wrench)
           while (m) { int L = __ffs(m) - 1; m &= m - 1; Fd = vadd(Fd, ld3(M.linkF[L])); Md = vadd(Md, ld3(M.linkM[L])); }
           v3 aj = ld3(M.ja[j]);
           float g = vdot(aj, vsub(Md, vcross(ld3(M.jo[j]), Fd)));
           M.qd[j] = M.qdfree[j] + g / M.ieff[j];
         }
         __syncwarp();
-        if (tid < ROBOT_TID0 + SDX_NL) link_twist(S, M, tid - ROBOT_TID0, my_anc);
+        if ((ract >> (tid - ROBOT_TID0)) & 1u) link_twist(S, M, tid - ROBOT_TID0, my_anc);   // phase A reads only the twists of links in contact
       }
 #ifdef SIM_PROFILE
       if (prof && (tid & 31) == 0) prof[((it + 1) * 2 + 1) * 8 + (tid >> 5)] = clock64();
