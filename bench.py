@@ -26,10 +26,10 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = 15956   # algorithmic HBM bytes / env-step (fp32 rollout)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_simulate launch at 16 384 envs, from the committed ncu --set full capture
-# (profiles/r01_ncu_k_simulate_v10_16384envs.txt: 127.1 MB read + 280.2 MB written; the writes include the contact records that
+# (profiles/r01_ncu_k_simulate_v11_16384envs.txt: 127.1 MB read + 282.1 MB written; the writes include the contact records that
 # live in global memory behind L1 since SIM_GLOBAL_CONTACTS and the warm-start impulse cache)
-NCU_TRAFFIC_BYTES_PER_ENV = (127.120896e6 + 280.205056e6) / 16384
-NCU_ISSUE_ACTIVE = 0.4649            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
+NCU_TRAFFIC_BYTES_PER_ENV = (127.127296e6 + 282.132224e6) / 16384
+NCU_ISSUE_ACTIVE = 0.5068            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
 
 
 def measured_peaks():
@@ -375,7 +375,7 @@ def main():
             "ppo": ppo_info,
             "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": NCU_TRAFFIC_BYTES_PER_ENV * n,
-                         "traffic_source": "ncu --set full at 16384 envs, profiles/r01_ncu_k_simulate_v10_16384envs.txt (scaled by envs per launch)",
+                         "traffic_source": "ncu --set full at 16384 envs, profiles/r01_ncu_k_simulate_v11_16384envs.txt (scaled by envs per launch)",
                          "issue_slots_busy_ncu": NCU_ISSUE_ACTIVE,
                          "ms_per_launch": sim_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
