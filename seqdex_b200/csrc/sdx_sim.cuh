@@ -626,7 +626,7 @@ SIM_BROAD_UNROLL
         float m = margin + M.sab[a].w + M.sab[t].w;
         unsigned short mk = 0;
         PairGeom G;
-        const bool dead = a < NB && (M.sflag[a] & 1) && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)));   // kept list, both asleep by now
+        const bool dead = !rebuild && a < NB && (M.sflag[a] & 1) && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)));   // kept list, both asleep by now
         if (!dead && pair_geom(M, a, t, m, G, t >= NB + nrs)) {
           int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
           for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, margin, &d)) mk |= (unsigned short)(1u << p); }
@@ -717,6 +717,10 @@ SIM_BROAD_UNROLL
     __syncthreads();
     PMARK(7);
     const int ncon = M.ncon;
+    unsigned ract = 0u;                                        // robot warp: links with at least one contact
+    // An env without a single contact in this sub-step (a heap that sleeps, the hand in the air) has nothing to solve: bodies
+    // keep their free velocities, which is exactly what 17 empty passes would leave -- 40 barriers and three scans are skipped.
+    if (ncon > 0) {
     // 7. incidence: owned contacts of a body are one contiguous range (contacts are generated owner-major);
     //    target-side contacts go to a per-body list, filled with atomics and then sorted ascending
     //    (=> the summation order of phase B is fixed, whatever the fill order was)
@@ -771,7 +775,6 @@ SIM_BROAD_UNROLL
       }
       if (tid == 0) M.nact = base;
     }
-    unsigned ract = 0u;                                        // robot warp: links with at least one contact
     if (tid >= ROBOT_TID0) {
       const int L = tid - ROBOT_TID0;
       const bool has = L < SDX_NL && M.nb[NB + L] > 0;
@@ -779,7 +782,7 @@ SIM_BROAD_UNROLL
       if (L < SDX_NL && !has) { st3(M.linkF[L], V3(0.0f, 0.0f, 0.0f)); st3(M.linkM[L], V3(0.0f, 0.0f, 0.0f)); }
       if (L < SDX_ND) {
         int nn = 0;
-        unsigned m = my_desc;
+        unsigned m = my_desc & ract;                           // descendants in contact (the others count zero)
         while (m) { int L2 = __ffs(m) - 1; m &= m - 1; nn += M.nb[NB + L2]; }
         M.nj[L] = nn;
       }
@@ -912,6 +915,10 @@ SIM_BROAD_UNROLL
       if (prof && (tid & 31) == 0) prof[((it + 1) * 2 + 1) * 8 + (tid >> 5)] = clock64();
 #endif
       __syncthreads();
+    }
+    } else {
+      if (tid >= ROBOT_TID0 && tid < ROBOT_TID0 + SDX_NL) { st3(M.linkF[tid - ROBOT_TID0], V3(0.0f, 0.0f, 0.0f)); st3(M.linkM[tid - ROBOT_TID0], V3(0.0f, 0.0f, 0.0f)); }
+      PMARK(8); PMARK(9);
     }
     PMARK(10);
     for (int i = tid; i < ncon; i += SIM_THREADS) { const float4 F4 = M.cf4[i]; wsw[4 * i + 1] = F4.x; wsw[4 * i + 2] = F4.y; wsw[4 * i + 3] = F4.z; }

@@ -31,7 +31,8 @@ REC = 18 * 2 * 8 + 16                                     # SIM_PROF_REC in csrc
 ptr = con.data_ptr() + n * 1024 * 8 * 4
 raw = torch.empty(n * 2 * REC, dtype=torch.int64, device="cuda")
 ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(raw.data_ptr()), ctypes.c_void_p(ptr), n * 2 * REC * 8, 3)
-p = raw.cpu().numpy().reshape(n * 2, REC).astype(np.float64)
+p_all = raw.cpu().numpy().reshape(n * 2, REC).astype(np.float64)
+p = p_all[p_all[:, 289] > 0]                                  # solver statistics: sub-steps that have contacts (the others skip it)
 t = p[:, :18 * 2 * 8].reshape(-1, 18, 2, 8)[:, :17]           # [env x sub-step, pass (it = -1..15), {arrive after A, arrive after B}, warp]
 t0, ncon, nact, nrob = p[:, 288], p[:, 289], p[:, 290], p[:, 291]
 relA = t[:, :, 0, :].max(axis=2)                              # barrier release times = slowest arrival
@@ -40,7 +41,7 @@ start = np.concatenate([t0[:, None], relB[:, :-1]], axis=1)   # a pass starts wh
 durA, durB = relA - start, relB - relA
 workA = t[:, :, 0, :] - start[:, :, None]                     # per warp: its own time in phase A / phase B
 workB = t[:, :, 1, :] - relA[:, :, None]
-marks = p[:, 292:304]
+marks = p_all[:, 292:304]
 names = ["kinematics + free velocities + twists", "world AABBs", "broad phase", "pair offsets scan", "narrow pass 1 (pair masks)",
          "contact offsets", "narrow pass 2 (contacts + warm start)", "incidence lists + work items", "effective masses",
          "solver: 17 passes", "integrate + impulse cache"]
@@ -49,6 +50,7 @@ tot = marks[:, 11] - marks[:, 0]
 print(f"sub-step total {tot.mean():.0f} cycles (thread 0, barrier to barrier)")
 for k, nm in enumerate(names):
     print(f"  {nm:40s} {stage[:, k].mean():8.0f} cycles  {100 * stage[:, k].mean() / tot.mean():5.1f} %")
+print(f"sub-steps without a single contact (solver and incidence stages skipped): {100 * (p_all[:, 289] == 0).mean():.1f} %")
 print(f"{len(p)} env x sub-step records; contacts {ncon.mean():.0f}, awake touched bricks {nact.mean():.1f}, robot links in contact {nrob.mean():.2f}")
 print(f"solver loop {(relB[:, -1] - t0).mean():.0f} cycles per sub-step = 17 passes")
 print(f"phase A per pass: {durA[:, 1:].mean():.0f} cycles (p90 {np.percentile(durA[:, 1:], 90):.0f});  phase B per pass: {durB.mean():.0f} (p90 {np.percentile(durB, 90):.0f})")
