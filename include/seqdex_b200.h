@@ -162,6 +162,18 @@ int64_t sdx_launch_count(const sdx_env_t* env);
 
 /* dst = clamp(tensor(kind), -lim, lim): VecTask's clip_obs into caller memory (VR:174-175) */
 int sdx_clamped_copy(sdx_env_t* env, int kind, float* dst_dev, float lim);
+/* Domain randomisation, non-physical half.  BaseTask.step adds noise to the actions before pre_physics_step
+ * (BT:131-132) and to obs_buf after post_physics_step (BT:149-150); apply_randomizations prepares its parameters (BT:263-340).
+ *   sdx_dr_randn : dst[i] ~ N(0,1) -- the correlated-noise tensor, redrawn when the parameters are refreshed (BT:293-296)
+ *   sdx_dr_noise : dst = op(src, (corr * a_corr + b_corr) + white * a + b)
+ *                  distribution 0 gaussian (a_corr, b_corr, a, b = var_corr, mu_corr, var, mu; white ~ N(0,1)),
+ *                               1 uniform  (hi_corr - lo_corr, lo_corr, hi - lo, lo;           white ~ U[0,1));
+ *                  operation 0 additive, 1 scaling.  White noise: Philox(seed, element / 4, counter) -- pass a fresh counter per call.
+ *   sdx_set_gravity : sim_params.gravity (BT:342-355), z component, effective from the next sdx_simulate. */
+int sdx_dr_randn(sdx_env_t* env, float* dst_dev, int64_t n, uint64_t seed, uint32_t counter);
+int sdx_dr_noise(sdx_env_t* env, float* dst_dev, const float* src_dev, const float* corr_dev, int64_t n, float a_corr, float b_corr,
+                 float a, float b, int distribution, int operation, uint64_t seed, uint32_t counter);
+int sdx_set_gravity(sdx_env_t* env, float gravity_z);
 /* rows [142][13] of the actors that carry no simulation state (hand base, table, bin, fixed bricks, ...) for the facade */
 int sdx_set_static_rows(sdx_env_t* env, const float* rows_host);
 /* sdx_set_heap_bank from a device buffer (bank synthesised on the GPU) */

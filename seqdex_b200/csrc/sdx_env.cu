@@ -12,6 +12,7 @@
 #include "sdx_task.cuh"
 #include "sdx_task_orient.cuh"
 #include "sdx_camera.cuh"
+#include "sdx_dr.cuh"
 #include "sdx_task_search.cuh"
 
 static thread_local std::string g_err;
@@ -554,6 +555,34 @@ extern "C" int sdx_clamped_copy(sdx_env_t* E, int kind, float* dst_dev, float li
   k_clamp_copy<<<(unsigned)((ne + 255) / 256), 256, 0, E->stream>>>((const float*)E->buf[kind], dst_dev, ne, lim);
   E->launches++;
   CKL();
+  return 0;
+}
+
+/* domain randomisation: correlated-noise tensor and the noise hook of BaseTask.step (BT:131-132, 149-150, 263-340) */
+extern "C" int sdx_dr_randn(sdx_env_t* E, float* dst_dev, int64_t n, uint64_t seed, uint32_t counter) {
+  if (!E || !dst_dev || n <= 0) { g_err = "sdx_dr_randn: bad arguments"; return -1; }
+  CK(cudaSetDevice(E->device));
+  k_dr_randn<<<(unsigned)((n + 1023) / 1024), 256, 0, E->stream>>>(dst_dev, n, seed, counter);
+  E->launches++;
+  CKL();
+  return 0;
+}
+extern "C" int sdx_dr_noise(sdx_env_t* E, float* dst_dev, const float* src_dev, const float* corr_dev, int64_t n, float a_corr,
+                            float b_corr, float a, float b, int distribution, int operation, uint64_t seed, uint32_t counter) {
+  if (!E || !dst_dev || !src_dev || !corr_dev || n <= 0) { g_err = "sdx_dr_noise: bad arguments"; return -1; }
+  if (distribution < 0 || distribution > 1 || operation < 0 || operation > 1) { g_err = "sdx_dr_noise: unknown distribution / operation"; return -1; }
+  CK(cudaSetDevice(E->device));
+  k_dr_noise<<<(unsigned)((n + 1023) / 1024), 256, 0, E->stream>>>(dst_dev, src_dev, corr_dev, n, a_corr, b_corr, a, b, distribution, operation, seed, counter);
+  E->launches++;
+  CKL();
+  return 0;
+}
+/* sim_params.gravity randomisation (BT:342-355): the z component of gravity for every env from the next step on */
+extern "C" int sdx_set_gravity(sdx_env_t* E, float gravity_z) {
+  if (!E) { g_err = "sdx_set_gravity: bad arguments"; return -1; }
+  CK(cudaSetDevice(E->device));
+  E->host_scene.gravity_z = gravity_z;
+  CK(cudaMemcpyAsync(&E->scene->gravity_z, &E->host_scene.gravity_z, sizeof(float), cudaMemcpyHostToDevice, E->stream));
   return 0;
 }
 

@@ -7,6 +7,7 @@ from __future__ import annotations
 import torch
 
 from ..env import SdxEnv, make_heap_bank
+from ..randomization import RandomizedTaskMixin
 from ..scene import Scene
 
 
@@ -18,7 +19,7 @@ DEFAULT_CFG = {   # cfg/allegro_hand_block_assembly_grasp_sim.yaml (the keys thi
 }
 
 
-class BlockAssemblyGraspSim:
+class BlockAssemblyGraspSim(RandomizedTaskMixin):
     num_obs_dict = {"partial_contact": 132}      # GS:191-195
     stack_obs = 3                                # GS:189
 
@@ -28,8 +29,6 @@ class BlockAssemblyGraspSim:
         self.cfg = cfg
         if device_type not in ("cuda", "GPU"):
             raise RuntimeError("seqdex_b200 runs on CUDA devices only (the reference's --pipeline=cpu has no counterpart here)")
-        if cfg.get("task", {}).get("randomize", False):
-            raise NotImplementedError("domain randomisation (BT:229-423) is outside the hot path (SURVEY.md section 8f.4)")
         env_cfg, sim_cfg = cfg["env"], cfg.get("sim", {})
         physx = sim_cfg.get("physx", {})
         self.num_envs = int(env_cfg["numEnvs"])
@@ -63,10 +62,13 @@ class BlockAssemblyGraspSim:
         zeros = torch.zeros(self.num_envs, device=self.device)
         self.extras = {"emergence_reward": zeros, "heap_movement_penalty": zeros, "meta_reward": self.meta_rew_buf,
                        "student_obs_buf": self.obs_buf[:, 0:30], "success_buf": torch.zeros_like(self.reset_buf)}   # GS:458-459, 1071-1073
+        self._dr_init(cfg, seed)                    # GS:106-107 / OR:106-107 (task.randomize)
 
     # ---- BaseTask.step (BT:130-150)
     def step(self, actions):
+        actions = self._dr_before(actions)         # BT:131-132 (only with task.randomize)
         self.env.step(actions)
+        self._dr_after()                          # BT:149-150
         self.meta_rew_buf += self.rew_buf          # GS:1069
 
     def pre_physics_step(self, actions):

@@ -10,6 +10,7 @@ import torch
 
 from ..camera import SEARCH_CAMERA, look_at
 from ..env import SdxEnv
+from ..randomization import RandomizedTaskMixin
 from ..scene import Scene
 
 DEFAULT_CFG = {   # cfg/allegro_hand_block_assembly_search.yaml (the keys this task reads)
@@ -20,7 +21,7 @@ DEFAULT_CFG = {   # cfg/allegro_hand_block_assembly_search.yaml (the keys this t
 }
 
 
-class BlockAssemblySearch:
+class BlockAssemblySearch(RandomizedTaskMixin):
     num_obs_dict = {"partial_contact": 62}       # SE:149-153
     stack_obs = 3                                # SE:147
 
@@ -30,8 +31,6 @@ class BlockAssemblySearch:
         self.cfg = cfg
         if device_type not in ("cuda", "GPU"):
             raise RuntimeError("seqdex_b200 runs on CUDA devices only (the reference's --pipeline=cpu has no counterpart here)")
-        if cfg.get("task", {}).get("randomize", False):
-            raise NotImplementedError("domain randomisation (BT:229-423) is outside the hot path (SURVEY.md section 8f.4)")
         env_cfg, sim_cfg = cfg["env"], cfg.get("sim", {})
         physx = sim_cfg.get("physx", {})
         self.num_envs = int(env_cfg["numEnvs"])
@@ -67,10 +66,13 @@ class BlockAssemblySearch:
                        "student_obs_buf": self.obs_buf[:, 0:30], "success_buf": torch.zeros_like(self.reset_buf)}
         self._gate = None
         self._tvalue_seed = seed if tvalue_seed is None else tvalue_seed
+        self._dr_init(cfg, seed)                    # SE:106-107 (task.randomize)
 
     # ---- BaseTask.step (BT:130-150)
     def step(self, actions):
+        actions = self._dr_before(actions)         # BT:131-132 (only with task.randomize)
         self.env.step(actions)
+        self._dr_after()                          # BT:149-150
         self.meta_rew_buf += self.rew_buf          # SE:954
 
     def pre_physics_step(self, actions):

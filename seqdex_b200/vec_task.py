@@ -89,6 +89,11 @@ class RLgamesVecTaskPython(VecTask):
     def step_into(self, actions, obs_out, states_out):
         """step() writing the clamped observations straight into caller buffers (same values as step(); saves the two
         temporaries torch.clamp allocates every step).  Actions are clamped inside the pre-physics kernel."""
+        if getattr(self.task, "randomizer", None) is not None:    # domain randomisation: noise goes on the CLAMPED actions (VR:166, BT:131)
+            self.task.step(torch.clamp(actions, -self.clip_actions, self.clip_actions))
+            torch.clamp(self.task.obs_buf, -self.clip_obs, self.clip_obs, out=obs_out)
+            self.task.env.clamped_copy("STATES", states_out, self.clip_obs)
+            return self.task.rew_buf, self.task.reset_buf, self.task.extras
         self.task.step(actions)
         self.task.env.clamped_copy("OBS", obs_out, self.clip_obs)
         self.task.env.clamped_copy("STATES", states_out, self.clip_obs)
