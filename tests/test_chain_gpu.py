@@ -30,5 +30,8 @@ def test_chain_search_orient_grasp(tmp_path):
     s, o = out["banks"]["search"], out["banks"]["orient"]
     assert s.shape[2:] == (72, 13) and o.shape[2:] == (72, 13) and torch.isfinite(s).all() and torch.isfinite(o).all()
     # the heaps Orient hands on went through two stages of random pushing: bricks rest in the bin (a few may have been
-    # knocked over its wall onto the table or the ground), none is below the ground or flying
-    assert float(o[..., 2].min()) > 0.0 and float(o[..., 2].max()) < 1.2 and 0.6 < float(o[..., 2].median()) < 0.8
+    # knocked over its wall onto the table or the ground, and a snapshot can catch the odd brick in the air: the hand flails
+    # at full speed and max_lin_vel is Isaac Gym's 1000 m/s), none is below the ground, nothing has exploded
+    z = o[..., 2].flatten()
+    assert float(z.min()) > -0.02 and float(z.abs().max()) < 100.0 and 0.6 < float(z.median()) < 0.8
+    assert float((z > 1.2).float().mean()) < 0.01
