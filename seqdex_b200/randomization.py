@@ -38,67 +38,42 @@ def schedule_scaling(cfg, last_step):                       # BT:269-277
 
 
 def nonphysical_params(cfg, last_step):
-    """the numbers a noise_lambda closes over (BT:279-334), plus the same in the form sdx_dr_noise takes"""
+    """the four numbers a noise_lambda closes over (BT:279-334) under their reference names, plus the same in the form
+    sdx_dr_noise takes.  Additive noise grows from nothing (every number times the schedule factor s); scaling noise grows
+    from the identity (spreads times s, centres / bounds interpolated between 1 and their value)."""
     dist, op_type = cfg["distribution"], cfg["operation"]
-    if op_type not in ("additive", "scaling"):
-        raise ValueError(f"unknown operation {op_type!r}")
+    if op_type not in ("additive", "scaling") or dist not in ("gaussian", "uniform"):
+        raise ValueError(f"unknown operation / distribution {op_type!r} / {dist!r}")
     s = schedule_scaling(cfg, last_step)
-    if dist == "gaussian":
-        mu, var = cfg["range"]
-        mu_corr, var_corr = cfg.get("range_correlated", [0., 0.])
-        if op_type == "additive":
-            mu *= s
-            var *= s
-            mu_corr *= s
-            var_corr *= s
-        else:
-            var = var * s                                   # scale up var over time
-            mu = mu * s + 1.0 * (1.0 - s)                   # linearly interpolate
-            var_corr = var_corr * s
-            mu_corr = mu_corr * s + 1.0 * (1.0 - s)
-        return {"mu": mu, "var": var, "mu_corr": mu_corr, "var_corr": var_corr, "distribution": 0, "operation": int(op_type == "scaling"),
-                "a_corr": var_corr, "b_corr": mu_corr, "a": var, "b": mu}
-    if dist == "uniform":
-        lo, hi = cfg["range"]
-        lo_corr, hi_corr = cfg.get("range_correlated", [0., 0.])
-        if op_type == "additive":
-            lo *= s
-            hi *= s
-            lo_corr *= s
-            hi_corr *= s
-        else:
-            lo = lo * s + 1.0 * (1.0 - s)
-            hi = hi * s + 1.0 * (1.0 - s)
-            lo_corr = lo_corr * s + 1.0 * (1.0 - s)
-            hi_corr = hi_corr * s + 1.0 * (1.0 - s)
-        return {"lo": lo, "hi": hi, "lo_corr": lo_corr, "hi_corr": hi_corr, "distribution": 1, "operation": int(op_type == "scaling"),
-                "a_corr": hi_corr - lo_corr, "b_corr": lo_corr, "a": hi - lo, "b": lo}
-    raise ValueError(f"unknown distribution {dist!r}")
+    grow = (lambda x: x * s)
+    blend = grow if op_type == "additive" else (lambda x: x * s + 1.0 * (1.0 - s))
+    first, second = cfg["range"]
+    first_c, second_c = cfg.get("range_correlated", [0., 0.])
+    if dist == "gaussian":                                  # range = (mean, spread): BT:280-299
+        mu, var, mu_corr, var_corr = blend(first), grow(second), blend(first_c), grow(second_c)
+        named = {"mu": mu, "var": var, "mu_corr": mu_corr, "var_corr": var_corr}
+        a_corr, b_corr, a, b = var_corr, mu_corr, var, mu
+    else:                                                   # range = (low, high): BT:303-327
+        lo, hi, lo_corr, hi_corr = blend(first), blend(second), blend(first_c), blend(second_c)
+        named = {"lo": lo, "hi": hi, "lo_corr": lo_corr, "hi_corr": hi_corr}
+        a_corr, b_corr, a, b = hi_corr - lo_corr, lo_corr, hi - lo, lo
+    return dict(named, distribution=int(dist == "uniform"), operation=int(op_type == "scaling"), a_corr=a_corr, b_corr=b_corr, a=a, b=b)
 
 
 def physical_sample(cfg, shape, curr_step, rng):
-    """isaacgym.gymutil.generate_random_samples, restated (see module docstring)"""
+    """isaacgym.gymutil.generate_random_samples, restated (see module docstring): same schedule treatment as above, numpy draws"""
     dist, op = cfg["distribution"], cfg["operation"]
     s = schedule_scaling(cfg, curr_step)
-    a, b = cfg["range"]
+    grow = (lambda x: x * s)
+    blend = grow if op == "additive" else ((lambda x: x * s + 1.0 * (1.0 - s)) if op == "scaling" else (lambda x: x))
+    first, second = cfg["range"]
     if dist == "gaussian":
-        if op == "additive":
-            a *= s
-            b *= s
-        elif op == "scaling":
-            b = b * s
-            a = a * s + 1.0 * (1.0 - s)
-        return rng.normal(a, b, shape)
-    if op == "additive":
-        a *= s
-        b *= s
-    elif op == "scaling":
-        a = a * s + 1.0 * (1.0 - s)
-        b = b * s + 1.0 * (1.0 - s)
+        return rng.normal(blend(first), grow(second) if op in ("additive", "scaling") else second, shape)
+    lo, hi = blend(first), blend(second)
     if dist == "loguniform":
-        return np.exp(rng.uniform(np.log(a), np.log(b), shape))
+        return np.exp(rng.uniform(np.log(lo), np.log(hi), shape))
     if dist == "uniform":
-        return rng.uniform(a, b, shape)
+        return rng.uniform(lo, hi, shape)
     raise ValueError(f"unknown distribution {dist!r}")
 
 
