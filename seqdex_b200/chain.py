@@ -53,6 +53,7 @@ def run_chain(num_envs=256, device_id=0, episodes=(2, 2, 1), policies=None, tval
     policies = policies or {}
     device = f"cuda:{device_id}"
     out = {}
+    torch.manual_seed(seed)                         # train_rlgames.py:65 set_seed: VecTask.reset draws from the global generator
     # ---- stage 1: dig the target brick out of the heap
     search = BlockAssemblySearch(_cfg(num_envs, 75, 0.6), device_id=device_id, seed=seed, record_heaps=bank_capacity)
     env = RLgamesVecTaskPython(search, device)

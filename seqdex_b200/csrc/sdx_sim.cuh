@@ -5,14 +5,17 @@
 //   load   : free-brick tile [13][72] f32 (3744 B, contiguous per env) by TMA bulk copy
 //            (cp.async.bulk -> mbarrier), DoF block [3][24] by plain loads
 //   per sub-step (h = dt/substeps):
-//     forward kinematics (quaternion chain), shape poses, free velocities (gravity, implicit PD)
-//     broad phase   : one thread per owner shape, world-AABB test against every target box
+//     forward kinematics (robot warp in lockstep, chain by shuffles), shape poses, free velocities (gravity, implicit PD),
+//     world-frame inverse inertia of every brick
+//     broad phase   : FIRST sub-step of a step (or after a sleeping brick was woken): two threads per owner shape, world-AABB
+//                     test against every target box with the travel bounds of all sub-steps left; later sub-steps keep the lists
 //     narrow phase  : ordered pairs -> SAT reference face -> sample points -> contacts (two-pass,
-//                     deterministic compaction: owner, candidate, point order)
-//     CSR incidence : per body, contacts in index order (fixed summation order => reproducible)
+//                     deterministic compaction: owner, candidate, point order) + warm-start lookup (galloping from the same slot)
+//     -- a sub-step without a single contact skips the three stages below --
+//     CSR incidence : per body, contacts in index order (fixed summation order => reproducible); 16-byte work items for phase B
 //     solver        : mass-splitting Jacobi on total impulses; phase A = 1 thread / contact,
-//                     phase B = 1 thread / body gathers its incident impulses; the articulation sees
-//                     contacts through per-link wrenches -> joint-space impulses (diag. inertia)
+//                     phase B = 2 lanes / awake touched brick gather its incident impulses; the articulation sees
+//                     contacts through per-link wrenches -> joint-space impulses (diag. inertia), links in contact only
 //     integrate
 //   store  : brick tile by TMA bulk store, DoF block, and ONLY the rows the task reads
 //            (24 link rows, 6x7 Jacobian of link7, net contact force per link)
