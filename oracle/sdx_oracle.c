@@ -317,6 +317,18 @@ static float body_k(const sdx_scene_t* S, const work_t* W, int body, v3 wpt, v3 
  *             else E >= sleep_energy or touched by a hot brick -> 1   (awake, timer restarted)
  *             else                                            -> slp + 1 (saturating at 255)
  * sleep_substeps = 0 disables the mechanism. */
+/* test hook (tests/test_physics_invariants.py): 0 = a fresh broad phase in every sub-step with this sub-step's travel bounds
+ * only -- what the kept lists must be equivalent to as long as no candidate is missed */
+static int g_broad_reuse = 1;
+void sdxo_set_broad_reuse(int on) { g_broad_reuse = on; }
+/* audit of the candidate lists: [0] pairs a fresh sweep finds in sub-steps that (re)built the lists, [1] of those not in the lists
+ * (KC overflow), [2] / [3] the same in sub-steps that kept the lists, [4] missing although the owner's list had room (a pair
+ * that came into range after the lists were built) */
+static int g_reuse_audit = 0;
+static long g_reuse_stats[5];
+void sdxo_reuse_audit(int on) { g_reuse_audit = on; for (int i = 0; i < 5; ++i) g_reuse_stats[i] = 0; }
+void sdxo_reuse_stats(long out[5]) { for (int i = 0; i < 5; ++i) out[i] = g_reuse_stats[i]; }
+
 static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_out, float* jac7, float* netf,
                     int* ncontact, float* condump, float* ws, int* wsn, int ws_cur, unsigned char* slp, work_t* W) {
   const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;
@@ -411,10 +423,10 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     /* The candidate lists are built in the FIRST sub-step of a step for ALL its sub-steps -- the travel bounds scaled by the
      * number of sub-steps left, plus the speed gravity adds in between -- and rebuilt in a later sub-step only if a brick that
      * was asleep when they were built has been woken since (its pairs with sleeping bricks and statics were filtered). */
-    int rebuild = sub == 0;
+    int rebuild = sub == 0 || !g_broad_reuse;
     if (sub > 0) for (int b = 0; b < NB; ++b) if (W->built_asleep[b] && !W->asleep[b]) rebuild = 1;
     if (rebuild) {
-      const int left = S->substeps - sub;
+      const int left = g_broad_reuse ? S->substeps - sub : 1;
       const float infl = (float)left, slack = (float)(left - 1) * ((h * h) * fabsf(S->gravity_z));
       for (int b = 0; b < NB; ++b) W->built_asleep[b] = W->asleep[b];
       W->cand_dropped = 0;
@@ -433,6 +445,24 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           if (hit) { if (k < KC) W->cand[a][k++] = (unsigned char)t; else W->cand_dropped++; }
         }
         W->ncand[a] = k;
+      }
+    }
+    if (g_reuse_audit) {   /* test hook: what would a fresh broad phase of THIS sub-step list, and is it in the lists in use? */
+      for (int a = 0; a < n_owner; ++a) {
+        if (a < NB && a >= nbr) continue;
+        for (int t = 0; t < n_target; ++t) {
+          if (t == a || (t < NB && t >= nbr) || (a >= NB && t >= NB && t < NB + nrs)) continue;
+          if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue;
+          v3 d = vsub(W->sc[a], W->sc[t]);
+          float m = margin + W->spd[a] + W->spd[t];
+          if (!(fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
+                fabsf(d.z) <= W->sa[a].z + W->sa[t].z + m)) continue;
+          int found = 0;
+          for (int ci = 0; ci < W->ncand[a]; ++ci) if (W->cand[a][ci] == t) found = 1;
+          __sync_fetch_and_add(&g_reuse_stats[rebuild ? 0 : 2], 1);                                   /* pairs a fresh sweep finds */
+          if (!found) __sync_fetch_and_add(&g_reuse_stats[(rebuild ? 0 : 2) + 1], 1);                 /* ... missing from the lists */
+          if (!found && W->ncand[a] < KC) __sync_fetch_and_add(&g_reuse_stats[4], 1);                 /* missing though the owner's list had room */
+        }
       }
     }
     /* 4. narrow phase, per ordered pair (owner a, target t): reference face of t = its axis of least
