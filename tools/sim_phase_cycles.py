@@ -1,6 +1,10 @@
 #!/usr/bin/env python
-"""Per-warp cycle accounting of k_simulate's solver loop (SIM_PROFILE build: clock64 around phase A / its barrier / phase B / its
-barrier, summed over the 17 passes of a sub-step).  Usage: SEQDEX_B200_LIB=.../libseqdex_b200_prof.so tools/sim_phase_cycles.py"""
+"""Per-stage and per-warp cycle accounting of k_simulate (SIM_PROFILE build: clock64 of thread 0 after every stage barrier of a
+sub-step, and per warp at both barriers of each of the 17 solver passes).
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC -shared -DSIM_PROFILE \
+       -o seqdex_b200/libseqdex_b200_prof.so seqdex_b200/csrc/sdx_env.cu seqdex_b200/csrc/sdx_ppo.cu
+  SEQDEX_B200_LIB=$PWD/seqdex_b200/libseqdex_b200_prof.so python tools/sim_phase_cycles.py      # on a B200
+Output of the round's runs: profiles/r01_sim_stage_cycles.txt, r01_ab_*.txt."""
 import ctypes
 import os
 import sys
