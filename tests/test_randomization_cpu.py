@@ -81,3 +81,61 @@ def test_unsupported_sections_fail_loudly():
     R.check_supported({"frequency": 10, "observations": {}, "actions": {}, "sim_params": {"gravity": {}}, "actor_params": {}})
     with pytest.raises(NotImplementedError):
         R.check_supported({"sim_params": {"dt": {}}})
+
+
+class _RecordingLib:
+    """stands in for the CUDA library: records the C-ABI calls DomainRandomizer makes (host logic only, no compute)"""
+
+    def __init__(self):
+        self.calls = []
+
+    def _rec(self, name):
+        def f(*args):
+            self.calls.append((name, [getattr(a, "value", a) for a in args]))
+            return 0
+        return f
+
+    def __getattr__(self, name):
+        if name.startswith("sdx_"):
+            return self._rec(name)
+        raise AttributeError(name)
+
+
+def test_domain_randomizer_host_logic():
+    """the call sequence of a randomised task over a refresh (BT:229-340): parameters from the schedule at the current frame, the
+    correlated tensor redrawn exactly once per refresh, a fresh Philox counter for every kernel call, gravity set on refresh only"""
+    import types
+    import torch
+    lib = _RecordingLib()
+    scene = types.SimpleNamespace(c=types.SimpleNamespace(gravity_z=-9.81))
+    env = types.SimpleNamespace(L=lib, h=1234, n=4, device=torch.device("cpu"), scene=scene)
+    params = {"frequency": 3,
+              "observations": {"range": [0, .002], "range_correlated": [0, .001], "operation": "additive", "distribution": "gaussian",
+                               "schedule": "linear", "schedule_steps": 10},
+              "sim_params": {"gravity": {"range": [0, 0.4], "operation": "additive", "distribution": "gaussian"}},
+              "actor_params": {}}
+    r = R.DomainRandomizer(env, params, seed=22)
+    obs, out = torch.zeros(4, 6), torch.zeros(4, 6)
+    acts = torch.ones(4, 23)
+    refreshed = []
+    for step in range(7):
+        refreshed.append(r.apply_randomizations(torch.ones(4, dtype=torch.int64)))
+        assert r.noise("actions", acts, None) is acts                      # not configured: the tensor itself comes back
+        assert r.noise("observations", obs, out) is out
+        r.step_done()
+    assert refreshed == [True, False, False, True, False, False, True]    # frames 0, 3, 6
+    names = [c[0] for c in lib.calls]
+    assert names.count("sdx_set_gravity") == 3 and names.count("sdx_dr_randn") == 3 and names.count("sdx_dr_noise") == 7
+    counters = [c[1][-1] for c in lib.calls if c[0] in ("sdx_dr_randn", "sdx_dr_noise")]
+    assert counters == sorted(set(counters)) and len(counters) == 10      # every kernel call gets its own stream
+    seeds = {c[1][-2] for c in lib.calls if c[0] in ("sdx_dr_randn", "sdx_dr_noise")}
+    assert len(seeds) == 1
+    # the numbers handed to sdx_dr_noise are the schedule's at the frame of the last refresh (frame 3 -> s = 0.3, frame 6 -> 0.6)
+    noise_calls = [c[1] for c in lib.calls if c[0] == "sdx_dr_noise"]
+    for k, frame in ((3, 3), (4, 3), (5, 3), (6, 6)):
+        p = R.nonphysical_params(dict(params["observations"]), frame)
+        a_corr, b_corr, a, b, dist, op = noise_calls[k][5:11]
+        assert (dist, op) == (0, 0)
+        np.testing.assert_allclose([a_corr, b_corr, a, b], [p["a_corr"], p["b_corr"], p["a"], p["b"]], rtol=1e-6, atol=0)
+    assert noise_calls[0][4] == 24                                        # element count
+    assert r.frame == 7 and int(r.randomize_buf[0]) == 1                  # BT:246-249: zeroed at frames 3 and 6 (due AND resetting), +1 per step
