@@ -30,6 +30,8 @@ ALGO_BYTES_PER_ENV_STEP = 15956   # algorithmic HB
 # live in global memory behind L1 since SIM_GLOBAL_CONTACTS and the warm-start impulse cache)
 NCU_TRAFFIC_BYTES_PER_ENV = (127.127296e6 + 282.132224e6) / 16384
 NCU_ISSUE_ACTIVE = 0.5068            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
+ALGO_FLOP_PER_ENV_STEP = 1.48e6      # counted fp32 work of the contact step in this episode mix (oracle counters)
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # B200: 148 SMs x 128 fp32 lanes x 2 (FMA) x 1.965 GHz
 
 
 def measured_peaks():
@@ -377,6 +379,10 @@ def main():
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": NCU_TRAFFIC_BYTES_PER_ENV * n,
                          "traffic_source": "ncu --set full at 16384 envs, profiles/r01_ncu_k_simulate_v11_16384envs.txt (scaled by envs per launch)",
                          "issue_slots_busy_ncu": NCU_ISSUE_ACTIVE,
+                         "fp32_alu": {"algorithmic_flop_per_env_step": ALGO_FLOP_PER_ENV_STEP, "peak_tflops": FP32_PEAK_TFLOPS,
+                                      "achieved_tflops": ALGO_FLOP_PER_ENV_STEP * n / (sim_ms * 1e-3) / 1e12,
+                                      "frac": ALGO_FLOP_PER_ENV_STEP * n / (sim_ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS,
+                                      "note": "GraspSim mix; neither roofline bounds the kernel (DESIGN.md sections 6, 11)"},
                          "ms_per_launch": sim_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
                          "note": "state-streaming bound is loose: the kernel is bound by block-barrier waits between ~40 phases per sub-step "
