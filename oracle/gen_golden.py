@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 REF = "/root/reference/dexteroushandenvs"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+OUT = os.environ.get("SEQDEX_GOLDEN_OUT") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")   # override: tests/test_golden_regen.py
 
 
 # ---------------------------------------------------------------- isaacgym.torch_utils (public restatement)
