@@ -129,6 +129,31 @@ def host_bank(scene, per_type=2, settle=150):
     return rows.reshape(8, per_type, 72, 13)
 
 
+TASKS = {"grasp_sim": ("BlockAssemblyGraspSim", 396), "orient": ("BlockAssemblyOrient", 186), "search": ("BlockAssemblySearch", 186)}
+
+
+def make_config(args, world):
+    """the `config` object of the JSON line -- identical for this arm and for --impl reference (same workload, two implementations)"""
+    task_name = TASKS[args.task][0]
+    n = args.num_envs
+    lockstep = args.task in ("orient", "search")
+    mbs = min(args.minibatch, 8 * n)
+    return {"workload": (f"{task_name} num_envs={n} per GPU, PPO bf16: every 8 env steps (policy + central-value forward, "
+                         "VecTask.step = reset_idx + IK + contact step 2x16 + obs/reward/t-value) then GAE and "
+                         f"5 mini-epochs x {8 * n // mbs} minibatches for actor and central value"
+                         if args.mode == "ppo" else
+                         f"{task_name} num_envs={n} per GPU, rollout only: VecTask.step, U(-1,1) actions"),
+            "mode": args.mode, "minibatch": mbs,
+            "num_envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-sharded x{world}, no data-path collective",
+            "l2": "env state (260 MB at 16384 envs) exceeds the 126 MB L2; no explicit flush",
+            "heap_bank_per_type": args.bank_per_type,
+            "episodes": (f"lockstep as in the reference (time-outs every 75 steps; each reset runs the scripted reset_idx inside the "
+                         f"timed region: 103 contact steps for Orient OR:1390-1695, 60 + render + 1 + render for Search "
+                         f"SE:1274-1537, 989-1019); {PRE_STEPS} untimed steps before warm-up" if lockstep else
+                         f"staggered: progress ~ U[0,{STAGGER}) then {PRE_STEPS} untimed steps before warm-up (stationary mix of "
+                         "fresh and settled heaps; resting bricks sleep with PhysX's default threshold and 0.4 s timer)")}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -157,10 +182,11 @@ def run_reference(args):
         "impl": "reference", "metric": "env-steps/sec at num_envs=16384 (BlockAssemblyGraspSim)", "value": val, "unit": "env-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BlockAssemblyGraspSim num_envs=16384 rollout (VecTask.step), CPU sample", "sample_envs": n},
+        "config": make_config(args, max(args.gpus, 1)),
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": int(cores), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "Isaac Gym (closed binary) is not installable here; this arm times the repo's CPU oracle of the same path",
+        "note": "Isaac Gym (closed binary) is not installable here; this arm times the repo's CPU oracle of the same path: VecTask.step of "
+                f"a {n}-env sample (the rollout; PPO's tensor work is not part of the CPU arm)",
     })
 
 
@@ -306,20 +332,38 @@ def main():
         agent = A2CAgent(venv, PPOConfig(minibatch_size=min(args.minibatch, 8 * n)), device=local,
                          dist_group=dist.group.WORLD if world > 1 else None)
         H = agent.H
-        iters, witers = max(K // H, 1), max(W // H, 1)
+        iters, witers = max(-(-K // H), 1), max(W // H, 1)      # whole PPO iterations covering at least K env steps
         for _ in range(witers):
             ppo_info = agent.train_epoch()
         barrier()
         l0, p0 = env.launch_count(), ppo_launch()
         step_ev.clear()
         asleep0 = float((env.tensor("SLEEP") >= max(scene.c.sleep_substeps, 1)).float().mean())
+        it_ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
         e0.record()
-        for _ in range(iters):
+        it_ev[0].record()
+        for it in range(iters):
             ppo_info = agent.train_epoch()
+            it_ev[it + 1].record()
         e1.record()
         barrier()
+        timed_s = e0.elapsed_time(e1) * 1e-3
         ms = e0.elapsed_time(e1) * K / (iters * H)
+        it_ms = [it_ev[i].elapsed_time(it_ev[i + 1]) for i in range(iters)]
         ppo_info = dict(ppo_info or {})
+        ppo_info["timed_region"] = {"seconds": timed_s, "env_steps_timed": iters * H, "ppo_iterations": iters,
+                                    "ms_per_iteration_min_median_max": [float(np.min(it_ms)), float(np.median(it_ms)), float(np.max(it_ms))],
+                                    "note": f"`value` = envs x {iters * H} steps / that time (whole iterations covering the {K} steps asked for)"}
+        from seqdex_b200.dist_utils import params_digest
+        dg = params_digest(agent.actor.params, agent.cv.params)
+        if world > 1:
+            dgs = [torch.zeros_like(dg) for _ in range(world)]
+            dist.all_gather(dgs, dg)
+        else:
+            dgs = [dg]
+        ppo_info["lockstep"] = {"params_digest": [int(x) for x in dg.tolist()], "ranks": world,
+                                "all_ranks_equal": bool(all(torch.equal(dgs[0], x) for x in dgs)),
+                                "note": "digest of actor + central-value parameters all-gathered after the timed region: data-parallel replicas must be bit-identical"}
         ppo_info["env_step_ms_in_loop"] = float(np.mean([a.elapsed_time(b) for a, b in step_ev]))
         ppo_info["bricks_asleep_frac_start_end"] = [asleep0, float((env.tensor("SLEEP") >= max(scene.c.sleep_substeps, 1)).float().mean())]
         launches = (env.launch_count() - l0 + ppo_launch() - p0) * K // (iters * H)
@@ -341,13 +385,14 @@ def main():
         env.step_host(h_act, h_obs, h_st, h_rew, h_rs)
     g1.record()
     barrier()
-    e2e_ms = max(g0.elapsed_time(g1), 1000 * (time.perf_counter() - t0) * 0.0)
+    e2e_wall_ms = 1000 * (time.perf_counter() - t0)      # host clock around the same region (sdx_step_host ends in a stream synchronize)
+    e2e_ms = g0.elapsed_time(g1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    tms = torch.tensor([ms, e2e_ms, sim_ms, ro_ms], device=dev, dtype=torch.float64)
+    tms = torch.tensor([ms, e2e_ms, sim_ms, ro_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, sim_ms, ro_ms = (float(x) for x in tms.tolist())
+    ms, e2e_ms, sim_ms, ro_ms, e2e_wall_ms = (float(x) for x in tms.tolist())
     nc = env.tensor("NCONTACT").cpu().numpy()
     if rank == 0:
         peak, which = measured_peaks()
@@ -356,22 +401,12 @@ def main():
             "metric": f"env-steps/sec at num_envs=16384 ({task_name})", "value": world * n * K / (ms * 1e-3),
             "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": (f"{task_name} num_envs={n} per GPU, PPO bf16: every 8 env steps (policy + central-value forward, "
-                                    "VecTask.step = reset_idx + IK + contact step 2x16 + obs/reward/t-value) then GAE and "
-                                    f"5 mini-epochs x {8 * n // min(args.minibatch, 8 * n)} minibatches for actor and central value"
-                                    if args.mode == "ppo" else
-                                    f"{task_name} num_envs={n} per GPU, rollout only: VecTask.step, U(-1,1) actions"),
-                       "mode": args.mode, "minibatch": min(args.minibatch, 8 * n),
-                       "num_envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-sharded x{world}, no data-path collective",
-                       "l2": "env state (260 MB at 16384 envs) exceeds the 126 MB L2; no explicit flush",
-                       "heap_bank_per_type": args.bank_per_type,
-                       "episodes": (f"lockstep as in the reference (time-outs every 75 steps; each reset runs the scripted reset_idx inside the "
-                                    f"timed region: 103 contact steps for Orient OR:1390-1695, 60 + render + 1 + render for Search "
-                                    f"SE:1274-1537, 989-1019); {PRE_STEPS} untimed steps before warm-up" if orient else
-                                    f"staggered: progress ~ U[0,{STAGGER}) then {PRE_STEPS} untimed steps before warm-up (stationary mix of "
-                                    "fresh and settled heaps; resting bricks sleep with PhysX's default threshold and 0.4 s timer)")},
+            "config": make_config(args, world),
             "e2e": {"value": world * n * E / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 23 * 4,
-                    "d2h_bytes_per_step": n * (obs_dim + 564 + 1) * 4 + n * 8, "steps": E},
+                    "d2h_bytes_per_step": n * (obs_dim + 564 + 1) * 4 + n * 8, "steps": E, "timer": "cuda events (max over ranks)",
+                    "value_wall_clock": world * n * E / (e2e_wall_ms * 1e-3),
+                    "scope": "VecTask.step through the C-ABI with pinned HOST buffers (sdx_step_host): the rollout only -- PPO is NOT in this "
+                             "loop, which is why it can exceed `value` (PPO in the loop, device-resident)"},
             "gpu_launches": int(launches),
             "rollout_only": {"value": world * n * KR / (ro_ms * 1e-3), "unit": "env-steps/s", "steps": KR, "ms_per_step": ro_ms / KR},
             "ppo": ppo_info,
@@ -392,7 +427,7 @@ def main():
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
         }
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(scene, bank=None if search else bank[:, :2].cpu().numpy(), stagger=not orient, n_envs=1024 if orient else None)
+            out["cpu_baseline"] = cpu_baseline(scene, bank=None if search else bank.cpu().numpy(), stagger=not orient, n_envs=1024 if orient else None)
         emit(out)
     if world > 1:
         dist.barrier()

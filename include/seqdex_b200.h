@@ -238,9 +238,23 @@ int sdx_mlp_sync(sdx_mlp_t* m, void* stream);
 int sdx_mlp_forward(sdx_mlp_t* m, const float* x_dev, int M, const float* mean, const float* var, int train, void* stream);
 /* whole-batch input conversion (once per PPO iteration) and forward on a row range of it */
 int sdx_mlp_convert_batch(sdx_mlp_t* m, const float* x_dev, int B, const float* mean, const float* var, void* xb_bf16, void* xt_bf16, void* stream);
+/* x_dev is a TIME-major rollout buffer [horizon][B / horizon][in]; rows of the converted batch are ENV-major
+ * (rl_games' swap_and_flatten01, RGC:1480-1481): row n * horizon + t <- x[t][n] */
+int sdx_mlp_convert_batch_env_major(sdx_mlp_t* m, const float* x_dev, int B, int horizon, const float* mean, const float* var, void* xb_bf16,
+                                    void* xt_bf16, void* stream);
 int sdx_mlp_forward_pre(sdx_mlp_t* m, const void* xb_bf16, const void* xt_bf16, int B, int row0, int M, int train, void* stream);
 int sdx_mlp_backward(sdx_mlp_t* m, const float* dout_dev, int M, void* stream);
 int sdx_mlp_adam(sdx_mlp_t* m, float lr, float b1, float b2, float eps, float max_norm, void* stream);   /* RGC:1102, 1866-1872 */
+/* same step with the learning rate read from device memory when the kernel runs (no host round trip for the adaptive schedule) */
+int sdx_mlp_adam_dev(sdx_mlp_t* m, const float* lr_dev, float b1, float b2, float eps, float max_norm, void* stream);
+/* rl_games' AdaptiveScheduler (schedule_type 'legacy' = after EVERY minibatch, RGC:1360-1365) on the device: kl = stats[2] * inv_count;
+ * kl > 2 thr: lr = max(lr / 1.5, lr_min); kl < 0.5 thr: lr = min(lr * 1.5, lr_max).  stats[0..4) are then added to accum[0..4)
+ * (accum[4] counts minibatches, accum[5] = the last kl) and cleared.  adaptive = 0 only moves the statistics. */
+int sdx_ppo_adaptive_lr(float* stats_dev, float inv_count, float kl_threshold, float lr_min, float lr_max, float* lr_dev,
+                        float* accum_dev, int adaptive, void* stream);
+/* the gradient buffer sdx_mlp_info returns has SDX_GRAD_TAIL extra floats behind the nparams gradients: loss statistics written
+ * there are summed by the same all-reduce as the gradients (RGC:1360-1363 averages the KL over ranks before the scheduler) */
+#define SDX_GRAD_TAIL 16
 /* Adam step counter of the MLP's optimiser (torch.optim.Adam state['step'], saved in rl_games checkpoints under 'optimizer',
  * RGC:1913-1933): set < 0 reads it, set >= 0 overwrites it (restore) */
 long long sdx_mlp_adam_step(sdx_mlp_t* m, long long set);

@@ -31,11 +31,26 @@ def heap_bank_to_reference(bank, scene):
     return out
 
 
+SAMPLE_RANGE = 5000      # GS:1508 samples random.sample(range(0, 5000), 1): rows beyond are never drawn
+
+
 def heap_bank_from_reference(lst):
-    """the reference's list -> ours ``[8, K, 72, 13]`` (velocities zeroed as ``GS:1513`` does on load); K = the shortest entry"""
+    """the reference's list -> ours ``[8, K, 72, 13]`` (velocities zeroed as ``GS:1513`` does on load).
+
+    The reference PREALLOCATES 10000 + 1024 rows per type and fills a prefix (SE:319-331, 1313-1343); the rest stays zero --
+    zero positions AND zero quaternions.  ``k_reset`` samples ``slot = r % K`` over all K rows we hand it, so only the leading
+    written rows may be kept: K = min over types of (leading non-zero rows, capped at the 5000 the reference samples from)."""
     assert len(lst) == 8, "the bank holds one tensor per target-brick type (env % 8)"
-    k = min(int(t.shape[0]) for t in lst)
-    out = torch.stack([torch.as_tensor(t, dtype=torch.float32)[:k].reshape(k, -1, 13)[:, :N_FREE] for t in lst]).clone()
+    ts = [torch.as_tensor(t, dtype=torch.float32).reshape(int(t.shape[0]), -1, 13)[:, :N_FREE] for t in lst]
+    filled = []
+    for ty, t in enumerate(ts):
+        written = (t.abs().sum(dim=(1, 2)) > 0).to(torch.int64)
+        lead = int(torch.cumprod(written, 0).sum())              # rows before the first all-zero row
+        if lead == 0:
+            raise ValueError(f"heap bank: brick type {ty} has no written row (the reference fills the rings from slot 0)")
+        filled.append(min(lead, SAMPLE_RANGE))
+    k = min(filled)
+    out = torch.stack([t[:k] for t in ts]).clone()
     out[..., 7:13] = 0
     return out.contiguous()
 

@@ -140,26 +140,49 @@ def central_value_flat(cv_sd, state_dim, hidden=HIDDEN):
     return flat, rms
 
 
-def adam_state_dict(m, v, step, slices, lr, order):
+def adam_state_dict(m, v, step, slices, lr, order, shapes=None):
     """flat Adam moments -> ``torch.optim.Adam.state_dict()`` with one entry per parameter tensor, in ``order``
-    (the order ``model.parameters()`` yields them, which is what the integer ids of a torch optimizer state mean)."""
+    (the order ``model.parameters()`` yields them, which is what the integer ids of a torch optimizer state mean).
+    Names that are not in ``slices`` (the a2c net's own, never-trained critic) get zero moments of ``shapes[name]``."""
     by = {n: (o, s) for n, o, s in slices}
     state = {}
     for i, name in enumerate(order):
-        o, s = by[name]
-        k = _numel(s)
-        state[i] = {"step": torch.tensor(float(step)), "exp_avg": m[o:o + k].detach().float().cpu().view(s).clone(),
-                    "exp_avg_sq": v[o:o + k].detach().float().cpu().view(s).clone()}
+        if name in by:
+            o, s = by[name]
+            k = _numel(s)
+            ea, es = m[o:o + k].detach().float().cpu().view(s).clone(), v[o:o + k].detach().float().cpu().view(s).clone()
+        else:
+            ea, es = torch.zeros(shapes[name]), torch.zeros(shapes[name])
+        state[i] = {"step": torch.tensor(float(step)), "exp_avg": ea, "exp_avg_sq": es}
     return {"state": state, "param_groups": [{"lr": lr, "betas": (0.9, 0.999), "eps": 1e-08, "weight_decay": 0, "amsgrad": False,
                                              "params": list(range(len(order)))}]}
 
 
-def actor_param_order(n_hidden=3):
-    """``parameters()`` order of A2CBuilder.Network (registration order: sigma is created last), actor tensors only"""
-    o = []
-    for l in range(n_hidden):
-        o += [f"W{l}", f"b{l}"]
-    return o + [f"W{n_hidden}", f"b{n_hidden}", "sigma"]
+def a2c_param_entries(in_dim, out_dim, hidden=HIDDEN):
+    """[(name, shape)] in the order ``A2CBuilder.Network.parameters()`` yields them -- the integer ids of rl_games' Adam state.
+    ``nn.Module.parameters()`` lists a module's OWN parameters first (``sigma``, a root-level nn.Parameter), then its sub-modules in
+    registration order: actor_mlp, critic_mlp (``separate: True``), value, mu.  rl_games' optimiser owns all 17 tensors, the
+    never-used critic trunk included, and ``A2CBase.set_full_state_weights`` always calls ``optimizer.load_state_dict``: a state
+    with any other count or order raises there.  Names: W/b = the actor trunk + mu head of ``ppo.MLP.slices``; ``critic_*`` /
+    ``value_*`` = tensors this engine does not train."""
+    dims = [in_dim, *hidden]
+    n = len(hidden)
+    e = [("sigma", (out_dim,))]
+    for l in range(n):
+        e += [(f"W{l}", (dims[l + 1], dims[l])), (f"b{l}", (dims[l + 1],))]
+    for l in range(n):
+        e += [(f"critic_W{l}", (dims[l + 1], dims[l])), (f"critic_b{l}", (dims[l + 1],))]
+    e += [("value_W", (1, hidden[-1])), ("value_b", (1,))]
+    e += [(f"W{n}", (out_dim, hidden[-1])), (f"b{n}", (out_dim,))]
+    return e
+
+
+def actor_param_order(in_dim=None, out_dim=None, hidden=HIDDEN):
+    """names of ``a2c_param_entries`` (all 17 tensors); the shapes are only needed to write zero moments for the critic"""
+    return [n for n, _ in a2c_param_entries(in_dim or 1, out_dim or 1, hidden)]
+
+
+LEGACY_ACTOR_ORDER = ["W0", "b0", "W1", "b1", "W2", "b2", "W3", "b3", "sigma"]   # files written by this package before the fix
 
 
 def save_checkpoint(filename, state):

@@ -9,6 +9,7 @@
 #include <math.h>
 
 #include "sdx_gemm.cuh"
+#include "../../include/seqdex_b200.h"
 
 extern "C" const char* sdx_last_error(void);
 void sdx_set_error(const char* msg);   // defined in sdx_env.cu
@@ -163,15 +164,19 @@ __global__ void k_fill_bf16(__nv_bfloat16* p, size_t n, float v) {
 }
 // fp32 [R, C] (ld) -> bf16 row-major [R, ldo] (cols [C, Cpad) zero-filled) and/or transposed bf16 [Cpad.., ldt];
 // optional per-column normalisation (x - mean) / sqrt(var + 1e-5) clamped to +-5 (rl_games RunningMeanStd)
+// perm_h > 0: output row r = n * perm_h + t reads source row t * (R / perm_h) + n -- rl_games' swap_and_flatten01 (time-major
+// rollout buffers [H][N] -> env-major batch rows, RGC:1480-1481) fused into the conversion
 __global__ void k_cvt_2way(const float* __restrict__ src, int R, int C, int ld, int Cpad, __nv_bfloat16* __restrict__ dst, int ldo,
-                           __nv_bfloat16* __restrict__ dst_t, int ldt, const float* __restrict__ mean, const float* __restrict__ var) {
+                           __nv_bfloat16* __restrict__ dst_t, int ldt, const float* __restrict__ mean, const float* __restrict__ var,
+                           int perm_h = 0) {
   __shared__ float tile[32][33];
   int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int r = r0 + i, c = c0 + threadIdx.x;
     float v = 0.0f;
     if (r < R && c < C) {
-      v = src[(size_t)r * ld + c];
+      const int rs = perm_h > 0 ? (r % perm_h) * (R / perm_h) + r / perm_h : r;
+      v = src[(size_t)rs * ld + c];
       if (mean) { v = (v - mean[c]) / sqrtf(var[c] + 1e-5f); v = fminf(fmaxf(v, -5.0f), 5.0f); }
     }
     tile[i][threadIdx.x] = v;
@@ -221,9 +226,11 @@ __global__ void k_sumsq_final(const float* __restrict__ partial, int nb, float* 
 }
 // torch.optim.Adam (eps 1e-8, no weight decay; RGC:1102) with rl_games' global grad-norm clip folded in (RGC:1866-1872)
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-                       float lr, float b1, float b2, float eps, float bc1, float bc2, float max_norm, const float* __restrict__ sumsq) {
+                       float lr, float b1, float b2, float eps, float bc1, float bc2, float max_norm, const float* __restrict__ sumsq,
+                       const float* __restrict__ lr_dev = nullptr) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (lr_dev) lr = *lr_dev;
   float scale = 1.0f;
   if (max_norm > 0.0f) { float nrm = sqrtf(*sumsq); scale = fminf(1.0f, max_norm / (nrm + 1e-6f)); }
   float gi = g[i] * scale;
@@ -281,7 +288,7 @@ extern "C" int sdx_mlp_create_ex(int in_dim, int out_dim, int h1, int h2, int h3
   m->sigma_off = off; if (has_sigma) off += out_dim;
   m->nparams = off;
   PCK(cudaMalloc(&m->params, off * 4)); PCK(cudaMemset(m->params, 0, off * 4));
-  PCK(cudaMalloc(&m->grads, off * 4)); PCK(cudaMemset(m->grads, 0, off * 4));
+  PCK(cudaMalloc(&m->grads, (off + SDX_GRAD_TAIL) * 4)); PCK(cudaMemset(m->grads, 0, (off + SDX_GRAD_TAIL) * 4));   // tail: loss statistics that ride along with the gradient all-reduce
   PCK(cudaMalloc(&m->adam_m, off * 4)); PCK(cudaMemset(m->adam_m, 0, off * 4));
   PCK(cudaMalloc(&m->adam_v, off * 4)); PCK(cudaMemset(m->adam_v, 0, off * 4));
   PCK(cudaMalloc(&m->out, (size_t)max_rows * out_dim * 4));
@@ -360,16 +367,24 @@ extern "C" int sdx_mlp_forward(sdx_mlp* m, const float* x, int M, const float* m
 }
 // Convert a whole rollout batch ONCE per iteration: x fp32 [B, in_dim] -> xb bf16 [B, in_pad] and xt bf16 [in_pad + 16, B]
 // (row in_pad = ones, for the bias gradient).  Minibatches are then row ranges of xb / column ranges of xt.
-extern "C" int sdx_mlp_convert_batch(sdx_mlp* m, const float* x, int B, const float* mean, const float* var, void* xb, void* xt, void* stream) {
+static int convert_batch(sdx_mlp* m, const float* x, int B, int horizon, const float* mean, const float* var, void* xb, void* xt, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (B % 8) { sdx_set_error("sdx_mlp_convert_batch: B must be a multiple of 8"); return -1; }
+  if (B % 8 || (horizon > 0 && B % horizon)) { sdx_set_error("sdx_mlp_convert_batch: B must be a multiple of 8 (and of the horizon)"); return -1; }
   dim3 blk(32, 8), grd((m->in_pad + 31) / 32, (B + 31) / 32);
-  k_cvt_2way<<<grd, blk, 0, st>>>(x, B, m->in_dim, m->in_dim, m->in_pad, (__nv_bfloat16*)xb, m->in_pad, (__nv_bfloat16*)xt, B, mean, var);
+  k_cvt_2way<<<grd, blk, 0, st>>>(x, B, m->in_dim, m->in_dim, m->in_pad, (__nv_bfloat16*)xb, m->in_pad, (__nv_bfloat16*)xt, B, mean, var, horizon);
   PCK(cudaMemsetAsync((__nv_bfloat16*)xt + (size_t)m->in_pad * B, 0, (size_t)16 * B * 2, st));
   k_fill_bf16<<<(unsigned)((B + 255) / 256), 256, 0, st>>>((__nv_bfloat16*)xt + (size_t)m->in_pad * B, (size_t)B, 1.0f);
   g_ppo_launches += 2;
   PCK(cudaGetLastError());
   return 0;
+}
+extern "C" int sdx_mlp_convert_batch(sdx_mlp* m, const float* x, int B, const float* mean, const float* var, void* xb, void* xt, void* stream) {
+  return convert_batch(m, x, B, 0, mean, var, xb, xt, stream);
+}
+/* x is a time-major rollout buffer [horizon][B / horizon][in_dim]; the converted batch is env-major (swap_and_flatten01) */
+extern "C" int sdx_mlp_convert_batch_env_major(sdx_mlp* m, const float* x, int B, int horizon, const float* mean, const float* var, void* xb, void* xt,
+                                               void* stream) {
+  return convert_batch(m, x, B, horizon, mean, var, xb, xt, stream);
 }
 // forward on rows [row0, row0 + M) of a converted batch (xb [B, in_pad], xt [in_pad + 16, B])
 extern "C" int sdx_mlp_forward_pre(sdx_mlp* m, const void* xb, const void* xt, int B, int row0, int M, int train, void* stream) {
@@ -412,7 +427,7 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
 }
 /* optimiser step counter (the `step` of torch.optim.Adam's state): read with set < 0, overwritten otherwise (checkpoint restore) */
 extern "C" long long sdx_mlp_adam_step(sdx_mlp* m, long long set) { if (set >= 0) m->adam_t = set; return m->adam_t; }
-extern "C" int sdx_mlp_adam(sdx_mlp* m, float lr, float b1, float b2, float eps, float max_norm, void* stream) {
+static int mlp_adam(sdx_mlp* m, float lr, const float* lr_dev, float b1, float b2, float eps, float max_norm, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   m->adam_t++;
   if (max_norm > 0.0f) {
@@ -422,10 +437,41 @@ extern "C" int sdx_mlp_adam(sdx_mlp* m, float lr, float b1, float b2, float eps,
   }
   g_ppo_launches++;
   float bc1 = 1.0f - powf(b1, (float)m->adam_t), bc2 = 1.0f - powf(b2, (float)m->adam_t);
-  k_adam<<<(unsigned)((m->nparams + 255) / 256), 256, 0, st>>>(m->params, m->grads, m->adam_m, m->adam_v, m->nparams, lr, b1, b2, eps, bc1, bc2, max_norm, m->scal);
+  k_adam<<<(unsigned)((m->nparams + 255) / 256), 256, 0, st>>>(m->params, m->grads, m->adam_m, m->adam_v, m->nparams, lr, b1, b2, eps, bc1, bc2, max_norm, m->scal, lr_dev);
   g_ppo_launches++;
   PCK(cudaGetLastError());
   return sdx_mlp_sync(m, stream);
+}
+extern "C" int sdx_mlp_adam(sdx_mlp* m, float lr, float b1, float b2, float eps, float max_norm, void* stream) {
+  return mlp_adam(m, lr, nullptr, b1, b2, eps, max_norm, stream);
+}
+/* the learning rate is read from device memory when the step runs: the adaptive-KL schedule is applied on the device after every
+ * minibatch (sdx_ppo_adaptive_lr) without a host round trip */
+extern "C" int sdx_mlp_adam_dev(sdx_mlp* m, const float* lr_dev, float b1, float b2, float eps, float max_norm, void* stream) {
+  return mlp_adam(m, 0.0f, lr_dev, b1, b2, eps, max_norm, stream);
+}
+// rl_games AdaptiveScheduler.update on the device (schedule_type 'legacy': after every minibatch, RGC:1360-1365): kl = stats[2] * inv_count;
+// kl > 2 thr -> lr = max(lr / 1.5, lr_min); kl < 0.5 thr -> lr = min(lr * 1.5, lr_max).  The minibatch statistics are then added to
+// accum[0..4) (+ accum[4] = minibatches seen, accum[5] = last kl) and cleared for the next minibatch.
+__global__ void k_adaptive_lr(float* __restrict__ stats, float inv_count, float thr, float lr_min, float lr_max, float* __restrict__ lr,
+                              float* __restrict__ accum, int adaptive) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float kl = stats[2] * inv_count;
+  if (adaptive) {
+    float l = *lr;
+    if (kl > 2.0f * thr) l = fmaxf(l / 1.5f, lr_min);
+    if (kl < 0.5f * thr) l = fminf(l * 1.5f, lr_max);
+    *lr = l;
+  }
+  for (int i = 0; i < 4; ++i) { accum[i] += stats[i]; stats[i] = 0.0f; }
+  accum[4] += 1.0f; accum[5] = kl;
+}
+extern "C" int sdx_ppo_adaptive_lr(float* stats_dev, float inv_count, float kl_threshold, float lr_min, float lr_max, float* lr_dev,
+                                   float* accum_dev, int adaptive, void* stream) {
+  k_adaptive_lr<<<1, 32, 0, (cudaStream_t)stream>>>(stats_dev, inv_count, kl_threshold, lr_min, lr_max, lr_dev, accum_dev, adaptive);
+  g_ppo_launches++;
+  PCK(cudaGetLastError());
+  return 0;
 }
 
 // =====================================================================================================
@@ -485,7 +531,7 @@ __global__ void k_ppo_actor_loss(const float* __restrict__ mu, const float* __re
       float hi = fmaxf(m_ - 1.1f, 0.0f), lo = fminf(m_ + 1.1f, 0.0f);
       bl += hi * hi + lo * lo;
       float so = expf(old_logstd[i]), dm = old_mu[(size_t)e * A + i] - m_;
-      kl += logf(sg / so + 1e-5f) + (so * so + dm * dm) / (2.0f * (sg * sg + 1e-5f)) - 0.5f;
+      kl += logf(so / sg + 1e-5f) + (sg * sg + dm * dm) / (2.0f * (so * so + 1e-5f)) - 0.5f;   // torch_ext.policy_kl(mu, sigma, old_mu, old_sigma), RGC:1903
     }
     nlp += 0.5f * (float)A * 1.8378770664093453f + sls;
     float ratio = expf(old_neglogp[e] - nlp), a = adv[e];

@@ -1,5 +1,5 @@
-"""Host-side helpers of the multi-GPU path: env sharding and the few collectives
-PPO needs.  Pure torch.distributed, so the logic is testable with the gloo backend on CPU."""
+"""Host-side helpers of the multi-GPU path: env sharding (bench.py) and the collectives of ``A2CAgent``
+(``ppo.py::_allreduce``).  Pure torch.distributed, so the logic is testable with the gloo backend on CPU."""
 from __future__ import annotations
 
 import torch
@@ -16,13 +16,30 @@ def shard_envs(global_envs: int, world: int, rank: int):
     return rank * per, per
 
 
-def allreduce_mean_(t: torch.Tensor, group=None):
-    """in-place average over ranks (gradient / KL all-reduce)"""
+def allreduce_(t: torch.Tensor, group=None, avg=True):
+    """in-place sum (avg: mean) over ranks -- the collective ``A2CAgent._allreduce`` issues for gradients + KL, advantage moments and
+    RunningMeanStd column moments"""
     world = dist.get_world_size(group)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        t.div_(world)
+        if avg:
+            t.div_(world)
     return t
+
+
+def allreduce_mean_(t: torch.Tensor, group=None):
+    return allreduce_(t, group, True)
+
+
+def params_digest(*tensors):
+    """64-bit digest of parameter tensors (sum of the fp32 bit patterns as int64, and of their squares mod 2^63): equal on every rank
+    iff the replicas are in lock-step; bench.py all-gathers it after the timed region"""
+    acc = torch.zeros(2, dtype=torch.int64, device=tensors[0].device)
+    for t in tensors:
+        b = t.detach().contiguous().view(torch.int32).to(torch.int64)
+        acc[0] += b.sum()
+        acc[1] += (b * (b & 0xFFFF)).sum()
+    return acc
 
 
 def global_moments(x: torch.Tensor, group=None):

@@ -28,6 +28,21 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+GRAD_TAIL = 16        # SDX_GRAD_TAIL (include/seqdex_b200.h)
+LR_MIN, LR_MAX = 1e-6, 1e-2   # rl_games AdaptiveScheduler bounds
+
+
+def adaptive_lr(lr, kl, kl_threshold):
+    """rl_games 1.5.2 ``AdaptiveScheduler.update`` (called at RGC:1360-1365 after every minibatch: the SeqDex yamls leave
+    ``schedule_type`` at its default 'legacy').  Host restatement of what ``sdx_ppo_adaptive_lr`` does on the device; used where a
+    learning rate lives on the host (checkpoint restore, tests/test_ppo_oracle_golden.py)."""
+    if kl > 2.0 * kl_threshold:
+        lr = max(lr / 1.5, LR_MIN)
+    if kl < 0.5 * kl_threshold:
+        lr = min(lr * 1.5, LR_MAX)
+    return lr
+
+
 class _View:
     def __init__(self, ptr, shape, typestr="<f4"):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
@@ -52,6 +67,9 @@ class MLP:
             self.nparams = n.value
             mk = lambda p, shp: torch.as_tensor(_View(p.value, shp), device=self.device)
             self.params, self.grads = mk(pp, [self.nparams]), mk(pg, [self.nparams])
+            # the gradient buffer carries GRAD_TAIL extra floats: loss statistics written there are summed by the SAME all-reduce
+            self.grads_ext = mk(pg, [self.nparams + GRAD_TAIL])
+            self.stats = self.grads_ext[self.nparams:self.nparams + 4]
             self.adam_m, self.adam_v = mk(pm, [self.nparams]), mk(pv, [self.nparams])
             self.out = mk(po, [max_rows, out_dim])
         self.dims = [in_dim, hidden[0], hidden[1], hidden[2], out_dim]
@@ -103,6 +121,10 @@ class MLP:
         """fp32 [B, in] -> bf16 [B, in_pad] + transposed bf16 [in_pad + 16, B] (ones row appended), once per iteration"""
         _lib.check(self.L.sdx_mlp_convert_batch(self.h, _p(x), x.shape[0], _p(mean), _p(var), _p(xb), _p(xt), _stream()))
 
+    def convert_batch_env_major(self, x, horizon, xb, xt, mean=None, var=None):
+        """x: TIME-major rollout buffer [H * N, in]; rows of the converted batch are ENV-major (rl_games' swap_and_flatten01)"""
+        _lib.check(self.L.sdx_mlp_convert_batch_env_major(self.h, _p(x), x.shape[0], int(horizon), _p(mean), _p(var), _p(xb), _p(xt), _stream()))
+
     def forward_pre(self, xb, xt, row0, M, train=True):
         _lib.check(self.L.sdx_mlp_forward_pre(self.h, _p(xb), _p(xt), xb.shape[0], row0, M, int(train), _stream()))
         return self.out[:M]
@@ -114,6 +136,11 @@ class MLP:
     def adam(self, lr, max_norm=1.0, b1=0.9, b2=0.999, eps=1e-8):
         _lib.check(self.L.sdx_mlp_adam(self.h, ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
                                        ctypes.c_float(max_norm), _stream()))
+
+    def adam_dev(self, lr_dev, max_norm=1.0, b1=0.9, b2=0.999, eps=1e-8):
+        """Adam step whose learning rate is read from device memory when the kernel runs"""
+        _lib.check(self.L.sdx_mlp_adam_dev(self.h, _p(lr_dev), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
+                                           ctypes.c_float(max_norm), _stream()))
 
     def torch_reference(self):
         """plain fp32 torch modules holding the same parameters (tests / checkpoint export)"""
@@ -169,7 +196,11 @@ class A2CAgent:
         self.actor = MLP(self.obs_dim, self.A, rows, has_sigma=True, device=device, seed=c.seed)
         self.cv = MLP(self.state_dim, 1, rows, has_sigma=False, device=device, seed=c.seed + 1)
         self.dist = dist_group
-        self.world = torch.distributed.get_world_size() if dist_group is not None else 1
+        self.world = torch.distributed.get_world_size(dist_group) if dist_group is not None else 1
+        self.rank = torch.distributed.get_rank(dist_group) if dist_group is not None else 0
+        # parameters start identical on every rank (same init seed); the exploration noise must NOT: rank r's env e would
+        # otherwise draw exactly rank 0's env e noise (Philox key = env index)
+        self.sample_seed = c.seed + 0x9E3779B1 * self.rank
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=self.device, dtype=dt)
         H, N, A = self.H, self.N, self.A
         self.b_obs, self.b_states = z(H, N, self.obs_dim), z(H, N, self.state_dim)
@@ -181,7 +212,9 @@ class A2CAgent:
         self.xb_obs, self.xt_obs = bf(self.B, self.actor.in_pad), bf(self.actor.in_pad + 16, self.B)
         self.xb_st, self.xt_st = bf(self.B, self.cv.in_pad), bf(self.cv.in_pad + 16, self.B)
         self.dmu, self.dv = z(self.mb, A), z(self.mb, 1)
-        self.stats, self.cv_stats = z(4), z(4)
+        self.stats, self.cv_stats = self.actor.stats, z(4)      # actor statistics live in the tail of the gradient buffer
+        self.lr_dev = torch.full((1,), float(c.learning_rate), device=self.device)
+        self.accum = z(8)                                      # per-iteration sums of the minibatch statistics | #minibatches | last kl
         self.mom = torch.zeros(2, device=self.device, dtype=torch.float64)
         self.colmom = torch.zeros(2 * self.state_dim, device=self.device, dtype=torch.float64)
         self.rms_mean, self.rms_var = z(self.state_dim), torch.ones(self.state_dim, device=self.device)
@@ -224,7 +257,7 @@ class A2CAgent:
         self.b_dones[t].copy_(self.dones)
         mu = self.actor.forward(self.b_obs[t])
         self.b_mu[t].copy_(mu)
-        _lib.check(L.sdx_ppo_sample(_p(self.b_mu[t]), _p(self.logstd), N, A, ctypes.c_uint64(self.cfg.seed), self.sample_counter,
+        _lib.check(L.sdx_ppo_sample(_p(self.b_mu[t]), _p(self.logstd), N, A, ctypes.c_uint64(self.sample_seed), self.sample_counter,
                                     _p(self.b_actions[t]), _p(self.b_neglogp[t]), _stream()))
         self.sample_counter += 1
         v = self.cv.forward(self.b_states[t], mean, var)
@@ -271,9 +304,8 @@ class A2CAgent:
 
     def _allreduce(self, t, avg=True):
         if self.dist is not None and self.world > 1:
-            torch.distributed.all_reduce(t, group=self.dist)
-            if avg:
-                t.div_(self.world)
+            from .dist_utils import allreduce_
+            allreduce_(t, self.dist, avg)
 
     # ---- update (RGC:1621-1683, 1339-1375, 1767-1911)
     def train_epoch(self):
@@ -281,28 +313,32 @@ class A2CAgent:
         return self.update()
 
     def update(self):
-        """prepare_dataset + central-value and actor mini-epochs on the rollout the buffers hold (RGC:1621-1683, PSR:277-319)"""
-        c, L, A, B, mb = self.cfg, self.L, self.A, self.B, self.mb
+        """prepare_dataset + central-value and actor mini-epochs on the rollout the buffers hold (RGC:1621-1683, 1306-1392, PSR:277-319).
+        The batch is ENV-major as in rl_games (``swap_and_flatten01``, RGC:1480-1481): a minibatch is a contiguous block of envs with
+        all H steps of each.  The adaptive-KL schedule runs after EVERY minibatch (``schedule_type`` defaults to 'legacy',
+        RGC:1360-1365), on the device."""
+        c, L, A, B, mb, H = self.cfg, self.L, self.A, self.B, self.mb, self.H
         Btot = B * self.world
-        obs, states = self.b_obs.view(B, -1), self.b_states.view(B, -1)
-        actions, mu_old, nlp_old = self.b_actions.view(B, A), self.b_mu.view(B, A), self.b_neglogp.view(B)
-        values, returns = self.b_values.view(B), self.b_returns.view(B)
-        adv = (self.b_returns - self.b_values).view(B).contiguous()
+        em = lambda t: t.transpose(0, 1).reshape(B, *t.shape[2:]).contiguous()          # swap_and_flatten01
+        actions, mu_old, nlp_old = em(self.b_actions), em(self.b_mu), em(self.b_neglogp)
+        values, returns = em(self.b_values), em(self.b_returns)
+        adv = (returns - values).contiguous()
+        states_tm = self.b_states.view(B, -1)
         if c.normalize_advantage:                       # (adv - mean) / (std + 1e-8) over the GLOBAL batch (RGC:1651)
             _lib.check(L.sdx_moments(_p(adv), B, _p(self.mom), _stream()))
             self._allreduce(self.mom, avg=False)
             _lib.check(L.sdx_normalize(_p(adv), B, _p(self.mom), ctypes.c_double(Btot), _stream()))
         if c.cv_normalize_input:                        # RunningMeanStd of the critic state, merged once per iteration
-            _lib.check(L.sdx_col_moments(_p(states), B, self.state_dim, _p(self.colmom), _stream()))
+            _lib.check(L.sdx_col_moments(_p(states_tm), B, self.state_dim, _p(self.colmom), _stream()))
             self._allreduce(self.colmom, avg=False)
             _lib.check(L.sdx_rms_merge(_p(self.rms_mean), _p(self.rms_var), _p(self.rms_count), _p(self.colmom), self.state_dim,
                                        ctypes.c_double(Btot), _stream()))
         nmb = B // mb
         inv = 1.0 / float(mb)
-        # inputs of both networks -> bf16 (row-major + transposed) ONCE per iteration; minibatches are slices of these
-        self.actor.convert_batch(obs, self.xb_obs, self.xt_obs)
-        self.cv.convert_batch(states, self.xb_st, self.xt_st, self.rms_mean if c.cv_normalize_input else None,
-                              self.rms_var if c.cv_normalize_input else None)
+        # inputs of both networks -> bf16 (row-major + transposed, env-major rows) ONCE per iteration; minibatches are slices of these
+        self.actor.convert_batch_env_major(self.b_obs.view(B, -1), H, self.xb_obs, self.xt_obs)
+        self.cv.convert_batch_env_major(states_tm, H, self.xb_st, self.xt_st, self.rms_mean if c.cv_normalize_input else None,
+                                        self.rms_var if c.cv_normalize_input else None)
         # The two networks' updates are independent once the rollout is in the buffers: the central-value chain goes to a side
         # stream so that its small kernels (loss, norm, Adam, unpack) and GEMM tails overlap the actor chain's GEMMs and vice
         # versa.  The steps of the two chains are ISSUED alternately (so that, with several GPUs, their all-reduces enter the
@@ -313,6 +349,7 @@ class A2CAgent:
         if side is not None:
             side.wait_stream(main)
         side_ctx = (lambda: torch.cuda.stream(side)) if side is not None else contextlib.nullcontext
+        na = self.actor.nparams
 
         def cv_step(i):       # central value network (asymmetric critic), own optimiser lr 1e-3
             s = slice(i * mb, (i + 1) * mb)
@@ -326,43 +363,37 @@ class A2CAgent:
         def actor_step(i):
             s = slice(i * mb, (i + 1) * mb)
             mu = self.actor.forward_pre(self.xb_obs, self.xt_obs, i * mb, mb)
-            self.actor.grads[self.actor.nparams - A:].zero_()
+            self.actor.grads[na - A:].zero_()
             _lib.check(L.sdx_ppo_actor_loss(_p(mu), _p(self.logstd), _p(actions[s]), _p(mu_old[s]), _p(self.old_logstd[i]), _p(nlp_old[s]),
                                             _p(adv[s]), mb, A, ctypes.c_float(c.e_clip), ctypes.c_float(c.bounds_loss_coef),
-                                            ctypes.c_float(inv), _p(self.dmu), _p(self.actor.grads[self.actor.nparams - A:]),
+                                            ctypes.c_float(inv), _p(self.dmu), _p(self.actor.grads[na - A:]),
                                             _p(self.stats), _stream()))
             mu_old[s].copy_(mu)                                  # dataset.update_mu_sigma (RGC:1358)
             self.old_logstd[i].copy_(self.logstd)
             self.actor.backward(self.dmu)
-            self._allreduce(self.actor.grads)
-            self.actor.adam(self.last_lr, c.grad_norm)
+            self._allreduce(self.actor.grads_ext[:na + 4])       # gradients AND the minibatch statistics (KL averaged over ranks, RGC:1361-1362)
+            self.actor.adam_dev(self.lr_dev, c.grad_norm)
+            _lib.check(L.sdx_ppo_adaptive_lr(_p(self.stats), ctypes.c_float(inv), ctypes.c_float(c.kl_threshold), ctypes.c_float(LR_MIN),
+                                             ctypes.c_float(LR_MAX), _p(self.lr_dev), _p(self.accum), int(c.lr_schedule == "adaptive"), _stream()))
 
         self.old_logstd.copy_(self.logstd.unsqueeze(0).expand(nmb, A))
-        st = self.stats
+        self.accum.zero_()
+        self.stats.zero_()
+        self.lr_dev.fill_(self.last_lr)
         for ep in range(max(c.mini_epochs, c.cv_mini_epochs)):
-            if ep < c.mini_epochs:
-                self.stats.zero_()
             for i in range(nmb):
                 if ep < c.cv_mini_epochs:
                     with side_ctx():
                         cv_step(i)
                 if ep < c.mini_epochs:
                     actor_step(i)
-            if ep >= c.mini_epochs:
-                continue
-            st = self.stats.clone()
-            self._allreduce(st)
-            kl = float(st[2]) / B                                     # one host sync per mini-epoch, like rl_games' av_kls
-            self.last_kl = kl
-            if c.lr_schedule == "adaptive":                          # RGC:1369-1374
-                if kl > 2.0 * c.kl_threshold:
-                    self.last_lr = max(self.last_lr / 1.5, 1e-6)
-                if kl < 0.5 * c.kl_threshold:
-                    self.last_lr = min(self.last_lr * 1.5, 1e-2)
         if side is not None:
             main.wait_stream(side)
+        acc = self.accum.tolist() + [float(self.lr_dev)]          # the iteration's one host read
+        nb = max(acc[4], 1.0) * mb
+        self.last_kl, self.last_lr = acc[5], acc[8]
         self.epoch_num += 1
-        return {"kl": self.last_kl, "lr": self.last_lr, "a_loss": float(st[0]) / B, "b_loss": float(st[1]) / B,
+        return {"kl": self.last_kl, "lr": self.last_lr, "a_loss": acc[0] / nb, "b_loss": acc[1] / nb, "kl_mean": acc[2] / nb,
                 "mean_reward": float(self.b_rewards.mean())}
 
     # ---- checkpoint (rl_games .pth layout, seqdex_b200/checkpoint.py; RGC:1913-1933, 2098-2106)
@@ -379,8 +410,9 @@ class A2CAgent:
         from . import checkpoint as ck
         state = self.get_weights()
         state["epoch"] = self.epoch_num
+        ent = ck.a2c_param_entries(self.obs_dim, self.A)
         state["optimizer"] = ck.adam_state_dict(self.actor.adam_m, self.actor.adam_v, self._adam_step(self.actor), self.actor.slices(),
-                                                self.last_lr, ck.actor_param_order())
+                                                self.last_lr, [n for n, _ in ent], shapes=dict(ent))
         state["assymetric_vf_nets"] = ck.central_value_state_dict(
             self.cv.params, self.state_dim, rms=(self.rms_mean, self.rms_var, self.rms_count) if self.cfg.cv_normalize_input else None)
         cvo = [n for n, _, _ in self.cv.slices()]
@@ -410,10 +442,14 @@ class A2CAgent:
         if load_optimizer_state:
             for mlp, key, order in ((self.actor, "optimizer", ck.actor_param_order()), (self.cv, "assymetric_vf_optimizer", [n for n, _, _ in self.cv.slices()])):
                 opt = weights.get(key)
+                if opt and key == "optimizer" and len(opt["state"]) == len(ck.LEGACY_ACTOR_ORDER):
+                    order = ck.LEGACY_ACTOR_ORDER
                 if not opt or len(opt["state"]) != len(order):
-                    continue        # e.g. a file written by rl_games itself: its optimizer also holds the unused critic trunk
+                    continue
                 by = {n: (o, s) for n, o, s in mlp.slices()}
                 for i, name in enumerate(order):
+                    if name not in by:
+                        continue    # the a2c net's own critic trunk / value head: rl_games' optimiser holds them, this engine does not train them
                     o, shp = by[name]
                     k = opt["state"][i]["exp_avg"].numel()
                     mlp.adam_m[o:o + k].copy_(opt["state"][i]["exp_avg"].reshape(-1))

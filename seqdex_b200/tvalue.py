@@ -33,26 +33,37 @@ class TValueTrainer:
         self.stats = torch.zeros(4, device=self.device)
         self.L = _lib.load()
 
+    @staticmethod
+    def make_batch(succ_rows, fail_rows, noise_s, noise_f):
+        """TVT:216-220: rows + 0.05 x U(-1, 1) noise, each half re-normalised to a unit quaternion; labels 1 (success) then 0"""
+        xs = succ_rows + noise_s * 0.05
+        xs = xs / xs.norm(dim=-1, keepdim=True)
+        xf = fail_rows + noise_f * 0.05
+        xf = xf / xf.norm(dim=-1, keepdim=True)
+        h = xs.shape[0]
+        y = torch.cat([torch.ones(h, dtype=torch.int32, device=xs.device), torch.zeros(xf.shape[0], dtype=torch.int32, device=xs.device)])
+        return torch.cat([xs, xf]).contiguous(), y
+
     def _sample(self):
         h = self.batch // 2
         i = torch.randint(len(self.succ), (h,), device=self.device, generator=self.gen)
         j = torch.randint(len(self.fail), (h,), device=self.device, generator=self.gen)
-        x = torch.cat([self.succ[i], self.fail[j]])
-        x = x + (torch.rand(x.shape, device=self.device, generator=self.gen) * 0.1 - 0.05)   # TVT:216-219
-        x = x / x.norm(dim=-1, keepdim=True)                                                 # TVT:220
-        y = torch.cat([torch.ones(h, dtype=torch.int32, device=self.device), torch.zeros(h, dtype=torch.int32, device=self.device)])
-        return x.contiguous(), y
+        noise = torch.rand(2 * h, 4, device=self.device, generator=self.gen) * 2 - 1         # TVT:210 torch_rand_float(-1, 1, ...)
+        return self.make_batch(self.succ[i], self.fail[j], noise[:h], noise[h:])
+
+    def step(self, x, y):
+        """forward, BCE-with-logits on the ELU outputs, backward, Adam(lr) (TVT:222-229); returns the device statistics (sum of losses at [0])"""
+        z = self.net.forward(x, train=True)
+        self.stats.zero_()
+        _lib.check(self.L.sdx_tvalue_bce(_p(z), _p(y), x.shape[0], _p(self.dz), _p(self.stats), _stream()))
+        self.net.backward(self.dz)
+        self.net.adam(self.lr, max_norm=0.0)
+        return self.stats
 
     def train_rollout(self, iters):
         last = None
         for _ in range(iters):
-            x, y = self._sample()
-            z = self.net.forward(x, train=True)
-            self.stats.zero_()
-            _lib.check(self.L.sdx_tvalue_bce(_p(z), _p(y), self.batch, _p(self.dz), _p(self.stats), _stream()))
-            self.net.backward(self.dz)
-            self.net.adam(self.lr, max_norm=0.0)
-            last = self.stats
+            last = self.step(*self._sample())
         return float(last[0]) / (2 * self.batch) if last is not None else float("nan")
 
     @torch.no_grad()

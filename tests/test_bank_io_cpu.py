@@ -24,6 +24,31 @@ def test_heap_bank_pickle_round_trip_in_reference_layout(scene, tmp_path):
     np.testing.assert_array_equal(back.numpy(), bank)
 
 
+def test_reference_written_bank_is_trimmed_to_its_written_rows(scene, tmp_path):
+    """the reference preallocates 10000 + 1024 rows per type and fills a prefix (SE:319-331); the zero rows behind it (zero
+    quaternions!) must never reach ``set_heap_bank``, whose reset kernel samples ``slot % K`` over every row it is given"""
+    bank = lattice_bank(scene, 7)
+    ref = []
+    for ty in range(8):
+        t = torch.zeros(11024, 132, 13)
+        k = 7 if ty != 5 else 4                                # type 5 has banked fewer heaps
+        t[:k, :72] = torch.from_numpy(bank[ty, :k])
+        ref.append(t)
+    p = tmp_path / "saved_searching_ternimal_states_good_mo_tvalue.pkl"
+    with open(p, "wb") as f:
+        pickle.dump(ref, f)
+    back = bank_io.load_heap_bank(p)
+    assert tuple(back.shape) == (8, 4, 72, 13)                 # K = the fewest leading written rows of any type
+    q = back[..., 3:7]
+    assert float((q.norm(dim=-1) - 1).abs().max()) < 1e-5      # no zero-quaternion row survives
+    ref[2][:] = 0
+    with open(p, "wb") as f:
+        pickle.dump(ref, f)
+    import pytest
+    with pytest.raises(ValueError):
+        bank_io.load_heap_bank(p)
+
+
 def test_tvalue_dataset_names_and_round_trip(tmp_path):
     rng = np.random.default_rng(0)
     s, f = rng.normal(size=(5, 4)).astype(np.float32), rng.normal(size=(12, 4)).astype(np.float32)

@@ -20,12 +20,14 @@ class _A2CNetwork(torch.nn.Module):
                 layers += [torch.nn.Linear(d, u), torch.nn.ELU()]
                 d = u
             return torch.nn.Sequential(*layers)
+        # registration order of rl_games' A2CBuilder.Network: actor_mlp, critic_mlp, value, then mu and the sigma parameter
         self.actor_mlp = trunk()
         if not central_value:
             self.critic_mlp = trunk()
+        self.value = torch.nn.Linear(units[-1], 1)
+        if not central_value:
             self.mu = torch.nn.Linear(units[-1], actions)
             self.sigma = torch.nn.Parameter(torch.zeros(actions))
-        self.value = torch.nn.Linear(units[-1], 1)
 
 
 class _Model(torch.nn.Module):
@@ -101,20 +103,30 @@ def test_central_value_round_trip_with_running_mean_std():
 
 
 def test_adam_state_dict_is_loadable_by_torch_optim(tmp_path):
+    """rl_games' Adam owns ALL parameters of the a2c network in ``parameters()`` order -- sigma first (a root-level nn.Parameter),
+    then actor_mlp, critic_mlp, value, mu: 17 tensors -- and ``A2CBase.set_full_state_weights`` always loads the optimiser state,
+    so the state we write must load into exactly that optimiser and put every moment on the right tensor."""
     sl, n = ck.mlp_slices(64, 3, hidden=(64, 64, 64), has_sigma=True)
     m, v = _flat(n, 3), _flat(n, 4).abs()
-    osd = ck.adam_state_dict(m, v, 17, sl, 3e-4, ck.actor_param_order())
+    ent = ck.a2c_param_entries(64, 3, hidden=(64, 64, 64))
+    osd = ck.adam_state_dict(m, v, 17, sl, 3e-4, [k for k, _ in ent], shapes=dict(ent))
     net = _A2CNetwork(64, 3, units=(64, 64, 64))
-    # entries follow checkpoint.actor_param_order(): trunk, mu head, sigma
-    by_shape = [tuple(osd["state"][i]["exp_avg"].shape) for i in range(len(osd["state"]))]
-    assert by_shape == [(64, 64), (64,), (64, 64), (64,), (64, 64), (64,), (3, 64), (3,), (3,)]
-    ours = [dict(net.named_parameters())[k] for k in ("actor_mlp.0.weight", "actor_mlp.0.bias", "actor_mlp.2.weight", "actor_mlp.2.bias",
-                                                        "actor_mlp.4.weight", "actor_mlp.4.bias", "mu.weight", "mu.bias", "sigma")]
-    opt = torch.optim.Adam(ours, lr=1.0)
-    opt.load_state_dict(osd)
+    names = [k for k, _ in net.named_parameters()]
+    assert names[0] == "sigma" and names[1].startswith("actor_mlp") and names[7].startswith("critic_mlp") and names[13:] == [
+        "value.weight", "value.bias", "mu.weight", "mu.bias"] and len(names) == 17
+    assert [tuple(osd["state"][i]["exp_avg"].shape) for i in range(17)] == [tuple(p.shape) for p in net.parameters()]
+    opt = torch.optim.Adam(net.parameters(), lr=1.0)
+    opt.load_state_dict(osd)                                  # raises on any count / shape mismatch
     assert opt.param_groups[0]["lr"] == 3e-4
-    assert float(opt.state[ours[0]]["step"]) == 17.0
-    assert torch.equal(opt.state[ours[-1]]["exp_avg"], m[n - 3:])
+    P = dict(net.named_parameters())
+    by = {k: (o, shp) for k, o, shp in sl}
+    assert float(opt.state[P["sigma"]]["step"]) == 17.0
+    assert torch.equal(opt.state[P["sigma"]]["exp_avg"], m[n - 3:])
+    o, shp = by["W1"]
+    assert torch.equal(opt.state[P["actor_mlp.2.weight"]]["exp_avg"], m[o:o + 64 * 64].view(64, 64))
+    o, shp = by["b3"]
+    assert torch.equal(opt.state[P["mu.bias"]]["exp_avg_sq"], v[o:o + 3])
+    assert float(opt.state[P["critic_mlp.0.weight"]]["exp_avg"].abs().max()) == 0.0     # never trained here: zero moments
     # file round trip through the reference's save / load helpers (torch_ext.save_checkpoint appends '.pth')
     fn = ck.save_checkpoint(os.path.join(tmp_path, "nn", "last_allegro_ep_8"), {"model": ck.actor_state_dict(_flat(ck.mlp_slices(396, 23, has_sigma=True)[1], 9), 396, 23),
                                                                                 "optimizer": osd, "epoch": 8})

@@ -11,7 +11,13 @@ import torch.multiprocessing as mp
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from seqdex_b200.dist_utils import allreduce_mean_, global_moments, shard_envs
+    from seqdex_b200.dist_utils import global_moments, shard_envs
+    from seqdex_b200.ppo import A2CAgent
+
+    import types
+    _agent = types.SimpleNamespace(dist=dist.group.WORLD, world=world)     # the two attributes A2CAgent._allreduce reads; the method is the product's
+    _Agent = lambda: _agent
+    allreduce_mean_ = lambda t: A2CAgent._allreduce(_agent, t, avg=True)
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(20, 32), torch.nn.ELU(), torch.nn.Linear(32, 3))
     x, y = torch.randn(64, 20), torch.randn(64, 3)
@@ -27,7 +33,13 @@ def _worker(rank, world, port, q):
     allreduce_mean_(flat)
     adv = torch.randn(64) * 3 + 1
     mean, std, n = global_moments(adv[start:start + per])
-    ok = (torch.allclose(flat, full, atol=1e-6), abs(float(mean) - float(adv.double().mean())) < 1e-9,
+    cnt = torch.ones(3)
+    A2CAgent._allreduce(_Agent(), cnt, avg=False)        # the sum form (advantage / RunningMeanStd moments)
+    from seqdex_b200.dist_utils import params_digest
+    d = params_digest(flat)
+    ds = [torch.zeros_like(d) for _ in range(world)]
+    dist.all_gather(ds, d)
+    ok = (torch.allclose(flat, full, atol=1e-6), bool((cnt == world).all()), all(torch.equal(ds[0], x) for x in ds), abs(float(mean) - float(adv.double().mean())) < 1e-9,
           abs(float(std) - float(adv.double().std())) < 1e-9, int(n) == 64)
     q.put((rank, ok))
     dist.barrier()

@@ -16,6 +16,8 @@ GENERATORS = {
     "gen_golden_search.py": ["search_post_physics.npz", "search_pre_physics.npz"],
     "gen_golden_dr.py": ["dr_params.npz"],
     "gen_golden_reset.py": ["reset_idx.npz"],
+    "gen_golden_ppo.py": ["ppo_neglogp.npz", "ppo_ac_loss.npz", "ppo_play_steps.npz", "ppo_prepare_dataset.npz", "ppo_schedule_legacy.npz",
+                          "ppo_schedule_standard.npz", "tvalue_trainer.npz"],
 }
 
 pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/dexteroushandenvs"), reason="needs the reference tree (build container only)")

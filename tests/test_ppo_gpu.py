@@ -95,7 +95,8 @@ def test_actor_loss_kernel_vs_torch():
     loss = a_loss.mean() + bc * b_loss.mean()
     loss.backward()
     sig, so = torch.exp(logstd.detach()), torch.exp(old_logstd)
-    kl = (torch.log(sig / so + 1e-5) + (so ** 2 + (old_mu - mu.detach()) ** 2) / (2 * (sig ** 2 + 1e-5)) - 0.5).sum(-1)
+    from oracle import ppo_oracle as PO
+    kl = PO.policy_kl(mu.detach(), sig.expand(M, A), old_mu, so.expand(M, A))      # policy_kl(mu, sigma, old_mu, old_sigma), RGC:1903
     dmu, dls, stats = torch.zeros(M, A, device="cuda"), torch.zeros(A, device="cuda"), torch.zeros(4, device="cuda")
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     _lib.check(L.sdx_ppo_actor_loss(p(mu.detach().contiguous()), p(logstd.detach()), p(actions), p(old_mu), p(old_logstd), p(old_nlp), p(adv), M, A,
