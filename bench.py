@@ -240,6 +240,7 @@ def main():
     from seqdex_b200.env import SdxEnv, make_heap_bank
     from seqdex_b200.scene import Scene
     from seqdex_b200.tasks.block_assembly_grasp_sim import default_tvalue_weights
+    from seqdex_b200.tasks.cfg import scene_from_cfg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,9 +254,8 @@ def main():
     search = args.task == "search"
     # Orient's reset_idx is a script over the WHOLE sim (103 extra contact steps whenever any env resets, OR:1390-1695), so its
     # episodes run in lockstep as in the reference (time-outs only); GraspSim's per-env resets are staggered (see below)
-    scene = (Scene(task="BlockAssemblySearch", episode_length=75, act_moving_average=0.6) if search else
-             Scene(task="BlockAssemblyOrient", episode_length=75, act_moving_average=0.2) if orient else Scene())
     task_name = "BlockAssemblySearch" if search else "BlockAssemblyOrient" if orient else "BlockAssemblyGraspSim"
+    scene = scene_from_cfg(task_name)               # the task's yaml-stated sim / env parameters (contact_offset 0.02 for Orient / Search)
     obs_dim = 186 if orient else 396
     env = SdxEnv(scene, n, local, seed=22 + rank)
     if search:                                      # Search resets from the drop lattice and renders its overview camera
@@ -423,7 +423,15 @@ def main():
                          "note": "state-streaming bound is loose: the kernel is bound by block-barrier waits between ~40 phases per sub-step "
                                  "(45 % of warp stall samples, DESIGN.md section 11), not by HBM"},
             "clocks": sampler.summary(),
-            "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "dropped_max": int(nc[:, 1].max())},
+            "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "table": 1024,
+                                 "dropped_max": int(nc[:, 1].max()),                       # contacts beyond the table AFTER shedding speculative ones
+                                 "shed_level_max": int(nc[:, 2].max()), "envs_shedding_frac": float((nc[:, 2] > 0).mean()),
+                                 "candidate_pairs_dropped_max": int((nc[:, 3] & 0xFFFF).max()),
+                                 "envs_dropping_candidates_frac": float(((nc[:, 3] & 0xFFFF) > 0).mean()),
+                                 "static_pairs_dropped_max": int((nc[:, 3] >> 16).max()),
+                                 "contact_offset": float(scene.c.contact_offset),
+                                 "note": "last step of the run, over all envs of rank 0; shed level 1/2/3 = speculative range halved / quartered / "
+                                         "touching contacts only (csrc/sdx_sim.cuh); statics claim candidate slots first"},
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
         }
         if not args.no_cpu_baseline:

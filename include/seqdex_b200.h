@@ -43,7 +43,8 @@ typedef struct sdx_scene_t {
   int substeps, iters, max_episode_length, sleep_substeps;   /* sleep_substeps: quiet sub-steps before a brick sleeps; 0 = never */
   float dt, gravity_z, contact_offset, friction, baumgarte, slop, max_depen_vel, brick_ang_damp, max_ang_vel,
       max_lin_vel, brick_lin_damp, sleep_energy;   /* sleep_energy: mass-normalised kinetic energy below which a brick is quiet */
-  float base_pos[3], base_quat[4], pad2;
+  float base_pos[3], base_quat[4];
+  float face_margin;   /* a sample point counts as over the reference face up to this far beyond its edge (NOT the speculative contact_offset) */
   int body_parent[SDX_NL];
   unsigned link_anc_mask[SDX_NL];            /* bit j: DoF j moves link */
   float joint_xyz[SDX_ND * 3], joint_quat[SDX_ND * 4], joint_axis[SDX_ND * 3];
@@ -93,7 +94,9 @@ enum {
   SDX_T_TARGET_INIT = 12,/* f32 [N][7]   segmentation_target_init_{pos,rot} (GS:1547-1548)           */
   SDX_T_SUCCESSES = 13, /* f32 [N]                                                                   */
   SDX_T_CONSEC = 14,    /* f32 [1]       consecutive_successes                                       */
-  SDX_T_NCONTACT = 15,  /* i32 [N][2]    contacts in the last sub-step | dropped (overflow)          */
+  SDX_T_NCONTACT = 15,  /* i32 [N][4]    contacts in the last sub-step | contacts beyond SDX_MAX_CONTACTS after shedding | most shedding of
+                           speculative contacts any sub-step of the step needed (0 none .. 3 touching contacts only) | candidate pairs
+                           beyond the per-owner cap (low 16 bits; of those, pairs against statics: high 16 bits, always 0) */
   SDX_T_ROOT = 16,      /* f32 [N*142][13] actor_root_state_tensor, filled by sdx_refresh            */
   SDX_T_RB = 17,        /* f32 [N*165][13] rigid_body_state_tensor, filled by sdx_refresh            */
   SDX_T_DOF_STATE = 18, /* f32 [N*23][2]   dof_state_tensor, filled by sdx_refresh                    */

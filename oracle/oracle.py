@@ -93,7 +93,7 @@ class OracleEnv:
         self.target_init = np.zeros((n, 7), np.float32)
         self.successes = np.zeros(n, np.float32)
         self.consec = np.zeros(1, np.float32)
-        self.ncontact = np.zeros((n, 2), np.int32)
+        self.ncontact = np.zeros((n, 4), np.int32)   # contacts | beyond the table | shed level | candidate pairs beyond KC (hi 16: vs statics)
         self.episode = np.zeros(n, np.int32)
         self.condump = np.zeros((n, MAXC, 8), np.float32)
         self.ws = np.zeros((n, 2, MAXC, 4), np.float32)

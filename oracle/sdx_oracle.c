@@ -48,7 +48,8 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   int substeps, iters, max_episode_length, sleep_substeps;
   float dt, gravity_z, contact_offset, friction, baumgarte, slop, max_depen_vel, brick_ang_damp, max_ang_vel,
       max_lin_vel, brick_lin_damp, sleep_energy;
-  float base_pos[3], base_quat[4], pad2;
+  float base_pos[3], base_quat[4];
+  float face_margin;   /* a sample point counts as over the reference face up to this far beyond its edge (NOT the speculative contact_offset) */
   int body_parent[SDX_NL];
   unsigned link_anc_mask[SDX_NL];
   float joint_xyz[SDX_ND * 3], joint_quat[SDX_ND * 4], joint_axis[SDX_ND * 3];
@@ -239,7 +240,8 @@ typedef struct {
   v3 linkF[SDX_NL], linkM[SDX_NL];
   uint32_t ckey[SDX_MAX_CONTACTS];
   unsigned char asleep[NB], hot[NB], touch[NB];   /* sleeping (see sim_env): touch bit0 = robot, bit1 = hot brick */
-  unsigned char built_asleep[NB]; int cand_dropped; /* candidate lists are kept over the sub-steps of a step (see sim_env 3.) */
+  unsigned char built_asleep[NB]; int cand_dropped, cand_dropped_static; /* candidate lists are kept over the sub-steps of a step (see sim_env 3.) */
+  int shed_level;   /* most speculative-contact shedding any sub-step of the step needed (0 = none) */
 } work_t;
 
 /* W = R diag(1/I) R^T (symmetric, six numbers), formed ONCE per sub-step and brick -- the kernel keeps it as two 16-byte
@@ -303,7 +305,8 @@ static float body_k(const sdx_scene_t* S, const work_t* W, int body, v3 wpt, v3 
 
 /* one env, one control step = `substeps` sub-steps (gym.simulate, BT:140; yaml sim: substeps 2,
  * 16 position iterations).  brick: [13][72]; dof: [3][24]; link_out: [24][13]; jac7: [6][7];
- * netf: [24][3]; ncontact: [2]; condump: [MAXC][8] or NULL */
+ * netf: [24][3]; ncontact: [4] = contacts of the last sub-step | contacts beyond the table (after shedding) | shed level | candidate
+ * pairs beyond KC (low 16 bits; of which against statics: high 16 bits); condump: [MAXC][8] or NULL */
 /* ws: [2][MAXC][4] impulse cache of this env (key bits, f.xyz), wsn: [2] entry counts, ws_cur: buffer holding the latest list
  *
  * SLEEPING (what PhysX does to resting actors; its defaults apply to the reference because the yaml sets none):
@@ -335,6 +338,8 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
   const int n_owner = NB + nrs, n_target = NB + nrs + nst;
   const float h = S->dt / (float)S->substeps;
   const float margin = S->contact_offset;
+  const float fmargin = S->face_margin;   /* how far beyond the edge of the reference face a sample point still counts as over it */
+  W->shed_level = 0;
   for (int b = 0; b < NB; ++b) {
     W->bx[b] = V3(brick[0 * NB + b], brick[1 * NB + b], brick[2 * NB + b]);
     W->bq[b].x = brick[3 * NB + b]; W->bq[b].y = brick[4 * NB + b]; W->bq[b].z = brick[5 * NB + b]; W->bq[b].w = brick[6 * NB + b];
@@ -429,9 +434,13 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       const int left = g_broad_reuse ? S->substeps - sub : 1;
       const float infl = (float)left, slack = (float)(left - 1) * ((h * h) * fabsf(S->gravity_z));
       for (int b = 0; b < NB; ++b) W->built_asleep[b] = W->asleep[b];
-      W->cand_dropped = 0;
+      W->cand_dropped = 0; W->cand_dropped_static = 0;
+      /* per owner: dynamic targets (bricks, then robot boxes) and statics are swept separately; the statics claim their slots
+       * FIRST (a brick must never lose its floor / wall pair to a crowd of neighbours), the dynamic targets fill what is left in
+       * ascending order; the list itself stays ascending: dynamic part, then statics */
       for (int a = 0; a < n_owner; ++a) {
-        int k = 0;
+        unsigned char dyn[KC], sta[KC];
+        int nd = 0, nd_all = 0, ns = 0, ns_all = 0;
         if (a < NB && a >= nbr) { W->ncand[a] = 0; continue; }
         for (int t = 0; t < n_target; ++t) {
           if (t == a) continue;
@@ -442,9 +451,16 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           float m = margin + infl * (W->spd[a] + W->spd[t]) + slack;
           int hit = fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
                     fabsf(d.z) <= W->sa[a].z + W->sa[t].z + m;
-          if (hit) { if (k < KC) W->cand[a][k++] = (unsigned char)t; else W->cand_dropped++; }
+          if (!hit) continue;
+          if (t >= NB + nrs) { if (ns < KC) sta[ns++] = (unsigned char)t; ns_all++; }
+          else { if (nd < KC) dyn[nd++] = (unsigned char)t; nd_all++; }
         }
-        W->ncand[a] = k;
+        const int kd = nd_all < KC - ns ? nd_all : KC - ns;
+        for (int i = 0; i < kd; ++i) W->cand[a][i] = dyn[i];
+        for (int i = 0; i < ns; ++i) W->cand[a][kd + i] = sta[i];
+        W->ncand[a] = kd + ns;
+        W->cand_dropped += (nd_all - kd) + (ns_all - ns);
+        W->cand_dropped_static += ns_all - ns;
       }
     }
     if (g_reuse_audit) {   /* test hook: what would a fresh broad phase of THIS sub-step list, and is it in the lists in use? */
@@ -468,13 +484,18 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     /* 4. narrow phase, per ordered pair (owner a, target t): reference face of t = its axis of least
      *    overlap with a (SAT over t's three face axes); a's sample points that lie over that face and
      *    within the speculative margin below/above it become contacts.  Order: owner, candidate, point. */
-    W->ncon = 0; W->ndropped = W->cand_dropped;
+    /* SHEDDING: contacts with a positive gap are speculative; if the table would overflow, the speculative range is halved (twice),
+     * then dropped altogether -- the contacts that go first are the ones that cannot act in this sub-step anyway -- before any
+     * touching contact is lost.  Level 0 = the full range m, 1 = m / 2, 2 = m / 4, 3 = touching contacts only. */
+    int level = 0; float gs = 1.0f;
+  regenerate:
+    W->ncon = 0; W->ndropped = 0;
     for (int a = 0; a < n_owner; ++a) {
       int npts = (a < NB && W->sh[a].x > 0.04f) ? 12 : 8; /* long bricks add 4 mid-edge points */
       for (int ci = 0; ci < W->ncand[a]; ++ci) {
         int t = W->cand[a][ci];
         if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue; /* kept list, both asleep by now */
-        float m = margin + W->spd[a] + W->spd[t];
+        float m = (margin + W->spd[a] + W->spd[t]) * gs;
         v3 lc = mtmul(W->sR[t], vsub(W->sc[a], W->sc[t]));
         float C[9]; /* C = R_t^T R_a */
         for (int r = 0; r < 3; ++r)
@@ -501,8 +522,8 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           float lk = k == 0 ? l.x : (k == 1 ? l.y : l.z);
           float depth = htk - sgf * lk;
           if (!(depth > -m)) continue;
-          int inface = (k == 0 || fabsf(l.x) <= ht.x + margin) && (k == 1 || fabsf(l.y) <= ht.y + margin) &&
-                       (k == 2 || fabsf(l.z) <= ht.z + margin);
+          int inface = (k == 0 || fabsf(l.x) <= ht.x + fmargin) && (k == 1 || fabsf(l.y) <= ht.y + fmargin) &&
+                       (k == 2 || fabsf(l.z) <= ht.z + fmargin);
           if (!inface) continue;
           if (W->ncon >= SDX_MAX_CONTACTS) { W->ndropped++; continue; }
           contact_t* c = &W->con[W->ncon++];
@@ -532,6 +553,8 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         }
       }
     }
+    if (W->ndropped > 0 && level < 3) { ++level; gs = level == 3 ? 0.0f : gs * 0.5f; goto regenerate; }
+    if (level > W->shed_level) W->shed_level = level;
     /* 5. incidence + mass-splitting counts.  Contacts are generated owner-major, so the contacts a body OWNS
      *    are one contiguous range; the contacts in which it is the TARGET are listed in ascending order. */
     for (int b = 0; b < NBODY; ++b) { W->astart[b] = 0; W->aend[b] = 0; W->nb[b] = 0; }
@@ -691,7 +714,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     jac7[0 * 7 + j] = lin.x; jac7[1 * 7 + j] = lin.y; jac7[2 * 7 + j] = lin.z;
     jac7[3 * 7 + j] = W->K.ja[j].x; jac7[4 * 7 + j] = W->K.ja[j].y; jac7[5 * 7 + j] = W->K.ja[j].z;
   }
-  ncontact[0] = W->ncon; ncontact[1] = W->ndropped;
+  ncontact[0] = W->ncon; ncontact[1] = W->ndropped; ncontact[2] = W->shed_level; ncontact[3] = W->cand_dropped | (W->cand_dropped_static << 16);
 }
 
 typedef struct {
@@ -703,7 +726,7 @@ static void* sim_worker(void* arg) {
   work_t* W = (work_t*)malloc(sizeof(work_t));
   for (int e = J->tid; e < J->n; e += J->nthreads)
     sim_env(J->S, J->brick + (size_t)e * 13 * NB, J->dof + (size_t)e * 72, J->link + (size_t)e * SDX_NL * 13,
-            J->jac7 + (size_t)e * 42, J->netf + (size_t)e * SDX_NL * 3, J->ncontact + 2 * e,
+            J->jac7 + (size_t)e * 42, J->netf + (size_t)e * SDX_NL * 3, J->ncontact + 4 * e,
             J->condump ? J->condump + (size_t)e * SDX_MAX_CONTACTS * 8 : 0, J->ws + (size_t)e * 2 * SDX_MAX_CONTACTS * 4, J->wsn + 2 * e,
             J->ws_cur, J->slp + (size_t)e * NB, W);
   free(W);

@@ -75,7 +75,7 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
     case SDX_T_RESET: case SDX_T_PROGRESS: s[0] = n; dt = 1; break;
     case SDX_T_TARGET_INIT: s[0] = n; s[1] = 7; nd = 2; break;
     case SDX_T_CONSEC: s[0] = 1; break;
-    case SDX_T_NCONTACT: s[0] = n; s[1] = 2; nd = 2; dt = 2; break;
+    case SDX_T_NCONTACT: s[0] = n; s[1] = 4; nd = 2; dt = 2; break;
     case SDX_T_ROOT: s[0] = n * SDX_ACTORS_PER_ENV; s[1] = 13; nd = 2; break;
     case SDX_T_RB: s[0] = n * SDX_RB_PER_ENV; s[1] = 13; nd = 2; break;
     case SDX_T_DOF_STATE: s[0] = n * SDX_ND; s[1] = 2; nd = 2; break;

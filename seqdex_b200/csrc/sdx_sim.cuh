@@ -111,7 +111,8 @@ struct SimSmem {
   int astart[NBODY], aend[NBODY], boff[NBODY + 1], bcur[NBODY];
   int poff[NOWN + 1];
   int scan[SIM_THREADS];
-  int ncon, ndropped, ndrop_cand;      // ndrop_cand: candidates beyond KC when the lists were last built
+  int ncon, ndropped;                  // contacts of the sub-step | contacts beyond MAXC (after shedding the speculative ones)
+  int ndrop_cand, ndrop_static;        // candidate pairs beyond KC when the lists were last built | of those, pairs against statics (statics claim their slots first: 0)
   int nact;                            // bricks phase B has to visit: awake AND touched by at least one contact (irec, ascending)
   unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
   // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
@@ -122,8 +123,8 @@ struct SimSmem {
   float4 cf4[MAXC];   // total impulse f.xyz | unused          (also scratch: candidate overflow lists, pair tables)
 };
 
-static_assert(NOWN * KC * 2 <= 8192 && 8192 + NOWN * KC * 2 <= MAXC * 16 && NOWN * KC + NOWN * 4 <= MAXC * 16,
-              "the pair tables / candidate overflow lists are laid out inside the impulse array (cf4)");
+static_assert(NOWN * KC * 2 <= 8192 && 8192 + NOWN * KC * 2 <= MAXC * 16 && NOWN * KC + NOWN * 16 + NOWN * KSTAT <= MAXC * 16 && KSTAT <= KC,
+              "the pair tables / candidate scratch lists are laid out inside the impulse array (cf4)");
 
 // exclusive prefix sum of arr[0..n) (n <= 256) by ONE warp, in place; returns the total to every lane
 __device__ SIM_SCAN_INLINE int warp_excl_scan(int* arr, int n, int lane) {
@@ -386,6 +387,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   const int substeps = S->substeps, iters = S->iters;
   const float h = S->dt / (float)substeps;
   const float margin = S->contact_offset;
+  const float fmargin = S->face_margin;          // in-face tolerance (NOT the speculative range)
+  int shed_max = 0;                              // block-uniform: most shedding any sub-step needed
   float* gbrick = brick + (size_t)e * 13 * NB;
   float* gdof = dof + (size_t)e * 72;
 #if SIM_GLOBAL_CONTACTS
@@ -539,37 +542,39 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       const v3 hs = ld3(M.sh[t]);
       M.sab[t] = make_float4(hs.x, hs.y, hs.z, 0.0f);
     }
-    if (tid == 0) { M.ndropped = 0; }
     // The candidate lists are built in the FIRST sub-step of a step for ALL its sub-steps (travel bounds scaled by the number of
     // sub-steps left, plus the speed gravity adds in between) and rebuilt later only if a brick that was asleep when they were
     // built has been woken since: its pairs with sleeping bricks and statics were filtered (oracle: sim_env 3.)
     const int rebuild = __syncthreads_or(sub == 0 || (tid < NB && built_asleep && !asleep));
     PMARK(2);
-    // 5. broad phase: TWO threads per owner shape (thread tid: owner tid & 127, target-range half tid >> 7); the second
-    //    half's hits go to a scratch list (in the idle impulse array) and are appended in target order, so the candidate
-    //    lists -- including what overflows KC -- are the ones a single ascending sweep produces
+    // 5. broad phase: TWO threads per owner shape (thread tid: owner tid & 127, target-range half tid >> 7).  Dynamic targets
+    //    (bricks, robot boxes) and statics are listed separately; at the merge the STATICS CLAIM THEIR SLOTS FIRST -- a brick must
+    //    never lose its floor / wall pair to a crowd of neighbours -- and the dynamic targets fill what is left in ascending order.
+    //    The list stays ascending (dynamic part, then statics) and equals what the oracle's single sweep produces.
     if (rebuild) {
       const int left = substeps - sub;
       const float infl = (float)left, slack = (float)(left - 1) * ((h * h) * fabsf(S->gravity_z));
       built_asleep = asleep;
-      unsigned char* tmpc = cf_bytes;                                       // [NOWN][KC]
-      int* tmpn = reinterpret_cast<int*>(cf_bytes + NOWN * KC);             // [NOWN]
+      unsigned char* tmpc = cf_bytes;                                       // [NOWN][KC]    dynamic hits of the second half
+      int* tmpn = reinterpret_cast<int*>(cf_bytes + NOWN * KC);             // [NOWN][4]     all dynamic hits of half 0 | half 1 | statics kept | statics seen
+      unsigned char* tmps = cf_bytes + NOWN * KC + NOWN * 16;               // [NOWN][KSTAT] static hits
+      if (tid == 0) { M.ndrop_cand = 0; M.ndrop_static = 0; }
       const int a = tid & 127, half = tid >> 7;
       if (a < n_owner) {
-        int k = 0, dropped = 0;
+        int k = 0, kall = 0, ks = 0, ksall = 0;
         if (!(a < NB && a >= nbr)) {
           const v3 ca = ld3(M.sc[a]);
           const float4 A4 = M.sab[a];
           const bool a_sl = a < NB && (M.sflag[a] & 1);
-          const int tmid = n_target >> 1;
+          const int tmid = n_target >> 1;                        // < NB + nrs: the statics all fall into the second half
           const int tlo = half ? tmid : 0, thi = half ? n_target : tmid;
           unsigned char* dst = half ? tmpc + a * KC : M.cand[a];
-          auto test = [&](int t) {
+          unsigned char* sdst = tmps + a * KSTAT;
+          auto hit = [&](int t) {
             const v3 d = vsub(ca, ld3(M.sc[t]));
             const float4 T4 = M.sab[t];
             const float m = margin + infl * (A4.w + T4.w) + slack;
-            const bool hit = fabsf(d.x) <= A4.x + T4.x + m && fabsf(d.y) <= A4.y + T4.y + m && fabsf(d.z) <= A4.z + T4.z + m;
-            if (hit) { if (k < KC) dst[k++] = (unsigned char)t; else dropped++; }
+            return fabsf(d.x) <= A4.x + T4.x + m && fabsf(d.y) <= A4.y + T4.y + m && fabsf(d.z) <= A4.z + T4.z + m;
           };
           // the target index space is bricks [0, nbr) | robot shapes [NB, NB+nrs) | statics [NB+nrs, n_target): one loop per
           // class with the class-level filters hoisted (same ascending order as one sweep over t)
@@ -577,27 +582,33 @@ SIM_BROAD_UNROLL
           for (int t = max(tlo, 0); t < min(thi, nbr); ++t) {
             if (t == a) continue;
             if (a_sl && (M.sflag[t] & 1)) continue;              // neither box can move
-            test(t);
+            if (hit(t)) { if (k < KC) dst[k++] = (unsigned char)t; kall++; }
           }
           if (a < NB) {                                          // robot-robot pairs are filtered (GS:906)
 SIM_BROAD_UNROLL
-            for (int t = max(tlo, NB); t < min(thi, NB + nrs); ++t) test(t);
+            for (int t = max(tlo, NB); t < min(thi, NB + nrs); ++t)
+              if (hit(t)) { if (k < KC) dst[k++] = (unsigned char)t; kall++; }
           }
           if (!a_sl) {                                           // a sleeping brick against a static: neither box can move
 SIM_BROAD_UNROLL
-            for (int t = max(tlo, NB + nrs); t < thi; ++t) test(t);
+            for (int t = max(tlo, NB + nrs); t < thi; ++t)
+              if (hit(t)) { if (ks < KSTAT) sdst[ks++] = (unsigned char)t; ksall++; }
           }
         }
-        if (half) tmpn[a] = k; else M.ncand[a] = k;
-        if (dropped) atomicAdd(&M.ndropped, dropped);
+        if (half) { tmpn[4 * a + 1] = kall; tmpn[4 * a + 2] = ks; tmpn[4 * a + 3] = ksall; } else tmpn[4 * a] = kall;
       }
       __syncthreads();
       if (tid < n_owner) {
-        int k = M.ncand[tid], dropped = 0;
-        const int n1 = tmpn[tid];
-        for (int i = 0; i < n1; ++i) { if (k < KC) M.cand[tid][k++] = tmpc[tid * KC + i]; else dropped++; }
-        M.ncand[tid] = k;
-        if (dropped) atomicAdd(&M.ndropped, dropped);
+        const int nd0_all = tmpn[4 * tid], nd1_all = tmpn[4 * tid + 1], ns = tmpn[4 * tid + 2], ns_all = tmpn[4 * tid + 3];
+        const int nd_all = nd0_all + nd1_all;
+        const int kd = min(nd_all, KC - ns);
+        const int nd0 = min(nd0_all, KC);
+        for (int i = nd0; i < kd; ++i) M.cand[tid][i] = tmpc[tid * KC + (i - nd0)];
+        for (int i = 0; i < ns; ++i) M.cand[tid][kd + i] = tmps[tid * KSTAT + i];
+        M.ncand[tid] = kd + ns;
+        const int dropped = (nd_all - kd) + (ns_all - ns);
+        if (dropped) atomicAdd(&M.ndrop_cand, dropped);
+        if (ns_all > ns) atomicAdd(&M.ndrop_static, ns_all - ns);
       }
       __syncthreads();
       PMARK(3);
@@ -605,11 +616,10 @@ SIM_BROAD_UNROLL
         for (int a = tid; a < n_owner; a += 32) M.poff[a] = M.ncand[a];
         __syncwarp();
         int tot = warp_excl_scan(M.poff, n_owner, tid);
-        if (tid == 0) { M.poff[n_owner] = tot; M.ndrop_cand = M.ndropped; }
+        if (tid == 0) M.poff[n_owner] = tot;
       }
       __syncthreads();
     } else {
-      if (tid == 0) M.ndropped = M.ndrop_cand;                 // lists, pair offsets and their drop count stand
       PMARK(3);
     }
     PMARK(4);
@@ -620,37 +630,50 @@ SIM_BROAD_UNROLL
     const int p0 = tid * PP, p1 = min(npairs, p0 + PP);
     unsigned short* pmask = reinterpret_cast<unsigned short*>(cf_bytes);          // [npairs] <= 3328 * 2 B < 8 KB
     unsigned short* pstart = reinterpret_cast<unsigned short*>(cf_bytes + 8192);  // [npairs]
-    int mycount = 0;
-    {
+    // SHEDDING: contacts with a positive gap are speculative.  If the table would overflow, the speculative range is halved
+    // (twice) and then dropped altogether -- the contacts that go first are those that cannot act in this sub-step anyway --
+    // before a touching contact is lost (oracle: sim_env 4.).  Block-uniform loop; level 0 in all but the most crowded sub-steps.
+    int mycount, incl, total, level = 0;
+    float gs = 1.0f;
+    for (;;) {
+      mycount = 0;
       int a = 0;
       for (int i = p0; i < p1; ++i) {
         while (M.poff[a + 1] <= i) ++a;
         int t = M.cand[a][i - M.poff[a]];
-        float m = margin + M.sab[a].w + M.sab[t].w;
+        float m = (margin + M.sab[a].w + M.sab[t].w) * gs;
         unsigned short mk = 0;
         PairGeom G;
         const bool dead = !rebuild && a < NB && (M.sflag[a] & 1) && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)));   // kept list, both asleep by now
         if (!dead && pair_geom(M, a, t, m, G, t >= NB + nrs)) {
           int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
-          for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, margin, &d)) mk |= (unsigned short)(1u << p); }
+          for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, fmargin, &d)) mk |= (unsigned short)(1u << p); }
         }
         pmask[i] = mk;
         mycount += __popc((unsigned)mk);
       }
-    }
-    // running contact offsets: warp-level inclusive scan of the per-thread counts + the totals of the warps before (one barrier)
-    int incl = mycount;
+      // running contact offsets: warp-level inclusive scan of the per-thread counts + the totals of the warps before (one barrier)
+      incl = mycount;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
-    if ((tid & 31) == 31) M.scan[tid >> 5] = incl;
-    if (tid < NBODY) { M.astart[tid] = 0; M.aend[tid] = 0; M.nb[tid] = 0; }
-    __syncthreads();
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
+      if ((tid & 31) == 31) M.scan[tid >> 5] = incl;
+      if (tid < NBODY) { M.astart[tid] = 0; M.aend[tid] = 0; M.nb[tid] = 0; }
+      __syncthreads();
+      total = 0;
+#pragma unroll
+      for (int w = 0; w < SIM_THREADS / 32; ++w) total += M.scan[w];
+      if (total <= MAXC || level == 3) break;
+      ++level;
+      gs = level == 3 ? 0.0f : gs * 0.5f;
+      __syncthreads();                                           // everyone has read the warp totals before they are rewritten
+    }
+    shed_max = max(shed_max, level);
     PMARK(5);
     {
-      int run = incl - mycount, total = 0;
+      int run = incl - mycount;
 #pragma unroll
-      for (int w = 0; w < SIM_THREADS / 32; ++w) { const int v = M.scan[w]; if (w < (tid >> 5)) run += v; total += v; }
-      if (tid == 0) { M.ncon = total < MAXC ? total : MAXC; if (total > MAXC) atomicAdd(&M.ndropped, total - MAXC); }
+      for (int w = 0; w < SIM_THREADS / 32; ++w) { const int v = M.scan[w]; if (w < (tid >> 5)) run += v; }
+      if (tid == 0) { M.ncon = total < MAXC ? total : MAXC; M.ndropped = total > MAXC ? total - MAXC : 0; }
       for (int i = p0; i < p1; ++i) { pstart[i] = (unsigned short)min(run, 65535); run += __popc((unsigned)pmask[i]); }
     }
     __syncthreads();
@@ -682,11 +705,11 @@ SIM_BROAD_UNROLL
         int lo = 0, hi = n_owner - 1;                  // owner a with poff[a] <= i < poff[a+1]
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (M.poff[mid] <= i) lo = mid; else hi = mid - 1; }
         const int a = lo, t = M.cand[a][i - M.poff[a]];
-        float m = margin + M.sab[a].w + M.sab[t].w;
+        float m = (margin + M.sab[a].w + M.sab[t].w) * gs;
         PairGeom G;
         pair_geom(M, a, t, m, G, t >= NB + nrs);
         float depth;
-        point_hit(G, p, m, margin, &depth);
+        point_hit(G, p, m, fmargin, &depth);
         v3 wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
         const uint32_t wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
         float bias = 0.0f;
@@ -1009,7 +1032,7 @@ SIM_BROAD_UNROLL
     J[0 * 7 + j] = lin.x; J[1 * 7 + j] = lin.y; J[2 * 7 + j] = lin.z;
     J[3 * 7 + j] = aj.x; J[4 * 7 + j] = aj.y; J[5 * 7 + j] = aj.z;
   }
-  if (tid == 64) { ncontact[2 * e] = M.ncon; ncontact[2 * e + 1] = M.ndropped; }
+  if (tid == 64) { ncontact[4 * e] = M.ncon; ncontact[4 * e + 1] = M.ndropped; ncontact[4 * e + 2] = shed_max; ncontact[4 * e + 3] = M.ndrop_cand | (M.ndrop_static << 16); }
   if (tid < NB) slp[(size_t)e * NB + tid] = (unsigned char)slpc;
   if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }

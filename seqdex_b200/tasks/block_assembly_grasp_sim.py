@@ -9,14 +9,10 @@ import torch
 from ..env import SdxEnv, make_heap_bank
 from ..randomization import RandomizedTaskMixin
 from ..scene import Scene
+from .cfg import TASK_CFG, scene_from_cfg
 
 
-DEFAULT_CFG = {   # cfg/allegro_hand_block_assembly_grasp_sim.yaml (the keys this task reads)
-    "env": {"numEnvs": 2048, "episodeLength": 150, "actionsMovingAverage": 1.0, "controlFrequencyInv": 1,
-            "observationType": "partial_contact", "asymmetric_observations": True, "averFactor": 0.1},
-    "sim": {"substeps": 2, "physx": {"num_position_iterations": 16, "contact_offset": 0.002, "max_depenetration_velocity": 1000.0}},
-    "task": {"randomize": False},
-}
+DEFAULT_CFG = TASK_CFG["BlockAssemblyGraspSim"]   # cfg/allegro_hand_block_assembly_grasp_sim.yaml: env scalars + the whole sim block (tasks/cfg.py)
 
 
 class BlockAssemblyGraspSim(RandomizedTaskMixin):
@@ -39,12 +35,7 @@ class BlockAssemblyGraspSim(RandomizedTaskMixin):
         self.headless = headless
         self.one_frame_num_obs, self.one_frame_num_states = 132, 188
         self.num_obs, self.num_states, self.num_actions = 132 * 3, 188 * 3, 23      # GS:209-211
-        self.scene = Scene(task="BlockAssemblyGraspSim", seed=seed, dt=1.0 / 60.0, substeps=int(sim_cfg.get("substeps", 2)),
-                           iters=int(physx.get("num_position_iterations", 16)),
-                           contact_offset=float(physx.get("contact_offset", 0.002)),
-                           max_depen_vel=float(physx.get("max_depenetration_velocity", 1000.0)),
-                           episode_length=self.max_episode_length,
-                           act_moving_average=float(env_cfg.get("actionsMovingAverage", 1.0)))
+        self.scene = scene_from_cfg("BlockAssemblyGraspSim", cfg, seed)
         self.env = SdxEnv(self.scene, self.num_envs, device_id, seed)
         if heap_bank is None:   # GS:412-413 loads an unshipped pickle; we synthesise the same kind of data
             heap_bank = make_heap_bank(self.scene, bank_per_type, device_id, seed=seed)

@@ -9,14 +9,10 @@ import torch
 from ..env import SdxEnv, make_heap_bank
 from ..randomization import RandomizedTaskMixin
 from ..scene import Scene
+from .cfg import TASK_CFG, scene_from_cfg
 from .block_assembly_grasp_sim import default_tvalue_weights
 
-DEFAULT_CFG = {   # cfg/allegro_hand_block_assembly_orient.yaml (the keys this task reads)
-    "env": {"numEnvs": 2048, "episodeLength": 75, "actionsMovingAverage": 0.2, "controlFrequencyInv": 1,
-            "observationType": "partial_contact", "asymmetric_observations": True, "averFactor": 0.1},
-    "sim": {"substeps": 2, "physx": {"num_position_iterations": 16, "contact_offset": 0.002, "max_depenetration_velocity": 1000.0}},
-    "task": {"randomize": False},
-}
+DEFAULT_CFG = TASK_CFG["BlockAssemblyOrient"]   # cfg/allegro_hand_block_assembly_orient.yaml: env scalars + the whole sim block (tasks/cfg.py)
 
 
 class BlockAssemblyOrient(RandomizedTaskMixin):
@@ -40,12 +36,7 @@ class BlockAssemblyOrient(RandomizedTaskMixin):
         self.headless = headless
         self.one_frame_num_obs, self.one_frame_num_states = 62, 188
         self.num_obs, self.num_states, self.num_actions = 62 * 3, 188 * 3, 23       # OR:206-208
-        self.scene = Scene(task="BlockAssemblyOrient", seed=seed, dt=1.0 / 60.0, substeps=int(sim_cfg.get("substeps", 2)),
-                           iters=int(physx.get("num_position_iterations", 16)),
-                           contact_offset=float(physx.get("contact_offset", 0.002)),
-                           max_depen_vel=float(physx.get("max_depenetration_velocity", 1000.0)),
-                           episode_length=self.max_episode_length,
-                           act_moving_average=float(env_cfg.get("actionsMovingAverage", 0.2)))
+        self.scene = scene_from_cfg("BlockAssemblyOrient", cfg, seed)
         self.env = SdxEnv(self.scene, self.num_envs, device_id, seed)
         if heap_bank is None:   # OR:419-420 loads the pickle Search writes (unshipped); we synthesise the same kind of data
             heap_bank = make_heap_bank(self.scene, bank_per_type, device_id, seed=seed)

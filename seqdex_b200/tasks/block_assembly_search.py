@@ -12,13 +12,9 @@ from ..camera import SEARCH_CAMERA, look_at
 from ..env import SdxEnv
 from ..randomization import RandomizedTaskMixin
 from ..scene import Scene
+from .cfg import TASK_CFG, scene_from_cfg
 
-DEFAULT_CFG = {   # cfg/allegro_hand_block_assembly_search.yaml (the keys this task reads)
-    "env": {"numEnvs": 2048, "episodeLength": 75, "handResetStep": 45, "actionsMovingAverage": 0.6, "controlFrequencyInv": 1,
-            "observationType": "partial_contact", "asymmetric_observations": True, "averFactor": 0.1, "enable_camera_sensors": True},
-    "sim": {"substeps": 2, "physx": {"num_position_iterations": 16, "contact_offset": 0.002, "max_depenetration_velocity": 1000.0}},
-    "task": {"randomize": False},
-}
+DEFAULT_CFG = TASK_CFG["BlockAssemblySearch"]   # cfg/allegro_hand_block_assembly_search.yaml: env scalars + the whole sim block (tasks/cfg.py)
 
 
 class BlockAssemblySearch(RandomizedTaskMixin):
@@ -41,12 +37,7 @@ class BlockAssemblySearch(RandomizedTaskMixin):
         self.headless = headless
         self.one_frame_num_obs, self.one_frame_num_states = 62, 188
         self.num_obs, self.num_states, self.num_actions = 62 * 3, 188 * 3, 23       # SE:168-175
-        self.scene = Scene(task="BlockAssemblySearch", seed=seed, dt=1.0 / 60.0, substeps=int(sim_cfg.get("substeps", 2)),
-                           iters=int(physx.get("num_position_iterations", 16)),
-                           contact_offset=float(physx.get("contact_offset", 0.002)),
-                           max_depen_vel=float(physx.get("max_depenetration_velocity", 1000.0)),
-                           episode_length=self.max_episode_length,
-                           act_moving_average=float(env_cfg.get("actionsMovingAverage", 0.6)))
+        self.scene = scene_from_cfg("BlockAssemblySearch", cfg, seed)
         self.env = SdxEnv(self.scene, self.num_envs, device_id, seed)
         self.camera = look_at(**SEARCH_CAMERA)                                       # SE:755-758, 875
         self.env.set_camera(self.camera)

@@ -67,10 +67,9 @@ def test_orient_and_search_batch_invariance_across_scripted_resets():
     """4096 envs vs 32 envs through the first scripted reset and a few steps (Orient: 53 contact steps inside reset_idx; Search: 60 +
     the ray-cast render): the first 32 envs agree bit for bit"""
     from seqdex_b200.camera import SEARCH_CAMERA, look_at
-    from seqdex_b200.scene import Scene
-    for task, kw, extra in (("BlockAssemblyOrient", dict(episode_length=75, act_moving_average=0.2), ()),
-                            ("BlockAssemblySearch", dict(episode_length=75, act_moving_average=0.6), ("SEG", "EMERGENCE", "TVOBS"))):
-        sc = Scene(task=task, **kw)
+    from seqdex_b200.tasks.cfg import scene_from_cfg
+    for task, extra in (("BlockAssemblyOrient", ()), ("BlockAssemblySearch", ("SEG", "EMERGENCE", "TVOBS"))):
+        sc = scene_from_cfg(task)                       # yaml-stated parameters: contact_offset 0.02
         hook = (lambda g: g.set_camera(look_at(**SEARCH_CAMERA))) if task.endswith("Search") else None
         bank = None if task.endswith("Search") else lattice_bank(sc, 2)
         outs = []

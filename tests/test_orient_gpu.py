@@ -15,8 +15,8 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.fixture(scope="module")
 def oscene():
-    from seqdex_b200.scene import Scene
-    return Scene(task="BlockAssemblyOrient", episode_length=75, act_moving_average=0.2)
+    from seqdex_b200.tasks.cfg import scene_from_cfg
+    return scene_from_cfg("BlockAssemblyOrient")   # the yaml-stated sim / env parameters (contact_offset 0.02)
 
 
 def _cmp(name, a, b):

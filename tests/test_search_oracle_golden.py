@@ -14,8 +14,8 @@ G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 @pytest.fixture(scope="module")
 def sscene():
-    from seqdex_b200.scene import Scene
-    return Scene(task="BlockAssemblySearch", episode_length=75, act_moving_average=0.6)
+    from seqdex_b200.tasks.cfg import scene_from_cfg
+    return scene_from_cfg("BlockAssemblySearch")   # the yaml-stated sim / env parameters (contact_offset 0.02)
 
 
 def _load(name):
