@@ -263,6 +263,13 @@ static inline v3 brick_Iinv_mul(const work_t* W, int b, v3 u) {
             fmaf(w[5], u.z, fmaf(w[4], u.y, w[2] * u.x)));
 }
 
+/* lanes that share a brick's incidences in phase B: the smallest power of two that leaves each lane at most 4 (capped at a warp) */
+static inline int phaseb_lanes(int ninc) {
+  int L = 1;
+  while (L < 32 && 4 * L < ninc) L <<= 1;
+  return L;
+}
+
 static void link_twists(const sdx_scene_t* S, work_t* W) {
   for (int L = 0; L < SDX_NL; ++L) {
     v3 w = V3(0, 0, 0), v = V3(0, 0, 0);
@@ -612,11 +619,15 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         f = vmad(t2, l2, vmad(t1, l1, vscale(n, ln)));
         c->f[0] = f.x; c->f[1] = f.y; c->f[2] = f.z;
       }
-      for (int b = 0; b < NBODY; ++b) { /* phase B: one body each; TWO interleaved partial sums (even / odd incidences), combined 0+1 */
+      for (int b = 0; b < NBODY; ++b) { /* phase B: one body each.  The incidences of a body are dealt round-robin to L partial sums
+                                         * (L = phaseb_lanes: a power of two, so that no partial holds more than 4 of them up to 128; links: 2)
+                                         * which are then combined by a butterfly: p[k] += p[k ^ o] for o = 1, 2, 4 ...  -- the order a group
+                                         * of L lanes produces with xor-shuffles, whatever lanes of whatever warp the group sits on */
         int na = W->aend[b] - W->astart[b], nbl = W->boff[b + 1] - W->boff[b];
         if (b < NB && (W->asleep[b] || na + nbl == 0)) continue; /* asleep: stays at rest; untouched: keeps its free velocity */
-        v3 Fk[2], Tk[2];
-        for (int k = 0; k < 2; ++k) { Fk[k] = V3(0, 0, 0); Tk[k] = V3(0, 0, 0); }
+        const int L = b < NB ? phaseb_lanes(na + nbl) : 2;
+        v3 Fk[32], Tk[32];
+        for (int k = 0; k < L; ++k) { Fk[k] = V3(0, 0, 0); Tk[k] = V3(0, 0, 0); }
         v3 xb = b < NB ? W->bx[b] : V3(0, 0, 0);
         for (int e = 0; e < na + nbl; ++e) {
           int i = e < na ? W->astart[b] + e : W->blist[W->boff[b] + (e - na)];
@@ -624,12 +635,17 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           v3 f = V3(c->f[0], c->f[1], c->f[2]);
           if (e >= na) f = vneg(f);
           v3 wpt = V3(c->w[0], c->w[1], c->w[2]);
-          int k = e & 1;
+          int k = e & (L - 1);
           Fk[k] = vadd(Fk[k], f);
           Tk[k] = vadd(Tk[k], vcross(vsub(wpt, xb), f));
         }
-        v3 F = vadd(Fk[0], Fk[1]);
-        v3 T = vadd(Tk[0], Tk[1]);
+        for (int o = 1; o < L; o <<= 1) {
+          v3 Fn[32], Tn[32];
+          for (int k = 0; k < L; ++k) { Fn[k] = vadd(Fk[k], Fk[k ^ o]); Tn[k] = vadd(Tk[k], Tk[k ^ o]); }
+          for (int k = 0; k < L; ++k) { Fk[k] = Fn[k]; Tk[k] = Tn[k]; }
+        }
+        v3 F = Fk[0];
+        v3 T = Tk[0];
         if (b < NB) {
           W->bv[b] = vmad(F, S->br_invm[b], W->vfree[b]);
           W->bw[b] = vadd(W->wfree[b], brick_Iinv_mul(W, b, T));

@@ -82,6 +82,7 @@
 #ifndef SIM_GATHER_U
 #define SIM_GATHER_U 1                 /* incidences whose loads phase B issues together per lane (2 / 4 measured slower: 5.56 / 5.87 vs 5.18 ms) */
 #endif
+#define PB_LANES_MAX 1152              /* sum of phase-B lane groups: < NB + (2 MAXC) / 2, rounded up to whole warps */
 #define PPMAX 26                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
 
 struct SimSmem {
@@ -102,7 +103,7 @@ struct SimSmem {
   float4 bfw[NB];   // free angular velocity .xyz
   float4 bI0[NB];   // world-frame inverse inertia R diag(1/I) R^T: xx xy xz yy
   float4 bI1[NB];   //                                              yz zz
-  int4 irec[NB];    // phase-B work items (one per awake, touched brick): a0 | na | b0 | body + (ntot << 8)
+  int4 irec[NB];    // phase-B record of brick b (valid while it is awake and touched): a0 | na | b0 | b + (ntot << 8) + (log2 lanes << 20)
   float lq[SDX_NL][4], ja[SDX_ND][3], jo[SDX_ND][3];
   float q[SDX_ND + 1], qd[SDX_ND + 1], tgt[SDX_ND + 1], qdfree[SDX_ND + 1], ieff[SDX_ND + 1];
   float linkF[SDX_NL][3], linkM[SDX_NL][3];
@@ -113,7 +114,8 @@ struct SimSmem {
   int scan[SIM_THREADS];
   int ncon, ndropped;                  // contacts of the sub-step | contacts beyond MAXC (after shedding the speculative ones)
   int ndrop_cand, ndrop_static;        // candidate pairs beyond KC when the lists were last built | of those, pairs against statics (statics claim their slots first: 0)
-  int nact;                            // bricks phase B has to visit: awake AND touched by at least one contact (irec, ascending)
+  int nact;                            // lanes phase B occupies: sum over awake, touched bricks of their lane-group size
+  unsigned char lmap[PB_LANES_MAX];    // phase-B lane -> brick
   unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
   // contact records as three 16-byte vectors (one LDS.128 / STS.128 each)
 #if !SIM_GLOBAL_CONTACTS
@@ -255,37 +257,28 @@ __device__ __forceinline__ v3 brick_Iinv_mul(const float4 w0, const float4 w1, v
             fmaf(w1.y, u.z, fmaf(w1.x, u.y, w0.z * u.x)));
 }
 
-// phase B's inner loop: lane k of a body's lane pair sums the impulses (and their moments about xb) of the incidences
-// e = k, k + 2, k + 4, ... of that body -- owned contacts [a0, a0 + na) first, then the ascending target-side list at b0 --
-// strictly in that order (the oracle's Fk[k] / Tk[k]).  The loads of U consecutive incidences are issued together before
-// the first add, so a lane waits for one shared-memory + one L1 round trip per U incidences instead of per incidence.
-template <int U>
+// phase B's inner loop: lane k of a body's group of L lanes sums the impulses (and their moments about xb) of the incidences
+// e = k, k + L, k + 2 L, ... of that body -- owned contacts [a0, a0 + na) first, then the ascending target-side list at b0 --
+// strictly in that order (the oracle's Fk[k] / Tk[k]).
 __device__ __forceinline__ void gather_incident(const SimSmem& M, const float4* CA, int a0, int na, int b0, int ntot,
-                                                int k, v3 xb, v3* Fo, v3* To) {
+                                                int k, int L, v3 xb, v3* Fo, v3* To) {
   v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
 #pragma unroll 1
-  for (int e0 = k; e0 < ntot; e0 += 2 * U) {
-    int idx[U];
-    float4 F4[U], A4[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int ee = e0 + 2 * u;
-      idx[u] = ee < na ? a0 + ee : (ee < ntot ? (int)M.blist[b0 + (ee - na)] : 0);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) { F4[u] = M.cf4[idx[u]]; A4[u] = CA[idx[u]]; }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int ee = e0 + 2 * u;
-      if (ee < ntot) {
-        v3 f = V3(F4[u].x, F4[u].y, F4[u].z);
-        if (ee >= na) f = vneg(f);
-        F = vadd(F, f);
-        T = vadd(T, vcross(vsub(V3(A4[u].x, A4[u].y, A4[u].z), xb), f));
-      }
-    }
+  for (int ee = k; ee < ntot; ee += L) {
+    const int idx = ee < na ? a0 + ee : (int)M.blist[b0 + (ee - na)];
+    const float4 F4 = M.cf4[idx], A4 = CA[idx];
+    v3 f = V3(F4.x, F4.y, F4.z);
+    if (ee >= na) f = vneg(f);
+    F = vadd(F, f);
+    T = vadd(T, vcross(vsub(V3(A4.x, A4.y, A4.z), xb), f));
   }
   *Fo = F; *To = T;
+}
+// lanes that share a brick's incidences in phase B: the smallest power of two that leaves each lane at most 4 (capped at a warp)
+__device__ __forceinline__ int phaseb_lg(int ninc) {
+  int lg = 0;
+  while (lg < 5 && (4 << lg) < ninc) ++lg;
+  return lg;
 }
 
 __device__ __forceinline__ void contact_axes(const SimSmem& M, uint32_t word, v3* n, v3* t1, v3* t2) {
@@ -786,20 +779,40 @@ SIM_BROAD_UNROLL
       M.nb[tid] = (M.aend[tid] - M.astart[tid]) + (o1 - o0);
     }
     __syncthreads();
-    if (tid < 32) {                                            // warp 0: compact the bricks phase B has to visit
-      int base = 0;
+    if (tid < 32) {                                            // warp 0: lay out phase B's lane groups
+      // A brick that is awake and touched gets a group of L = 2^lg lanes (phaseb_lg: at most 4 incidences per lane).  Groups are
+      // placed class by class in DESCENDING size, so every group is aligned to its own size and never straddles a warp; where a
+      // group sits does not matter for the result (its lanes only talk to each other, by xor-shuffles).
+      bool act[(NB + 31) / 32]; int lgs[(NB + 31) / 32], pos[(NB + 31) / 32];
 #pragma unroll
       for (int r = 0; r < (NB + 31) / 32; ++r) {
         const int b = r * 32 + tid;
-        const bool act = b < NB && !(M.sflag[b] & 1) && M.nb[b] > 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, act);
-        if (act) {                                             // phase B's work item: everything a lane pair needs in one LDS.128
-          const int a0 = M.astart[b];
-          M.irec[base + __popc(bal & ((1u << tid) - 1u))] = make_int4(a0, M.aend[b] - a0, M.boff[b], b | (M.nb[b] << 8));
-        }
-        base += __popc(bal);
+        act[r] = b < NB && !(M.sflag[b] & 1) && M.nb[b] > 0;
+        lgs[r] = act[r] ? phaseb_lg(M.nb[b]) : -1;
+        pos[r] = -1;
       }
-      if (tid == 0) M.nact = base;
+      int total = 0;
+#pragma unroll 1
+      for (int c = 5; c >= 0; --c) {
+        int run = 0;
+#pragma unroll
+        for (int r = 0; r < (NB + 31) / 32; ++r) {
+          const unsigned bal = __ballot_sync(0xffffffffu, lgs[r] == c);
+          if (lgs[r] == c) pos[r] = total + ((run + __popc(bal & ((1u << tid) - 1u))) << c);
+          run += __popc(bal);
+        }
+        total += run << c;
+      }
+#pragma unroll
+      for (int r = 0; r < (NB + 31) / 32; ++r) {
+        const int b = r * 32 + tid;
+        if (b < NB) M.bcur[b] = pos[r];
+        if (act[r]) {                                            // everything a lane needs in one LDS.128
+          const int a0 = M.astart[b];
+          M.irec[b] = make_int4(a0, M.aend[b] - a0, M.boff[b], b | (M.nb[b] << 8) | (lgs[r] << 20));
+        }
+      }
+      if (tid == 0) M.nact = total;
     }
     if (tid >= ROBOT_TID0) {
       const int L = tid - ROBOT_TID0;
@@ -822,7 +835,11 @@ SIM_BROAD_UNROLL
       }
     __syncthreads();
     PMARK(8);
-    // 8. inverse mass-split effective masses along n, t1, t2
+    // 8. inverse mass-split effective masses along n, t1, t2  (|| the lane -> brick map of phase B, group by group)
+    if (tid < NB) {
+      const int pos = M.bcur[tid];
+      if (pos >= 0) { const int L = 1 << ((M.irec[tid].w >> 20) & 7); for (int k = 0; k < L; ++k) M.lmap[pos + k] = (unsigned char)tid; }
+    }
     for (int i = tid; i < ncon; i += SIM_THREADS) {
       const float4 A4 = CA[i];
       uint32_t wd = __float_as_uint(CB[i].w);
@@ -886,23 +903,23 @@ SIM_BROAD_UNROLL
       // once per sub-step), and the joint-space update is skipped entirely while the robot touches nothing.
       const bool robot_warp = tid >= ROBOT_TID0;
       if (!robot_warp) {
-        const int nact = M.nact;
+        const int nl = M.nact;
 #pragma unroll 1
-#if SIM_DEAL_RR
-        for (int base = (tid >> 5); base < nact; base += 16 * NBW) {      // warp-uniform: the warp's first item
-          const int item = base + ((tid & 31) >> 1) * NBW;
-#else
-        for (int base = (tid >> 5) * 16; base < nact; base += 16 * NBW) {
-          const int item = base + ((tid & 31) >> 1);
-#endif
-          const bool live = item < nact;
-          const int4 r = M.irec[live ? item : 0];
-          const int body = r.w & 255;
+        for (int base = tid & ~31; base < nl; base += 32 * NBW) {          // warp-uniform: this warp's 32-lane window
+          const int p = base + (tid & 31);
+          const bool live = p < nl;
+          const int4 r = M.irec[live ? (int)M.lmap[p] : 0];
+          const int body = live ? r.w & 255 : 0, lg = live ? (r.w >> 20) & 7 : 0, L = 1 << lg, k = p & (L - 1);
           v3 F, T;
-          gather_incident<SIM_GATHER_U>(M, CA, r.x, r.y, r.z, live ? (r.w >> 8) : 0, tid & 1, ld3(M.bx[body]), &F, &T);
-          F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
-          T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
-          if (!(tid & 1) && live) {
+          gather_incident(M, CA, r.x, r.y, r.z, live ? (r.w >> 8) & 4095 : 0, k, L, ld3(M.bx[body]), &F, &T);
+          const int steps = __reduce_max_sync(0xffffffffu, lg);             // butterfly over the group: p[k] += p[k ^ o], o = 1, 2, 4 ...
+#pragma unroll 1
+          for (int o = 1; o < (1 << steps); o <<= 1) {
+            const float fx = __shfl_xor_sync(0xffffffffu, F.x, o), fy = __shfl_xor_sync(0xffffffffu, F.y, o), fz = __shfl_xor_sync(0xffffffffu, F.z, o);
+            const float tx = __shfl_xor_sync(0xffffffffu, T.x, o), ty = __shfl_xor_sync(0xffffffffu, T.y, o), tz = __shfl_xor_sync(0xffffffffu, T.z, o);
+            if (o < L) { F.x += fx; F.y += fy; F.z += fz; T.x += tx; T.y += ty; T.z += tz; }
+          }
+          if (k == 0 && live) {
             const float4 fv = M.bfv[body], fw = M.bfw[body];
             st3(M.bv[body], vmad(F, fv.w, V3(fv.x, fv.y, fv.z)));
             st3(M.bw[body], vadd(V3(fw.x, fw.y, fw.z), brick_Iinv_mul(M.bI0[body], M.bI1[body], T)));
@@ -917,7 +934,7 @@ SIM_BROAD_UNROLL
           const int body = NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
           const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
           v3 F, T;
-          gather_incident<SIM_GATHER_U>(M, CA, a0, na, b0, ntot, item & 1, V3(0.0f, 0.0f, 0.0f), &F, &T);
+          gather_incident(M, CA, a0, na, b0, ntot, item & 1, 2, V3(0.0f, 0.0f, 0.0f), &F, &T);
           F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
           T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
           if (!(item & 1) && live) { st3(M.linkF[body - NB], F); st3(M.linkM[body - NB], T); }
