@@ -92,7 +92,9 @@ def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None, stagger=True):
     cores = oracle.lib().sdxo_get_threads()
     n = n_envs or 32 * cores
     env = oracle.OracleEnv(scene, n)
-    if bank is not None:
+    if bank is not None and int(scene.c.task) == 3:
+        env.set_grasp_bank(*bank)
+    elif bank is not None:
         env.set_heap_bank(bank)
     if int(scene.c.task) == 2:
         from seqdex_b200.camera import SEARCH_CAMERA, look_at
@@ -129,7 +131,8 @@ def host_bank(scene, per_type=2, settle=150):
     return rows.reshape(8, per_type, 72, 13)
 
 
-TASKS = {"grasp_sim": ("BlockAssemblyGraspSim", 396), "orient": ("BlockAssemblyOrient", 186), "search": ("BlockAssemblySearch", 186)}
+TASKS = {"grasp_sim": ("BlockAssemblyGraspSim", 396), "orient": ("BlockAssemblyOrient", 186), "search": ("BlockAssemblySearch", 186),
+         "insert": ("BlockAssemblyInsertSim", 75)}
 
 
 def make_config(args, world):
@@ -190,6 +193,57 @@ def run_reference(args):
     })
 
 
+def run_chain_bench(args):
+    """BASELINE configs[3]: the task chain with transition-feasibility (t-value) gates, every rank on its own shard of envs with the
+    hand-offs resident on the device (seqdex_b200/chain.py).  `--num-envs` is PER GPU: configs[3] = --gpus 8 --num-envs 1024."""
+    import torch
+    import torch.distributed as dist
+    from seqdex_b200.chain import run_chain
+    from seqdex_b200.tasks.block_assembly_grasp_sim import default_tvalue_weights
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.num_envs
+    w = default_tvalue_weights(1)
+    w[-1] += 50.0            # no trained gate checkpoints ship with the reference: the success logit is biased open so every stage hands on
+    eps = max(1, -(-args.steps // 75))
+    sampler = ClockSampler(local)
+    sampler.start()
+    timing = {}
+    out = run_chain(num_envs=n, device_id=local, episodes=(eps, eps, eps, eps), tvalue_weights=w, bank_capacity=max(64, n // 8), seed=22 + rank,
+                    timing=timing)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    stages = list(timing)
+    t = torch.tensor([timing[k][0] for k in stages], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = dict(zip(stages, t.tolist()))
+    steps = {k: timing[k][1] for k in stages}
+    tot_s, tot_steps = sum(secs.values()), sum(steps.values())
+    if rank == 0:
+        emit({
+            "metric": "env-steps/sec, full chain with t-value switching (BASELINE configs[3])", "value": world * n * tot_steps / tot_s,
+            "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * tot_s / tot_steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"chain {' -> '.join(stages)} at num_envs={n} per GPU ({n * world} global), {eps} episode(s) per stage, uniform-random "
+                                   "policies, device-resident hand-offs (heap rings -> next stage's bank), gates = the stages' t-value / pixel tests",
+                       "num_envs_per_gpu": n, "global_envs": n * world, "parallelism": f"env-sharded x{world}, no data-path collective",
+                       "timed": "VecTask.step loops of every stage incl. the scripted resets (CUDA events, max over ranks); env construction and bank hand-over outside"},
+            "per_stage": {k: {"env_steps_per_s": world * n * steps[k] / secs[k], "steps": steps[k], "seconds": secs[k]} for k in stages},
+            "gates": {"search_heaps_per_type": out.get("search_heaps_per_type"), "orient_heaps_per_type": out.get("orient_heaps_per_type"),
+                      "grasp_terminal_states": out.get("grasp_terminal_states"), "insert_success_rate": out.get("insert_success_rate")},
+            "mean_rewards": {k: out.get(f"{k}_mean_reward") for k in stages},
+            "e2e": {"value": world * n * tot_steps / tot_s, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "scope": "device-resident chain (policies on the device); the host-buffer path is measured by --task grasp_sim"},
+            "clocks": sampler.summary(),
+        })
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 _REAL_STDOUT = None
 
 
@@ -226,7 +280,7 @@ def main():
     ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
                     help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
                          "rollout: VecTask.step only with U(-1,1) actions")
-    ap.add_argument("--task", default="grasp_sim", choices=["grasp_sim", "orient", "search"],
+    ap.add_argument("--task", default="grasp_sim", choices=["grasp_sim", "orient", "search", "insert", "chain"],
                     help="grasp_sim: BlockAssemblyGraspSim, the BASELINE.json metric (configs[1]); orient: BlockAssemblyOrient (configs[2]: "
                          "32768 envs over 2 GPUs = --gpus 2 with the default 16384 envs per GPU)")
     ap.add_argument("--minibatch", type=int, default=32768,
@@ -234,6 +288,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.task == "chain":
+        return run_chain_bench(args)
 
     import torch
     import torch.distributed as dist
@@ -254,11 +310,16 @@ def main():
     search = args.task == "search"
     # Orient's reset_idx is a script over the WHOLE sim (103 extra contact steps whenever any env resets, OR:1390-1695), so its
     # episodes run in lockstep as in the reference (time-outs only); GraspSim's per-env resets are staggered (see below)
-    task_name = "BlockAssemblySearch" if search else "BlockAssemblyOrient" if orient else "BlockAssemblyGraspSim"
+    insert = args.task == "insert"
+    task_name = TASKS[args.task][0]
     scene = scene_from_cfg(task_name)               # the task's yaml-stated sim / env parameters (contact_offset 0.02 for Orient / Search)
-    obs_dim = 186 if orient else 396
+    obs_dim, state_dim = TASKS[args.task][1], (188 if insert else 564)
     env = SdxEnv(scene, n, local, seed=22 + rank)
-    if search:                                      # Search resets from the drop lattice and renders its overview camera
+    if insert:                                      # InsertSim restores banked grasps (IS:372-375): synthetic stand-ins here, GraspSim's rings in --task chain
+        from seqdex_b200.tasks.block_assembly_insert_sim import synthetic_grasp_bank
+        bank = synthetic_grasp_bank(scene, args.bank_per_type, seed=22 + rank)
+        env.set_grasp_bank(*bank)
+    elif search:                                      # Search resets from the drop lattice and renders its overview camera
         from seqdex_b200.camera import SEARCH_CAMERA, look_at
         env.set_camera(look_at(**SEARCH_CAMERA))
         bank = None
@@ -318,7 +379,7 @@ def main():
         class _Task:      # the task surface VecTask needs, over the SAME env (no second simulation state)
             pass
         task = _Task()
-        task.env, task.num_envs, task.num_obs, task.num_states, task.num_actions, task.device = env, n, obs_dim, 564, 23, f"cuda:{local}"
+        task.env, task.num_envs, task.num_obs, task.num_states, task.num_actions, task.device = env, n, obs_dim, state_dim, 23, f"cuda:{local}"
         task.obs_buf, task.states_buf, task.rew_buf, task.reset_buf = (env.tensor(k) for k in ("OBS", "STATES", "REW", "RESET"))
         task.extras = {}
         step_ev = []                    # CUDA events around every VecTask.step of the timed PPO iterations
@@ -372,7 +433,7 @@ def main():
     h_act = torch.empty(n, 23, dtype=torch.float32).pin_memory()
     h_act.copy_(acts[0].cpu())
     h_obs = torch.empty(n, obs_dim, dtype=torch.float32).pin_memory()
-    h_st = torch.empty(n, 564, dtype=torch.float32).pin_memory()
+    h_st = torch.empty(n, state_dim, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(n, dtype=torch.float32).pin_memory()
     h_rs = torch.empty(n, dtype=torch.int64).pin_memory()
     for _ in range(3):
@@ -403,7 +464,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(args, world),
             "e2e": {"value": world * n * E / (e2e_ms * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": n * 23 * 4,
-                    "d2h_bytes_per_step": n * (obs_dim + 564 + 1) * 4 + n * 8, "steps": E, "timer": "cuda events (max over ranks)",
+                    "d2h_bytes_per_step": n * (obs_dim + state_dim + 1) * 4 + n * 8, "steps": E, "timer": "cuda events (max over ranks)",
                     "value_wall_clock": world * n * E / (e2e_wall_ms * 1e-3),
                     "scope": "VecTask.step through the C-ABI with pinned HOST buffers (sdx_step_host): the rollout only -- PPO is NOT in this "
                              "loop, which is why it can exceed `value` (PPO in the loop, device-resident)"},
@@ -435,7 +496,8 @@ def main():
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
         }
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(scene, bank=None if search else bank.cpu().numpy(), stagger=not orient, n_envs=1024 if orient else None)
+            out["cpu_baseline"] = cpu_baseline(scene, bank=None if search else bank if insert else bank.cpu().numpy(), stagger=not orient,
+                                               n_envs=1024 if orient else None)
         emit(out)
     if world > 1:
         dist.barrier()

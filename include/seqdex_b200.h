@@ -66,7 +66,9 @@ typedef struct sdx_scene_t {
   int pad3[2];
   float default_dof[SDX_ND];  /* Search: arm_hand_default_dof_pos, the pose that parks the hand beside the bin (SE:207-211) */
   float prepare_dof[SDX_ND];  /* Search: arm_hand_prepare_dof_pos_list[0], where an episode starts (SE:220-223, 316) */
-  float pad4[2];
+  float insert_plate_zw[2];   /* InsertSim: (z, w) of gymapi.Quat.from_euler_zyx(0, 0, 1.57), the base-plate's second yaw (IS:1436-1437) */
+  int st_mod[SDX_MAX_STATIC], st_rem[SDX_MAX_STATIC];   /* static s exists only in envs with env % st_mod == st_rem (st_mod 0: in every env);
+                                                            InsertSim's base-plate is 4x4x{1,2,4} by env % 3 (IS:971-977) */
 } sdx_scene_t;
 
 /* tasks sharing the scene, the contact step and the PPO engine (SURVEY.md section 8a "per-task dimensions"):
@@ -74,6 +76,8 @@ typedef struct sdx_scene_t {
 #define SDX_TASK_GRASP_SIM 0   /* BlockAssemblyGraspSim: obs 132 x 3, states 188 x 3, episode 150 (GS:191-211) */
 #define SDX_TASK_ORIENT 1      /* BlockAssemblyOrient:   obs  62 x 3, states 188 x 3, episode  75 (OR:189-214)  */
 #define SDX_TASK_SEARCH 2      /* BlockAssemblySearch:   obs  62 x 3, states 188 x 3, episode  75 (SE:149-175); BASELINE configs[0] */
+#define SDX_TASK_INSERT_SIM 3  /* BlockAssemblyInsertSim: obs 75 x 1, states 188 x 1, episode 125 (IS:172-193); last link of configs[3] */
+#define SDX_INSERT_OBS_FRAME 75
 #define SDX_ORIENT_OBS_FRAME 62
 #define SDX_ORIENT_BANK_WRAP 10000   /* OR:1478-1479: ring index returns to 0 after slot 10000 */
 
@@ -109,7 +113,10 @@ enum {
   SDX_T_SEG = 25,       /* i32 [N][3]    Search: pixels showing the target | centre row | centre column of the last render (SE:1231-1241) */
   SDX_T_EMERGENCE = 26, /* f32 [N]       Search: emergence reward = 5 x (pixels now - pixels at the last render) (SE:1640-1646)   */
   SDX_T_TVOBS = 27,     /* f32 [N][650]  Search: the transition-feasibility gate's input, 10 frames x 65 (SE:400, 1154-1166)      */
-  SDX_T_COUNT = 28
+  SDX_T_PLATE = 28,     /* f32 [N][7]    InsertSim: root pose of the base-plate ("extra lego", IS:1438-1446)                               */
+  SDX_T_ROT_ERR = 29,   /* f32 [N][3]    InsertSim: wrist orientation error of the last pre_physics_step (IS:1531), read by the reward      */
+  SDX_T_SUCCESS = 30,   /* f32 [N][2]    InsertSim: success_buf written at reset (IS:1348-1350): [inserted, not inserted]                   */
+  SDX_T_COUNT = 31
 };
 
 /* pinhole camera of the segmentation features (see sdx_segmentation_features) */
@@ -203,6 +210,13 @@ int sdx_orient_heap_bank(sdx_env_t* env, int capacity, void** rows_dev, void** i
  * capacity > 0 allocates rings rows [8][capacity + 1][72][13], hand [8][capacity + 1][23][2] f32, index i32[8] */
 int sdx_set_camera(sdx_env_t* env, const sdx_camera_t* cam);
 int sdx_search_bank(sdx_env_t* env, int capacity, void** rows_dev, void** hand_dev, void** index_dev);
+/* InsertSim (IS = tasks/block_assembly/allegro_hand_block_assembly_insert_sim.py): the banked grasps its reset_idx restores
+ * (saved_grasping_{object,hand}_ternimal_states_*.pkl, IS:372-375, 1449-1453): obj [8][per_type][13] root rows of the grasped brick,
+ * hand [8][per_type][23][2] DoF states.  Device or host pointers (is_device). */
+int sdx_set_grasp_bank(sdx_env_t* env, const float* hand, const float* obj, int per_type, int is_device);
+/* test hook of the InsertSim parity tests: the bank slot every env restores on its next resets (NULL: drawn from Philox) and the
+ * base-plate yaw index of the next reset_idx calls (-1: drawn) */
+int sdx_insert_test_hooks(sdx_env_t* env, const int* slot_by_env_host, int plate_yaw);
 /* number of contact steps the last sdx_pre_physics spent inside reset_idx (0 when nobody reset; 103 for a full Orient reset) */
 int sdx_last_reset_sim_steps(const sdx_env_t* env);
 /* BlockAssemblySearch's camera features (SE = tasks/block_assembly/allegro_hand_block_assembly_search.py): the reference renders

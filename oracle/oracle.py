@@ -76,7 +76,13 @@ class OracleEnv:
         self.netf = np.zeros((n, NL, 3), np.float32)
         self.actions = np.zeros((n, 23), np.float32)
         self.task = int(scene.c.task)               # 0 BlockAssemblyGraspSim, 1 BlockAssemblyOrient
-        self.obs = np.zeros((n, 396 if self.task == 0 else 186), np.float32)
+        self.obs = np.zeros((n, {0: 396, 3: 75}.get(self.task, 186)), np.float32)
+        if self.task == 3:                          # BlockAssemblyInsertSim: base-plate pose, wrist orientation error, success_buf, banked grasps
+            self.plate = np.zeros((n, 7), np.float32)   # written by the first reset_idx (every env starts with its reset flag set, BT:63)
+            self.rot_err = np.zeros((n, 3), np.float32)
+            self.success_buf = np.zeros((n, 2), np.float32)
+            self.grasp_obj = self.grasp_hand = None
+            self.plate_yaw = None
         if self.task == 2:                          # BlockAssemblySearch: camera features, emergence reward, the gate's 10-frame input
             self.seg = np.zeros((n, 3), np.int32)
             self.emergence = np.zeros(n, np.float32)
@@ -84,7 +90,7 @@ class OracleEnv:
             self.tvobs = np.zeros((n, 650), np.float32)
             self.cam = None
             self.sb_wrap = 0
-        self.states = np.zeros((n, 564), np.float32)
+        self.states = np.zeros((n, 188 if self.task == 3 else 564), np.float32)
         self.rew = np.zeros(n, np.float32)
         self.reset = np.ones(n, np.int64)           # BT:63
         self.progress = np.zeros(n, np.int64)
@@ -244,7 +250,43 @@ class OracleEnv:
                                         fp(self.rew), fp(self.tvalue), fp(self.finger_dist), fp(self.successes), fp(self.consec),
                                         int(count_step))
 
+    # ---- BlockAssemblyInsertSim (IS:1328-1565)
+    def set_grasp_bank(self, hand, obj):
+        """hand [8, K, 23, 2], obj [8, K, 13]: saved_grasping_{hand,object}_ternimal_states (IS:372-375)"""
+        self.grasp_hand = np.ascontiguousarray(hand, np.float32)
+        self.grasp_obj = np.ascontiguousarray(obj, np.float32).reshape(8, -1, 13)
+
+    def plate_yaw_draw(self):
+        """random.sample([0, 1], 1), ONE draw per reset_idx call (IS:1435): Philox(seed, total_steps) here"""
+        if self.plate_yaw is not None:
+            return int(self.plate_yaw)
+        return int(dr_philox_bit(self.seed, self.total_steps))
+
+    def _insert_reset_idx(self, slots=None):
+        """slots (test hook): the bank slot per ENV, or one per resetting env in env order (what the golden generator recorded)"""
+        assert self.grasp_obj is not None, "reset needs the banked grasps (IS:372-375)"
+        if slots is None:
+            slots = getattr(self, "slot_by_env", None)
+        so = None
+        if slots is not None:
+            so = np.zeros(self.n, np.int32)
+            if len(slots) == self.n:
+                so[:] = slots
+            else:
+                so[np.flatnonzero(self.reset)] = slots
+        self.L.sdxo_insert_reset(self.S, self.n, ctypes.c_uint64(self.seed), fp(self.grasp_obj), fp(self.grasp_hand), int(self.grasp_obj.shape[1]),
+                                 self.plate_yaw_draw(), ip(so) if so is not None else None, int(self.total_steps > 0), fp(self.brick), fp(self.dof),
+                                 fp(self.plate), fp(self.target_init), lp(self.progress), lp(self.reset), fp(self.successes), fp(self.success_buf),
+                                 ip(self.episode), ip(self.wsn), self.slp.ctypes.data_as(ctypes.c_void_p))
+        self.refresh_links()                      # the hand was teleported: pre_physics reads its pose before any contact step
+
     def pre_physics(self, actions):
+        if self.task == 3:
+            if self.reset.any():
+                self._insert_reset_idx()
+            a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)   # VR:166
+            self.L.sdxo_insert_pre_physics(self.S, self.n, fp(a), fp(self.actions), fp(self.dof), fp(self.link), fp(self.jac7), fp(self.rot_err))
+            return
         if self.task == 2:
             self.last_reset_sim_steps = 0
             if self.reset.any():
@@ -276,6 +318,12 @@ class OracleEnv:
                                 lp(self.progress), fp(self.target_init))
 
     def post_physics(self):
+        if self.task == 3:
+            self.L.sdxo_insert_post_physics(self.S, self.n, fp(self.brick), fp(self.dof), fp(self.link), fp(self.actions), fp(self.target_init),
+                                            fp(self.plate), fp(self.rot_err), lp(self.progress), lp(self.reset), fp(self.obs), fp(self.states),
+                                            fp(self.rew), fp(self.finger_dist), fp(self.successes), fp(self.consec))
+            self.total_steps += 1
+            return
         if self.task == 2:
             self._search_post()
             self.total_steps += 1
@@ -294,6 +342,13 @@ class OracleEnv:
         self.simulate()
         self.post_physics()
         return (np.clip(self.obs, -5, 5), np.clip(self.states, -5, 5), self.rew, self.reset)   # VR:171-177
+
+
+def dr_philox_bit(seed, counter):
+    """low bit of Philox4x32-10(seed; counter, 0xC0FFEE, 7): the base-plate yaw draw of InsertSim's reset_idx (same stream in csrc/sdx_env.cu)"""
+    out = (ctypes.c_uint32 * 4)()
+    lib().sdxo_philox(ctypes.c_uint64(seed), ctypes.c_uint32(counter & 0xFFFFFFFF), ctypes.c_uint32(0xC0FFEE), ctypes.c_uint32(7), out)
+    return out[0] & 1
 
 
 def gae(rewards, values, dones, last_values, last_dones, gamma, tau):

@@ -11,6 +11,7 @@
 #include "sdx_sim.cuh"
 #include "sdx_task.cuh"
 #include "sdx_task_orient.cuh"
+#include "sdx_task_insert.cuh"
 #include "sdx_camera.cuh"
 #include "sdx_dr.cuh"
 #include "sdx_task_search.cuh"
@@ -56,8 +57,13 @@ struct sdx_env {
   float *sb_rows = nullptr, *sb_hand = nullptr; int* sb_index = nullptr; int sb_wrap = 0;
   int64_t* progress0_host = nullptr;   // pinned: progress_buf[0] (SE:989 reads it on the host every step)
   float4* cscratch = nullptr;      // [n][2][MAXC] contact records of k_simulate (SIM_GLOBAL_CONTACTS)
+  // BlockAssemblyInsertSim
+  float *ib_obj = nullptr, *ib_hand = nullptr; int ib_per_type = 0;   // the banked grasps reset_idx restores (sdx_set_grasp_bank)
+  int* slot_by_env = nullptr;      // test hook: reset slots given per env instead of drawn
+  int plate_yaw_override = -1;
 };
-static int obs_frame(const sdx_env* E) { return E->task == SDX_TASK_GRASP_SIM ? SDX_OBS_FRAME : SDX_ORIENT_OBS_FRAME; }
+static int obs_frame(const sdx_env* E) { return E->task == SDX_TASK_GRASP_SIM ? SDX_OBS_FRAME : E->task == SDX_TASK_INSERT_SIM ? SDX_INSERT_OBS_FRAME : SDX_ORIENT_OBS_FRAME; }
+static int obs_stack(const sdx_env* E) { return E->task == SDX_TASK_INSERT_SIM ? 1 : SDX_STACK; }   // IS:171 stack_obs = 1
 
 static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim, int* dtype) {
   int64_t n = E->n;
@@ -69,8 +75,8 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
     case SDX_T_JAC7: s[0] = n; s[1] = 6; s[2] = 7; nd = 3; break;
     case SDX_T_NETF: s[0] = n; s[1] = SDX_NL; s[2] = 3; nd = 3; break;
     case SDX_T_ACTIONS: s[0] = n; s[1] = 23; nd = 2; break;
-    case SDX_T_OBS: s[0] = n; s[1] = 3 * obs_frame(E); nd = 2; break;
-    case SDX_T_STATES: s[0] = n; s[1] = 3 * SDX_STATE_FRAME; nd = 2; break;
+    case SDX_T_OBS: s[0] = n; s[1] = obs_stack(E) * obs_frame(E); nd = 2; break;
+    case SDX_T_STATES: s[0] = n; s[1] = obs_stack(E) * SDX_STATE_FRAME; nd = 2; break;
     case SDX_T_REW: case SDX_T_TVALUE: case SDX_T_SUCCESSES: s[0] = n; break;
     case SDX_T_RESET: case SDX_T_PROGRESS: s[0] = n; dt = 1; break;
     case SDX_T_TARGET_INIT: s[0] = n; s[1] = 7; nd = 2; break;
@@ -88,6 +94,9 @@ static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim
     case SDX_T_SEG: s[0] = n; s[1] = 3; nd = 2; dt = 2; break;
     case SDX_T_EMERGENCE: s[0] = n; break;
     case SDX_T_TVOBS: s[0] = E->task == SDX_TASK_SEARCH ? n : 1; s[1] = SEARCH_TVOBS; nd = 2; break;
+    case SDX_T_PLATE: s[0] = n; s[1] = 7; nd = 2; break;
+    case SDX_T_ROT_ERR: s[0] = n; s[1] = 3; nd = 2; break;
+    case SDX_T_SUCCESS: s[0] = n; s[1] = 2; nd = 2; break;
     default: return 0;
   }
   if (shape) for (int i = 0; i < 4; ++i) shape[i] = s[i];
@@ -105,7 +114,7 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaSetDevice(device));
   sdx_env* E = new sdx_env();
   E->n = num_envs; E->device = device; E->seed = seed; E->host_scene = *scene;
-  if (scene->task != SDX_TASK_GRASP_SIM && scene->task != SDX_TASK_ORIENT && scene->task != SDX_TASK_SEARCH) { g_err = "sdx_create: unknown scene.task"; delete E; return -1; }
+  if (scene->task != SDX_TASK_GRASP_SIM && scene->task != SDX_TASK_ORIENT && scene->task != SDX_TASK_SEARCH && scene->task != SDX_TASK_INSERT_SIM) { g_err = "sdx_create: unknown scene.task"; delete E; return -1; }
   E->task = scene->task;
   CK(cudaMalloc(&E->scene, sizeof(sdx_scene_t)));
   CK(cudaMemcpy(E->scene, scene, sizeof(sdx_scene_t), cudaMemcpyHostToDevice));
@@ -131,8 +140,8 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaMalloc(&E->ob_slot, n * 4));
   CK(cudaMalloc(&E->last_pixels, n * 4)); CK(cudaMemset(E->last_pixels, 0, n * 4));
   CK(cudaMallocHost(&E->progress0_host, 8)); *E->progress0_host = 0;
-  CK(cudaMalloc(&E->stage_obs, n * 3 * obs_frame(E) * 4));
-  CK(cudaMalloc(&E->stage_states, n * 3 * SDX_STATE_FRAME * 4));
+  CK(cudaMalloc(&E->stage_obs, n * obs_stack(E) * obs_frame(E) * 4));
+  CK(cudaMalloc(&E->stage_states, n * obs_stack(E) * SDX_STATE_FRAME * 4));
   CK(cudaMalloc(&E->stage_actions, n * 23 * 4));
 #if SIM_GLOBAL_CONTACTS
   CK(cudaMalloc(&E->cscratch, n * 2 * MAXC * sizeof(float4)));
@@ -152,6 +161,7 @@ extern "C" void sdx_destroy(sdx_env_t* E) {
   cudaFree(E->stage_obs); cudaFree(E->stage_states); cudaFree(E->stage_actions);
   cudaFree(E->cscratch);
   cudaFree(E->last_pixels); cudaFree(E->sb_rows); cudaFree(E->sb_hand); cudaFree(E->sb_index); cudaFreeHost(E->progress0_host);
+  cudaFree(E->ib_obj); cudaFree(E->ib_hand); cudaFree(E->slot_by_env);
   cudaFree(E->flag_count); cudaFreeHost(E->flag_count_host); cudaFree(E->ob_slot); cudaFree(E->ob_rows); cudaFree(E->ob_index);
   delete E;
 }
@@ -285,10 +295,63 @@ extern "C" int sdx_reset_all(sdx_env_t* E) {
 
 static int orient_pre_physics(sdx_env_t* E, const float* actions_dev);
 static int search_pre_physics(sdx_env_t* E, const float* actions_dev);
+/* the base-plate yaw of a reset_idx call: random.sample([0, 1], 1), ONE draw for all envs that reset (IS:1435).  Philox(seed; step) bit */
+static int insert_plate_yaw(const sdx_env_t* E) {
+  if (E->plate_yaw_override >= 0) return E->plate_yaw_override;
+  uint32_t k0 = (uint32_t)E->seed, k1 = (uint32_t)(E->seed >> 32), c[4] = {(uint32_t)E->total_steps, 0xC0FFEEu, 7u, 0u};
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (int)(c[0] & 1u);
+}
+static int insert_pre_physics(sdx_env_t* E, const float* actions_dev) {
+  const int n = E->n;
+  if (!E->ib_obj) { g_err = "sdx_pre_physics: InsertSim needs the banked grasps (sdx_set_grasp_bank; IS:372-375)"; return -1; }
+  k_insert_reset<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, E->seed, E->ib_obj, E->ib_hand, E->ib_per_type, insert_plate_yaw(E), E->slot_by_env,
+                                                       E->total_steps > 0 ? 1 : 0, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_PLATE), F(SDX_T_TARGET_INIT),
+                                                       I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), F(SDX_T_SUCCESS), I32(SDX_T_EPISODE),
+                                                       I32(SDX_T_WSN), (unsigned char*)E->buf[SDX_T_SLEEP]);
+  // the hand may have been teleported: the link rows / Jacobian pre_physics reads must be those of the restored joint angles
+  k_refresh_links<<<(n + 63) / 64, 64, 0, E->stream>>>(E->scene, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7), n);
+  k_insert_pre_physics<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, actions_dev, F(SDX_T_ACTIONS), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+                                                             F(SDX_T_ROT_ERR));
+  E->launches += 3;
+  CKL();
+  return 0;
+}
+extern "C" int sdx_set_grasp_bank(sdx_env_t* E, const float* hand, const float* obj, int per_type, int is_device) {
+  if (!E || !hand || !obj || per_type <= 0) { g_err = "sdx_set_grasp_bank: bad arguments"; return -1; }
+  if (E->task != SDX_TASK_INSERT_SIM) { g_err = "sdx_set_grasp_bank: the env does not run BlockAssemblyInsertSim"; return -1; }
+  CK(cudaSetDevice(E->device));
+  CK(cudaStreamSynchronize(E->stream));
+  cudaFree(E->ib_obj); cudaFree(E->ib_hand);
+  CK(cudaMalloc(&E->ib_obj, (size_t)8 * per_type * 13 * 4));
+  CK(cudaMalloc(&E->ib_hand, (size_t)8 * per_type * 46 * 4));
+  const cudaMemcpyKind kind = is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  CK(cudaMemcpy(E->ib_obj, obj, (size_t)8 * per_type * 13 * 4, kind));
+  CK(cudaMemcpy(E->ib_hand, hand, (size_t)8 * per_type * 46 * 4, kind));
+  E->ib_per_type = per_type;
+  return 0;
+}
+/* test hook: the slot every env restores on its next resets (nullptr: drawn from Philox) and the plate yaw index (-1: drawn) */
+extern "C" int sdx_insert_test_hooks(sdx_env_t* E, const int* slot_by_env_host, int plate_yaw) {
+  CK(cudaSetDevice(E->device));
+  cudaFree(E->slot_by_env); E->slot_by_env = nullptr;
+  if (slot_by_env_host) {
+    CK(cudaMalloc(&E->slot_by_env, (size_t)E->n * 4));
+    CK(cudaMemcpy(E->slot_by_env, slot_by_env_host, (size_t)E->n * 4, cudaMemcpyHostToDevice));
+  }
+  E->plate_yaw_override = plate_yaw;
+  return 0;
+}
 extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
   CK(cudaSetDevice(E->device));
   const int n = E->n;
   if (E->task == SDX_TASK_SEARCH) return search_pre_physics(E, actions_dev);     // Search resets from the drop lattice: no bank
+  if (E->task == SDX_TASK_INSERT_SIM) return insert_pre_physics(E, actions_dev);
   if (!E->bank) { g_err = "sdx_pre_physics: no heap bank set (reset_idx samples it, GS:1507-1511)"; return -1; }
   if (E->task == SDX_TASK_ORIENT) return orient_pre_physics(E, actions_dev);
   if (E->total_steps > 0) {
@@ -495,6 +558,17 @@ extern "C" int sdx_post_physics(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
   const int n = E->n;
   if (E->task == SDX_TASK_SEARCH) return search_post_physics(E);
+  if (E->task == SDX_TASK_INSERT_SIM) {
+    k_insert_post_physics<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_ACTIONS),
+                                                              F(SDX_T_TARGET_INIT), F(SDX_T_PLATE), F(SDX_T_ROT_ERR), I64(SDX_T_PROGRESS), I64(SDX_T_RESET),
+                                                              F(SDX_T_OBS), F(SDX_T_STATES), F(SDX_T_REW), E->finger_dist, F(SDX_T_SUCCESSES), E->red_count,
+                                                              E->red_sum);
+    k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
+    E->launches += 2;
+    E->total_steps++;
+    CKL();
+    return 0;
+  }
   if (E->task == SDX_TASK_ORIENT) {
     if (orient_observe(E, 1)) return -1;
     k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
@@ -526,7 +600,7 @@ extern "C" int sdx_step_host(sdx_env_t* E, const float* actions_host, float* obs
   const size_t n = E->n;
   CK(cudaMemcpyAsync(E->stage_actions, actions_host, n * 23 * 4, cudaMemcpyHostToDevice, E->stream));
   if (sdx_step(E, E->stage_actions)) return -1;
-  const size_t no = n * 3 * obs_frame(E), ns = n * 3 * SDX_STATE_FRAME;
+  const size_t no = n * obs_stack(E) * obs_frame(E), ns = n * obs_stack(E) * SDX_STATE_FRAME;
   k_clamp_copy<<<(unsigned)((no + 255) / 256), 256, 0, E->stream>>>(F(SDX_T_OBS), E->stage_obs, no, 5.0f);
   k_clamp_copy<<<(unsigned)((ns + 255) / 256), 256, 0, E->stream>>>(F(SDX_T_STATES), E->stage_states, ns, 5.0f);
   E->launches += 2;

@@ -413,7 +413,9 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   }
   for (int s = tid; s < nst; s += SIM_THREADS) {
     int t = NB + nrs + s;
-    st3(M.sc[t], V3(S->st_c[3 * s], S->st_c[3 * s + 1], S->st_c[3 * s + 2]));
+    v3 stc = V3(S->st_c[3 * s], S->st_c[3 * s + 1], S->st_c[3 * s + 2]);
+    if (S->st_mod[s] > 0 && e % S->st_mod[s] != S->st_rem[s]) stc.z = -1000.0f;   // not part of this env's scene (InsertSim's base-plate by env % 3, IS:971-977)
+    st3(M.sc[t], stc);
     st3(M.sh[t], V3(S->st_h[3 * s], S->st_h[3 * s + 1], S->st_h[3 * s + 2]));
 #pragma unroll
     for (int i = 0; i < 9; ++i) M.sR[t][i] = (i % 4 == 0) ? 1.0f : 0.0f;

@@ -12,7 +12,7 @@ from .scene import Scene
 
 T = dict(BRICK=0, DOF=1, LINK=2, JAC7=3, NETF=4, ACTIONS=5, OBS=6, STATES=7, REW=8, RESET=9, PROGRESS=10, TVALUE=11,
          TARGET_INIT=12, SUCCESSES=13, CONSEC=14, NCONTACT=15, ROOT=16, RB=17, DOF_STATE=18, JACOBIAN=19, EPISODE=20,
-         CONTACTS=21, WS=22, WSN=23, SLEEP=24, SEG=25, EMERGENCE=26, TVOBS=27)
+         CONTACTS=21, WS=22, WSN=23, SLEEP=24, SEG=25, EMERGENCE=26, TVOBS=27, PLATE=28, ROT_ERR=29, SUCCESS=30)
 _DT = {0: (torch.float32, "<f4"), 1: (torch.int64, "<i8"), 2: (torch.int32, "<i4"), 3: (torch.uint8, "|u1")}
 
 
@@ -168,6 +168,22 @@ class SdxEnv:
         _lib.check(self.L.sdx_search_bank(self.h, self._sb_wrap, ctypes.byref(r), ctypes.byref(h), ctypes.byref(i)))
         return (self._view(r.value, (8, self._sb_wrap + 1, 72, 13)), self._view(h.value, (8, self._sb_wrap + 1, 23, 2)),
                 self._view(i.value, (8,), "<i4"))
+
+    # ---- BlockAssemblyInsertSim
+    def set_grasp_bank(self, hand, obj):
+        """the banked grasps InsertSim's reset_idx restores (IS:372-375, 1449-1453): hand [8, K, 23, 2], obj [8, K, 13] (or [8, K, 1, 13]);
+        numpy or torch, host or device (GraspSim's rings hand over on the device)"""
+        if isinstance(hand, torch.Tensor) and hand.is_cuda:
+            h, o = hand.contiguous().float(), obj.contiguous().float().reshape(8, -1, 13)
+            _lib.check(self.L.sdx_set_grasp_bank(self.h, ctypes.c_void_p(h.data_ptr()), ctypes.c_void_p(o.data_ptr()), int(h.shape[1]), 1))
+        else:
+            h = np.ascontiguousarray(hand.cpu().numpy() if isinstance(hand, torch.Tensor) else hand, np.float32)
+            o = np.ascontiguousarray(obj.cpu().numpy() if isinstance(obj, torch.Tensor) else obj, np.float32).reshape(8, -1, 13)
+            _lib.check(self.L.sdx_set_grasp_bank(self.h, h.ctypes.data_as(ctypes.c_void_p), o.ctypes.data_as(ctypes.c_void_p), int(h.shape[1]), 0))
+
+    def insert_test_hooks(self, slot_by_env=None, plate_yaw=-1):
+        s = None if slot_by_env is None else np.ascontiguousarray(slot_by_env, np.int32)
+        _lib.check(self.L.sdx_insert_test_hooks(self.h, s.ctypes.data_as(ctypes.c_void_p) if s is not None else None, int(plate_yaw)))
 
     def last_reset_sim_steps(self):
         return int(self.L.sdx_last_reset_sim_steps(self.h))

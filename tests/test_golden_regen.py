@@ -17,6 +17,7 @@ GENERATORS = {
     "gen_golden_dr.py": ["dr_params.npz"],
     "gen_golden_reset.py": ["reset_idx.npz"],
     "gen_golden_cfg.py": ["task_cfg.json"],
+    "gen_golden_insert.py": ["insert_post_physics.npz", "insert_pre_physics.npz", "insert_reset.npz"],
     "gen_golden_ppo.py": ["ppo_neglogp.npz", "ppo_ac_loss.npz", "ppo_play_steps.npz", "ppo_prepare_dataset.npz", "ppo_schedule_legacy.npz",
                           "ppo_schedule_standard.npz", "tvalue_trainer.npz"],
 }
