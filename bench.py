@@ -42,6 +42,23 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def measured_tensor_peak():
+    """dense bf16 TFLOP/s of this pool's B200s: the SUSTAINED figure (the GEMMs run inside a long step), else the recipe's fallback"""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# algorithmic tensor work of PPO per env-step (SURVEY.md 8d, with the a2c net's dead critic trunk left out, DESIGN.md section 6):
+#   inference : actor 396-1024-512-256-23 + central value 564-1024-512-256-1, one forward each per env-step
+#   update    : 5 mini-epochs x (forward + dX + dW) of both nets over every sample
+ACTOR_MAC = 396 * 1024 + 1024 * 512 + 512 * 256 + 256 * 23
+CV_MAC = 564 * 1024 + 1024 * 512 + 512 * 256 + 256 * 1
+PPO_FLOP_PER_ENV_STEP = 2.0 * (ACTOR_MAC + CV_MAC) * (1 + 5 * 3)
+
+
 class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
@@ -426,6 +443,7 @@ def main():
                                 "all_ranks_equal": bool(all(torch.equal(dgs[0], x) for x in dgs)),
                                 "note": "digest of actor + central-value parameters all-gathered after the timed region: data-parallel replicas must be bit-identical"}
         ppo_info["env_step_ms_in_loop"] = float(np.mean([a.elapsed_time(b) for a, b in step_ev]))
+        ppo_info["ppo_ms_per_iteration"] = float(np.median(it_ms)) - H * ppo_info["env_step_ms_in_loop"]
         ppo_info["bricks_asleep_frac_start_end"] = [asleep0, float((env.tensor("SLEEP") >= max(scene.c.sleep_substeps, 1)).float().mean())]
         launches = (env.launch_count() - l0 + ppo_launch() - p0) * K // (iters * H)
     # ---- end to end through the C-ABI with HOST buffers (sdx_step_host): H2D actions, D2H obs/states/rew/reset
@@ -483,6 +501,7 @@ def main():
                          "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
                          "note": "state-streaming bound is loose: the kernel is bound by block-barrier waits between ~40 phases per sub-step "
                                  "(45 % of warp stall samples, DESIGN.md section 11), not by HBM"},
+            "roofline_tensor": None,
             "clocks": sampler.summary(),
             "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "table": 1024,
                                  "dropped_max": int(nc[:, 1].max()),                       # contacts beyond the table AFTER shedding speculative ones
@@ -495,6 +514,16 @@ def main():
                                          "touching contacts only (csrc/sdx_sim.cuh); statics claim candidate slots first"},
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
         }
+        if args.mode == "ppo" and args.task == "grasp_sim" and ppo_info.get("ppo_ms_per_iteration", 0) > 0:
+            tpeak, tsrc = measured_tensor_peak()
+            ach = PPO_FLOP_PER_ENV_STEP * n * 8 / (ppo_info["ppo_ms_per_iteration"] * 1e-3) / 1e12
+            out["roofline_tensor"] = {
+                "bound": "tensor", "kernels": "k_gemm_tn / k_gemm_tn2 (tcgen05, csrc/sdx_gemm.cuh) and everything else of the PPO part of an iteration",
+                "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "peak_source": tsrc,
+                "algorithmic_flop_per_env_step": PPO_FLOP_PER_ENV_STEP, "ppo_ms_per_iteration": ppo_info["ppo_ms_per_iteration"],
+                "note": "algorithmic bf16 FLOPs of the policy / central-value forward passes and the 5 mini-epochs of updates over ALL PPO time of an "
+                        "iteration (iteration time minus its 8 env steps): GEMMs, their conversions, loss / Adam kernels and launch gaps included; "
+                        "per-kernel tensor-pipe counters: profiles/r02_ncu_gemm.txt"}
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(scene, bank=None if search else bank if insert else bank.cpu().numpy(), stagger=not orient,
                                                n_envs=1024 if orient else None)

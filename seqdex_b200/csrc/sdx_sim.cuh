@@ -45,6 +45,12 @@
 #ifndef SIM_MIN_CTAS
 #define SIM_MIN_CTAS (SIM_GLOBAL_CONTACTS ? 4 : 3)   /* CTAs per SM the register budget is sized for */
 #endif
+// SIM_GLOBAL_CF: the impulse array (and the scratch tables that share its storage) also live in the per-env global scratch behind L1:
+// 30.5 KB of shared memory per CTA instead of 46.5 KB.  Together with 128-thread CTAs that puts SIX envs on an SM instead of four
+// (the SM's 256 KB of shared memory + L1 holds about six envs' working sets).
+#ifndef SIM_GLOBAL_CF
+#define SIM_GLOBAL_CF (SIM_THREADS == 128)
+#endif
 #define ROBOT_TID0 (SIM_THREADS - 32)  /* the LAST warp owns the articulation: lane j = DoF j, lane L = link L */
 #define NBW (ROBOT_TID0 / 32)          /* brick warps */
 #define SIM_PROF_REC (18 * 2 * 8 + 16)  /* SIM_PROFILE builds: int64 counters per env and sub-step */
@@ -122,9 +128,12 @@ struct SimSmem {
   float4 ca[MAXC];    // contact point w.xyz | bias
   float4 cb[MAXC];    // 1/den along n, t1, t2 | packed word (bodies, target shape, face axis, sign)
 #endif
+#if !SIM_GLOBAL_CF
   float4 cf4[MAXC];   // total impulse f.xyz | unused          (also scratch: candidate overflow lists, pair tables)
+#endif
 };
 
+static_assert(SIM_THREADS == 256 || SIM_THREADS == 128, "the broad phase deals (owner, half) pairs over 256 or 128 threads");
 static_assert(NOWN * KC * 2 <= 8192 && 8192 + NOWN * KC * 2 <= MAXC * 16 && NOWN * KC + NOWN * 16 + NOWN * KSTAT <= MAXC * 16 && KSTAT <= KC,
               "the pair tables / candidate scratch lists are laid out inside the impulse array (cf4)");
 
@@ -260,13 +269,13 @@ __device__ __forceinline__ v3 brick_Iinv_mul(const float4 w0, const float4 w1, v
 // phase B's inner loop: lane k of a body's group of L lanes sums the impulses (and their moments about xb) of the incidences
 // e = k, k + L, k + 2 L, ... of that body -- owned contacts [a0, a0 + na) first, then the ascending target-side list at b0 --
 // strictly in that order (the oracle's Fk[k] / Tk[k]).
-__device__ __forceinline__ void gather_incident(const SimSmem& M, const float4* CA, int a0, int na, int b0, int ntot,
+__device__ __forceinline__ void gather_incident(const SimSmem& M, const float4* CA, const float4* CF, int a0, int na, int b0, int ntot,
                                                 int k, int L, v3 xb, v3* Fo, v3* To) {
   v3 F = V3(0.0f, 0.0f, 0.0f), T = V3(0.0f, 0.0f, 0.0f);
 #pragma unroll 1
   for (int ee = k; ee < ntot; ee += L) {
     const int idx = ee < na ? a0 + ee : (int)M.blist[b0 + (ee - na)];
-    const float4 F4 = M.cf4[idx], A4 = CA[idx];
+    const float4 F4 = CF[idx], A4 = CA[idx];
     v3 f = V3(F4.x, F4.y, F4.z);
     if (ee >= na) f = vneg(f);
     F = vadd(F, f);
@@ -370,7 +379,7 @@ __global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
            int* __restrict__ ncontact, float* __restrict__ condump, float* ws, int* wsn, int ws_cur,
-           unsigned char* __restrict__ slp, int n_envs, float4* cscratch /* [n_envs][2][MAXC] when SIM_GLOBAL_CONTACTS */) {
+           unsigned char* __restrict__ slp, int n_envs, float4* cscratch /* [n_envs][3][MAXC]: contact records (SIM_GLOBAL_CONTACTS), impulses (SIM_GLOBAL_CF) */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SimSmem& M = *reinterpret_cast<SimSmem*>(smem_raw);
   const int e = blockIdx.x, tid = threadIdx.x;
@@ -385,13 +394,18 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   float* gbrick = brick + (size_t)e * 13 * NB;
   float* gdof = dof + (size_t)e * 72;
 #if SIM_GLOBAL_CONTACTS
-  float4* const CA = cscratch + (size_t)e * 2 * MAXC;   // plain (coherent, L1-cached) loads / stores: written and read by this CTA only
+  float4* const CA = cscratch + (size_t)e * 3 * MAXC;   // plain (coherent, L1-cached) loads / stores: written and read by this CTA only
   float4* const CB = CA + MAXC;
 #else
   float4* const CA = M.ca;
   float4* const CB = M.cb;
 #endif
-  unsigned char* const cf_bytes = reinterpret_cast<unsigned char*>(&M.cf4[0]);   // 16 KB of scratch while the impulses are not live
+#if SIM_GLOBAL_CF
+  float4* const CF = cscratch + (size_t)e * 3 * MAXC + 2 * MAXC;
+#else
+  float4* const CF = M.cf4;
+#endif
+  unsigned char* const cf_bytes = reinterpret_cast<unsigned char*>(CF);   // 16 KB of scratch while the impulses are not live
 
   // ---- TMA bulk load of the env's brick tile into shared memory
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&M.mbar);
@@ -554,7 +568,8 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       int* tmpn = reinterpret_cast<int*>(cf_bytes + NOWN * KC);             // [NOWN][4]     all dynamic hits of half 0 | half 1 | statics kept | statics seen
       unsigned char* tmps = cf_bytes + NOWN * KC + NOWN * 16;               // [NOWN][KSTAT] static hits
       if (tid == 0) { M.ndrop_cand = 0; M.ndrop_static = 0; }
-      const int a = tid & 127, half = tid >> 7;
+      const int a = tid & 127;
+      for (int half = tid >> 7; half < 2; half += SIM_THREADS >> 7)   // 256 threads: one (owner, half) each; 128 threads: both halves in turn
       if (a < n_owner) {
         int k = 0, kall = 0, ks = 0, ksall = 0;
         if (!(a < NB && a >= nbr)) {
@@ -731,7 +746,7 @@ SIM_BROAD_UNROLL
               else { dir = 2; mid = (lo2 + hi2) >> 1; }
             }
           }
-          M.cf4[slot] = make_float4(f0.x, f0.y, f0.z, 0.0f);
+          CF[slot] = make_float4(f0.x, f0.y, f0.z, 0.0f);
         }
       }
     }
@@ -878,7 +893,7 @@ SIM_BROAD_UNROLL
     for (int it = -1; it < iters; ++it) {                      // it = -1: phase B only = apply the warm-start impulses
       if (it >= 0)
       for (int i = tid; i < ncon; i += SIM_THREADS) {          // phase A: one thread per contact
-        const float4 A4 = CA[i], B4 = CB[i], F4 = M.cf4[i];
+        const float4 A4 = CA[i], B4 = CB[i], F4 = CF[i];
         uint32_t wd = __float_as_uint(B4.w);
         int a = wd & 255, b = (wd >> 8) & 255;
         v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
@@ -892,7 +907,7 @@ SIM_BROAD_UNROLL
         float l1 = clampf(fmaf(-vdot(vrel, t1), B4.y, vdot(f, t1)), -lim, lim);
         float l2 = clampf(fmaf(-vdot(vrel, t2), B4.z, vdot(f, t2)), -lim, lim);
         f = vmad(t2, l2, vmad(t1, l1, vscale(n, ln)));
-        M.cf4[i] = make_float4(f.x, f.y, f.z, 0.0f);
+        CF[i] = make_float4(f.x, f.y, f.z, 0.0f);
       }
 #ifdef SIM_PROFILE
       if (prof && (tid & 31) == 0) prof[((it + 1) * 2 + 0) * 8 + (tid >> 5)] = clock64();
@@ -913,7 +928,7 @@ SIM_BROAD_UNROLL
           const int4 r = M.irec[live ? (int)M.lmap[p] : 0];
           const int body = live ? r.w & 255 : 0, lg = live ? (r.w >> 20) & 7 : 0, L = 1 << lg, k = p & (L - 1);
           v3 F, T;
-          gather_incident(M, CA, r.x, r.y, r.z, live ? (r.w >> 8) & 4095 : 0, k, L, ld3(M.bx[body]), &F, &T);
+          gather_incident(M, CA, CF, r.x, r.y, r.z, live ? (r.w >> 8) & 4095 : 0, k, L, ld3(M.bx[body]), &F, &T);
           const int steps = __reduce_max_sync(0xffffffffu, lg);             // butterfly over the group: p[k] += p[k ^ o], o = 1, 2, 4 ...
 #pragma unroll 1
           for (int o = 1; o < (1 << steps); o <<= 1) {
@@ -936,7 +951,7 @@ SIM_BROAD_UNROLL
           const int body = NB + (live ? (int)__fns(ract, 0, (item >> 1) + 1) : 0);
           const int a0 = M.astart[body], na = M.aend[body] - a0, b0 = M.boff[body], ntot = live ? na + (M.boff[body + 1] - b0) : 0;
           v3 F, T;
-          gather_incident(M, CA, a0, na, b0, ntot, item & 1, 2, V3(0.0f, 0.0f, 0.0f), &F, &T);
+          gather_incident(M, CA, CF, a0, na, b0, ntot, item & 1, 2, V3(0.0f, 0.0f, 0.0f), &F, &T);
           F.x += __shfl_xor_sync(0xffffffffu, F.x, 1); F.y += __shfl_xor_sync(0xffffffffu, F.y, 1); F.z += __shfl_xor_sync(0xffffffffu, F.z, 1);
           T.x += __shfl_xor_sync(0xffffffffu, T.x, 1); T.y += __shfl_xor_sync(0xffffffffu, T.y, 1); T.z += __shfl_xor_sync(0xffffffffu, T.z, 1);
           if (!(item & 1) && live) { st3(M.linkF[body - NB], F); st3(M.linkM[body - NB], T); }
@@ -966,7 +981,7 @@ SIM_BROAD_UNROLL
       PMARK(8); PMARK(9);
     }
     PMARK(10);
-    for (int i = tid; i < ncon; i += SIM_THREADS) { const float4 F4 = M.cf4[i]; wsw[4 * i + 1] = F4.x; wsw[4 * i + 2] = F4.y; wsw[4 * i + 3] = F4.z; }
+    for (int i = tid; i < ncon; i += SIM_THREADS) { const float4 F4 = CF[i]; wsw[4 * i + 1] = F4.x; wsw[4 * i + 2] = F4.y; wsw[4 * i + 3] = F4.z; }
     if (tid == 0) gwsn[1 - rb] = ncon;
     rb = 1 - rb;
     if (iters == 0 && tid < SDX_NL) { st3(M.linkF[tid], V3(0, 0, 0)); st3(M.linkM[tid], V3(0, 0, 0)); }

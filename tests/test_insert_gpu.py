@@ -140,13 +140,14 @@ def test_insert_whole_episodes_bit_exact(iscene, oracle_lib, n):
     hand, obj = synthetic_grasp_bank(iscene, 3, seed=5)
     g.set_grasp_bank(hand, obj); o.set_grasp_bank(hand, obj)
     rng = np.random.default_rng(7)
-    resets = 0
+    resets, yaws = 0, set()
     for t in range(140):
         a = rng.uniform(-1, 1, size=(n, 23)).astype(np.float32) * (0.3 if t % 50 < 25 else 1.0)
         g.step(torch.from_numpy(a).cuda()); o.step(a)
         resets += int(o.reset.sum())
+        yaws |= set(np.unique(o.plate[:, 5]).tolist())
         if t % 10 == 9 or t < 3:
             _all(g, o, f"step {t}")
     _all(g, o, "end")
     assert resets >= n and np.isfinite(o.brick[:, :, :8]).all()
-    assert len(np.unique(o.plate[:, 5])) == 2, "both base-plate yaws must occur"
+    assert len(yaws) == 2, "both base-plate yaws must occur over the run"

@@ -27,6 +27,11 @@ def timeit(fn, iters=20):
 
 
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+ONCE = "--once" in sys.argv       # one launch per shape and library (for an ncu capture of every variant): no timing loop
+if ONCE:
+    def timeit(fn, iters=1):      # noqa: F811
+        flush.zero_(); fn(); torch.cuda.synchronize()
+        return 1.0
 print(f"{'shape':34s} {'mode':>4s} {'ours us':>9s} {'TF/s':>7s} {'cublas us':>10s} {'TF/s':>7s}")
 for (N, K, mode, name) in [(1024, 448, 0, "fwd L1"), (512, 1024, 0, "fwd L2"), (256, 512, 0, "fwd L3"), (1024, 512, 1, "dX L2"), (512, 256, 1, "dX L3"),
                            (1024, 448, 3, "plain")]:
