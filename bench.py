@@ -26,10 +26,10 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = 15956   # algorithmic HBM bytes / env-step (fp32 rollout)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_simulate launch at 16 384 envs, from the committed ncu --set full capture
-# (profiles/r01_ncu_k_simulate_v11_16384envs.txt: 127.1 MB read + 282.1 MB written; the writes include the contact records that
+# (profiles/r02_ncu_k_simulate_16384envs.txt: 128.2 MB read + 290.4 MB written; the writes include the contact records that
 # live in global memory behind L1 since SIM_GLOBAL_CONTACTS and the warm-start impulse cache)
-NCU_TRAFFIC_BYTES_PER_ENV = (127.127296e6 + 282.132224e6) / 16384
-NCU_ISSUE_ACTIVE = 0.5068            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
+NCU_TRAFFIC_BYTES_PER_ENV = (128.228608e6 + 290.438656e6) / 16384
+NCU_ISSUE_ACTIVE = 0.5224            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
 ALGO_FLOP_PER_ENV_STEP = 1.48e6      # counted fp32 work of the contact step in this episode mix (oracle counters)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # B200: 148 SMs x 128 fp32 lanes x 2 (FMA) x 1.965 GHz
 
@@ -294,6 +294,7 @@ def main():
     ap.add_argument("--bank-per-type", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sleep-off", action="store_true", help="skip the extra rollout with sleeping switched off (reported beside the default)")
     ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
                     help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
                          "rollout: VecTask.step only with U(-1,1) actions")
@@ -468,6 +469,33 @@ def main():
     e2e_ms = g0.elapsed_time(g1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # ---- what the solver costs on a LIVE heap: the same rollout with sleeping switched off (PhysX's sleeping is on by default and so is
+    #      ours; this number is reported beside the default so the reader sees what the mechanism saves) -- untimed set-up, rank 0 only
+    sleep_off = None
+    if rank == 0 and args.task == "grasp_sim" and not args.no_sleep_off:
+        scene2 = scene_from_cfg(task_name, sleep_time=0.0)
+        env2 = SdxEnv(scene2, n, local, seed=22 + rank)
+        env2.set_heap_bank(bank)
+        env2.set_tvalue_weights(default_tvalue_weights(22))
+        env2.step(acts[0])
+        env2.tensor("PROGRESS").copy_(torch.randint(0, STAGGER, (n,), device=dev, generator=gen))
+        for i in range(PRE_STEPS):
+            env2.step(torch.rand(n, 23, device=dev, generator=gen) * 2 - 1)
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(16)]
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(16):
+            env2.pre_physics(acts[W + i % K])
+            ev2[i][0].record(); env2.simulate(); ev2[i][1].record()
+            env2.post_physics()
+        s1.record()
+        torch.cuda.synchronize()
+        nc2 = env2.tensor("NCONTACT").cpu().numpy()
+        sleep_off = {"k_simulate_ms_per_launch": float(np.mean([a.elapsed_time(b) for a, b in ev2])),
+                     "rollout_env_steps_per_s": n * 16 / (s0.elapsed_time(s1) * 1e-3), "contacts_per_env_mean": float(nc2[:, 0].mean()),
+                     "envs_shedding_frac": float((nc2[:, 2] > 0).mean()), "dropped_max": int(nc2[:, 1].max()),
+                     "note": "rank 0, same episode mix and bank, Scene(sleep_time=0): no brick ever sleeps"}
+        env2.close()
     tms = torch.tensor([ms, e2e_ms, sim_ms, ro_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -491,7 +519,7 @@ def main():
             "ppo": ppo_info,
             "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": NCU_TRAFFIC_BYTES_PER_ENV * n,
-                         "traffic_source": "ncu --set full at 16384 envs, profiles/r01_ncu_k_simulate_v11_16384envs.txt (scaled by envs per launch)",
+                         "traffic_source": "ncu --set full at 16384 envs, profiles/r02_ncu_k_simulate_16384envs.txt (scaled by envs per launch)",
                          "issue_slots_busy_ncu": NCU_ISSUE_ACTIVE,
                          "fp32_alu": {"algorithmic_flop_per_env_step": ALGO_FLOP_PER_ENV_STEP, "peak_tflops": FP32_PEAK_TFLOPS,
                                       "achieved_tflops": ALGO_FLOP_PER_ENV_STEP * n / (sim_ms * 1e-3) / 1e12,
@@ -499,8 +527,9 @@ def main():
                                       "note": "GraspSim mix; neither roofline bounds the kernel (DESIGN.md sections 6, 11)"},
                          "ms_per_launch": sim_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
-                         "note": "state-streaming bound is loose: the kernel is bound by block-barrier waits between ~40 phases per sub-step "
-                                 "(45 % of warp stall samples, DESIGN.md section 11), not by HBM"},
+                         "note": "state-streaming bound is loose: the kernel is instruction- and latency-bound (2.6 G warp-instructions per launch = 2.2 ms "
+                                 "at full issue rate; issue slots 52 % busy, LSU data pipe 56 %, 29 % of shared-memory wavefronts are bank-conflict "
+                                 "replays; DESIGN.md section 11), not HBM-bound"},
             "roofline_tensor": None,
             "clocks": sampler.summary(),
             "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "table": 1024,
@@ -513,6 +542,7 @@ def main():
                                  "note": "last step of the run, over all envs of rank 0; shed level 1/2/3 = speculative range halved / quartered / "
                                          "touching contacts only (csrc/sdx_sim.cuh); statics claim candidate slots first"},
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
+            "sleep_off": sleep_off,
         }
         if args.mode == "ppo" and args.task == "grasp_sim" and ppo_info.get("ppo_ms_per_iteration", 0) > 0:
             tpeak, tsrc = measured_tensor_peak()
