@@ -261,6 +261,12 @@ int sdx_mlp_convert_batch_env_major(sdx_mlp_t* m, const float* x_dev, int B, int
                                     void* xt_bf16, void* stream);
 int sdx_mlp_forward_pre(sdx_mlp_t* m, const void* xb_bf16, const void* xt_bf16, int B, int row0, int M, int train, void* stream);
 int sdx_mlp_backward(sdx_mlp_t* m, const float* dout_dev, int M, void* stream);
+/* the same gradients published LAYER BY LAYER (output layer first): layer l's slice of the flat gradient vector is final right after its dW
+ * GEMM, an event marks it, and sdx_mlp_wait_layer lets another stream wait for it -- the data-parallel caller all-reduces layer l over NCCL
+ * while the layers below are still being differentiated (rl_games' multi_gpu path all-reduces after the whole backward, RGC:1860-1870) */
+int sdx_mlp_backward_pipelined(sdx_mlp_t* m, const float* dout_dev, int M, void* stream);
+int sdx_mlp_wait_layer(sdx_mlp_t* m, int layer, void* waiting_stream);
+int sdx_mlp_layer_range(sdx_mlp_t* m, int layer, int64_t* begin, int64_t* end);
 int sdx_mlp_adam(sdx_mlp_t* m, float lr, float b1, float b2, float eps, float max_norm, void* stream);   /* RGC:1102, 1866-1872 */
 /* same step with the learning rate read from device memory when the kernel runs (no host round trip for the adaptive schedule) */
 int sdx_mlp_adam_dev(sdx_mlp_t* m, const float* lr_dev, float b1, float b2, float eps, float max_norm, void* stream);

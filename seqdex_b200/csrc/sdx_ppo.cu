@@ -155,6 +155,8 @@ struct sdx_mlp {
   __nv_bfloat16 *W[4], *Wt[4], *A[4], *At[4], *dZ[5], *dZt[5];
   const __nv_bfloat16 *a0, *at0; int ldt0;   // layer-0 input of the last forward (own staging buffers or a caller-converted batch)
   long long adam_t;
+  cudaEvent_t layer_done[4];   // recorded when layer l's gradient slice is complete in `grads` (pipelined all-reduce, sdx_mlp_backward_pipelined)
+  int pipelined;                // last backward ran pipelined: per-layer unpack already done
 };
 static inline int pad64(int x) { return (x + 63) / 64 * 64; }
 
@@ -305,6 +307,7 @@ extern "C" int sdx_mlp_create_ex(int in_dim, int out_dim, int h1, int h2, int h3
     PCK(cudaMalloc(&m->dZ[l + 1], R * Npad * 2)); PCK(cudaMemset(m->dZ[l + 1], 0, R * Npad * 2));
     PCK(cudaMalloc(&m->dZt[l + 1], (size_t)Npad * R * 2)); PCK(cudaMemset(m->dZt[l + 1], 0, (size_t)Npad * R * 2));
   }
+  for (int l = 0; l < 4; ++l) PCK(cudaEventCreateWithFlags(&m->layer_done[l], cudaEventDisableTiming));
   PCK(cudaDeviceSynchronize());
   *out = m;
   return 0;
@@ -315,6 +318,7 @@ extern "C" int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sig
 extern "C" void sdx_mlp_destroy(sdx_mlp* m) {
   if (!m) return;
   cudaFree(m->params); cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->out); cudaFree(m->scal);
+  for (int l = 0; l < 4; ++l) cudaEventDestroy(m->layer_done[l]);
   for (int l = 0; l < 4; ++l) { cudaFree(m->W[l]); cudaFree(m->Wt[l]); cudaFree(m->A[l]); cudaFree(m->At[l]); cudaFree(m->gW[l]); cudaFree(m->dZ[l + 1]); cudaFree(m->dZt[l + 1]); }
   delete m;
 }
@@ -395,7 +399,7 @@ extern "C" int sdx_mlp_forward_pre(sdx_mlp* m, const void* xb, const void* xt, i
   return mlp_forward_core(m, M, train, stream);
 }
 // dout: fp32 [M, out_dim] = dLoss/d(out).  Fills m->grads (W and b of every layer; sigma is the loss kernel's job).
-extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stream) {
+static int mlp_backward(sdx_mlp* m, const float* dout, int M, void* stream, int pipelined) {
   if (M > m->max_rows || M <= 0) { sdx_set_error("sdx_mlp_backward: M exceeds max_rows"); return -1; }
   cudaStream_t st = (cudaStream_t)stream;
   int opad = pad64(m->out_dim);
@@ -410,19 +414,42 @@ extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stre
     int splits = 296 / tiles; if (splits < 1) splits = 1;   // two tiles per persistent CTA: the second one's main loop hides the first one's reduction epilogue
     if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, l == 0 ? (const void*)m->at0 : (const void*)m->At[l], K + 16, l == 0 ? m->ldt0 : m->max_rows, nullptr, nullptr, 0,
                          nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
+    if (pipelined) {   // this layer's slice of the flat gradient vector is final NOW: publish it before the layers below are differentiated
+      const int kreal = l == 0 ? m->in_dim : m->d[l];
+      const int tot = N * (kreal + 1);
+      k_unpack_grads<<<(tot + 255) / 256, 256, 0, st>>>(m->gW[l], N, kreal, m->d[l], ldg, m->grads + m->w_off[l], m->grads + m->b_off[l]);
+      g_ppo_launches++;
+      PCK(cudaEventRecord(m->layer_done[l], st));
+    }
     if (l > 0) {
       int Kd = pad64(N);
       if (sdx_gemm_bf16_tn(1, m->dZ[l + 1], M, Kd, Kd, m->Wt[l], K, Kd, nullptr, m->A[l], K, m->dZ[l], K, m->dZt[l], m->max_rows, nullptr, 0, 1, stream)) return -1;
     }
   }
-  {
+  if (!pipelined) {
     int mx = 0;
     for (int l = 0; l < 4; ++l) { int a = m->d[l + 1] * ((l == 0 ? m->in_dim : m->d[l]) + 1); mx = a > mx ? a : mx; }
-    dim3 grd((mx + 255) / 256, 4);
-    k_unpack_all<<<grd, 256, 0, st>>>(make_tab(m));
+    dim3 grd2((mx + 255) / 256, 4);
+    k_unpack_all<<<grd2, 256, 0, st>>>(make_tab(m));
     g_ppo_launches++;
   }
   PCK(cudaGetLastError());
+  return 0;
+}
+extern "C" int sdx_mlp_backward(sdx_mlp* m, const float* dout, int M, void* stream) { return mlp_backward(m, dout, M, stream, 0); }
+/* same gradients, published layer by layer: layer l's slice of the flat gradient vector [w_off[l], b_off[l] + rows) is written right
+ * after its dW GEMM and an event is recorded, so a data-parallel caller can all-reduce layer l while layers l-1 .. 0 are still being
+ * differentiated (sdx_mlp_wait_layer makes another stream wait for that event) */
+extern "C" int sdx_mlp_backward_pipelined(sdx_mlp* m, const float* dout, int M, void* stream) { return mlp_backward(m, dout, M, stream, 1); }
+extern "C" int sdx_mlp_wait_layer(sdx_mlp* m, int layer, void* waiting_stream) {
+  if (layer < 0 || layer > 3) { sdx_set_error("sdx_mlp_wait_layer: layer out of range"); return -1; }
+  PCK(cudaStreamWaitEvent((cudaStream_t)waiting_stream, m->layer_done[layer], 0));
+  return 0;
+}
+/* element range [begin, end) of layer l's gradients (weights then bias) in the flat vector */
+extern "C" int sdx_mlp_layer_range(sdx_mlp* m, int layer, int64_t* begin, int64_t* end) {
+  if (layer < 0 || layer > 3) { sdx_set_error("sdx_mlp_layer_range: layer out of range"); return -1; }
+  *begin = (int64_t)m->w_off[layer]; *end = (int64_t)(m->b_off[layer] + m->d[layer + 1]);
   return 0;
 }
 /* optimiser step counter (the `step` of torch.optim.Adam's state): read with set < 0, overwritten otherwise (checkpoint restore) */

@@ -133,6 +133,20 @@ class MLP:
         assert dout.is_contiguous() and dout.dtype == torch.float32
         _lib.check(self.L.sdx_mlp_backward(self.h, _p(dout), dout.shape[0], _stream()))
 
+    def backward_pipelined(self, dout):
+        """same gradients, published layer by layer (output layer first) with an event per layer: see ``wait_layer``"""
+        assert dout.is_contiguous() and dout.dtype == torch.float32
+        _lib.check(self.L.sdx_mlp_backward_pipelined(self.h, _p(dout), dout.shape[0], _stream()))
+
+    def wait_layer(self, layer, stream):
+        """make ``stream`` wait until layer ``layer``'s slice of ``grads`` is final (after the last backward_pipelined)"""
+        _lib.check(self.L.sdx_mlp_wait_layer(self.h, int(layer), ctypes.c_void_p(stream.cuda_stream)))
+
+    def layer_range(self, layer):
+        b, e = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(self.L.sdx_mlp_layer_range(self.h, int(layer), ctypes.byref(b), ctypes.byref(e)))
+        return int(b.value), int(e.value)
+
     def adam(self, lr, max_norm=1.0, b1=0.9, b2=0.999, eps=1e-8):
         _lib.check(self.L.sdx_mlp_adam(self.h, ctypes.c_float(lr), ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps),
                                        ctypes.c_float(max_norm), _stream()))
@@ -307,6 +321,36 @@ class A2CAgent:
             from .dist_utils import allreduce_
             allreduce_(t, self.dist, avg)
 
+    def _backward_and_allreduce(self, mlp, dout, tail=0):
+        """backward + gradient exchange.  One rank: plain backward.  Several: the backward publishes its gradients layer by layer
+        (output layer first) and each layer's slice is all-reduced -- on a communication stream that waits only for THAT layer's
+        event -- while the layers below are still being differentiated; the output layer's bucket carries everything behind it in
+        the flat vector (sigma and ``tail`` statistics floats, written by the loss kernel before the backward started).  The
+        compute stream waits for the communication stream before the optimiser step."""
+        if self.dist is None or self.world == 1:
+            mlp.backward(dout)
+            return
+        cur = torch.cuda.current_stream()
+        comm = self._comm_stream(cur)
+        mlp.backward_pipelined(dout)
+        end_all = mlp.nparams + tail
+        for layer in (3, 2, 1, 0):
+            b, e = mlp.layer_range(layer)
+            if layer == 3:
+                e = end_all       # sigma gradient / statistics: written by the loss kernel BEFORE the backward on `cur`, so layer 3's event covers them
+            mlp.wait_layer(layer, comm)
+            with torch.cuda.stream(comm):
+                self._allreduce(mlp.grads_ext[b:e])
+        cur.wait_stream(comm)
+
+    def _comm_stream(self, cur):
+        """one communication stream per compute stream (the actor and the central-value chains run on two streams)"""
+        d = self.__dict__.setdefault("_comm_streams", {})
+        k = cur.cuda_stream
+        if k not in d:
+            d[k] = torch.cuda.Stream(device=self.device)
+        return d[k]
+
     # ---- update (RGC:1621-1683, 1339-1375, 1767-1911)
     def train_epoch(self):
         self.play_steps()
@@ -356,8 +400,7 @@ class A2CAgent:
             v = self.cv.forward_pre(self.xb_st, self.xt_st, i * mb, mb)
             _lib.check(L.sdx_ppo_value_loss(_p(v), _p(values[s]), _p(returns[s]), mb, ctypes.c_float(c.e_clip), int(c.clip_value),
                                             ctypes.c_float(inv), _p(self.dv), _p(self.cv_stats), _stream()))
-            self.cv.backward(self.dv)
-            self._allreduce(self.cv.grads)
+            self._backward_and_allreduce(self.cv, self.dv)
             self.cv.adam(c.cv_learning_rate, c.grad_norm)
 
         def actor_step(i):
@@ -370,8 +413,7 @@ class A2CAgent:
                                             _p(self.stats), _stream()))
             mu_old[s].copy_(mu)                                  # dataset.update_mu_sigma (RGC:1358)
             self.old_logstd[i].copy_(self.logstd)
-            self.actor.backward(self.dmu)
-            self._allreduce(self.actor.grads_ext[:na + 4])       # gradients AND the minibatch statistics (KL averaged over ranks, RGC:1361-1362)
+            self._backward_and_allreduce(self.actor, self.dmu, tail=4)   # gradients AND the minibatch statistics (KL averaged over ranks, RGC:1361-1362)
             self.actor.adam_dev(self.lr_dev, c.grad_norm)
             _lib.check(L.sdx_ppo_adaptive_lr(_p(self.stats), ctypes.c_float(inv), ctypes.c_float(c.kl_threshold), ctypes.c_float(LR_MIN),
                                              ctypes.c_float(LR_MAX), _p(self.lr_dev), _p(self.accum), int(c.lr_schedule == "adaptive"), _stream()))
