@@ -185,6 +185,10 @@ class PPOConfig:
         self.kl_threshold, self.bounds_loss_coef = 0.02, 0.001
         self.normalize_advantage, self.cv_normalize_input = True, True
         self.lr_schedule = "adaptive"
+        # data parallel: all-reduce each layer's gradients as soon as its dW GEMM retires (overlapping the layers below) instead of one
+        # exchange after the whole backward.  MEASURED SLOWER at these sizes (2 x B200: 7.38 vs 7.22 ms/step -- four latency-bound NCCL
+        # launches of <= 2 MB instead of one of 8.5 MB), so it is off by default (profiles/r02_allreduce_pipelining.txt)
+        self.pipeline_allreduce = False
         self.seed = 22
         for k, v in kw.items():
             if not hasattr(self, k):
@@ -329,6 +333,10 @@ class A2CAgent:
         compute stream waits for the communication stream before the optimiser step."""
         if self.dist is None or self.world == 1:
             mlp.backward(dout)
+            return
+        if not self.cfg.pipeline_allreduce:
+            mlp.backward(dout)
+            self._allreduce(mlp.grads_ext[:mlp.nparams + tail])
             return
         cur = torch.cuda.current_stream()
         comm = self._comm_stream(cur)

@@ -264,3 +264,34 @@ def test_ppo_learns_on_the_cuda_env(scene):
     first, last = sum(rew[:15]) / 15, sum(rew[-15:]) / 15
     assert all(math.isfinite(r) for r in rew)
     assert last > 5.0 * first and last > 0.03, (first, last)
+
+
+def test_pipelined_backward_publishes_the_same_gradients_layer_by_layer():
+    """sdx_mlp_backward_pipelined (per-layer unpack + event, what the data-parallel agent all-reduces layer by layer) == sdx_mlp_backward;
+    a side stream that waits for layer l's event sees that layer's final slice while the layers below are still being differentiated"""
+    from seqdex_b200.ppo import MLP
+    torch.manual_seed(6)
+    m = MLP(396, 23, 2048, has_sigma=True, seed=4)
+    x = torch.randn(2048, 396, device="cuda")
+    dout = torch.randn(2048, 23, device="cuda") / 2048
+    m.forward(x, train=True)
+    m.backward(dout)
+    ref = m.grads.clone()
+    m.grads.zero_()
+    m.forward(x, train=True)
+    side = torch.cuda.Stream()
+    snap = {}
+    m.backward_pipelined(dout)
+    for layer in (3, 2, 1, 0):
+        b, e = m.layer_range(layer)
+        m.wait_layer(layer, side)
+        with torch.cuda.stream(side):
+            snap[layer] = (b, e, m.grads[b:e].clone())
+    torch.cuda.synchronize()
+    n = m.nparams - 23                       # sigma is the loss kernel's business
+    torch.testing.assert_close(m.grads[:n], ref[:n], rtol=1e-4, atol=1e-6)          # split-K atomics: order-dependent last bits
+    ends = []
+    for layer, (b, e, g) in snap.items():
+        torch.testing.assert_close(g, ref[b:e], rtol=1e-4, atol=1e-6)
+        ends.append((b, e))
+    assert sorted(ends)[0][0] == 0 and sorted(ends)[-1][1] == n and all(sorted(ends)[i][1] == sorted(ends)[i + 1][0] for i in range(3))
