@@ -291,7 +291,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--num-envs", type=int, default=16384, help="envs PER GPU (weak scaling)")
-    ap.add_argument("--bank-per-type", type=int, default=64)
+    ap.add_argument("--bank-per-type", type=int, default=5000,
+                    help="settled heaps per brick type in the bank reset_idx samples: the reference samples rows [0, 5000) of its pickle (GS:1508)")
     ap.add_argument("--e2e-steps", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sleep-off", action="store_true", help="skip the extra rollout with sleeping switched off (reported beside the default)")
@@ -335,7 +336,7 @@ def main():
     env = SdxEnv(scene, n, local, seed=22 + rank)
     if insert:                                      # InsertSim restores banked grasps (IS:372-375): synthetic stand-ins here, GraspSim's rings in --task chain
         from seqdex_b200.tasks.block_assembly_insert_sim import synthetic_grasp_bank
-        bank = synthetic_grasp_bank(scene, args.bank_per_type, seed=22 + rank)
+        bank = synthetic_grasp_bank(scene, min(args.bank_per_type, 64), seed=22 + rank)
         env.set_grasp_bank(*bank)
     elif search:                                      # Search resets from the drop lattice and renders its overview camera
         from seqdex_b200.camera import SEARCH_CAMERA, look_at
