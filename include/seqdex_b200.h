@@ -69,6 +69,12 @@ typedef struct sdx_scene_t {
   float insert_plate_zw[2];   /* InsertSim: (z, w) of gymapi.Quat.from_euler_zyx(0, 0, 1.57), the base-plate's second yaw (IS:1436-1437) */
   int st_mod[SDX_MAX_STATIC], st_rem[SDX_MAX_STATIC];   /* static s exists only in envs with env % st_mod == st_rem (st_mod 0: in every env);
                                                             InsertSim's base-plate is 4x4x{1,2,4} by env % 3 (IS:971-977) */
+  /* COMPOUND free bodies: body b (n_bricks of them: state, mass, inertia) is the union of the collision boxes a with bs_body[a] == b
+   * (n_bshapes boxes, those of one body consecutive; half extents br_half[a], centre bs_c[a] in the body's COM frame, axes = the body's).
+   * n_bshapes == 0 (every BlockAssembly scene): each body is ONE box -- n_bricks boxes, box a = body a, centred on its COM. */
+  int n_bshapes;
+  int bs_body[SDX_MAX_BRICKS];
+  float bs_c[SDX_MAX_BRICKS * 3];
 } sdx_scene_t;
 
 /* tasks sharing the scene, the contact step and the PPO engine (SURVEY.md section 8a "per-task dimensions"):

@@ -73,6 +73,9 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   float prepare_dof[SDX_ND];  /* Search: arm_hand_prepare_dof_pos_list[0], where an episode starts (SE:220-223, 316) */
   float insert_plate_zw[2];   /* InsertSim: (z, w) of gymapi.Quat.from_euler_zyx(0, 0, 1.57), the base-plate's second yaw (IS:1436-1437) */
   int st_mod[SDX_MAX_STATIC], st_rem[SDX_MAX_STATIC];   /* static s exists only in envs with env % st_mod == st_rem (st_mod 0: everywhere) */
+  int n_bshapes;                       /* collision boxes of the free bodies; 0 = every body is one box (n_bricks boxes, box a = body a) */
+  int bs_body[SDX_MAX_BRICKS];         /* box -> body; boxes of one body are consecutive */
+  float bs_c[SDX_MAX_BRICKS * 3];      /* box centre in its body's COM frame (axes = the body's) */
 } sdx_scene_t;
 #define ORIENT_OBS_FRAME 62
 #define ORIENT_BANK_WRAP 10000
@@ -241,6 +244,7 @@ typedef struct {
   v3 linkF[SDX_NL], linkM[SDX_NL];
   uint32_t ckey[SDX_MAX_CONTACTS];
   unsigned char asleep[NB], hot[NB], touch[NB];   /* sleeping (see sim_env): touch bit0 = robot, bit1 = hot brick */
+  float brad[NB];   /* bounding radius of a free body about its COM: max over its boxes of |centre| + half diagonal */
   unsigned char built_asleep[NB]; int cand_dropped, cand_dropped_static; /* candidate lists are kept over the sub-steps of a step (see sim_env 3.) */
   int shed_level;   /* most speculative-contact shedding any sub-step of the step needed (0 = none) */
 } work_t;
@@ -342,12 +346,22 @@ void sdxo_reuse_stats(long out[5]) { for (int i = 0; i < 5; ++i) out[i] = g_reus
 
 static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_out, float* jac7, float* netf,
                     int* ncontact, float* condump, float* ws, int* wsn, int ws_cur, unsigned char* slp, work_t* W, int env) {
-  const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;
+  const int nbr = S->n_bricks, nbs = S->n_bshapes > 0 ? S->n_bshapes : S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;   /* bodies | their boxes (a body may be a compound of boxes) */
   const int n_owner = NB + nrs, n_target = NB + nrs + nst;
   const float h = S->dt / (float)S->substeps;
   const float margin = S->contact_offset;
   const float fmargin = S->face_margin;   /* how far beyond the edge of the reference face a sample point still counts as over it */
   W->shed_level = 0;
+  for (int b = 0; b < NB; ++b) {
+    float r = 0.0f;
+    for (int a = 0; a < nbs; ++a)
+      if (S->bs_body[a] == b) {
+        v3 c = V3(S->bs_c[3 * a], S->bs_c[3 * a + 1], S->bs_c[3 * a + 2]), hh = V3(S->br_half[3 * a], S->br_half[3 * a + 1], S->br_half[3 * a + 2]);
+        float cand = sqrtf(vdot(c, c)) + sqrtf(vdot(hh, hh));
+        if (cand > r) r = cand;
+      }
+    W->brad[b] = r;
+  }
   for (int b = 0; b < NB; ++b) {
     W->bx[b] = V3(brick[0 * NB + b], brick[1 * NB + b], brick[2 * NB + b]);
     W->bq[b].x = brick[3 * NB + b]; W->bq[b].y = brick[4 * NB + b]; W->bq[b].z = brick[5 * NB + b]; W->bq[b].w = brick[6 * NB + b];
@@ -378,13 +392,14 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     /* 1. kinematics + shape poses */
     robot_fk(S, W->q, &W->K);
     for (int L = 0; L < SDX_NL; ++L) { W->bx[NB + L] = W->K.lx[L]; W->bq[NB + L] = W->K.lq[L]; qmat(W->K.lq[L], W->bR[NB + L]); }
-    for (int b = 0; b < NB; ++b) {
-      qmat(W->bq[b], W->bR[b]);
-      W->sc[b] = W->bx[b];
-      for (int i = 0; i < 9; ++i) W->sR[b][i] = W->bR[b][i];
-      W->sh[b] = V3(S->br_half[3 * b], S->br_half[3 * b + 1], S->br_half[3 * b + 2]);
-      W->srad[b] = sqrtf(vdot(W->sh[b], W->sh[b]));
-      W->sbody[b] = b;
+    for (int b = 0; b < NB; ++b) qmat(W->bq[b], W->bR[b]);
+    for (int a = 0; a < NB; ++a) {          /* boxes of the free bodies: box a rides on body bs_body[a] at bs_c[a] in that body's COM frame */
+      const int b = a < nbs ? S->bs_body[a] : a;
+      W->sc[a] = a < nbs ? vadd(W->bx[b], mmul(W->bR[b], V3(S->bs_c[3 * a], S->bs_c[3 * a + 1], S->bs_c[3 * a + 2]))) : W->bx[b];
+      for (int i = 0; i < 9; ++i) W->sR[a][i] = W->bR[b][i];
+      W->sh[a] = V3(S->br_half[3 * a], S->br_half[3 * a + 1], S->br_half[3 * a + 2]);
+      W->srad[a] = sqrtf(vdot(W->sh[a], W->sh[a]));
+      W->sbody[a] = b;
     }
     for (int r = 0; r < nrs; ++r) {
       int t = NB + r, L = S->rs_body[r];
@@ -450,12 +465,11 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       for (int a = 0; a < n_owner; ++a) {
         unsigned char dyn[KC], sta[KC];
         int nd = 0, nd_all = 0, ns = 0, ns_all = 0;
-        if (a < NB && a >= nbr) { W->ncand[a] = 0; continue; }
+        if (a < NB && a >= nbs) { W->ncand[a] = 0; continue; }
         for (int t = 0; t < n_target; ++t) {
-          if (t == a) continue;
-          if (t < NB && t >= nbr) continue;
+          if (t < NB && (t >= nbs || (a < NB && W->sbody[t] == W->sbody[a]))) continue;   /* no box, or a box of the same body */
           if (a >= NB && t >= NB && t < NB + nrs) continue; /* robot-robot filtered (GS:906 filter -1) */
-          if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue; /* neither box can move */
+          if (a < NB && W->asleep[W->sbody[a]] && (t >= NB + nrs || (t < NB && W->asleep[W->sbody[t]]))) continue; /* neither box can move */
           v3 d = vsub(W->sc[a], W->sc[t]);
           float m = margin + infl * (W->spd[a] + W->spd[t]) + slack;
           int hit = fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
@@ -474,10 +488,10 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
     }
     if (g_reuse_audit) {   /* test hook: what would a fresh broad phase of THIS sub-step list, and is it in the lists in use? */
       for (int a = 0; a < n_owner; ++a) {
-        if (a < NB && a >= nbr) continue;
+        if (a < NB && a >= nbs) continue;
         for (int t = 0; t < n_target; ++t) {
-          if (t == a || (t < NB && t >= nbr) || (a >= NB && t >= NB && t < NB + nrs)) continue;
-          if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue;
+          if ((t < NB && (t >= nbs || (a < NB && W->sbody[t] == W->sbody[a]))) || (a >= NB && t >= NB && t < NB + nrs)) continue;
+          if (a < NB && W->asleep[W->sbody[a]] && (t >= NB + nrs || (t < NB && W->asleep[W->sbody[t]]))) continue;
           v3 d = vsub(W->sc[a], W->sc[t]);
           float m = margin + W->spd[a] + W->spd[t];
           if (!(fabsf(d.x) <= W->sa[a].x + W->sa[t].x + m && fabsf(d.y) <= W->sa[a].y + W->sa[t].y + m &&
@@ -503,7 +517,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       int npts = (a < NB && W->sh[a].x > 0.04f) ? 12 : 8; /* long bricks add 4 mid-edge points */
       for (int ci = 0; ci < W->ncand[a]; ++ci) {
         int t = W->cand[a][ci];
-        if (a < NB && W->asleep[a] && (t >= NB + nrs || (t < NB && W->asleep[t]))) continue; /* kept list, both asleep by now */
+        if (a < NB && W->asleep[W->sbody[a]] && (t >= NB + nrs || (t < NB && W->asleep[W->sbody[t]]))) continue; /* kept list, both asleep by now */
         float m = (margin + W->spd[a] + W->spd[t]) * gs;
         v3 lc = mtmul(W->sR[t], vsub(W->sc[a], W->sc[t]));
         float C[9]; /* C = R_t^T R_a */
@@ -681,7 +695,7 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
       float v2 = vdot(v, v), mv = S->max_lin_vel;
       if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); W->bv[b] = v; }
       {
-        float E = 0.5f * (vdot(v, v) + vdot(w, w) * (W->srad[b] * W->srad[b] * (1.0f / 3.0f)));
+        float E = 0.5f * (vdot(v, v) + vdot(w, w) * (W->brad[b] * W->brad[b] * (1.0f / 3.0f)));
         int c = slp[b];
         if ((W->touch[b] & 1) || E >= S->wake_energy) c = 0;
         else if ((W->touch[b] & 2) || E >= S->sleep_energy) c = 1;

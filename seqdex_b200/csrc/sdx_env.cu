@@ -109,6 +109,11 @@ static size_t dtype_size(int dt) { return dt == 1 ? 8 : (dt == 3 ? 1 : 4); }
 extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, uint64_t seed, sdx_env_t** out) {
   if (!scene || !out || num_envs <= 0) { g_err = "sdx_create: bad arguments"; return -1; }
   if (scene->n_static > KSTAT || scene->n_rshapes > SDX_MAX_RSHAPES || scene->n_bricks > NB) { g_err = "sdx_create: scene exceeds kernel tables"; return -1; }
+  if (scene->n_bshapes < 0 || scene->n_bshapes > NB) { g_err = "sdx_create: n_bshapes out of range"; return -1; }
+  for (int a = 0; a < scene->n_bshapes; ++a)
+    if (scene->bs_body[a] < 0 || scene->bs_body[a] >= scene->n_bricks || (a > 0 && scene->bs_body[a] < scene->bs_body[a - 1])) {
+      g_err = "sdx_create: bs_body must map every box to a body, the boxes of one body consecutive"; return -1;
+    }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "sdx_create: no CUDA device (this library has no CPU path)"; return -1; }
   CK(cudaSetDevice(device));
@@ -146,7 +151,8 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
 #if SIM_GLOBAL_CONTACTS
   CK(cudaMalloc(&E->cscratch, n * 3 * MAXC * sizeof(float4)));
 #endif
-  CK(cudaFuncSetAttribute(k_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
+  CK(cudaFuncSetAttribute(k_simulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
+  CK(cudaFuncSetAttribute(k_simulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
   *out = E;
   return sdx_reset_all(E);
 }
@@ -376,7 +382,8 @@ extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
 
 extern "C" int sdx_simulate(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
-  k_simulate<<<E->n, SIM_THREADS, sizeof(SimSmem), E->stream>>>(E->scene, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+  auto kern = E->host_scene.n_bshapes > 0 ? k_simulate<true> : k_simulate<false>;      // compound free bodies or one box per body
+  kern<<<E->n, SIM_THREADS, sizeof(SimSmem), E->stream>>>(E->scene, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
                                                               F(SDX_T_NETF), I32(SDX_T_NCONTACT),
                                                               E->dump_contacts ? F(SDX_T_CONTACTS) : nullptr, F(SDX_T_WS), I32(SDX_T_WSN),
                                                               E->ws_cur, (unsigned char*)E->buf[SDX_T_SLEEP], E->n, E->cscratch);

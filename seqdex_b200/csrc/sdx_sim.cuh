@@ -109,6 +109,7 @@ struct SimSmem {
   float4 bfw[NB];   // free angular velocity .xyz
   float4 bI0[NB];   // world-frame inverse inertia R diag(1/I) R^T: xx xy xz yy
   float4 bI1[NB];   //                                              yz zz
+  float4 bq[NB];    // COMPOUND scenes only: body orientation, read by the boxes that ride on the body
   int4 irec[NB];    // phase-B record of brick b (valid while it is awake and touched): a0 | na | b0 | b + (ntot << 8) + (log2 lanes << 20)
   float lq[SDX_NL][4], ja[SDX_ND][3], jo[SDX_ND][3];
   float q[SDX_ND + 1], qd[SDX_ND + 1], tgt[SDX_ND + 1], qdfree[SDX_ND + 1], ieff[SDX_ND + 1];
@@ -375,6 +376,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
   }
 }
 
+// CMP: the scene has COMPOUND free bodies (a body = several boxes, sdx_scene_t::n_bshapes > 0).  The one-box-per-body instantiation
+// (every BlockAssembly scene) is the code it always was: box index == body index.
+template <bool CMP>
 __global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
@@ -385,6 +389,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   const int e = blockIdx.x, tid = threadIdx.x;
   if (e >= n_envs) return;
   const int nbr = S->n_bricks, nrs = S->n_rshapes, nst = S->n_static;
+  const int nbs = CMP ? S->n_bshapes : nbr;          // collision boxes of the free bodies (CMP: box a rides on body bs_body[a])
   const int n_owner = NB + nrs, n_target = NB + nrs + nst;
   const int substeps = S->substeps, iters = S->iters;
   const float h = S->dt / (float)substeps;
@@ -441,6 +446,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   v3 bxr = V3(0, 0, 0), bvr = V3(0, 0, 0), bwr = V3(0, 0, 0);
   q4 bqr = Q4(0, 0, 0, 1);
   v3 halfb = V3(0, 0, 0);
+  float brad = 0.0f;                                             // bounding radius of this thread's body about its COM
   bool built_asleep = false;                                     // was this brick asleep when the candidate lists were built?
   int slpc = (tid < NB) ? (int)slp[(size_t)e * NB + tid] : 0;   // sub-steps since this brick was last hot (oracle: sim_env SLEEPING)
   const int sleep_n = S->sleep_substeps;
@@ -456,7 +462,17 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
     halfb = V3(S->br_half[3 * tid], S->br_half[3 * tid + 1], S->br_half[3 * tid + 2]);
     st3(M.sh[tid], halfb);
     M.srad[tid] = sqrtf(vdot(halfb, halfb));
-    M.sbody[tid] = (unsigned char)tid;
+    M.sbody[tid] = (unsigned char)(CMP && tid < nbs ? S->bs_body[tid] : tid);
+    brad = M.srad[tid];
+    if (CMP) {                                                   // bounding radius of body tid: max over its boxes of |centre| + half diagonal
+      brad = 0.0f;
+      for (int a = 0; a < nbs; ++a)
+        if (S->bs_body[a] == tid) {
+          const v3 c = V3(S->bs_c[3 * a], S->bs_c[3 * a + 1], S->bs_c[3 * a + 2]), hh = V3(S->br_half[3 * a], S->br_half[3 * a + 1], S->br_half[3 * a + 2]);
+          const float cand = sqrtf(vdot(c, c)) + sqrtf(vdot(hh, hh));
+          if (cand > brad) brad = cand;
+        }
+    }
   }
   if (tid < nrs) {
     int t = NB + tid;
@@ -494,8 +510,14 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       M.touch[tid] = 0;
       const float invm = asleep ? 0.0f : S->br_invm[tid];    // a sleeping brick is immovable for this sub-step
       const v3 invI = asleep ? V3(0.0f, 0.0f, 0.0f) : V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]);
-      qmat(bqr, M.sR[tid]);
-      st3(M.sc[tid], bxr); st3(M.bx[tid], bxr);
+      float Rb[9];
+      qmat(bqr, Rb);
+      if (!CMP) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M.sR[tid][i] = Rb[i];
+        st3(M.sc[tid], bxr);
+      } else M.bq[tid] = make_float4(bqr.x, bqr.y, bqr.z, bqr.w);
+      st3(M.bx[tid], bxr);
       float damp = 1.0f - h * S->brick_ang_damp;
       float ldamp = 1.0f - h * S->brick_lin_damp;
       v3 vfree = vscale(V3(bvr.x, bvr.y, bvr.z + h * S->gravity_z), ldamp);
@@ -504,10 +526,17 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       st3(M.bv[tid], vfree); st3(M.bw[tid], wfree);
       M.bfv[tid] = make_float4(vfree.x, vfree.y, vfree.z, invm);
       M.bfw[tid] = make_float4(wfree.x, wfree.y, wfree.z, 0.0f);
-      brick_world_invI(M.sR[tid], invI, &M.bI0[tid], &M.bI1[tid]);
+      brick_world_invI(Rb, invI, &M.bI0[tid], &M.bI1[tid]);
     }
     __syncthreads();
-    // 2. robot shape poses || implicit PD free joint velocities
+    // 2. robot shape poses || implicit PD free joint velocities (CMP: || the boxes of the compound bodies)
+    if (CMP && tid < NB) {
+      const int b = M.sbody[tid];
+      const float4 q4b = M.bq[b];
+      qmat(Q4(q4b.x, q4b.y, q4b.z, q4b.w), M.sR[tid]);
+      const v3 xb = ld3(M.bx[b]);
+      st3(M.sc[tid], tid < nbs ? vadd(xb, mmul(M.sR[tid], V3(S->bs_c[3 * tid], S->bs_c[3 * tid + 1], S->bs_c[3 * tid + 2]))) : xb);
+    }
     if (tid < nrs) {
       int t = NB + tid, L = S->rs_body[tid];
       q4 qL = Q4(M.lq[L][0], M.lq[L][1], M.lq[L][2], M.lq[L][3]);
@@ -572,10 +601,11 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       for (int half = tid >> 7; half < 2; half += SIM_THREADS >> 7)   // 256 threads: one (owner, half) each; 128 threads: both halves in turn
       if (a < n_owner) {
         int k = 0, kall = 0, ks = 0, ksall = 0;
-        if (!(a < NB && a >= nbr)) {
+        if (!(a < NB && a >= nbs)) {
           const v3 ca = ld3(M.sc[a]);
           const float4 A4 = M.sab[a];
-          const bool a_sl = a < NB && (M.sflag[a] & 1);
+          const int sba = M.sbody[a];
+          const bool a_sl = a < NB && (M.sflag[sba] & 1);
           const int tmid = n_target >> 1;                        // < NB + nrs: the statics all fall into the second half
           const int tlo = half ? tmid : 0, thi = half ? n_target : tmid;
           unsigned char* dst = half ? tmpc + a * KC : M.cand[a];
@@ -589,9 +619,9 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
           // the target index space is bricks [0, nbr) | robot shapes [NB, NB+nrs) | statics [NB+nrs, n_target): one loop per
           // class with the class-level filters hoisted (same ascending order as one sweep over t)
 SIM_BROAD_UNROLL
-          for (int t = max(tlo, 0); t < min(thi, nbr); ++t) {
-            if (t == a) continue;
-            if (a_sl && (M.sflag[t] & 1)) continue;              // neither box can move
+          for (int t = max(tlo, 0); t < min(thi, nbs); ++t) {
+            if (CMP ? (int)M.sbody[t] == sba : t == a) continue;   // itself (CMP: any box of the same body)
+            if (a_sl && (M.sflag[CMP ? (int)M.sbody[t] : t] & 1)) continue;              // neither box can move
             if (hit(t)) { if (k < KC) dst[k++] = (unsigned char)t; kall++; }
           }
           if (a < NB) {                                          // robot-robot pairs are filtered (GS:906)
@@ -654,7 +684,7 @@ SIM_BROAD_UNROLL
         float m = (margin + M.sab[a].w + M.sab[t].w) * gs;
         unsigned short mk = 0;
         PairGeom G;
-        const bool dead = !rebuild && a < NB && (M.sflag[a] & 1) && (t >= NB + nrs || (t < NB && (M.sflag[t] & 1)));   // kept list, both asleep by now
+        const bool dead = !rebuild && a < NB && (M.sflag[CMP ? (int)M.sbody[a] : a] & 1) && (t >= NB + nrs || (t < NB && (M.sflag[CMP ? (int)M.sbody[t] : t] & 1)));   // kept list, both asleep by now
         if (!dead && pair_geom(M, a, t, m, G, t >= NB + nrs)) {
           int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
           for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, fmargin, &d)) mk |= (unsigned short)(1u << p); }
@@ -997,8 +1027,7 @@ SIM_BROAD_UNROLL
       float v2 = vdot(v, v), mv = S->max_lin_vel;
       if (v2 > mv * mv) { v = vscale(v, mv / sqrtf(v2)); }
       {
-        const float rad = M.srad[tid];
-        const float E = 0.5f * (vdot(v, v) + vdot(w, w) * (rad * rad * (1.0f / 3.0f)));
+        const float E = 0.5f * (vdot(v, v) + vdot(w, w) * (brad * brad * (1.0f / 3.0f)));
         const unsigned tc = M.touch[tid];
         if ((tc & 1) || E >= S->wake_energy) slpc = 0;
         else if ((tc & 2) || E >= S->sleep_energy) slpc = 1;
