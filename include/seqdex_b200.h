@@ -75,6 +75,11 @@ typedef struct sdx_scene_t {
   int n_bshapes;
   int bs_body[SDX_MAX_BRICKS];
   float bs_c[SDX_MAX_BRICKS * 3];
+  /* ToolPositioningGrasp / Orient (TG = tasks/tool_positioning/allegro_hand_tool_positioning_grasp.py, TO = ..._orient.py) */
+  float tool_reset_pos[3];    /* where reset_idx puts the tool: (0.29, 0.19, 0.675) (TG:1496-1498) */
+  float tool_pitch_sc[8];     /* (sin, cos) of k * 1.571 / 2, k = 0..3: the tool's pitch at reset is target_rot_rand * 1.571 (TG:1493-1495) */
+  float tool_plate_pose[7];   /* the "extra lego" the tool's orientation is measured against: (0.25, -0.2, 0.618), Quat.from_euler_zyx(0, 3.1415, 0) (TG:1505-1512) */
+  float tool_pad[2];
 } sdx_scene_t;
 
 /* tasks sharing the scene, the contact step and the PPO engine (SURVEY.md section 8a "per-task dimensions"):
@@ -83,7 +88,11 @@ typedef struct sdx_scene_t {
 #define SDX_TASK_ORIENT 1      /* BlockAssemblyOrient:   obs  62 x 3, states 188 x 3, episode  75 (OR:189-214)  */
 #define SDX_TASK_SEARCH 2      /* BlockAssemblySearch:   obs  62 x 3, states 188 x 3, episode  75 (SE:149-175); BASELINE configs[0] */
 #define SDX_TASK_INSERT_SIM 3  /* BlockAssemblyInsertSim: obs 75 x 1, states 188 x 1, episode 125 (IS:172-193); last link of configs[3] */
+#define SDX_TASK_TOOL_GRASP 4  /* ToolPositioningGrasp:   obs 156 x 3, states 188 x 3, episode 150 (TG:224-243); BASELINE configs[4] */
+#define SDX_TASK_TOOL_ORIENT 5 /* ToolPositioningOrient:  obs 156 x 3, states 188 x 3, episode 125 (TO:170-189); BASELINE configs[4] */
 #define SDX_INSERT_OBS_FRAME 75
+#define SDX_TOOL_OBS_FRAME 156
+#define SDX_TOOL_BANK_WRAP 10000     /* TG:1453-1454: the grasp ring's index returns to 0 after slot 10000 */
 #define SDX_ORIENT_OBS_FRAME 62
 #define SDX_ORIENT_BANK_WRAP 10000   /* OR:1478-1479: ring index returns to 0 after slot 10000 */
 
@@ -119,9 +128,9 @@ enum {
   SDX_T_SEG = 25,       /* i32 [N][3]    Search: pixels showing the target | centre row | centre column of the last render (SE:1231-1241) */
   SDX_T_EMERGENCE = 26, /* f32 [N]       Search: emergence reward = 5 x (pixels now - pixels at the last render) (SE:1640-1646)   */
   SDX_T_TVOBS = 27,     /* f32 [N][650]  Search: the transition-feasibility gate's input, 10 frames x 65 (SE:400, 1154-1166)      */
-  SDX_T_PLATE = 28,     /* f32 [N][7]    InsertSim: root pose of the base-plate ("extra lego", IS:1438-1446)                               */
+  SDX_T_PLATE = 28,     /* f32 [N][7]    InsertSim / tool tasks: root pose of the base-plate ("extra lego", IS:1438-1446, TG:1505-1512)      */
   SDX_T_ROT_ERR = 29,   /* f32 [N][3]    InsertSim: wrist orientation error of the last pre_physics_step (IS:1531), read by the reward      */
-  SDX_T_SUCCESS = 30,   /* f32 [N][2]    InsertSim: success_buf written at reset (IS:1348-1350): [inserted, not inserted]                   */
+  SDX_T_SUCCESS = 30,   /* f32 [N][2]    InsertSim / tool tasks: success_buf written at reset (IS:1348-1350; TG:1428, TO:1282 column 0 only) */
   SDX_T_COUNT = 31
 };
 
@@ -223,6 +232,18 @@ int sdx_set_grasp_bank(sdx_env_t* env, const float* hand, const float* obj, int 
 /* test hook of the InsertSim parity tests: the bank slot every env restores on its next resets (NULL: drawn from Philox) and the
  * base-plate yaw index of the next reset_idx calls (-1: drawn) */
 int sdx_insert_test_hooks(sdx_env_t* env, const int* slot_by_env_host, int plate_yaw);
+/* ToolPositioningGrasp / ToolPositioningOrient (BASELINE configs[4]; TG, TO as above).  One free body, the tool (a compound of boxes,
+ * n_bshapes > 0), the same arm and hand, the same 188-slot privileged frame; observation frame 156 x 3.
+ *   TG: sdx_pre_physics = banking of good grasps into the sdx_grasp_bank rings (tool above 0.8 m, fingers within 0.4, within 1 rad of
+ *       the plate's orientation; ring wraps after slot SDX_TOOL_BANK_WRAP; TG:1436-1457) -> reset_idx (tool to tool_reset_pos with pitch
+ *       k x 1.571, k one draw per call, and a per-env yaw; hand to prepare_arm + finger_reset_unscaled; observation history zeroed;
+ *       TG:1412-1578) -> targets (arm IK on 0.2 a[0:3], lift from step 60, parked at insert_prep0 from step 91; TG:1580-1675).
+ *   TO: sdx_pre_physics = reset_idx restoring a banked grasp, tool root row INCLUDING its velocities and the hand's DoF positions and
+ *       velocities (sdx_set_grasp_bank; TO:1265-1436) -> targets (fingers only; the arm holds its previous target, TO:1438-1509).
+ * SDX_T_PLATE holds the plate pose (extra_target_{pos,rot}), SDX_T_SUCCESS[:, 0] success_buf (TG:1428, TO:1282).
+ * sdx_tool_test_hooks: parity-test hook like sdx_insert_test_hooks -- bank slot per env (NULL: drawn), pitch index k of the next
+ * reset_idx calls (-1: drawn), yaw draw u in [-1, 1) per env (NULL: drawn). */
+int sdx_tool_test_hooks(sdx_env_t* env, const int* slot_by_env_host, int pitch_k, const float* yaw_u_host);
 /* number of contact steps the last sdx_pre_physics spent inside reset_idx (0 when nobody reset; 103 for a full Orient reset) */
 int sdx_last_reset_sim_steps(const sdx_env_t* env);
 /* BlockAssemblySearch's camera features (SE = tasks/block_assembly/allegro_hand_block_assembly_search.py): the reference renders

@@ -76,7 +76,14 @@ class OracleEnv:
         self.netf = np.zeros((n, NL, 3), np.float32)
         self.actions = np.zeros((n, 23), np.float32)
         self.task = int(scene.c.task)               # 0 BlockAssemblyGraspSim, 1 BlockAssemblyOrient
-        self.obs = np.zeros((n, {0: 396, 3: 75}.get(self.task, 186)), np.float32)
+        self.obs = np.zeros((n, {0: 396, 3: 75, 4: 468, 5: 468}.get(self.task, 186)), np.float32)
+        if self.task in (4, 5):                     # ToolPositioningGrasp / Orient: plate pose, success_buf, camera-frame tool quaternion, banked grasps
+            self.plate = np.zeros((n, 7), np.float32)
+            self.success_buf = np.zeros((n, 2), np.float32)
+            self.qcam = np.zeros((n, 4), np.float32)
+            self.grasp_obj = self.grasp_hand = None
+            self.pitch_k = None                     # test hooks: pitch index of the next reset_idx calls, yaw draw / bank slot per env
+            self.yaw_u = None
         if self.task == 3:                          # BlockAssemblyInsertSim: base-plate pose, wrist orientation error, success_buf, banked grasps
             self.plate = np.zeros((n, 7), np.float32)   # written by the first reset_idx (every env starts with its reset flag set, BT:63)
             self.rot_err = np.zeros((n, 3), np.float32)
@@ -280,7 +287,40 @@ class OracleEnv:
                                  ip(self.episode), ip(self.wsn), self.slp.ctypes.data_as(ctypes.c_void_p))
         self.refresh_links()                      # the hand was teleported: pre_physics reads its pose before any contact step
 
+    # ---- ToolPositioningGrasp / ToolPositioningOrient (TG:1412-1675, TO:1265-1509)
+    def pitch_draw(self):
+        """random.sample(range(4), 1), ONE draw per reset_idx call (TG:1489): Philox(seed, total_steps) here, as in csrc/sdx_env.cu"""
+        if self.pitch_k is not None:
+            return int(self.pitch_k)
+        out = (ctypes.c_uint32 * 4)()
+        self.L.sdxo_philox(ctypes.c_uint64(self.seed), ctypes.c_uint32(self.total_steps & 0xFFFFFFFF), ctypes.c_uint32(0xC0FFEE), ctypes.c_uint32(7), out)
+        return int(out[0] & 3)
+
+    def _tool_reset_idx(self):
+        orient = int(self.task == 5)
+        if orient:
+            assert self.grasp_obj is not None, "reset needs the banked grasps (TO:365-368)"
+        elif self.total_steps > 0:
+            self.L.sdxo_tool_bank(self.S, self.n, fp(self.brick), fp(self.dof), lp(self.reset), fp(self.finger_dist), fp(self.plate),
+                                  fp(self.gb_hand), fp(self.gb_obj), ip(self.gb_index))
+        slots = getattr(self, "slot_by_env", None)
+        so = np.ascontiguousarray(slots, np.int32) if slots is not None else None
+        yu = np.ascontiguousarray(self.yaw_u, np.float32) if self.yaw_u is not None else None
+        self.L.sdxo_tool_reset(self.S, self.n, orient, ctypes.c_uint64(self.seed), fp(self.grasp_obj), fp(self.grasp_hand),
+                               int(self.grasp_obj.shape[1]) if orient else 0, self.pitch_draw(), ip(so) if so is not None else None, fp(yu),
+                               int(self.total_steps > 0), fp(self.brick), fp(self.dof), fp(self.plate), fp(self.target_init), lp(self.progress),
+                               lp(self.reset), fp(self.successes), fp(self.success_buf), ip(self.episode), ip(self.wsn),
+                               self.slp.ctypes.data_as(ctypes.c_void_p), fp(self.obs), fp(self.states))
+        self.refresh_links()                      # the hand was teleported: pre_physics reads its pose before any contact step
+
     def pre_physics(self, actions):
+        if self.task in (4, 5):
+            if self.reset.any():
+                self._tool_reset_idx()
+            a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)   # VR:166
+            self.L.sdxo_tool_pre_physics(self.S, self.n, int(self.task == 5), fp(a), fp(self.actions), fp(self.dof), fp(self.link), fp(self.jac7),
+                                         lp(self.progress))
+            return
         if self.task == 3:
             if self.reset.any():
                 self._insert_reset_idx()
@@ -318,6 +358,12 @@ class OracleEnv:
                                 lp(self.progress), fp(self.target_init))
 
     def post_physics(self):
+        if self.task in (4, 5):
+            self.L.sdxo_tool_post_physics(self.S, self.n, int(self.task == 5), fp(self.brick), fp(self.dof), fp(self.link), fp(self.actions),
+                                          fp(self.target_init), fp(self.plate), lp(self.progress), lp(self.reset), fp(self.obs), fp(self.states),
+                                          fp(self.rew), fp(self.qcam), fp(self.finger_dist), fp(self.successes), fp(self.consec))
+            self.total_steps += 1
+            return
         if self.task == 3:
             self.L.sdxo_insert_post_physics(self.S, self.n, fp(self.brick), fp(self.dof), fp(self.link), fp(self.actions), fp(self.target_init),
                                             fp(self.plate), fp(self.rot_err), lp(self.progress), lp(self.reset), fp(self.obs), fp(self.states),

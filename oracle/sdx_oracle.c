@@ -76,6 +76,10 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   int n_bshapes;                       /* collision boxes of the free bodies; 0 = every body is one box (n_bricks boxes, box a = body a) */
   int bs_body[SDX_MAX_BRICKS];         /* box -> body; boxes of one body are consecutive */
   float bs_c[SDX_MAX_BRICKS * 3];      /* box centre in its body's COM frame (axes = the body's) */
+  float tool_reset_pos[3];             /* tool tasks: where reset_idx puts the tool (TG:1496-1498) */
+  float tool_pitch_sc[8];              /* (sin, cos) of k * 1.571 / 2, k = 0..3 (TG:1493-1495) */
+  float tool_plate_pose[7];            /* the "extra lego" pose after reset_idx (TG:1505-1512) */
+  float tool_pad[2];
 } sdx_scene_t;
 #define ORIENT_OBS_FRAME 62
 #define ORIENT_BANK_WRAP 10000
@@ -1857,4 +1861,263 @@ void sdxo_insert_reset(const sdx_scene_t* S, int n, uint64_t seed, const float* 
     for (int b = 0; b < NB; ++b) slp[(size_t)e * NB + b] = 0;
     episode[e] += 1;
   }
+}
+
+
+/* ================================================================== ToolPositioningGrasp / ToolPositioningOrient (BASELINE configs[4])
+ * TG = tasks/tool_positioning/allegro_hand_tool_positioning_grasp.py, TO = tasks/tool_positioning/allegro_hand_tool_positioning_orient.py.
+ * One free body per env: the tool (body 0, a compound of boxes).  Observation frame 156 x 3 (TG:1338-1368 = TO:1201-1236), privileged
+ * frame 188 x 3 (TG:1274-1336; TO:1137-1199 puts the plate pose in 181:188), rewards / resets TG:1741-1893 and TO:1574-1626,
+ * reset_idx TG:1412-1578 and TO:1265-1436, pre_physics_step TG:1580-1675 and TO:1438-1509.
+ * PARITY: pre-physics, observations, reward / reset flags and reset_idx of BOTH tasks PINNED to the reference's own Python
+ * (oracle/gen_golden_tool.py -> tests/golden/tool_*.npz). */
+#define TOOL_OBS 156
+#define TOOL_BODY 0
+#define TOOL_BANK_WRAP 10000
+static inline float tool_rot_dist(q4 tq, q4 eq) {   /* TG:1871-1872, TO:1587-1588 */
+  q4 d = qmul(tq, qconj(eq));
+  float nn = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+  return 2.0f * sdx_asin(nn > 1.0f ? 1.0f : nn);
+}
+static inline float tool_signed_sq(float d) { return (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * (d * d); }   /* torch.sign(d) * d ** 2 */
+/* pytorch3d.transforms.quaternion_to_matrix (third party, not in /root/reference; published algorithm: (r, i, j, k) = q[0..3],
+ * two_s = 2 / |q|^2, the usual nine entries).  The reference hands it xyzw quaternions (TG:1853-1854), so "r" is the x component. */
+static void tool_p3d_matrix(q4 q, float* M) {
+  const float r = q.x, i = q.y, j = q.z, k = q.w;
+  const float two_s = 2.0f / (r * r + i * i + j * j + k * k);
+  M[0] = 1.0f - two_s * (j * j + k * k); M[1] = two_s * (i * j - k * r); M[2] = two_s * (i * k + j * r);
+  M[3] = two_s * (i * j + k * r); M[4] = 1.0f - two_s * (i * i + k * k); M[5] = two_s * (j * k - i * r);
+  M[6] = two_s * (i * k - j * r); M[7] = two_s * (j * k + i * r); M[8] = 1.0f - two_s * (i * i + j * j);
+}
+
+/* TG reset_idx's banking (TG:1436-1457), a sequential loop over the resetting envs in env order: the tool above 0.8 m, within 0.4 of
+ * the fingertips (the unweighted sum of compute_observations) and within 1 rad of the plate's orientation -> (hand DoF state, tool
+ * root row) into the ring of type env % 8; the index returns to 0 after slot 10000.  (The reference's eight lists alias ONE tensor,
+ * TG:441-442; the rings here are separate.) */
+void sdxo_tool_bank(const sdx_scene_t* S, int n, const float* brick, const float* dof, const int64_t* reset, const float* finger_dist,
+                    const float* plate, float* gb_hand, float* gb_obj, int* gb_index) {
+  for (int e = 0; e < n; ++e) {
+    if (!reset[e]) continue;
+    const int ty = e % 8;
+    float row[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, TOOL_BODY, row);
+    const float* pl = plate + 7 * e;
+    q4 tq = {row[3], row[4], row[5], row[6]}, eq = {pl[3], pl[4], pl[5], pl[6]};
+    if (row[2] > 0.8f && finger_dist[e] < 0.4f && tool_rot_dist(tq, eq) < 1.0f) {
+      const int slot = gb_index[ty];
+      float* hd = gb_hand + ((size_t)ty * 11024 + slot) * 46;
+      const float* d = dof + (size_t)e * 72;
+      for (int j = 0; j < SDX_ND; ++j) { hd[2 * j] = d[j]; hd[2 * j + 1] = d[24 + j]; }
+      float* ob = gb_obj + ((size_t)ty * 11024 + slot) * 13;
+      for (int q = 0; q < 13; ++q) ob[q] = row[q];
+      gb_index[ty] += 1;
+    }
+    if (gb_index[ty] > TOOL_BANK_WRAP) gb_index[ty] = 0;
+  }
+}
+
+/* reset_idx for the envs whose reset flag is set.  success_buf[:, 0] first (TG:1425-1428 rot_dist < 0.3; TO:1279-1282 < 0.5).
+ * orient = 0 (TG:1459-1578): the tool to tool_reset_pos with quat_from_euler_xyz(0, k * 1.571, u * 3.14) -- k = pitch_k, ONE
+ * random.sample(range(4)) per call; u per env in [-1, 1) (yaw_u, a test hook, names it; else Philox) --, velocities zero; the hand to
+ * prepare_arm (= arm_hand_default_dof_pos[:7], TG:284) and the scaled finger_reset_unscaled, targets = positions; obs_buf and every
+ * history frame of the env zeroed (TG:1563-1568; states_buf itself is not, but its only unrefreshed slot, 141, is never written).
+ * orient = 1 (TO:1380-1436): the tool's WHOLE root row (velocities too) and the hand's DoF positions AND velocities from a banked
+ * grasp (slot = Philox % per_type; slot_by_env names it), targets = positions; history kept.
+ * Both: the plate to tool_plate_pose, target_init = the tool's new pose. */
+void sdxo_tool_reset(const sdx_scene_t* S, int n, int orient, uint64_t seed, const float* bank_obj, const float* bank_hand, int per_type,
+                     int pitch_k, const int* slot_by_env, const float* yaw_u, int do_success, float* brick, float* dof, float* plate,
+                     float* target_init, int64_t* progress, int64_t* reset, float* successes, float* success_buf, int* episode, int* wsn,
+                     unsigned char* slp, float* obs, float* states) {
+  for (int e = 0; e < n; ++e) {
+    if (!reset[e]) continue;
+    float* B = brick + (size_t)e * 13 * NB;
+    float* d = dof + (size_t)e * 72;
+    float* pl = plate + 7 * e;
+    if (do_success) {
+      float tg[13];
+      brick_root_row(S, B, TOOL_BODY, tg);
+      q4 tq = {tg[3], tg[4], tg[5], tg[6]}, eq = {pl[3], pl[4], pl[5], pl[6]};
+      float rd = tool_rot_dist(tq, eq);
+      success_buf[2 * e] = rd < (orient ? 0.5f : 0.3f) ? 1.0f : 0.0f;
+    }
+    uint32_t r[4];
+    philox(seed, (uint32_t)e, (uint32_t)episode[e], 1u, r);
+    float row[13];
+    if (orient) {
+      int slot = slot_by_env ? slot_by_env[e] : (int)(r[0] % (uint32_t)per_type);
+      const float* ob = bank_obj + (((size_t)(e % 8)) * per_type + slot) * 13;
+      const float* hd = bank_hand + (((size_t)(e % 8)) * per_type + slot) * 46;
+      for (int k = 0; k < 13; ++k) row[k] = ob[k];
+      for (int j = 0; j < SDX_ND; ++j) { d[j] = hd[2 * j]; d[24 + j] = hd[2 * j + 1]; d[48 + j] = hd[2 * j]; }
+    } else {
+      float u = yaw_u ? yaw_u[e] : (float)(r[1] >> 8) * (2.0f / 16777216.0f) - 1.0f;
+      float sy, cy;
+      sdx_sincos((u * 3.14f) * 0.5f, &sy, &cy);
+      float sp = S->tool_pitch_sc[2 * pitch_k], cp = S->tool_pitch_sc[2 * pitch_k + 1];
+      row[0] = S->tool_reset_pos[0]; row[1] = S->tool_reset_pos[1]; row[2] = S->tool_reset_pos[2];
+      row[3] = 0.0f - sy * sp; row[4] = cy * sp; row[5] = sy * cp; row[6] = cy * cp;
+      for (int k = 7; k < 13; ++k) row[k] = 0.0f;
+      for (int j = 0; j < 7; ++j) { d[j] = S->prepare_arm[j]; d[24 + j] = 0.0f; d[48 + j] = S->prepare_arm[j]; }
+      for (int i = 0; i < 16; ++i) {
+        float v = scalef(S->finger_reset_unscaled[i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+        d[7 + i] = v; d[24 + 7 + i] = 0.0f; d[48 + 7 + i] = v;
+      }
+      float* o = obs + (size_t)e * 3 * TOOL_OBS;
+      for (int k = 0; k < 3 * TOOL_OBS; ++k) o[k] = 0.0f;
+      float* s = states + (size_t)e * 3 * STATE_FRAME;
+      for (int k = 0; k < 3 * STATE_FRAME; ++k) s[k] = 0.0f;
+    }
+    brick_from_root_row(S, B, TOOL_BODY, row);
+    for (int k = 0; k < 7; ++k) { pl[k] = S->tool_plate_pose[k]; target_init[7 * e + k] = row[k]; }
+    progress[e] = 0; reset[e] = 0; successes[e] = 0.0f;
+    wsn[2 * e] = 0; wsn[2 * e + 1] = 0;
+    for (int b = 0; b < NB; ++b) slp[(size_t)e * NB + b] = 0;
+    episode[e] += 1;
+  }
+}
+
+/* pre_physics_step after resets.  Fingers = EMA of the scaled actions.  TG (TG:1617-1636): arm = IK for (0.2 a[0:3] -- from step 60
+ * on a pure 0.1 lift --, 5 x the orientation error to hand_target_quat); from step 91 on the arm goes to insert_prep0
+ * (= arm_hand_insertion_prepare_dof_pos_list[0]) and the fingers hold their previous targets.  TO (TO:1471-1473): the arm holds its
+ * previous target. */
+void sdxo_tool_pre_physics(const sdx_scene_t* S, int n, int orient, const float* actions_in, float* actions, float* dof, const float* link,
+                           const float* jac7, const int64_t* progress) {
+  for (int e = 0; e < n; ++e) {
+    const float* a = actions_in + 23 * (size_t)e;
+    float* d = dof + (size_t)e * 72;
+    float cur[23];
+    for (int k = 0; k < 23; ++k) actions[23 * (size_t)e + k] = a[k];
+    for (int i = 0; i < 16; ++i) {
+      float t = scalef(a[7 + i], S->dof_lo[7 + i], S->dof_hi[7 + i]);
+      cur[7 + i] = S->act_moving_average * t + (1.0f - S->act_moving_average) * d[48 + 7 + i];
+    }
+    if (orient) {
+      for (int j = 0; j < 7; ++j) cur[j] = clampf(d[48 + j], S->dof_lo[j], S->dof_hi[j]);
+    } else {
+      const int64_t pg = progress[e];
+      float dpose[6] = {a[0] * 0.2f, a[1] * 0.2f, a[2] * 0.2f, 0.0f, 0.0f, 0.0f};
+      if (pg >= 60) { dpose[2] = 0.1f; dpose[0] = 0.0f; dpose[1] = 0.0f; }
+      const float* hb = link + ((size_t)e * SDX_NL + 7) * 13;
+      q4 want = {S->hand_target_quat[0], S->hand_target_quat[1], S->hand_target_quat[2], S->hand_target_quat[3]};
+      q4 hq = {hb[3], hb[4], hb[5], hb[6]};
+      v3 re = orientation_error(want, hq);
+      dpose[3] = re.x * 5.0f; dpose[4] = re.y * 5.0f; dpose[5] = re.z * 5.0f;
+      float u[7];
+      control_ik(jac7 + 42 * (size_t)e, dpose, u);
+      for (int j = 0; j < 7; ++j) cur[j] = d[j] + u[j];
+      if (pg > 90) {
+        for (int j = 0; j < 7; ++j) cur[j] = S->insert_prep0[j];
+        for (int i = 7; i < 23; ++i) cur[i] = d[48 + i];
+      }
+    }
+    for (int j = 0; j < 23; ++j) d[48 + j] = clampf(cur[j], S->dof_lo[j], S->dof_hi[j]);
+  }
+}
+
+/* post_physics_step: progress += 1, observations, reward, reset flags.  obs [n][468], states [n][564] (UNCLAMPED task buffers; the
+ * two older frames of each are the previous calls' newest, TG:1334-1336, 1366-1368).  TG writes successes (TG:1866-1868). */
+void sdxo_tool_post_physics(const sdx_scene_t* S, int n, int orient, const float* brick, const float* dof, const float* link,
+                            const float* actions, const float* target_init, const float* plate, int64_t* progress, int64_t* reset,
+                            float* obs, float* states, float* rew, float* qcam, float* finger_dist_out, float* successes, float* consec) {
+  int64_t num_resets = 0; float finished = 0.0f;
+  for (int e = 0; e < n; ++e) {
+    progress[e] += 1;
+    const int64_t pg = progress[e];
+    float* o = obs + (size_t)e * 3 * TOOL_OBS;
+    float* s = states + (size_t)e * 3 * STATE_FRAME;
+    for (int k = 2 * TOOL_OBS - 1; k >= 0; --k) o[TOOL_OBS + k] = o[k];
+    for (int k = 2 * STATE_FRAME - 1; k >= 0; --k) s[STATE_FRAME + k] = s[k];
+    const float* L = link + (size_t)e * SDX_NL * 13;
+    const float* d = dof + (size_t)e * 72;
+    const float* hb = L + 7 * 13;
+    const float* ff = L + 11 * 13; const float* mf = L + 19 * 13; const float* rf = L + 23 * 13; const float* th = L + 15 * 13; /* TG:218-221 */
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, TOOL_BODY, tg);
+    v3 tp = V3(tg[0], tg[1], tg[2]); q4 tq = {tg[3], tg[4], tg[5], tg[6]};
+    v3 tip[4]; const float* fsr[4] = {ff, mf, rf, th};
+    float nrm[4];
+    for (int i = 0; i < 4; ++i) { /* TG:1200-1203 */
+      q4 fq = {fsr[i][3], fsr[i][4], fsr[i][5], fsr[i][6]};
+      tip[i] = vadd(V3(fsr[i][0], fsr[i][1], fsr[i][2]), qrot(fq, V3(0.0f, 0.0f, 1.0f * 0.04f)));
+      v3 dd = vsub(tp, tip[i]); nrm[i] = sqrtf(vdot(dd, dd));
+    }
+    float fdist = nrm[0] + nrm[1] + nrm[2] + nrm[3]; /* TG:1221-1222 */
+    finger_dist_out[e] = fdist;
+    q4 hq = {hb[3], hb[4], hb[5], hb[6]}; v3 hp = V3(hb[0], hb[1], hb[2]);
+    q4 cq0 = {S->cam_off_quat[0], S->cam_off_quat[1], S->cam_off_quat[2], S->cam_off_quat[3]};
+    q4 cq = qmul(hq, cq0); v3 cp = vadd(qrot(hq, V3(S->cam_off_pos[0], S->cam_off_pos[1], S->cam_off_pos[2])), hp);
+    q4 cqi = qconj(cq); v3 cpi = vneg(qrot(cqi, cp));
+    q4 cvq = qmul(cqi, tq); v3 cvp = vadd(qrot(cqi, tp), cpi);
+    qcam[4 * e] = cvq.x; qcam[4 * e + 1] = cvq.y; qcam[4 * e + 2] = cvq.z; qcam[4 * e + 3] = cvq.w;
+    const float* ti = target_init + 7 * e;
+    const float* pl = plate + 7 * e;
+    v3 ep = V3(pl[0], pl[1], pl[2]); q4 eq = {pl[3], pl[4], pl[5], pl[6]};
+    /* ---- observation frame (TG:1338-1364 = TO:1201-1232) */
+    for (int j = 0; j < 23; ++j) { o[j] = unscalef(d[j], S->dof_lo[j], S->dof_hi[j]); o[23 + j] = actions[23 * (size_t)e + j]; }
+    for (int k = 0; k < 7; ++k) { o[46 + k] = hb[k]; o[53 + k] = tg[k]; o[61 + k] = pl[k]; }
+    o[60] = (float)pg / (float)S->max_episode_length;
+    o[68] = tp.x - ep.x; o[69] = tp.y - ep.y; o[70] = tp.z - ep.z;
+    { q4 r = qmul(tq, qconj(eq)); o[71] = r.x; o[72] = r.y; o[73] = r.z; o[74] = r.w; }
+    for (int k = 0; k < 13; ++k) { o[75 + k] = ff[k]; o[88 + k] = rf[k]; o[101 + k] = mf[k]; o[114 + k] = th[k]; }
+    for (int j = 0; j < 23; ++j) o[127 + j] = S->vel_obs_scale * d[24 + j];
+    for (int k = 0; k < 6; ++k) o[150 + k] = tg[7 + k];
+    /* ---- privileged frame (TG:1274-1332; TO:1137-1195 differs in 181:188); slot 141 is never written */
+    for (int j = 0; j < 23; ++j) { s[j] = unscalef(d[j], S->dof_lo[j], S->dof_hi[j]); s[23 + j] = S->vel_obs_scale * d[24 + j]; }
+    s[46] = tip[0].x; s[47] = tip[0].y; s[48] = tip[0].z;
+    s[49] = tip[2].x; s[50] = tip[2].y; s[51] = tip[2].z;
+    s[52] = tip[1].x; s[53] = tip[1].y; s[54] = tip[1].z;
+    s[55] = tip[3].x; s[56] = tip[3].y; s[57] = tip[3].z;
+    for (int k = 0; k < 23; ++k) s[58 + k] = actions[23 * (size_t)e + k];
+    for (int k = 0; k < 7; ++k) { s[81 + k] = hb[k]; s[88 + k] = tg[k]; }
+    for (int k = 0; k < 6; ++k) s[95 + k] = hb[7 + k];
+    for (int k = 0; k < 4; ++k) { s[101 + k] = ff[3 + k]; s[111 + k] = mf[3 + k]; s[121 + k] = rf[3 + k]; s[131 + k] = th[3 + k]; }
+    for (int k = 0; k < 6; ++k) { s[105 + k] = ff[7 + k]; s[115 + k] = mf[7 + k]; s[125 + k] = rf[7 + k]; s[135 + k] = th[7 + k]; }
+    for (int k = 0; k < 6; ++k) s[142 + k] = tg[7 + k];
+    s[148] = ti[0]; s[149] = ti[1]; s[150] = ti[2];
+    s[151] = tp.x - ti[0]; s[152] = tp.y - ti[1]; s[153] = tp.z - ti[2];
+    s[154] = hp.x - tp.x; s[155] = hp.y - tp.y; s[156] = hp.z - tp.z;
+    { q4 rel = qmul(hq, qconj(tq)); s[157] = rel.x; s[158] = rel.y; s[159] = rel.z; s[160] = rel.w; }
+    { v3 a = vsub(tp, tip[0]), b = vsub(tp, tip[2]), c = vsub(tp, tip[1]), dd = vsub(tp, tip[3]);
+      s[161] = a.x; s[162] = a.y; s[163] = a.z; s[164] = b.x; s[165] = b.y; s[166] = b.z;
+      s[167] = c.x; s[168] = c.y; s[169] = c.z; s[170] = dd.x; s[171] = dd.y; s[172] = dd.z; }
+    s[173] = fdist;
+    s[174] = cvp.x; s[175] = cvp.y; s[176] = cvp.z; s[177] = cvq.x; s[178] = cvq.y; s[179] = cvq.z; s[180] = cvq.w;
+    if (orient) { for (int k = 0; k < 7; ++k) s[181 + k] = pl[k]; }
+    else { s[181] = cvp.x; s[182] = cvp.y; s[183] = cvp.z; s[184] = cvq.x; s[185] = cvq.y; s[186] = cvq.z; s[187] = cvq.w; }
+    /* ---- reward / resets */
+    float dist = nrm[0] + nrm[1] + nrm[2] + 3.0f * nrm[3];
+    float rd = tool_rot_dist(tq, eq);
+    int64_t rs = reset[e];
+    float sc = successes[e];
+    if (orient) { /* TO:1574-1626 */
+      if (dist >= 20.0f) rs = 1;
+      if ((float)pg >= (float)S->max_episode_length - 1.0f) rs = 1;
+      rew[e] = (rd < 0.2f ? 1.0f : 0.0f) + sdx_exp(-1.0f * rd);
+    } else { /* TG:1741-1893 */
+      float zal = tool_signed_sq(qrot(tq, V3(0.0f, 0.0f, 1.0f)).z);
+      if (dist <= -1.0f) rs = 1;
+      if (pg >= 150 && zal <= 0.75f) rs = 1;
+      if (pg >= 150 && dist >= 0.4f) rs = 1;
+      float ay = tp.y - ti[1], ax = tp.x - ti[0];
+      if (pg <= 90 && (ay < 0.0f ? -ay : ay) >= 0.08f) rs = 1;
+      if (pg <= 90 && (ax < 0.0f ? -ax : ax) >= 0.08f) rs = 1;
+      if ((float)pg >= (float)S->max_episode_length - 1.0f) rs = 1;
+      float Mi[9], Mc[9];
+      q4 tiq = {ti[3], ti[4], ti[5], ti[6]};
+      tool_p3d_matrix(tiq, Mi);
+      tool_p3d_matrix(tq, Mc);
+      float i0 = 0.0f * Mi[0] + 1.0f * Mi[3] + 0.0f * Mi[6], i1 = 0.0f * Mi[1] + 1.0f * Mi[4] + 0.0f * Mi[7], i2 = 0.0f * Mi[2] + 1.0f * Mi[5] + 0.0f * Mi[8];
+      float c0 = Mc[0] * i0 + Mc[1] * i1 + Mc[2] * i2, c1 = Mc[3] * i0 + Mc[4] * i1 + Mc[5] * i2, c2 = Mc[6] * i0 + Mc[7] * i1 + Mc[8] * i2;
+      float angle_difference = (0.0f * c0 + 1.0f * c1 + 0.0f * c2) - 1.0f;
+      sc = -angle_difference >= 1.95f ? 1.0f : 0.0f;
+      float cl = dist - 0.4f; if (cl < 0.0f) cl = 0.0f;
+      float cr = rd - 0.5f; if (cr < 0.0f) cr = 0.0f;
+      float up = clampf(tp.z - 0.6f, 0.0f, 0.2f);
+      rew[e] = sdx_exp(-1.0f * (5.0f * cl + cr)) * (1.0f + 10.0f * up) + (rd < 0.5f ? 1.0f : 0.0f);
+      successes[e] = sc;
+    }
+    reset[e] = rs;
+    num_resets += rs; finished += sc * (float)rs;
+  }
+  if (num_resets > 0) consec[0] = S->av_factor * finished / (float)num_resets + (1.0f - S->av_factor) * consec[0];
 }

@@ -12,6 +12,7 @@
 #include "sdx_task.cuh"
 #include "sdx_task_orient.cuh"
 #include "sdx_task_insert.cuh"
+#include "sdx_task_tool.cuh"
 #include "sdx_camera.cuh"
 #include "sdx_dr.cuh"
 #include "sdx_task_search.cuh"
@@ -61,8 +62,14 @@ struct sdx_env {
   float *ib_obj = nullptr, *ib_hand = nullptr; int ib_per_type = 0;   // the banked grasps reset_idx restores (sdx_set_grasp_bank)
   int* slot_by_env = nullptr;      // test hook: reset slots given per env instead of drawn
   int plate_yaw_override = -1;
+  // ToolPositioningGrasp / Orient
+  float* yaw_u = nullptr;          // test hook: the yaw draw per env
+  int pitch_override = -1;
 };
-static int obs_frame(const sdx_env* E) { return E->task == SDX_TASK_GRASP_SIM ? SDX_OBS_FRAME : E->task == SDX_TASK_INSERT_SIM ? SDX_INSERT_OBS_FRAME : SDX_ORIENT_OBS_FRAME; }
+static bool is_tool(int task) { return task == SDX_TASK_TOOL_GRASP || task == SDX_TASK_TOOL_ORIENT; }
+static int obs_frame(const sdx_env* E) {
+  return E->task == SDX_TASK_GRASP_SIM ? SDX_OBS_FRAME : E->task == SDX_TASK_INSERT_SIM ? SDX_INSERT_OBS_FRAME : is_tool(E->task) ? SDX_TOOL_OBS_FRAME : SDX_ORIENT_OBS_FRAME;
+}
 static int obs_stack(const sdx_env* E) { return E->task == SDX_TASK_INSERT_SIM ? 1 : SDX_STACK; }   // IS:171 stack_obs = 1
 
 static size_t kind_elems(const sdx_env* E, int kind, int64_t shape[4], int* ndim, int* dtype) {
@@ -119,7 +126,7 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaSetDevice(device));
   sdx_env* E = new sdx_env();
   E->n = num_envs; E->device = device; E->seed = seed; E->host_scene = *scene;
-  if (scene->task != SDX_TASK_GRASP_SIM && scene->task != SDX_TASK_ORIENT && scene->task != SDX_TASK_SEARCH && scene->task != SDX_TASK_INSERT_SIM) { g_err = "sdx_create: unknown scene.task"; delete E; return -1; }
+  if (scene->task < SDX_TASK_GRASP_SIM || scene->task > SDX_TASK_TOOL_ORIENT) { g_err = "sdx_create: unknown scene.task"; delete E; return -1; }
   E->task = scene->task;
   CK(cudaMalloc(&E->scene, sizeof(sdx_scene_t)));
   CK(cudaMemcpy(E->scene, scene, sizeof(sdx_scene_t), cudaMemcpyHostToDevice));
@@ -167,7 +174,7 @@ extern "C" void sdx_destroy(sdx_env_t* E) {
   cudaFree(E->stage_obs); cudaFree(E->stage_states); cudaFree(E->stage_actions);
   cudaFree(E->cscratch);
   cudaFree(E->last_pixels); cudaFree(E->sb_rows); cudaFree(E->sb_hand); cudaFree(E->sb_index); cudaFreeHost(E->progress0_host);
-  cudaFree(E->ib_obj); cudaFree(E->ib_hand); cudaFree(E->slot_by_env);
+  cudaFree(E->ib_obj); cudaFree(E->ib_hand); cudaFree(E->slot_by_env); cudaFree(E->yaw_u);
   cudaFree(E->flag_count); cudaFreeHost(E->flag_count_host); cudaFree(E->ob_slot); cudaFree(E->ob_rows); cudaFree(E->ob_index);
   delete E;
 }
@@ -302,8 +309,7 @@ extern "C" int sdx_reset_all(sdx_env_t* E) {
 static int orient_pre_physics(sdx_env_t* E, const float* actions_dev);
 static int search_pre_physics(sdx_env_t* E, const float* actions_dev);
 /* the base-plate yaw of a reset_idx call: random.sample([0, 1], 1), ONE draw for all envs that reset (IS:1435).  Philox(seed; step) bit */
-static int insert_plate_yaw(const sdx_env_t* E) {
-  if (E->plate_yaw_override >= 0) return E->plate_yaw_override;
+static uint32_t reset_call_draw(const sdx_env_t* E) {
   uint32_t k0 = (uint32_t)E->seed, k1 = (uint32_t)(E->seed >> 32), c[4] = {(uint32_t)E->total_steps, 0xC0FFEEu, 7u, 0u};
   for (int r = 0; r < 10; ++r) {
     uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
@@ -311,7 +317,47 @@ static int insert_plate_yaw(const sdx_env_t* E) {
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
-  return (int)(c[0] & 1u);
+  return c[0];
+}
+static int insert_plate_yaw(const sdx_env_t* E) { return E->plate_yaw_override >= 0 ? E->plate_yaw_override : (int)(reset_call_draw(E) & 1u); }
+/* the tool's pitch index of a reset_idx call: random.sample(range(4), 1), ONE draw for all envs that reset (TG:1489) */
+static int tool_pitch_k(const sdx_env_t* E) { return E->pitch_override >= 0 ? E->pitch_override : (int)(reset_call_draw(E) & 3u); }
+static int tool_pre_physics(sdx_env_t* E, const float* actions_dev) {
+  const int n = E->n, orient = E->task == SDX_TASK_TOOL_ORIENT;
+  if (orient && !E->ib_obj) { g_err = "sdx_pre_physics: ToolPositioningOrient needs the banked grasps (sdx_set_grasp_bank; TO:365-368)"; return -1; }
+  if (!orient && E->total_steps > 0) {
+    k_tool_bank<<<8, 256, 0, E->stream>>>(E->scene, n, F(SDX_T_BRICK), F(SDX_T_DOF), I64(SDX_T_RESET), E->finger_dist, F(SDX_T_PLATE), E->gb_hand,
+                                          E->gb_obj, E->gb_index);
+    E->launches++;
+  }
+  k_tool_reset<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, orient, E->seed, E->ib_obj, E->ib_hand, E->ib_per_type, tool_pitch_k(E), E->slot_by_env,
+                                                     E->yaw_u, E->total_steps > 0 ? 1 : 0, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_PLATE),
+                                                     F(SDX_T_TARGET_INIT), I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_SUCCESSES), F(SDX_T_SUCCESS),
+                                                     I32(SDX_T_EPISODE), I32(SDX_T_WSN), (unsigned char*)E->buf[SDX_T_SLEEP], F(SDX_T_OBS), F(SDX_T_STATES));
+  // the hand has been teleported: the link rows / Jacobian pre_physics reads must be those of the new joint angles
+  k_refresh_links<<<(n + 63) / 64, 64, 0, E->stream>>>(E->scene, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7), n);
+  k_tool_pre_physics<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, orient, actions_dev, F(SDX_T_ACTIONS), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+                                                           I64(SDX_T_PROGRESS));
+  E->launches += 3;
+  CKL();
+  return 0;
+}
+extern "C" int sdx_tool_test_hooks(sdx_env_t* E, const int* slot_by_env_host, int pitch_k, const float* yaw_u_host) {
+  if (!E || !is_tool(E->task)) { g_err = "sdx_tool_test_hooks: the env does not run a ToolPositioning task"; return -1; }
+  if (pitch_k > 3) { g_err = "sdx_tool_test_hooks: pitch index out of range"; return -1; }
+  CK(cudaSetDevice(E->device));
+  cudaFree(E->slot_by_env); E->slot_by_env = nullptr;
+  cudaFree(E->yaw_u); E->yaw_u = nullptr;
+  if (slot_by_env_host) {
+    CK(cudaMalloc(&E->slot_by_env, (size_t)E->n * 4));
+    CK(cudaMemcpy(E->slot_by_env, slot_by_env_host, (size_t)E->n * 4, cudaMemcpyHostToDevice));
+  }
+  if (yaw_u_host) {
+    CK(cudaMalloc(&E->yaw_u, (size_t)E->n * 4));
+    CK(cudaMemcpy(E->yaw_u, yaw_u_host, (size_t)E->n * 4, cudaMemcpyHostToDevice));
+  }
+  E->pitch_override = pitch_k;
+  return 0;
 }
 static int insert_pre_physics(sdx_env_t* E, const float* actions_dev) {
   const int n = E->n;
@@ -330,7 +376,7 @@ static int insert_pre_physics(sdx_env_t* E, const float* actions_dev) {
 }
 extern "C" int sdx_set_grasp_bank(sdx_env_t* E, const float* hand, const float* obj, int per_type, int is_device) {
   if (!E || !hand || !obj || per_type <= 0) { g_err = "sdx_set_grasp_bank: bad arguments"; return -1; }
-  if (E->task != SDX_TASK_INSERT_SIM) { g_err = "sdx_set_grasp_bank: the env does not run BlockAssemblyInsertSim"; return -1; }
+  if (E->task != SDX_TASK_INSERT_SIM && E->task != SDX_TASK_TOOL_ORIENT) { g_err = "sdx_set_grasp_bank: the env runs neither BlockAssemblyInsertSim nor ToolPositioningOrient"; return -1; }
   CK(cudaSetDevice(E->device));
   CK(cudaStreamSynchronize(E->stream));
   cudaFree(E->ib_obj); cudaFree(E->ib_hand);
@@ -358,6 +404,7 @@ extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
   const int n = E->n;
   if (E->task == SDX_TASK_SEARCH) return search_pre_physics(E, actions_dev);     // Search resets from the drop lattice: no bank
   if (E->task == SDX_TASK_INSERT_SIM) return insert_pre_physics(E, actions_dev);
+  if (is_tool(E->task)) return tool_pre_physics(E, actions_dev);
   if (!E->bank) { g_err = "sdx_pre_physics: no heap bank set (reset_idx samples it, GS:1507-1511)"; return -1; }
   if (E->task == SDX_TASK_ORIENT) return orient_pre_physics(E, actions_dev);
   if (E->total_steps > 0) {
@@ -570,6 +617,17 @@ extern "C" int sdx_post_physics(sdx_env_t* E) {
                                                               F(SDX_T_TARGET_INIT), F(SDX_T_PLATE), F(SDX_T_ROT_ERR), I64(SDX_T_PROGRESS), I64(SDX_T_RESET),
                                                               F(SDX_T_OBS), F(SDX_T_STATES), F(SDX_T_REW), E->finger_dist, F(SDX_T_SUCCESSES), E->red_count,
                                                               E->red_sum);
+    k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
+    E->launches += 2;
+    E->total_steps++;
+    CKL();
+    return 0;
+  }
+  if (is_tool(E->task)) {
+    k_tool_post_physics<<<(n + POST_WARPS - 1) / POST_WARPS, 32 * POST_WARPS, 0, E->stream>>>(
+        E->scene, n, E->task == SDX_TASK_TOOL_ORIENT, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_ACTIONS), F(SDX_T_TARGET_INIT), F(SDX_T_PLATE),
+        I64(SDX_T_PROGRESS), I64(SDX_T_RESET), F(SDX_T_OBS), F(SDX_T_STATES), F(SDX_T_REW), E->qcam, E->finger_dist, F(SDX_T_SUCCESSES), E->red_count,
+        E->red_sum);
     k_finalize<<<1, 1, 0, E->stream>>>(E->scene, E->red_count, E->red_sum, F(SDX_T_CONSEC));
     E->launches += 2;
     E->total_steps++;

@@ -126,6 +126,12 @@ class SdxEnv:
         _lib.check(self.L.sdx_grasp_bank(self.h, ctypes.byref(h), ctypes.byref(o), ctypes.byref(i)))
         return self._view(h.value, (8, 11024, 23, 2)), self._view(o.value, (8, 11024, 13)), self._view(i.value, (8,), "<i4")
 
+    def aux(self):
+        """(camera-frame target quaternion [N, 4], arm_hand_finger_dist [N]) of the last compute_observations, as device views"""
+        q, f = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(self.L.sdx_aux(self.h, ctypes.byref(q), ctypes.byref(f)))
+        return self._view(q.value, (self.n, 4)), self._view(f.value, (self.n,))
+
     def enable_tvalue_dataset(self, capacity=65536):
         """record the t-value training rows on the device (the reference's save_hdf5 branch, GS:1402-1438)"""
         _lib.check(self.L.sdx_tvalue_dataset(self.h, int(capacity), None, None, None))
@@ -184,6 +190,13 @@ class SdxEnv:
     def insert_test_hooks(self, slot_by_env=None, plate_yaw=-1):
         s = None if slot_by_env is None else np.ascontiguousarray(slot_by_env, np.int32)
         _lib.check(self.L.sdx_insert_test_hooks(self.h, s.ctypes.data_as(ctypes.c_void_p) if s is not None else None, int(plate_yaw)))
+
+    def tool_test_hooks(self, slot_by_env=None, pitch_k=-1, yaw_u=None):
+        """parity-test hook of the ToolPositioning tasks (sdx_tool_test_hooks): bank slot per env, pitch index, yaw draw per env"""
+        s = None if slot_by_env is None else np.ascontiguousarray(slot_by_env, np.int32)
+        u = None if yaw_u is None else np.ascontiguousarray(yaw_u, np.float32)
+        _lib.check(self.L.sdx_tool_test_hooks(self.h, s.ctypes.data_as(ctypes.c_void_p) if s is not None else None, int(pitch_k),
+                                              u.ctypes.data_as(ctypes.c_void_p) if u is not None else None))
 
     def last_reset_sim_steps(self):
         return int(self.L.sdx_last_reset_sim_steps(self.h))

@@ -1,0 +1,133 @@
+"""ToolPositioningGrasp / ToolPositioningOrient (BASELINE ``configs[4]``) with the reference's BaseTask surface (BT:24-150;
+TG = tasks/tool_positioning/allegro_hand_tool_positioning_grasp.py:130-1919, TO = tasks/tool_positioning/
+allegro_hand_tool_positioning_orient.py:77-1652), backed by the CUDA kernels behind the C-ABI (``scene.task = SDX_TASK_TOOL_GRASP /
+SDX_TASK_TOOL_ORIENT``, csrc/sdx_task_tool.cuh).
+
+Grasp picks the hammer up from the bin and banks the good grasps (lifted, fingers on it, within 1 rad of the plate's orientation) into
+per-type rings -- what the reference pickles as ``saved_orient_grasp_{object,hand}_init_tvalue_temporal.pkl`` (TG:1459-1467); Orient
+starts every episode from one of those grasps (TO:365-368, 1393-1398) and has to turn the hammer in the hand until it is aligned with
+the plate.
+
+Physics model (DESIGN.md "ToolPositioning"): the hammer is a COMPOUND of two boxes (handle + head, scene.HAMMER_BOXES) with the URDF's
+density; Isaac Gym collides a V-HACD decomposition of harmmer.obj.  Observations, rewards, resets, banking and both reset_idx are the
+reference's, pinned by goldens (tests/golden/tool_*.npz).  There is no PyTorch implementation of any phase here."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..env import SdxEnv
+from ..randomization import RandomizedTaskMixin
+from ..scene import FINGERTIP_BODIES, HAND_BASE_BODY, TOOL_DEFAULT_ARM, FINGER_RESET_UNSCALED, robot_fk, quat_from_euler_zyx
+from .cfg import TASK_CFG, scene_from_cfg
+
+
+def synthetic_tool_grasp_bank(scene, per_type=4, seed=0):
+    """Stand-in for the unshipped ``saved_orient_grasp_{object,hand}_init_tvalue_temporal.pkl`` (TO:365-368) when no ToolPositioningGrasp
+    run hands its rings over: the hand at Grasp's reset pose (TG:1536-1548) with the hammer's handle between the fingertips, roughly in
+    the plate's orientation, small jitter per row, at rest.  Returns (hand [8, K, 23, 2], obj [8, K, 13])."""
+    rng = np.random.default_rng(seed)
+    lo, hi = scene.dof_lo, scene.dof_hi
+    q = np.concatenate([np.asarray(TOOL_DEFAULT_ARM), 0.5 * (np.asarray(FINGER_RESET_UNSCALED) + 1.0) * (hi[7:] - lo[7:]) + lo[7:]])
+    X, R, _, _ = robot_fk(q)
+    tips = np.stack([X[b] + R[b] @ np.array([0.0, 0.0, 0.04]) for b in FINGERTIP_BODIES])
+    centre = 0.5 * (tips.mean(0) + X[HAND_BASE_BODY])
+    hand = np.zeros((8, per_type, 23, 2), np.float32)
+    obj = np.zeros((8, per_type, 13), np.float32)
+    hand[..., 0] = q.astype(np.float32)
+    obj[..., 0:3] = centre.astype(np.float32) + rng.uniform(-0.005, 0.005, size=(8, per_type, 3)).astype(np.float32)
+    base = np.asarray(quat_from_euler_zyx(0.0, 3.1415, 0.0))
+    for t in range(8):
+        for k in range(per_type):
+            a = rng.uniform(-0.4, 0.4)
+            dq = np.array([0.0, 0.0, np.sin(a / 2), np.cos(a / 2)])
+            x1, y1, z1, w1 = base; x2, y2, z2, w2 = dq
+            obj[t, k, 3:7] = [w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
+                              w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2]
+    return hand, obj
+
+
+class _ToolPositioning(RandomizedTaskMixin):
+    num_obs_dict = {"partial_contact": 156, "student_partial_contact": 30}     # TG:224-227, TO:170-173
+    stack_obs = 3                                                              # TG:222, TO:168
+    TASK = None
+
+    def _setup(self, cfg, device_type, device_id, headless, seed):
+        cfg = cfg or TASK_CFG[self.TASK]
+        self.cfg = cfg
+        if device_type not in ("cuda", "GPU"):
+            raise RuntimeError("seqdex_b200 runs on CUDA devices only (the reference's --pipeline=cpu has no counterpart here)")
+        env_cfg = cfg["env"]
+        self.num_envs = int(env_cfg["numEnvs"])
+        self.max_episode_length = int(env_cfg.get("episodeLength", TASK_CFG[self.TASK]["env"]["episodeLength"]))
+        self.control_freq_inv = int(env_cfg.get("controlFrequencyInv", 1))
+        self.device = f"cuda:{device_id}"
+        self.device_id = device_id
+        self.headless = headless
+        self.one_frame_num_obs, self.one_frame_num_states = 156, 188
+        self.num_obs, self.num_states, self.num_actions = 156 * 3, 188 * 3, 23      # TG:238-243
+        self.scene = scene_from_cfg(self.TASK, cfg, seed)
+        self.env = SdxEnv(self.scene, self.num_envs, device_id, seed)
+
+    def _bind(self, cfg, seed):
+        t = self.env.tensor
+        self.obs_buf, self.states_buf, self.rew_buf = t("OBS"), t("STATES"), t("REW")
+        self.reset_buf, self.progress_buf = t("RESET"), t("PROGRESS")
+        self.successes, self.consecutive_successes = t("SUCCESSES"), t("CONSEC")
+        self.actions = t("ACTIONS")
+        self.segmentation_target_init = t("TARGET_INIT")
+        self.success_buf = t("SUCCESS")               # column 0: the episode that just ended finished aligned with the plate (TG:1428, TO:1282)
+        self.extra_target_pose = t("PLATE")           # the plate's root pose (TG:1505-1512)
+        self.meta_rew_buf = torch.zeros(self.num_envs, device=self.device)
+        zeros = torch.zeros(self.num_envs, device=self.device)
+        self.extras = {"emergence_reward": zeros, "heap_movement_penalty": zeros, "meta_reward": self.meta_rew_buf,
+                       "student_obs_buf": self.obs_buf[:, 0:30], "success_buf": torch.zeros_like(self.reset_buf)}
+        self._dr_init(cfg or TASK_CFG[self.TASK], seed)
+
+    # ---- BaseTask.step (BT:130-150)
+    def step(self, actions):
+        actions = self._dr_before(actions)
+        self.env.step(actions)
+        self._dr_after()
+        self.meta_rew_buf += self.rew_buf          # TG:1087
+
+    def pre_physics_step(self, actions):
+        self.env.pre_physics(actions)
+
+    def post_physics_step(self):
+        self.env.post_physics()
+
+    def get_states(self):
+        return self.states_buf
+
+    def render(self, sync_frame_time=False):
+        return None
+
+    def success_rate(self):
+        """mean of success_buf[:, 0] (the reference prints it at every reset, TG:1429)"""
+        return float(self.success_buf[:, 0].mean())
+
+
+class ToolPositioningGrasp(_ToolPositioning):
+    TASK = "ToolPositioningGrasp"
+
+    def __init__(self, cfg=None, sim_params=None, physics_engine=None, device_type="cuda", device_id=0, headless=True,
+                 agent_index=None, is_multi_agent=False, seed=22):
+        self._setup(cfg, device_type, device_id, headless, seed)
+        self._bind(cfg, seed)
+
+    def grasp_bank(self):
+        """the rings reset_idx fills (TG:1436-1457): (hand [8, 11024, 23, 2], obj [8, 11024, 13], index [8]) on the device"""
+        return self.env.grasp_bank()
+
+
+class ToolPositioningOrient(_ToolPositioning):
+    TASK = "ToolPositioningOrient"
+
+    def __init__(self, cfg=None, sim_params=None, physics_engine=None, device_type="cuda", device_id=0, headless=True,
+                 agent_index=None, is_multi_agent=False, grasp_bank=None, bank_per_type=4, seed=22):
+        self._setup(cfg, device_type, device_id, headless, seed)
+        if grasp_bank is None:   # TO:365-368 loads two unshipped pickles; we synthesise the same kind of data
+            grasp_bank = synthetic_tool_grasp_bank(self.scene, bank_per_type, seed)
+        self.env.set_grasp_bank(*grasp_bank)
+        self._bind(cfg, seed)
