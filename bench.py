@@ -109,7 +109,7 @@ def cpu_baseline(scene, seconds=12.0, n_envs=None, bank=None, stagger=True):
     cores = oracle.lib().sdxo_get_threads()
     n = n_envs or 32 * cores
     env = oracle.OracleEnv(scene, n)
-    if bank is not None and int(scene.c.task) == 3:
+    if bank is not None and int(scene.c.task) in (3, 5):
         env.set_grasp_bank(*bank)
     elif bank is not None:
         env.set_heap_bank(bank)
@@ -149,7 +149,7 @@ def host_bank(scene, per_type=2, settle=150):
 
 
 TASKS = {"grasp_sim": ("BlockAssemblyGraspSim", 396), "orient": ("BlockAssemblyOrient", 186), "search": ("BlockAssemblySearch", 186),
-         "insert": ("BlockAssemblyInsertSim", 75)}
+         "insert": ("BlockAssemblyInsertSim", 75), "tool_grasp": ("ToolPositioningGrasp", 468), "tool_orient": ("ToolPositioningOrient", 468)}
 
 
 def make_config(args, world):
@@ -299,9 +299,10 @@ def main():
     ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
                     help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
                          "rollout: VecTask.step only with U(-1,1) actions")
-    ap.add_argument("--task", default="grasp_sim", choices=["grasp_sim", "orient", "search", "insert", "chain"],
+    ap.add_argument("--task", default="grasp_sim", choices=["grasp_sim", "orient", "search", "insert", "chain", "tool_grasp", "tool_orient"],
                     help="grasp_sim: BlockAssemblyGraspSim, the BASELINE.json metric (configs[1]); orient: BlockAssemblyOrient (configs[2]: "
-                         "32768 envs over 2 GPUs = --gpus 2 with the default 16384 envs per GPU)")
+                         "32768 envs over 2 GPUs = --gpus 2 with the default 16384 envs per GPU); tool_grasp / tool_orient: the two "
+                         "ToolPositioning tasks of configs[4] (65536 envs over 8 GPUs = --gpus 8 --num-envs 8192)")
     ap.add_argument("--minibatch", type=int, default=32768,
                     help="PPO minibatch; the yaml's 4 is a 4-env smoke value (SURVEY.md section 7): default = batch/4 at 16384 envs x horizon 8")
     args = ap.parse_args()
@@ -334,7 +335,13 @@ def main():
     scene = scene_from_cfg(task_name)               # the task's yaml-stated sim / env parameters (contact_offset 0.02 for Orient / Search)
     obs_dim, state_dim = TASKS[args.task][1], (188 if insert else 564)
     env = SdxEnv(scene, n, local, seed=22 + rank)
-    if insert:                                      # InsertSim restores banked grasps (IS:372-375): synthetic stand-ins here, GraspSim's rings in --task chain
+    if args.task == "tool_grasp":                   # resets to a fixed start pose (TG:1459-1578): no bank
+        bank = None
+    elif args.task == "tool_orient":                # restores banked grasps (TO:365-368): synthetic stand-ins here
+        from seqdex_b200.tasks.tool_positioning import synthetic_tool_grasp_bank
+        bank = synthetic_tool_grasp_bank(scene, min(args.bank_per_type, 64), seed=22 + rank)
+        env.set_grasp_bank(*bank)
+    elif insert:                                    # InsertSim restores banked grasps (IS:372-375): synthetic stand-ins here, GraspSim's rings in --task chain
         from seqdex_b200.tasks.block_assembly_insert_sim import synthetic_grasp_bank
         bank = synthetic_grasp_bank(scene, min(args.bank_per_type, 64), seed=22 + rank)
         env.set_grasp_bank(*bank)
@@ -506,7 +513,7 @@ def main():
         peak, which = measured_peaks()
         achieved = ALGO_BYTES_PER_ENV_STEP * n / (sim_ms * 1e-3) / 1e9
         out = {
-            "metric": f"env-steps/sec at num_envs=16384 ({task_name})", "value": world * n * K / (ms * 1e-3),
+            "metric": f"env-steps/sec at num_envs={n} ({task_name})" if n != 16384 or args.task != "grasp_sim" else "env-steps/sec at num_envs=16384 (BlockAssemblyGraspSim)", "value": world * n * K / (ms * 1e-3),
             "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": make_config(args, world),
@@ -555,8 +562,11 @@ def main():
                 "note": "algorithmic bf16 FLOPs of the policy / central-value forward passes and the 5 mini-epochs of updates over ALL PPO time of an "
                         "iteration (iteration time minus its 8 env steps): GEMMs, their conversions, loss / Adam kernels and launch gaps included; "
                         "per-kernel tensor-pipe counters: profiles/r02_ncu_gemm.txt"}
+        if args.task.startswith("tool"):
+            out["roofline"]["note"] = ("ToolPositioning scene (ONE free body of two boxes + the arm and hand): the per-env byte / flop / ncu constants above "
+                                       "are the 72-brick GraspSim scene's and overstate this scene's traffic; ms_per_launch and the shares are measured")
         if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(scene, bank=None if search else bank if insert else bank.cpu().numpy(), stagger=not orient,
+            out["cpu_baseline"] = cpu_baseline(scene, bank=None if bank is None else bank if isinstance(bank, tuple) else bank.cpu().numpy(), stagger=not orient,
                                                n_envs=1024 if orient else None)
         emit(out)
     if world > 1:

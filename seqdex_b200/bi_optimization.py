@@ -11,8 +11,11 @@ it is treated as the SPECIFICATION of the schedule: the same two functions, the 
 device (``chain.py``) and the rows the t-value trainer needs recorded by the env (``sdx_tvalue_dataset``) or gathered from the task's
 buffers instead of going through HDF5 files.
 
-``ToolPositioning`` (BO:127-134: Grasp, Orient forward; Orient backward) is the same loop over two tasks this engine does not have;
-asking for it raises ``NotImplementedError``.
+``ToolPositioning`` (BO:127-134) is the same loop over two tasks: ToolPositioningGrasp and ToolPositioningOrient forward (Orient starts
+from the grasps Grasp banked), Orient backward with its rows recorded, then the t-value fit.  What Orient records (TO:1287-1296) is the
+tool's pose at the START of the episode, 7 wide, labelled by the episode's success; ``TValue_Trainer`` holds 4-wide rows (TVT:158-159) and
+re-normalises each row to a unit quaternion (TVT:217), so as written the 7-wide assignment fails -- here the quaternion part of the
+pose is what is fitted.
 
 Nothing here computes: PPO is ``ppo.A2CAgent`` (CUDA kernels), the t-value fit is ``tvalue.TValueTrainer``.
 """
@@ -26,11 +29,14 @@ import torch
 from . import bank_io
 from .chain import grasp_bank_for_insert
 from .ppo import A2CAgent, PPOConfig
-from .tasks import BlockAssemblyGraspSim, BlockAssemblyInsertSim, BlockAssemblyOrient, BlockAssemblySearch
+from .tasks import (BlockAssemblyGraspSim, BlockAssemblyInsertSim, BlockAssemblyOrient, BlockAssemblySearch, ToolPositioningGrasp,
+                    ToolPositioningOrient)
+from .tasks.tool_positioning import synthetic_tool_grasp_bank
 from .tvalue import TValueTrainer
 from .vec_task import RLgamesVecTaskPython
 
 STAGES = ("BlockAssemblySearch", "BlockAssemblyOrient", "BlockAssemblyGraspSim", "BlockAssemblyInsertSim")
+TOOL_STAGES = ("ToolPositioningGrasp", "ToolPositioningOrient")
 # the PPO yaml main_rlgames picks per task (BO:44-52): ppo_continuous_insert.yaml = minibatch 4096, critic_coef 4 -- the value loss is
 # the central-value net's here, which has its own optimiser, so only the minibatch differs
 _PPO = {"BlockAssemblyInsertSim": dict(minibatch_size=4096)}
@@ -43,6 +49,7 @@ class StageState:
         self.heaps_medium = None      # Search  -> Orient   : saved_searching_ternimal_states_medium_mo_tvalue.pkl
         self.heaps_good = None        # Orient  -> GraspSim : saved_searching_ternimal_states_good_mo_tvalue.pkl
         self.grasps = None            # GraspSim -> InsertSim: saved_grasping_{hand,object}_ternimal_states_good_mo_sim.pkl
+        self.tool_grasps = None       # ToolPositioningGrasp -> Orient: saved_orient_grasp_{object,hand}_init_tvalue_temporal.pkl (TO:365-368)
         self.tvalue = {}              # task -> flat GraspInsertTValue weights fitted by transition_value_trainer
         self.datasets = {}            # task -> (success rows [n, 4], failure rows [m, 4])
 
@@ -64,6 +71,10 @@ def _build(task, num_envs, state, device_id, seed, bank_capacity):
         return t
     if task == "BlockAssemblyInsertSim":
         return BlockAssemblyInsertSim(_cfg(num_envs), device_id=device_id, seed=seed, grasp_bank=state.grasps)
+    if task == "ToolPositioningGrasp":
+        return ToolPositioningGrasp(_cfg(num_envs), device_id=device_id, seed=seed)
+    if task == "ToolPositioningOrient":
+        return ToolPositioningOrient(_cfg(num_envs), device_id=device_id, seed=seed, grasp_bank=state.tool_grasps)
     raise ValueError(task)
 
 
@@ -85,6 +96,8 @@ def _harvest(task_name, task, state, seed):
         state.grasps, _ = grasp_bank_for_insert(env, task.scene, seed=seed)
         s, f, _ = env.tvalue_dataset()
         state.datasets[task_name] = (s.clone(), f.clone())
+    elif task_name == "ToolPositioningGrasp":
+        state.tool_grasps, _ = grasp_bank_for_insert(env, task.scene, seed=seed, synthetic=synthetic_tool_grasp_bank)
 
 
 def main_rlgames(task, num_envs, use_t_value=False, policy_path="", state=None, iterations=4, device_id=0, seed=22, work_dir="runs",
@@ -104,20 +117,26 @@ def main_rlgames(task, num_envs, use_t_value=False, policy_path="", state=None, 
         agent.restore(policy_path)
     rows_s, rows_f = [], []
     info = {}
+    steps_done = 0
+    record = use_t_value and task in ("BlockAssemblyInsertSim", "ToolPositioningOrient")
     for _ in range(iterations):
-        if task == "BlockAssemblyInsertSim" and use_t_value:
+        if record:
             # one rollout step at a time so that the rows can be gathered where the reference gathers them (in reset_idx)
             if agent.obs is None:
                 first = venv.reset()
                 agent.set_obs(first["obs"], first["states"])
             for k in range(agent.H):
                 a = agent.act(k)
-                qcam = t.states_buf[:, 177:181].clone()                      # camera_view_segmentation_target_rot of the state the episode may end in
+                if task == "ToolPositioningOrient":
+                    qcam = t.segmentation_target_init[:, 3:7].clone()        # t_value_obs_buf: the pose the episode STARTED from (TO:1290, 1400)
+                else:
+                    qcam = t.states_buf[:, 177:181].clone()                  # camera_view_segmentation_target_rot of the state the episode may end in
                 o, rew, dones, _ = venv.step(a)
                 agent.next_obs.copy_(o["obs"]); agent.next_states.copy_(o["states"])
                 agent.record(k, rew, dones)
                 ended = t.progress_buf == 1                                   # envs whose reset_idx ran in this step (progress 0 -> 1): success_buf is theirs (IS:1348-1350)
-                if bool(ended.any()):
+                steps_done += 1
+                if steps_done > 1 and bool(ended.any()):                      # the resets of the very first step end no episode (total_steps > 0, IS:1388, TO:1287)
                     ok = t.success_buf[:, 0] > 0.5
                     rows_s.append(qcam[ended & ok]); rows_f.append(qcam[ended & ~ok])
             agent.finish_rollout()
@@ -149,16 +168,30 @@ def transition_value_trainer(task, rollout, state, device_id=0, seed=22, min_row
 def bi_optimization(tasks="BlockAssembly", rounds=10, num_envs=None, iterations=4, tvalue_rollout=10000, device_id=0, seed=22, work_dir="runs",
                     log=None):
     """BO:115-134.  ``num_envs``: dict task -> envs (the script's 128 / 512 / 512 / 512 by default)."""
-    if tasks == "ToolPositioning":
-        raise NotImplementedError("ToolPositioningGrasp / ToolPositioningOrient are not built (DESIGN.md section 1); the schedule is BO:127-134")
-    if tasks != "BlockAssembly":
+    if tasks not in ("BlockAssembly", "ToolPositioning"):
         raise Exception("Unrecognized task!")                                 # BO:136-138
-    ne = {"BlockAssemblySearch": 128, "BlockAssemblyOrient": 512, "BlockAssemblyGraspSim": 512, "BlockAssemblyInsertSim": 512}
+    ne = {"BlockAssemblySearch": 128, "BlockAssemblyOrient": 512, "BlockAssemblyGraspSim": 512, "BlockAssemblyInsertSim": 512,
+          "ToolPositioningGrasp": 512, "ToolPositioningOrient": 512}
     ne.update(num_envs or {})
     state = StageState()
     history = []
     say = log or (lambda *a: None)
     kw = dict(iterations=iterations, device_id=device_id, seed=seed, work_dir=work_dir)
+    if tasks == "ToolPositioning":                                            # BO:127-134
+        for i in range(rounds):
+            rec = {"round": i}
+            paths = {}
+            for task in TOOL_STAGES:
+                paths[task], info = main_rlgames(task, ne[task], state=state, **kw)
+                rec[f"forward/{task}"] = info.get("mean_reward")
+                say(i, "forward", task, info)
+            task = "ToolPositioningOrient"
+            _, info = main_rlgames(task, ne[task], use_t_value=True, policy_path=paths[task], state=state, **kw)
+            rec[f"backward/{task}"] = info.get("mean_reward")
+            rec[f"tvalue/{task}"] = transition_value_trainer(task, tvalue_rollout, state, device_id, seed)
+            say(i, "backward", task, info, rec[f"tvalue/{task}"])
+            history.append(rec)
+        return history, state
     for i in range(rounds):
         rec = {"round": i}
         # forward initialisation (BO:118-121)

@@ -54,15 +54,16 @@ def _run(env, policy, steps, timing=None, name=None):
     return float(rew_sum) / max(steps, 1)
 
 
-def grasp_bank_for_insert(grasp_env, scene, fill=4, seed=0):
+def grasp_bank_for_insert(grasp_env, scene, fill=4, seed=0, synthetic=synthetic_grasp_bank):
     """GraspSim's terminal-state rings -> the bank InsertSim restores from: (hand [8, K, 23, 2], obj [8, K, 13]) on the device, K = the
     most grasps any brick type banked; a type that banked fewer cycles through its own rows, a type that banked NONE (an untrained
-    policy rarely lifts every type) is filled with the synthetic stand-in grasps, and how many types that were is returned."""
+    policy rarely lifts every type) is filled with the synthetic stand-in grasps, and how many types that were is returned.
+    The same hand-over serves ToolPositioningGrasp -> ToolPositioningOrient (``synthetic`` = tasks.tool_positioning.synthetic_tool_grasp_bank)."""
     hand, obj, idx = grasp_env.grasp_bank()
     torch.cuda.synchronize()
     counts = [min(int(c), hand.shape[1]) for c in idx.cpu().tolist()]
     K = max(max(counts), fill)
-    sh, so = synthetic_grasp_bank(scene, K, seed)
+    sh, so = synthetic(scene, K, seed)
     out_h = torch.from_numpy(sh).to(hand.device)
     out_o = torch.from_numpy(so).to(hand.device)
     for ty, c in enumerate(counts):

@@ -18,6 +18,8 @@ GENERATORS = {
     "gen_golden_reset.py": ["reset_idx.npz"],
     "gen_golden_cfg.py": ["task_cfg.json"],
     "gen_golden_insert.py": ["insert_post_physics.npz", "insert_pre_physics.npz", "insert_reset.npz"],
+    "gen_golden_tool.py": ["tool_grasp_post.npz", "tool_grasp_pre.npz", "tool_grasp_reset.npz", "tool_orient_post.npz", "tool_orient_pre.npz",
+                           "tool_orient_reset.npz"],
     "gen_golden_ppo.py": ["ppo_neglogp.npz", "ppo_ac_loss.npz", "ppo_play_steps.npz", "ppo_prepare_dataset.npz", "ppo_schedule_legacy.npz",
                           "ppo_schedule_standard.npz", "tvalue_trainer.npz"],
 }
