@@ -244,6 +244,12 @@ int sdx_insert_test_hooks(sdx_env_t* env, const int* slot_by_env_host, int plate
  * sdx_tool_test_hooks: parity-test hook like sdx_insert_test_hooks -- bank slot per env (NULL: drawn), pitch index k of the next
  * reset_idx calls (-1: drawn), yaw draw u in [-1, 1) per env (NULL: drawn). */
 int sdx_tool_test_hooks(sdx_env_t* env, const int* slot_by_env_host, int pitch_k, const float* yaw_u_host);
+/* ToolPositioningOrient's online t-value update (TO:1305-1350; `if_t_value`, hard-wired False at TO:377, so opt-in here): the labels
+ * reset_idx computes for ALL envs from their current state -- success = the tool within 1 cm of the plate's position and within 0.1 rad
+ * of its orientation or that orientation turned by pi about z (TO:1306-1316).  Writes SDX_T_SUCCESS = [success, not success] and
+ * label_dev i32[N] = 0 (success) / 1 (failure), the class index sdx_tvalue_bce takes.  The rows are SDX_T_TARGET_INIT
+ * (t_value_obs_buf = the pose each episode started from, TO:1400); the five Adam steps run on sdx_mlp_* (tasks/tool_positioning.py). */
+int sdx_tool_tvalue_labels(sdx_env_t* env, int* label_dev);
 /* number of contact steps the last sdx_pre_physics spent inside reset_idx (0 when nobody reset; 103 for a full Orient reset) */
 int sdx_last_reset_sim_steps(const sdx_env_t* env);
 /* BlockAssemblySearch's camera features (SE = tasks/block_assembly/allegro_hand_block_assembly_search.py): the reference renders

@@ -327,12 +327,57 @@ def main():
                 C.reset_idx(r, env_ids, torch.tensor([], dtype=torch.long))
             so = np.zeros(N, np.int32); so[env_ids.numpy()] = slots
             extra = dict(slot_by_env=so, bank_obj=torch.stack(r.saved_grasping_object_ternimal_states_list).numpy(),
-                         bank_hand=torch.stack(r.saved_grasping_hand_ternimal_states_list).numpy(), t_value_obs=r.t_value_obs_buf.numpy())
-        np.savez(os.path.join(OUT, f"tool_{name}_reset.npz"), root_out=root2.numpy(), dof_out=dof2.numpy(), prev_targets=r.prev_targets.numpy(),
-                 cur_targets=r.cur_targets.numpy(), init_pos=r.segmentation_target_init_pos.numpy(), init_rot=r.segmentation_target_init_rot.numpy(),
-                 progress_out=r.progress_buf.numpy(), reset_out=r.reset_buf.numpy(), successes_out=r.successes.numpy(), success_buf=r.success_buf.numpy(),
-                 **rin, **extra)
-        print(f"tool {name} golden vectors written to", os.path.normpath(OUT), "| successes at reset:", r.success_buf[env_ids, 0].tolist())
+                         bank_hand=torch.stack(r.saved_grasping_hand_ternimal_states_list).numpy(), t_value_obs=r.t_value_obs_buf.numpy().copy())
+            first = dict(root_out=root2.numpy().copy(), dof_out=dof2.numpy().copy(), prev_targets=r.prev_targets.numpy().copy(),
+                         cur_targets=r.cur_targets.numpy().copy(), init_pos=r.segmentation_target_init_pos.numpy().copy(),
+                         init_rot=r.segmentation_target_init_rot.numpy().copy(), progress_out=r.progress_buf.numpy().copy(),
+                         reset_out=r.reset_buf.numpy().copy(), successes_out=r.successes.numpy().copy(), success_buf=r.success_buf.numpy().copy())
+            # ---- a second reset_idx call with the online t-value update switched on (TO:1305-1350; `if_t_value` is hard-wired False at TO:377)
+            from policy_sequencing.terminal_value_function import GraspInsertTValue
+            torch.manual_seed(99)
+            r.if_t_value = True
+            r.t_value = GraspInsertTValue(input_dim=7, output_dim=2)
+            r.t_value_optimizer = torch.optim.Adam(r.t_value.parameters(), lr=0.0003)              # TO:384
+            r.bce_logits_loss = torch.nn.BCEWithLogitsLoss()                                       # TO:387
+            r.extras, r.max_episode_length, r.t_value_save_path = {}, 125, "/nonexistent"
+            r.t_value_obs_buf = torch.cat([torch.randn(N, 3) * 0.1 + torch.tensor([0.2, -0.1, 0.9]), rq(N)], -1)
+            r.extra_target_pos, r.extra_target_rot = root2[f.extra_object_indices, 0:3].clone(), root2[f.extra_object_indices, 3:7].clone()
+            r.symmetry_extra_target_rot = TU.quat_mul(r.extra_target_rot, to_torch([0.0, 0.0, 1.0, 0.0]).repeat(N, 1))
+            tpos, trot = root2[f.lego_segmentation_indices, 0:3].clone(), root2[f.lego_segmentation_indices, 3:7].clone()
+            for e in range(0, N, 2):                    # half of the envs ended aligned with the plate (or its pi-about-z twin) within 1 cm
+                tpos[e] = r.extra_target_pos[e] + torch.randn(3) * 0.003
+                dq = torch.tensor([0.01, -0.02, 0.015, 1.0])
+                base = r.symmetry_extra_target_rot[e] if e % 4 == 0 else r.extra_target_rot[e]
+                trot[e] = TU.quat_mul(base[None], (dq / dq.norm())[None])[0]
+            tpos[2] = r.extra_target_pos[2] + torch.tensor([0.02, 0.0, 0.0])                       # aligned but 2 cm away: a failure
+            r.segmentation_target_pos, r.segmentation_target_rot = tpos, trot
+            w0 = torch.cat([p_.detach().reshape(-1) for p_ in r.t_value.parameters()]).numpy().copy()
+            losses = []
+            real_bce = r.bce_logits_loss
+
+            def rec_bce(pred, target):
+                out_ = real_bce(pred, target)
+                losses.append(float(out_))
+                return out_
+            r.bce_logits_loss = rec_bce
+            env_ids2 = torch.tensor([1, 2, 6])
+            r.reset_buf[env_ids2] = 1
+            tv_in = r.t_value_obs_buf.numpy().copy()
+            calls["n"] = 0
+            slots[:] = slots[:3] + slots[3:]
+            with mock.patch.object(M.random, "sample", fake_sample), mock.patch.object(M, "print", lambda *a, **k: None, create=True):
+                C.reset_idx(r, env_ids2, torch.tensor([], dtype=torch.long))
+            w5 = torch.cat([p_.detach().reshape(-1) for p_ in r.t_value.parameters()]).numpy().copy()
+            extra.update(tv_obs_in=tv_in, tv_target_pos=tpos.numpy(), tv_target_rot=trot.numpy(), tv_plate=root2[f.extra_object_indices, 0:7].numpy().copy(),
+                         tv_success_buf=r.success_buf.numpy().copy(), tv_w0=w0, tv_w5=w5, tv_losses=np.asarray(losses, np.float32),
+                         tv_pred_last=r.predict_success_confident.detach().numpy().copy())
+            print("tool orient online t-value: successes", int(r.success_buf[:, 0].sum()), "of", N, "losses", [round(x, 4) for x in losses])
+        outs = first if name == "orient" else dict(
+            root_out=root2.numpy(), dof_out=dof2.numpy(), prev_targets=r.prev_targets.numpy(), cur_targets=r.cur_targets.numpy(),
+            init_pos=r.segmentation_target_init_pos.numpy(), init_rot=r.segmentation_target_init_rot.numpy(), progress_out=r.progress_buf.numpy(),
+            reset_out=r.reset_buf.numpy(), successes_out=r.successes.numpy(), success_buf=r.success_buf.numpy())
+        np.savez(os.path.join(OUT, f"tool_{name}_reset.npz"), **outs, **rin, **extra)
+        print(f"tool {name} golden vectors written to", os.path.normpath(OUT), "| successes at reset:", outs["success_buf"][env_ids.numpy(), 0].tolist())
 
 
 if __name__ == "__main__":

@@ -313,6 +313,12 @@ class OracleEnv:
                                self.slp.ctypes.data_as(ctypes.c_void_p), fp(self.obs), fp(self.states))
         self.refresh_links()                      # the hand was teleported: pre_physics reads its pose before any contact step
 
+    def tool_tvalue_labels(self):
+        """TO:1305-1316: success_buf for ALL envs from the current state; returns the class index per env (0 success, 1 failure)"""
+        label = np.zeros(self.n, np.int32)
+        self.L.sdxo_tool_tvalue_labels(self.S, self.n, fp(self.brick), fp(self.plate), fp(self.success_buf), ip(label))
+        return label
+
     def pre_physics(self, actions):
         if self.task in (4, 5):
             if self.reset.any():

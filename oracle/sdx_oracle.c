@@ -2121,3 +2121,18 @@ void sdxo_tool_post_physics(const sdx_scene_t* S, int n, int orient, const float
   }
   if (num_resets > 0) consec[0] = S->av_factor * finished / (float)num_resets + (1.0f - S->av_factor) * consec[0];
 }
+
+/* ToolPositioningOrient, online t-value update (TO:1305-1316): success_buf for ALL envs from the current state; label = the column that is 1 */
+void sdxo_tool_tvalue_labels(const sdx_scene_t* S, int n, const float* brick, const float* plate, float* success_buf, int* label) {
+  for (int e = 0; e < n; ++e) {
+    float tg[13];
+    brick_root_row(S, brick + (size_t)e * 13 * NB, TOOL_BODY, tg);
+    const float* pl = plate + 7 * e;
+    q4 tq = {tg[3], tg[4], tg[5], tg[6]}, eq = {pl[3], pl[4], pl[5], pl[6]};
+    float rd = rot_dist_sym(tq, eq);
+    v3 dp = vsub(V3(pl[0], pl[1], pl[2]), V3(tg[0], tg[1], tg[2]));
+    float ok = (sqrtf(vdot(dp, dp)) < 0.01f && rd < 0.1f) ? 1.0f : 0.0f;
+    success_buf[2 * e] = ok; success_buf[2 * e + 1] = ok <= 0.5f ? 1.0f : 0.0f;
+    label[e] = ok > 0.5f ? 0 : 1;
+  }
+}

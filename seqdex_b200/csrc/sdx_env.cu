@@ -342,6 +342,14 @@ static int tool_pre_physics(sdx_env_t* E, const float* actions_dev) {
   CKL();
   return 0;
 }
+extern "C" int sdx_tool_tvalue_labels(sdx_env_t* E, int* label_dev) {
+  if (!E || !label_dev || E->task != SDX_TASK_TOOL_ORIENT) { g_err = "sdx_tool_tvalue_labels: needs a ToolPositioningOrient env and a device label buffer"; return -1; }
+  CK(cudaSetDevice(E->device));
+  k_tool_tvalue_labels<<<(E->n + 127) / 128, 128, 0, E->stream>>>(E->scene, E->n, F(SDX_T_BRICK), F(SDX_T_PLATE), F(SDX_T_SUCCESS), label_dev);
+  E->launches++;
+  CKL();
+  return 0;
+}
 extern "C" int sdx_tool_test_hooks(sdx_env_t* E, const int* slot_by_env_host, int pitch_k, const float* yaw_u_host) {
   if (!E || !is_tool(E->task)) { g_err = "sdx_tool_test_hooks: the env does not run a ToolPositioning task"; return -1; }
   if (pitch_k > 3) { g_err = "sdx_tool_test_hooks: pitch index out of range"; return -1; }

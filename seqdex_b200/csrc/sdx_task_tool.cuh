@@ -82,6 +82,23 @@ k_tool_bank(const sdx_scene_t* __restrict__ S, int n, const float* __restrict__ 
   if (tid == 0) gb_index[ty] = (base + total) % (SDX_TOOL_BANK_WRAP + 1);
 }
 
+// Labels of ToolPositioningOrient's online t-value update (TO:1305-1316), for ALL envs from their CURRENT state: success = the tool within
+// 1 cm of the plate's position and within 0.1 rad of its orientation or that orientation turned by pi about z.  Writes
+// success_buf = [success, not success] and label = the column that is 1 (0 success, 1 failure: the target layout of sdx_tvalue_bce).
+__global__ void k_tool_tvalue_labels(const sdx_scene_t* __restrict__ S, int n, const float* __restrict__ brick, const float* __restrict__ plate,
+                                     float* __restrict__ success_buf, int* __restrict__ label) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float tg[13];
+  brick_root_row(S, brick + (size_t)e * 13 * NB, TOOL_BODY, tg);
+  const float* pl = plate + 7 * e;
+  const float rd = rot_dist_sym(Q4(tg[3], tg[4], tg[5], tg[6]), Q4(pl[3], pl[4], pl[5], pl[6]));
+  const v3 dp = vsub(V3(pl[0], pl[1], pl[2]), V3(tg[0], tg[1], tg[2]));
+  const float ok = (sqrtf(vdot(dp, dp)) < 0.01f && rd < 0.1f) ? 1.0f : 0.0f;
+  success_buf[2 * e] = ok; success_buf[2 * e + 1] = ok <= 0.5f ? 1.0f : 0.0f;
+  label[e] = ok > 0.5f ? 0 : 1;
+}
+
 // orient = 0: TG reset_idx; orient = 1: TO reset_idx.  slot_by_env / yaw_u (nullable) are the parity tests' hooks.
 __global__ void __launch_bounds__(128)
 k_tool_reset(const sdx_scene_t* __restrict__ S, int n, int orient, uint64_t seed, const float* __restrict__ bank_obj,

@@ -198,6 +198,13 @@ class SdxEnv:
         _lib.check(self.L.sdx_tool_test_hooks(self.h, s.ctypes.data_as(ctypes.c_void_p) if s is not None else None, int(pitch_k),
                                               u.ctypes.data_as(ctypes.c_void_p) if u is not None else None))
 
+    def tool_tvalue_labels(self, out=None):
+        """ToolPositioningOrient's online t-value labels (TO:1305-1316): int32 [N] on the device, 0 success / 1 failure; also writes SUCCESS"""
+        if out is None:
+            out = torch.zeros(self.n, dtype=torch.int32, device=self.device)
+        _lib.check(self.L.sdx_tool_tvalue_labels(self.h, ctypes.c_void_p(out.data_ptr())))
+        return out
+
     def last_reset_sim_steps(self):
         return int(self.L.sdx_last_reset_sim_steps(self.h))
 

@@ -13,9 +13,12 @@ density; Isaac Gym collides a V-HACD decomposition of harmmer.obj.  Observations
 reference's, pinned by goldens (tests/golden/tool_*.npz).  There is no PyTorch implementation of any phase here."""
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
+from .. import _lib
 from ..env import SdxEnv
 from ..randomization import RandomizedTaskMixin
 from ..scene import FINGERTIP_BODIES, HAND_BASE_BODY, TOOL_DEFAULT_ARM, FINGER_RESET_UNSCALED, robot_fk, quat_from_euler_zyx
@@ -125,9 +128,53 @@ class ToolPositioningOrient(_ToolPositioning):
     TASK = "ToolPositioningOrient"
 
     def __init__(self, cfg=None, sim_params=None, physics_engine=None, device_type="cuda", device_id=0, headless=True,
-                 agent_index=None, is_multi_agent=False, grasp_bank=None, bank_per_type=4, seed=22):
+                 agent_index=None, is_multi_agent=False, grasp_bank=None, bank_per_type=4, seed=22, if_t_value=False):
         self._setup(cfg, device_type, device_id, headless, seed)
         if grasp_bank is None:   # TO:365-368 loads two unshipped pickles; we synthesise the same kind of data
             grasp_bank = synthetic_tool_grasp_bank(self.scene, bank_per_type, seed)
         self.env.set_grasp_bank(*grasp_bank)
         self._bind(cfg, seed)
+        # the online t-value update inside reset_idx (TO:1305-1350).  The reference hard-wires `self.if_t_value = False` (TO:377), so it
+        # is opt-in here: GraspInsertTValue(input_dim=7) on the tensor-core MLP, Adam(lr=3e-4), BCE-with-logits (TO:379-387)
+        self.if_t_value = bool(if_t_value)
+        self.total_steps = 0
+        if self.if_t_value:
+            from ..ppo import MLP
+            self.t_value = MLP(7, 2, self.num_envs, device=device_id, seed=seed, hidden=(256, 128, 64))
+            self._tv_label = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+            self._tv_dz = torch.zeros(self.num_envs, 2, device=self.device)
+            self._tv_stats = torch.zeros(4, device=self.device)
+
+    def online_t_value_update(self, steps=5, lr=0.0003):
+        """TO:1305-1350: labels for ALL envs from their current state (``sdx_tool_tvalue_labels``: within 1 cm and 0.1 rad of the plate's
+        pose or its pi-about-z twin; also what ``success_buf`` holds afterwards), rows = ``t_value_obs_buf`` = the pose each episode
+        started from (``SDX_T_TARGET_INIT``), five Adam steps of BCE-with-logits on the net's ELU outputs.  Returns the last loss."""
+        L = _lib.load()
+        n = self.num_envs
+        labels = self.env.tool_tvalue_labels(self._tv_label)
+        x = self.segmentation_target_init.contiguous()
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        z = None
+        for _ in range(steps):
+            z = self.t_value.forward(x, train=True)
+            self._tv_stats.zero_()
+            _lib.check(L.sdx_tvalue_bce(ctypes.c_void_p(z.data_ptr()), ctypes.c_void_p(labels.data_ptr()), n, ctypes.c_void_p(self._tv_dz.data_ptr()),
+                                        ctypes.c_void_p(self._tv_stats.data_ptr()), stream))
+            self.t_value.backward(self._tv_dz)
+            self.t_value.adam(lr, max_norm=0.0)
+        loss = self._tv_stats[0] / (2 * n)
+        y = torch.nn.functional.elu(z)                                   # predict_success_confident of the last forward (TO:1321)
+        self.extras["BCE_loss"] = loss
+        self.extras["predict_success_confident"], self.extras["predict_unsuccess_confident"] = y[:, 0].mean(), y[:, 1].mean()
+        self.extras["success_buf"] = self.success_buf[:, 0].mean()
+        return loss
+
+    def step(self, actions):
+        if self.if_t_value and self.total_steps > 0 and bool(self.reset_buf.any()):     # reset_idx is about to run (TO:1446-1447)
+            self.online_t_value_update()
+            keep = self.success_buf.clone()           # the labels are what success_buf holds when reset_idx returns (TO:1312-1316 after :1282)
+            super().step(actions)
+            self.success_buf.copy_(keep)
+        else:
+            super().step(actions)
+        self.total_steps += 1

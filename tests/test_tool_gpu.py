@@ -227,3 +227,49 @@ def test_tool_grasp_scripted_lift_banks_grasps():
     assert torch.isfinite(t.obs_buf).all() and torch.isfinite(t.rew_buf).all()
     assert float(t.rew_buf.min()) >= 0.0 and float(t.rew_buf.max()) <= 4.0 + 1e-5        # exp(...) <= 1, x (1 + 10 * 0.2) + 1 (TG:1877)
     assert float(z.min()) > 0.55, "no hammer may fall through the bin / table"
+
+
+def test_tool_orient_online_tvalue_update_vs_reference(oracle_lib):
+    """the online t-value update of TO's reset_idx (TO:1305-1350) executed by the reference with `if_t_value` on: same labels (kernel ==
+    oracle == reference), and five Adam steps on the tensor-core MLP follow the reference's five losses within bf16 tolerance"""
+    from seqdex_b200.tasks import ToolPositioningOrient
+    d = dict(np.load(os.path.join(G, "tool_orient_reset.npz")))
+    n = d["tv_obs_in"].shape[0]
+    t = ToolPositioningOrient({"env": {"numEnvs": n}, "sim": {}, "task": {"randomize": False}}, if_t_value=True)
+    o = oracle_lib.OracleEnv(t.scene, n)
+    rows = np.zeros((n, 13), np.float32)
+    rows[:, 0:3], rows[:, 3:7] = d["tv_target_pos"], d["tv_target_rot"]
+    o.set_brick_roots(_rows72(rows))
+    o.plate[:] = d["tv_plate"]
+    t.env.tensor("BRICK").copy_(torch.from_numpy(o.brick))
+    t.env.tensor("PLATE").copy_(torch.from_numpy(o.plate))
+    t.segmentation_target_init.copy_(torch.from_numpy(d["tv_obs_in"]))
+    t.t_value.load_flat(torch.from_numpy(d["tv_w0"]))
+    losses = []
+    for k in range(5):
+        losses.append(float(t.online_t_value_update(steps=1)))
+    torch.cuda.synchronize()
+    _cmp("labels", t._tv_label, o.tool_tvalue_labels())
+    _cmp("success_buf", t.success_buf, o.success_buf)
+    np.testing.assert_array_equal(t.success_buf.cpu().numpy(), d["tv_success_buf"])
+    np.testing.assert_allclose(losses, d["tv_losses"], rtol=0, atol=3e-3)
+    assert losses[-1] < losses[0]
+    dw, dref = t.t_value.params.cpu() - torch.from_numpy(d["tv_w0"]), torch.from_numpy(d["tv_w5"] - d["tv_w0"])
+    big = dref.abs() > 1.2e-3                                                # five Adam steps at lr 3e-4 with a steady gradient sign move 1.5e-3
+    assert int(big.sum()) > 1000
+    assert float((torch.sign(dw[big]) == torch.sign(dref[big])).float().mean()) > 0.97
+    assert float((dw - dref).abs().mean()) < 2e-4
+
+
+def test_tool_orient_runs_with_online_tvalue():
+    """with `if_t_value` the update runs inside step() whenever reset_idx is about to (TO:1305), and success_buf then holds its labels"""
+    from seqdex_b200.tasks import ToolPositioningOrient
+    t = ToolPositioningOrient({"env": {"numEnvs": 64}, "sim": {}, "task": {"randomize": False}}, if_t_value=True)
+    w0 = t.t_value.params.clone()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for k in range(130):                                                      # one 125-step episode: every env times out once
+        t.step(torch.rand(64, 23, device="cuda", generator=g) * 2 - 1)
+    assert "BCE_loss" in t.extras and torch.isfinite(t.extras["BCE_loss"])
+    assert float((t.t_value.params - w0).abs().max()) > 0
+    sb = t.success_buf
+    assert torch.equal(sb[:, 1], (sb[:, 0] <= 0.5).float())                   # TO:1316

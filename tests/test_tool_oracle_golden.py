@@ -204,3 +204,19 @@ def test_tool_orient_reset_idx_matches_reference(oracle_lib):
     np.testing.assert_array_equal(o.success_buf[ids, 0], d["success_buf"][ids, 0])
     assert 0 < d["success_buf"][ids, 0].sum() < len(ids)
     assert np.all(o.obs == 1.5) and np.all(o.states == -2.5)                            # TO keeps its history across resets
+
+
+def test_tool_orient_online_tvalue_labels_match_reference(oracle_lib):
+    """TO:1305-1316, executed by the reference with `if_t_value` switched on: success_buf for ALL envs = within 1 cm of the plate and within
+    0.1 rad of its orientation or the pi-about-z twin"""
+    d = _load("tool_orient_reset.npz")
+    n = d["tv_obs_in"].shape[0]
+    o = oracle_lib.OracleEnv(_scene("orient"), n)
+    rows = np.zeros((n, 13), np.float32)
+    rows[:, 0:3], rows[:, 3:7] = d["tv_target_pos"], d["tv_target_rot"]
+    o.set_brick_roots(_rows72(rows))
+    o.plate[:] = d["tv_plate"]
+    label = o.tool_tvalue_labels()
+    np.testing.assert_array_equal(o.success_buf, d["tv_success_buf"])
+    np.testing.assert_array_equal(label, (d["tv_success_buf"][:, 0] < 0.5).astype(np.int32))
+    assert 4 <= d["tv_success_buf"][:, 0].sum() < n and d["tv_success_buf"][2, 0] == 0.0      # env 2: aligned but 2 cm away
