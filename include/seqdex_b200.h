@@ -250,6 +250,14 @@ int sdx_tool_test_hooks(sdx_env_t* env, const int* slot_by_env_host, int pitch_k
  * label_dev i32[N] = 0 (success) / 1 (failure), the class index sdx_tvalue_bce takes.  The rows are SDX_T_TARGET_INIT
  * (t_value_obs_buf = the pose each episode started from, TO:1400); the five Adam steps run on sdx_mlp_* (tasks/tool_positioning.py). */
 int sdx_tool_tvalue_labels(sdx_env_t* env, int* label_dev);
+/* ToolPositioningChain's inner-policy call (TC = tasks/tool_positioning/allegro_hand_tool_positioning_chain.py:1733-1768): at step 118 of
+ * env 0's clock pre_physics_step runs 125 steps of a FROZEN policy inside the outer step -- predict on insertion_obs_buf, fingers = the
+ * scaled actions, arm = its previous target, gym.simulate.  sdx_tool_inner_step is one such step (actions -> targets -> contact step; the
+ * task's own ACTIONS tensor, observations and reward are untouched); sdx_tool_insertion_obs is compute_insertion_observations
+ * (TC:1404-1440): the observation frame just written to SDX_T_OBS with the inner policy's last actions in 23:46 and the inner episode
+ * clock (ins_progress / ins_max_len) in slot 60, shifted into the caller's own [N][468] history buffer. */
+int sdx_tool_inner_step(sdx_env_t* env, const float* actions_dev);
+int sdx_tool_insertion_obs(sdx_env_t* env, const float* ins_actions_dev, const int64_t* ins_progress_dev, int ins_max_len, float* ins_obs_dev);
 /* number of contact steps the last sdx_pre_physics spent inside reset_idx (0 when nobody reset; 103 for a full Orient reset) */
 int sdx_last_reset_sim_steps(const sdx_env_t* env);
 /* BlockAssemblySearch's camera features (SE = tasks/block_assembly/allegro_hand_block_assembly_search.py): the reference renders

@@ -8,7 +8,8 @@ with Isaac Gym stubbed exactly as in gen_golden.py:
     compute_reward         TG:1077-1105 / TO:988-1016   (-> compute_hand_reward TG:1741-1893 / TO:1574-1626, TorchScript)
     pre_physics_step       TG:1580-1675 / TO:1438-1509  (no-reset branch)
     reset_idx              TG:1412-1578 (banking of good grasps, tool / hand to their start poses, history zeroed)
-                           TO:1265-1436 (a banked grasp restored)
+                           TO:1265-1436 (a banked grasp restored; a second call with `if_t_value` on: the online t-value update TO:1305-1350)
+    compute_insertion_observations   tasks/tool_positioning/allegro_hand_tool_positioning_chain.py:1404-1440 (ToolPositioningChain's second buffer)
 pytorch3d (third party, absent here) is needed by TG's reward for one function: oracle/p3d_transforms_restated.py.
 Runs only in the build container; writes tests/golden/tool_{grasp,orient}_{post,pre,reset}.npz.
 
@@ -184,6 +185,20 @@ def main():
                         f"consec{call}": f.consecutive_successes.numpy().copy(), f"finger_dist{call}": f.arm_hand_finger_dist.numpy().copy()})
             print(f"tool {name} call {call}: rew range", float(f.rew_buf.min()), float(f.rew_buf.max()), "resets", int(f.reset_buf.sum()),
                   "successes", int(f.successes.sum()), "bonus envs", int((f.rew_buf > 1).sum()))
+        if name == "grasp":
+            # ToolPositioningChain.compute_insertion_observations (TC:1404-1440) on the state of the second call: the second observation
+            # buffer the frozen inner policy reads (TC:1742)
+            import tasks.tool_positioning.allegro_hand_tool_positioning_chain as TC
+            f.insertion_one_frame_num_obs, f.insertion_max_episode_length = 156, 125
+            f.insertion_obs_buf = torch.zeros(N, 468)
+            ins_hist = [torch.randn(N, 156) * 0.3 for _ in range(3)]
+            f.insertion_obs_buf_stack_frames = [h.clone() for h in ins_hist]
+            f.insertion_actions = torch.rand(N, 23) * 2 - 1
+            f.insertion_progress_buf = torch.tensor(rng.integers(0, 125, size=N), dtype=torch.long)
+            with torch.no_grad():
+                TC.ToolPositioningChain.compute_insertion_observations(f)
+            out.update(ins_hist=torch.stack(ins_hist[:2], 1).numpy(), ins_actions=f.insertion_actions.numpy().copy(),
+                       ins_progress=f.insertion_progress_buf.numpy().copy(), ins_obs=f.insertion_obs_buf.numpy().copy())
         np.savez(os.path.join(OUT, f"tool_{name}_post.npz"), **out)
 
         # ---- pre_physics_step, no-reset branch

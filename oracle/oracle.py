@@ -313,6 +313,19 @@ class OracleEnv:
                                self.slp.ctypes.data_as(ctypes.c_void_p), fp(self.obs), fp(self.states))
         self.refresh_links()                      # the hand was teleported: pre_physics reads its pose before any contact step
 
+    def tool_insertion_obs(self, ins_actions, ins_progress, ins_obs, ins_max_len=125):
+        """ToolPositioningChain.compute_insertion_observations (TC:1404-1440) into the caller's [n, 468] buffer"""
+        a = np.ascontiguousarray(ins_actions, np.float32)
+        p = np.ascontiguousarray(ins_progress, np.int64)
+        self.L.sdxo_tool_insertion_obs(self.n, fp(self.obs), fp(a), lp(p), int(ins_max_len), fp(ins_obs))
+
+    def tool_inner_step(self, actions):
+        """one step of ToolPositioningChain's inner loop (TC:1733-1768): fingers from the actions, arm holds, contact step"""
+        a = np.ascontiguousarray(np.clip(actions, -1.0, 1.0), np.float32)
+        scratch = np.zeros_like(self.actions)
+        self.L.sdxo_tool_pre_physics(self.S, self.n, 1, fp(a), fp(scratch), fp(self.dof), fp(self.link), fp(self.jac7), lp(self.progress))
+        self.simulate()
+
     def tool_tvalue_labels(self):
         """TO:1305-1316: success_buf for ALL envs from the current state; returns the class index per env (0 success, 1 failure)"""
         label = np.zeros(self.n, np.int32)

@@ -2136,3 +2136,16 @@ void sdxo_tool_tvalue_labels(const sdx_scene_t* S, int n, const float* brick, co
     label[e] = ok > 0.5f ? 0 : 1;
   }
 }
+
+/* ToolPositioningChain, compute_insertion_observations (TC:1404-1440): the frame compute_contact_observations has just written, with the
+ * inner policy's last actions in 23:46 and the inner clock in slot 60, over the buffer's own history frames */
+void sdxo_tool_insertion_obs(int n, const float* obs, const float* ins_actions, const int64_t* ins_progress, int ins_max_len, float* ins_obs) {
+  for (int e = 0; e < n; ++e) {
+    const float* o = obs + (size_t)e * 3 * TOOL_OBS;
+    float* io = ins_obs + (size_t)e * 3 * TOOL_OBS;
+    for (int k = 2 * TOOL_OBS - 1; k >= 0; --k) io[TOOL_OBS + k] = io[k];
+    for (int k = 0; k < TOOL_OBS; ++k) io[k] = o[k];
+    for (int k = 0; k < 23; ++k) io[23 + k] = ins_actions[23 * (size_t)e + k];
+    io[60] = (float)ins_progress[e] / (float)ins_max_len;
+  }
+}

@@ -342,6 +342,27 @@ static int tool_pre_physics(sdx_env_t* E, const float* actions_dev) {
   CKL();
   return 0;
 }
+/* ToolPositioningChain (TC:1733-1768): one step of the inner loop -- the frozen policy's actions drive the fingers, the arm holds its previous
+ * target (= ToolPositioningOrient's pre-physics, TO:1455-1473), then the contact step.  No reset, no observation, no reward. */
+extern "C" int sdx_tool_inner_step(sdx_env_t* E, const float* actions_dev) {
+  if (!E || !actions_dev || !is_tool(E->task)) { g_err = "sdx_tool_inner_step: needs a ToolPositioning env and device actions"; return -1; }
+  CK(cudaSetDevice(E->device));
+  const int n = E->n;
+  k_tool_pre_physics<<<(n + 127) / 128, 128, 0, E->stream>>>(E->scene, n, 1, actions_dev, E->stage_actions, F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
+                                                           I64(SDX_T_PROGRESS));
+  E->launches++;
+  CKL();
+  return sdx_simulate(E);
+}
+extern "C" int sdx_tool_insertion_obs(sdx_env_t* E, const float* ins_actions_dev, const int64_t* ins_progress_dev, int ins_max_len, float* ins_obs_dev) {
+  if (!E || !ins_actions_dev || !ins_progress_dev || !ins_obs_dev || !is_tool(E->task) || ins_max_len <= 0) { g_err = "sdx_tool_insertion_obs: bad arguments"; return -1; }
+  CK(cudaSetDevice(E->device));
+  k_tool_insertion_obs<<<(E->n + POST_WARPS - 1) / POST_WARPS, 32 * POST_WARPS, 0, E->stream>>>(E->n, F(SDX_T_OBS), ins_actions_dev, ins_progress_dev, ins_max_len,
+                                                                                              ins_obs_dev);
+  E->launches++;
+  CKL();
+  return 0;
+}
 extern "C" int sdx_tool_tvalue_labels(sdx_env_t* E, int* label_dev) {
   if (!E || !label_dev || E->task != SDX_TASK_TOOL_ORIENT) { g_err = "sdx_tool_tvalue_labels: needs a ToolPositioningOrient env and a device label buffer"; return -1; }
   CK(cudaSetDevice(E->device));

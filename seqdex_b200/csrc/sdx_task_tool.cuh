@@ -99,6 +99,31 @@ __global__ void k_tool_tvalue_labels(const sdx_scene_t* __restrict__ S, int n, c
   label[e] = ok > 0.5f ? 0 : 1;
 }
 
+// ToolPositioningChain's second observation buffer (TC = tasks/tool_positioning/allegro_hand_tool_positioning_chain.py:1404-1440): the frame
+// compute_contact_observations has just written (TC:1306 calls this right after it) with the INNER policy's last actions in 23:46 and the
+// inner episode clock in slot 60, over its own two history frames.  One warp per env.
+__global__ void __launch_bounds__(32 * POST_WARPS)
+k_tool_insertion_obs(int n, const float* __restrict__ obs, const float* __restrict__ ins_actions, const int64_t* __restrict__ ins_progress,
+                     int ins_max_len, float* __restrict__ ins_obs) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * POST_WARPS + wid;
+  if (e >= n) return;
+  const float* o = obs + (size_t)e * 3 * TOOL_OBS;
+  float* io = ins_obs + (size_t)e * 3 * TOOL_OBS;
+  float ho[(2 * TOOL_OBS + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (2 * TOOL_OBS + 31) / 32; ++i) { const int k = lane + 32 * i; ho[i] = k < 2 * TOOL_OBS ? io[k] : 0.0f; }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < (2 * TOOL_OBS + 31) / 32; ++i) { const int k = lane + 32 * i; if (k < 2 * TOOL_OBS) io[TOOL_OBS + k] = ho[i]; }
+  for (int k = lane; k < TOOL_OBS; k += 32) {
+    float v = o[k];
+    if (k >= 23 && k < 46) v = ins_actions[23 * (size_t)e + (k - 23)];
+    if (k == 60) v = (float)ins_progress[e] / (float)ins_max_len;
+    io[k] = v;
+  }
+}
+
 // orient = 0: TG reset_idx; orient = 1: TO reset_idx.  slot_by_env / yaw_u (nullable) are the parity tests' hooks.
 __global__ void __launch_bounds__(128)
 k_tool_reset(const sdx_scene_t* __restrict__ S, int n, int orient, uint64_t seed, const float* __restrict__ bank_obj,

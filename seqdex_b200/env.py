@@ -198,6 +198,15 @@ class SdxEnv:
         _lib.check(self.L.sdx_tool_test_hooks(self.h, s.ctypes.data_as(ctypes.c_void_p) if s is not None else None, int(pitch_k),
                                               u.ctypes.data_as(ctypes.c_void_p) if u is not None else None))
 
+    def tool_inner_step(self, actions):
+        """one step of ToolPositioningChain's inner loop (sdx_tool_inner_step; TC:1733-1768)"""
+        _lib.check(self.L.sdx_tool_inner_step(self.h, ctypes.c_void_p(actions.data_ptr())))
+
+    def tool_insertion_obs(self, ins_actions, ins_progress, ins_obs, ins_max_len=125):
+        """ToolPositioningChain.compute_insertion_observations (sdx_tool_insertion_obs; TC:1404-1440) into ``ins_obs`` [N, 468]"""
+        _lib.check(self.L.sdx_tool_insertion_obs(self.h, ctypes.c_void_p(ins_actions.data_ptr()), ctypes.c_void_p(ins_progress.data_ptr()),
+                                                 int(ins_max_len), ctypes.c_void_p(ins_obs.data_ptr())))
+
     def tool_tvalue_labels(self, out=None):
         """ToolPositioningOrient's online t-value labels (TO:1305-1316): int32 [N] on the device, 0 success / 1 failure; also writes SUCCESS"""
         if out is None:

@@ -124,6 +124,66 @@ class ToolPositioningGrasp(_ToolPositioning):
         return self.env.grasp_bank()
 
 
+class ToolPositioningChain(ToolPositioningGrasp):
+    """The inner-policy call of ``ToolPositioningChain`` (TC = tasks/tool_positioning/allegro_hand_tool_positioning_chain.py:1733-1768) on
+    ToolPositioningGrasp's scene, observations, reward and reset: when env 0's clock reads 118, ``pre_physics_step`` runs 125 steps of a
+    FROZEN ToolPositioningOrient policy inside the outer step -- ``insert_policy.predict`` on the clamped ``insertion_obs_buf``
+    (TC:1742; the buffer is NOT refreshed inside the loop, so the policy sees one observation 125 times and only its action noise
+    varies -- reproduced as written), fingers = the scaled actions, arm = its previous target, contact step -- and
+    ``compute_observations`` additionally fills ``insertion_obs_buf`` (TC:1306, 1404-1440).
+
+    What TC changes beyond that is NOT built: its three tool types with fixed bases (TC:800, 816), the ``replan`` bookkeeping and its
+    ``success_buf`` variant (TC:1488-1518), the bank gate without the orientation test (TC:1531-1536) and the mid-air teleport of
+    resetting tools (TC:1813-1825) -- evaluation scaffolding around checkpoints that live in the authors' home directory (TC:558)."""
+    TASK = "ToolPositioningGrasp"
+    INNER_AT, INNER_STEPS, INNER_EPISODE = 118, 125, 125               # TC:1733-1734, 561
+
+    def __init__(self, cfg=None, sim_params=None, physics_engine=None, device_type="cuda", device_id=0, headless=True,
+                 agent_index=None, is_multi_agent=False, seed=22, insert_policy=None, insert_policy_path=None):
+        super().__init__(cfg, sim_params, physics_engine, device_type, device_id, headless, agent_index, is_multi_agent, seed)
+        from ..policy_sequencing import NNController
+        self.insertion_num_obs = 3 * 156                                 # TC:533-537
+        self.insertion_obs_buf = torch.zeros(self.num_envs, self.insertion_num_obs, device=self.device)
+        self.insertion_actions = torch.zeros(self.num_envs, 23, device=self.device)
+        self.insertion_progress_buf = torch.zeros(self.num_envs, dtype=torch.int64, device=self.device)
+        # insert_network.yaml: units [1024, 512, 256] (utils/robot_controller/nn_controller.py:7-58)
+        self.insert_policy = insert_policy or NNController(num_actors=self.num_envs, units=(1024, 512, 256), obs_dim=self.insertion_num_obs,
+                                                           device=device_id, seed=seed)
+        if insert_policy_path:
+            self.insert_policy.load(insert_policy_path)                  # TC:558
+        self.inner_calls = 0
+
+    def pre_physics_step(self, actions):
+        inner = False
+        if int(self.progress_buf[0]) == self.INNER_AT and not bool(self.reset_buf[0]):   # TC:1733 reads env 0's clock on the host (after reset_idx)
+            inner = True
+            dof = self.env.tensor("DOF")
+            prev_arm, was_reset = dof[:, 2, :7].clone(), self.reset_buf.bool().clone()
+        self.env.pre_physics(actions)                                    # reset_idx, then TG's targets (TC:1688-1731)
+        if inner:
+            # inside the loop the arm holds prev_targets (TC:1752-1754), which at this point still are the PREVIOUS step's targets
+            # (they are only updated at TC:1776) -- for an env reset_idx has just reset, the pose it was reset to
+            dof[:, 2, :7] = torch.where(was_reset[:, None], dof[:, 0, :7], prev_arm)
+            for _ in range(self.INNER_STEPS):
+                self.insertion_progress_buf.zero_()                      # TC:1739 (inside the loop, as written)
+                self.insertion_actions = self.insert_policy.predict(torch.clamp(self.insertion_obs_buf, -5.0, 5.0), deterministic=False).contiguous()
+                self.env.tool_inner_step(self.insertion_actions)
+                self.insertion_progress_buf += 1                         # TC:1768
+            self.inner_calls += 1
+
+    def post_physics_step(self):
+        self.env.post_physics()
+        self.env.tool_insertion_obs(self.insertion_actions, self.insertion_progress_buf, self.insertion_obs_buf, self.INNER_EPISODE)   # TC:1306
+
+    def step(self, actions):
+        actions = self._dr_before(actions)
+        self.pre_physics_step(actions)
+        self.env.simulate()
+        self.post_physics_step()
+        self._dr_after()
+        self.meta_rew_buf += self.rew_buf
+
+
 class ToolPositioningOrient(_ToolPositioning):
     TASK = "ToolPositioningOrient"
 

@@ -273,3 +273,49 @@ def test_tool_orient_runs_with_online_tvalue():
     assert float((t.t_value.params - w0).abs().max()) > 0
     sb = t.success_buf
     assert torch.equal(sb[:, 1], (sb[:, 0] <= 0.5).float())                   # TO:1316
+
+
+def test_tool_chain_insertion_obs_and_inner_step(oracle_lib):
+    """ToolPositioningChain's two C-ABI pieces against the oracle: compute_insertion_observations on the golden inputs (== the reference's
+    output exactly), and the inner loop's step (fingers from the actions, arm holds, contact step) bit for bit over 20 steps"""
+    from seqdex_b200.env import SdxEnv
+    d = dict(np.load(os.path.join(G, "tool_grasp_post.npz")))
+    n = len(d["progress0"])
+    sc = _scene("grasp")
+    g, o = SdxEnv(sc, n), oracle_lib.OracleEnv(sc, n)
+    g.tensor("OBS").copy_(torch.from_numpy(d["obs1"]))
+    ins = torch.zeros(n, 468, device="cuda")
+    ins[:, 0:312] = torch.from_numpy(d["ins_hist"].reshape(n, 312)).cuda()
+    g.tool_insertion_obs(torch.from_numpy(d["ins_actions"]).cuda(), torch.from_numpy(d["ins_progress"]).cuda(), ins)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(ins.cpu().numpy(), d["ins_obs"])
+    rng = np.random.default_rng(2)
+    a = rng.uniform(-1, 1, size=(n, 23)).astype(np.float32)
+    g.step(torch.from_numpy(a).cuda()); o.step(a)                        # every env reset once, the hammer falls
+    acts_before = g.tensor("ACTIONS").clone()
+    for k in range(20):
+        a = rng.uniform(-1, 1, size=(n, 23)).astype(np.float32)
+        g.tool_inner_step(torch.from_numpy(a).cuda()); o.tool_inner_step(a)
+    torch.cuda.synchronize()
+    for name, ov in (("BRICK", o.brick), ("DOF", o.dof), ("LINK", o.link), ("NCONTACT", o.ncontact), ("PROGRESS", o.progress)):
+        _cmp(f"inner: {name}", g.tensor(name), ov)
+    assert torch.equal(g.tensor("ACTIONS"), acts_before)                  # the task's own actions tensor is untouched by the inner loop
+
+
+def test_tool_chain_task_runs_the_inner_policy_at_step_118():
+    from seqdex_b200.tasks import ToolPositioningChain
+    n = 32
+    t = ToolPositioningChain({"env": {"numEnvs": n}, "sim": {}, "task": {"randomize": False}})
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    launches = []
+    for k in range(125):
+        l0 = t.env.launch_count()
+        t.step((torch.rand(n, 23, device="cuda", generator=gen) * 2 - 1) * 0.2)
+        launches.append(t.env.launch_count() - l0)
+    # episodes run in lockstep under small actions (no early reset), so env 0's clock reads 118 at the 119th call
+    assert t.inner_calls == 1
+    assert launches[118] >= 2 * 125 and max(launches[:118]) < 20           # 125 x (targets + contact step) inside ONE outer step (TC:1734)
+    assert int(t.insertion_progress_buf.max()) == 1                       # zeroed inside the loop, incremented at its end (TC:1739, 1768)
+    assert torch.isfinite(t.insertion_obs_buf).all() and torch.isfinite(t.obs_buf).all()
+    np.testing.assert_array_equal(t.insertion_obs_buf[:, 23:46].cpu().numpy(), t.insertion_actions.cpu().numpy())
+    assert torch.equal(t.insertion_obs_buf[:, 0:23], t.obs_buf[:, 0:23]) and torch.equal(t.insertion_obs_buf[:, 61:156], t.obs_buf[:, 61:156])

@@ -220,3 +220,18 @@ def test_tool_orient_online_tvalue_labels_match_reference(oracle_lib):
     np.testing.assert_array_equal(o.success_buf, d["tv_success_buf"])
     np.testing.assert_array_equal(label, (d["tv_success_buf"][:, 0] < 0.5).astype(np.int32))
     assert 4 <= d["tv_success_buf"][:, 0].sum() < n and d["tv_success_buf"][2, 0] == 0.0      # env 2: aligned but 2 cm away
+
+
+def test_tool_chain_insertion_observations_match_reference(oracle_lib):
+    """ToolPositioningChain.compute_insertion_observations (TC:1404-1440) executed by the reference right after the second
+    compute_observations call of the Grasp golden: the inner policy's actions in 23:46, the inner clock in slot 60, its own history"""
+    d = _load("tool_grasp_post.npz")
+    n = len(d["progress0"])
+    o = oracle_lib.OracleEnv(_scene("grasp"), n)
+    o.obs[:] = d["obs1"]
+    ins = np.zeros((n, 468), np.float32)
+    ins[:, 0:312] = d["ins_hist"].reshape(n, 312)
+    o.tool_insertion_obs(d["ins_actions"], d["ins_progress"], ins)
+    np.testing.assert_array_equal(ins, d["ins_obs"])
+    np.testing.assert_array_equal(ins[:, 23:46], d["ins_actions"])
+    np.testing.assert_array_equal(ins[:, 156:468], d["ins_hist"].reshape(n, 312))
