@@ -323,6 +323,9 @@ int sdx_ppo_adaptive_lr(float* stats_dev, float inv_count, float kl_threshold, f
  * RGC:1913-1933): set < 0 reads it, set >= 0 overwrites it (restore) */
 long long sdx_mlp_adam_step(sdx_mlp_t* m, long long set);
 long long sdx_ppo_launch_count(void);
+/* a CUDA graph captured from the sdx_mlp_* / sdx_ppo_* entry points replays their kernels without passing through them: the caller adds
+ * the number of kernels one replay launches (counted during the capture) so that sdx_ppo_launch_count stays the number actually launched */
+void sdx_ppo_add_launches(long long n);
 
 /* a = mu + exp(logstd) N(0,1) (Philox), neglogp (RGC:2115-2127) */
 int sdx_ppo_sample(const float* mu, const float* logstd, int M, int A, uint64_t seed, uint32_t counter, float* actions,

@@ -154,7 +154,8 @@ struct sdx_mlp {
   float *params, *grads, *adam_m, *adam_v, *out, *scal, *gW[4];
   __nv_bfloat16 *W[4], *Wt[4], *A[4], *At[4], *dZ[5], *dZt[5];
   const __nv_bfloat16 *a0, *at0; int ldt0;   // layer-0 input of the last forward (own staging buffers or a caller-converted batch)
-  long long adam_t;
+  long long* adam_t;   // DEVICE: optimiser step counter, followed by float bc[2] = 1 - beta^t (k_adam_tick) -- on the device so that a captured
+                       // CUDA graph of the update replays with the right bias corrections
   cudaEvent_t layer_done[4];   // recorded when layer l's gradient slice is complete in `grads` (pipelined all-reduce, sdx_mlp_backward_pipelined)
   int pipelined;                // last backward ran pipelined: per-layer unpack already done
 };
@@ -226,12 +227,20 @@ __global__ void k_sumsq_final(const float* __restrict__ partial, int nb, float* 
     if (threadIdx.x == 0) *out = s;
   }
 }
+// step += 1; bias corrections 1 - beta^step for the k_adam that follows (one thread)
+__global__ void k_adam_tick(long long* __restrict__ t, float b1, float b2) {
+  const long long s = *t + 1;
+  *t = s;
+  float* bc = (float*)(t + 1);
+  bc[0] = 1.0f - powf(b1, (float)s); bc[1] = 1.0f - powf(b2, (float)s);
+}
 // torch.optim.Adam (eps 1e-8, no weight decay; RGC:1102) with rl_games' global grad-norm clip folded in (RGC:1866-1872)
 __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n,
-                       float lr, float b1, float b2, float eps, float bc1, float bc2, float max_norm, const float* __restrict__ sumsq,
+                       float lr, float b1, float b2, float eps, const long long* __restrict__ tick, float max_norm, const float* __restrict__ sumsq,
                        const float* __restrict__ lr_dev = nullptr) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const float bc1 = ((const float*)(tick + 1))[0], bc2 = ((const float*)(tick + 1))[1];
   if (lr_dev) lr = *lr_dev;
   float scale = 1.0f;
   if (max_norm > 0.0f) { float nrm = sqrtf(*sumsq); scale = fminf(1.0f, max_norm / (nrm + 1e-6f)); }
@@ -295,6 +304,7 @@ extern "C" int sdx_mlp_create_ex(int in_dim, int out_dim, int h1, int h2, int h3
   PCK(cudaMalloc(&m->adam_v, off * 4)); PCK(cudaMemset(m->adam_v, 0, off * 4));
   PCK(cudaMalloc(&m->out, (size_t)max_rows * out_dim * 4));
   PCK(cudaMalloc(&m->scal, 2048)); PCK(cudaMemset(m->scal, 0, 2048));   // [0] grad norm^2, [16..16+296) per-block partials
+  PCK(cudaMalloc(&m->adam_t, 16)); PCK(cudaMemset(m->adam_t, 0, 16));
   size_t R = max_rows;
   for (int l = 0; l < 4; ++l) {
     int K = m->d[l], N = m->d[l + 1], Npad = pad64(N);
@@ -317,7 +327,7 @@ extern "C" int sdx_mlp_create(int in_dim, int out_dim, int max_rows, int has_sig
 }
 extern "C" void sdx_mlp_destroy(sdx_mlp* m) {
   if (!m) return;
-  cudaFree(m->params); cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->out); cudaFree(m->scal);
+  cudaFree(m->params); cudaFree(m->grads); cudaFree(m->adam_m); cudaFree(m->adam_v); cudaFree(m->out); cudaFree(m->scal); cudaFree(m->adam_t);
   for (int l = 0; l < 4; ++l) cudaEventDestroy(m->layer_done[l]);
   for (int l = 0; l < 4; ++l) { cudaFree(m->W[l]); cudaFree(m->Wt[l]); cudaFree(m->A[l]); cudaFree(m->At[l]); cudaFree(m->gW[l]); cudaFree(m->dZ[l + 1]); cudaFree(m->dZt[l + 1]); }
   delete m;
@@ -453,18 +463,27 @@ extern "C" int sdx_mlp_layer_range(sdx_mlp* m, int layer, int64_t* begin, int64_
   return 0;
 }
 /* optimiser step counter (the `step` of torch.optim.Adam's state): read with set < 0, overwritten otherwise (checkpoint restore) */
-extern "C" long long sdx_mlp_adam_step(sdx_mlp* m, long long set) { if (set >= 0) m->adam_t = set; return m->adam_t; }
+extern "C" long long sdx_mlp_adam_step(sdx_mlp* m, long long set) {
+  long long t = 0;
+  cudaDeviceSynchronize();
+  if (set >= 0) { cudaMemcpy(m->adam_t, &set, 8, cudaMemcpyHostToDevice); return set; }
+  cudaMemcpy(&t, m->adam_t, 8, cudaMemcpyDeviceToHost);
+  return t;
+}
+/* kernels a replayed CUDA graph launched on behalf of this library (the graph was captured from these entry points; the counter only
+ * sees the capture) */
+extern "C" void sdx_ppo_add_launches(long long n) { g_ppo_launches += n; }
 static int mlp_adam(sdx_mlp* m, float lr, const float* lr_dev, float b1, float b2, float eps, float max_norm, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  m->adam_t++;
+  k_adam_tick<<<1, 1, 0, st>>>(m->adam_t, b1, b2);
+  g_ppo_launches++;
   if (max_norm > 0.0f) {
     k_sumsq<<<296, 256, 0, st>>>(m->grads, m->nparams, m->scal + 16);
     k_sumsq_final<<<1, 256, 0, st>>>(m->scal + 16, 296, m->scal);
     g_ppo_launches++;
   }
   g_ppo_launches++;
-  float bc1 = 1.0f - powf(b1, (float)m->adam_t), bc2 = 1.0f - powf(b2, (float)m->adam_t);
-  k_adam<<<(unsigned)((m->nparams + 255) / 256), 256, 0, st>>>(m->params, m->grads, m->adam_m, m->adam_v, m->nparams, lr, b1, b2, eps, bc1, bc2, max_norm, m->scal, lr_dev);
+  k_adam<<<(unsigned)((m->nparams + 255) / 256), 256, 0, st>>>(m->params, m->grads, m->adam_m, m->adam_v, m->nparams, lr, b1, b2, eps, m->adam_t, max_norm, m->scal, lr_dev);
   g_ppo_launches++;
   PCK(cudaGetLastError());
   return sdx_mlp_sync(m, stream);

@@ -295,3 +295,36 @@ def test_pipelined_backward_publishes_the_same_gradients_layer_by_layer():
         torch.testing.assert_close(g, ref[b:e], rtol=1e-4, atol=1e-6)
         ends.append((b, e))
     assert sorted(ends)[0][0] == 0 and sorted(ends)[-1][1] == n and all(sorted(ends)[i][1] == sorted(ends)[i + 1][0] for i in range(3))
+
+
+def test_update_as_cuda_graph_follows_the_eager_update(monkeypatch):
+    """A2CAgent.update captures its ~800 launches into one CUDA graph from the second call on (the learning rate, the Adam step and the
+    statistics live on the device).  The dW GEMMs reduce their split-K partials with float atomics, so two runs of the SAME path already
+    differ in the last bits of the gradients (and Adam turns a sign flip of a near-zero gradient into a full step): the check is that the
+    graph path counts its optimiser steps on the device -- a graph with host-side counters would freeze the bias corrections --,
+    keeps the adaptive learning rate alive, and moves the parameters the way the eager path does."""
+    from seqdex_b200.ppo import A2CAgent, PPOConfig
+    from seqdex_b200.tasks import BlockAssemblyGraspSim
+    from seqdex_b200.vec_task import RLgamesVecTaskPython
+    cfg = {"env": {"numEnvs": 256, "episodeLength": 150, "actionsMovingAverage": 1.0}, "sim": {"substeps": 2, "physx": {}}, "task": {"randomize": False}}
+    out = {}
+    for mode in ("0", "force", "0b"):
+        monkeypatch.setenv("SEQDEX_PPO_GRAPH", mode[0] if mode != "force" else mode)
+        torch.manual_seed(17)                       # VecTask.reset draws its first actions from the global generator
+        task = BlockAssemblyGraspSim(cfg, bank_per_type=2)
+        agent = A2CAgent(RLgamesVecTaskPython(task, "cuda:0"), PPOConfig(minibatch_size=512))
+        w0 = (agent.actor.params.clone(), agent.cv.params.clone())
+        infos = [agent.train_epoch() for _ in range(6)]
+        torch.cuda.synchronize()
+        assert (getattr(agent, "_graph", None) is not None) == (mode == "force")
+        out[mode] = (agent.actor.params - w0[0], agent.cv.params - w0[1], infos, agent._adam_step(agent.actor), agent._adam_step(agent.cv))
+        task.env.close()
+    cos = lambda a, b: float((a * b).sum() / (a.norm() * b.norm()))
+    a, b, a2 = out["0"], out["force"], out["0b"]
+    assert a[3] == b[3] == 6 * 5 * 4 and a[4] == b[4] == 6 * 5 * 4        # 6 iterations x 5 mini-epochs x 4 minibatches, counted on the device
+    assert all(math.isfinite(i["kl"]) and 1e-6 <= i["lr"] <= 1e-2 for i in b[2])
+    assert len({i["lr"] for i in b[2]}) > 1                               # the device-side schedule keeps adapting under replay
+    # graph vs eager agree as well as eager vs eager does (the run-to-run spread of the atomics), within a factor
+    ref_a, ref_c = cos(a[0], a2[0]), cos(a[1], a2[1])
+    assert cos(a[0], b[0]) > 0.8 * ref_a and cos(a[1], b[1]) > 0.8 * ref_c, (cos(a[0], b[0]), ref_a, cos(a[1], b[1]), ref_c)
+    assert 0.5 < float(b[0].norm() / a[0].norm()) < 2.0
