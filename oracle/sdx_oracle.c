@@ -865,10 +865,10 @@ float sdxo_tvalue_one(const float* wts, const float* qin) {
   const float* W1 = wts; const float* b1 = W1 + 256 * 4; const float* W2 = b1 + 256; const float* b2 = W2 + 128 * 256;
   const float* W3 = b2 + 128; const float* b3 = W3 + 64 * 128; const float* W4 = b3 + 64; const float* b4 = W4 + 2 * 64;
   float h1[256], h2[128], h3[64];
-  for (int o = 0; o < 256; ++o) { float a = b1[o]; for (int k = 0; k < 4; ++k) a = a + W1[o * 4 + k] * qin[k]; h1[o] = sdx_elu(a); }
-  for (int o = 0; o < 128; ++o) { float a = b2[o]; for (int k = 0; k < 256; ++k) a = a + W2[o * 256 + k] * h1[k]; h2[o] = sdx_elu(a); }
-  for (int o = 0; o < 64; ++o) { float a = b3[o]; for (int k = 0; k < 128; ++k) a = a + W3[o * 128 + k] * h2[k]; h3[o] = sdx_elu(a); }
-  float a = b4[1]; for (int k = 0; k < 64; ++k) a = a + W4[64 + k] * h3[k];
+  for (int o = 0; o < 256; ++o) { float a = b1[o]; for (int k = 0; k < 4; ++k) a = fmaf(W1[o * 4 + k], qin[k], a); h1[o] = sdx_elu(a); }   /* one fused multiply-add per weight, as the kernel */
+  for (int o = 0; o < 128; ++o) { float a = b2[o]; for (int k = 0; k < 256; ++k) a = fmaf(W2[o * 256 + k], h1[k], a); h2[o] = sdx_elu(a); }
+  for (int o = 0; o < 64; ++o) { float a = b3[o]; for (int k = 0; k < 128; ++k) a = fmaf(W3[o * 128 + k], h2[k], a); h3[o] = sdx_elu(a); }
+  float a = b4[1]; for (int k = 0; k < 64; ++k) a = fmaf(W4[64 + k], h3[k], a);
   a = sdx_elu(a);
   return 1.0f / (1.0f + sdx_exp(-a));
 }

@@ -4,7 +4,7 @@
 //   k_pre_physics   : actions -> DoF targets, 6x7 DLS IK         (GS:1570-1638, 1796-1804)
 //   k_post_physics  : observations + privileged states + reward + reset flags
 //                     (GS:1090-1332, 1706-1776), one warp per env, coalesced row writes
-//   k_tvalue        : GraspInsertTValue MLP + sigmoid            (TVF:30-46, GS:1200-1201)
+//   k_tvalue        : GraspInsertTValue MLP + sigmoid, one fused multiply-add per weight (TVF:30-46, GS:1200-1201)
 //   facade kernels  : Isaac-Gym-shaped tensors (refresh_* / set_*_indexed, GS:1091-1095, 1514-1545)
 #pragma once
 #include "sdx_math.cuh"
@@ -403,7 +403,7 @@ k_tvalue(const float* __restrict__ wts, int n, const float* __restrict__ qcam, f
     float w0 = W1[o * 4], w1 = W1[o * 4 + 1], w2 = W1[o * 4 + 2], w3 = W1[o * 4 + 3], bb = b1[o];
 #pragma unroll
     for (int v = 0; v < TV_ENVS; ++v) {
-      float a = bb; a = a + w0 * x[v][0]; a = a + w1 * x[v][1]; a = a + w2 * x[v][2]; a = a + w3 * x[v][3];
+      float a = bb; a = fmaf(w0, x[v][0], a); a = fmaf(w1, x[v][1], a); a = fmaf(w2, x[v][2], a); a = fmaf(w3, x[v][3], a);
       h1[wid][v][o] = sdx_elu(a);
     }
   }
@@ -422,7 +422,7 @@ k_tvalue(const float* __restrict__ wts, int n, const float* __restrict__ qcam, f
       for (int r = 0; r < 4; ++r) {
         float w = W2t[k * 128 + lane + 32 * r];
 #pragma unroll
-        for (int v = 0; v < TV_ENVS; ++v) acc[r][v] = acc[r][v] + w * hv[v];
+        for (int v = 0; v < TV_ENVS; ++v) acc[r][v] = fmaf(w, hv[v], acc[r][v]);
       }
     }
 #pragma unroll
@@ -442,7 +442,7 @@ k_tvalue(const float* __restrict__ wts, int n, const float* __restrict__ qcam, f
       for (int r = 0; r < 2; ++r) {
         float w = W3t[k * 64 + lane + 32 * r];
 #pragma unroll
-        for (int v = 0; v < TV_ENVS; ++v) acc[r][v] = acc[r][v] + w * h2[wid][v][k];
+        for (int v = 0; v < TV_ENVS; ++v) acc[r][v] = fmaf(w, h2[wid][v][k], acc[r][v]);
       }
     }
 #pragma unroll
@@ -453,7 +453,7 @@ k_tvalue(const float* __restrict__ wts, int n, const float* __restrict__ qcam, f
   __syncwarp();
   if (lane < TV_ENVS && e0 + lane < n) {
     float a = b4[1];
-    for (int k = 0; k < 64; ++k) a = a + W4[64 + k] * h3[wid][lane][k];
+    for (int k = 0; k < 64; ++k) a = fmaf(W4[64 + k], h3[wid][lane][k], a);
     a = sdx_elu(a);
     const float v = 1.0f / (1.0f + sdx_exp(-a));
     tvalue[e0 + lane] = thresh > 0.0f ? (v > thresh ? 1.0f : 0.0f) : v;   // Orient keeps only the thresholded gate (OR:1203-1205)

@@ -97,3 +97,19 @@ def test_create_fails_loudly_without_bank(scene):
     e = SdxEnv(scene, 8)
     with pytest.raises(RuntimeError, match="heap bank"):
         e.step(torch.zeros(8, 23, device="cuda"))
+
+
+def test_facade_dump_is_current():
+    """tests/golden/facade_dump.npz -- the facade tensors the reference's own compute_observations is run on in
+    tests/test_facade_reference_cpu.py -- is what tools/dump_facade.py produces with today's kernels, bit for bit"""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("dump_facade", os.path.join(here, "..", "tools", "dump_facade.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    new = mod.make_dump()
+    old = dict(np.load(os.path.join(here, "golden", "facade_dump.npz")))
+    assert set(new) == set(old)
+    for k in new:
+        assert np.array_equal(new[k], old[k]), f"{k} differs: regenerate with `python tools/dump_facade.py` on a B200 and re-run tests/test_facade_reference_cpu.py"
