@@ -44,4 +44,5 @@ def test_generator_reproduces_the_committed_vectors(script, tmp_path):
 
 def test_every_golden_file_has_a_generator():
     made = {n for names in GENERATORS.values() for n in names} | {"dr_configs.json"}
+    made |= {"facade_dump.npz"}     # produced ON A B200 by tools/dump_facade.py (the facade's tensors); tests/test_facade_gpu.py re-creates it bit for bit
     assert set(os.listdir(GOLDEN)) == made
