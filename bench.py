@@ -26,10 +26,10 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = 15956   # algorithmic HBM bytes / env-step (fp32 rollout)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_simulate launch at 16 384 envs, from the committed ncu --set full capture
-# (profiles/r02_ncu_k_simulate_16384envs.txt: 128.2 MB read + 290.4 MB written; the writes include the contact records that
+# (profiles/r02_ncu_k_simulate_final.txt: 128.2 MB read + 289.3 MB written; the writes include the contact records that
 # live in global memory behind L1 since SIM_GLOBAL_CONTACTS and the warm-start impulse cache)
-NCU_TRAFFIC_BYTES_PER_ENV = (128.228608e6 + 290.438656e6) / 16384
-NCU_ISSUE_ACTIVE = 0.5224            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
+NCU_TRAFFIC_BYTES_PER_ENV = (128.175e6 + 289.338e6) / 16384
+NCU_ISSUE_ACTIVE = 0.5176            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
 ALGO_FLOP_PER_ENV_STEP = 1.48e6      # counted fp32 work of the contact step in this episode mix (oracle counters)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # B200: 148 SMs x 128 fp32 lanes x 2 (FMA) x 1.965 GHz
 
@@ -419,13 +419,16 @@ def main():
         agent = A2CAgent(venv, PPOConfig(minibatch_size=min(args.minibatch, 8 * n)), device=local,
                          dist_group=dist.group.WORLD if world > 1 else None)
         H = agent.H
-        iters, witers = max(-(-K // H), 1), max(W // H, 1)      # whole PPO iterations covering at least K env steps
+        # whole PPO iterations covering at least K env steps; at least TWO untimed iterations first: the agent's second update() call
+        # captures the update into a CUDA graph (ppo.A2CAgent.update), and one-off set-up does not belong in the timed region
+        iters, witers = max(-(-K // H), 1), max(-(-W // H), 2)
         for _ in range(witers):
             ppo_info = agent.train_epoch()
         barrier()
         l0, p0 = env.launch_count(), ppo_launch()
         step_ev.clear()
         asleep0 = float((env.tensor("SLEEP") >= max(scene.c.sleep_substeps, 1)).float().mean())
+        contacts0 = float(env.tensor("NCONTACT")[:, 0].float().mean())
         it_ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
         e0.record()
         it_ev[0].record()
@@ -440,6 +443,11 @@ def main():
         ppo_info = dict(ppo_info or {})
         ppo_info["timed_region"] = {"seconds": timed_s, "env_steps_timed": iters * H, "ppo_iterations": iters,
                                     "ms_per_iteration_min_median_max": [float(np.min(it_ms)), float(np.median(it_ms)), float(np.max(it_ms))],
+                                    "ms_per_iteration_first_last": [float(it_ms[0]), float(it_ms[-1])],
+                                    "contacts_per_env_mean_start_end": [contacts0, float(env.tensor("NCONTACT")[:, 0].float().mean())],
+                                    "drift": "the policy is being TRAINED inside the timed region: as it learns to reach for the target brick the hand "
+                                             "spends more time in the heap, contacts per env and with them the contact step's time rise over the "
+                                             "iterations (a longer --steps therefore reports a lower value than a short one)",
                                     "note": f"`value` = envs x {iters * H} steps / that time (whole iterations covering the {K} steps asked for)"}
         from seqdex_b200.dist_utils import params_digest
         dg = params_digest(agent.actor.params, agent.cv.params)
@@ -527,7 +535,7 @@ def main():
             "ppo": ppo_info,
             "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": NCU_TRAFFIC_BYTES_PER_ENV * n,
-                         "traffic_source": "ncu --set full at 16384 envs, profiles/r02_ncu_k_simulate_16384envs.txt (scaled by envs per launch)",
+                         "traffic_source": "ncu --set full at 16384 envs, profiles/r02_ncu_k_simulate_final.txt (scaled by envs per launch)",
                          "issue_slots_busy_ncu": NCU_ISSUE_ACTIVE,
                          "fp32_alu": {"algorithmic_flop_per_env_step": ALGO_FLOP_PER_ENV_STEP, "peak_tflops": FP32_PEAK_TFLOPS,
                                       "achieved_tflops": ALGO_FLOP_PER_ENV_STEP * n / (sim_ms * 1e-3) / 1e12,
