@@ -65,6 +65,7 @@ static int set_attrs() {
   PCK(cudaFuncSetAttribute(k_gemm_tn<256, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmW) + 1024));
   PCK(cudaFuncSetAttribute(k_gemm_tn2<256, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmP) + 1024));
   PCK(cudaFuncSetAttribute(k_gemm_tn2<256, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmP) + 1024));
+  PCK(cudaFuncSetAttribute(k_gemm_tn2<256, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GSmP) + 1024));
   g_attr_set = true;
   return 0;
 }
@@ -83,7 +84,12 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
   static int pair_ok = -1;
   if (pair_ok < 0) { const char* e = getenv("SDX_GEMM_PAIR"); pair_ok = e ? atoi(e) : 1; }
   // CTA pairs (cta_group::2, 256 x 256 tile per pair) for the large bf16-output GEMMs: half the operand bytes per SM
-  const bool pair = pair_ok && ((mode == 0 && N >= 256) || (mode == 1 && N >= 1024)) && (long long)M * N >= (long long)256 * 256 * 74;
+  // ... and for the split-K dW GEMMs (mode 2): 128 x 128 tiles pull (128 + 128) x 64 x 2 B out of L2 per 128 x 128 x 64 MACs and are
+  // L2-bandwidth-bound (537 MB through L2 for dW L1 at M = 32768: 65-80 us); a 256 x 256 tile per CTA pair halves the bytes per MAC
+  static int pair_dw = -1;
+  if (pair_dw < 0) { const char* e = getenv("SDX_GEMM_PAIR_DW"); pair_dw = e ? atoi(e) : 1; }
+  const bool pair = pair_ok && (((mode == 0 && N >= 256) || (mode == 1 && N >= 1024)) && (long long)M * N >= (long long)256 * 256 * 74 ||
+                                (mode == 2 && pair_dw && M >= 256 && N >= 256 && K >= 8192));
   const bool wide = !pair && wide_ok && mode == 0 && N >= 256 && (long long)M * N >= (long long)GEMM_BM * 256 * 148;
   const int BNsel = (wide || pair) ? 256 : GEMM_BN;
   if (make_map(&ma, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM)) return -1;
@@ -118,7 +124,8 @@ extern "C" int sdx_gemm_bf16_tn(int mode, const void* A, int M, int K, int lda, 
     const size_t smp = sizeof(GSmP) + 1024;
     const int pairs = n_tiles < n_sm / 2 ? n_tiles : n_sm / 2;
     if (mode == 0) k_gemm_tn2<256, 4, 0><<<2 * pairs, GEMM_THREADS, smp, st>>>(ma, mb, mo, mt, mh, g);
-    else k_gemm_tn2<256, 4, 1><<<2 * pairs, GEMM_THREADS, smp, st>>>(ma, mb, mo, mt, mh, g);
+    else if (mode == 1) k_gemm_tn2<256, 4, 1><<<2 * pairs, GEMM_THREADS, smp, st>>>(ma, mb, mo, mt, mh, g);
+    else k_gemm_tn2<256, 4, 2><<<2 * pairs, GEMM_THREADS, smp, st>>>(ma, mb, mo, mt, mh, g);
   } else if (wide) {
     const size_t smw = sizeof(GSmW) + 1024;
     if (mode == 0) k_gemm_tn<256, 3, 0><<<grid, GEMM_THREADS, smw, st>>>(ma, mb, mo, mt, mh, g);
@@ -422,6 +429,13 @@ static int mlp_backward(sdx_mlp* m, const float* dout, int M, void* stream, int 
     PCK(cudaMemsetAsync(m->gW[l], 0, (size_t)N * ldg * 4, st));
     int tiles = ((N + 127) / 128) * ((K + 16 + 127) / 128);
     int splits = 296 / tiles; if (splits < 1) splits = 1;   // two tiles per persistent CTA: the second one's main loop hides the first one's reduction epilogue
+    static int dw_items = -1;                                // CTA-pair dW (256 x 256 tiles, sdx_gemm_bf16_tn): work items per pair (1: 47 / 52 / 29 us, 2: 49 / 53 / 33 us)
+    if (dw_items < 0) { const char* e = getenv("SDX_GEMM_DW_ITEMS"); dw_items = e ? atoi(e) : 1; }
+    { const char* e = getenv("SDX_GEMM_PAIR_DW");
+      if ((!e || atoi(e)) && N >= 256 && K + 16 >= 256 && M >= 8192) {
+        const int t2 = ((N + 255) / 256) * ((K + 16 + 255) / 256);
+        splits = (74 * dw_items) / t2; if (splits < 1) splits = 1;
+      } }
     if (sdx_gemm_bf16_tn(2, m->dZt[l + 1], N, M, m->max_rows, l == 0 ? (const void*)m->at0 : (const void*)m->At[l], K + 16, l == 0 ? m->ldt0 : m->max_rows, nullptr, nullptr, 0,
                          nullptr, 0, nullptr, 0, m->gW[l], ldg, splits, stream)) return -1;
     if (pipelined) {   // this layer's slice of the flat gradient vector is final NOW: publish it before the layers below are differentiated

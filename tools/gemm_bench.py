@@ -53,8 +53,13 @@ for (Nl, Kl, name) in [(1024, 448, "dW L1"), (512, 1024, "dW L2"), (256, 512, "d
     B = (torch.randn(Kl + 16, M, device="cuda") * 0.1).bfloat16()
     outf = torch.zeros(Nl, Kl + 16, device="cuda")
     tiles = ((Nl + 127) // 128) * ((Kl + 16 + 127) // 128)
-    for splits in sorted({max(1, (148 + tiles - 1) // tiles), max(1, (296 + tiles - 1) // tiles)}):
+    t2 = ((Nl + 255) // 256) * ((Kl + 16 + 255) // 256)
+    ref = torch.matmul(A.float(), B.float().T)
+    for splits in sorted({max(1, (148 + tiles - 1) // tiles), max(1, (296 + tiles - 1) // tiles), max(1, 74 // t2), max(1, 148 // t2)}):
         fn = lambda: _lib.check(L.sdx_gemm_bf16_tn(2, p(A), Nl, M, M, p(B), Kl + 16, M, None, None, 0, None, 0, None, 0, p(outf), Kl + 16, splits, st()))
+        outf.zero_(); fn(); torch.cuda.synchronize()
+        err = float((outf - ref).abs().max() / ref.abs().max())
+        assert err < 2e-3, (name, splits, err)               # split-K fp32 accumulation of bf16 products against the fp32 matmul
         t = timeit(fn)
         tc = timeit(lambda: torch.matmul(A, B.T))
         fl = 2.0 * M * Nl * (Kl + 16)
