@@ -378,7 +378,8 @@ class A2CAgent:
         would have to be captured by the communicator)."""
         self.lr_dev.fill_(self.last_lr)
         mode = os.environ.get("SEQDEX_PPO_GRAPH", "1")
-        graph_ok = mode != "0" and (self.world == 1 or (mode == "force" and not self.cfg.pipeline_allreduce))
+        graph_ok = (mode != "0" and not getattr(self, "_graph_failed", False)
+                    and (self.world == 1 or (mode == "force" and not self.cfg.pipeline_allreduce)))
         if graph_ok and getattr(self, "_graph", None) is not None:
             self._graph.replay()
             self.L.sdx_ppo_add_launches(ctypes.c_longlong(self._graph_launches))
@@ -393,9 +394,9 @@ class A2CAgent:
             except Exception:
                 if mode == "force":
                     raise
-                # capture is an optimisation: fall back to the eager path for good (e.g. a collective the communicator cannot capture)
+                # capture is an optimisation: this agent falls back to the eager path for good (e.g. a collective the communicator cannot capture)
                 torch.cuda.synchronize()
-                os.environ["SEQDEX_PPO_GRAPH"] = "0"
+                self._graph_failed = True
                 self._update_body()
             else:
                 self._graph, self._graph_launches = g, int(self.L.sdx_ppo_launch_count()) - l0

@@ -18,11 +18,20 @@ from seqdex_b200.scene import Scene                      # noqa: E402
 from seqdex_b200.tasks.block_assembly_grasp_sim import default_tvalue_weights   # noqa: E402
 
 n = int(os.environ.get('SIM_PROF_ENVS', '2048'))
-scene = Scene()
-bank = make_heap_bank(scene, 8)
-env = SdxEnv(scene, n)
-env.set_heap_bank(bank)
-env.set_tvalue_weights(default_tvalue_weights(22))
+TASK = os.environ.get('SIM_PROF_TASK', 'BlockAssemblyGraspSim')        # or ToolPositioningGrasp / ToolPositioningOrient (one free body)
+if TASK.startswith('ToolPositioning'):
+    from seqdex_b200.tasks.cfg import scene_from_cfg
+    from seqdex_b200.tasks.tool_positioning import synthetic_tool_grasp_bank
+    scene = scene_from_cfg(TASK)
+    env = SdxEnv(scene, n)
+    if TASK.endswith('Orient'):
+        env.set_grasp_bank(*synthetic_tool_grasp_bank(scene, 8, 0))
+else:
+    scene = Scene()
+    bank = make_heap_bank(scene, 8)
+    env = SdxEnv(scene, n)
+    env.set_heap_bank(bank)
+    env.set_tvalue_weights(default_tvalue_weights(22))
 gen = torch.Generator(device="cuda").manual_seed(1)
 env.step(torch.rand(n, 23, device="cuda", generator=gen) * 2 - 1)
 env.tensor("PROGRESS").copy_(torch.randint(0, 75, (n,), device="cuda", generator=gen))
