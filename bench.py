@@ -296,6 +296,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sleep-off", action="store_true", help="skip the extra rollout with sleeping switched off (reported beside the default)")
+    ap.add_argument("--edge-contacts", type=int, default=1, choices=[0, 1],
+                    help="0: the contact step without edge-edge contacts (the round-1 / early round-2 geometry; DESIGN.md section 3c), for A/B runs")
     ap.add_argument("--mode", default="ppo", choices=["ppo", "rollout"],
                     help="ppo: PPO training in the loop (policy forward, env step, GAE, 5 mini-epochs of updates every 8 steps); "
                          "rollout: VecTask.step only with U(-1,1) actions")
@@ -332,7 +334,7 @@ def main():
     # episodes run in lockstep as in the reference (time-outs only); GraspSim's per-env resets are staggered (see below)
     insert = args.task == "insert"
     task_name = TASKS[args.task][0]
-    scene = scene_from_cfg(task_name)               # the task's yaml-stated sim / env parameters (contact_offset 0.02 for Orient / Search)
+    scene = scene_from_cfg(task_name, edge_contacts=bool(args.edge_contacts))   # the task's yaml-stated sim / env parameters (contact_offset 0.02 for Orient / Search)
     obs_dim, state_dim = TASKS[args.task][1], (188 if insert else 564)
     env = SdxEnv(scene, n, local, seed=22 + rank)
     if args.task == "tool_grasp":                   # resets to a fixed start pose (TG:1459-1578): no bank

@@ -79,7 +79,10 @@ typedef struct sdx_scene_t {
   float tool_reset_pos[3];    /* where reset_idx puts the tool: (0.29, 0.19, 0.675) (TG:1496-1498) */
   float tool_pitch_sc[8];     /* (sin, cos) of k * 1.571 / 2, k = 0..3: the tool's pitch at reset is target_rot_rand * 1.571 (TG:1493-1495) */
   float tool_plate_pose[7];   /* the "extra lego" the tool's orientation is measured against: (0.25, -0.2, 0.618), Quat.from_euler_zyx(0, 3.1415, 0) (TG:1505-1512) */
-  float tool_pad[2];
+  /* EDGE-EDGE contacts (k_simulate's narrow phase): edge_contacts > 0.5 completes the corner-vs-face test with the separating-axis test
+   * over the nine edge-pair axes; a pair whose axis of least overlap is an edge pair -- by more than edge_pref [m] over every face axis --
+   * gets one contact at the closest points of the two edges, normal = that axis */
+  float edge_contacts, edge_pref;
 } sdx_scene_t;
 
 /* tasks sharing the scene, the contact step and the PPO engine (SURVEY.md section 8a "per-task dimensions"):

@@ -79,7 +79,7 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   float tool_reset_pos[3];             /* tool tasks: where reset_idx puts the tool (TG:1496-1498) */
   float tool_pitch_sc[8];              /* (sin, cos) of k * 1.571 / 2, k = 0..3 (TG:1493-1495) */
   float tool_plate_pose[7];            /* the "extra lego" pose after reset_idx (TG:1505-1512) */
-  float tool_pad[2];
+  float edge_contacts, edge_pref;      /* edge-edge contacts on (> 0.5) | how much smaller than every face overlap the edge overlap must be [m] */
 } sdx_scene_t;
 #define ORIENT_OBS_FRAME 62
 #define ORIENT_BANK_WRAP 10000
@@ -227,6 +227,7 @@ typedef struct {
   float bias;      /* target normal velocity */
   float inv[3];    /* 1 / (mass-split effective inverse mass) along n, t1, t2 */
   float f[3];      /* total impulse of the contact, world frame: lam_n n + lam_1 t1 + lam_2 t2 */
+  float n[3];      /* edge-edge contacts (word & EDGE_BIT): the normal, world frame */
 } contact_t;
 
 typedef struct {
@@ -292,8 +293,16 @@ static void link_twists(const sdx_scene_t* S, work_t* W) {
   }
 }
 
+#define EDGE_POINT 12
+#define EDGE_BIT (1u << 27)
 static void contact_axes(const work_t* W, const contact_t* c, v3* n, v3* t1, v3* t2) {
   int sh = (c->word >> 16) & 255, k = (c->word >> 24) & 3;
+  if (c->word & EDGE_BIT) { /* explicit normal; t1 = the target's edge direction (perpendicular to n by construction), t2 = n x t1 */
+    *n = V3(c->n[0], c->n[1], c->n[2]);
+    *t1 = mcol(W->sR[sh], k);
+    *t2 = vcross(*n, *t1);
+    return;
+  }
   float sg = ((c->word >> 26) & 1) ? -1.0f : 1.0f;
   *n = vscale(mcol(W->sR[sh], k), sg);
   *t1 = mcol(W->sR[sh], (k + 1) % 3);
@@ -347,6 +356,65 @@ static int g_reuse_audit = 0;
 static long g_reuse_stats[5];
 void sdxo_reuse_audit(int on) { g_reuse_audit = on; for (int i = 0; i < 5; ++i) g_reuse_stats[i] = 0; }
 void sdxo_reuse_stats(long out[5]) { for (int i = 0; i < 5; ++i) out[i] = g_reuse_stats[i]; }
+
+/* EDGE-EDGE contact of the pair (owner a, target t), in t's frame.  The corner-vs-face test cannot see two boxes that cross edge over
+ * edge: no corner of either lies over a face of the other until they have sunk centimetres into each other.  This is the rest of the
+ * separating-axis test: the owner's three face axes and the nine edge-pair axes t_r x a_c.  When every axis overlaps by more than -m and
+ * the axis of LEAST overlap is an edge pair -- by more than `pref` over every face axis -- one contact is generated at the closest points
+ * of the two edges, normal = that axis (pointing from t to a), depth = the overlap along it.  (csrc/sdx_sim.cuh: edge_contact, same text.) */
+static int edge_contact(const float* C, v3 lc, v3 ha, v3 ht, float m, float pref, v3* p_out, v3* n_out, float* depth_out, int* r_out) {
+  float A[9];
+  for (int i = 0; i < 9; ++i) A[i] = fabsf(C[i]);
+  const float hav[3] = {ha.x, ha.y, ha.z}, htv[3] = {ht.x, ht.y, ht.z}, lcv[3] = {lc.x, lc.y, lc.z};
+  float of = htv[0] + (A[0] * hav[0] + A[1] * hav[1] + A[2] * hav[2]) - fabsf(lcv[0]);
+  { const float o1 = htv[1] + (A[3] * hav[0] + A[4] * hav[1] + A[5] * hav[2]) - fabsf(lcv[1]); if (o1 < of) of = o1; }
+  { const float o2 = htv[2] + (A[6] * hav[0] + A[7] * hav[1] + A[8] * hav[2]) - fabsf(lcv[2]); if (o2 < of) of = o2; }
+  for (int c = 0; c < 3; ++c) { /* the owner's face axes */
+    const float la = lcv[0] * C[c] + lcv[1] * C[3 + c] + lcv[2] * C[6 + c];
+    const float oa = hav[c] + (A[c] * htv[0] + A[3 + c] * htv[1] + A[6 + c] * htv[2]) - fabsf(la);
+    if (oa < -m) return 0;
+    if (oa < of) of = oa;
+  }
+  float be = 1e30f; int br = -1, bc = -1;
+  for (int rc = 0; rc < 9; ++rc) { /* edge pairs: axis t_r x a_c */
+    const int r = rc / 3, c = rc - 3 * r;
+    const float cc = C[3 * r + c], s2 = 1.0f - cc * cc;
+    if (s2 < 1e-3f) continue; /* edges within 2 degrees of parallel: the face axes cover it */
+    const int r1 = r == 2 ? 0 : r + 1, r2 = r == 0 ? 2 : r - 1, c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+    const float ra = hav[c1] * A[3 * r + c2] + hav[c2] * A[3 * r + c1];
+    const float rb = htv[r1] * A[3 * r2 + c] + htv[r2] * A[3 * r1 + c];
+    const float dist = fabsf(lcv[r2] * C[3 * r1 + c] - lcv[r1] * C[3 * r2 + c]);
+    const float ov = (ra + rb - dist) / sqrtf(s2);
+    if (ov < -m) return 0;
+    if (ov < be) { be = ov; br = r; bc = c; }
+  }
+  if (br < 0 || !(be < of - pref)) return 0; /* a face axis is (about) the axis of least overlap: the corner-face contacts have it */
+  const int r = br, c = bc;
+  const float cc = C[3 * r + c], s2 = 1.0f - cc * cc, s = sqrtf(s2);
+  const v3 ac = V3(C[c], C[3 + c], C[6 + c]); /* the owner's axis c in t's frame */
+  v3 n = r == 0 ? V3(0.0f, -ac.z, ac.y) : (r == 1 ? V3(ac.z, 0.0f, -ac.x) : V3(-ac.y, ac.x, 0.0f)); /* e_r x ac */
+  n = V3(n.x / s, n.y / s, n.z / s);
+  if (n.x * lcv[0] + n.y * lcv[1] + n.z * lcv[2] < 0.0f) n = vneg(n); /* from t towards a */
+  const float nv[3] = {n.x, n.y, n.z};
+  float pt[3], pa[3] = {lcv[0], lcv[1], lcv[2]};
+  for (int k = 0; k < 3; ++k) pt[k] = k == r ? 0.0f : (nv[k] >= 0.0f ? htv[k] : -htv[k]); /* t's edge: its support towards a */
+  for (int k = 0; k < 3; ++k) {
+    if (k == c) continue;
+    const float nk = nv[0] * C[k] + nv[1] * C[3 + k] + nv[2] * C[6 + k];
+    const float co = nk >= 0.0f ? -hav[k] : hav[k]; /* a's edge: its support towards t */
+    pa[0] = pa[0] + co * C[k]; pa[1] = pa[1] + co * C[3 + k]; pa[2] = pa[2] + co * C[6 + k];
+  }
+  const float d0[3] = {pa[0] - pt[0], pa[1] - pt[1], pa[2] - pt[2]};
+  const float de = d0[r], da = d0[0] * ac.x + d0[1] * ac.y + d0[2] * ac.z;
+  float u = (de - cc * da) / s2, v = (cc * de - da) / s2; /* closest points of the two edge LINES, clamped to the edges */
+  u = clampf(u, -htv[r], htv[r]); v = clampf(v, -hav[c], hav[c]);
+  float qt[3] = {pt[0], pt[1], pt[2]};
+  qt[r] = u;
+  const v3 qa = V3(pa[0] + v * ac.x, pa[1] + v * ac.y, pa[2] + v * ac.z);
+  *p_out = V3(0.5f * (qt[0] + qa.x), 0.5f * (qt[1] + qa.y), 0.5f * (qt[2] + qa.z));
+  *n_out = n; *depth_out = be; *r_out = r;
+  return 1;
+}
 
 static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_out, float* jac7, float* netf,
                     int* ncontact, float* condump, float* ws, int* wsn, int ws_cur, unsigned char* slp, work_t* W, int env) {
@@ -541,21 +609,34 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
         uint32_t sg = lck >= 0.0f ? 0u : 1u;
         if (t >= NB + nrs && k == 2) { sgf = 1.0f; sg = 0u; } /* statics rest on each other: their z faces only push UP */
         float htk = k == 0 ? ht.x : (k == 1 ? ht.y : ht.z);
-        for (int p = 0; p < npts; ++p) {
+        for (int p = 0; p <= EDGE_POINT; ++p) {
+          if (p >= npts && p < EDGE_POINT) continue;
+          float depth; v3 wpt; uint32_t word; v3 en = V3(0.0f, 0.0f, 0.0f);
+          if (p == EDGE_POINT) { /* the pair's edge-edge contact, once per unordered pair (owner index below target index) */
+            if (!(S->edge_contacts > 0.5f && a < t)) continue;
+            v3 ep; int er;
+            if (!edge_contact(C, lc, ha, ht, m, S->edge_pref, &ep, &en, &depth, &er)) continue;
+            wpt = vadd(W->sc[t], mmul(W->sR[t], ep));
+            en = mmul(W->sR[t], en);
+            word = (uint32_t)W->sbody[a] | ((uint32_t)W->sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)er << 24) | EDGE_BIT;
+          } else {
           v3 pl;
           if (p < 8) pl = V3((p & 1) ? ha.x : -ha.x, (p & 2) ? ha.y : -ha.y, (p & 4) ? ha.z : -ha.z);
           else pl = V3(0.0f, (p & 1) ? ha.y : -ha.y, (p & 2) ? ha.z : -ha.z);
           v3 l = vadd(lc, mmul(C, pl));
           float lk = k == 0 ? l.x : (k == 1 ? l.y : l.z);
-          float depth = htk - sgf * lk;
+          depth = htk - sgf * lk;
           if (!(depth > -m)) continue;
           int inface = (k == 0 || fabsf(l.x) <= ht.x + fmargin) && (k == 1 || fabsf(l.y) <= ht.y + fmargin) &&
                        (k == 2 || fabsf(l.z) <= ht.z + fmargin);
           if (!inface) continue;
+          wpt = vadd(W->sc[a], mmul(W->sR[a], pl));
+          word = (uint32_t)W->sbody[a] | ((uint32_t)W->sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)k << 24) | (sg << 26);
+          }
           if (W->ncon >= SDX_MAX_CONTACTS) { W->ndropped++; continue; }
           contact_t* c = &W->con[W->ncon++];
-          v3 wpt = vadd(W->sc[a], mmul(W->sR[a], pl));
-          c->word = (uint32_t)W->sbody[a] | ((uint32_t)W->sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)k << 24) | (sg << 26);
+          c->word = word;
+          c->n[0] = en.x; c->n[1] = en.y; c->n[2] = en.z;
           c->w[0] = wpt.x; c->w[1] = wpt.y; c->w[2] = wpt.z;
           float bias = 0.0f;
           if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }

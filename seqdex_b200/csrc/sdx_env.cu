@@ -57,7 +57,7 @@ struct sdx_env {
   float* last_pixels = nullptr;
   float *sb_rows = nullptr, *sb_hand = nullptr; int* sb_index = nullptr; int sb_wrap = 0;
   int64_t* progress0_host = nullptr;   // pinned: progress_buf[0] (SE:989 reads it on the host every step)
-  float4* cscratch = nullptr;      // [n][3][MAXC] contact records / impulses of k_simulate (SIM_GLOBAL_CONTACTS, SIM_GLOBAL_CF)
+  float4* cscratch = nullptr;      // [n][4][MAXC] contact records / impulses / edge-contact normals of k_simulate
   // BlockAssemblyInsertSim
   float *ib_obj = nullptr, *ib_hand = nullptr; int ib_per_type = 0;   // the banked grasps reset_idx restores (sdx_set_grasp_bank)
   int* slot_by_env = nullptr;      // test hook: reset slots given per env instead of drawn
@@ -156,7 +156,7 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
   CK(cudaMalloc(&E->stage_states, n * obs_stack(E) * SDX_STATE_FRAME * 4));
   CK(cudaMalloc(&E->stage_actions, n * 23 * 4));
 #if SIM_GLOBAL_CONTACTS
-  CK(cudaMalloc(&E->cscratch, n * 3 * MAXC * sizeof(float4)));
+  CK(cudaMalloc(&E->cscratch, n * 4 * MAXC * sizeof(float4)));
 #endif
   CK(cudaFuncSetAttribute(k_simulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
   CK(cudaFuncSetAttribute(k_simulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));

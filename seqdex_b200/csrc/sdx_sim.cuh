@@ -298,6 +298,16 @@ __device__ __forceinline__ void contact_axes(const SimSmem& M, uint32_t word, v3
   *t1 = mcol(M.sR[sh], (k + 1) % 3);
   *t2 = mcol(M.sR[sh], (k + 2) % 3);
 }
+// edge-edge contacts carry their normal explicitly (CN); t1 = the target's edge direction (axis k of its box, perpendicular to n by
+// construction), t2 = n x t1
+__device__ __forceinline__ void contact_axes_e(const SimSmem& M, uint32_t word, const float4* CN, int i, v3* n, v3* t1, v3* t2) {
+  if (word & (1u << 27)) {
+    const float4 N4 = CN[i];
+    *n = V3(N4.x, N4.y, N4.z);
+    *t1 = mcol(M.sR[(word >> 16) & 255], (word >> 24) & 3);
+    *t2 = vcross(*n, *t1);
+  } else contact_axes(M, word, n, t1, t2);
+}
 
 __device__ float body_k(const sdx_scene_t* __restrict__ S, const SimSmem& M, int body, v3 wpt, v3 d) {
   if (body == STATIC_BODY) return 0.0f;
@@ -364,6 +374,96 @@ __device__ __forceinline__ bool point_hit(const PairGeom& G, int p, float m, flo
   return inface;
 }
 
+// EDGE-EDGE contact of the pair (owner a, target t), in t's frame (oracle: edge_contact, operation for operation).  The corner-vs-face
+// test above cannot see two boxes that cross edge over edge: no corner of either lies over a face of the other until they have sunk
+// centimetres into each other (84 % of the overlaps deeper than 2 mm in a settled heap were of this kind).  This is the rest of the
+// separating-axis test: the owner's three face axes and the nine edge-pair axes t_r x a_c.  When every axis overlaps by more than
+// -m and the axis of LEAST overlap is an edge pair -- by more than `pref` over every face axis -- one contact is generated at the
+// closest points of the two edges, normal = that axis (pointing from t to a), depth = the overlap along it.
+#define EDGE_POINT 12                  /* its bit in the pair mask / its "sample point" number in the warm-start key */
+#define EDGE_BIT (1u << 27)            /* contact word: the normal is explicit (CN), t1 = axis k of the target shape */
+struct EdgeGeom { v3 p, n; float depth; int r; };
+__device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+// The SAT part, fully unrolled so that C / |C| stay in registers.  An edge axis whose UN-normalised overlap already is no smaller than the
+// least face overlap cannot be the axis of least overlap (the normalised overlap is ov / s with s <= 1): its square root and division are
+// skipped -- the result is what the plain loop of the oracle computes.  Returns the edge pair (r, c) in *rc (r * 3 + c) or -1.
+__device__ __forceinline__ bool edge_sat(const PairGeom& G, float m, float pref, int* rc_out, float* be_out) {
+  const float* C = G.C;
+  float A[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) A[i] = fabsf(C[i]);
+  const float hav[3] = {G.ha.x, G.ha.y, G.ha.z}, htv[3] = {G.ht.x, G.ht.y, G.ht.z}, lcv[3] = {G.lc.x, G.lc.y, G.lc.z};
+  float of = htv[0] + (A[0] * hav[0] + A[1] * hav[1] + A[2] * hav[2]) - fabsf(lcv[0]);
+  { const float o1 = htv[1] + (A[3] * hav[0] + A[4] * hav[1] + A[5] * hav[2]) - fabsf(lcv[1]); if (o1 < of) of = o1; }
+  { const float o2 = htv[2] + (A[6] * hav[0] + A[7] * hav[1] + A[8] * hav[2]) - fabsf(lcv[2]); if (o2 < of) of = o2; }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {                                      // the owner's face axes
+    const float la = lcv[0] * C[c] + lcv[1] * C[3 + c] + lcv[2] * C[6 + c];
+    const float oa = hav[c] + (A[c] * htv[0] + A[3 + c] * htv[1] + A[6 + c] * htv[2]) - fabsf(la);
+    if (oa < -m) return false;
+    if (oa < of) of = oa;
+  }
+  float be = 1e30f; int brc = -1;
+#pragma unroll
+  for (int rc = 0; rc < 9; ++rc) {                                   // edge pairs: axis t_r x a_c
+    const int r = rc / 3, c = rc - 3 * r;
+    const float cc = C[3 * r + c], s2 = 1.0f - cc * cc;
+    if (s2 < 1e-3f) continue;                                        // edges within 2 degrees of parallel: the face axes cover it
+    const int r1 = r == 2 ? 0 : r + 1, r2 = r == 0 ? 2 : r - 1, c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+    const float ra = hav[c1] * A[3 * r + c2] + hav[c2] * A[3 * r + c1];
+    const float rb = htv[r1] * A[3 * r2 + c] + htv[r2] * A[3 * r1 + c];
+    const float dist = fabsf(lcv[r2] * C[3 * r1 + c] - lcv[r1] * C[3 * r2 + c]);
+    const float raw = ra + rb - dist;
+    if (raw >= 0.0f && raw >= of - pref) continue;                   // ov = raw / s >= raw: not below the face axes, and not separating
+    const float ov = raw / sqrtf(s2);
+    if (ov < -m) return false;
+    if (ov < be) { be = ov; brc = rc; }
+  }
+  if (brc < 0 || !(be < of - pref)) return false;                    // a face axis is (about) the axis of least overlap: the corner-face contacts have it
+  *rc_out = brc; *be_out = be;
+  return true;
+}
+// the contact of the edge pair (r, c) pass 1 found (it travels in the pair mask): closest points of the two edges, normal, and the
+// depth = the overlap along that axis, evaluated by the expression edge_sat (and the oracle) used when it chose the pair
+__device__ __noinline__ void edge_point(const PairGeom& G, int rc, EdgeGeom& E) {
+  const float* C = G.C;
+  const int r = rc / 3, c = rc - 3 * r;
+  const float hav[3] = {G.ha.x, G.ha.y, G.ha.z}, htv[3] = {G.ht.x, G.ht.y, G.ht.z}, lcv[3] = {G.lc.x, G.lc.y, G.lc.z};
+  const float cc = C[3 * r + c], s2 = 1.0f - cc * cc, s = sqrtf(s2);
+  float be;
+  {
+    const int r1 = r == 2 ? 0 : r + 1, r2 = r == 0 ? 2 : r - 1, c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+    const float ra = hav[c1] * fabsf(C[3 * r + c2]) + hav[c2] * fabsf(C[3 * r + c1]);
+    const float rb = htv[r1] * fabsf(C[3 * r2 + c]) + htv[r2] * fabsf(C[3 * r1 + c]);
+    const float dist = fabsf(lcv[r2] * C[3 * r1 + c] - lcv[r1] * C[3 * r2 + c]);
+    be = (ra + rb - dist) / s;
+  }
+  const v3 ac = V3(C[c], C[3 + c], C[6 + c]);                        // the owner's axis c in t's frame
+  v3 n = r == 0 ? V3(0.0f, -ac.z, ac.y) : (r == 1 ? V3(ac.z, 0.0f, -ac.x) : V3(-ac.y, ac.x, 0.0f));   // e_r x ac
+  n = V3(n.x / s, n.y / s, n.z / s);
+  if (n.x * lcv[0] + n.y * lcv[1] + n.z * lcv[2] < 0.0f) n = vneg(n);                                   // from t towards a
+  const float nv[3] = {n.x, n.y, n.z};
+  float pt[3], pa[3] = {lcv[0], lcv[1], lcv[2]};
+  for (int k = 0; k < 3; ++k) pt[k] = k == r ? 0.0f : (nv[k] >= 0.0f ? htv[k] : -htv[k]);              // t's edge: its support towards a
+  for (int k = 0; k < 3; ++k) {
+    if (k == c) continue;
+    const float nk = nv[0] * C[k] + nv[1] * C[3 + k] + nv[2] * C[6 + k];
+    const float co = nk >= 0.0f ? -hav[k] : hav[k];                                                     // a's edge: its support towards t
+    pa[0] = pa[0] + co * C[k]; pa[1] = pa[1] + co * C[3 + k]; pa[2] = pa[2] + co * C[6 + k];
+  }
+  const float d0[3] = {pa[0] - pt[0], pa[1] - pt[1], pa[2] - pt[2]};
+  const float de = d0[r], da = d0[0] * ac.x + d0[1] * ac.y + d0[2] * ac.z;
+  float u = (de - cc * da) / s2, v = (cc * de - da) / s2;            // closest points of the two edge LINES, clamped to the edges
+  u = clampf(u, -htv[r], htv[r]); v = clampf(v, -hav[c], hav[c]);
+  float qt[3] = {pt[0], pt[1], pt[2]};
+  qt[r] = u;
+  const v3 qa = V3(pa[0] + v * ac.x, pa[1] + v * ac.y, pa[2] + v * ac.z);
+  E.p = V3(0.5f * (qt[0] + qa.x), 0.5f * (qt[1] + qa.y), 0.5f * (qt[2] + qa.z));
+  E.n = n; E.depth = be; E.r = r;
+}
+
+// contacts of a pair: the sample points that hit (bits 0-11) + its edge-edge contact (bits 12-15 non-zero)
+__device__ __forceinline__ int mask_count(unsigned mk) { return __popc(mk & 0xfffu) + ((mk >> EDGE_POINT) ? 1 : 0); }
 __device__ __forceinline__ void touch_or(unsigned char* flags, int i, unsigned bits) {
   atomicOr(reinterpret_cast<unsigned*>(flags) + (i >> 2), bits << (8 * (i & 3)));
 }
@@ -383,7 +483,7 @@ __global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
            int* __restrict__ ncontact, float* __restrict__ condump, float* ws, int* wsn, int ws_cur,
-           unsigned char* __restrict__ slp, int n_envs, float4* cscratch /* [n_envs][3][MAXC]: contact records (SIM_GLOBAL_CONTACTS), impulses (SIM_GLOBAL_CF) */) {
+           unsigned char* __restrict__ slp, int n_envs, float4* cscratch /* [n_envs][4][MAXC]: contact records (SIM_GLOBAL_CONTACTS), impulses (SIM_GLOBAL_CF), explicit normals of edge contacts */) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SimSmem& M = *reinterpret_cast<SimSmem*>(smem_raw);
   const int e = blockIdx.x, tid = threadIdx.x;
@@ -399,17 +499,20 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   float* gbrick = brick + (size_t)e * 13 * NB;
   float* gdof = dof + (size_t)e * 72;
 #if SIM_GLOBAL_CONTACTS
-  float4* const CA = cscratch + (size_t)e * 3 * MAXC;   // plain (coherent, L1-cached) loads / stores: written and read by this CTA only
+  float4* const CA = cscratch + (size_t)e * 4 * MAXC;   // plain (coherent, L1-cached) loads / stores: written and read by this CTA only
   float4* const CB = CA + MAXC;
 #else
   float4* const CA = M.ca;
   float4* const CB = M.cb;
 #endif
 #if SIM_GLOBAL_CF
-  float4* const CF = cscratch + (size_t)e * 3 * MAXC + 2 * MAXC;
+  float4* const CF = cscratch + (size_t)e * 4 * MAXC + 2 * MAXC;
 #else
   float4* const CF = M.cf4;
 #endif
+  float4* const CN = cscratch + (size_t)e * 4 * MAXC + 3 * MAXC;         // explicit normals (edge-edge contacts only)
+  const bool edges = S->edge_contacts > 0.5f;
+  const float epref = S->edge_pref;
   unsigned char* const cf_bytes = reinterpret_cast<unsigned char*>(CF);   // 16 KB of scratch while the impulses are not live
 
   // ---- TMA bulk load of the env's brick tile into shared memory
@@ -688,9 +791,10 @@ SIM_BROAD_UNROLL
         if (!dead && pair_geom(M, a, t, m, G, t >= NB + nrs)) {
           int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
           for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, fmargin, &d)) mk |= (unsigned short)(1u << p); }
+          if (edges && a < t) { int erc; float ebe; if (edge_sat(G, m, epref, &erc, &ebe)) mk |= (unsigned short)((erc + 1) << EDGE_POINT); }   // once per unordered pair; bits 12-15: edge pair + 1
         }
         pmask[i] = mk;
-        mycount += __popc((unsigned)mk);
+        mycount += mask_count(mk);
       }
       // running contact offsets: warp-level inclusive scan of the per-thread counts + the totals of the warps before (one barrier)
       incl = mycount;
@@ -714,7 +818,7 @@ SIM_BROAD_UNROLL
 #pragma unroll
       for (int w = 0; w < SIM_THREADS / 32; ++w) { const int v = M.scan[w]; if (w < (tid >> 5)) run += v; }
       if (tid == 0) { M.ncon = total < MAXC ? total : MAXC; M.ndropped = total > MAXC ? total - MAXC : 0; }
-      for (int i = p0; i < p1; ++i) { pstart[i] = (unsigned short)min(run, 65535); run += __popc((unsigned)pmask[i]); }
+      for (int i = p0; i < p1; ++i) { pstart[i] = (unsigned short)min(run, 65535); run += mask_count(pmask[i]); }
     }
     __syncthreads();
     PMARK(6);
@@ -741,7 +845,8 @@ SIM_BROAD_UNROLL
         int i = stash_pair[r];
         unsigned mk = stash_mask[r];
         int j = stash_j[r], p = 0;
-        for (;; ++p) { if (mk & (1u << p)) { if (j == 0) break; --j; } }
+        if (j >= __popc(mk & 0xfffu)) p = EDGE_POINT;             // the pair's last contact: its edge-edge contact
+        else for (;; ++p) { if (mk & (1u << p)) { if (j == 0) break; --j; } }
         int lo = 0, hi = n_owner - 1;                  // owner a with poff[a] <= i < poff[a+1]
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (M.poff[mid] <= i) lo = mid; else hi = mid - 1; }
         const int a = lo, t = M.cand[a][i - M.poff[a]];
@@ -749,9 +854,21 @@ SIM_BROAD_UNROLL
         PairGeom G;
         pair_geom(M, a, t, m, G, t >= NB + nrs);
         float depth;
-        point_hit(G, p, m, fmargin, &depth);
-        v3 wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
-        const uint32_t wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
+        v3 wpt;
+        uint32_t wdn;
+        if (p == EDGE_POINT) {
+          EdgeGeom E;
+          edge_point(G, (int)(mk >> EDGE_POINT) - 1, E);
+          depth = E.depth;
+          wpt = vadd(ld3(M.sc[t]), mmul(M.sR[t], E.p));
+          const v3 nw = mmul(M.sR[t], E.n);
+          CN[slot] = make_float4(nw.x, nw.y, nw.z, 0.0f);
+          wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)E.r << 24) | EDGE_BIT;
+        } else {
+          point_hit(G, p, m, fmargin, &depth);
+          wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
+          wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
+        }
         float bias = 0.0f;
         if (depth > S->slop) { bias = S->baumgarte * (depth - S->slop) / h; if (bias > S->max_depen_vel) bias = S->max_depen_vel; }
         else if (depth < 0.0f) bias = depth / h;
@@ -895,17 +1012,20 @@ SIM_BROAD_UNROLL
 #if SIM_SMALL_CODE
       float inv[3];
       const int sh = (wd >> 16) & 255, k = (wd >> 24) & 3;
+      v3 en = V3(0.0f, 0.0f, 0.0f), et1 = en, et2 = en;
+      if (wd & EDGE_BIT) contact_axes_e(M, wd, CN, i, &en, &et1, &et2);
 #pragma unroll 1
       for (int ax = 0; ax < 3; ++ax) {                        // n, t1, t2 in turn (contact_axes), one copy of body_k x 2
         const int col = k + ax >= 3 ? k + ax - 3 : k + ax;
         v3 d = mcol(M.sR[sh], col);
         if (ax == 0) d = vscale(d, ((wd >> 26) & 1) ? -1.0f : 1.0f);
+        if (wd & EDGE_BIT) d = ax == 0 ? en : (ax == 1 ? et1 : et2);
         const float iv = 1.0f / (body_k(S, M, a, wpt, d) + body_k(S, M, b, wpt, d));
         if (ax == 0) inv[0] = iv; else if (ax == 1) inv[1] = iv; else inv[2] = iv;
       }
       CB[i] = make_float4(inv[0], inv[1], inv[2], __uint_as_float(wd));
 #else
-      v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
+      v3 n, t1, t2; contact_axes_e(M, wd, CN, i, &n, &t1, &t2);
       float i0 = 1.0f / (body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n));
       float i1 = 1.0f / (body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1));
       float i2 = 1.0f / (body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2));
@@ -926,7 +1046,7 @@ SIM_BROAD_UNROLL
         const float4 A4 = CA[i], B4 = CB[i], F4 = CF[i];
         uint32_t wd = __float_as_uint(B4.w);
         int a = wd & 255, b = (wd >> 8) & 255;
-        v3 n, t1, t2; contact_axes(M, wd, &n, &t1, &t2);
+        v3 n, t1, t2; contact_axes_e(M, wd, CN, i, &n, &t1, &t2);
         v3 wpt = V3(A4.x, A4.y, A4.z);
         v3 f = V3(F4.x, F4.y, F4.z);
         v3 vrel = vadd(ldv(M.bv[a]), vcross(ldv(M.bw[a]), vsub(wpt, ldv(M.bx[a]))));
