@@ -363,6 +363,13 @@ void sdxo_reuse_stats(long out[5]) { for (int i = 0; i < 5; ++i) out[i] = g_reus
  * the axis of LEAST overlap is an edge pair -- by more than `pref` over every face axis -- one contact is generated at the closest points
  * of the two edges, normal = that axis (pointing from t to a), depth = the overlap along it.  (csrc/sdx_sim.cuh: edge_contact, same text.) */
 static int edge_contact(const float* C, v3 lc, v3 ha, v3 ht, float m, float pref, v3* p_out, v3* n_out, float* depth_out, int* r_out) {
+  /* one axis of each box (nearly) parallel, t_r || a_c: every edge-pair axis t_r' x a_c' then coincides with a face axis of one of the
+   * boxes (or vanishes), so a face axis holds the least overlap -- no edge-edge contact (csrc/sdx_sim.cuh: edge_axes_parallel) */
+  {
+    float mx = C[0] * C[0];
+    for (int i = 1; i < 9; ++i) { const float c2 = C[i] * C[i]; mx = c2 > mx ? c2 : mx; }
+    if (1.0f - mx < 1e-3f) return 0;
+  }
   float A[9];
   for (int i = 0; i < 9; ++i) A[i] = fabsf(C[i]);
   const float hav[3] = {ha.x, ha.y, ha.z}, htv[3] = {ht.x, ht.y, ht.z}, lcv[3] = {lc.x, lc.y, lc.z};

@@ -158,8 +158,10 @@ extern "C" int sdx_create(const sdx_scene_t* scene, int num_envs, int device, ui
 #if SIM_GLOBAL_CONTACTS
   CK(cudaMalloc(&E->cscratch, n * 4 * MAXC * sizeof(float4)));
 #endif
-  CK(cudaFuncSetAttribute(k_simulate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
-  CK(cudaFuncSetAttribute(k_simulate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
+  CK(cudaFuncSetAttribute(k_simulate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
+  CK(cudaFuncSetAttribute(k_simulate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
+  CK(cudaFuncSetAttribute(k_simulate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
+  CK(cudaFuncSetAttribute(k_simulate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SimSmem)));
   *out = E;
   return sdx_reset_all(E);
 }
@@ -458,7 +460,8 @@ extern "C" int sdx_pre_physics(sdx_env_t* E, const float* actions_dev) {
 
 extern "C" int sdx_simulate(sdx_env_t* E) {
   CK(cudaSetDevice(E->device));
-  auto kern = E->host_scene.n_bshapes > 0 ? k_simulate<true> : k_simulate<false>;      // compound free bodies or one box per body
+  const bool cmp = E->host_scene.n_bshapes > 0, edge = E->host_scene.edge_contacts > 0.5f;   // compound free bodies or one box per body | edge-edge contacts
+  auto kern = cmp ? (edge ? k_simulate<true, true> : k_simulate<true, false>) : (edge ? k_simulate<false, true> : k_simulate<false, false>);
   kern<<<E->n, SIM_THREADS, sizeof(SimSmem), E->stream>>>(E->scene, F(SDX_T_BRICK), F(SDX_T_DOF), F(SDX_T_LINK), F(SDX_T_JAC7),
                                                               F(SDX_T_NETF), I32(SDX_T_NCONTACT),
                                                               E->dump_contacts ? F(SDX_T_CONTACTS) : nullptr, F(SDX_T_WS), I32(SDX_T_WSN),

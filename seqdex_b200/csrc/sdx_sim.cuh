@@ -121,6 +121,7 @@ struct SimSmem {
   int scan[SIM_THREADS];
   int ncon, ndropped;                  // contacts of the sub-step | contacts beyond MAXC (after shedding the speculative ones)
   int ndrop_cand, ndrop_static;        // candidate pairs beyond KC when the lists were last built | of those, pairs against statics (statics claim their slots first: 0)
+  int nelist;                          // EDGE: pairs queued for the edge-axis test of this sub-step (narrow phase, pass 1b)
   int nact;                            // lanes phase B occupies: sum over awake, touched bricks of their lane-group size
   unsigned char lmap[PB_LANES_MAX];    // phase-B lane -> brick
   unsigned char sflag[NB], touch[NB];  // sleeping: sflag bit0 = asleep this sub-step, bit1 = hot at its start; touch bit0 = robot, bit1 = hot brick
@@ -300,13 +301,30 @@ __device__ __forceinline__ void contact_axes(const SimSmem& M, uint32_t word, v3
 }
 // edge-edge contacts carry their normal explicitly (CN); t1 = the target's edge direction (axis k of its box, perpendicular to n by
 // construction), t2 = n x t1
+template <bool EDGE>
 __device__ __forceinline__ void contact_axes_e(const SimSmem& M, uint32_t word, const float4* CN, int i, v3* n, v3* t1, v3* t2) {
-  if (word & (1u << 27)) {
+  if (EDGE && (word & (1u << 27))) {
     const float4 N4 = CN[i];
     *n = V3(N4.x, N4.y, N4.z);
     *t1 = mcol(M.sR[(word >> 16) & 255], (word >> 24) & 3);
     *t2 = vcross(*n, *t1);
   } else contact_axes(M, word, n, t1, t2);
+}
+
+// the same axes WITHOUT a branch, for the solver's phase A (a warp that holds one edge contact would otherwise run both paths in every
+// pass): the explicit normal N4 = CN[i] is loaded for every contact (garbage for the others: selected away, never computed with)
+template <bool EDGE>
+__device__ __forceinline__ void contact_axes_sel(const SimSmem& M, uint32_t word, const float4 N4, v3* n, v3* t1, v3* t2) {
+  if (!EDGE) { contact_axes(M, word, n, t1, t2); return; }
+  const int sh = (word >> 16) & 255, k = (word >> 24) & 3;
+  const float sg = ((word >> 26) & 1) ? -1.0f : 1.0f;
+  const bool e = (word & (1u << 27)) != 0u;
+  const v3 c0 = mcol(M.sR[sh], k), c1 = mcol(M.sR[sh], (k + 1) % 3), c2 = mcol(M.sR[sh], (k + 2) % 3);
+  const v3 nf = vscale(c0, sg);
+  *n = e ? V3(N4.x, N4.y, N4.z) : nf;
+  *t1 = e ? c0 : c1;
+  const v3 tx = vcross(*n, c0);
+  *t2 = e ? tx : c2;
 }
 
 __device__ float body_k(const sdx_scene_t* __restrict__ S, const SimSmem& M, int body, v3 wpt, v3 d) {
@@ -384,6 +402,15 @@ __device__ __forceinline__ bool point_hit(const PairGeom& G, int p, float m, flo
 #define EDGE_BIT (1u << 27)            /* contact word: the normal is explicit (CN), t1 = axis k of the target shape */
 struct EdgeGeom { v3 p, n; float depth; int r; };
 __device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+// A pair of boxes with one axis of each (nearly) parallel has no edge-edge contact: with t_r || a_c every edge-pair axis t_r' x a_c'
+// coincides with a face axis of one of the boxes (or vanishes), so the face axes already hold the least overlap -- every brick that
+// lies flat on the slab or on another flat brick.  Same threshold as the per-axis test below (1 - cc^2 < 1e-3: within 2 degrees).
+__device__ __forceinline__ bool edge_axes_parallel(const float* C) {
+  float mx = C[0] * C[0];
+#pragma unroll
+  for (int i = 1; i < 9; ++i) { const float c2 = C[i] * C[i]; mx = c2 > mx ? c2 : mx; }
+  return 1.0f - mx < 1e-3f;
+}
 // The SAT part, fully unrolled so that C / |C| stay in registers.  An edge axis whose UN-normalised overlap already is no smaller than the
 // least face overlap cannot be the axis of least overlap (the normalised overlap is ov / s with s <= 1): its square root and division are
 // skipped -- the result is what the plain loop of the oracle computes.  Returns the edge pair (r, c) in *rc (r * 3 + c) or -1.
@@ -425,40 +452,46 @@ __device__ __forceinline__ bool edge_sat(const PairGeom& G, float m, float pref,
 }
 // the contact of the edge pair (r, c) pass 1 found (it travels in the pair mask): closest points of the two edges, normal, and the
 // depth = the overlap along that axis, evaluated by the expression edge_sat (and the oracle) used when it chose the pair
-__device__ __noinline__ void edge_point(const PairGeom& G, int rc, EdgeGeom& E) {
+__device__ __forceinline__ void edge_point(const PairGeom& G, int rc, EdgeGeom& E) {
+  // r, c are run-time values: every indexed access is a select over registers (an array indexed at run time would live in local memory)
   const float* C = G.C;
   const int r = rc / 3, c = rc - 3 * r;
-  const float hav[3] = {G.ha.x, G.ha.y, G.ha.z}, htv[3] = {G.ht.x, G.ht.y, G.ht.z}, lcv[3] = {G.lc.x, G.lc.y, G.lc.z};
-  const float cc = C[3 * r + c], s2 = 1.0f - cc * cc, s = sqrtf(s2);
+  const int r1 = r == 2 ? 0 : r + 1, r2 = r == 0 ? 2 : r - 1, c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
+  const v3 ha = G.ha, ht = G.ht, lc = G.lc;
+  const v3 Cr = r == 0 ? V3(C[0], C[1], C[2]) : (r == 1 ? V3(C[3], C[4], C[5]) : V3(C[6], C[7], C[8]));        // row r
+  const v3 Cr1 = r1 == 0 ? V3(C[0], C[1], C[2]) : (r1 == 1 ? V3(C[3], C[4], C[5]) : V3(C[6], C[7], C[8]));
+  const v3 Cr2 = r2 == 0 ? V3(C[0], C[1], C[2]) : (r2 == 1 ? V3(C[3], C[4], C[5]) : V3(C[6], C[7], C[8]));
+  const float cc = sel3(Cr.x, Cr.y, Cr.z, c), s2 = 1.0f - cc * cc, s = sqrtf(s2);
   float be;
   {
-    const int r1 = r == 2 ? 0 : r + 1, r2 = r == 0 ? 2 : r - 1, c1 = c == 2 ? 0 : c + 1, c2 = c == 0 ? 2 : c - 1;
-    const float ra = hav[c1] * fabsf(C[3 * r + c2]) + hav[c2] * fabsf(C[3 * r + c1]);
-    const float rb = htv[r1] * fabsf(C[3 * r2 + c]) + htv[r2] * fabsf(C[3 * r1 + c]);
-    const float dist = fabsf(lcv[r2] * C[3 * r1 + c] - lcv[r1] * C[3 * r2 + c]);
+    const float ra = sel3(ha.x, ha.y, ha.z, c1) * fabsf(sel3(Cr.x, Cr.y, Cr.z, c2)) + sel3(ha.x, ha.y, ha.z, c2) * fabsf(sel3(Cr.x, Cr.y, Cr.z, c1));
+    const float rb = sel3(ht.x, ht.y, ht.z, r1) * fabsf(sel3(Cr2.x, Cr2.y, Cr2.z, c)) + sel3(ht.x, ht.y, ht.z, r2) * fabsf(sel3(Cr1.x, Cr1.y, Cr1.z, c));
+    const float dist = fabsf(sel3(lc.x, lc.y, lc.z, r2) * sel3(Cr1.x, Cr1.y, Cr1.z, c) - sel3(lc.x, lc.y, lc.z, r1) * sel3(Cr2.x, Cr2.y, Cr2.z, c));
     be = (ra + rb - dist) / s;
   }
-  const v3 ac = V3(C[c], C[3 + c], C[6 + c]);                        // the owner's axis c in t's frame
+  const v3 ac = V3(sel3(C[0], C[1], C[2], c), sel3(C[3], C[4], C[5], c), sel3(C[6], C[7], C[8], c));   // the owner's axis c in t's frame
   v3 n = r == 0 ? V3(0.0f, -ac.z, ac.y) : (r == 1 ? V3(ac.z, 0.0f, -ac.x) : V3(-ac.y, ac.x, 0.0f));   // e_r x ac
   n = V3(n.x / s, n.y / s, n.z / s);
-  if (n.x * lcv[0] + n.y * lcv[1] + n.z * lcv[2] < 0.0f) n = vneg(n);                                   // from t towards a
-  const float nv[3] = {n.x, n.y, n.z};
-  float pt[3], pa[3] = {lcv[0], lcv[1], lcv[2]};
-  for (int k = 0; k < 3; ++k) pt[k] = k == r ? 0.0f : (nv[k] >= 0.0f ? htv[k] : -htv[k]);              // t's edge: its support towards a
-  for (int k = 0; k < 3; ++k) {
+  if (n.x * lc.x + n.y * lc.y + n.z * lc.z < 0.0f) n = vneg(n);                                         // from t towards a
+  v3 pt = V3(r == 0 ? 0.0f : (n.x >= 0.0f ? ht.x : -ht.x), r == 1 ? 0.0f : (n.y >= 0.0f ? ht.y : -ht.y),
+             r == 2 ? 0.0f : (n.z >= 0.0f ? ht.z : -ht.z));                                             // t's edge: its support towards a
+  v3 pa = lc;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {                                                                        // a's edge: its support towards t
     if (k == c) continue;
-    const float nk = nv[0] * C[k] + nv[1] * C[3 + k] + nv[2] * C[6 + k];
-    const float co = nk >= 0.0f ? -hav[k] : hav[k];                                                     // a's edge: its support towards t
-    pa[0] = pa[0] + co * C[k]; pa[1] = pa[1] + co * C[3 + k]; pa[2] = pa[2] + co * C[6 + k];
+    const float nk = n.x * C[k] + n.y * C[3 + k] + n.z * C[6 + k];
+    const float hk = k == 0 ? ha.x : (k == 1 ? ha.y : ha.z);
+    const float co = nk >= 0.0f ? -hk : hk;
+    pa.x = pa.x + co * C[k]; pa.y = pa.y + co * C[3 + k]; pa.z = pa.z + co * C[6 + k];
   }
-  const float d0[3] = {pa[0] - pt[0], pa[1] - pt[1], pa[2] - pt[2]};
-  const float de = d0[r], da = d0[0] * ac.x + d0[1] * ac.y + d0[2] * ac.z;
+  const v3 d0 = V3(pa.x - pt.x, pa.y - pt.y, pa.z - pt.z);
+  const float de = sel3(d0.x, d0.y, d0.z, r), da = d0.x * ac.x + d0.y * ac.y + d0.z * ac.z;
   float u = (de - cc * da) / s2, v = (cc * de - da) / s2;            // closest points of the two edge LINES, clamped to the edges
-  u = clampf(u, -htv[r], htv[r]); v = clampf(v, -hav[c], hav[c]);
-  float qt[3] = {pt[0], pt[1], pt[2]};
-  qt[r] = u;
-  const v3 qa = V3(pa[0] + v * ac.x, pa[1] + v * ac.y, pa[2] + v * ac.z);
-  E.p = V3(0.5f * (qt[0] + qa.x), 0.5f * (qt[1] + qa.y), 0.5f * (qt[2] + qa.z));
+  const float htr = sel3(ht.x, ht.y, ht.z, r), hac = sel3(ha.x, ha.y, ha.z, c);
+  u = clampf(u, -htr, htr); v = clampf(v, -hac, hac);
+  const v3 qt = V3(r == 0 ? u : pt.x, r == 1 ? u : pt.y, r == 2 ? u : pt.z);
+  const v3 qa = V3(pa.x + v * ac.x, pa.y + v * ac.y, pa.z + v * ac.z);
+  E.p = V3(0.5f * (qt.x + qa.x), 0.5f * (qt.y + qa.y), 0.5f * (qt.z + qa.z));
   E.n = n; E.depth = be; E.r = r;
 }
 
@@ -478,7 +511,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 
 // CMP: the scene has COMPOUND free bodies (a body = several boxes, sdx_scene_t::n_bshapes > 0).  The one-box-per-body instantiation
 // (every BlockAssembly scene) is the code it always was: box index == body index.
-template <bool CMP>
+// EDGE: edge-edge contacts (sdx_scene_t::edge_contacts > 0.5); the instantiation without them carries none of their code
+// (code size is a performance number in this kernel).
+template <bool CMP, bool EDGE>
 __global__ void __launch_bounds__(SIM_THREADS, SIM_MIN_CTAS)
 k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* __restrict__ dof,
            float* __restrict__ link_out, float* __restrict__ jac7, float* __restrict__ netf,
@@ -511,7 +546,6 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   float4* const CF = M.cf4;
 #endif
   float4* const CN = cscratch + (size_t)e * 4 * MAXC + 3 * MAXC;         // explicit normals (edge-edge contacts only)
-  const bool edges = S->edge_contacts > 0.5f;
   const float epref = S->edge_pref;
   unsigned char* const cf_bytes = reinterpret_cast<unsigned char*>(CF);   // 16 KB of scratch while the impulses are not live
 
@@ -519,6 +553,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
   const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&M.mbar);
   const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(M.tile);
   if (tid == 0) {
+    M.nelist = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -778,6 +813,7 @@ SIM_BROAD_UNROLL
     // before a touching contact is lost (oracle: sim_env 4.).  Block-uniform loop; level 0 in all but the most crowded sub-steps.
     int mycount, incl, total, level = 0;
     float gs = 1.0f;
+    unsigned short* const elist = reinterpret_cast<unsigned short*>(CN);           // EDGE: pairs queued for the edge-axis test (CN is not live before pass 2)
     for (;;) {
       mycount = 0;
       int a = 0;
@@ -791,10 +827,30 @@ SIM_BROAD_UNROLL
         if (!dead && pair_geom(M, a, t, m, G, t >= NB + nrs)) {
           int npts = (a < NB && G.ha.x > 0.04f) ? 12 : 8;
           for (int p = 0; p < npts; ++p) { float d; if (point_hit(G, p, m, fmargin, &d)) mk |= (unsigned short)(1u << p); }
-          if (edges && a < t) { int erc; float ebe; if (edge_sat(G, m, epref, &erc, &ebe)) mk |= (unsigned short)((erc + 1) << EDGE_POINT); }   // once per unordered pair; bits 12-15: edge pair + 1
+          // edge-edge contact, once per unordered pair: the pair is only QUEUED here (a few pairs per warp qualify; testing them in
+          // place would cost every warp the whole nine-axis loop) -- pass 1b below tests the queue with one pair per thread
+          if (EDGE && a < t && !edge_axes_parallel(G.C)) elist[atomicAdd(&M.nelist, 1)] = (unsigned short)i;
         }
         pmask[i] = mk;
         mycount += mask_count(mk);
+      }
+      if (EDGE) {
+        __syncthreads();
+        // pass 1b (EDGE): the rest of the separating-axis test for the queued pairs; bits 12-15 of the pair mask: edge pair + 1
+        const int nel = M.nelist;
+        for (int j = tid; j < nel; j += SIM_THREADS) {
+          const int i = elist[j];
+          int lo = 0, hi = n_owner - 1;                  // owner a with poff[a] <= i < poff[a+1]
+          while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (M.poff[mid] <= i) lo = mid; else hi = mid - 1; }
+          const int ea = lo, et = M.cand[ea][i - M.poff[ea]];
+          const float m = (margin + M.sab[ea].w + M.sab[et].w) * gs;
+          PairGeom G;
+          pair_geom(M, ea, et, m, G, false);
+          int erc; float ebe;
+          if (edge_sat(G, m, epref, &erc, &ebe)) pmask[i] = (unsigned short)(pmask[i] | ((erc + 1) << EDGE_POINT));
+        }
+        __syncthreads();
+        if (nel > 0) { mycount = 0; for (int i = p0; i < p1; ++i) mycount += mask_count(pmask[i]); }
       }
       // running contact offsets: warp-level inclusive scan of the per-thread counts + the totals of the warps before (one barrier)
       incl = mycount;
@@ -802,6 +858,7 @@ SIM_BROAD_UNROLL
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if ((tid & 31) >= o) incl += t; }
       if ((tid & 31) == 31) M.scan[tid >> 5] = incl;
       if (tid < NBODY) { M.astart[tid] = 0; M.aend[tid] = 0; M.nb[tid] = 0; }
+      if (EDGE && tid == 0) M.nelist = 0;                        // for the next level / the next sub-step (everyone has read it)
       __syncthreads();
       total = 0;
 #pragma unroll
@@ -827,6 +884,7 @@ SIM_BROAD_UNROLL
       const int ncon_w = M.ncon;
       unsigned short stash_mask[MAXC / SIM_THREADS], stash_pair[MAXC / SIM_THREADS];   // read the tables BEFORE they are overwritten
       unsigned char stash_j[MAXC / SIM_THREADS];
+      uint32_t* const equeue = reinterpret_cast<uint32_t*>(CB);                      // EDGE: queue of pass 2e (CB is written by the loop after it)
 #pragma unroll
       for (int r = 0; r < MAXC / SIM_THREADS; ++r) {
         int slot = r * SIM_THREADS + tid;
@@ -835,9 +893,34 @@ SIM_BROAD_UNROLL
           int lo = 0, hi = npairs - 1;                 // largest i with pstart[i] <= slot (that pair is non-empty)
           while (lo < hi) { int mid = (lo + hi + 1) >> 1; if ((int)pstart[mid] <= slot) lo = mid; else hi = mid - 1; }
           stash_pair[r] = (unsigned short)lo; stash_mask[r] = pmask[lo]; stash_j[r] = (unsigned char)(slot - (int)pstart[lo]);
+          // EDGE: the pair's last contact is its edge-edge contact -- queued (slot | pair) for pass 2e below: one thread per edge contact
+          // instead of every warp that holds one walking through the closest-point construction
+          if (EDGE && (stash_mask[r] >> EDGE_POINT) && (int)stash_j[r] >= __popc(stash_mask[r] & 0xfffu))
+            equeue[atomicAdd(&M.nelist, 1)] = (uint32_t)slot | ((uint32_t)lo << 16);
         }
       }
       __syncthreads();
+      if (EDGE) {
+        // pass 2e (EDGE): closest points of the two edges; world point | depth -> CA[slot], world normal | target edge axis -> CN[slot]
+        const int nel = M.nelist;
+        for (int q = tid; q < nel; q += SIM_THREADS) {
+          const uint32_t ent = equeue[q];
+          const int slot = ent & 0xffff, i = ent >> 16;
+          int lo = 0, hi = n_owner - 1;
+          while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (M.poff[mid] <= i) lo = mid; else hi = mid - 1; }
+          const int a = lo, t = M.cand[a][i - M.poff[a]];
+          PairGeom G;
+          pair_geom(M, a, t, 1e30f, G, false);
+          EdgeGeom E;
+          edge_point(G, (int)(pmask[i] >> EDGE_POINT) - 1, E);
+          const v3 wpt = vadd(ld3(M.sc[t]), mmul(M.sR[t], E.p));
+          const v3 nw = mmul(M.sR[t], E.n);
+          CA[slot] = make_float4(wpt.x, wpt.y, wpt.z, E.depth);
+          CN[slot] = make_float4(nw.x, nw.y, nw.z, __int_as_float(E.r));
+        }
+        __syncthreads();
+        if (tid == 0) M.nelist = 0;
+      }
 #pragma unroll 1
       for (int r = 0; r < MAXC / SIM_THREADS; ++r) {
         int slot = r * SIM_THREADS + tid;
@@ -845,26 +928,22 @@ SIM_BROAD_UNROLL
         int i = stash_pair[r];
         unsigned mk = stash_mask[r];
         int j = stash_j[r], p = 0;
-        if (j >= __popc(mk & 0xfffu)) p = EDGE_POINT;             // the pair's last contact: its edge-edge contact
+        if (EDGE && j >= __popc(mk & 0xfffu)) p = EDGE_POINT;             // the pair's last contact: its edge-edge contact
         else for (;; ++p) { if (mk & (1u << p)) { if (j == 0) break; --j; } }
         int lo = 0, hi = n_owner - 1;                  // owner a with poff[a] <= i < poff[a+1]
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (M.poff[mid] <= i) lo = mid; else hi = mid - 1; }
         const int a = lo, t = M.cand[a][i - M.poff[a]];
         float m = (margin + M.sab[a].w + M.sab[t].w) * gs;
-        PairGeom G;
-        pair_geom(M, a, t, m, G, t >= NB + nrs);
         float depth;
         v3 wpt;
         uint32_t wdn;
-        if (p == EDGE_POINT) {
-          EdgeGeom E;
-          edge_point(G, (int)(mk >> EDGE_POINT) - 1, E);
-          depth = E.depth;
-          wpt = vadd(ld3(M.sc[t]), mmul(M.sR[t], E.p));
-          const v3 nw = mmul(M.sR[t], E.n);
-          CN[slot] = make_float4(nw.x, nw.y, nw.z, 0.0f);
-          wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)E.r << 24) | EDGE_BIT;
+        if (EDGE && p == EDGE_POINT) {                                    // geometry from pass 2e
+          const float4 g = CA[slot];
+          wpt = V3(g.x, g.y, g.z); depth = g.w;
+          wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)__float_as_int(CN[slot].w) << 24) | EDGE_BIT;
         } else {
+          PairGeom G;
+          pair_geom(M, a, t, m, G, t >= NB + nrs);
           point_hit(G, p, m, fmargin, &depth);
           wpt = vadd(ld3(M.sc[a]), mmul(M.sR[a], sample_point(G.ha, p)));
           wdn = (uint32_t)M.sbody[a] | ((uint32_t)M.sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)G.k << 24) | (G.sg << 26);
@@ -1013,19 +1092,19 @@ SIM_BROAD_UNROLL
       float inv[3];
       const int sh = (wd >> 16) & 255, k = (wd >> 24) & 3;
       v3 en = V3(0.0f, 0.0f, 0.0f), et1 = en, et2 = en;
-      if (wd & EDGE_BIT) contact_axes_e(M, wd, CN, i, &en, &et1, &et2);
+      if (EDGE && (wd & EDGE_BIT)) contact_axes_e<EDGE>(M, wd, CN, i, &en, &et1, &et2);
 #pragma unroll 1
       for (int ax = 0; ax < 3; ++ax) {                        // n, t1, t2 in turn (contact_axes), one copy of body_k x 2
         const int col = k + ax >= 3 ? k + ax - 3 : k + ax;
         v3 d = mcol(M.sR[sh], col);
         if (ax == 0) d = vscale(d, ((wd >> 26) & 1) ? -1.0f : 1.0f);
-        if (wd & EDGE_BIT) d = ax == 0 ? en : (ax == 1 ? et1 : et2);
+        if (EDGE && (wd & EDGE_BIT)) d = ax == 0 ? en : (ax == 1 ? et1 : et2);
         const float iv = 1.0f / (body_k(S, M, a, wpt, d) + body_k(S, M, b, wpt, d));
         if (ax == 0) inv[0] = iv; else if (ax == 1) inv[1] = iv; else inv[2] = iv;
       }
       CB[i] = make_float4(inv[0], inv[1], inv[2], __uint_as_float(wd));
 #else
-      v3 n, t1, t2; contact_axes_e(M, wd, CN, i, &n, &t1, &t2);
+      v3 n, t1, t2; contact_axes_e<EDGE>(M, wd, CN, i, &n, &t1, &t2);
       float i0 = 1.0f / (body_k(S, M, a, wpt, n) + body_k(S, M, b, wpt, n));
       float i1 = 1.0f / (body_k(S, M, a, wpt, t1) + body_k(S, M, b, wpt, t1));
       float i2 = 1.0f / (body_k(S, M, a, wpt, t2) + body_k(S, M, b, wpt, t2));
@@ -1046,7 +1125,8 @@ SIM_BROAD_UNROLL
         const float4 A4 = CA[i], B4 = CB[i], F4 = CF[i];
         uint32_t wd = __float_as_uint(B4.w);
         int a = wd & 255, b = (wd >> 8) & 255;
-        v3 n, t1, t2; contact_axes_e(M, wd, CN, i, &n, &t1, &t2);
+        const float4 N4 = EDGE ? CN[i] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        v3 n, t1, t2; contact_axes_sel<EDGE>(M, wd, N4, &n, &t1, &t2);
         v3 wpt = V3(A4.x, A4.y, A4.z);
         v3 f = V3(F4.x, F4.y, F4.z);
         v3 vrel = vadd(ldv(M.bv[a]), vcross(ldv(M.bw[a]), vsub(wpt, ldv(M.bx[a]))));

@@ -27,7 +27,7 @@ if TASK.startswith('ToolPositioning'):
     if TASK.endswith('Orient'):
         env.set_grasp_bank(*synthetic_tool_grasp_bank(scene, 8, 0))
 else:
-    scene = Scene()
+    scene = Scene(edge_contacts=os.environ.get('SIM_PROF_EDGE', '1') != '0')
     bank = make_heap_bank(scene, 8)
     env = SdxEnv(scene, n)
     env.set_heap_bank(bank)
