@@ -83,6 +83,9 @@ typedef struct sdx_scene_t {
    * over the nine edge-pair axes; a pair whose axis of least overlap is an edge pair -- by more than edge_pref [m] over every face axis --
    * gets one contact at the closest points of the two edges, normal = that axis */
   float edge_contacts, edge_pref;
+  /* warm start of a contact that involves a robot link or a HOT brick (touched by the robot or faster than the wake threshold in the
+   * previous sub-step): such contacts change too fast for their last impulse to be trusted at warm_start (resting contacts: 0.98) */
+  float warm_start_hot;
 } sdx_scene_t;
 
 /* tasks sharing the scene, the contact step and the PPO engine (SURVEY.md section 8a "per-task dimensions"):

@@ -80,6 +80,7 @@ typedef struct sdx_scene_t { /* must mirror include/seqdex_b200.h */
   float tool_pitch_sc[8];              /* (sin, cos) of k * 1.571 / 2, k = 0..3 (TG:1493-1495) */
   float tool_plate_pose[7];            /* the "extra lego" pose after reset_idx (TG:1505-1512) */
   float edge_contacts, edge_pref;      /* edge-edge contacts on (> 0.5) | how much smaller than every face overlap the edge overlap must be [m] */
+  float warm_start_hot;                /* warm start of contacts that involve a robot link or a hot brick */
 } sdx_scene_t;
 #define ORIENT_OBS_FRAME 62
 #define ORIENT_BANK_WRAP 10000
@@ -660,7 +661,13 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
                 union { float f; uint32_t u; } kv; kv.f = wsr[4 * mid];
                 if (kv.u < key) lo = mid + 1;
                 else if (kv.u > key) hi = mid - 1;
-                else { c->f[0] = S->warm_start * wsr[4 * mid + 1]; c->f[1] = S->warm_start * wsr[4 * mid + 2]; c->f[2] = S->warm_start * wsr[4 * mid + 3]; break; }
+                else {
+                  /* a contact that involves a robot link or a HOT brick (hit by the robot / faster than the wake threshold in the last
+                   * sub-step) moves too fast for its last impulse to be trusted as far as a resting contact's */
+                  const int hotc = a >= NB || W->hot[W->sbody[a]] || (t < NB ? W->hot[W->sbody[t]] : (t < NB + nrs));
+                  const float wf = hotc ? S->warm_start_hot : S->warm_start;
+                  c->f[0] = wf * wsr[4 * mid + 1]; c->f[1] = wf * wsr[4 * mid + 2]; c->f[2] = wf * wsr[4 * mid + 3]; break;
+                }
               }
             }
           }

@@ -964,7 +964,13 @@ SIM_BROAD_UNROLL
             int lo2 = 0, hi2 = nprev - 1, mid = slot < hi2 ? slot : hi2, step = 1, dir = 0;
             while (lo2 <= hi2) {
               const uint32_t kv = __float_as_uint(wsr[4 * mid]);
-              if (kv == key) { f0 = V3(warm * wsr[4 * mid + 1], warm * wsr[4 * mid + 2], warm * wsr[4 * mid + 3]); break; }
+              if (kv == key) {
+                // a contact that involves a robot link or a HOT brick (hit by the robot / faster than the wake threshold in the last sub-step)
+                // moves too fast for its last impulse to be trusted as far as a resting contact's (oracle: hotc)
+                const bool hotc = a >= NB || (M.sflag[M.sbody[a]] & 2) || (t < NB ? (M.sflag[M.sbody[t]] & 2) != 0 : t < NB + nrs);
+                const float wf = hotc ? S->warm_start_hot : warm;
+                f0 = V3(wf * wsr[4 * mid + 1], wf * wsr[4 * mid + 2], wf * wsr[4 * mid + 3]); break;
+              }
               const int d = kv < key ? 1 : -1;
               if (d > 0) lo2 = mid + 1; else hi2 = mid - 1;
               if (dir == 0) dir = d;

@@ -98,10 +98,10 @@ def test_orient_and_search_batch_invariance_across_scripted_resets():
 def test_benchmark_mix_overflow_counters_and_settled_penetration(scene):
     """VERDICT r1 item 8 at BASELINE's full size.  (a) 300 steps of the benchmark's episode mix (random actions, staggered resets) at
     16 384 envs: no touching contact is ever dropped (speculative ones are shed first), no brick ever loses a pair against a static
-    box.  (b) a heap left alone settles with its touching contacts near the 0.5 mm slop (median < 1.2 mm).  MEASURED, not yet good: about
-    10 % of the touching contacts of a 9-layer heap are deeper than 2 mm after 150 steps (max ~3 cm) -- 16 mass-splitting Jacobi passes
-    do not fully carry a 9-high stack, and two bricks crossing edge to edge generate no contact until a corner reaches a face
-    (DESIGN.md section 3).  The bound below pins the measured level so that it cannot get worse unnoticed."""
+    box.  (b) a heap left alone settles with its touching contacts near the 0.5 mm slop.  MEASURED on 512 settled 9-layer heaps (165 k
+    touching contacts): median depth 0.55 mm, 0.6 % deeper than 2 mm, deepest 11.6 mm.  Round 2 started at 0.84 mm / 9.9 % / 29 mm; what
+    moved it: edge-edge contacts (two bricks crossing edge over edge used to be invisible until a corner reached a face) and resting
+    contacts warm-started at 0.98 instead of 0.85.  The bounds below pin that level."""
     from seqdex_b200.env import SdxEnv, make_heap_bank
     from seqdex_b200.tasks.block_assembly_grasp_sim import default_tvalue_weights
     bank = make_heap_bank(scene, 8)
@@ -145,4 +145,4 @@ def test_benchmark_mix_overflow_counters_and_settled_penetration(scene):
     frac_deep = float((touching > 2e-3).float().mean())
     print(f"settled heaps: {touching.numel()} touching contacts, median depth {float(touching.median()) * 1e3:.3f} mm, "
           f"> 2 mm: {100 * frac_deep:.3f} %, max {float(touching.max()) * 1e3:.2f} mm")
-    assert float(touching.median()) < 1.2e-3 and frac_deep < 0.15 and float(touching.max()) < 0.05, (float(touching.median()), frac_deep, float(touching.max()))
+    assert float(touching.median()) < 0.8e-3 and frac_deep < 0.02 and float(touching.max()) < 0.03, (float(touching.median()), frac_deep, float(touching.max()))
