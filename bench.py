@@ -489,9 +489,10 @@ def main():
     sampler.join(timeout=2)
     # ---- what the solver costs on a LIVE heap: the same rollout with sleeping switched off (PhysX's sleeping is on by default and so is
     #      ours; this number is reported beside the default so the reader sees what the mechanism saves) -- untimed set-up, rank 0 only
-    sleep_off = None
-    if rank == 0 and args.task == "grasp_sim" and not args.no_sleep_off:
-        scene2 = scene_from_cfg(task_name, sleep_time=0.0)
+    sleep_off = edge_off = None
+
+    def companion_rollout(note, **scene_kw):
+        scene2 = scene_from_cfg(task_name, **scene_kw)
         env2 = SdxEnv(scene2, n, local, seed=22 + rank)
         env2.set_heap_bank(bank)
         env2.set_tvalue_weights(default_tvalue_weights(22))
@@ -509,11 +510,22 @@ def main():
         s1.record()
         torch.cuda.synchronize()
         nc2 = env2.tensor("NCONTACT").cpu().numpy()
-        sleep_off = {"k_simulate_ms_per_launch": float(np.mean([a.elapsed_time(b) for a, b in ev2])),
-                     "rollout_env_steps_per_s": n * 16 / (s0.elapsed_time(s1) * 1e-3), "contacts_per_env_mean": float(nc2[:, 0].mean()),
-                     "envs_shedding_frac": float((nc2[:, 2] > 0).mean()), "dropped_max": int(nc2[:, 1].max()),
-                     "note": "rank 0, same episode mix and bank, Scene(sleep_time=0): no brick ever sleeps"}
+        res = {"k_simulate_ms_per_launch": float(np.mean([a.elapsed_time(b) for a, b in ev2])),
+               "rollout_env_steps_per_s": n * 16 / (s0.elapsed_time(s1) * 1e-3), "contacts_per_env_mean": float(nc2[:, 0].mean()),
+               "envs_shedding_frac": float((nc2[:, 2] > 0).mean()), "dropped_max": int(nc2[:, 1].max()),
+               "bricks_asleep_frac": float((env2.tensor("SLEEP") >= scene2.c.sleep_substeps).float().mean()) if scene2.c.sleep_substeps else 0.0,
+               "note": note}
         env2.close()
+        return res
+
+    if rank == 0 and args.task == "grasp_sim" and not args.no_sleep_off:
+        sleep_off = companion_rollout("rank 0, same episode mix and bank, Scene(sleep_time=0): no brick ever sleeps",
+                                      sleep_time=0.0, edge_contacts=bool(args.edge_contacts))
+        # what the edge-edge contacts cost (round 1 / early round 2 ran without them): the same rollout with the
+        # instantiation of k_simulate that carries none of their code
+        if args.edge_contacts:
+            edge_off = companion_rollout("rank 0, same episode mix and bank, Scene(edge_contacts=False): corner-vs-face contacts only "
+                                         "(k_simulate<.., EDGE = false>), as every measurement before the last week of round 2", edge_contacts=False)
     tms = torch.tensor([ms, e2e_ms, sim_ms, ro_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -561,6 +573,7 @@ def main():
                                          "touching contacts only (csrc/sdx_sim.cuh); statics claim candidate slots first"},
             "bricks_asleep_frac": float((env.tensor("SLEEP") >= scene.c.sleep_substeps).float().mean()) if scene.c.sleep_substeps else 0.0,
             "sleep_off": sleep_off,
+            "edge_off": edge_off,
         }
         if args.mode == "ppo" and args.task == "grasp_sim" and ppo_info.get("ppo_ms_per_iteration", 0) > 0:
             tpeak, tsrc = measured_tensor_peak()

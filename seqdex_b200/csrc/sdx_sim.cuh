@@ -89,6 +89,9 @@
 #define SIM_GATHER_U 1                 /* incidences whose loads phase B issues together per lane (2 / 4 measured slower: 5.56 / 5.87 vs 5.18 ms) */
 #endif
 #define PB_LANES_MAX 1152              /* sum of phase-B lane groups: < NB + (2 MAXC) / 2, rounded up to whole warps */
+#ifndef SIM_PASS1_STRIDED
+#define SIM_PASS1_STRIDED 1
+#endif
 #define PPMAX 26                       /* pairs per thread in the narrow phase (SIM_THREADS*PPMAX >= pairs) */
 
 struct SimSmem {
@@ -817,7 +820,11 @@ SIM_BROAD_UNROLL
     for (;;) {
       mycount = 0;
       int a = 0;
-      for (int i = p0; i < p1; ++i) {
+      // EDGE: pairs are dealt to the threads round-robin (a warp's range of the pair list is one owner class -- bricks with many hits, robot
+      // boxes with none -- so contiguous chunks leave the warps unevenly loaded; the barrier this needs is there anyway for pass 1b: 5.11 ->
+      // 5.08 ms per launch); the contact COUNTS below are still taken per contiguous chunk.  Without edge contacts: contiguous chunks, no barrier.
+      constexpr bool strided = EDGE && SIM_PASS1_STRIDED;
+      for (int i = strided ? tid : p0; i < (strided ? npairs : p1); i += strided ? SIM_THREADS : 1) {
         while (M.poff[a + 1] <= i) ++a;
         int t = M.cand[a][i - M.poff[a]];
         float m = (margin + M.sab[a].w + M.sab[t].w) * gs;
@@ -850,7 +857,7 @@ SIM_BROAD_UNROLL
           if (edge_sat(G, m, epref, &erc, &ebe)) pmask[i] = (unsigned short)(pmask[i] | ((erc + 1) << EDGE_POINT));
         }
         __syncthreads();
-        if (nel > 0) { mycount = 0; for (int i = p0; i < p1; ++i) mycount += mask_count(pmask[i]); }
+        if (nel > 0 || strided) { mycount = 0; for (int i = p0; i < p1; ++i) mycount += mask_count(pmask[i]); }
       }
       // running contact offsets: warp-level inclusive scan of the per-thread counts + the totals of the warps before (one barrier)
       incl = mycount;
