@@ -89,6 +89,9 @@
 #define SIM_GATHER_U 1                 /* incidences whose loads phase B issues together per lane (2 / 4 measured slower: 5.56 / 5.87 vs 5.18 ms) */
 #endif
 #define PB_LANES_MAX 1152              /* sum of phase-B lane groups: < NB + (2 MAXC) / 2, rounded up to whole warps */
+#ifndef SIM_KIN_FUSED
+#define SIM_KIN_FUSED 1                  /* kinematics .. world AABBs behind one block barrier: the robot warp runs the articulation's chain on its own */
+#endif
 #ifndef SIM_BROAD_SYM
 #define SIM_BROAD_SYM 1                  /* broad phase: every unordered pair of moving shapes tested once, hits entered in both shapes' bit rows */
 #endif
@@ -649,6 +652,95 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
 #define PMARK(k) do { } while (0)
 #endif
     PMARK(0);
+#if SIM_KIN_FUSED
+    // 1.-4. kinematics, poses, free velocities, world AABBs behind ONE block barrier (the vote below; compound scenes: two).  Everything
+    //    about the articulation is the robot warp's own business -- FK, then a lane per DoF (implicit PD) and per robot box (pose), then a
+    //    lane per link (twist), then a lane per box again (AABB + travel bound), __syncwarp between -- and a brick thread needs nothing but
+    //    its own brick: it used to wait at three block barriers for the robot's chain.  Same arithmetic, stage for stage.
+    auto shape_aabb = [&](int t) {
+      const float* R = M.sR[t];
+      v3 hh = ld3(M.sh[t]);
+      const v3 ext = V3(fabsf(R[0]) * hh.x + fabsf(R[1]) * hh.y + fabsf(R[2]) * hh.z,
+                        fabsf(R[3]) * hh.x + fabsf(R[4]) * hh.y + fabsf(R[5]) * hh.z,
+                        fabsf(R[6]) * hh.x + fabsf(R[7]) * hh.y + fabsf(R[8]) * hh.z);
+      int bd = M.sbody[t];
+      v3 dc = vsub(ld3(M.sc[t]), ld3(M.bx[bd]));
+      float reach = sqrtf(vdot(dc, dc)) + M.srad[t];
+      v3 bv = ld3(M.bv[bd]), bw = ld3(M.bw[bd]);
+      M.sab[t] = make_float4(ext.x, ext.y, ext.z, h * (sqrtf(vdot(bv, bv)) + sqrtf(vdot(bw, bw)) * reach));
+    };
+    bool asleep = false;
+    if (tid >= ROBOT_TID0) {
+      const int lane = tid - ROBOT_TID0;
+      robot_fk(S, M, lane);                                      // ends in __syncwarp
+      if (CMP) __syncthreads();                                  // (pairs with the brick threads' barrier below)
+      if (lane < nrs) {                                          // robot box poses
+        int t = NB + lane, L = S->rs_body[lane];
+        q4 qL = Q4(M.lq[L][0], M.lq[L][1], M.lq[L][2], M.lq[L][3]);
+        q4 ql = Q4(S->rs_quat[4 * lane], S->rs_quat[4 * lane + 1], S->rs_quat[4 * lane + 2], S->rs_quat[4 * lane + 3]);
+        st3(M.sc[t], vadd(ld3(M.bx[NB + L]), qrot(qL, V3(S->rs_c[3 * lane], S->rs_c[3 * lane + 1], S->rs_c[3 * lane + 2]))));
+        qmat(qmul(qL, ql), M.sR[t]);
+      }
+      if (lane < SDX_ND) {                                       // implicit PD free joint velocities
+        int j = lane;
+        float I = S->dof_inertia[j], kp = S->dof_kp[j], kd = S->dof_kd[j];
+        float ieff = I + h * kd + (h * h) * kp;
+        float qdo = M.qd[j];
+        float qn = (I * qdo + h * kp * (M.tgt[j] - M.q[j])) / ieff;
+        float tau = I * (qn - qdo) / h;
+        if (tau > S->dof_effort[j]) qn = qdo + S->dof_effort[j] * h / I;
+        if (tau < -S->dof_effort[j]) qn = qdo - S->dof_effort[j] * h / I;
+        qn = clampf(qn, -S->dof_vmax[j], S->dof_vmax[j]);
+        M.ieff[j] = ieff; M.qdfree[j] = qn; M.qd[j] = qn;
+      }
+      __syncwarp();
+      if (lane < SDX_NL) link_twist(S, M, lane, my_anc);
+      __syncwarp();
+      if (lane < nrs) shape_aabb(NB + lane);
+    } else {
+      if (tid < NB) {
+        asleep = tid < nbr && sleep_n > 0 && slpc >= sleep_n;
+        M.sflag[tid] = (unsigned char)((asleep ? 1 : 0) | ((tid < nbr && slpc == 0) ? 2 : 0));
+        M.touch[tid] = 0;
+        const float invm = asleep ? 0.0f : S->br_invm[tid];    // a sleeping brick is immovable for this sub-step
+        const v3 invI = asleep ? V3(0.0f, 0.0f, 0.0f) : V3(S->br_invI[3 * tid], S->br_invI[3 * tid + 1], S->br_invI[3 * tid + 2]);
+        float Rb[9];
+        qmat(bqr, Rb);
+        if (!CMP) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) M.sR[tid][i] = Rb[i];
+          st3(M.sc[tid], bxr);
+        } else M.bq[tid] = make_float4(bqr.x, bqr.y, bqr.z, bqr.w);
+        st3(M.bx[tid], bxr);
+        float damp = 1.0f - h * S->brick_ang_damp;
+        float ldamp = 1.0f - h * S->brick_lin_damp;
+        v3 vfree = vscale(V3(bvr.x, bvr.y, bvr.z + h * S->gravity_z), ldamp);
+        v3 wfree = vscale(bwr, damp);
+        if (tid >= nbr || asleep) { vfree = V3(0.0f, 0.0f, 0.0f); wfree = V3(0.0f, 0.0f, 0.0f); }
+        st3(M.bv[tid], vfree); st3(M.bw[tid], wfree);
+        M.bfv[tid] = make_float4(vfree.x, vfree.y, vfree.z, invm);
+        M.bfw[tid] = make_float4(wfree.x, wfree.y, wfree.z, 0.0f);
+        brick_world_invI(Rb, invI, &M.bI0[tid], &M.bI1[tid]);
+      }
+      if (CMP) {
+        __syncthreads();                                         // the boxes of a compound body read their body's frame
+        if (tid < NB) {
+          const int b = M.sbody[tid];
+          const float4 q4b = M.bq[b];
+          qmat(Q4(q4b.x, q4b.y, q4b.z, q4b.w), M.sR[tid]);
+          const v3 xb = ld3(M.bx[b]);
+          st3(M.sc[tid], tid < nbs ? vadd(xb, mmul(M.sR[tid], V3(S->bs_c[3 * tid], S->bs_c[3 * tid + 1], S->bs_c[3 * tid + 2]))) : xb);
+        }
+      }
+      if (tid < NB) shape_aabb(tid);
+      for (int s2 = tid; s2 < nst; s2 += ROBOT_TID0) {           // statics: AABB = the box itself, no travel (rewritten each sub-step: aliased storage)
+        int t = NB + nrs + s2;
+        const v3 hs = ld3(M.sh[t]);
+        M.sab[t] = make_float4(hs.x, hs.y, hs.z, 0.0f);
+      }
+    }
+    PMARK(1);
+#else
     // 1. kinematics (one thread walks the chain) || brick poses + free velocities
     if (tid >= ROBOT_TID0) robot_fk(S, M, tid - ROBOT_TID0);
     bool asleep = false;
@@ -728,6 +820,7 @@ k_simulate(const sdx_scene_t* __restrict__ S, float* __restrict__ brick, float* 
       const v3 hs = ld3(M.sh[t]);
       M.sab[t] = make_float4(hs.x, hs.y, hs.z, 0.0f);
     }
+#endif
     // The candidate lists are built in the FIRST sub-step of a step for ALL its sub-steps (travel bounds scaled by the number of
     // sub-steps left, plus the speed gravity adds in between) and rebuilt later only if a brick that was asleep when they were
     // built has been woken since: its pairs with sleeping bricks and statics were filtered (oracle: sim_env 3.)
