@@ -26,10 +26,10 @@ sys.path.insert(0, ROOT)
 
 ALGO_BYTES_PER_ENV_STEP = 15956   # algorithmic HBM bytes / env-step (fp32 rollout)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_simulate launch at 16 384 envs, from the committed ncu --set full capture
-# (profiles/r02_ncu_k_simulate_final.txt: 128.2 MB read + 289.3 MB written; the writes include the contact records that
-# live in global memory behind L1 since SIM_GLOBAL_CONTACTS and the warm-start impulse cache)
-NCU_TRAFFIC_BYTES_PER_ENV = (128.175e6 + 289.338e6) / 16384
-NCU_ISSUE_ACTIVE = 0.5176            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
+# (profiles/r02_ncu_k_simulate_final2.txt: 180.2 MB read + 363.7 MB written; the writes include the contact records and the
+# edge-contact normals that live in global memory behind L1 and the warm-start impulse cache)
+NCU_TRAFFIC_BYTES_PER_ENV = (180.210e6 + 363.700e6) / 16384
+NCU_ISSUE_ACTIVE = 0.4974            # smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture
 ALGO_FLOP_PER_ENV_STEP = 1.48e6      # counted fp32 work of the contact step in this episode mix (oracle counters)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # B200: 148 SMs x 128 fp32 lanes x 2 (FMA) x 1.965 GHz
 
@@ -491,27 +491,32 @@ def main():
     #      ours; this number is reported beside the default so the reader sees what the mechanism saves) -- untimed set-up, rank 0 only
     sleep_off = edge_off = None
 
-    def companion_rollout(note, **scene_kw):
+    def companion_rollout(note, own_bank=False, **scene_kw):
         scene2 = scene_from_cfg(task_name, **scene_kw)
+        # a heap banked under one contact model is not at rest under another (a brick that rested on an edge-edge contact starts to sink and
+        # wakes its neighbours): a companion that changes the contact model settles its own bank, exactly as the main arm did
+        bank2 = make_heap_bank(scene2, args.bank_per_type, local, seed=22 + rank) if own_bank else bank
         env2 = SdxEnv(scene2, n, local, seed=22 + rank)
-        env2.set_heap_bank(bank)
+        env2.set_heap_bank(bank2)
         env2.set_tvalue_weights(default_tvalue_weights(22))
         env2.step(acts[0])
         env2.tensor("PROGRESS").copy_(torch.randint(0, STAGGER, (n,), device=dev, generator=gen))
         for i in range(PRE_STEPS):
             env2.step(torch.rand(n, 23, device=dev, generator=gen) * 2 - 1)
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(16)]
+        for i in range(W):                                                  # the same timeline as the main arm's rollout-only phase
+            env2.step(acts[i])
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KR)]
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for i in range(16):
-            env2.pre_physics(acts[W + i % K])
+        for i in range(KR):
+            env2.pre_physics(acts[W + i])
             ev2[i][0].record(); env2.simulate(); ev2[i][1].record()
             env2.post_physics()
         s1.record()
         torch.cuda.synchronize()
         nc2 = env2.tensor("NCONTACT").cpu().numpy()
         res = {"k_simulate_ms_per_launch": float(np.mean([a.elapsed_time(b) for a, b in ev2])),
-               "rollout_env_steps_per_s": n * 16 / (s0.elapsed_time(s1) * 1e-3), "contacts_per_env_mean": float(nc2[:, 0].mean()),
+               "rollout_env_steps_per_s": n * KR / (s0.elapsed_time(s1) * 1e-3), "steps": KR, "contacts_per_env_mean": float(nc2[:, 0].mean()),
                "envs_shedding_frac": float((nc2[:, 2] > 0).mean()), "dropped_max": int(nc2[:, 1].max()),
                "bricks_asleep_frac": float((env2.tensor("SLEEP") >= scene2.c.sleep_substeps).float().mean()) if scene2.c.sleep_substeps else 0.0,
                "note": note}
@@ -524,8 +529,9 @@ def main():
         # what the edge-edge contacts cost (round 1 / early round 2 ran without them): the same rollout with the
         # instantiation of k_simulate that carries none of their code
         if args.edge_contacts:
-            edge_off = companion_rollout("rank 0, same episode mix and bank, Scene(edge_contacts=False): corner-vs-face contacts only "
-                                         "(k_simulate<.., EDGE = false>), as every measurement before the last week of round 2", edge_contacts=False)
+            edge_off = companion_rollout("rank 0, same episode mix and timeline, Scene(edge_contacts=False): corner-vs-face contacts only "
+                                         "(k_simulate<.., EDGE = false>) on a bank settled under that model, as every measurement before the last week "
+                                         "of round 2; compare with rollout_only / roofline.ms_per_launch", own_bank=True, edge_contacts=False)
     tms = torch.tensor([ms, e2e_ms, sim_ms, ro_ms, e2e_wall_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -549,7 +555,7 @@ def main():
             "ppo": ppo_info,
             "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "traffic": NCU_TRAFFIC_BYTES_PER_ENV * n,
-                         "traffic_source": "ncu --set full at 16384 envs, profiles/r02_ncu_k_simulate_final.txt (scaled by envs per launch)",
+                         "traffic_source": "ncu --set full at 16384 envs, profiles/r02_ncu_k_simulate_final2.txt (scaled by envs per launch)",
                          "issue_slots_busy_ncu": NCU_ISSUE_ACTIVE,
                          "fp32_alu": {"algorithmic_flop_per_env_step": ALGO_FLOP_PER_ENV_STEP, "peak_tflops": FP32_PEAK_TFLOPS,
                                       "achieved_tflops": ALGO_FLOP_PER_ENV_STEP * n / (sim_ms * 1e-3) / 1e12,
@@ -557,9 +563,9 @@ def main():
                                       "note": "GraspSim mix; neither roofline bounds the kernel (DESIGN.md sections 6, 11)"},
                          "ms_per_launch": sim_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * n,
                          "share_of_step": sim_ms * K / ms, "share_of_rollout_step": sim_ms * KR / ro_ms,
-                         "note": "state-streaming bound is loose: the kernel is instruction- and latency-bound (2.6 G warp-instructions per launch = 2.2 ms "
-                                 "at full issue rate; issue slots 52 % busy, LSU data pipe 56 %, 29 % of shared-memory wavefronts are bank-conflict "
-                                 "replays; DESIGN.md section 11), not HBM-bound"},
+                         "note": "state-streaming bound is loose: the kernel is instruction- and latency-bound (2.7 G warp-instructions per launch = 2.3 ms "
+                                 "at full issue rate; issue slots 50 % busy, 41 % of the stall samples are block-barrier waits behind the slowest warp "
+                                 "of a stage; DESIGN.md sections 11, 11.4), not HBM-bound"},
             "roofline_tensor": None,
             "clocks": sampler.summary(),
             "contacts_per_env": {"mean": float(nc[:, 0].mean()), "max": int(nc[:, 0].max()), "table": 1024,

@@ -623,7 +623,10 @@ static void sim_env(const sdx_scene_t* S, float* brick, float* dof, float* link_
           if (p == EDGE_POINT) { /* the pair's edge-edge contact, once per unordered pair (owner index below target index) */
             if (!(S->edge_contacts > 0.5f && a < t)) continue;
             v3 ep; int er;
-            if (!edge_contact(C, lc, ha, ht, m, S->edge_pref, &ep, &en, &depth, &er)) continue;
+            /* speculative range of an edge-edge contact: the travel bounds, plus at most the geometric tolerance (2 mm) of the contact offset --
+             * the contact exists to resolve crossings the corner test cannot see, not to anticipate them from 2 cm away (Orient / Search) */
+            const float me = ((margin < fmargin ? margin : fmargin) + W->spd[a] + W->spd[t]) * gs;
+            if (!edge_contact(C, lc, ha, ht, me, S->edge_pref, &ep, &en, &depth, &er)) continue;
             wpt = vadd(W->sc[t], mmul(W->sR[t], ep));
             en = mmul(W->sR[t], en);
             word = (uint32_t)W->sbody[a] | ((uint32_t)W->sbody[t] << 8) | ((uint32_t)t << 16) | ((uint32_t)er << 24) | EDGE_BIT;

@@ -1038,7 +1038,9 @@ SIM_BROAD_UNROLL
           PairGeom G;
           pair_geom(M, ea, et, m, G, false);
           int erc; float ebe;
-          if (edge_sat(G, m, epref, &erc, &ebe)) pmask[i] = (unsigned short)(pmask[i] | ((erc + 1) << EDGE_POINT));
+          // speculative range of an edge-edge contact: the travel bounds plus at most the geometric tolerance of the contact offset (oracle: me)
+          const float me = ((margin < fmargin ? margin : fmargin) + M.sab[ea].w + M.sab[et].w) * gs;
+          if (edge_sat(G, me, epref, &erc, &ebe)) pmask[i] = (unsigned short)(pmask[i] | ((erc + 1) << EDGE_POINT));
         }
         __syncthreads();
         if (nel > 0 || strided) { mycount = 0; for (int i = p0; i < p1; ++i) mycount += mask_count(pmask[i]); }
