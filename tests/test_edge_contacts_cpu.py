@@ -82,3 +82,59 @@ def test_settled_heap_true_overlaps(oracle_lib):
     assert on["deeper_5mm"] <= 4 and on["deeper_5mm"] * 5 <= off["deeper_5mm"]
     assert on["deeper_2mm"] * 2 <= off["deeper_2mm"]
     assert on["median_mm"] < 1.2 and on["speed_p95"] < 0.05
+
+
+def test_boxes_with_a_parallel_axis_pair_get_no_edge_contact(oracle_lib):
+    """two FLAT bricks (z axes parallel) crossing each other in the plane at 45 degrees, interpenetrating sideways: every edge-pair axis
+    coincides with a face axis of one of them, so the pair is skipped before the nine-axis loop (edge_axes_parallel) -- whatever the
+    corner-vs-face test generates, no contact carries the edge bit"""
+    s = Scene(edge_contacts=True, sleep_time=0.0, substeps=1)      # one sub-step: the dump shows the contacts of the poses set here
+    s.c.n_bricks = 2
+    s.c.gravity_z = 0.0
+    e = oracle_lib.OracleEnv(s, 1)
+    b = e.brick
+    half = np.ctypeslib.as_array(s.c.br_half).reshape(-1, 3)
+    b[0, :, :2] = 0
+    b[0, 0:3, 0] = (0.0, 0.0, 3.0)
+    b[0, 3:7, 0] = (0.0, 0.0, 0.0, 1.0)
+    b[0, 0:3, 1] = (half[0, 0] * 0.9, 0.0, 3.0 + 0.2 * half[0, 2])
+    b[0, 3:7, 1] = (0.0, 0.0, np.sin(np.pi / 8), np.cos(np.pi / 8))                  # yawed 45 degrees about the shared z axis
+    e.slp[:] = 0
+    e.simulate(dump=True)
+    n = int(e.ncontact[0, 0])
+    words = e.condump[0, :n, 0].view(np.uint32)
+    assert n > 0 and not any(int(w) & EDGE_BIT for w in words), [hex(w) for w in words]
+
+
+def test_resting_contacts_are_warm_started_harder_than_hot_ones(oracle_lib):
+    """sdx_scene_t::warm_start (0.98) seeds a persisting contact between bodies at rest, warm_start_hot (0.85) one that involves a hot brick
+    (faster than the wake threshold / touched by the robot in the last sub-step): a brick resting on the slab keeps its support impulse
+    almost entirely from one sub-step to the next, so the solver's first pass has little left to find"""
+    def first_pass_support(hot):
+        s = Scene(sleep_time=0.0)
+        s.c.n_bricks = 1
+        s.c.iters = 0                                     # only the warm-start pass (it = -1) acts: what is carried over is all there is
+        e = oracle_lib.OracleEnv(s, 1)
+        s16 = Scene(sleep_time=0.0)
+        s16.c.n_bricks = 1
+        e16 = oracle_lib.OracleEnv(s16, 1)
+        rows = e16.brick_roots()
+        rows[0, 0, 0:3] = (0.25, 0.2, 0.62)               # over the slab of the bin
+        rows[0, 0, 3:7] = (0, 0, 0, 1)
+        rows[0, 0, 7:13] = 0
+        e16.set_brick_roots(rows)
+        for _ in range(60):
+            e16.simulate()                                # settle with the full solver: the cache now holds the support impulses
+        assert abs(e16.brick[0, 9, 0]) < 5e-3
+        # hand the settled state and the impulse cache to the zero-iteration env
+        e.brick[:] = e16.brick
+        e.ws[:] = e16.ws
+        e.wsn[:] = e16.wsn
+        e.ws_cur = e16.ws_cur
+        e.slp[:] = 0 if hot else 5                        # 0 = hot in the last sub-step
+        e.simulate()
+        return float(e.brick[0, 9, 0])                    # vertical velocity after one step carried by the cached impulses alone
+    vz_rest, vz_hot = first_pass_support(False), first_pass_support(True)
+    # gravity adds -g h per sub-step; the cached support takes 98 % / 85 % of it back
+    assert vz_hot < vz_rest < 0.0, (vz_rest, vz_hot)
+    assert vz_rest > 0.4 * vz_hot, (vz_rest, vz_hot)
