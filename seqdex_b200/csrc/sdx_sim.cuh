@@ -1118,6 +1118,11 @@ SIM_BROAD_UNROLL
       for (int r = 0; r < MAXC / SIM_THREADS; ++r) {
         int slot = r * SIM_THREADS + tid;
         if (slot >= ncon_w) break;
+        // warm start, first probe: the cached record of the SAME slot (key | impulse: one 16-byte load), issued here so that its trip to L2 /
+        // HBM runs under the geometry below instead of after it
+        float4 w4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        int mid = -1;
+        if (warm > 0.0f && nprev > 0) { mid = slot < nprev - 1 ? slot : nprev - 1; w4 = *reinterpret_cast<const float4*>(wsr + 4 * mid); }
         int i = stash_pair[r];
         unsigned mk = stash_mask[r];
         int j = stash_j[r], p = 0;
@@ -1154,15 +1159,18 @@ SIM_BROAD_UNROLL
             // the keys of both sub-steps ascend with the contact order and most contacts persist in place: look at the same
             // slot first, gallop away from it, then bisect the bracket (finds what a plain bisection finds, in 1-3 probes
             // for a settled heap instead of 10 dependent global loads)
-            int lo2 = 0, hi2 = nprev - 1, mid = slot < hi2 ? slot : hi2, step = 1, dir = 0;
+            int lo2 = 0, hi2 = nprev - 1, step = 1, dir = 0;
+            bool first = true;
             while (lo2 <= hi2) {
-              const uint32_t kv = __float_as_uint(wsr[4 * mid]);
+              if (!first) w4 = *reinterpret_cast<const float4*>(wsr + 4 * mid);
+              first = false;
+              const uint32_t kv = __float_as_uint(w4.x);
               if (kv == key) {
                 // a contact that involves a robot link or a HOT brick (hit by the robot / faster than the wake threshold in the last sub-step)
                 // moves too fast for its last impulse to be trusted as far as a resting contact's (oracle: hotc)
                 const bool hotc = a >= NB || (M.sflag[M.sbody[a]] & 2) || (t < NB ? (M.sflag[M.sbody[t]] & 2) != 0 : t < NB + nrs);
                 const float wf = hotc ? S->warm_start_hot : warm;
-                f0 = V3(wf * wsr[4 * mid + 1], wf * wsr[4 * mid + 2], wf * wsr[4 * mid + 3]); break;
+                f0 = V3(wf * w4.y, wf * w4.z, wf * w4.w); break;
               }
               const int d = kv < key ? 1 : -1;
               if (d > 0) lo2 = mid + 1; else hi2 = mid - 1;
