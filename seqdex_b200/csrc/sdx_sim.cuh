@@ -6,11 +6,14 @@
 //            (cp.async.bulk -> mbarrier), DoF block [3][24] by plain loads
 //   per sub-step (h = dt/substeps):
 //     forward kinematics (robot warp in lockstep, chain by shuffles), shape poses, free velocities (gravity, implicit PD),
-//     world-frame inverse inertia of every brick
-//     broad phase   : FIRST sub-step of a step (or after a sleeping brick was woken): two threads per owner shape, world-AABB
-//                     test against every target box with the travel bounds of all sub-steps left; later sub-steps keep the lists
+//     world-frame inverse inertia of every brick, world AABBs -- ONE block barrier: the robot warp runs the articulation's whole chain
+//     broad phase   : FIRST sub-step of a step (or after a sleeping brick was woken): every unordered pair of moving shapes is box-tested
+//                     ONCE (ring pairing, two threads per owner) with the travel bounds of all sub-steps left, hits entered in both shapes'
+//                     128-bit rows; the candidate lists are read off the rows in ascending order; later sub-steps keep the lists
 //     narrow phase  : ordered pairs -> SAT reference face -> sample points -> contacts (two-pass,
-//                     deterministic compaction: owner, candidate, point order) + warm-start lookup (galloping from the same slot)
+//                     deterministic compaction: owner, candidate, point order) + warm-start lookup (galloping from the same slot);
+//                     EDGE instantiation: pairs without a parallel axis pair are queued and the nine edge-pair axes tested one pair per
+//                     thread (pass 1b); a pair's edge-edge contact is constructed one contact per thread (pass 2e)
 //     -- a sub-step without a single contact skips the three stages below --
 //     CSR incidence : per body, contacts in index order (fixed summation order => reproducible); 16-byte work items for phase B
 //     solver        : mass-splitting Jacobi on total impulses; phase A = 1 thread / contact,
