@@ -73,15 +73,16 @@ def test_without_edge_contacts_the_ridges_pass_through_each_other(oracle_lib):
 
 def test_settled_heap_true_overlaps(oracle_lib):
     """the lattice of 72 bricks dropped and left to settle (sleeping off): TRUE overlaps of all pairs of bricks by the full 15-axis
-    separating-axis test in numpy, independent of the contacts generated.  Measured (4 envs, 200 steps): without edge contacts 58 pairs
-    deeper than 5 mm (max 24 mm), with them 2 (max 14 mm); pairs deeper than 2 mm 163 -> 65."""
+    separating-axis test in numpy, independent of the contacts generated.  Measured here (2 envs, 150 steps, resting contacts warm-started
+    at 0.98): without edge contacts 54 of 206 overlapping pairs deeper than 2 mm, 22 deeper than 5 mm, deepest 18.8 mm; with them 1 of 203,
+    none, 2.1 mm (8 envs x 240 steps: DESIGN.md section 3c)."""
     import edge_contact_audit as A
     off = A.audit(False, 2, 150)
     on = A.audit(True, 2, 150)
     print(off, on)
-    assert on["deeper_5mm"] <= 4 and on["deeper_5mm"] * 5 <= off["deeper_5mm"]
-    assert on["deeper_2mm"] * 2 <= off["deeper_2mm"]
-    assert on["median_mm"] < 1.2 and on["speed_p95"] < 0.05
+    assert on["deeper_5mm"] <= 1 and off["deeper_5mm"] >= 10
+    assert on["deeper_2mm"] <= 6 and on["deeper_2mm"] * 5 <= off["deeper_2mm"]
+    assert on["median_mm"] < 0.9 and on["max_mm"] < 6.0 and on["speed_p95"] < 0.05
 
 
 def test_boxes_with_a_parallel_axis_pair_get_no_edge_contact(oracle_lib):
